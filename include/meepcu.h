@@ -1,0 +1,221 @@
+/* meepcu.h -- C ABI of libmeepcuda.so: the B200 (sm_100a) implementation of Meep's
+ * per-timestep field update (the PMack10/meep_nl fork), behind the seam
+ * `fields::step()` (reference src/step.cpp:35-140).
+ *
+ * Everything that crosses this boundary is a plain pointer, size or POD struct:
+ * no C++ types, no torch types, no exceptions.  Every function returns
+ * MEEPCU_OK (0) or a negative MEEPCU_E* code; the message is available from
+ * meepcu_last_error() (the reference-side shim turns that into
+ * meep::abort("%s", ...), reference src/mympi.cpp:244-263).
+ *
+ * Ownership: all host arrays handed in stay owned by the caller (the
+ * reference's fields_chunk / structure_chunk, new[]/delete[],
+ * src/fields.cpp:164-209).  The context owns device mirrors and remembers the
+ * host addresses so that meepcu_sync_to_host()/meepcu_sync_from_host() can move
+ * data back and forth and so that connection / metal / polarisation pointers can
+ * be given exactly as the reference stores them (as realnum* into those arrays).
+ *
+ * Threading: one caller thread per context (the reference is single threaded
+ * per process around fields::step, src/meep.hpp:1637).
+ *
+ * The same ABI is implemented, on the CPU and in place on the caller's arrays,
+ * by oracle/liboracle_meep.so (test infrastructure, never loaded by the product).
+ */
+#ifndef MEEPCU_H
+#define MEEPCU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MEEPCU_ABI_VERSION 1
+
+/* ---- enums: numeric values are the reference's (src/meep/vec.hpp:27-79) ---- */
+#define MEEPCU_NUM_COMPONENTS 20 /* Ex,Ey,Er,Ep,Ez,Hx..Hz,Dx..Dz,Bx..Bz           vec.hpp:31-52 */
+#define MEEPCU_NUM_FIELD_TYPES 8 /* E,H,D,B,PE,PH,WE,WH                           vec.hpp:66-75 */
+enum { MEEPCU_Ex = 0, MEEPCU_Ey, MEEPCU_Er, MEEPCU_Ep, MEEPCU_Ez,
+       MEEPCU_Hx, MEEPCU_Hy, MEEPCU_Hr, MEEPCU_Hp, MEEPCU_Hz,
+       MEEPCU_Dx, MEEPCU_Dy, MEEPCU_Dr, MEEPCU_Dp, MEEPCU_Dz,
+       MEEPCU_Bx, MEEPCU_By, MEEPCU_Br, MEEPCU_Bp, MEEPCU_Bz };
+enum { MEEPCU_D1 = 0, MEEPCU_D2 = 1, MEEPCU_D3 = 2, MEEPCU_Dcyl = 3 };          /* vec.hpp:65 */
+enum { MEEPCU_X = 0, MEEPCU_Y, MEEPCU_Z, MEEPCU_R, MEEPCU_P, MEEPCU_NO_DIRECTION }; /* vec.hpp:77 */
+enum { MEEPCU_E_STUFF = 0, MEEPCU_H_STUFF, MEEPCU_D_STUFF, MEEPCU_B_STUFF,
+       MEEPCU_PE_STUFF, MEEPCU_PH_STUFF, MEEPCU_WE_STUFF, MEEPCU_WH_STUFF };
+/* connect_phase, src/meep.hpp:741 */
+enum { MEEPCU_CONNECT_PHASE = 0, MEEPCU_CONNECT_NEGATE = 1, MEEPCU_CONNECT_COPY = 2 };
+
+/* how update_eh treats chi2/chi3:
+ *   FORK_LITERAL  : what the fork's CPU code computes as compiled -- diagonal
+ *                   E = chi1inv*D, plus the Newton-Raphson chi2 solve in non-PML
+ *                   chunks whose off-diagonal chi1inv rows and chi3 are allocated
+ *                   (step_generic.cpp:730-816, newton_raphson.cpp:93-359).
+ *   UPSTREAM_PADE : upstream Meep's Kerr/Pockels Pade update that the fork
+ *                   commented out (step_generic.cpp:546-553,617-619,772-773,...). */
+enum { MEEPCU_NL_FORK_LITERAL = 0, MEEPCU_NL_UPSTREAM_PADE = 1 };
+
+/* error codes */
+enum { MEEPCU_OK = 0, MEEPCU_EINVAL = -1, MEEPCU_EUNSUPPORTED = -2, MEEPCU_ECUDA = -3,
+       MEEPCU_ENOMEM = -4, MEEPCU_ESTATE = -5, MEEPCU_ENCCL = -6, MEEPCU_ENONFINITE = -7 };
+
+typedef struct meepcu_ctx meepcu_ctx;
+
+/* Replaces the scalar state of `fields` / `fields_chunk` (src/meep.hpp:1733-1750). */
+typedef struct {
+  int abi_version;   /* MEEPCU_ABI_VERSION */
+  int realnum_bytes; /* sizeof(realnum): 8, or 4 for the --enable-single build (meep.hpp:42-46) */
+  int is_real;       /* fields::is_real: 1 = only cmp 0 exists */
+  int dim;           /* grid_volume::dim (D1/D2/D3; Dcyl -> MEEPCU_EUNSUPPORTED) */
+  double a;          /* resolution */
+  double dt;         /* fields::dt = Courant/a */
+  double courant;    /* fields_chunk::Courant: the dt/dx factor passed to step_curl (step_db.cpp:125) */
+  double beta;       /* fields::beta, 2D exp(i beta z) term (step_db.cpp:148-175) */
+  int nl_mode;       /* MEEPCU_NL_* */
+  int device;        /* CUDA device ordinal for this context (ignored by the oracle) */
+  int t;             /* fields::t at attach time */
+  int reserved[7];
+} meepcu_config;
+
+/* One fields_chunk + its structure_chunk (src/meep.hpp:590-598,1461-1485).  Array length is
+ * ntot = prod_d (num[d]+1) over the directions the dimensionality has, z fastest, then y, then x
+ * (src/vec.cpp:293-296,482-494).  A NULL pointer means "not allocated" exactly as in the
+ * reference; f[Hc]==f[Bc] means H aliases B (src/fields.cpp:493-517). */
+typedef struct {
+  int num[3];   /* grid_volume::num_direction(X,Y,Z); 0 for absent directions */
+  int io[3];    /* grid_volume::little_corner(), half-pixel units, X,Y,Z */
+  void *f[MEEPCU_NUM_COMPONENTS][2];      /* fields_chunk::f        */
+  void *f_u[MEEPCU_NUM_COMPONENTS][2];    /* fields_chunk::f_u      (PML, integrated from D/B) */
+  void *f_w[MEEPCU_NUM_COMPONENTS][2];    /* fields_chunk::f_w      (PML, E/H integrated from W) */
+  void *f_cond[MEEPCU_NUM_COMPONENTS][2]; /* fields_chunk::f_cond   (PML + conductivity) */
+  const void *chi1inv[MEEPCU_NUM_COMPONENTS][5];      /* structure_chunk::chi1inv */
+  const void *chi2[MEEPCU_NUM_COMPONENTS];            /* structure_chunk::chi2    */
+  const void *chi3[MEEPCU_NUM_COMPONENTS];            /* structure_chunk::chi3    */
+  const void *conductivity[MEEPCU_NUM_COMPONENTS][5]; /* structure_chunk::conductivity */
+  const void *condinv[MEEPCU_NUM_COMPONENTS][5];      /* structure_chunk::condinv */
+  const void *sig[6], *kap[6], *siginv[6];            /* structure_chunk::sig/kap/siginv (uPML) */
+  int sigsize[6];                                     /* structure_chunk::sigsize */
+  int rank;     /* owning rank (structure_chunk::n_proc()); single-GPU: 0 */
+  int reserved[7];
+} meepcu_chunk_desc;
+
+/* lorentzian_susceptibility (src/susceptibility.cpp:98-281, src/meep.hpp:262-330).  */
+typedef struct {
+  int ft;                     /* MEEPCU_E_STUFF or MEEPCU_H_STUFF (which pol[] list) */
+  double omega_0, gamma;      /* as stored by the reference (frequency units, not angular) */
+  int no_omega_0_denominator; /* 1 = Drude */
+  const void *sigma[MEEPCU_NUM_COMPONENTS][5]; /* susceptibility::sigma[c][d], NULL when trivial */
+  void *P[MEEPCU_NUM_COMPONENTS][2];           /* lorentzian_data::P (NULL: device-only, zero) */
+  void *P_prev[MEEPCU_NUM_COMPONENTS][2];      /* lorentzian_data::P_prev */
+  int reserved[8];
+} meepcu_susceptibility_desc;
+
+/* src_vol (src/meep_internals.hpp:49-82) attached to fields_chunk::sources[ft]. */
+typedef struct {
+  int ft;            /* MEEPCU_D_STUFF or MEEPCU_B_STUFF: which sources[] list it is in */
+  int c;             /* src_vol::c (an E/H/D/B component; only its direction/type matter) */
+  int src_time_id;   /* index into the per-step meepcu_src_sample table */
+  int is_integrated; /* src_time::is_integrated */
+  size_t n;          /* src_vol::num_points() */
+  const ptrdiff_t *index; /* src_vol::index_at(j) */
+  const double *amp;      /* src_vol::amplitude(j) as (re,im) pairs */
+} meepcu_source_desc;
+
+/* dft_chunk (src/dft.cpp:57-129,265-307, src/meep.hpp:1126-1221). */
+typedef struct {
+  int c;            /* dft_chunk::c */
+  int is[3], ie[3]; /* dft_chunk::is / ie (ivec, X,Y,Z) */
+  double s0[3], s1[3], e0[3], e1[3]; /* interpolation weights at the region's ends (X,Y,Z) */
+  double dV0, dV1;
+  ptrdiff_t avg1, avg2;  /* yee2cent offsets in host-array elements (0: none) */
+  int include_dV_and_interp_weights, sqrt_dV_and_interp_weights;
+  int decimation_factor;
+  int Nomega;
+  const double *omega;   /* dft_chunk::omega[Nomega] (angular: 2 pi f) */
+  double scale[2];       /* dft_chunk::scale (re,im) */
+  void *dft;             /* dft_chunk::dft, complex<realnum>[N*Nomega]; NULL: device only */
+  int reserved[8];
+} meepcu_dft_desc;
+
+/* The values of one src_time at the four sampling points of one fields::step()
+ * (src/step.cpp:64,74,96,106; src_time::update, src/meep.hpp:972-978), as (re,im). */
+typedef struct {
+  double current_B[2]; /* current() after update(time(),        dt): step_source(B_stuff) */
+  double dipole_H[2];  /* dipole()  after update(time()+dt/2,   dt): integrated H sources  */
+  double current_D[2]; /* current() after update(time()+dt/2,   dt): step_source(D_stuff) */
+  double dipole_E[2];  /* dipole()  after update(time()+dt,     dt): integrated E sources  */
+} meepcu_src_sample;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+const char *meepcu_last_error(void);
+const char *meepcu_backend(void); /* "cuda-sm_100a" or "oracle-cpu" */
+int meepcu_abi_version(void);
+
+int meepcu_create(const meepcu_config *cfg, meepcu_ctx **out);
+int meepcu_destroy(meepcu_ctx *ctx);
+
+/* ---- description of the problem (called once, or again after the host re-allocates) ------ */
+int meepcu_add_chunk(meepcu_ctx *ctx, const meepcu_chunk_desc *desc, int *chunk_id);
+int meepcu_add_susceptibility(meepcu_ctx *ctx, int chunk_id, const meepcu_susceptibility_desc *desc);
+int meepcu_add_source(meepcu_ctx *ctx, int chunk_id, const meepcu_source_desc *desc);
+int meepcu_add_dft(meepcu_ctx *ctx, int chunk_id, const meepcu_dft_desc *desc, int *dft_id);
+
+/* fields_chunk::zeroes[ft] (src/boundaries.cpp:309-339): pointers into registered f arrays. */
+int meepcu_set_metal(meepcu_ctx *ctx, int ft, size_t n, void *const *ptrs);
+
+/* One (field type, connect_phase) family of local chunk-to-chunk connections, flattened over all
+ * chunk pairs in the reference's send order (src/step.cpp:252-279, boundaries.cpp:347-623):
+ * dst[i] / src[i] are fields_chunk::connections_in / connections_out entries.  For
+ * MEEPCU_CONNECT_PHASE entries come in (re,im) pairs and phases holds n/2 complex<realnum>. */
+int meepcu_add_connections(meepcu_ctx *ctx, int ft, int phase_kind, size_t n, void *const *dst,
+                           const void *const *src, const void *phases);
+
+/* Connections whose other end lives on another rank (the MPI_Isend/Irecv pairs of
+ * src/mympi.cpp:107-135): the local end only.  Both sides must list entries in the same order. */
+int meepcu_add_remote_send(meepcu_ctx *ctx, int ft, int phase_kind, int peer_rank, size_t n,
+                           const void *const *src);
+int meepcu_add_remote_recv(meepcu_ctx *ctx, int ft, int phase_kind, int peer_rank, size_t n,
+                           void *const *dst, const void *phases);
+/* NCCL bootstrap for >1 rank: rank 0 calls meepcu_comm_unique_id, the host distributes the
+ * 128 bytes (MPI, torch.distributed, a file ...), every rank calls meepcu_comm_init. */
+int meepcu_comm_unique_id(void *id128);
+int meepcu_comm_init(meepcu_ctx *ctx, int rank, int nranks, const void *id128);
+
+/* Freeze the description: allocate device mirrors, upload everything, build the tile lists. */
+int meepcu_finalize(meepcu_ctx *ctx);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+/* Advance nsteps time steps == nsteps calls of fields::step() (src/step.cpp:35-140), including
+ * step_db, step_source, step_boundaries, update_eh, update_pols and update_dfts.
+ * samples[s*n_src_times + j] holds src_time j's values for step s (may be NULL if there are none). */
+int meepcu_step(meepcu_ctx *ctx, int nsteps, int n_src_times, const meepcu_src_sample *samples);
+
+/* ---- coherence with the host object graph -------------------------------- */
+int meepcu_sync_to_host(meepcu_ctx *ctx);   /* device -> caller's arrays (fields, aux, P, dft) */
+int meepcu_sync_from_host(meepcu_ctx *ctx); /* caller's arrays -> device (fields, aux, P, dft, materials) */
+int meepcu_get_time(meepcu_ctx *ctx, int *t);
+int meepcu_set_time(meepcu_ctx *ctx, int t);
+/* the per-step NaN test of src/step.cpp:138-139, evaluated lazily on the device */
+int meepcu_check_finite(meepcu_ctx *ctx, int *ok);
+/* one element of a registered host array, read from the device mirror (fields::get_field probes) */
+int meepcu_read_value(meepcu_ctx *ctx, const void *host_ptr, double *out);
+
+/* ---- introspection ------------------------------------------------------------------------ */
+/* seconds accumulated per reference time_sink (src/meep.hpp:1610-1633), CUDA-event based */
+int meepcu_get_timers(meepcu_ctx *ctx, double out[22]);
+typedef struct {
+  int64_t kernel_launches;    /* kernels of this library launched so far */
+  int64_t steps;              /* time steps executed */
+  int64_t device_bytes;       /* bytes of device memory owned by the context */
+  int64_t cells;              /* sum over chunks of owned cells (nx*ny*nz) */
+  int64_t algorithmic_bytes_per_step; /* compulsory HBM bytes per step (DESIGN.md accounting) */
+  double last_step_ms;        /* device time of the last meepcu_step call (CUDA events) */
+  int64_t reserved[8];
+} meepcu_stats;
+int meepcu_get_stats(meepcu_ctx *ctx, meepcu_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEEPCU_H */

@@ -1,0 +1,463 @@
+// meepcu_shim.hpp -- the reference-side binding of the C ABI in include/meepcu.h.
+//
+// This is the (header-only) piece a Meep maintainer adds to libmeep so that `fields::step()`
+// (reference src/step.cpp:35-140) runs on the GPU: it walks the existing C++ object graph
+// (fields -> fields_chunk -> structure_chunk, src/meep.hpp:590-598,1461-1485,1733-2339),
+// describes it to libmeepcuda.so with plain pointers, and forwards step()/sync calls.
+// It is compiled only where the reference headers exist (oracle/Makefile builds
+// oracle/_ref/*/ref_driver with it); INTEGRATION.md shows the 12-line patch to step.cpp.
+//
+// The same shim drives oracle/liboracle_meep.so (same ABI, CPU, in place), which is how the
+// oracle is pinned against the unmodified reference.
+//
+// Access to private members: a maintainer would declare `friend class meepcu::attachment;` in
+// `fields` and `fields_chunk`; out of tree we include meep.hpp with private/protected opened.
+#ifndef MEEPCU_SHIM_HPP
+#define MEEPCU_SHIM_HPP
+
+#include <algorithm>
+#include <complex>
+#include <functional>
+#include <limits>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include <stdio.h>
+#include <stddef.h>
+#include <string.h>
+#include <math.h>
+#include <dlfcn.h>
+
+#ifndef MEEPCU_SHIM_NO_OPEN_PRIVATE
+#define private public
+#define protected public
+#endif
+#include "meep.hpp"
+#include "meep_internals.hpp"
+#ifndef MEEPCU_SHIM_NO_OPEN_PRIVATE
+#undef private
+#undef protected
+#endif
+
+#include "meepcu.h"
+
+namespace meepcu {
+
+// ---- the ABI, resolved at run time so that libmeep does not link against CUDA ----------------
+struct api {
+  void *handle;
+#define MEEPCU_FN(name) decltype(&::meepcu_##name) name;
+  MEEPCU_FN(last_error)
+  MEEPCU_FN(backend)
+  MEEPCU_FN(abi_version)
+  MEEPCU_FN(create)
+  MEEPCU_FN(destroy)
+  MEEPCU_FN(add_chunk)
+  MEEPCU_FN(add_susceptibility)
+  MEEPCU_FN(add_source)
+  MEEPCU_FN(add_dft)
+  MEEPCU_FN(set_metal)
+  MEEPCU_FN(add_connections)
+  MEEPCU_FN(finalize)
+  MEEPCU_FN(step)
+  MEEPCU_FN(sync_to_host)
+  MEEPCU_FN(sync_from_host)
+  MEEPCU_FN(get_time)
+  MEEPCU_FN(set_time)
+  MEEPCU_FN(check_finite)
+  MEEPCU_FN(read_value)
+  MEEPCU_FN(get_timers)
+  MEEPCU_FN(get_stats)
+#undef MEEPCU_FN
+  explicit api(const char *path) {
+    handle = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!handle) meep::abort("meepcu: cannot load %s: %s", path, dlerror());
+#define MEEPCU_FN(name)                                                                            \
+  name = (decltype(name))dlsym(handle, "meepcu_" #name);                                           \
+  if (!name) meep::abort("meepcu: %s lacks symbol meepcu_" #name, path);
+    MEEPCU_FN(last_error)
+    MEEPCU_FN(backend)
+    MEEPCU_FN(abi_version)
+    MEEPCU_FN(create)
+    MEEPCU_FN(destroy)
+    MEEPCU_FN(add_chunk)
+    MEEPCU_FN(add_susceptibility)
+    MEEPCU_FN(add_source)
+    MEEPCU_FN(add_dft)
+    MEEPCU_FN(set_metal)
+    MEEPCU_FN(add_connections)
+    MEEPCU_FN(finalize)
+    MEEPCU_FN(step)
+    MEEPCU_FN(sync_to_host)
+    MEEPCU_FN(sync_from_host)
+    MEEPCU_FN(get_time)
+    MEEPCU_FN(set_time)
+    MEEPCU_FN(check_finite)
+    MEEPCU_FN(read_value)
+    MEEPCU_FN(get_timers)
+    MEEPCU_FN(get_stats)
+#undef MEEPCU_FN
+    if (abi_version() != MEEPCU_ABI_VERSION) meep::abort("meepcu: ABI version mismatch in %s", path);
+  }
+};
+
+// Optional observer of every ABI call (oracle/trace_recorder.hpp records golden traces with it).
+struct observer {
+  virtual ~observer() {}
+  virtual void on_create(const meepcu_config &) {}
+  virtual void on_chunk(int, const meepcu_chunk_desc &, size_t /*ntot*/) {}
+  virtual void on_susceptibility(int, const meepcu_susceptibility_desc &, size_t /*ntot*/) {}
+  virtual void on_source(int, const meepcu_source_desc &) {}
+  virtual void on_dft(int, const meepcu_dft_desc &, size_t /*N*/) {}
+  virtual void on_metal(int, size_t, void *const *) {}
+  virtual void on_connections(int, int, size_t, void *const *, const void *const *, const void *) {}
+  virtual void on_finalize() {}
+  virtual void on_step(int, int, const meepcu_src_sample *) {}
+};
+
+// One attachment = one meepcu context mirroring one `fields` object.
+class attachment {
+public:
+  attachment(meep::fields &f_, api &a_, int nl_mode = MEEPCU_NL_FORK_LITERAL, int device = 0,
+             observer *obs_ = 0)
+      : f(f_), a(a_), ctx(0), obs(obs_) {
+    describe(nl_mode, device);
+  }
+  ~attachment() {
+    if (ctx) a.destroy(ctx);
+  }
+
+  // == fields::step() repeated n times (src/step.cpp:35-140), fields stay on the device
+  void step(int n = 1) {
+    const int nsrc = (int)src_times.size();
+    std::vector<meepcu_src_sample> smp((size_t)n * std::max(nsrc, 1));
+    for (int s = 0; s < n; ++s) {
+      const double tm = (f.t + s) * f.dt; // fields::time()
+      for (int j = 0; j < nsrc; ++j) {
+        meep::src_time *st = src_times[j];
+        meepcu_src_sample &o = smp[(size_t)s * nsrc + j];
+        st->update(tm, f.dt); // step.cpp:64
+        put(o.current_B, st->current());
+        st->update(tm + 0.5 * f.dt, f.dt); // step.cpp:74,96
+        put(o.dipole_H, st->dipole());
+        put(o.current_D, st->current());
+        st->update(tm + f.dt, f.dt); // step.cpp:106
+        put(o.dipole_E, st->dipole());
+      }
+    }
+    if (obs) obs->on_step(n, nsrc, smp.data());
+    check(a.step(ctx, n, nsrc, nsrc ? smp.data() : 0));
+    f.t += n;
+  }
+  void sync_to_host() { check(a.sync_to_host(ctx)); }
+  void sync_from_host() {
+    check(a.set_time(ctx, f.t));
+    check(a.sync_from_host(ctx));
+  }
+  bool finite() {
+    int ok = 1;
+    check(a.check_finite(ctx, &ok));
+    return ok != 0;
+  }
+  meepcu_stats stats() {
+    meepcu_stats s;
+    check(a.get_stats(ctx, &s));
+    return s;
+  }
+  meepcu_ctx *context() { return ctx; }
+
+  // Perform, eagerly and without stepping, every allocation the reference makes lazily inside its
+  // first step (step_db.cpp:67-75, update_eh.cpp:204-216, update_pols.cpp:49-55), then reconnect
+  // the chunks (boundaries.cpp:171-183).  After this the set of arrays is stable.
+  static void allocate_lazily_created_arrays(meep::fields &f) {
+    using namespace meep;
+    const int is_real = f.is_real; // used by the reference's DOCMP macro
+    for (int i = 0; i < f.num_chunks; i++) f.chunks[i]->s->update_condinv(); // step.cpp:61-62
+    for (int i = 0; i < f.num_chunks; i++) {
+      fields_chunk *fc = f.chunks[i];
+      if (!fc->is_mine()) continue;
+      structure_chunk *s = fc->s;
+      const grid_volume &gv = fc->gv;
+      const size_t ntot = gv.ntot();
+      field_type dbs[2] = {B_stuff, D_stuff};
+      for (int k = 0; k < 2; ++k) { // step_db.cpp:48-75
+        field_type ft = dbs[k];
+        DOCMP FOR_FT_COMPONENTS(ft, cc) {
+          if (!fc->f[cc][cmp]) continue;
+          const direction d_c = component_direction(cc);
+          const direction dsig0 = cycle_direction(gv.dim, d_c, 1);
+          const direction dsig = s->sigsize[dsig0] > 1 ? dsig0 : NO_DIRECTION;
+          const direction dsigu0 = cycle_direction(gv.dim, d_c, 2);
+          const direction dsigu = s->sigsize[dsigu0] > 1 ? dsigu0 : NO_DIRECTION;
+          if (dsig != NO_DIRECTION && s->conductivity[cc][d_c] && !fc->f_cond[cc][cmp]) {
+            fc->f_cond[cc][cmp] = new realnum[ntot];
+            memset(fc->f_cond[cc][cmp], 0, sizeof(realnum) * ntot);
+          }
+          if (dsigu != NO_DIRECTION && !fc->f_u[cc][cmp]) {
+            fc->f_u[cc][cmp] = new realnum[ntot];
+            memcpy(fc->f_u[cc][cmp], fc->f[cc][cmp], ntot * sizeof(realnum));
+          }
+        }
+      }
+      field_type ehs[2] = {H_stuff, E_stuff};
+      for (int k = 0; k < 2; ++k) { // update_eh.cpp:67-226
+        field_type ft = ehs[k];
+        field_type ft2 = ft == E_stuff ? D_stuff : B_stuff;
+        bool have_int_sources = false;
+        for (const src_vol &sv : fc->sources[ft2])
+          if (sv.t()->is_integrated) have_int_sources = true;
+        bool have_f_minus_p = false;
+        FOR_FT_COMPONENTS(ft, ec) DOCMP {
+          if (!fc->f[ec][cmp]) continue;
+          bool need = have_int_sources;
+          for (polarization_state *p = fc->pol[ft]; p && !need; p = p->next)
+            need = need || p->s->needs_P(ec, cmp, fc->f);
+          if (need && cmp == 0) have_f_minus_p = true;
+        }
+        DOCMP FOR_FT_COMPONENTS(ft, ec) {
+          if (!fc->f[ec][cmp]) continue;
+          component dc = field_type_component(ft2, ec);
+          const direction d_ec = component_direction(ec);
+          const direction dsigw = s->sigsize[d_ec] > 1 ? d_ec : NO_DIRECTION;
+          if (fc->f[ec][cmp] == fc->f[dc][cmp] &&
+              (s->chi1inv[ec][d_ec] || have_f_minus_p || dsigw != NO_DIRECTION)) {
+            fc->f[ec][cmp] = new realnum[ntot];
+            memcpy(fc->f[ec][cmp], fc->f[dc][cmp], ntot * sizeof(realnum));
+          }
+          if (!fc->f_w[ec][cmp] && dsigw != NO_DIRECTION) {
+            fc->f_w[ec][cmp] = new realnum[ntot];
+            memcpy(fc->f_w[ec][cmp], fc->f[ec][cmp], ntot * sizeof(realnum));
+          }
+          if (fc->needs_W_prev(ec))
+            meep::abort("meepcu: susceptibilities that need W_prev are outside the GPU path");
+        }
+        for (polarization_state *p = fc->pol[ft]; p; p = p->next) { // update_pols.cpp:49-55
+          if (!p->data) {
+            p->data = p->s->new_internal_data(fc->f, gv);
+            if (p->data) p->s->init_internal_data(fc->f, fc->dt, gv, p->data);
+          }
+        }
+      }
+    }
+    f.chunk_connections_valid = false;
+    f.connect_chunks();
+  }
+
+private:
+  meep::fields &f;
+  api &a;
+  meepcu_ctx *ctx;
+  observer *obs;
+  std::vector<meep::src_time *> src_times;
+  std::vector<std::vector<double> > keep_amp; // storage handed to the ABI during description
+
+  static void put(double o[2], std::complex<double> z) {
+    o[0] = z.real();
+    o[1] = z.imag();
+  }
+  void check(int rc) {
+    if (rc != MEEPCU_OK) meep::abort("meepcu (%s): %s", a.backend(), a.last_error());
+  }
+
+  void describe(int nl_mode, int device) {
+    using namespace meep;
+    if (f.gv.dim == Dcyl) meep::abort("meepcu: cylindrical coordinates are outside the GPU path");
+    if (f.bfast_scaled_k[0] || f.bfast_scaled_k[1] || f.bfast_scaled_k[2])
+      meep::abort("meepcu: BFAST is outside the GPU path");
+    if (f.is_phasing()) meep::abort("meepcu: phase_material is outside the GPU path");
+    for (int i = 0; i < f.num_chunks; i++)
+      if (!f.chunks[i]->is_mine())
+        meep::abort("meepcu: MPI-distributed chunks: use one process and several GPUs instead");
+    allocate_lazily_created_arrays(f);
+
+    meepcu_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.abi_version = MEEPCU_ABI_VERSION;
+    cfg.realnum_bytes = (int)sizeof(realnum);
+    cfg.is_real = f.is_real;
+    cfg.dim = (int)f.gv.dim;
+    cfg.a = f.a;
+    cfg.dt = f.dt;
+    cfg.courant = f.num_chunks ? f.chunks[0]->Courant : f.dt * f.a;
+    cfg.beta = f.beta;
+    cfg.nl_mode = nl_mode;
+    cfg.device = device;
+    cfg.t = f.t;
+    if (obs) obs->on_create(cfg);
+    check(a.create(&cfg, &ctx));
+
+    // src_time list -> ids (fields::sources, src/meep.hpp:1736)
+    std::map<const src_time *, int> src_id;
+    for (src_time *s = f.sources; s; s = s->next) {
+      src_id[s] = (int)src_times.size();
+      src_times.push_back(s);
+    }
+
+    for (int i = 0; i < f.num_chunks; i++) {
+      fields_chunk *fc = f.chunks[i];
+      structure_chunk *s = fc->s;
+      const grid_volume &gv = fc->gv;
+      meepcu_chunk_desc d;
+      memset(&d, 0, sizeof d);
+      const direction xyz[3] = {X, Y, Z};
+      for (int k = 0; k < 3; ++k) {
+        d.num[k] = has_direction(gv.dim, xyz[k]) ? gv.num_direction(xyz[k]) : 0;
+        d.io[k] = has_direction(gv.dim, xyz[k]) ? gv.little_corner().in_direction(xyz[k]) : 0;
+      }
+      FOR_COMPONENTS(c) {
+        for (int cmp = 0; cmp < 2; ++cmp) {
+          d.f[c][cmp] = fc->f[c][cmp];
+          d.f_u[c][cmp] = fc->f_u[c][cmp];
+          d.f_w[c][cmp] = fc->f_w[c][cmp];
+          d.f_cond[c][cmp] = fc->f_cond[c][cmp];
+        }
+        for (int dd = 0; dd < 5; ++dd) {
+          d.chi1inv[c][dd] = s->chi1inv[c][dd];
+          d.conductivity[c][dd] = s->conductivity[c][dd];
+          d.condinv[c][dd] = s->condinv[c][dd];
+        }
+        d.chi2[c] = s->chi2[c];
+        d.chi3[c] = s->chi3[c];
+      }
+      for (int dd = 0; dd < 6; ++dd) {
+        d.sig[dd] = s->sig[dd];
+        d.kap[dd] = s->kap[dd];
+        d.siginv[dd] = s->siginv[dd];
+        d.sigsize[dd] = s->sigsize[dd];
+      }
+      d.rank = 0;
+      int id = -1;
+      if (obs) obs->on_chunk(i, d, gv.ntot());
+      check(a.add_chunk(ctx, &d, &id));
+      if (id != i) meep::abort("meepcu: chunk numbering mismatch");
+
+      // polarizations, in list order (update_eh.cpp:130-131, update_pols.cpp:46)
+      field_type ehs[2] = {E_stuff, H_stuff};
+      for (int k = 0; k < 2; ++k)
+        for (polarization_state *p = fc->pol[ehs[k]]; p; p = p->next) {
+          const lorentzian_susceptibility *ls =
+              dynamic_cast<const lorentzian_susceptibility *>(p->s);
+          if (!ls || typeid(*p->s) != typeid(lorentzian_susceptibility))
+            meep::abort("meepcu: only Lorentzian/Drude susceptibilities are on the GPU path");
+          meepcu_susceptibility_desc sd;
+          memset(&sd, 0, sizeof sd);
+          sd.ft = (int)ehs[k];
+          sd.omega_0 = ls->omega_0;
+          sd.gamma = ls->gamma;
+          sd.no_omega_0_denominator = ls->no_omega_0_denominator;
+          FOR_COMPONENTS(c) {
+            for (int dd = 0; dd < 5; ++dd) sd.sigma[c][dd] = ls->sigma[c][dd];
+            if (p->data)
+              for (int cmp = 0; cmp < 2; ++cmp) {
+                // lorentzian_data layout, susceptibility.cpp:98-139: P then P_prev, ntot apart
+                realnum *P = ls->cinternal_notowned_ptr(0, c, cmp, 0, p->data);
+                sd.P[c][cmp] = P;
+                sd.P_prev[c][cmp] = P ? P + gv.ntot() : 0;
+              }
+          }
+          if (obs) obs->on_susceptibility(i, sd, gv.ntot());
+          check(a.add_susceptibility(ctx, i, &sd));
+        }
+
+      // sources (fields_chunk::sources[D_stuff|B_stuff])
+      field_type dbs[2] = {B_stuff, D_stuff};
+      for (int k = 0; k < 2; ++k)
+        for (const src_vol &sv : fc->sources[dbs[k]]) {
+          meepcu_source_desc sd;
+          memset(&sd, 0, sizeof sd);
+          sd.ft = (int)dbs[k];
+          sd.c = (int)sv.c;
+          sd.src_time_id = src_id.at(sv.t());
+          sd.is_integrated = sv.t()->is_integrated;
+          sd.n = sv.num_points();
+          std::vector<ptrdiff_t> idx(sd.n);
+          std::vector<double> amp(2 * sd.n);
+          for (size_t j = 0; j < sd.n; ++j) {
+            idx[j] = sv.index_at(j);
+            amp[2 * j] = sv.amplitude(j).real();
+            amp[2 * j + 1] = sv.amplitude(j).imag();
+          }
+          sd.index = idx.data();
+          sd.amp = amp.data();
+          if (obs) obs->on_source(i, sd);
+          check(a.add_source(ctx, i, &sd));
+        }
+
+      // DFT chunks (fields_chunk::dft_chunks, dft.cpp:57-129)
+      for (dft_chunk *dc = fc->dft_chunks; dc; dc = dc->next_in_chunk) {
+        meepcu_dft_desc dd;
+        memset(&dd, 0, sizeof dd);
+        dd.c = (int)dc->c;
+        for (int k = 0; k < 3; ++k) {
+          const bool has = has_direction(gv.dim, xyz[k]);
+          dd.is[k] = has ? dc->is.in_direction(xyz[k]) : 0;
+          dd.ie[k] = has ? dc->ie.in_direction(xyz[k]) : 0;
+          dd.s0[k] = dc->s0.in_direction(xyz[k]);
+          dd.s1[k] = dc->s1.in_direction(xyz[k]);
+          dd.e0[k] = dc->e0.in_direction(xyz[k]);
+          dd.e1[k] = dc->e1.in_direction(xyz[k]);
+        }
+        dd.dV0 = dc->dV0;
+        dd.dV1 = dc->dV1;
+        dd.avg1 = dc->avg1;
+        dd.avg2 = dc->avg2;
+        dd.include_dV_and_interp_weights = dc->include_dV_and_interp_weights;
+        dd.sqrt_dV_and_interp_weights = dc->sqrt_dV_and_interp_weights;
+        dd.decimation_factor = dc->get_decimation_factor();
+        dd.Nomega = (int)dc->omega.size();
+        dd.omega = dc->omega.data();
+        dd.scale[0] = dc->scale.real();
+        dd.scale[1] = dc->scale.imag();
+        dd.dft = dc->dft;
+        if (obs) obs->on_dft(i, dd, dc->N);
+        check(a.add_dft(ctx, i, &dd, 0));
+      }
+    }
+
+    // metal points and chunk connections, per field type (boundaries.cpp:309-623)
+    FOR_FIELD_TYPES(ft) {
+      std::vector<void *> z;
+      for (int i = 0; i < f.num_chunks; i++)
+        for (size_t k = 0; k < f.chunks[i]->num_zeroes[ft]; ++k)
+          z.push_back(f.chunks[i]->zeroes[ft][k]);
+      if (obs) obs->on_metal((int)ft, z.size(), z.data());
+      check(a.set_metal(ctx, (int)ft, z.size(), z.data()));
+
+      for (connect_phase ip : all_connect_phases) {
+        std::vector<void *> dst;
+        std::vector<const void *> src;
+        std::vector<std::complex<realnum> > ph;
+        // same order as step_boundaries' send loop (step.cpp:252-268)
+        for (const comms_operation &op : f.comms_sequence_for_field[ft].send_ops) {
+          const chunk_pair pair{(int)op.my_chunk_idx, (int)op.other_chunk_idx};
+          const comms_key key = {ft, ip, pair};
+          if (!f.get_comm_size(key)) continue;
+          const std::vector<realnum *> &out = f.chunks[pair.first]->connections_out.at(key);
+          const std::vector<realnum *> &in = f.chunks[pair.second]->connections_in.at(key);
+          if (out.size() != in.size()) meep::abort("meepcu: connection size mismatch");
+          for (size_t n = 0; n < out.size(); ++n) {
+            src.push_back(out[n]);
+            dst.push_back(in[n]);
+          }
+          if (ip == CONNECT_PHASE) {
+            const std::vector<std::complex<realnum> > &p =
+                f.chunks[pair.second]->connection_phases.at(key);
+            ph.insert(ph.end(), p.begin(), p.end());
+          }
+        }
+        if (dst.empty()) continue;
+        if (obs) obs->on_connections((int)ft, (int)ip, dst.size(), dst.data(), src.data(), ph.data());
+        check(a.add_connections(ctx, (int)ft, (int)ip, dst.size(), dst.data(), src.data(),
+                                ph.data()));
+      }
+    }
+    if (obs) obs->on_finalize();
+    check(a.finalize(ctx));
+  }
+};
+
+} // namespace meepcu
+#endif

@@ -1,0 +1,1234 @@
+// oracle_meep.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// A plain, single-threaded-per-loop CPU restatement of the reference's per-timestep field update
+// (PMack10/meep_nl, /root/reference/src), implementing the C ABI of include/meepcu.h *in place*
+// on the caller's host arrays.  It exists so that tests can compare the CUDA path against an
+// independent implementation on the same inputs on machines that do not have the reference
+// (the GPU box).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference leg may load it; libmeepcuda.so never does.
+//
+// Parity status: PINNED.  tests/test_oracle_vs_reference.py drives the unmodified reference
+// (oracle/_ref/*/libmeep_ref.a, built by oracle/build_ref.sh) and this file from the same
+// fields object through oracle/ref_driver.cpp and requires bit-identical arrays; the traces and
+// results of those runs are committed under tests/golden/ and re-checked without the reference.
+//
+// Each function cites the reference lines it restates.  Loops are written per component and per
+// chunk exactly like the reference (this is deliberately NOT the fused structure of the kernels).
+//
+// Build: g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC (see oracle/Makefile).  No -march, no
+// -ffast-math: the arithmetic must be the plain IEEE sequence of the reference's build.
+
+#include "../include/meepcu.h"
+
+#include <cmath>
+#include <complex>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+// ---- component / direction helpers (src/meep/vec.hpp:414-592, src/fields.cpp:411-425) ----------
+enum { Ex = 0, Hx = 5, Dx = 10, Bx = 15 };
+inline bool is_electric(int c) { return c < Hx; }
+inline bool is_magnetic(int c) { return c >= Hx && c < Dx; }
+inline bool is_D(int c) { return c >= Dx && c < Bx; }
+inline bool is_B(int c) { return c >= Bx && c < 20; }
+inline int comp_type(int c) { return is_electric(c) ? 0 : is_magnetic(c) ? 1 : is_D(c) ? 2 : 3; }
+inline int first_comp(int ft) { return 5 * ft; } // E,H,D,B -> Ex,Hx,Dx,Bx
+inline int comp_dir(int c) {                     // component_direction
+  static const int d[5] = {MEEPCU_X, MEEPCU_Y, MEEPCU_R, MEEPCU_P, MEEPCU_Z};
+  return d[c % 5];
+}
+inline int dir_comp(int c, int d) { // direction_component(c, d)
+  static const int off[5] = {0, 1, 4, 2, 3};
+  return (c / 5) * 5 + off[d];
+}
+inline int cycle_dir(int d, int shift) { return (d + shift + 99) % 3; } // cartesian only
+inline bool cross_negative(int a, int b) { return ((3 + b - a) % 3) == 2; }
+inline int cross(int a, int b) { return (3 + 2 * a - b) % 3; }
+
+struct Grid { // the parts of grid_volume the hot path uses (src/meep/vec.hpp:1014-1178)
+  int dim;
+  int num[3];
+  int io[3];
+  bool has[3];         // has_direction(dim, d)
+  ptrdiff_t stride[3]; // set_strides, src/vec.cpp:482-494
+  size_t ntot;         // update_ntot, src/vec.cpp:293-296
+  void init(int dim_, const int num_[3], const int io_[3]) {
+    dim = dim_;
+    has[0] = has[1] = (dim == MEEPCU_D2 || dim == MEEPCU_D3);
+    has[2] = (dim == MEEPCU_D1 || dim == MEEPCU_D3);
+    for (int d = 0; d < 3; ++d) {
+      num[d] = has[d] ? num_[d] : 0;
+      io[d] = has[d] ? io_[d] : 0;
+    }
+    ntot = 1;
+    for (int d = 0; d < 3; ++d)
+      if (has[d]) ntot *= (size_t)(num[d] + 1);
+    stride[0] = stride[1] = stride[2] = 0;
+    if (has[2]) stride[2] = 1;
+    if (has[1]) stride[1] = num[2] + 1;
+    if (has[0]) stride[0] = (ptrdiff_t)(num[2] + 1) * (num[1] + 1);
+  }
+  bool has_field(int c) const { // grid_volume::has_field
+    if (dim == MEEPCU_D1) return c == 0 || c == 6 || c == 10 || c == 16; // Ex,Hy,Dx,By
+    int d = comp_dir(c);
+    return d < MEEPCU_R;
+  }
+  int yee_shift(int c, int d) const { // iyee_shift(c).in_direction(d)
+    if (!has[d]) return 0;
+    int dc = comp_dir(c);
+    if ((is_electric(c) || is_D(c)) && d == dc) return 1;
+    if ((is_magnetic(c) || is_B(c)) && d != dc) return 1;
+    return 0;
+  }
+  int yucky_dir(int n) const { return dim == MEEPCU_D2 ? (n + 2) % 3 : n; } // src/vec.cpp:262-272
+};
+
+// LOOP_OVER_IVECS restated (src/meep/vec.hpp:151-168)
+struct Loop {
+  ptrdiff_t n[3], s[3], idx0;
+  int is[3];  // loop_is1..3 (yucky order)
+  int dir[3]; // loop_d1..3
+  Loop(const Grid &g, const int is_[3], const int ie_[3]) {
+    idx0 = 0;
+    for (int k = 0; k < 3; ++k) {
+      int d = g.yucky_dir(k);
+      dir[k] = d;
+      int isv = g.has[d] ? is_[d] : 0, iev = g.has[d] ? ie_[d] : 0;
+      is[k] = isv;
+      n[k] = (iev - isv) / 2 + 1;
+      s[k] = g.stride[d];
+      int off = g.has[d] ? (is_[d] - g.io[d]) : 0;
+      idx0 += (off / 2) * s[k];
+    }
+  }
+};
+#define OLOOP(L, idx)                                                                              \
+  for (ptrdiff_t loop_i1 = 0; loop_i1 < (L).n[0]; ++loop_i1)                                       \
+    for (ptrdiff_t loop_i2 = 0; loop_i2 < (L).n[1]; ++loop_i2)                                     \
+      for (ptrdiff_t loop_i3 = 0, idx = (L).idx0 + loop_i1 * (L).s[0] + loop_i2 * (L).s[1];        \
+           loop_i3 < (L).n[2]; ++loop_i3, idx += (L).s[2])
+
+// KSTRIDE_DEF / KDEF restated (src/meep_internals.hpp:241-252)
+struct KIdx {
+  int k0, s1, s2, s3;
+  KIdx() : k0(0), s1(0), s2(0), s3(0) {}
+  KIdx(const Grid &g, int dsig, const int is[3]) {
+    k0 = is[dsig] - g.io[dsig];
+    s1 = g.yucky_dir(0) == dsig ? 2 : 0;
+    s2 = g.yucky_dir(1) == dsig ? 2 : 0;
+    s3 = g.yucky_dir(2) == dsig ? 2 : 0;
+  }
+  int at(ptrdiff_t i1, ptrdiff_t i2, ptrdiff_t i3) const {
+    return (int)(((k0 + s1 * i1) + s2 * i2) + s3 * i3);
+  }
+};
+
+struct SrcVol {
+  int ft, c, src_time_id, is_integrated;
+  std::vector<ptrdiff_t> index;
+  std::vector<std::complex<double> > amp;
+};
+
+struct CtxBase {
+  meepcu_config cfg;
+  int t;
+  bool finalized;
+  virtual ~CtxBase() {}
+  virtual int add_chunk(const meepcu_chunk_desc *d, int *id) = 0;
+  virtual int add_susc(int chunk, const meepcu_susceptibility_desc *d) = 0;
+  virtual int add_source(int chunk, const meepcu_source_desc *d) = 0;
+  virtual int add_dft(int chunk, const meepcu_dft_desc *d, int *id) = 0;
+  virtual int set_metal(int ft, size_t n, void *const *ptrs) = 0;
+  virtual int add_conn(int ft, int kind, size_t n, void *const *dst, const void *const *src,
+                       const void *phases) = 0;
+  virtual int step(int nsteps, int nsrc, const meepcu_src_sample *smp) = 0;
+  virtual int check_finite(int *ok) = 0;
+  virtual int read_value(const void *p, double *out) = 0;
+  virtual int64_t cells() = 0;
+};
+
+template <class T> struct Susc {
+  meepcu_susceptibility_desc d;
+};
+
+template <class T> struct Dft {
+  meepcu_dft_desc d;
+  std::vector<double> omega;
+  std::vector<std::complex<T> > own; // storage when the caller passed dft == NULL
+  std::complex<T> *dft;
+  size_t N;
+};
+
+template <class T> struct Chunk {
+  meepcu_chunk_desc d;
+  Grid g;
+  std::vector<Susc<T> > pol[2]; // [E_stuff], [H_stuff]
+  std::vector<SrcVol> sources[4]; // indexed by ft (only D_STUFF, B_STUFF used)
+  std::vector<Dft<T> > dfts;    // in list order (newest first, like the reference's linked list)
+  std::vector<T> fmp_store[MEEPCU_NUM_COMPONENTS][2]; // f_minus_p scratch (update_eh.cpp:94-103)
+  // step plan (src/fields.cpp:441-469)
+  bool have_plus[20], have_minus[20];
+  int plus_c[20], minus_c[20], plus_d[20], minus_d[20];
+
+  T *F(int c, int cmp) const { return (T *)d.f[c][cmp]; }
+};
+
+template <class T> struct Conn {
+  std::vector<T *> dst;
+  std::vector<const T *> src;
+  std::vector<std::complex<T> > phase;
+};
+
+template <class T> struct Impl : CtxBase {
+  std::vector<Chunk<T> > chunks;
+  std::vector<T *> zeroes[MEEPCU_NUM_FIELD_TYPES];
+  Conn<T> conn[MEEPCU_NUM_FIELD_TYPES][3];
+
+  // ---------------------------------------------------------------------------------------------
+  int add_chunk(const meepcu_chunk_desc *d, int *id) {
+    Chunk<T> ch;
+    ch.d = *d;
+    ch.g.init(cfg.dim, d->num, d->io);
+    // figure_out_step_plan, src/fields.cpp:441-469
+    for (int c = 0; c < 20; ++c) ch.have_plus[c] = ch.have_minus[c] = false;
+    for (int c1 = 0; c1 < 20; ++c1) {
+      if (!d->f[c1][0]) continue;
+      int dc1 = comp_dir(c1);
+      for (int c2 = 0; c2 < 20; ++c2) {
+        if (!((is_electric(c1) && is_magnetic(c2)) || (is_D(c1) && is_magnetic(c2)) ||
+              (is_magnetic(c1) && is_electric(c2)) || (is_B(c1) && is_electric(c2))))
+          continue;
+        int dc2 = comp_dir(c2);
+        if (dc1 >= MEEPCU_R || dc2 >= MEEPCU_R) continue; // no cylindrical support
+        if (dc1 != dc2 && ch.g.has_field(c2) && ch.g.has_field(c1) && ch.g.has[cross(dc1, dc2)]) {
+          int dd = cross(dc1, dc2);
+          if (cross_negative(dc2, dc1)) {
+            ch.minus_c[c1] = c2;
+            ch.have_minus[c1] = true;
+            ch.minus_d[c1] = dd;
+          }
+          else {
+            ch.plus_c[c1] = c2;
+            ch.have_plus[c1] = true;
+            ch.plus_d[c1] = dd;
+          }
+        }
+      }
+    }
+    chunks.push_back(ch);
+    if (id) *id = (int)chunks.size() - 1;
+    return MEEPCU_OK;
+  }
+  int add_susc(int chunk, const meepcu_susceptibility_desc *d) {
+    if (chunk < 0 || chunk >= (int)chunks.size()) return fail(MEEPCU_EINVAL, "bad chunk id");
+    if (d->ft != MEEPCU_E_STUFF && d->ft != MEEPCU_H_STUFF)
+      return fail(MEEPCU_EINVAL, "susceptibility ft must be E_stuff or H_stuff");
+    Susc<T> s;
+    s.d = *d;
+    chunks[chunk].pol[d->ft].push_back(s);
+    return MEEPCU_OK;
+  }
+  int add_source(int chunk, const meepcu_source_desc *d) {
+    if (chunk < 0 || chunk >= (int)chunks.size()) return fail(MEEPCU_EINVAL, "bad chunk id");
+    if (d->ft != MEEPCU_D_STUFF && d->ft != MEEPCU_B_STUFF)
+      return fail(MEEPCU_EINVAL, "source ft must be D_stuff or B_stuff");
+    SrcVol sv;
+    sv.ft = d->ft;
+    sv.c = d->c;
+    sv.src_time_id = d->src_time_id;
+    sv.is_integrated = d->is_integrated;
+    sv.index.assign(d->index, d->index + d->n);
+    sv.amp.resize(d->n);
+    for (size_t j = 0; j < d->n; ++j)
+      sv.amp[j] = std::complex<double>(d->amp[2 * j], d->amp[2 * j + 1]);
+    chunks[chunk].sources[d->ft].push_back(sv);
+    return MEEPCU_OK;
+  }
+  int add_dft(int chunk, const meepcu_dft_desc *d, int *id) {
+    if (chunk < 0 || chunk >= (int)chunks.size()) return fail(MEEPCU_EINVAL, "bad chunk id");
+    Chunk<T> &ch = chunks[chunk];
+    Dft<T> f;
+    f.d = *d;
+    f.omega.assign(d->omega, d->omega + d->Nomega);
+    f.N = 1;
+    for (int dd = 0; dd < 3; ++dd)
+      if (ch.g.has[dd]) f.N *= (size_t)((d->ie[dd] - d->is[dd]) / 2 + 1);
+    ch.dfts.push_back(f);
+    Dft<T> &r = ch.dfts.back();
+    if (d->dft)
+      r.dft = (std::complex<T> *)d->dft;
+    else {
+      r.own.assign(r.N * d->Nomega, std::complex<T>(0, 0));
+      r.dft = NULL; // fixed up at use (vector may move)
+    }
+    if (id) *id = (int)ch.dfts.size() - 1;
+    return MEEPCU_OK;
+  }
+  int set_metal(int ft, size_t n, void *const *ptrs) {
+    if (ft < 0 || ft >= MEEPCU_NUM_FIELD_TYPES) return fail(MEEPCU_EINVAL, "bad field type");
+    zeroes[ft].clear();
+    for (size_t i = 0; i < n; ++i) zeroes[ft].push_back((T *)ptrs[i]);
+    return MEEPCU_OK;
+  }
+  int add_conn(int ft, int kind, size_t n, void *const *dst, const void *const *src,
+               const void *phases) {
+    if (ft < 0 || ft >= MEEPCU_NUM_FIELD_TYPES || kind < 0 || kind > 2)
+      return fail(MEEPCU_EINVAL, "bad connection family");
+    Conn<T> &c = conn[ft][kind];
+    for (size_t i = 0; i < n; ++i) {
+      c.dst.push_back((T *)dst[i]);
+      c.src.push_back((const T *)src[i]);
+    }
+    if (kind == MEEPCU_CONNECT_PHASE) {
+      const std::complex<T> *ph = (const std::complex<T> *)phases;
+      for (size_t i = 0; i < n / 2; ++i) c.phase.push_back(ph[i]);
+    }
+    return MEEPCU_OK;
+  }
+  int64_t cells() {
+    int64_t tot = 0;
+    for (size_t i = 0; i < chunks.size(); ++i) {
+      int64_t n = 1;
+      for (int d = 0; d < 3; ++d)
+        if (chunks[i].g.has[d]) n *= chunks[i].g.num[d];
+      tot += n;
+    }
+    return tot;
+  }
+
+  // ---------------------------------------------------------------------------------------------
+  // step_curl, src/step_generic.cpp:69-253.  The 16 hand-specialised loops of the reference are
+  // the four stages below with absent terms dropped; each retained expression is written with
+  // the reference's operand order so that the roundings are identical.
+  void step_curl(T *f, const T *g1, const T *g2, ptrdiff_t s1, ptrdiff_t s2, const Grid &g,
+                 const int is[3], const int ie[3], T dtdx, int dsig, const T *sig, const T *kap,
+                 const T *siginv, T *fu, int dsigu, const T *sigu, const T *kapu, const T *siginvu,
+                 T dt, const T *cnd, const T *cndinv, T *fcnd) {
+    if (!g1) { // :76-80
+      std::swap(g1, g2);
+      std::swap(s1, s2);
+      dtdx = -dtdx;
+    }
+    Loop L(g, is, ie);
+    KIdx K, KU;
+    if (dsig != MEEPCU_NO_DIRECTION) K = KIdx(g, dsig, is);
+    if (dsigu != MEEPCU_NO_DIRECTION) KU = KIdx(g, dsigu, is);
+    const T dt2 = dt * 0.5;
+#pragma omp parallel for collapse(2)
+    OLOOP(L, i) {
+      T curl = g2 ? (g1[i + s1] - g1[i] + g2[i] - g2[i + s2]) : (g1[i + s1] - g1[i]);
+      if (dsig == MEEPCU_NO_DIRECTION) {
+        if (dsigu == MEEPCU_NO_DIRECTION) {
+          if (cnd) // :95,101
+            f[i] = ((1 - dt2 * cnd[i]) * f[i] - dtdx * curl) * cndinv[i];
+          else // :108,112
+            f[i] -= dtdx * curl;
+        }
+        else {
+          const int ku = KU.at(loop_i1, loop_i2, loop_i3);
+          T fprev = fu[i];
+          if (cnd) // :124-127
+            fu[i] = ((1 - dt2 * cnd[i]) * fprev - dtdx * curl) * cndinv[i];
+          else // :144
+            fu[i] -= dtdx * curl;
+          f[i] = siginvu[ku] * ((kapu[ku] - sigu[ku]) * f[i] + fu[i] - fprev);
+        }
+      }
+      else {
+        const int k = K.at(loop_i1, loop_i2, loop_i3);
+        if (dsigu == MEEPCU_NO_DIRECTION) {
+          if (cnd) { // :167-171
+            T fcnd_prev = fcnd[i];
+            fcnd[i] = ((1 - dt2 * cnd[i]) * fcnd[i] - dtdx * curl) * cndinv[i];
+            f[i] = ((kap[k] - sig[k]) * f[i] + (fcnd[i] - fcnd_prev)) * siginv[k];
+          }
+          else // :187
+            f[i] = ((kap[k] - sig[k]) * f[i] - dtdx * curl) * siginv[k];
+        }
+        else {
+          const int ku = KU.at(loop_i1, loop_i2, loop_i3);
+          T fprev = fu[i];
+          if (cnd) { // :208-214
+            T fcnd_prev = fcnd[i];
+            fcnd[i] = ((1 - dt2 * cnd[i]) * fcnd[i] - dtdx * curl) * cndinv[i];
+            fu[i] = ((kap[k] - sig[k]) * fu[i] + (fcnd[i] - fcnd_prev)) * siginv[k];
+          }
+          else // :236
+            fu[i] = ((kap[k] - sig[k]) * fu[i] - dtdx * curl) * siginv[k];
+          f[i] = siginvu[ku] * ((kapu[ku] - sigu[ku]) * f[i] + fu[i] - fprev);
+        }
+      }
+    }
+  }
+
+  // fields_chunk::step_db, src/step_db.cpp:44-146 (Cartesian part; no bfast, no tiles: the loop
+  // body is independent per point so tiling does not change results)
+  int step_db(int ft) {
+    for (size_t ic = 0; ic < chunks.size(); ++ic) {
+      Chunk<T> &ch = chunks[ic];
+      const Grid &g = ch.g;
+      for (int cmp = 0; cmp < 2; ++cmp)
+        for (int cc = first_comp(ft); cc < first_comp(ft) + 5; ++cc) {
+          if (!ch.F(cc, cmp)) continue;
+          const int d_c = comp_dir(cc);
+          const bool have_p = ch.have_plus[cc], have_m = ch.have_minus[cc];
+          const int dsig0 = cycle_dir(d_c, 1);
+          const int dsig = ch.d.sigsize[dsig0] > 1 ? dsig0 : MEEPCU_NO_DIRECTION;
+          const int dsigu0 = cycle_dir(d_c, 2);
+          const int dsigu = ch.d.sigsize[dsigu0] > 1 ? dsigu0 : MEEPCU_NO_DIRECTION;
+          ptrdiff_t stride_p = have_p ? g.stride[ch.plus_d[cc]] : 0;
+          ptrdiff_t stride_m = have_m ? g.stride[ch.minus_d[cc]] : 0;
+          const T *f_p = have_p ? ch.F(ch.plus_c[cc], cmp) : NULL;
+          const T *f_m = have_m ? ch.F(ch.minus_c[cc], cmp) : NULL;
+          if (!f_p && !f_m) continue; // nothing to curl from (reference would dereference NULL)
+          const T *cnd = (const T *)ch.d.conductivity[cc][d_c];
+          const T *cndinv = (const T *)ch.d.condinv[cc][d_c];
+          T *fcnd = (T *)ch.d.f_cond[cc][cmp];
+          T *fu = (T *)ch.d.f_u[cc][cmp];
+          if (dsig != MEEPCU_NO_DIRECTION && cnd && !fcnd)
+            return fail(MEEPCU_ESTATE, "f_cond not allocated (step_db.cpp:67-70)");
+          if (dsigu != MEEPCU_NO_DIRECTION && !fu)
+            return fail(MEEPCU_ESTATE, "f_u not allocated (step_db.cpp:71-75)");
+          if (ft == MEEPCU_D_STUFF) { // :81-84
+            stride_p = -stride_p;
+            stride_m = -stride_m;
+          }
+          int is[3], ie[3];
+          for (int d = 0; d < 3; ++d) { // little_owned_corner0(cc), big_corner()
+            is[d] = g.io[d] + 2 - g.yee_shift(cc, d);
+            ie[d] = g.io[d] + 2 * g.num[d];
+          }
+          step_curl(ch.F(cc, cmp), f_p, f_m, stride_p, stride_m, g, is, ie, (T)cfg.courant, dsig,
+                    (const T *)ch.d.sig[dsig], (const T *)ch.d.kap[dsig],
+                    (const T *)ch.d.siginv[dsig], dsigu != MEEPCU_NO_DIRECTION ? fu : NULL, dsigu,
+                    (const T *)ch.d.sig[dsigu], (const T *)ch.d.kap[dsigu],
+                    (const T *)ch.d.siginv[dsigu], (T)cfg.dt, cnd, cndinv, fcnd);
+        }
+    }
+    if (cfg.dim == MEEPCU_D2 && cfg.beta != 0)
+      return fail(MEEPCU_EUNSUPPORTED, "beta != 0 (step_beta) not restated in the oracle yet");
+    return MEEPCU_OK;
+  }
+
+  // fields_chunk::step_source, src/step.cpp:296-319
+  void step_source(int ft, const meepcu_src_sample *smp) {
+    for (size_t ic = 0; ic < chunks.size(); ++ic) {
+      Chunk<T> &ch = chunks[ic];
+      for (size_t is = 0; is < ch.sources[ft].size(); ++is) {
+        const SrcVol &sv = ch.sources[ft][is];
+        const int c = dir_comp(first_comp(ft), comp_dir(sv.c));
+        const T *cndinv = (const T *)ch.d.condinv[c][comp_dir(sv.c)];
+        if (!sv.is_integrated && ch.F(c, 0) &&
+            ((ft == MEEPCU_D_STUFF && is_electric(sv.c)) ||
+             (ft == MEEPCU_B_STUFF && is_magnetic(sv.c)))) {
+          const double *cur = ft == MEEPCU_D_STUFF ? smp[sv.src_time_id].current_D
+                                                   : smp[sv.src_time_id].current_B;
+          const std::complex<double> current(cur[0], cur[1]);
+          for (size_t j = 0; j < sv.index.size(); ++j) {
+            const ptrdiff_t i = sv.index[j];
+            std::complex<double> A = sv.amp[j] * current * cfg.dt;
+            if (cndinv) A = sv.amp[j] * current * cfg.dt * double(cndinv[i]);
+            ch.F(c, 0)[i] -= real(A);
+            if (!cfg.is_real) ch.F(c, 1)[i] -= imag(A);
+          }
+        }
+      }
+    }
+  }
+
+  // fields::step_boundaries, src/step.cpp:226-288 + process_incoming_chunk_data :173-224, for
+  // chunks that all live in this process: metals first, gather every outgoing value, then scatter.
+  void step_boundaries(int ft) {
+    for (size_t i = 0; i < zeroes[ft].size(); ++i) *(zeroes[ft][i]) = 0.0; // boundaries.cpp:304-307
+    std::vector<T> block[3];
+    for (int k = 0; k < 3; ++k) {
+      const Conn<T> &c = conn[ft][k];
+      block[k].resize(c.src.size());
+      for (size_t n = 0; n < c.src.size(); ++n) block[k][n] = *(c.src[n]);
+    }
+    {
+      const Conn<T> &c = conn[ft][MEEPCU_CONNECT_PHASE];
+      const std::vector<T> &b = block[MEEPCU_CONNECT_PHASE];
+      for (size_t n = 0; n < c.src.size() / 2; ++n) { // :188-194
+        std::complex<T> temp = c.phase[n] * std::complex<T>(b[2 * n], b[2 * n + 1]);
+        *(c.dst[2 * n]) = temp.real();
+        *(c.dst[2 * n + 1]) = temp.imag();
+      }
+    }
+    {
+      const Conn<T> &c = conn[ft][MEEPCU_CONNECT_NEGATE];
+      for (size_t n = 0; n < c.src.size(); ++n) *(c.dst[n]) = -block[MEEPCU_CONNECT_NEGATE][n];
+    }
+    {
+      const Conn<T> &c = conn[ft][MEEPCU_CONNECT_COPY];
+      for (size_t n = 0; n < c.src.size(); ++n) *(c.dst[n]) = block[MEEPCU_CONNECT_COPY][n];
+    }
+  }
+
+  // ---- Newton-Raphson chi2 solve, src/newton_raphson.cpp:93-359 -------------------------------
+  struct Parameters { T A, B, C, D, E, F, G, H; }; // newton_raphson.hpp:11-13
+  static void equations(double x, double y, double z, const Parameters &p1, const Parameters &p2,
+                        const Parameters &p3, double F[3]) { // :144-155
+    F[0] = p1.A - (p1.B * x + p1.F * y * z + p1.G * x * z + p1.H * x * y);
+    F[1] = p2.A - (p2.B * y + p2.F * y * z + p2.G * x * z + p2.H * x * y);
+    F[2] = p3.A - (p3.B * z + p3.F * y * z + p3.G * x * z + p3.H * x * y);
+  }
+  static void jacobian(double x, double y, double z, const Parameters &p1, const Parameters &p2,
+                       const Parameters &p3, double J[3][3]) { // :157-168
+    J[0][0] = -p1.B - p1.G * z - p1.H * y;
+    J[0][1] = -p1.F * z - p1.H * x;
+    J[0][2] = -p1.F * y - p1.G * x;
+    J[1][0] = -p2.G * z - p2.H * y;
+    J[1][1] = -p2.B - p2.F * z - p2.H * x;
+    J[1][2] = -p2.F * y - p2.G * x;
+    J[2][0] = -p3.G * z - p3.H * y;
+    J[2][1] = -p3.F * z - p3.H * x;
+    J[2][2] = -p3.B - p3.F * y - p3.G * x;
+  }
+  static void solve3(const double J[3][3], const double F[3], double x[3]) { // :170-194
+    double A[3][3], b[3];
+    for (int i = 0; i < 3; ++i) {
+      b[i] = F[i];
+      for (int j = 0; j < 3; ++j) A[i][j] = J[i][j];
+    }
+    const int n = 3;
+    for (int i = 0; i < n; i++)
+      for (int j = i + 1; j < n; j++) {
+        double factor = A[j][i] / A[i][i];
+        for (int k = i; k < n; k++) A[j][k] -= factor * A[i][k];
+        b[j] -= factor * b[i];
+      }
+    for (int i = n - 1; i >= 0; i--) {
+      x[i] = b[i];
+      for (int j = i + 1; j < n; j++) x[i] -= A[i][j] * x[j];
+      x[i] /= A[i][i];
+    }
+  }
+  static bool newton_raphson(T x, T y, T z, const Parameters &p1, const Parameters &p2,
+                             const Parameters &p3, T *fw, T *fw_2, T *fw_3, double tol1,
+                             double tol2, double tol3, int max_iterations) { // :93-142
+    for (int iter = 0; iter < max_iterations; iter++) {
+      double F[3], J[3][3], delta[3];
+      equations(x, y, z, p1, p2, p3, F);
+      jacobian(x, y, z, p1, p2, p3, J);
+      solve3(J, F, delta);
+      x -= delta[0];
+      y -= delta[1];
+      z -= delta[2];
+      if (fabs(delta[0]) < tol1 && fabs(delta[1]) < tol2 && fabs(delta[2]) < tol3) {
+        double ax = std::abs(x), ay = std::abs(y), az = std::abs(z);
+        double fieldCheckPercent = (ax > ay ? (ax > az ? ax : az) : (ay > az ? ay : az)) * 1e-4;
+        double fCheck[3];
+        equations(x, y, z, p1, p2, p3, fCheck);
+        if (fCheck[0] <= fieldCheckPercent && fCheck[1] <= fieldCheckPercent &&
+            fCheck[2] <= fieldCheckPercent) {
+          *fw = x;
+          *fw_2 = y;
+          *fw_3 = z;
+          return true;
+        }
+      }
+    }
+    return false;
+  }
+  // runNR :209-359.  Returns false when the deterministic seed ladder is exhausted (the reference
+  // then draws std::random_device seeds: parity is undefined from there on).
+  static bool runNR(T seed1, T seed2, T seed3, T *fw, T *fw_2, T *fw_3, const Parameters &p1,
+                    const Parameters &p2, const Parameters &p3) {
+    const double TOLERANCE = 1e-8, seedMax = 1e33;
+    int max_iterations = 250;
+    double tol1 = fmax(fabs(TOLERANCE * (*fw)) * 0.0001, TOLERANCE);
+    double tol2 = fmax(fabs(TOLERANCE * (*fw_2)) * 0.0001, TOLERANCE);
+    double tol3 = fmax(fabs(TOLERANCE * (*fw_3)) * 0.0001, TOLERANCE);
+    double _seed1 = seed1, _seed2 = seed2, _seed3 = seed3;
+    for (int i = 0; i < 15; ++i) {
+      if (newton_raphson(_seed1, _seed2, _seed3, p1, p2, p3, fw, fw_2, fw_3, tol1, tol2, tol3,
+                         max_iterations))
+        return true;
+      switch (i) {
+        case 0: _seed1 = seed1 * seedMax; max_iterations = 600; break;
+        case 1: _seed1 = seed1; _seed2 = seed2 * seedMax; break;
+        case 2: _seed2 = seed2; _seed3 = seed3 * seedMax; break;
+        case 3: _seed3 = seed3; _seed1 = -seed1 * seedMax; break;
+        case 4: _seed1 = seed1; _seed2 = -seed2 * seedMax; break;
+        case 5: _seed2 = seed2; _seed3 = -seed3 * seedMax; break;
+        case 6: _seed1 = seed1 * seedMax; _seed2 = seed2 * seedMax; _seed3 = seed3; break;
+        case 7: _seed1 = seed1 * seedMax; _seed2 = seed2; _seed3 = seed3 * seedMax; break;
+        case 8: _seed1 = seed1; _seed2 = seed2 * seedMax; _seed3 = seed3 * seedMax; break;
+        case 9: _seed1 = -seed1 * seedMax; _seed2 = -seed2 * seedMax; _seed3 = seed3; break;
+        case 10: _seed1 = -seed1 * seedMax; _seed2 = seed2; _seed3 = -seed3 * seedMax; break;
+        case 11: _seed1 = seed1; _seed2 = -seed2 * seedMax; _seed3 = -seed3 * seedMax; break;
+        case 12: _seed1 = seed1 * seedMax; _seed2 = seed2 * seedMax; _seed3 = seed3 * seedMax; break;
+        case 13: _seed1 = -seed1 * seedMax; _seed2 = -seed2 * seedMax; _seed3 = -seed3 * seedMax; break;
+        default: return false;
+      }
+    }
+    return false;
+  }
+
+  // calc_nonlinear_u, src/step_generic.cpp:546-553 (upstream form, without the fork's cout/sleep)
+  static inline T calc_nonlinear_u(const T Dsqr, const T Di, const T chi1inv, const T chi2,
+                                   const T chi3) {
+    T c2 = Di * chi2 * (chi1inv * chi1inv);
+    T c3 = Dsqr * chi3 * (chi1inv * chi1inv * chi1inv);
+    return (1 + c2 + 2 * c3) / (1 + 2 * c2 + 3 * c3);
+  }
+
+  long nr_failures;
+
+  // step_update_EDHB, src/step_generic.cpp:576-906
+  int step_update_EDHB(T *f, int fc, const Grid &gr, const int is[3], const int ie[3], const T *g,
+                       const T *g1, const T *g2, const T *u, const T *u1, const T *u2, ptrdiff_t s,
+                       ptrdiff_t s1, ptrdiff_t s2, const T *chi2, const T *chi3, T *fw, int dsigw,
+                       const T *sigw, const T *kapw) {
+    if (!f) return MEEPCU_OK;
+    if ((!g1 && g2) || (g1 && g2 && !u1 && u2)) { // :590-594
+      std::swap(g1, g2);
+      std::swap(u1, u2);
+      std::swap(s1, s2);
+    }
+    if (!u1 && u2) return fail(MEEPCU_EINVAL, "bug - didn't swap off-diagonal terms!?");
+    const bool pade = cfg.nl_mode == MEEPCU_NL_UPSTREAM_PADE;
+    if ((u1 || chi3) && !u)
+      return fail(MEEPCU_EINVAL, "chi1inv diagonal missing where the reference dereferences it");
+    Loop L(gr, is, ie);
+#define OFFDIAG(u, g, sx)                                                                          \
+  (0.25 * ((g[i] + g[i - sx]) * u[i] + (g[i + s] + g[(i + s) - sx]) * u[i + s]))
+
+    if (dsigw != MEEPCU_NO_DIRECTION) { // PML case :603-727
+      if (!fw) return fail(MEEPCU_ESTATE, "f_w not allocated (update_eh.cpp:212-216)");
+      KIdx KW(gr, dsigw, is);
+#pragma omp parallel for collapse(2)
+      OLOOP(L, i) {
+        const int kw = KW.at(loop_i1, loop_i2, loop_i3);
+        T fwprev = fw[i], kapwkw = kapw[kw], sigwkw = sigw[kw];
+        if (!pade) { // fork: every branch is fw = g*u (or g), :626-725
+          if (u)
+            fw[i] = (g[i] * u[i]);
+          else
+            fw[i] = g[i];
+        }
+        else { // upstream formulas the fork commented out
+          if (u1 && u2) {
+            T gs = g[i], us = u[i];
+            if (chi3) { // :609-621
+              T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
+              T g2s = g2[i] + g2[i + s] + g2[i - s2] + g2[i + (s - s2)];
+              fw[i] = (gs * us + OFFDIAG(u1, g1, s1) + OFFDIAG(u2, g2, s2)) *
+                      calc_nonlinear_u(gs * gs + 0.0625 * (g1s * g1s + g2s * g2s), gs, us, chi2[i],
+                                       chi3[i]);
+            }
+            else // :632
+              fw[i] = (gs * us + OFFDIAG(u1, g1, s1) + OFFDIAG(u2, g2, s2));
+          }
+          else if (u1) {
+            T gs = g[i], us = u[i];
+            if (chi3) { // :646-647
+              T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
+              fw[i] = (gs * us + OFFDIAG(u1, g1, s1)) *
+                      calc_nonlinear_u(gs * gs + 0.0625 * (g1s * g1s), gs, us, chi2[i], chi3[i]);
+            }
+            else // :659
+              fw[i] = (gs * us + OFFDIAG(u1, g1, s1));
+          }
+          else if (chi3) { // :668-705
+            T gs = g[i], us = u[i];
+            if (g1 && g2) {
+              T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
+              T g2s = g2[i] + g2[i + s] + g2[i - s2] + g2[i + (s - s2)];
+              fw[i] = (gs * us) * calc_nonlinear_u(gs * gs + 0.0625 * (g1s * g1s + g2s * g2s), gs,
+                                                   us, chi2[i], chi3[i]);
+            }
+            else if (g1) {
+              T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
+              fw[i] = (gs * us) *
+                      calc_nonlinear_u(gs * gs + 0.0625 * (g1s * g1s), gs, us, chi2[i], chi3[i]);
+            }
+            else
+              fw[i] = (gs * us) * calc_nonlinear_u(gs * gs, gs, us, chi2[i], chi3[i]);
+          }
+          else if (u)
+            fw[i] = (g[i] * u[i]);
+          else
+            fw[i] = g[i];
+        }
+        f[i] += (kapwkw + sigwkw) * fw[i] - (kapwkw - sigwkw) * fwprev;
+      }
+      return MEEPCU_OK;
+    }
+
+    // ---- no PML :728-905 ----
+    if (!pade) {
+      if (u1 && u2 && chi3) { // the fork's Newton-Raphson branch :732-816
+        if (!chi2) return fail(MEEPCU_EINVAL, "chi2 missing in the NR branch (reference derefs it)");
+        if (!(fc == 0 || fc == 1 || fc == 4))
+          return fail(MEEPCU_EUNSUPPORTED, "NR branch reached for a non-E component (:808-811)");
+        long fails = 0;
+#pragma omp parallel for collapse(2) reduction(+ : fails)
+        OLOOP(L, i) {
+          T gs = g[i];
+          T gs_2 = (g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)]) * 0.25;
+          T gs_3 = (g2[i] + g2[i + s] + g2[i - s2] + g2[i + (s - s2)]) * 0.25;
+          T us = 1 / u[i];
+          T us_2 = us, us_3 = us;
+          T dummyF1 = 0.0, dummyF2 = 0.0;
+          T chi2new = chi2[i];
+          int zeroEpsCounter = 0;
+          if (u[i] == 0) zeroEpsCounter += 1;
+          if (u1[i] == 0) zeroEpsCounter += 1;
+          if (u2[i] == 0) zeroEpsCounter += 1;
+          if (chi2new == 0 || zeroEpsCounter > 1) { f[i] = (g[i] * u[i]); }
+          else {
+            bool ok = true;
+            if (fc == 0) {
+              Parameters p1 = {gs, us, 0.0, 0.0, 0.0, chi2new, 0.0, 0.0};
+              Parameters p2 = {gs_2, us_2, 0.0, 0.0, 0.0, 0.0, chi2new, 0.0};
+              Parameters p3 = {gs_3, us_3, 0.0, 0.0, 0.0, 0.0, 0.0, chi2new};
+              T seed1 = f[i], seed2 = gs_2 * u[i], seed3 = gs_3 * u[i];
+              ok = runNR(seed1, seed2, seed3, &f[i], &dummyF1, &dummyF2, p1, p2, p3);
+            }
+            else if (fc == 1) {
+              Parameters p1 = {gs_3, us_3, 0.0, 0.0, 0.0, chi2new, 0.0, 0.0};
+              Parameters p2 = {gs, us, 0.0, 0.0, 0.0, 0.0, chi2new, 0.0};
+              Parameters p3 = {gs_2, us_2, 0.0, 0.0, 0.0, 0.0, 0.0, chi2new};
+              T seed1 = gs_3 * u[i], seed2 = f[i], seed3 = gs_2 * u[i];
+              ok = runNR(seed1, seed2, seed3, &dummyF1, &f[i], &dummyF2, p1, p2, p3);
+            }
+            else {
+              Parameters p1 = {gs_2, us_2, 0.0, 0.0, 0.0, chi2new, 0.0, 0.0};
+              Parameters p2 = {gs_3, us_3, 0.0, 0.0, 0.0, 0.0, chi2new, 0.0};
+              Parameters p3 = {gs, us, 0.0, 0.0, 0.0, 0.0, 0.0, chi2new};
+              T seed1 = gs_2 * u[i], seed2 = gs_3 * u[i], seed3 = f[i];
+              ok = runNR(seed1, seed2, seed3, &dummyF1, &dummyF1, &f[i], p1, p2, p3);
+            }
+            if (!ok) fails += 1;
+          }
+        }
+        nr_failures += fails;
+        return MEEPCU_OK;
+      }
+      // every other fork branch is f = g*u, or f = g when u is NULL (:817-903)
+#pragma omp parallel for collapse(2)
+      OLOOP(L, i) {
+        if (u)
+          f[i] = (g[i] * u[i]);
+        else
+          f[i] = g[i];
+      }
+      return MEEPCU_OK;
+    }
+
+    // upstream (UPSTREAM_PADE) non-PML formulas, restored from the fork's comments
+#pragma omp parallel for collapse(2)
+    OLOOP(L, i) {
+      if (u1 && u2) {
+        T gs = g[i], us = u[i];
+        if (chi3) { // :768-773
+          T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
+          T g2s = g2[i] + g2[i + s] + g2[i - s2] + g2[i + (s - s2)];
+          f[i] = (gs * us + OFFDIAG(u1, g1, s1) + OFFDIAG(u2, g2, s2)) *
+                 calc_nonlinear_u(gs * gs + 0.0625 * (g1s * g1s + g2s * g2s), gs, us, chi2[i],
+                                  chi3[i]);
+        }
+        else // :823
+          f[i] = (gs * us + OFFDIAG(u1, g1, s1) + OFFDIAG(u2, g2, s2));
+      }
+      else if (u1) {
+        T gs = g[i], us = u[i];
+        if (chi3) { // :835-836
+          T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
+          f[i] = (gs * us + OFFDIAG(u1, g1, s1)) *
+                 calc_nonlinear_u(gs * gs + 0.0625 * (g1s * g1s), gs, us, chi2[i], chi3[i]);
+        }
+        else // :844
+          f[i] = (gs * us + OFFDIAG(u1, g1, s1));
+      }
+      else if (chi3) {
+        T gs = g[i], us = u[i];
+        if (g1 && g2) { // :862-863
+          T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
+          T g2s = g2[i] + g2[i + s] + g2[i - s2] + g2[i + (s - s2)];
+          f[i] = (gs * us) * calc_nonlinear_u(gs * gs + 0.0625 * (g1s * g1s + g2s * g2s), gs, us,
+                                              chi2[i], chi3[i]);
+        }
+        else if (g1) { // :873-874
+          T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
+          f[i] = (gs * us) *
+                 calc_nonlinear_u(gs * gs + 0.0625 * (g1s * g1s), gs, us, chi2[i], chi3[i]);
+        }
+        else // :884
+          f[i] = (gs * us) * calc_nonlinear_u(gs * gs, gs, us, chi2[i], chi3[i]);
+      }
+      else if (u)
+        f[i] = (g[i] * u[i]);
+      else
+        f[i] = g[i];
+    }
+#undef OFFDIAG
+    return MEEPCU_OK;
+  }
+
+  // fields_chunk::update_eh, src/update_eh.cpp:67-363
+  int update_eh(int ft, const meepcu_src_sample *smp) {
+    const int ft2 = ft == MEEPCU_E_STUFF ? MEEPCU_D_STUFF : MEEPCU_B_STUFF;
+    for (size_t ic = 0; ic < chunks.size(); ++ic) {
+      Chunk<T> &ch = chunks[ic];
+      const Grid &g = ch.g;
+      bool have_int_sources = false; // :71-79
+      for (size_t is = 0; is < ch.sources[ft2].size(); ++is)
+        if (ch.sources[ft2][is].is_integrated) have_int_sources = true;
+
+      T *fmp[MEEPCU_NUM_COMPONENTS][2];
+      memset(fmp, 0, sizeof fmp);
+      for (int ec = first_comp(ft); ec < first_comp(ft) + 5; ++ec) { // :84-105
+        const int dc = dir_comp(first_comp(ft2), comp_dir(ec));
+        for (int cmp = 0; cmp < 2; ++cmp) {
+          bool need_fmp = false;
+          if (ch.F(ec, cmp)) {
+            need_fmp = have_int_sources;
+            for (size_t ip = 0; ip < ch.pol[ft].size() && !need_fmp; ++ip)
+              need_fmp = need_fmp || ch.pol[ft][ip].d.P[ec][cmp] != NULL; // needs_P
+          }
+          if (need_fmp) {
+            ch.fmp_store[dc][cmp].resize(g.ntot);
+            fmp[dc][cmp] = ch.fmp_store[dc][cmp].data();
+          }
+        }
+      }
+      bool have_f_minus_p = false; // :106-112
+      for (int dc = first_comp(ft2); dc < first_comp(ft2) + 5; ++dc)
+        if (fmp[dc][0]) have_f_minus_p = true;
+
+      for (int ec = first_comp(ft); ec < first_comp(ft) + 5; ++ec) // :122-128
+        if (ch.F(ec, 0)) {
+          const int dc = dir_comp(first_comp(ft2), comp_dir(ec));
+          for (int cmp = 0; cmp < 2; ++cmp)
+            if (fmp[dc][cmp]) memcpy(fmp[dc][cmp], ch.F(dc, cmp), sizeof(T) * g.ntot);
+        }
+      for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip) { // :130-131 -> subtract_P :264-281
+        const meepcu_susceptibility_desc &sd = ch.pol[ft][ip].d;
+        for (int ec = first_comp(ft); ec < first_comp(ft) + 5; ++ec)
+          for (int cmp = 0; cmp < 2; ++cmp)
+            if (sd.P[ec][cmp]) {
+              const int dc = dir_comp(first_comp(ft2), comp_dir(ec));
+              if (fmp[dc][cmp]) {
+                const T *p = (const T *)sd.P[ec][cmp];
+                T *q = fmp[dc][cmp];
+                for (size_t i = 0; i < g.ntot; ++i) q[i] -= p[i];
+              }
+            }
+      }
+      if (have_f_minus_p) { // :136-146
+        for (size_t is = 0; is < ch.sources[ft2].size(); ++is) {
+          const SrcVol &sv = ch.sources[ft2][is];
+          if (sv.is_integrated && ch.F(sv.c, 0) && ft == comp_type(sv.c)) {
+            const int c = dir_comp(first_comp(ft2), comp_dir(sv.c));
+            const double *dp = ft == MEEPCU_E_STUFF ? smp[sv.src_time_id].dipole_E
+                                                    : smp[sv.src_time_id].dipole_H;
+            const std::complex<double> dipole(dp[0], dp[1]);
+            for (size_t j = 0; j < sv.index.size(); ++j) {
+              const std::complex<double> A = sv.amp[j] * dipole;
+              for (int cmp = 0; cmp < 2 - cfg.is_real; ++cmp)
+                fmp[c][cmp][sv.index[j]] -= (cmp) ? imag(A) : real(A);
+            }
+          }
+        }
+      }
+      const T *dmp[MEEPCU_NUM_COMPONENTS][2]; // :151-154
+      for (int dc = first_comp(ft2); dc < first_comp(ft2) + 5; ++dc)
+        for (int cmp = 0; cmp < 2; ++cmp) dmp[dc][cmp] = fmp[dc][cmp] ? fmp[dc][cmp] : ch.F(dc, cmp);
+
+      for (int cmp = 0; cmp < 2 - cfg.is_real; ++cmp) // :167-283
+        for (int ec = first_comp(ft); ec < first_comp(ft) + 5; ++ec) {
+          if (!ch.F(ec, cmp)) continue;
+          const int dc = dir_comp(first_comp(ft2), comp_dir(ec));
+          const int d_ec = comp_dir(ec);
+          if (d_ec >= MEEPCU_R) continue;
+          const int sgn = ft == MEEPCU_H_STUFF ? -1 : +1;
+          const ptrdiff_t s_ec = g.stride[d_ec] * sgn;
+          const int d_1 = cycle_dir(d_ec, 1);
+          const int dc_1 = dir_comp(dc, d_1);
+          const ptrdiff_t s_1 = g.stride[d_1] * sgn;
+          const int d_2 = cycle_dir(d_ec, 2);
+          const int dc_2 = dir_comp(dc, d_2);
+          const ptrdiff_t s_2 = g.stride[d_2] * sgn;
+          const int dsigw = ch.d.sigsize[d_ec] > 1 ? d_ec : MEEPCU_NO_DIRECTION;
+          if (ch.F(ec, cmp) == ch.F(dc, cmp)) {
+            if (ch.d.chi1inv[ec][d_ec] || have_f_minus_p || dsigw != MEEPCU_NO_DIRECTION)
+              return fail(MEEPCU_ESTATE, "H aliases B where update_eh.cpp:204-209 would split them");
+            continue; // :237
+          }
+          int is[3], ie[3];
+          for (int d = 0; d < 3; ++d) {
+            is[d] = g.io[d] + 2 - g.yee_shift(ec, d);
+            ie[d] = g.io[d] + 2 * g.num[d];
+          }
+          int rc = step_update_EDHB(
+              ch.F(ec, cmp), ec, g, is, ie, dmp[dc][cmp], dmp[dc_1][cmp], dmp[dc_2][cmp],
+              (const T *)ch.d.chi1inv[ec][d_ec],
+              dmp[dc_1][cmp] ? (const T *)ch.d.chi1inv[ec][d_1] : NULL,
+              dmp[dc_2][cmp] ? (const T *)ch.d.chi1inv[ec][d_2] : NULL, s_ec, s_1, s_2,
+              (const T *)ch.d.chi2[ec], (const T *)ch.d.chi3[ec], (T *)ch.d.f_w[ec][cmp], dsigw,
+              (const T *)ch.d.sig[dsigw], (const T *)ch.d.kap[dsigw]);
+          if (rc) return rc;
+        }
+    }
+    return MEEPCU_OK;
+  }
+
+  // fields_chunk::update_pols, src/update_pols.cpp:40-62 -> lorentzian_susceptibility::update_P,
+  // src/susceptibility.cpp:188-262
+  int update_pols(int ft) {
+    for (size_t ic = 0; ic < chunks.size(); ++ic) {
+      Chunk<T> &ch = chunks[ic];
+      const Grid &g = ch.g;
+      const T dt = (T)cfg.dt;
+      for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip) {
+        const meepcu_susceptibility_desc &sd = ch.pol[ft][ip].d;
+        const T pi = 3.141592653589793238462643383276; // src/meep.hpp:54 (const double pi)
+        const double dpi = 3.141592653589793238462643383276;
+        const T omega_0 = (T)sd.omega_0, gamma = (T)sd.gamma;
+        (void)pi;
+        // :191-194; omega_0/gamma are realnum members, pi is a double constant
+        const T omega2pi = 2 * dpi * omega_0, g2pi = gamma * 2 * dpi;
+        const T omega0dtsqr = omega2pi * omega2pi * dt * dt;
+        const T gamma1inv = 1 / (1 + g2pi * dt / 2), gamma1 = (1 - g2pi * dt / 2);
+        const T omega0dtsqr_denom = sd.no_omega_0_denominator ? 0 : omega0dtsqr;
+        for (int c = 0; c < 20; ++c)
+          for (int cmp = 0; cmp < 2; ++cmp) {
+            if (!sd.P[c][cmp]) continue;
+            const T *w = ch.d.f_w[c][cmp] ? (const T *)ch.d.f_w[c][cmp] : ch.F(c, cmp); // :43-44
+            const int d = comp_dir(c);
+            if (d >= MEEPCU_R) continue;
+            const T *s = (const T *)sd.sigma[c][d];
+            if (!(w && s)) continue;
+            T *p = (T *)sd.P[c][cmp], *pp = (T *)sd.P_prev[c][cmp];
+            const int sgn = is_magnetic(c) ? -1 : +1;
+            const ptrdiff_t is_ = g.stride[d] * sgn;
+            int d1 = cycle_dir(d, 1), d2 = cycle_dir(d, 2);
+            int c1 = dir_comp(c, d1), c2 = dir_comp(c, d2);
+            ptrdiff_t is1 = g.stride[d1] * sgn, is2 = g.stride[d2] * sgn;
+            const T *w1 = ch.d.f_w[c1][cmp] ? (const T *)ch.d.f_w[c1][cmp] : ch.F(c1, cmp);
+            const T *s1 = w1 ? (const T *)sd.sigma[c][d1] : NULL;
+            const T *w2 = ch.d.f_w[c2][cmp] ? (const T *)ch.d.f_w[c2][cmp] : ch.F(c2, cmp);
+            const T *s2 = w2 ? (const T *)sd.sigma[c][d2] : NULL;
+            if (s2 && !s1) {
+              std::swap(d1, d2);
+              std::swap(c1, c2);
+              std::swap(is1, is2);
+              std::swap(w1, w2);
+              std::swap(s1, s2);
+            }
+            int is[3], ie[3]; // PLOOP_OVER_VOL_OWNED: little_owned_corner(c) == corner0 (no Dcyl)
+            for (int dd = 0; dd < 3; ++dd) {
+              is[dd] = g.io[dd] + 2 - g.yee_shift(c, dd);
+              ie[dd] = g.io[dd] + 2 * g.num[dd];
+            }
+            Loop L(g, is, ie);
+#define POFFDIAG(u, g, sx, s)                                                                      \
+  (0.25 * ((g[i] + g[i - sx]) * u[i] + (g[i + s] + g[(i + s) - sx]) * u[i + s]))
+            if (s1 && s2) { // :225-241
+#pragma omp parallel for collapse(2)
+              OLOOP(L, i) {
+                if (s[i] != 0) {
+                  T pcur = p[i];
+                  p[i] = gamma1inv * (pcur * (2 - omega0dtsqr_denom) - gamma1 * pp[i] +
+                                      omega0dtsqr * (s[i] * w[i] + POFFDIAG(s1, w1, is1, is_) +
+                                                     POFFDIAG(s2, w2, is2, is_)));
+                  pp[i] = pcur;
+                }
+              }
+            }
+            else if (s1) { // :242-251
+#pragma omp parallel for collapse(2)
+              OLOOP(L, i) {
+                if (s[i] != 0) {
+                  T pcur = p[i];
+                  p[i] = gamma1inv * (pcur * (2 - omega0dtsqr_denom) - gamma1 * pp[i] +
+                                      omega0dtsqr * (s[i] * w[i] + POFFDIAG(s1, w1, is1, is_)));
+                  pp[i] = pcur;
+                }
+              }
+            }
+            else { // :252-259
+#pragma omp parallel for collapse(2)
+              OLOOP(L, i) {
+                T pcur = p[i];
+                p[i] = gamma1inv * (pcur * (2 - omega0dtsqr_denom) - gamma1 * pp[i] +
+                                    omega0dtsqr * (s[i] * w[i]));
+                pp[i] = pcur;
+              }
+            }
+#undef POFFDIAG
+          }
+      }
+    }
+    return MEEPCU_OK;
+  }
+
+  // fields::update_dfts / dft_chunk::update_dft, src/dft.cpp:249-307
+  void update_dfts() {
+    const double timeE = t * cfg.dt, timeH = t * cfg.dt - 0.5 * cfg.dt;
+    for (size_t ic = 0; ic < chunks.size(); ++ic) {
+      Chunk<T> &ch = chunks[ic];
+      const Grid &g = ch.g;
+      for (size_t id = ch.dfts.size(); id-- > 0;) { // newest first, like the linked list
+        Dft<T> &D = ch.dfts[id];
+        const meepcu_dft_desc &d = D.d;
+        if ((t % d.decimation_factor) != 0) continue;
+        const int c = d.c;
+        if (!ch.F(c, 0)) continue;
+        const double time = (is_magnetic(c) || is_B(c)) ? timeH : timeE;
+        const int Nomega = d.Nomega;
+        std::vector<std::complex<T> > dft_phase(Nomega);
+        const std::complex<double> scale(d.scale[0], d.scale[1]);
+        for (int i = 0; i < Nomega; ++i) {
+          std::complex<double> ph = std::polar(1.0, D.omega[i] * time) * scale;
+          dft_phase[i] = std::complex<T>((T)ph.real(), (T)ph.imag());
+        }
+        std::complex<T> *dft = D.dft ? D.dft : D.own.data();
+        const int numcmp = ch.F(c, 1) ? 2 : 1;
+        const T *f0 = ch.F(c, 0), *f1 = ch.F(c, 1);
+        Loop L(g, d.is, d.ie);
+        const ptrdiff_t avg1 = d.avg1, avg2 = d.avg2;
+        OLOOP(L, idx) {
+          size_t idx_dft = (loop_i1 * L.n[1] + loop_i2) * L.n[2] + loop_i3; // IVEC_LOOP_COUNTER
+          double w;
+          if (d.include_dV_and_interp_weights) {
+            // IVEC_LOOP_WEIGHT(s0,s1,e0,e1, dV0 + dV1*loop_i2), src/meep/vec.hpp:372-383
+            const ptrdiff_t li[3] = {loop_i1, loop_i2, loop_i3};
+            double w1[3];
+            for (int k = 0; k < 3; ++k) {
+              const ptrdiff_t i = li[k], n = L.n[k];
+              const int dir = L.dir[k];
+              w1[k] = (i > 1 && i < n - 2)
+                          ? 1.0
+                          : (i == 0 ? d.s0[dir]
+                                    : (i == 1       ? d.s1[dir]
+                                       : i == n - 1 ? d.e0[dir]
+                                                    : (i == n - 2 ? d.e1[dir] : 1.0)));
+            }
+            w = (w1[2] * (w1[1] * ((d.dV0 + d.dV1 * loop_i2) * w1[0])));
+            if (d.sqrt_dV_and_interp_weights) w = sqrt(w);
+          }
+          else
+            w = 1.0;
+          T f[2];
+          for (int cmp = 0; cmp < numcmp; ++cmp) {
+            const T *ff = cmp ? f1 : f0;
+            if (avg2)
+              f[cmp] = (w * 0.25) * (ff[idx] + ff[idx + avg1] + ff[idx + avg2] + ff[idx + (avg1 + avg2)]);
+            else if (avg1)
+              f[cmp] = (w * 0.5) * (ff[idx] + ff[idx + avg1]);
+            else
+              f[cmp] = w * ff[idx];
+          }
+          if (numcmp == 2) {
+            std::complex<T> fc(f[0], f[1]);
+            for (int i = 0; i < Nomega; ++i) dft[Nomega * idx_dft + i] += dft_phase[i] * fc;
+          }
+          else {
+            T fr = f[0];
+            for (int i = 0; i < Nomega; ++i)
+              dft[Nomega * idx_dft + i] +=
+                  std::complex<T>(fr * dft_phase[i].real(), fr * dft_phase[i].imag());
+          }
+        }
+      }
+    }
+  }
+
+  // fields::step, src/step.cpp:35-140
+  int step(int nsteps, int nsrc, const meepcu_src_sample *smp) {
+    int rc;
+    for (size_t ic = 0; ic < chunks.size(); ++ic) // validate src_time ids once
+      for (int ft = 0; ft < 4; ++ft)
+        for (size_t is = 0; is < chunks[ic].sources[ft].size(); ++is)
+          if (chunks[ic].sources[ft][is].src_time_id >= nsrc || (nsrc > 0 && !smp))
+            return fail(MEEPCU_EINVAL, "source refers to src_time %d but only %d samples given",
+                        chunks[ic].sources[ft][is].src_time_id, nsrc);
+    for (int s = 0; s < nsteps; ++s) {
+      const meepcu_src_sample *sm = smp ? smp + (size_t)s * nsrc : NULL;
+      if ((rc = step_db(MEEPCU_B_STUFF))) return rc;
+      step_source(MEEPCU_B_STUFF, sm);
+      step_boundaries(MEEPCU_B_STUFF);
+      if ((rc = update_eh(MEEPCU_H_STUFF, sm))) return rc;
+      step_boundaries(MEEPCU_WH_STUFF);
+      if ((rc = update_pols(MEEPCU_H_STUFF))) return rc;
+      step_boundaries(MEEPCU_PH_STUFF);
+      step_boundaries(MEEPCU_H_STUFF);
+      if ((rc = step_db(MEEPCU_D_STUFF))) return rc;
+      step_source(MEEPCU_D_STUFF, sm);
+      step_boundaries(MEEPCU_D_STUFF);
+      if ((rc = update_eh(MEEPCU_E_STUFF, sm))) return rc;
+      step_boundaries(MEEPCU_WE_STUFF);
+      if ((rc = update_pols(MEEPCU_E_STUFF))) return rc;
+      step_boundaries(MEEPCU_PE_STUFF);
+      step_boundaries(MEEPCU_E_STUFF);
+      t += 1;
+      update_dfts();
+    }
+    return MEEPCU_OK;
+  }
+
+  int check_finite(int *ok) {
+    *ok = 1;
+    for (size_t ic = 0; ic < chunks.size(); ++ic)
+      for (int c = 0; c < 20; ++c)
+        for (int cmp = 0; cmp < 2; ++cmp) {
+          const T *f = chunks[ic].F(c, cmp);
+          if (!f) continue;
+          for (size_t i = 0; i < chunks[ic].g.ntot; ++i)
+            if (!std::isfinite(f[i])) {
+              *ok = 0;
+              return MEEPCU_OK;
+            }
+        }
+    return MEEPCU_OK;
+  }
+  int read_value(const void *p, double *out) {
+    *out = (double)*(const T *)p;
+    return MEEPCU_OK;
+  }
+  Impl() : nr_failures(0) {}
+};
+
+} // namespace
+
+struct meepcu_ctx {
+  CtxBase *impl;
+};
+
+extern "C" {
+
+const char *meepcu_last_error(void) { return g_err.c_str(); }
+const char *meepcu_backend(void) { return "oracle-cpu"; }
+int meepcu_abi_version(void) { return MEEPCU_ABI_VERSION; }
+
+int meepcu_create(const meepcu_config *cfg, meepcu_ctx **out) {
+  if (!cfg || !out) return fail(MEEPCU_EINVAL, "null argument");
+  if (cfg->abi_version != MEEPCU_ABI_VERSION) return fail(MEEPCU_EINVAL, "ABI version mismatch");
+  if (cfg->dim == MEEPCU_Dcyl) return fail(MEEPCU_EUNSUPPORTED, "cylindrical coordinates");
+  if (cfg->dim < 0 || cfg->dim > 3) return fail(MEEPCU_EINVAL, "bad dim");
+  CtxBase *impl;
+  if (cfg->realnum_bytes == 8)
+    impl = new Impl<double>();
+  else if (cfg->realnum_bytes == 4)
+    impl = new Impl<float>();
+  else
+    return fail(MEEPCU_EINVAL, "realnum_bytes must be 4 or 8");
+  impl->cfg = *cfg;
+  impl->t = cfg->t;
+  impl->finalized = false;
+  *out = new meepcu_ctx;
+  (*out)->impl = impl;
+  return MEEPCU_OK;
+}
+int meepcu_destroy(meepcu_ctx *ctx) {
+  if (!ctx) return MEEPCU_OK;
+  delete ctx->impl;
+  delete ctx;
+  return MEEPCU_OK;
+}
+#define CHECK_CTX                                                                                  \
+  if (!ctx || !ctx->impl) return fail(MEEPCU_EINVAL, "null context")
+int meepcu_add_chunk(meepcu_ctx *ctx, const meepcu_chunk_desc *d, int *id) {
+  CHECK_CTX;
+  return ctx->impl->add_chunk(d, id);
+}
+int meepcu_add_susceptibility(meepcu_ctx *ctx, int chunk, const meepcu_susceptibility_desc *d) {
+  CHECK_CTX;
+  return ctx->impl->add_susc(chunk, d);
+}
+int meepcu_add_source(meepcu_ctx *ctx, int chunk, const meepcu_source_desc *d) {
+  CHECK_CTX;
+  return ctx->impl->add_source(chunk, d);
+}
+int meepcu_add_dft(meepcu_ctx *ctx, int chunk, const meepcu_dft_desc *d, int *id) {
+  CHECK_CTX;
+  return ctx->impl->add_dft(chunk, d, id);
+}
+int meepcu_set_metal(meepcu_ctx *ctx, int ft, size_t n, void *const *ptrs) {
+  CHECK_CTX;
+  return ctx->impl->set_metal(ft, n, ptrs);
+}
+int meepcu_add_connections(meepcu_ctx *ctx, int ft, int kind, size_t n, void *const *dst,
+                           const void *const *src, const void *phases) {
+  CHECK_CTX;
+  return ctx->impl->add_conn(ft, kind, n, dst, src, phases);
+}
+int meepcu_add_remote_send(meepcu_ctx *, int, int, int, size_t, const void *const *) {
+  return fail(MEEPCU_EUNSUPPORTED, "the oracle is single-process");
+}
+int meepcu_add_remote_recv(meepcu_ctx *, int, int, int, size_t, void *const *, const void *) {
+  return fail(MEEPCU_EUNSUPPORTED, "the oracle is single-process");
+}
+int meepcu_comm_unique_id(void *) { return fail(MEEPCU_EUNSUPPORTED, "the oracle is single-process"); }
+int meepcu_comm_init(meepcu_ctx *, int, int, const void *) {
+  return fail(MEEPCU_EUNSUPPORTED, "the oracle is single-process");
+}
+int meepcu_finalize(meepcu_ctx *ctx) {
+  CHECK_CTX;
+  ctx->impl->finalized = true;
+  return MEEPCU_OK;
+}
+int meepcu_step(meepcu_ctx *ctx, int nsteps, int nsrc, const meepcu_src_sample *smp) {
+  CHECK_CTX;
+  if (!ctx->impl->finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
+  return ctx->impl->step(nsteps, nsrc, smp);
+}
+int meepcu_sync_to_host(meepcu_ctx *ctx) {
+  CHECK_CTX;
+  return MEEPCU_OK; // in place
+}
+int meepcu_sync_from_host(meepcu_ctx *ctx) {
+  CHECK_CTX;
+  return MEEPCU_OK;
+}
+int meepcu_get_time(meepcu_ctx *ctx, int *t) {
+  CHECK_CTX;
+  *t = ctx->impl->t;
+  return MEEPCU_OK;
+}
+int meepcu_set_time(meepcu_ctx *ctx, int t) {
+  CHECK_CTX;
+  ctx->impl->t = t;
+  return MEEPCU_OK;
+}
+int meepcu_check_finite(meepcu_ctx *ctx, int *ok) {
+  CHECK_CTX;
+  return ctx->impl->check_finite(ok);
+}
+int meepcu_read_value(meepcu_ctx *ctx, const void *p, double *out) {
+  CHECK_CTX;
+  return ctx->impl->read_value(p, out);
+}
+int meepcu_get_timers(meepcu_ctx *ctx, double out[22]) {
+  CHECK_CTX;
+  for (int i = 0; i < 22; ++i) out[i] = 0;
+  return MEEPCU_OK;
+}
+int meepcu_get_stats(meepcu_ctx *ctx, meepcu_stats *out) {
+  CHECK_CTX;
+  memset(out, 0, sizeof *out);
+  out->cells = ctx->impl->cells();
+  return MEEPCU_OK;
+}
+}

@@ -1,0 +1,516 @@
+// ref_driver.cpp -- TEST INFRASTRUCTURE.  Links the UNMODIFIED reference core
+// (oracle/_ref/<flavour>/libmeep_ref.a, built from /root/reference/src by oracle/build_ref.sh)
+// with the reference-side shim (meep_nl_b200/shim/meepcu_shim.hpp) and drives named test
+// problems through the reference's own public C++ API, in one of these modes:
+//
+//   --mode ref       step with the reference CPU code only (timing: the CPU baseline)
+//   --mode shim      build the problem twice; step twin A with the reference CPU code and
+//                    twin B through the C ABI of --lib (libmeepcuda.so or liboracle_meep.so);
+//                    sync back and compare EVERY array (fields, PML aux, P, DFT)
+//   --mode gpu       step through --lib only (timing of the drop-in path incl. attach)
+//   --record FILE    (with --mode shim) also write a replayable ABI trace + expected arrays
+//
+// Results are written as one JSON object to --json FILE (stdout carries the fork's debug
+// prints).
+#include "trace_recorder.hpp"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <math.h>
+#include <omp.h>
+
+using namespace meep;
+using std::complex;
+
+// ------------------------------------------------------------------------------------------
+// test problems
+// ------------------------------------------------------------------------------------------
+static double one(const vec &) { return 1.0; }
+static double g_slab_lo, g_slab_hi, g_slab_eps;
+static double wvg_eps(const vec &p) { return fabs(p.y() - 4.0) < 0.5 ? 12.0 : 1.0; }
+static double rods(const vec &r) { // tests/known_results.cpp:29-41
+  vec p = r;
+  while (p.x() < -0.5) p.set_direction(X, p.x() + 1.0);
+  while (p.x() > 0.5) p.set_direction(X, p.x() - 1.0);
+  while (p.y() < -0.5) p.set_direction(Y, p.y() + 1.0);
+  while (p.y() > 0.5) p.set_direction(Y, p.y() - 1.0);
+  if (p.x() * p.x() + p.y() * p.y() < 0.3) return 12.0;
+  return 1.0;
+}
+static double sigma763(const vec &) { return 7.63; }
+static double slab_eps_z(const vec &p) { return (p.z() > g_slab_lo && p.z() < g_slab_hi) ? g_slab_eps : 1.0; }
+static double ring_eps(const vec &p);
+static double ring_sigma(const vec &p);
+static double g_ring_c[3], g_ring_r0, g_ring_r1, g_ring_h;
+static double ring_mask(const vec &p) {
+  double dx = p.x() - g_ring_c[0], dy = p.y() - g_ring_c[1], dz = p.z() - g_ring_c[2];
+  double r = sqrt(dx * dx + dy * dy);
+  return (r >= g_ring_r0 && r <= g_ring_r1 && fabs(dz) <= 0.5 * g_ring_h) ? 1.0 : 0.0;
+}
+static double ring_eps(const vec &p) { return ring_mask(p) ? 11.56 : 1.0; }
+static double ring_sigma(const vec &p) { return ring_mask(p); }
+
+// SURVEY Appendix A "nr3d": eps 2.25 everywhere, off-diagonal chi1inv rows made non-trivial
+// (1e-30) so that the fork's NR branch is selected, chi2 = given, chi3 = 1 (flag)
+class nr_material : public material_function {
+public:
+  double chi2v;
+  bool slab; // restrict chi2 to a z slab
+  explicit nr_material(double c2, bool slab_ = false) : chi2v(c2), slab(slab_) {}
+  virtual double chi1p1(field_type ft, const vec &r) {
+    (void)r;
+    return ft == E_stuff ? 2.25 : 1.0;
+  }
+  virtual void eff_chi1inv_row(component c, double row[3], const volume &v, double tol, int maxeval) {
+    (void)v; (void)tol; (void)maxeval;
+    if (is_electric(c)) {
+      row[0] = row[1] = row[2] = 1e-30;
+      row[component_direction(c) % 3] = 1 / 2.25;
+    }
+    else {
+      row[0] = row[1] = row[2] = 0;
+      row[component_direction(c) % 3] = 1;
+    }
+  }
+  virtual bool has_chi3(component c) { return is_electric(c); }
+  virtual double chi3(component c, const vec &r) { (void)c; (void)r; return 1.0; }
+  virtual bool has_chi2(component c) { return is_electric(c); }
+  virtual double chi2(component c, const vec &r) {
+    (void)c;
+    if (slab && !(r.z() > g_slab_lo && r.z() < g_slab_hi)) return 0.0;
+    return chi2v;
+  }
+};
+
+// diagonal-eps Kerr medium (tests/harmonics.cpp physics) for the UPSTREAM_PADE mode
+class kerr_material : public material_function {
+public:
+  double eps_, chi2v, chi3v;
+  kerr_material(double e, double c2, double c3) : eps_(e), chi2v(c2), chi3v(c3) {}
+  virtual double chi1p1(field_type ft, const vec &r) {
+    (void)r;
+    return ft == E_stuff ? eps_ : 1.0;
+  }
+  virtual bool has_chi3(component c) { return is_electric(c) && chi3v != 0; }
+  virtual double chi3(component c, const vec &r) { (void)c; (void)r; return chi3v; }
+  virtual bool has_chi2(component c) { return is_electric(c) && chi2v != 0; }
+  virtual double chi2(component c, const vec &r) { (void)c; (void)r; return chi2v; }
+};
+
+struct problem {
+  grid_volume gv;
+  structure *s;
+  fields *f;
+  material_function *mat;
+  std::vector<dft_flux> fluxes;
+  long cells;
+  problem() : s(0), f(0), mat(0), cells(0) {}
+  ~problem() {
+    delete f;
+    delete s;
+    delete mat;
+  }
+};
+
+static vec kvec_for(const grid_volume &gv) { // tests/known_results.cpp:97-103
+  switch (gv.dim) {
+    case D1: return vec(0.3);
+    case D2: return vec(0.3, 0.4);
+    case D3: return vec(0.3, 0.5, 0.8);
+    default: return veccyl(0.3, 0.2);
+  }
+}
+
+// name[:n[:param]]
+static problem *build(const std::string &spec, int nchunks) {
+  std::string name = spec;
+  int n = 0;
+  double param = 0;
+  size_t c1 = spec.find(':');
+  if (c1 != std::string::npos) {
+    name = spec.substr(0, c1);
+    n = atoi(spec.c_str() + c1 + 1);
+    size_t c2 = spec.find(':', c1 + 1);
+    if (c2 != std::string::npos) param = atof(spec.c_str() + c2 + 1);
+  }
+  const double a = 10.0;
+  const complex<double> kr_amp(0, -2 * pi * 0.2);
+  problem *p = new problem;
+  if (name == "vac3d") { // BASELINE config 2
+    if (!n) n = 32;
+    p->gv = vol3d(n / a, n / a, n / a, a);
+    p->s = new structure(p->gv, one, pml(1.0), identity(), nchunks);
+    p->f = new fields(p->s);
+    p->f->use_real_fields();
+    p->f->add_point_source(Ez, 0.15, 0.1, 0.0, 4.0, p->gv.center(), 1.0);
+  }
+  else if (name == "vac3d_cplx") {
+    if (!n) n = 24;
+    p->gv = vol3d(n / a, n / a, n / a, a);
+    p->s = new structure(p->gv, one, pml(0.5), identity(), nchunks);
+    p->f = new fields(p->s);
+    p->f->add_point_source(Ez, 0.15, 0.1, 0.0, 4.0, p->gv.center(), complex<double>(0.3, 1.0));
+    p->f->add_point_source(Hx, 0.25, 0.2, 0.0, 4.0, p->gv.center() + vec(0.2, 0.1, -0.1), 0.7);
+  }
+  else if (name == "wvg2d") { // BASELINE config 1
+    p->gv = vol2d(16, 8, a);
+    p->s = new structure(p->gv, wvg_eps, pml(1.0), identity(), nchunks, 0.5, false);
+    p->f = new fields(p->s);
+    p->f->use_real_fields();
+    gaussian_src_time src(0.15, 0.1);
+    p->f->add_point_source(Ez, src, vec(1.0, 4.0));
+  }
+  else if (name == "nr3d") { // BASELINE config 3a, fork Newton-Raphson chi2
+    if (!n) n = 16;
+    if (param == 0) param = 1e-2;
+    p->gv = vol3d(n / a, n / a, n / a, a);
+    p->mat = new nr_material(param);
+    p->s = new structure(p->gv, *p->mat, no_pml(), identity(), nchunks);
+    p->f = new fields(p->s);
+    p->f->use_real_fields();
+    vec c = p->gv.center();
+    p->f->add_point_source(Ez, 0.3, 0.2, 0.0, 4.0, c, 1.0);
+    p->f->add_point_source(Ex, 0.3, 0.2, 0.0, 4.0, c + vec(0.2, 0.1, 0), 1.0);
+    p->f->add_point_source(Ey, 0.3, 0.2, 0.0, 4.0, c + vec(0, 0.2, 0.1), 1.0);
+  }
+  else if (name == "nrslab3d") { // config 3a with PML and a chi2 slab in the middle third in z
+    if (!n) n = 30;
+    if (param == 0) param = 1e-2;
+    p->gv = vol3d(n / a, n / a, n / a, a);
+    g_slab_lo = n / a / 3;
+    g_slab_hi = 2 * n / a / 3;
+    p->mat = new nr_material(param, true);
+    p->s = new structure(p->gv, *p->mat, pml(0.5), identity(), nchunks);
+    p->f = new fields(p->s);
+    p->f->use_real_fields();
+    vec c = p->gv.center();
+    p->f->add_point_source(Ez, 0.3, 0.2, 0.0, 4.0, c, 1.0);
+    p->f->add_point_source(Ex, 0.3, 0.2, 0.0, 4.0, c + vec(0.2, 0.1, 0), 1.0);
+    p->f->add_point_source(Ey, 0.3, 0.2, 0.0, 4.0, c + vec(0, 0.2, 0.1), 1.0);
+  }
+  else if (name == "kerr3d") { // config 3b: diagonal eps + chi2/chi3 (Pade in UPSTREAM mode)
+    if (!n) n = 20;
+    if (param == 0) param = 1e-2;
+    p->gv = vol3d(n / a, n / a, n / a, a);
+    p->mat = new kerr_material(2.25, 0.5 * param, param);
+    p->s = new structure(p->gv, *p->mat, pml(0.5), identity(), nchunks);
+    p->f = new fields(p->s);
+    p->f->use_real_fields();
+    vec c = p->gv.center();
+    p->f->add_point_source(Ex, 1.0 / 3, 0.2, 0.0, 4.0, c, 5.0);
+    p->f->add_point_source(Ez, 0.3, 0.2, 0.0, 4.0, c + vec(0.1, 0.2, 0), 3.0);
+  }
+  else if (name == "kerr1d") { // tests/harmonics.cpp-like 1D Kerr
+    if (!n) n = 100;
+    if (param == 0) param = 1e-3;
+    p->gv = vol1d(n / a, a);
+    p->mat = new kerr_material(1.0, 0.0, param);
+    p->s = new structure(p->gv, *p->mat, pml(1.0), identity(), nchunks);
+    p->f = new fields(p->s);
+    p->f->use_real_fields();
+    p->f->add_point_source(Ex, 0.3, 0.1, 0.0, 4.0, vec(2.0), 1.0);
+  }
+  else if (name == "lorentz3d") { // BASELINE config 4 shape: Lorentzian ring + DFT flux planes
+    if (!n) n = 32;
+    p->gv = vol3d(n / a, n / a, n / a, a);
+    const double L = n / a;
+    g_ring_c[0] = g_ring_c[1] = g_ring_c[2] = L / 2;
+    g_ring_r0 = 0.15 * L;
+    g_ring_r1 = 0.30 * L;
+    g_ring_h = 0.2 * L;
+    p->s = new structure(p->gv, ring_eps, pml(0.1 * L > 1.0 ? 1.0 : 0.1 * L), identity(), nchunks,
+                         0.5, false);
+    p->s->add_susceptibility(ring_sigma, E_stuff, lorentzian_susceptibility(1.1, 1e-5));
+    p->f = new fields(p->s);
+    p->f->use_real_fields();
+    p->f->add_point_source(Ez, 0.15, 0.1, 0.0, 4.0, vec(L / 2 + 0.22 * L, L / 2, L / 2), 1.0);
+    int nf = param > 0 ? (int)param : 8;
+    const double lo = 0.15 * L, hi = 0.85 * L;
+    p->fluxes.push_back(p->f->add_dft_flux_plane(volume(vec(hi, lo, lo), vec(hi, hi, hi)), 0.1, 0.2, nf));
+    p->fluxes.push_back(p->f->add_dft_flux_plane(volume(vec(lo, hi, lo), vec(hi, hi, hi)), 0.1, 0.2, nf));
+    p->fluxes.push_back(p->f->add_dft_flux_plane(volume(vec(lo, lo, hi), vec(hi, hi, hi)), 0.1, 0.2, nf));
+    p->fluxes.push_back(p->f->add_dft_flux_plane(volume(vec(lo, lo, lo), vec(lo, hi, hi)), 0.1, 0.2, nf));
+  }
+  else if (name == "phc3d") { // BASELINE config 5 shape: slab, PML in z, Bloch-periodic x,y, fp32-able
+    if (!n) n = 16;
+    p->gv = vol3d(n / a, n / a, 1.5 * n / a, a);
+    g_slab_lo = 0.75 * n / a - 0.25;
+    g_slab_hi = 0.75 * n / a + 0.25;
+    g_slab_eps = 12.0;
+    p->s = new structure(p->gv, slab_eps_z, pml(0.4, Z), identity(), nchunks, 0.5, false);
+    p->f = new fields(p->s);
+    p->f->use_bloch(X, 0.0);
+    p->f->use_bloch(Y, 0.0);
+    p->f->use_real_fields();
+    p->f->add_point_source(Ey, 0.25, 0.2, 0.0, 4.0, p->gv.center(), 1.0);
+  }
+  // ---- the 13 problems of tests/known_results.cpp:155-169 -----------------------------------
+  else if (name == "kr_polariton1d") {
+    p->gv = volone(1.0, a);
+    p->s = new structure(p->gv, one, no_pml(), identity(), nchunks);
+    p->s->add_susceptibility(sigma763, E_stuff, lorentzian_susceptibility(0.3, 0.1));
+    p->f = new fields(p->s);
+    p->f->add_point_source(Ex, 0.2, 3.0, 0.0, 2.0, p->gv.center(), kr_amp);
+  }
+  else if (name == "kr_metal2d" || name == "kr_metal3d") {
+    p->gv = name == "kr_metal2d" ? voltwo(1.0, 1.0, a) : vol3d(1.0, 1.0, 1.0, a);
+    p->s = new structure(p->gv, one, no_pml(), identity(), nchunks);
+    p->f = new fields(p->s);
+    p->f->add_point_source(Ez, 0.2, 3.0, 0.0, 2.0, p->gv.center(), kr_amp);
+  }
+  else if (name == "kr_pml2d") {
+    p->gv = voltwo(3.0, 3.0, a);
+    p->s = new structure(p->gv, one, pml(1.0), identity(), nchunks);
+    p->f = new fields(p->s);
+    p->f->add_point_source(Ez, 0.2, 3.0, 0.0, 2.0, p->gv.center(), kr_amp);
+  }
+  else if (name == "kr_xper2d" || name == "kr_xper3d") {
+    p->gv = name == "kr_xper2d" ? voltwo(1.0, 1.0, a) : vol3d(1.0, 1.0, 1.0, a);
+    p->s = new structure(p->gv, one, no_pml(), identity(), nchunks);
+    p->f = new fields(p->s);
+    p->f->add_point_source(Ez, 0.2, 3.0, 0.0, 2.0, p->gv.center(), kr_amp);
+    p->f->use_bloch(X, 0.1);
+  }
+  else if (name == "kr_per2d_rods" || name == "kr_per2d" || name == "kr_per3d_rods" ||
+           name == "kr_per3d") {
+    bool d3 = name.find("3d") != std::string::npos, rd = name.find("rods") != std::string::npos;
+    p->gv = d3 ? vol3d(1.0, 1.0, 1.0, a) : voltwo(1.0, 3.0, a);
+    p->s = new structure(p->gv, rd ? rods : one, no_pml(), identity(), nchunks);
+    p->f = new fields(p->s);
+    p->f->add_point_source(Ez, 0.2, 3.0, 0.0, 2.0, p->gv.center(), kr_amp);
+    p->f->use_bloch(kvec_for(p->gv));
+  }
+  else if (name == "kr_xper_ypml2d" || name == "kr_xper_ypml3d") {
+    p->gv = name == "kr_xper_ypml2d" ? voltwo(1.0, 3.0, a) : vol3d(1.0, 3.0, 1.0, a);
+    p->s = new structure(p->gv, one, pml(1.0, Y), identity(), nchunks);
+    p->f = new fields(p->s);
+    p->f->add_point_source(Ez, 0.2, 3.0, 0.0, 2.0, p->gv.center(), kr_amp);
+    p->f->use_bloch(X, 0.1);
+  }
+  else {
+    fprintf(stderr, "unknown case %s\n", name.c_str());
+    exit(2);
+  }
+  p->cells = 1;
+  LOOP_OVER_DIRECTIONS(p->gv.dim, d) p->cells *= p->gv.num_direction(d);
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// every mutable array of a fields object, in a deterministic order
+// ------------------------------------------------------------------------------------------
+struct marray {
+  const void *p;
+  size_t nbytes;
+  std::string name;
+};
+static std::vector<marray> collect(fields &f) {
+  std::vector<marray> out;
+  char nm[128];
+  for (int i = 0; i < f.num_chunks; i++) {
+    fields_chunk *fc = f.chunks[i];
+    const size_t nb = fc->gv.ntot() * sizeof(realnum);
+    FOR_COMPONENTS(c) for (int cmp = 0; cmp < 2; ++cmp) {
+      if (fc->f[c][cmp] && !(is_magnetic(c) &&
+                             fc->f[c][cmp] == fc->f[direction_component(Bx, component_direction(c))][cmp])) {
+        snprintf(nm, sizeof nm, "chunk%d.f[%s][%d]", i, component_name(c), cmp);
+        out.push_back({fc->f[c][cmp], nb, nm});
+      }
+      if (fc->f_u[c][cmp]) {
+        snprintf(nm, sizeof nm, "chunk%d.f_u[%s][%d]", i, component_name(c), cmp);
+        out.push_back({fc->f_u[c][cmp], nb, nm});
+      }
+      if (fc->f_w[c][cmp]) {
+        snprintf(nm, sizeof nm, "chunk%d.f_w[%s][%d]", i, component_name(c), cmp);
+        out.push_back({fc->f_w[c][cmp], nb, nm});
+      }
+      if (fc->f_cond[c][cmp]) {
+        snprintf(nm, sizeof nm, "chunk%d.f_cond[%s][%d]", i, component_name(c), cmp);
+        out.push_back({fc->f_cond[c][cmp], nb, nm});
+      }
+    }
+    field_type ehs[2] = {E_stuff, H_stuff};
+    for (int k = 0; k < 2; ++k) {
+      int ip = 0;
+      for (polarization_state *p = fc->pol[ehs[k]]; p; p = p->next, ++ip) {
+        if (!p->data) continue;
+        FOR_COMPONENTS(c) for (int cmp = 0; cmp < 2; ++cmp) {
+          realnum *P = p->s->cinternal_notowned_ptr(0, c, cmp, 0, p->data);
+          if (!P) continue;
+          snprintf(nm, sizeof nm, "chunk%d.pol%d_%d.P[%s][%d]", i, k, ip, component_name(c), cmp);
+          out.push_back({P, nb, nm});
+          snprintf(nm, sizeof nm, "chunk%d.pol%d_%d.P_prev[%s][%d]", i, k, ip, component_name(c), cmp);
+          out.push_back({P + fc->gv.ntot(), nb, nm});
+        }
+      }
+    }
+    int id = 0;
+    for (dft_chunk *dc = fc->dft_chunks; dc; dc = dc->next_in_chunk, ++id) {
+      snprintf(nm, sizeof nm, "chunk%d.dft%d[%s]", i, id, component_name(dc->c));
+      out.push_back({dc->dft, dc->N * dc->omega.size() * sizeof(complex<realnum>), nm});
+    }
+  }
+  return out;
+}
+
+struct cmp_result {
+  size_t narrays, nmismatch_arrays, nelems, nmismatch_elems;
+  double max_abs, sum_d2, sum_r2;
+  std::string first_bad;
+};
+static cmp_result compare(const std::vector<marray> &A, const std::vector<marray> &B) {
+  cmp_result r = {0, 0, 0, 0, 0, 0, 0, ""};
+  if (A.size() != B.size()) {
+    r.first_bad = "array lists differ in length";
+    r.nmismatch_arrays = 1;
+    return r;
+  }
+  for (size_t k = 0; k < A.size(); ++k) {
+    const realnum *a = (const realnum *)A[k].p, *b = (const realnum *)B[k].p;
+    size_t n = A[k].nbytes / sizeof(realnum);
+    if (A[k].nbytes != B[k].nbytes || A[k].name != B[k].name) {
+      r.first_bad = "layout mismatch at " + A[k].name;
+      r.nmismatch_arrays++;
+      continue;
+    }
+    size_t bad = 0;
+    for (size_t i = 0; i < n; ++i) {
+      double d = (double)a[i] - (double)b[i];
+      if (memcmp(&a[i], &b[i], sizeof(realnum)) != 0 && !(a[i] == b[i])) bad++; // -0 == +0 ok
+      if (fabs(d) > r.max_abs) r.max_abs = fabs(d);
+      r.sum_d2 += d * d;
+      r.sum_r2 += (double)a[i] * (double)a[i];
+    }
+    r.narrays++;
+    r.nelems += n;
+    r.nmismatch_elems += bad;
+    if (bad) {
+      if (r.first_bad.empty()) r.first_bad = A[k].name;
+      r.nmismatch_arrays++;
+    }
+  }
+  return r;
+}
+
+static double probe_value(problem *p) {
+  component c = p->gv.dim == D1 ? Ex : Ez;
+  return real(p->f->get_field(c, p->gv.center()));
+}
+
+int main(int argc, char **argv) {
+  initialize mpi(argc, argv);
+  verbosity = 0;
+  std::string mode = "ref", cas = "vac3d:32", lib, json, record;
+  int steps = 20, warmup = 0, nchunks = 0, nl_mode = MEEPCU_NL_FORK_LITERAL, device = 0, batch = 0;
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    if (a == "--mode") mode = argv[++i];
+    else if (a == "--case") cas = argv[++i];
+    else if (a == "--lib") lib = argv[++i];
+    else if (a == "--json") json = argv[++i];
+    else if (a == "--record") record = argv[++i];
+    else if (a == "--steps") steps = atoi(argv[++i]);
+    else if (a == "--warmup") warmup = atoi(argv[++i]);
+    else if (a == "--chunks") nchunks = atoi(argv[++i]);
+    else if (a == "--nl") nl_mode = atoi(argv[++i]);
+    else if (a == "--device") device = atoi(argv[++i]);
+    else if (a == "--batch") batch = atoi(argv[++i]);
+    else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
+  }
+  if (!batch) batch = steps;
+  FILE *jf = json.empty() ? stderr : fopen(json.c_str(), "w");
+  if (!jf) { fprintf(stderr, "cannot open %s\n", json.c_str()); return 2; }
+
+  int nthreads = 1;
+#pragma omp parallel
+  {
+#pragma omp master
+    nthreads = omp_get_num_threads();
+  }
+
+  if (mode == "ref") {
+    problem *p = build(cas, nchunks);
+    for (int i = 0; i < warmup; ++i) p->f->step();
+    double t0 = wall_time();
+    for (int i = 0; i < steps; ++i) p->f->step();
+    double t1 = wall_time();
+    fprintf(jf,
+            "{\"mode\":\"ref\",\"case\":\"%s\",\"realnum_bytes\":%d,\"steps\":%d,\"warmup\":%d,"
+            "\"threads\":%d,\"cells\":%ld,\"num_chunks\":%d,\"seconds\":%.6f,"
+            "\"mcells_per_s\":%.4f,\"probe\":%.17g}\n",
+            cas.c_str(), (int)sizeof(realnum), steps, warmup, nthreads, p->cells, p->f->num_chunks,
+            t1 - t0, p->cells * (double)steps / (t1 - t0) / 1e6, probe_value(p));
+    delete p;
+  }
+  else if (mode == "gpu") {
+    if (lib.empty()) { fprintf(stderr, "--lib required\n"); return 2; }
+    problem *p = build(cas, nchunks);
+    meepcu::api api(lib.c_str());
+    double ta = wall_time();
+    meepcu::attachment *att = new meepcu::attachment(*p->f, api, nl_mode, device);
+    double tb = wall_time();
+    if (warmup) att->step(warmup);
+    att->sync_to_host();
+    double t0 = wall_time();
+    for (int done = 0; done < steps; done += batch) att->step(std::min(batch, steps - done));
+    att->sync_to_host();
+    double t1 = wall_time();
+    meepcu_stats st = att->stats();
+    fprintf(jf,
+            "{\"mode\":\"gpu\",\"backend\":\"%s\",\"case\":\"%s\",\"realnum_bytes\":%d,\"steps\":%d,"
+            "\"warmup\":%d,\"cells\":%ld,\"num_chunks\":%d,\"attach_seconds\":%.6f,\"seconds\":%.6f,"
+            "\"mcells_per_s\":%.4f,\"kernel_launches\":%ld,\"device_bytes\":%ld,\"probe\":%.17g}\n",
+            api.backend(), cas.c_str(), (int)sizeof(realnum), steps, warmup, p->cells,
+            p->f->num_chunks, tb - ta, t1 - t0, p->cells * (double)steps / (t1 - t0) / 1e6,
+            (long)st.kernel_launches, (long)st.device_bytes, probe_value(p));
+    delete att;
+    delete p;
+  }
+  else if (mode == "shim") {
+    if (lib.empty()) { fprintf(stderr, "--lib required\n"); return 2; }
+    problem *A = build(cas, nchunks), *B = build(cas, nchunks);
+    meepcu::api api(lib.c_str());
+    meepcu::trace_recorder *rec = record.empty() ? 0 : new meepcu::trace_recorder(record.c_str());
+    // warm-up steps run on the reference CPU path on BOTH twins: the attach then happens in
+    // mid-simulation, with every lazily allocated array already live
+    for (int i = 0; i < warmup; ++i) { A->f->step(); B->f->step(); }
+    meepcu::attachment *att = new meepcu::attachment(*B->f, api, nl_mode, device, rec);
+    double t0 = wall_time();
+    for (int i = 0; i < steps; ++i) A->f->step();
+    double t1 = wall_time();
+    for (int done = 0; done < steps; done += batch) att->step(std::min(batch, steps - done));
+    att->sync_to_host();
+    double t2 = wall_time();
+    std::vector<marray> ma = collect(*A->f), mb = collect(*B->f);
+    cmp_result r = compare(ma, mb);
+    if (rec) {
+      if (ma.size() != mb.size()) meep::abort("cannot record: twins differ");
+      for (size_t k = 0; k < ma.size(); ++k) rec->expect(mb[k].p, ma[k].p);
+      rec->close();
+    }
+    double relL2 = r.sum_r2 > 0 ? sqrt(r.sum_d2 / r.sum_r2) : sqrt(r.sum_d2);
+    fprintf(jf,
+            "{\"mode\":\"shim\",\"backend\":\"%s\",\"case\":\"%s\",\"realnum_bytes\":%d,\"steps\":%d,"
+            "\"warmup\":%d,\"threads\":%d,\"cells\":%ld,\"num_chunks\":%d,\"arrays\":%zu,\"elements\":%zu,"
+            "\"mismatched_arrays\":%zu,\"mismatched_elements\":%zu,\"max_abs_diff\":%.6g,"
+            "\"rel_l2\":%.6g,\"first_bad\":\"%s\",\"ref_seconds\":%.6f,\"abi_seconds\":%.6f,"
+            "\"probe_ref\":%.17g,\"probe_abi\":%.17g,\"finite\":%d,\"t\":%d}\n",
+            api.backend(), cas.c_str(), (int)sizeof(realnum), steps, warmup, nthreads, A->cells,
+            A->f->num_chunks, r.narrays, r.nelems, r.nmismatch_arrays, r.nmismatch_elems, r.max_abs,
+            relL2, r.first_bad.c_str(), t1 - t0, t2 - t1, probe_value(A), probe_value(B),
+            (int)att->finite(), B->f->t);
+    delete att;
+    delete rec;
+    delete A;
+    delete B;
+  }
+  else {
+    fprintf(stderr, "unknown mode %s\n", mode.c_str());
+    return 2;
+  }
+  if (jf != stderr) fclose(jf);
+  return 0;
+}
