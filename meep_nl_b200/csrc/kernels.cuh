@@ -1,0 +1,743 @@
+// kernels.cuh -- sm_100a kernels of the per-timestep field update.
+//
+// Reference semantics restated here (each kernel cites the lines it replaces):
+//   k_half      : fields_chunk::step_db + step_curl        (src/step_db.cpp:44-146, step_generic.cpp:69-253)
+//                 fields_chunk::step_source                (src/step.cpp:296-319)
+//                 fields_chunk::zero_metal                 (src/boundaries.cpp:304-307)
+//                 fields_chunk::update_eh + step_update_EDHB, diagonal branches
+//                                                          (src/update_eh.cpp:67-283, step_generic.cpp:576-906)
+//                 lorentzian_susceptibility::subtract_P / update_P, isotropic
+//                                                          (src/susceptibility.cpp:188-281)
+//                 all fused in ONE pass over a chunk so that every array element moves once per
+//                 half step (DESIGN.md "bytes per cell").
+//   k_eh_general: step_update_EDHB branches that read neighbours of D-P: the fork's Newton-Raphson
+//                 chi2 solve (step_generic.cpp:730-816, newton_raphson.cpp:93-359) and upstream's
+//                 Pade/off-diagonal formulas (UPSTREAM_PADE mode)
+//   k_fmp       : f_minus_p = D - P - dipoles             (src/update_eh.cpp:122-146)
+//   k_conn_*    : fields::step_boundaries gather/scatter   (src/step.cpp:173-288)
+//   k_dft       : dft_chunk::update_dft                    (src/dft.cpp:265-307)
+//
+// Arithmetic is written with the reference's operand order and compiled with --fmad=false so
+// that results are bit-identical to the reference's x86-64 build (no FMA contraction there).
+//
+// Thread mapping (all grid kernels): a chunk's array is [nA][nB][pitch] with the fastest axis C
+// padded to `pitch` (multiple of 32 elements, rows 128B-aligned).  A CTA owns 256 consecutive
+// positions of the flattened (B,C) plane -- fully coalesced rows -- and marches along A over
+// [a0,a1).  One launch covers every chunk: CTAs find their (chunk, cmp, plane segment, A range)
+// in a tile table, and copy that chunk's parameter block to shared memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mcu {
+
+constexpr int kThreads = 256;
+constexpr int kMaxPol = 4;
+
+struct SrcEntry { // one source point, sorted by device index (stable in reference order)
+  long long idx;
+  double are, aim; // src_vol::amplitude(j)
+  int tid;         // src_time id
+  int pad;
+};
+
+template <class T> struct PolParams { // one lorentzian_susceptibility for one component/cmp
+  T *p, *pp;                          // lorentzian_data::P / P_prev   (NULL: this pol has no P here)
+  const T *s;                         // sigma[c][component_direction(c)] (NULL: no update)
+  T gamma1inv, gamma1, omega0dtsqr, omega0dtsqr_denom; // susceptibility.cpp:191-194
+};
+
+template <class T> struct CompParams {
+  // ---- curl update of the D/B component (step_curl's arguments after the g1/g2 swap) ----
+  T *f;
+  const T *g1, *g2;
+  long long s1, s2;
+  T dtdx, dt2;
+  int lo[3], hi[3]; // owned index range on the device axes A,B,C (inclusive)
+  T *fu, *fcnd;
+  const T *cnd, *cndinv;
+  const T *sig, *kap, *siginv;
+  int kaxis, koff; // k = 2*idx[kaxis] + koff   (kaxis < 0: no PML in the f update)
+  const T *sigu, *kapu, *siginvu;
+  int kuaxis, kuoff;
+  unsigned zmask_db; // metal planes: bit d -> idx[d]==lo[d], bit 3+d -> idx[d]==hi[d]
+  // ---- sources ----
+  const SrcEntry *csrc; // currents (step_source)
+  const SrcEntry *isrc; // integrated sources (update_eh.cpp:136-146)
+  int ncsrc, nisrc;
+  int csrc_amin, csrc_amax, isrc_amin, isrc_amax; // A range that contains source points
+  int src_has_cndinv;
+  // ---- E/H update (NULL e: H aliases B, or the update is done by k_eh_general) ----
+  T *e;
+  const T *u;
+  T *fw;
+  const T *sigw, *kapw;
+  int kwaxis, kwoff;
+  unsigned zmask_eh;
+  int npol;
+  PolParams<T> pol[kMaxPol];
+};
+
+template <class T> struct HalfParams { // one chunk, one of {B/H, D/E}, one cmp
+  int nA, nB, nC, pitch;
+  long long sA, sB; // device strides of axes A and B (C is 1)
+  int is_D;         // 1: D/E half (currents from current_D, dipoles from dipole_E)
+  int cmp;
+  double dt;
+  CompParams<T> comp[3];
+};
+
+struct Tile {
+  int param; // index into the HalfParams table
+  int a0, a1;
+  int p0; // first position of the flattened (B,C) plane
+};
+
+// meepcu_src_sample layout: current_B[2], dipole_H[2], current_D[2], dipole_E[2]
+__device__ __forceinline__ double2 sample_current(const double *smp, int tid, int is_D) {
+  const double *s = smp + 8 * tid + (is_D ? 4 : 0);
+  return make_double2(s[0], s[1]);
+}
+__device__ __forceinline__ double2 sample_dipole(const double *smp, int tid, int is_D) {
+  const double *s = smp + 8 * tid + (is_D ? 6 : 2);
+  return make_double2(s[0], s[1]);
+}
+
+__device__ __forceinline__ int src_lower_bound(const SrcEntry *t, int n, long long idx) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (t[mid].idx < idx) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// std::complex<double> product as libstdc++/libgcc evaluate it for finite operands
+__device__ __forceinline__ double2 cmul(double a, double b, double c, double d) {
+  return make_double2(a * c - b * d, a * d + b * c);
+}
+
+template <class T>
+__device__ __forceinline__ bool on_zero_plane(unsigned m, const int lo[3], const int hi[3], int ia,
+                                              int ib, int ic) {
+  if (!m) return false;
+  return ((m & 1u) && ia == lo[0]) || ((m & 2u) && ib == lo[1]) || ((m & 4u) && ic == lo[2]) ||
+         ((m & 8u) && ia == hi[0]) || ((m & 16u) && ib == hi[1]) || ((m & 32u) && ic == hi[2]);
+}
+
+// One point of one component: curl update, sources, metal, then (optionally) E/H + polarisations.
+template <class T, bool SIMPLE>
+__device__ __forceinline__ void update_point(const CompParams<T> &c, long long i, int ia, int ib,
+                                             int ic, const double *smp, int is_D, int cmp,
+                                             double dt) {
+  // ---------------- step_curl (step_generic.cpp:89-252) ----------------
+  T curl;
+  if (c.g2)
+    curl = (c.g1[i + c.s1] - c.g1[i] + c.g2[i] - c.g2[i + c.s2]);
+  else
+    curl = (c.g1[i + c.s1] - c.g1[i]);
+  T fnew;
+  if (SIMPLE) {
+    fnew = c.f[i] - c.dtdx * curl; // :108,112
+  }
+  else {
+    const int idx3[3] = {ia, ib, ic};
+    T fold = c.f[i];
+    if (c.kaxis < 0) {
+      if (c.kuaxis < 0) {
+        if (c.cnd) // :95,101
+          fnew = ((1 - c.dt2 * c.cnd[i]) * fold - c.dtdx * curl) * c.cndinv[i];
+        else
+          fnew = fold - c.dtdx * curl;
+      }
+      else { // :121-154
+        const int ku = 2 * idx3[c.kuaxis] + c.kuoff;
+        T fprev = c.fu[i], fun;
+        if (c.cnd)
+          fun = ((1 - c.dt2 * c.cnd[i]) * fprev - c.dtdx * curl) * c.cndinv[i];
+        else
+          fun = fprev - c.dtdx * curl;
+        c.fu[i] = fun;
+        fnew = c.siginvu[ku] * ((c.kapu[ku] - c.sigu[ku]) * fold + fun - fprev);
+      }
+    }
+    else {
+      const int k = 2 * idx3[c.kaxis] + c.koff;
+      if (c.kuaxis < 0) { // :164-196
+        if (c.cnd) {
+          T fcnd_prev = c.fcnd[i];
+          T fc = ((1 - c.dt2 * c.cnd[i]) * fcnd_prev - c.dtdx * curl) * c.cndinv[i];
+          c.fcnd[i] = fc;
+          fnew = ((c.kap[k] - c.sig[k]) * fold + (fc - fcnd_prev)) * c.siginv[k];
+        }
+        else
+          fnew = ((c.kap[k] - c.sig[k]) * fold - c.dtdx * curl) * c.siginv[k];
+      }
+      else { // :199-250
+        const int ku = 2 * idx3[c.kuaxis] + c.kuoff;
+        T fprev = c.fu[i], fun;
+        if (c.cnd) {
+          T fcnd_prev = c.fcnd[i];
+          T fc = ((1 - c.dt2 * c.cnd[i]) * fcnd_prev - c.dtdx * curl) * c.cndinv[i];
+          c.fcnd[i] = fc;
+          fun = ((c.kap[k] - c.sig[k]) * fprev + (fc - fcnd_prev)) * c.siginv[k];
+        }
+        else
+          fun = ((c.kap[k] - c.sig[k]) * fprev - c.dtdx * curl) * c.siginv[k];
+        c.fu[i] = fun;
+        fnew = c.siginvu[ku] * ((c.kapu[ku] - c.sigu[ku]) * fold + fun - fprev);
+      }
+    }
+  }
+  // ---------------- step_source (step.cpp:296-319) ----------------
+  if (c.ncsrc && ia >= c.csrc_amin && ia <= c.csrc_amax) {
+    for (int j = src_lower_bound(c.csrc, c.ncsrc, i); j < c.ncsrc && c.csrc[j].idx == i; ++j) {
+      const SrcEntry e = c.csrc[j];
+      const double2 cur = sample_current(smp, e.tid, is_D);
+      double2 A = cmul(e.are, e.aim, cur.x, cur.y);
+      A.x = A.x * dt;
+      A.y = A.y * dt;
+      if (c.src_has_cndinv) {
+        const double ci = double(c.cndinv[i]);
+        A.x = A.x * ci;
+        A.y = A.y * ci;
+      }
+      fnew = (T)((double)fnew - (cmp ? A.y : A.x));
+    }
+  }
+  // ---------------- zero_metal(D/B) inside step_boundaries (boundaries.cpp:304-307) -------------
+  if (on_zero_plane<T>(c.zmask_db, c.lo, c.hi, ia, ib, ic)) fnew = 0;
+  c.f[i] = fnew;
+
+  // ---------------- update_eh (update_eh.cpp:122-283; step_generic.cpp:706-725,888-903) ---------
+  if (!c.e) return;
+  T fmp = fnew;
+  if (!SIMPLE) {
+#pragma unroll
+    for (int ip = 0; ip < kMaxPol; ++ip)
+      if (ip < c.npol && c.pol[ip].p) fmp -= c.pol[ip].p[i]; // subtract_P, susceptibility.cpp:264-281
+  }
+  if (c.nisrc && ia >= c.isrc_amin && ia <= c.isrc_amax) {
+    for (int j = src_lower_bound(c.isrc, c.nisrc, i); j < c.nisrc && c.isrc[j].idx == i; ++j) {
+      const SrcEntry e = c.isrc[j];
+      const double2 dp = sample_dipole(smp, e.tid, is_D);
+      const double2 A = cmul(e.are, e.aim, dp.x, dp.y);
+      fmp = (T)((double)fmp - (cmp ? A.y : A.x));
+    }
+  }
+  const T gu = c.u ? (fmp * c.u[i]) : fmp;
+  T enew, w;
+  if (!SIMPLE && c.fw) { // PML: step_generic.cpp:708-724
+    const int idx3[3] = {ia, ib, ic};
+    const int kw = 2 * idx3[c.kwaxis] + c.kwoff;
+    const T fwprev = c.fw[i], kapwkw = c.kapw[kw], sigwkw = c.sigw[kw];
+    c.fw[i] = gu;
+    enew = c.e[i] + ((kapwkw + sigwkw) * gu - (kapwkw - sigwkw) * fwprev);
+    w = gu;
+  }
+  else {
+    enew = gu;
+    w = gu;
+  }
+  if (!SIMPLE) {
+    // update_pols runs before zero_metal(E) (step.cpp:109-122): it sees the un-zeroed W
+#pragma unroll
+    for (int ip = 0; ip < kMaxPol; ++ip)
+      if (ip < c.npol && c.pol[ip].p && c.pol[ip].s) { // susceptibility.cpp:252-259
+        const PolParams<T> &q = c.pol[ip];
+        const T pcur = q.p[i];
+        q.p[i] = q.gamma1inv * (pcur * (2 - q.omega0dtsqr_denom) - q.gamma1 * q.pp[i] +
+                                q.omega0dtsqr * (q.s[i] * w));
+        q.pp[i] = pcur;
+      }
+  }
+  if (on_zero_plane<T>(c.zmask_eh, c.lo, c.hi, ia, ib, ic)) enew = 0;
+  c.e[i] = enew;
+}
+
+template <class T, bool SIMPLE>
+__global__ void __launch_bounds__(kThreads)
+    k_half(const HalfParams<T> *__restrict__ params, const Tile *__restrict__ tiles,
+           const double *__restrict__ smp) {
+  __shared__ HalfParams<T> P;
+  const Tile t = tiles[blockIdx.x];
+  {
+    const int nw = (int)(sizeof(HalfParams<T>) / 4);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(params + t.param);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&P);
+    for (int k = threadIdx.x; k < nw; k += kThreads) dst[k] = src[k];
+  }
+  __syncthreads();
+  const int p = t.p0 + threadIdx.x;
+  const int ib = p / P.pitch, ic = p - ib * P.pitch;
+  if (ib >= P.nB || ic >= P.nC) return;
+  bool act[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const CompParams<T> &c = P.comp[k];
+    act[k] = c.f != nullptr && ib >= c.lo[1] && ib <= c.hi[1] && ic >= c.lo[2] && ic <= c.hi[2];
+  }
+  if (!(act[0] || act[1] || act[2])) return;
+  long long i = (long long)t.a0 * P.sA + (long long)ib * P.sB + ic;
+  for (int ia = t.a0; ia < t.a1; ++ia, i += P.sA) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const CompParams<T> &c = P.comp[k];
+      if (act[k] && ia >= c.lo[0] && ia <= c.hi[0])
+        update_point<T, SIMPLE>(c, i, ia, ib, ic, smp, P.is_D, P.cmp, P.dt);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// step_boundaries: dst[n] = src[n] (COPY), = -src[n] (NEGATE), complex phase multiply (PHASE).
+// Sources are owned points and destinations not-owned points, so gather and scatter can be one
+// pass (the reference stages through comm_blocks only because of MPI).
+// ------------------------------------------------------------------------------------------------
+template <class T> struct ConnTable {
+  T *const *dst;
+  const T *const *src;
+  const T *phase; // (re,im) per complex transfer, PHASE only
+  long long n;    // number of realnum transfers (PHASE: 2 per complex)
+};
+
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+    k_conn(ConnTable<T> phase, ConnTable<T> negate, ConnTable<T> copy) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long n = t0; n < copy.n; n += stride) *copy.dst[n] = *copy.src[n];
+  for (long long n = t0; n < negate.n; n += stride) *negate.dst[n] = -*negate.src[n];
+  for (long long n = t0; n < phase.n / 2; n += stride) { // step.cpp:188-194
+    const T pr = phase.phase[2 * n], pi = phase.phase[2 * n + 1];
+    const T br = *phase.src[2 * n], bi = *phase.src[2 * n + 1];
+    *phase.dst[2 * n] = pr * br - pi * bi;
+    *phase.dst[2 * n + 1] = pr * bi + pi * br;
+  }
+}
+
+// zero_metal for lists that are not fused into k_half (general fallback)
+template <class T> __global__ void k_zero(T *const *ptrs, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+    *ptrs[k] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// f_minus_p = D - sum P - integrated dipoles over the whole array incl. not-owned points
+// (update_eh.cpp:122-146), needed only where the E update reads neighbours of D-P.
+// ------------------------------------------------------------------------------------------------
+template <class T> struct FmpParams {
+  T *fmp;
+  const T *d;
+  const T *p[kMaxPol];
+  int npol;
+  long long n; // device elements
+  const SrcEntry *isrc;
+  int nisrc;
+  int is_D, cmp;
+};
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+    k_fmp(const FmpParams<T> *__restrict__ tab, int ntab, const double *__restrict__ smp) {
+  for (int it = blockIdx.y; it < ntab; it += gridDim.y) {
+    const FmpParams<T> q = tab[it];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < q.n; i += stride) {
+      T v = q.d[i];
+      for (int ip = 0; ip < q.npol; ++ip)
+        if (q.p[ip]) v -= q.p[ip][i];
+      q.fmp[i] = v;
+    }
+  }
+}
+template <class T>
+__global__ void k_fmp_src(const FmpParams<T> *__restrict__ tab, int ntab,
+                          const double *__restrict__ smp) {
+  // one thread per table; integrated sources are few and must be applied in list order
+  const int it = blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= ntab) return;
+  const FmpParams<T> q = tab[it];
+  for (int j = 0; j < q.nisrc; ++j) {
+    const SrcEntry e = q.isrc[j];
+    const double2 dp = sample_dipole(smp, e.tid, q.is_D);
+    const double2 A = cmul(e.are, e.aim, dp.x, dp.y);
+    q.fmp[e.idx] = (T)((double)q.fmp[e.idx] - (q.cmp ? A.y : A.x));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// step_update_EDHB in full generality for one component (step_generic.cpp:576-906), plus the
+// isotropic polarisation update and zero_metal(E), for chunks whose E update reads neighbours.
+// ------------------------------------------------------------------------------------------------
+template <class T> struct EhParams {
+  int nA, nB, nC, pitch;
+  long long sA, sB;
+  int lo[3], hi[3];
+  T *f;               // E (or H) component
+  int fc;             // component id (0 Ex, 1 Ey, 4 Ez): selects the NR argument order
+  const T *g, *g1, *g2; // dmp[dc], dmp[dc_1], dmp[dc_2] after the swap rule
+  const T *u, *u1, *u2;
+  long long s, s1, s2;
+  const T *chi2, *chi3;
+  T *fw;
+  const T *sigw, *kapw;
+  int kwaxis, kwoff;
+  int nl_mode;
+  unsigned zmask_eh;
+  int npol;
+  PolParams<T> pol[kMaxPol];
+  int *nr_fail; // device counter of cells whose NR seed ladder was exhausted
+};
+
+template <class T>
+__device__ __forceinline__ T calc_nonlinear_u(const T Dsqr, const T Di, const T chi1inv,
+                                              const T chi2, const T chi3) { // step_generic.cpp:546-553
+  T c2 = Di * chi2 * (chi1inv * chi1inv);
+  T c3 = Dsqr * chi3 * (chi1inv * chi1inv * chi1inv);
+  return (1 + c2 + 2 * c3) / (1 + 2 * c2 + 3 * c3);
+}
+
+// Newton-Raphson for  A_k = B_k v_k + chi2 * (product of the other two)   (newton_raphson.cpp).
+// For the zinc-blende tensor only F of eq.1, G of eq.2 and H of eq.3 are non-zero and equal to
+// chi2, but the arithmetic below keeps the reference's general expressions (with the zero
+// coefficients written out) so that every rounding is the same.
+template <class T> struct NRP { T A, B, F, G, H; };
+
+template <class T>
+__device__ __forceinline__ void nr_equations(double x, double y, double z, const NRP<T> &p1,
+                                             const NRP<T> &p2, const NRP<T> &p3, double F[3]) {
+  F[0] = p1.A - (p1.B * x + p1.F * y * z + p1.G * x * z + p1.H * x * y);
+  F[1] = p2.A - (p2.B * y + p2.F * y * z + p2.G * x * z + p2.H * x * y);
+  F[2] = p3.A - (p3.B * z + p3.F * y * z + p3.G * x * z + p3.H * x * y);
+}
+
+template <class T>
+__device__ bool nr_iterate(T x, T y, T z, const NRP<T> &p1, const NRP<T> &p2, const NRP<T> &p3,
+                           T out[3], double tol1, double tol2, double tol3, int max_iter) {
+  for (int iter = 0; iter < max_iter; iter++) { // newton_raphson.cpp:93-142
+    double F[3], J[3][3], b[3], d[3];
+    nr_equations<T>(x, y, z, p1, p2, p3, F);
+    J[0][0] = -p1.B - p1.G * z - p1.H * y;
+    J[0][1] = -p1.F * z - p1.H * x;
+    J[0][2] = -p1.F * y - p1.G * x;
+    J[1][0] = -p2.G * z - p2.H * y;
+    J[1][1] = -p2.B - p2.F * z - p2.H * x;
+    J[1][2] = -p2.F * y - p2.G * x;
+    J[2][0] = -p3.G * z - p3.H * y;
+    J[2][1] = -p3.F * z - p3.H * x;
+    J[2][2] = -p3.B - p3.F * y - p3.G * x;
+    b[0] = F[0]; b[1] = F[1]; b[2] = F[2];
+    // solveLinearSystem :170-194 (no pivoting)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = i + 1; j < 3; j++) {
+        const double factor = J[j][i] / J[i][i];
+#pragma unroll
+        for (int k = i; k < 3; k++) J[j][k] -= factor * J[i][k];
+        b[j] -= factor * b[i];
+      }
+#pragma unroll
+    for (int i = 2; i >= 0; i--) {
+      d[i] = b[i];
+#pragma unroll
+      for (int j = i + 1; j < 3; j++) d[i] -= J[i][j] * d[j];
+      d[i] /= J[i][i];
+    }
+    x -= d[0];
+    y -= d[1];
+    z -= d[2];
+    if (fabs(d[0]) < tol1 && fabs(d[1]) < tol2 && fabs(d[2]) < tol3) {
+      const double ax = fabs((double)x), ay = fabs((double)y), az = fabs((double)z);
+      const double chk = (ax > ay ? (ax > az ? ax : az) : (ay > az ? ay : az)) * 1e-4;
+      double Fc[3];
+      nr_equations<T>(x, y, z, p1, p2, p3, Fc);
+      if (Fc[0] <= chk && Fc[1] <= chk && Fc[2] <= chk) {
+        out[0] = x; out[1] = y; out[2] = z;
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+// runNR :209-359 with the deterministic part of the seed ladder
+template <class T>
+__device__ bool run_nr(T seed1, T seed2, T seed3, T out[3], const NRP<T> &p1, const NRP<T> &p2,
+                       const NRP<T> &p3) {
+  const double TOL = 1e-8, seedMax = 1e33;
+  int max_iter = 250;
+  const double tol1 = fmax(fabs(TOL * out[0]) * 0.0001, TOL);
+  const double tol2 = fmax(fabs(TOL * out[1]) * 0.0001, TOL);
+  const double tol3 = fmax(fabs(TOL * out[2]) * 0.0001, TOL);
+  double s1 = seed1, s2 = seed2, s3 = seed3;
+  for (int i = 0; i < 15; ++i) {
+    if (nr_iterate<T>((T)s1, (T)s2, (T)s3, p1, p2, p3, out, tol1, tol2, tol3, max_iter)) return true;
+    switch (i) {
+      case 0: s1 = seed1 * seedMax; max_iter = 600; break;
+      case 1: s1 = seed1; s2 = seed2 * seedMax; break;
+      case 2: s2 = seed2; s3 = seed3 * seedMax; break;
+      case 3: s3 = seed3; s1 = -seed1 * seedMax; break;
+      case 4: s1 = seed1; s2 = -seed2 * seedMax; break;
+      case 5: s2 = seed2; s3 = -seed3 * seedMax; break;
+      case 6: s1 = seed1 * seedMax; s2 = seed2 * seedMax; s3 = seed3; break;
+      case 7: s1 = seed1 * seedMax; s2 = seed2; s3 = seed3 * seedMax; break;
+      case 8: s1 = seed1; s2 = seed2 * seedMax; s3 = seed3 * seedMax; break;
+      case 9: s1 = -seed1 * seedMax; s2 = -seed2 * seedMax; s3 = seed3; break;
+      case 10: s1 = -seed1 * seedMax; s2 = seed2; s3 = -seed3 * seedMax; break;
+      case 11: s1 = seed1; s2 = -seed2 * seedMax; s3 = -seed3 * seedMax; break;
+      case 12: s1 = seed1 * seedMax; s2 = seed2 * seedMax; s3 = seed3 * seedMax; break;
+      case 13: s1 = -seed1 * seedMax; s2 = -seed2 * seedMax; s3 = -seed3 * seedMax; break;
+      default: return false;
+    }
+  }
+  return false;
+}
+
+#define MCU_OFFDIAG(u, g, sx)                                                                      \
+  (0.25 * ((g[i] + g[i - sx]) * u[i] + (g[i + s] + g[(i + s) - sx]) * u[i + s]))
+
+template <class T>
+__device__ __forceinline__ void eh_point(const EhParams<T> &q, long long i, int ia, int ib, int ic) {
+  const T *g = q.g, *g1 = q.g1, *g2 = q.g2, *u = q.u, *u1 = q.u1, *u2 = q.u2;
+  const long long s = q.s, s1 = q.s1, s2 = q.s2;
+  const bool pade = q.nl_mode == 1;
+  T val; // u*g with whatever nonlinear / off-diagonal terms apply
+  bool done_nr = false;
+  if (!pade) {
+    if (!q.fw && u1 && u2 && q.chi3) { // the fork's NR branch, step_generic.cpp:732-816
+      const T gs = g[i];
+      const T gs_2 = (g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)]) * 0.25;
+      const T gs_3 = (g2[i] + g2[i + s] + g2[i - s2] + g2[i + (s - s2)]) * 0.25;
+      const T ui = u[i];
+      const T us = 1 / ui;
+      const T chi2new = q.chi2[i];
+      int zeroEps = 0;
+      if (ui == 0) zeroEps += 1;
+      if (u1[i] == 0) zeroEps += 1;
+      if (u2[i] == 0) zeroEps += 1;
+      if (chi2new == 0 || zeroEps > 1) { val = (gs * ui); }
+      else {
+        T out[3];
+        NRP<T> p1, p2, p3;
+        T sd1, sd2, sd3;
+        const T z0 = 0.0;
+        int own;
+        if (q.fc == 0) {
+          p1 = {gs, us, chi2new, z0, z0};
+          p2 = {gs_2, us, z0, chi2new, z0};
+          p3 = {gs_3, us, z0, z0, chi2new};
+          sd1 = q.f[i]; sd2 = gs_2 * ui; sd3 = gs_3 * ui;
+          own = 0;
+        }
+        else if (q.fc == 1) {
+          p1 = {gs_3, us, chi2new, z0, z0};
+          p2 = {gs, us, z0, chi2new, z0};
+          p3 = {gs_2, us, z0, z0, chi2new};
+          sd1 = gs_3 * ui; sd2 = q.f[i]; sd3 = gs_2 * ui;
+          own = 1;
+        }
+        else {
+          p1 = {gs_2, us, chi2new, z0, z0};
+          p2 = {gs_3, us, z0, chi2new, z0};
+          p3 = {gs, us, z0, z0, chi2new};
+          sd1 = gs_2 * ui; sd2 = gs_3 * ui; sd3 = q.f[i];
+          own = 2;
+        }
+        out[0] = out[1] = out[2] = 0;
+        out[own] = q.f[i]; // *fw of this component = previous field; the dummies are 0
+        const bool ok = run_nr<T>(sd1, sd2, sd3, out, p1, p2, p3);
+        if (!ok) {
+          atomicAdd(q.nr_fail, 1);
+          out[own] = q.f[i];
+        }
+        val = out[own];
+      }
+      done_nr = true;
+    }
+    else
+      val = u ? (g[i] * u[i]) : g[i];
+  }
+  else {
+    if (u1 && u2) {
+      const T gs = g[i], us = u[i];
+      if (q.chi3) {
+        const T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
+        const T g2s = g2[i] + g2[i + s] + g2[i - s2] + g2[i + (s - s2)];
+        val = (gs * us + MCU_OFFDIAG(u1, g1, s1) + MCU_OFFDIAG(u2, g2, s2)) *
+              calc_nonlinear_u<T>(gs * gs + 0.0625 * (g1s * g1s + g2s * g2s), gs, us, q.chi2[i],
+                                  q.chi3[i]);
+      }
+      else
+        val = (gs * us + MCU_OFFDIAG(u1, g1, s1) + MCU_OFFDIAG(u2, g2, s2));
+    }
+    else if (u1) {
+      const T gs = g[i], us = u[i];
+      if (q.chi3) {
+        const T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
+        val = (gs * us + MCU_OFFDIAG(u1, g1, s1)) *
+              calc_nonlinear_u<T>(gs * gs + 0.0625 * (g1s * g1s), gs, us, q.chi2[i], q.chi3[i]);
+      }
+      else
+        val = (gs * us + MCU_OFFDIAG(u1, g1, s1));
+    }
+    else if (q.chi3) {
+      const T gs = g[i], us = u[i];
+      if (g1 && g2) {
+        const T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
+        const T g2s = g2[i] + g2[i + s] + g2[i - s2] + g2[i + (s - s2)];
+        val = (gs * us) * calc_nonlinear_u<T>(gs * gs + 0.0625 * (g1s * g1s + g2s * g2s), gs, us,
+                                              q.chi2[i], q.chi3[i]);
+      }
+      else if (g1) {
+        const T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
+        val = (gs * us) *
+              calc_nonlinear_u<T>(gs * gs + 0.0625 * (g1s * g1s), gs, us, q.chi2[i], q.chi3[i]);
+      }
+      else
+        val = (gs * us) * calc_nonlinear_u<T>(gs * gs, gs, us, q.chi2[i], q.chi3[i]);
+    }
+    else
+      val = u ? (g[i] * u[i]) : g[i];
+  }
+  (void)done_nr;
+  T enew, w;
+  if (q.fw) {
+    const int idx3[3] = {ia, ib, ic};
+    const int kw = 2 * idx3[q.kwaxis] + q.kwoff;
+    const T fwprev = q.fw[i], kapwkw = q.kapw[kw], sigwkw = q.sigw[kw];
+    q.fw[i] = val;
+    enew = q.f[i] + ((kapwkw + sigwkw) * val - (kapwkw - sigwkw) * fwprev);
+    w = val;
+  }
+  else {
+    enew = val;
+    w = val;
+  }
+#pragma unroll
+  for (int ip = 0; ip < kMaxPol; ++ip)
+    if (ip < q.npol && q.pol[ip].p && q.pol[ip].s) {
+      const PolParams<T> &pp = q.pol[ip];
+      const T pcur = pp.p[i];
+      pp.p[i] = pp.gamma1inv * (pcur * (2 - pp.omega0dtsqr_denom) - pp.gamma1 * pp.pp[i] +
+                                pp.omega0dtsqr * (pp.s[i] * w));
+      pp.pp[i] = pcur;
+    }
+  if (on_zero_plane<T>(q.zmask_eh, q.lo, q.hi, ia, ib, ic)) enew = 0;
+  q.f[i] = enew;
+}
+
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+    k_eh_general(const EhParams<T> *__restrict__ params, const Tile *__restrict__ tiles) {
+  __shared__ EhParams<T> P;
+  const Tile t = tiles[blockIdx.x];
+  {
+    const int nw = (int)(sizeof(EhParams<T>) / 4);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(params + t.param);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&P);
+    for (int k = threadIdx.x; k < nw; k += kThreads) dst[k] = src[k];
+  }
+  __syncthreads();
+  const int p = t.p0 + threadIdx.x;
+  const int ib = p / P.pitch, ic = p - ib * P.pitch;
+  if (ib < P.lo[1] || ib > P.hi[1] || ic < P.lo[2] || ic > P.hi[2]) return;
+  const int a0 = t.a0 > P.lo[0] ? t.a0 : P.lo[0];
+  const int a1 = t.a1 - 1 < P.hi[0] ? t.a1 - 1 : P.hi[0];
+  long long i = (long long)a0 * P.sA + (long long)ib * P.sB + ic;
+  for (int ia = a0; ia <= a1; ++ia, i += P.sA) eh_point<T>(P, i, ia, ib, ic);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dft_chunk::update_dft (dft.cpp:265-307).  One thread per (point, omega) element of dft[] so the
+// read-modify-write of the accumulator -- the dominant traffic -- is fully coalesced.
+// ------------------------------------------------------------------------------------------------
+template <class T> struct DftParams {
+  const T *f0, *f1;  // field component re / im (f1 NULL for real fields)
+  T *dft;            // complex<T>[N*Nomega] as (re,im) pairs
+  long long idx0;    // device index of the region's first point
+  long long st[3];   // device strides of the three loop levels (reference loop order)
+  int n[3];          // loop_n1..3
+  int dir[3];        // loop_d1..3 (direction index X/Y/Z -> 0..2)
+  long long avg1, avg2; // device offsets
+  double s0[3], s1[3], e0[3], e1[3], dV0, dV1;
+  int include_dV, sqrt_dV;
+  int Nomega;
+  int phase_group;   // which row of the per-step phase table
+  long long N;
+};
+struct DftWork {
+  int param;
+  long long e0; // first element (point*Nomega + omega) of this CTA
+};
+
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+    k_dft(const DftParams<T> *__restrict__ params, const DftWork *__restrict__ work,
+          const T *__restrict__ phases, const int *__restrict__ phase_off,
+          const unsigned char *__restrict__ active) {
+  const DftWork wk = work[blockIdx.x];
+  if (!active[wk.param]) return; // decimation: dft.cpp:259
+  const DftParams<T> &q = params[wk.param];
+  const long long e = wk.e0 + threadIdx.x;
+  if (e >= q.N * q.Nomega) return;
+  const long long pt = e / q.Nomega;
+  const int iw = (int)(e - pt * q.Nomega);
+  const int n2 = q.n[1], n3 = q.n[2];
+  const int i3 = (int)(pt % n3);
+  const long long r = pt / n3;
+  const int i2 = (int)(r % n2), i1 = (int)(r / n2);
+  const long long idx = q.idx0 + i1 * q.st[0] + i2 * q.st[1] + i3 * q.st[2];
+  double w;
+  if (q.include_dV) { // IVEC_LOOP_WEIGHT, vec.hpp:372-383
+    const int li[3] = {i1, i2, i3};
+    double w1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = li[k], n = q.n[k], dir = q.dir[k];
+      w1[k] = (i > 1 && i < n - 2)
+                  ? 1.0
+                  : (i == 0 ? q.s0[dir]
+                            : (i == 1 ? q.s1[dir]
+                                      : i == n - 1 ? q.e0[dir] : (i == n - 2 ? q.e1[dir] : 1.0)));
+    }
+    w = (w1[2] * (w1[1] * ((q.dV0 + q.dV1 * i2) * w1[0])));
+    if (q.sqrt_dV) w = sqrt(w);
+  }
+  else
+    w = 1.0;
+  T f[2];
+  const int numcmp = q.f1 ? 2 : 1;
+  for (int cmp = 0; cmp < numcmp; ++cmp) {
+    const T *ff = cmp ? q.f1 : q.f0;
+    if (q.avg2)
+      f[cmp] = (w * 0.25) * (ff[idx] + ff[idx + q.avg1] + ff[idx + q.avg2] + ff[idx + (q.avg1 + q.avg2)]);
+    else if (q.avg1)
+      f[cmp] = (w * 0.5) * (ff[idx] + ff[idx + q.avg1]);
+    else
+      f[cmp] = w * ff[idx];
+  }
+  const T *ph = phases + 2 * (phase_off[q.phase_group] + iw);
+  const T pr = ph[0], pi = ph[1];
+  T *d = q.dft + 2 * e;
+  if (numcmp == 2) { // complex<realnum> product, dft.cpp:295-299
+    d[0] = d[0] + (pr * f[0] - pi * f[1]);
+    d[1] = d[1] + (pr * f[1] + pi * f[0]);
+  }
+  else { // :300-305
+    d[0] = d[0] + f[0] * pr;
+    d[1] = d[1] + f[0] * pi;
+  }
+}
+
+// the per-step NaN test of step.cpp:138-139, over whole arrays, on demand
+template <class T> __global__ void k_nonfinite(const T *a, long long n, int *flag) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  int bad = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    if (!isfinite((double)a[i])) bad = 1;
+  if (bad) atomicOr(flag, 1);
+}
+
+} // namespace mcu

@@ -1,0 +1,1418 @@
+// meepcu.cu -- libmeepcuda.so: host side of the C ABI in include/meepcu.h.
+//
+// Owns the device mirrors of a `fields` object (reference src/meep.hpp:1461-1485,590-598),
+// turns the reference's per-chunk state into flat parameter / tile tables once
+// (meepcu_finalize), and then runs `fields::step()` (src/step.cpp:35-140) as a fixed sequence
+// of batched launches per time step:
+//
+//     k_half<B/H>  ->  k_conn(H)  ->  k_half<D/E>  ->  k_conn(E)  ->  k_dft
+//
+// (+ k_conn(D/P), k_fmp, k_eh_general only for chunks whose E update reads neighbours of D-P:
+// the fork's Newton-Raphson chi2 branch and the UPSTREAM_PADE mode.)  B/D/P halo copies that no
+// kernel consumes are deferred to meepcu_sync_to_host.
+//
+// There is NO CPU fallback: without a CUDA device every entry point that needs one fails with
+// MEEPCU_ECUDA.
+#include "../../include/meepcu.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace mcu;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(MEEPCU_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,  \
+                  __LINE__);                                                                       \
+  } while (0)
+#define RC(call)                                                                                   \
+  do {                                                                                             \
+    int rc_ = (call);                                                                              \
+    if (rc_ != MEEPCU_OK) return rc_;                                                              \
+  } while (0)
+
+// ---- component helpers (reference src/meep/vec.hpp:414-592, src/fields.cpp:411-425) -----------
+inline bool is_electric(int c) { return c < 5; }
+inline bool is_magnetic(int c) { return c >= 5 && c < 10; }
+inline bool is_D(int c) { return c >= 10 && c < 15; }
+inline bool is_B(int c) { return c >= 15 && c < 20; }
+inline int comp_ft(int c) { return is_electric(c) ? 0 : is_magnetic(c) ? 1 : is_D(c) ? 2 : 3; }
+inline int comp_dir(int c) {
+  static const int d[5] = {MEEPCU_X, MEEPCU_Y, MEEPCU_R, MEEPCU_P, MEEPCU_Z};
+  return d[c % 5];
+}
+inline int dir_comp(int ft, int d) { // direction_component(first_field_component(ft), d)
+  static const int off[3] = {0, 1, 4};
+  return 5 * ft + off[d];
+}
+
+enum ArrKind { A_GRID = 0, A_VEC = 1, A_DFT = 2 };
+
+struct ArrayRec {
+  const void *host;
+  char *dev;      // device base
+  int chunk;      // owning chunk (grid arrays)
+  int kind;
+  size_t n_host;  // host elements (A_DFT: complex elements)
+  size_t n_dev;   // device elements
+  bool mut;       // downloaded by sync_to_host
+  bool is_field;  // f[c][cmp] (NaN check)
+};
+
+struct Geom { // device layout of one chunk
+  int dim;
+  int num[3], io[3];
+  bool has[3];
+  long long hs[3]; // host strides X,Y,Z (grid_volume::stride)
+  long long ds[3]; // device strides X,Y,Z
+  int axis_of_dir[3]; // direction -> device axis (0=A,1=B,2=C), -1 if absent
+  int dir_of_axis[3]; // device axis -> direction, -1 if none
+  int nax[3];      // points per device axis
+  int pitch;
+  size_t ntot_host, ntot_dev;
+  int yee_shift(int c, int d) const {
+    if (!has[d]) return 0;
+    const int dc = comp_dir(c);
+    if ((is_electric(c) || is_D(c)) && d == dc) return 1;
+    if ((is_magnetic(c) || is_B(c)) && d != dc) return 1;
+    return 0;
+  }
+  bool has_field(int c) const {
+    if (dim == MEEPCU_D1) return c == 0 || c == 6 || c == 10 || c == 16;
+    return comp_dir(c) < MEEPCU_R;
+  }
+  long long dev_index(long long hidx) const { // host element index -> device element index
+    long long r = hidx, o = 0;
+    for (int d = 0; d < 3; ++d)
+      if (has[d]) {
+        long long q = r / hs[d];
+        r -= q * hs[d];
+        o += q * ds[d];
+      }
+    return o;
+  }
+  long long dev_offset(long long hoff) const { // signed relative offset (e.g. yee2cent avg1)
+    // decompose into per-direction steps of -1/0/+1 (offsets used by the reference are sums of
+    // +-stride(d) over distinct directions)
+    long long best = 0;
+    for (int sx = -1; sx <= 1; ++sx)
+      for (int sy = -1; sy <= 1; ++sy)
+        for (int sz = -1; sz <= 1; ++sz) {
+          if ((sx && !has[0]) || (sy && !has[1]) || (sz && !has[2])) continue;
+          if (sx * hs[0] + sy * hs[1] + sz * hs[2] == hoff) {
+            best = sx * ds[0] + sy * ds[1] + sz * ds[2];
+            return best;
+          }
+        }
+    return hoff == 0 ? 0 : (long long)1 << 62; // not representable
+  }
+};
+
+struct SuscH {
+  meepcu_susceptibility_desc d;
+};
+struct SrcH {
+  int ft, c, tid, integrated;
+  std::vector<long long> idx;
+  std::vector<double> amp;
+};
+struct DftH {
+  meepcu_dft_desc d;
+  std::vector<double> omega;
+  size_t N;
+  int phase_group;
+};
+struct ChunkH {
+  meepcu_chunk_desc d;
+  Geom g;
+  std::vector<SuscH> pol[2];
+  std::vector<SrcH> src;
+  std::vector<DftH> dft;
+  bool have_plus[20], have_minus[20];
+  int plus_c[20], minus_c[20], plus_d[20], minus_d[20];
+};
+struct PtrList {
+  std::vector<void *> dst;
+  std::vector<const void *> src;
+  std::vector<char> phases;
+};
+
+struct CtxBase {
+  meepcu_config cfg;
+  int t;
+  bool finalized;
+  virtual ~CtxBase() {}
+  virtual int add_chunk(const meepcu_chunk_desc *d, int *id) = 0;
+  virtual int add_susc(int chunk, const meepcu_susceptibility_desc *d) = 0;
+  virtual int add_source(int chunk, const meepcu_source_desc *d) = 0;
+  virtual int add_dft(int chunk, const meepcu_dft_desc *d, int *id) = 0;
+  virtual int set_metal(int ft, size_t n, void *const *ptrs) = 0;
+  virtual int add_conn(int ft, int kind, size_t n, void *const *dst, const void *const *src,
+                       const void *phases) = 0;
+  virtual int finalize() = 0;
+  virtual int step(int nsteps, int nsrc, const meepcu_src_sample *smp) = 0;
+  virtual int sync_to_host() = 0;
+  virtual int sync_from_host() = 0;
+  virtual int check_finite(int *ok) = 0;
+  virtual int read_value(const void *p, double *out) = 0;
+  virtual int get_stats(meepcu_stats *out) = 0;
+  virtual int get_timers(double out[22]) = 0;
+};
+
+template <class T> struct DevBuf { // simple growable device buffer
+  T *p;
+  size_t cap;
+  DevBuf() : p(0), cap(0) {}
+  int reserve(size_t n) {
+    if (n <= cap) return MEEPCU_OK;
+    if (p) cudaFree(p);
+    p = 0;
+    cap = 0;
+    CU(cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T)));
+    cap = n;
+    return MEEPCU_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = 0;
+    cap = 0;
+  }
+};
+
+template <class T> struct Ctx : CtxBase {
+  std::vector<ChunkH> chunks;
+  std::vector<void *> metal[MEEPCU_NUM_FIELD_TYPES];
+  PtrList conn[MEEPCU_NUM_FIELD_TYPES][3];
+
+  // ---- device state (valid after finalize) ----
+  std::map<const char *, ArrayRec> arrays; // by host base address
+  char *arena;
+  size_t arena_bytes;
+  cudaStream_t st;
+  cudaEvent_t ev0, ev1;
+  std::vector<char *> extra_dev; // other device allocations to free
+
+  // tables
+  HalfParams<T> *d_half;            // [nhalf]
+  std::vector<HalfParams<T> > h_half;
+  Tile *d_tiles[2][2];              // [half: 0=B/H 1=D/E][class: 0 simple 1 general]
+  int n_tiles[2][2];
+  EhParams<T> *d_eh;
+  std::vector<EhParams<T> > h_eh;
+  Tile *d_eh_tiles[2];
+  int n_eh_tiles[2];
+  FmpParams<T> *d_fmp[2];
+  int n_fmp[2];
+  bool fmp_has_src[2];
+  ConnTable<T> d_conn[MEEPCU_NUM_FIELD_TYPES][3];
+  T **d_zero[MEEPCU_NUM_FIELD_TYPES]; // unfused metal lists (only non-plane lists; normally empty)
+  long long n_zero[MEEPCU_NUM_FIELD_TYPES];
+  bool general_half[2];  // some chunk needs k_eh_general in this half
+  bool eager_db[2];      // exchange B / D halos every step
+  bool eager_p[2];       // exchange PH / PE halos every step
+  DftParams<T> *d_dft;
+  std::vector<DftParams<T> > h_dft;
+  std::vector<int> dft_decim, dft_is_h;
+  DftWork *d_dft_work;
+  int n_dft_work;
+  std::vector<int> phase_off;      // per group offset (complex elements) into a step's phase row
+  std::vector<std::vector<double> > group_omega;
+  std::vector<std::complex<double> > group_scale;
+  std::vector<int> group_is_h;
+  int phase_row;                   // complex elements per step
+  int *d_phase_off;
+  DevBuf<double> d_smp;
+  DevBuf<T> d_phases;
+  DevBuf<unsigned char> d_active;
+  int *d_flags; // [0] nr_fail, [1] nonfinite
+  SrcEntry *d_src;
+
+  int64_t launches, steps_done, cells, alg_bytes;
+  double last_ms;
+
+  Ctx() : arena(0), arena_bytes(0), st(0), ev0(0), ev1(0), d_half(0), d_eh(0), d_dft(0),
+          d_dft_work(0), n_dft_work(0), phase_row(0), d_phase_off(0), d_flags(0), d_src(0),
+          launches(0), steps_done(0), cells(0), alg_bytes(0), last_ms(0) {
+    memset(d_tiles, 0, sizeof d_tiles);
+    memset(n_tiles, 0, sizeof n_tiles);
+    memset(d_eh_tiles, 0, sizeof d_eh_tiles);
+    memset(n_eh_tiles, 0, sizeof n_eh_tiles);
+    memset(d_fmp, 0, sizeof d_fmp);
+    memset(n_fmp, 0, sizeof n_fmp);
+    memset(d_conn, 0, sizeof d_conn);
+    memset(d_zero, 0, sizeof d_zero);
+    memset(n_zero, 0, sizeof n_zero);
+    fmp_has_src[0] = fmp_has_src[1] = false;
+    general_half[0] = general_half[1] = false;
+    eager_db[0] = eager_db[1] = eager_p[0] = eager_p[1] = false;
+  }
+  ~Ctx() {
+    if (arena) cudaFree(arena);
+    for (size_t i = 0; i < extra_dev.size(); ++i) cudaFree(extra_dev[i]);
+    d_smp.release();
+    d_phases.release();
+    d_active.release();
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (st) cudaStreamDestroy(st);
+  }
+
+  // ------------------------------------------------------------------------------------------
+  int add_chunk(const meepcu_chunk_desc *d, int *id) {
+    if (finalized) return fail(MEEPCU_ESTATE, "context already finalized");
+    ChunkH ch;
+    ch.d = *d;
+    Geom &g = ch.g;
+    g.dim = cfg.dim;
+    g.has[0] = g.has[1] = (cfg.dim == MEEPCU_D2 || cfg.dim == MEEPCU_D3);
+    g.has[2] = (cfg.dim == MEEPCU_D1 || cfg.dim == MEEPCU_D3);
+    for (int k = 0; k < 3; ++k) {
+      g.num[k] = g.has[k] ? d->num[k] : 0;
+      g.io[k] = g.has[k] ? d->io[k] : 0;
+      if (g.num[k] < 0) return fail(MEEPCU_EINVAL, "negative grid size");
+    }
+    // host strides: set_strides, src/vec.cpp:482-494
+    g.hs[0] = g.hs[1] = g.hs[2] = 0;
+    if (g.has[2]) g.hs[2] = 1;
+    if (g.has[1]) g.hs[1] = g.num[2] + 1;
+    if (g.has[0]) g.hs[0] = (long long)(g.num[2] + 1) * (g.num[1] + 1);
+    g.ntot_host = 1;
+    for (int k = 0; k < 3; ++k)
+      if (g.has[k]) g.ntot_host *= (size_t)(g.num[k] + 1);
+    // device axes: existing directions by decreasing host stride, right-aligned on (A,B,C)
+    int dirs[3], nd = 0;
+    for (int k = 0; k < 3; ++k)
+      if (g.has[k]) dirs[nd++] = k; // X,Y,Z order == decreasing stride
+    for (int k = 0; k < 3; ++k) {
+      g.axis_of_dir[k] = -1;
+      g.dir_of_axis[k] = -1;
+      g.nax[k] = 1;
+      g.ds[k] = 0;
+    }
+    for (int j = 0; j < nd; ++j) {
+      const int ax = 3 - nd + j;
+      g.axis_of_dir[dirs[j]] = ax;
+      g.dir_of_axis[ax] = dirs[j];
+      g.nax[ax] = g.num[dirs[j]] + 1;
+    }
+    g.pitch = ((g.nax[2] + 31) / 32) * 32;
+    const long long sax[3] = {(long long)g.pitch * g.nax[1], (long long)g.pitch, 1};
+    for (int k = 0; k < 3; ++k)
+      if (g.has[k]) g.ds[k] = sax[g.axis_of_dir[k]];
+    g.ntot_dev = (size_t)g.pitch * g.nax[1] * g.nax[0];
+
+    // figure_out_step_plan, src/fields.cpp:441-469
+    for (int c = 0; c < 20; ++c) ch.have_plus[c] = ch.have_minus[c] = false;
+    for (int c1 = 0; c1 < 20; ++c1) {
+      if (!d->f[c1][0]) continue;
+      const int dc1 = comp_dir(c1);
+      if (dc1 >= MEEPCU_R) return fail(MEEPCU_EUNSUPPORTED, "cylindrical field component");
+      for (int c2 = 0; c2 < 20; ++c2) {
+        const bool pair = ((is_electric(c1) || is_D(c1)) && is_magnetic(c2)) ||
+                          ((is_magnetic(c1) || is_B(c1)) && is_electric(c2));
+        if (!pair) continue;
+        const int dc2 = comp_dir(c2);
+        if (dc2 >= MEEPCU_R || dc1 == dc2) continue;
+        const int dd = (3 + 2 * dc1 - dc2) % 3; // cross(dc1, dc2)
+        if (!(g.has_field(c2) && g.has_field(c1) && g.has[dd])) continue;
+        if (((3 + dc1 - dc2) % 3) == 2) { // cross_negative(dc2, dc1)
+          ch.minus_c[c1] = c2; ch.have_minus[c1] = true; ch.minus_d[c1] = dd;
+        }
+        else {
+          ch.plus_c[c1] = c2; ch.have_plus[c1] = true; ch.plus_d[c1] = dd;
+        }
+      }
+    }
+    chunks.push_back(ch);
+    if (id) *id = (int)chunks.size() - 1;
+    return MEEPCU_OK;
+  }
+  int add_susc(int chunk, const meepcu_susceptibility_desc *d) {
+    if (finalized) return fail(MEEPCU_ESTATE, "context already finalized");
+    if (chunk < 0 || chunk >= (int)chunks.size()) return fail(MEEPCU_EINVAL, "bad chunk id");
+    if (d->ft != MEEPCU_E_STUFF && d->ft != MEEPCU_H_STUFF)
+      return fail(MEEPCU_EINVAL, "susceptibility ft must be E_stuff or H_stuff");
+    SuscH s;
+    s.d = *d;
+    chunks[chunk].pol[d->ft].push_back(s);
+    if (chunks[chunk].pol[d->ft].size() > (size_t)kMaxPol)
+      return fail(MEEPCU_EUNSUPPORTED, "more than %d susceptibilities per chunk and field type", kMaxPol);
+    return MEEPCU_OK;
+  }
+  int add_source(int chunk, const meepcu_source_desc *d) {
+    if (finalized) return fail(MEEPCU_ESTATE, "context already finalized");
+    if (chunk < 0 || chunk >= (int)chunks.size()) return fail(MEEPCU_EINVAL, "bad chunk id");
+    if (d->ft != MEEPCU_D_STUFF && d->ft != MEEPCU_B_STUFF)
+      return fail(MEEPCU_EINVAL, "source ft must be D_stuff or B_stuff");
+    SrcH s;
+    s.ft = d->ft;
+    s.c = d->c;
+    s.tid = d->src_time_id;
+    s.integrated = d->is_integrated;
+    s.idx.assign(d->index, d->index + d->n);
+    s.amp.assign(d->amp, d->amp + 2 * d->n);
+    chunks[chunk].src.push_back(s);
+    return MEEPCU_OK;
+  }
+  int add_dft(int chunk, const meepcu_dft_desc *d, int *id) {
+    if (finalized) return fail(MEEPCU_ESTATE, "context already finalized");
+    if (chunk < 0 || chunk >= (int)chunks.size()) return fail(MEEPCU_EINVAL, "bad chunk id");
+    if (!d->dft) return fail(MEEPCU_EINVAL, "dft_chunk::dft host array required");
+    if (d->decimation_factor < 1) return fail(MEEPCU_EINVAL, "decimation_factor must be >= 1");
+    DftH f;
+    f.d = *d;
+    f.omega.assign(d->omega, d->omega + d->Nomega);
+    f.N = 1;
+    for (int k = 0; k < 3; ++k)
+      if (chunks[chunk].g.has[k]) f.N *= (size_t)((d->ie[k] - d->is[k]) / 2 + 1);
+    f.phase_group = -1;
+    chunks[chunk].dft.push_back(f);
+    if (id) *id = (int)chunks[chunk].dft.size() - 1;
+    return MEEPCU_OK;
+  }
+  int set_metal(int ft, size_t n, void *const *ptrs) {
+    if (finalized) return fail(MEEPCU_ESTATE, "context already finalized");
+    if (ft < 0 || ft >= MEEPCU_NUM_FIELD_TYPES) return fail(MEEPCU_EINVAL, "bad field type");
+    metal[ft].assign(ptrs, ptrs + n);
+    return MEEPCU_OK;
+  }
+  int add_conn(int ft, int kind, size_t n, void *const *dst, const void *const *src,
+               const void *phases) {
+    if (finalized) return fail(MEEPCU_ESTATE, "context already finalized");
+    if (ft < 0 || ft >= MEEPCU_NUM_FIELD_TYPES || kind < 0 || kind > 2)
+      return fail(MEEPCU_EINVAL, "bad connection family");
+    PtrList &c = conn[ft][kind];
+    c.dst.insert(c.dst.end(), dst, dst + n);
+    c.src.insert(c.src.end(), src, src + n);
+    if (kind == MEEPCU_CONNECT_PHASE) {
+      if (n % 2) return fail(MEEPCU_EINVAL, "PHASE connections come in (re,im) pairs");
+      const char *p = (const char *)phases;
+      c.phases.insert(c.phases.end(), p, p + (n / 2) * 2 * sizeof(T));
+    }
+    return MEEPCU_OK;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // array registry
+  int reg(const void *host, int chunk, int kind, size_t n_host, size_t n_dev, bool mut,
+          bool is_field = false) {
+    if (!host) return MEEPCU_OK;
+    const char *key = (const char *)host;
+    std::map<const char *, ArrayRec>::iterator it = arrays.find(key);
+    if (it != arrays.end()) {
+      if (it->second.n_host != n_host || it->second.kind != kind)
+        return fail(MEEPCU_EINVAL, "host array registered twice with different shapes");
+      it->second.mut = it->second.mut || mut;
+      it->second.is_field = it->second.is_field || is_field;
+      return MEEPCU_OK;
+    }
+    ArrayRec r = {host, 0, chunk, kind, n_host, n_dev, mut, is_field};
+    arrays[key] = r;
+    return MEEPCU_OK;
+  }
+  const ArrayRec *find(const void *p, size_t esz, size_t *elem) const {
+    if (!p) return 0;
+    std::map<const char *, ArrayRec>::const_iterator it = arrays.upper_bound((const char *)p);
+    if (it == arrays.begin()) return 0;
+    --it;
+    const size_t off = (const char *)p - it->first;
+    const size_t e = it->second.kind == A_DFT ? 2 * esz : esz;
+    if (off >= it->second.n_host * e) return 0;
+    if (elem) *elem = off / esz;
+    return &it->second;
+  }
+  T *dev(const void *host) const { // device base of a registered array (NULL stays NULL)
+    if (!host) return 0;
+    std::map<const char *, ArrayRec>::const_iterator it = arrays.find((const char *)host);
+    return it == arrays.end() ? 0 : (T *)it->second.dev;
+  }
+  // device address of one element given a host pointer into a registered GRID array
+  T *dev_elem(const void *p) const {
+    size_t e = 0;
+    const ArrayRec *r = find(p, sizeof(T), &e);
+    if (!r) return 0;
+    if (r->kind == A_GRID) return (T *)r->dev + chunks[r->chunk].g.dev_index((long long)e);
+    return (T *)r->dev + e;
+  }
+
+  int copy_array(const ArrayRec &r, bool to_host) {
+    if (r.kind == A_GRID) {
+      const Geom &g = chunks[r.chunk].g;
+      const size_t w = (size_t)g.nax[2] * sizeof(T), rows = (size_t)g.nax[0] * g.nax[1];
+      if (to_host)
+        CU(cudaMemcpy2DAsync((void *)r.host, w, r.dev, (size_t)g.pitch * sizeof(T), w, rows,
+                             cudaMemcpyDeviceToHost, st));
+      else
+        CU(cudaMemcpy2DAsync(r.dev, (size_t)g.pitch * sizeof(T), r.host, w, w, rows,
+                             cudaMemcpyHostToDevice, st));
+    }
+    else {
+      const size_t nb = r.n_host * sizeof(T) * (r.kind == A_DFT ? 2 : 1);
+      if (to_host)
+        CU(cudaMemcpyAsync((void *)r.host, r.dev, nb, cudaMemcpyDeviceToHost, st));
+      else
+        CU(cudaMemcpyAsync(r.dev, r.host, nb, cudaMemcpyHostToDevice, st));
+    }
+    return MEEPCU_OK;
+  }
+
+  template <class U> int upload(const std::vector<U> &v, U **out) {
+    *out = 0;
+    if (v.empty()) return MEEPCU_OK;
+    CU(cudaMalloc((void **)out, v.size() * sizeof(U)));
+    extra_dev.push_back((char *)*out);
+    CU(cudaMemcpy(*out, v.data(), v.size() * sizeof(U), cudaMemcpyHostToDevice));
+    return MEEPCU_OK;
+  }
+
+  // metal lists -> per-(array) plane masks; returns EUNSUPPORTED if a list is not a union of
+  // boundary planes of the owned region (it always is: boundaries.cpp:309-339 lists the owned
+  // points with IVEC_LOOP_AT_BOUNDARY that on_metal_boundary() accepts, i.e. whole faces)
+  int metal_masks(std::map<const char *, unsigned> &mask) {
+    for (int ft = 0; ft < MEEPCU_NUM_FIELD_TYPES; ++ft) {
+      if (metal[ft].empty()) continue;
+      // group by array
+      std::map<const char *, std::vector<long long> > by;
+      for (size_t k = 0; k < metal[ft].size(); ++k) {
+        size_t e = 0;
+        const ArrayRec *r = find(metal[ft][k], sizeof(T), &e);
+        if (!r || r->kind != A_GRID || !r->is_field)
+          return fail(MEEPCU_EINVAL, "metal pointer %zu of field type %d is not inside a field array", k, ft);
+        by[(const char *)r->host].push_back((long long)e);
+      }
+      for (std::map<const char *, std::vector<long long> >::iterator it = by.begin(); it != by.end(); ++it) {
+        const ArrayRec &r = arrays[it->first];
+        const ChunkH &ch = chunks[r.chunk];
+        const Geom &g = ch.g;
+        // which component is this array?  (needed for the owned range)
+        int comp = -1;
+        for (int c = 0; c < 20 && comp < 0; ++c)
+          for (int cmp = 0; cmp < 2; ++cmp)
+            if (ch.d.f[c][cmp] == r.host && comp_ft(c) == ft) comp = c;
+        if (comp < 0) return fail(MEEPCU_EINVAL, "metal list of field type %d refers to a foreign array", ft);
+        int lo[3], hi[3]; // owned range per direction (host index units)
+        for (int d = 0; d < 3; ++d) {
+          lo[d] = g.has[d] ? 1 - g.yee_shift(comp, d) : 0;
+          hi[d] = g.has[d] ? g.num[d] - g.yee_shift(comp, d) : 0;
+        }
+        long long cnt[6] = {0, 0, 0, 0, 0, 0};
+        std::vector<int> xyz(3 * it->second.size());
+        for (size_t k = 0; k < it->second.size(); ++k) {
+          long long rem = it->second[k];
+          for (int d = 0; d < 3; ++d) {
+            int q = 0;
+            if (g.has[d]) { q = (int)(rem / g.hs[d]); rem -= q * g.hs[d]; }
+            xyz[3 * k + d] = q;
+            if (g.has[d] && q == lo[d]) cnt[d]++;
+            if (g.has[d] && q == hi[d]) cnt[3 + d]++;
+          }
+        }
+        unsigned m = 0;
+        for (int d = 0; d < 3; ++d) {
+          if (!g.has[d]) continue;
+          long long face = 1;
+          for (int e = 0; e < 3; ++e)
+            if (e != d && g.has[e]) face *= (hi[e] - lo[e] + 1);
+          const int ax = g.axis_of_dir[d];
+          if (cnt[d] == face && lo[d] != hi[d]) m |= 1u << ax;
+          if (cnt[3 + d] == face) m |= 1u << (3 + ax);
+        }
+        for (size_t k = 0; k < it->second.size(); ++k) {
+          bool covered = false;
+          for (int d = 0; d < 3; ++d) {
+            if (!g.has[d]) continue;
+            const int ax = g.axis_of_dir[d];
+            if ((m & (1u << ax)) && xyz[3 * k + d] == lo[d]) covered = true;
+            if ((m & (1u << (3 + ax))) && xyz[3 * k + d] == hi[d]) covered = true;
+          }
+          if (!covered)
+            return fail(MEEPCU_EUNSUPPORTED, "metal point list is not a union of boundary faces");
+        }
+        mask[it->first] = m;
+      }
+    }
+    return MEEPCU_OK;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  int finalize() {
+    if (finalized) return fail(MEEPCU_ESTATE, "context already finalized");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      return fail(MEEPCU_ECUDA, "no CUDA device: libmeepcuda has no CPU fallback");
+    CU(cudaSetDevice(cfg.device));
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&ev0));
+    CU(cudaEventCreate(&ev1));
+    if (cfg.dim == MEEPCU_D2 && cfg.beta != 0)
+      return fail(MEEPCU_EUNSUPPORTED, "beta != 0 (step_beta) is not on the GPU path yet");
+
+    // ---- 1. register every array ----
+    for (size_t ic = 0; ic < chunks.size(); ++ic) {
+      ChunkH &ch = chunks[ic];
+      const Geom &g = ch.g;
+      const size_t nh = g.ntot_host, nd = g.ntot_dev;
+      for (int c = 0; c < 20; ++c) {
+        for (int cmp = 0; cmp < 2; ++cmp) {
+          RC(reg(ch.d.f[c][cmp], (int)ic, A_GRID, nh, nd, true, true));
+          RC(reg(ch.d.f_u[c][cmp], (int)ic, A_GRID, nh, nd, true));
+          RC(reg(ch.d.f_w[c][cmp], (int)ic, A_GRID, nh, nd, true));
+          RC(reg(ch.d.f_cond[c][cmp], (int)ic, A_GRID, nh, nd, true));
+        }
+        for (int d = 0; d < 5; ++d) {
+          RC(reg(ch.d.chi1inv[c][d], (int)ic, A_GRID, nh, nd, false));
+          RC(reg(ch.d.conductivity[c][d], (int)ic, A_GRID, nh, nd, false));
+          RC(reg(ch.d.condinv[c][d], (int)ic, A_GRID, nh, nd, false));
+        }
+        RC(reg(ch.d.chi2[c], (int)ic, A_GRID, nh, nd, false));
+        RC(reg(ch.d.chi3[c], (int)ic, A_GRID, nh, nd, false));
+      }
+      for (int d = 0; d < 3; ++d)
+        if (ch.d.sigsize[d] > 1) {
+          if (!ch.d.sig[d] || !ch.d.kap[d] || !ch.d.siginv[d])
+            return fail(MEEPCU_EINVAL, "sigsize > 1 but sig/kap/siginv missing");
+          RC(reg(ch.d.sig[d], (int)ic, A_VEC, ch.d.sigsize[d], ch.d.sigsize[d], false));
+          RC(reg(ch.d.kap[d], (int)ic, A_VEC, ch.d.sigsize[d], ch.d.sigsize[d], false));
+          RC(reg(ch.d.siginv[d], (int)ic, A_VEC, ch.d.sigsize[d], ch.d.sigsize[d], false));
+        }
+      for (int k = 0; k < 2; ++k)
+        for (size_t ip = 0; ip < ch.pol[k].size(); ++ip) {
+          const meepcu_susceptibility_desc &sd = ch.pol[k][ip].d;
+          for (int c = 0; c < 20; ++c) {
+            for (int d = 0; d < 5; ++d) RC(reg(sd.sigma[c][d], (int)ic, A_GRID, nh, nd, false));
+            for (int cmp = 0; cmp < 2; ++cmp) {
+              if ((sd.P[c][cmp] != 0) != (sd.P_prev[c][cmp] != 0))
+                return fail(MEEPCU_EINVAL, "P and P_prev must both be given");
+              RC(reg(sd.P[c][cmp], (int)ic, A_GRID, nh, nd, true));
+              RC(reg(sd.P_prev[c][cmp], (int)ic, A_GRID, nh, nd, true));
+            }
+          }
+        }
+      for (size_t id = 0; id < ch.dft.size(); ++id) {
+        const size_t n = ch.dft[id].N * ch.dft[id].d.Nomega;
+        RC(reg(ch.dft[id].d.dft, (int)ic, A_DFT, n, n, true));
+      }
+    }
+    // ---- 2. one arena ----
+    size_t total = 0;
+    for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it) {
+      const size_t nb = it->second.n_dev * sizeof(T) * (it->second.kind == A_DFT ? 2 : 1);
+      it->second.dev = (char *)total; // offset for now
+      total += (nb + 255) & ~(size_t)255;
+    }
+    arena_bytes = total + 256;
+    CU(cudaMalloc((void **)&arena, arena_bytes));
+    CU(cudaMemsetAsync(arena, 0, arena_bytes, st));
+    for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it)
+      it->second.dev = arena + (size_t)it->second.dev;
+    CU(cudaMalloc((void **)&d_flags, 4 * sizeof(int)));
+    extra_dev.push_back((char *)d_flags);
+    CU(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), st));
+    RC(sync_from_host());
+
+    // ---- 3. metal planes ----
+    std::map<const char *, unsigned> zmask;
+    RC(metal_masks(zmask));
+
+    // ---- 4. sources -> sorted device tables ----
+    std::vector<SrcEntry> all_src;
+    struct SrcRange { size_t c0, c1, i0, i1; int ca0, ca1, ia0, ia1; };
+    // per chunk, per half (0:B 1:D), per comp k, per cmp-independent
+    std::vector<SrcRange> ranges(chunks.size() * 2 * 3);
+    for (size_t ic = 0; ic < chunks.size(); ++ic) {
+      ChunkH &ch = chunks[ic];
+      const Geom &g = ch.g;
+      for (int half = 0; half < 2; ++half) {
+        const int ft2 = half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF;
+        const int ft = half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF;
+        for (int k = 0; k < 3; ++k) {
+          SrcRange &R = ranges[(ic * 2 + half) * 3 + k];
+          for (int pass = 0; pass < 2; ++pass) { // 0: currents, 1: integrated
+            std::vector<SrcEntry> tmp;
+            for (size_t is = 0; is < ch.src.size(); ++is) {
+              const SrcH &s = ch.src[is];
+              if (s.ft != ft2 || comp_dir(s.c) != k) continue;
+              if (comp_dir(s.c) >= MEEPCU_R) return fail(MEEPCU_EUNSUPPORTED, "cylindrical source");
+              bool use;
+              if (pass == 0) // step.cpp:301-302
+                use = !s.integrated && ch.d.f[dir_comp(ft2, k)][0] &&
+                      ((ft2 == MEEPCU_D_STUFF && is_electric(s.c)) ||
+                       (ft2 == MEEPCU_B_STUFF && is_magnetic(s.c)));
+              else // update_eh.cpp:138
+                use = s.integrated && ch.d.f[s.c][0] && ft == comp_ft(s.c);
+              if (!use) continue;
+              for (size_t j = 0; j < s.idx.size(); ++j) {
+                if (s.idx[j] < 0 || (size_t)s.idx[j] >= g.ntot_host)
+                  return fail(MEEPCU_EINVAL, "source index out of range");
+                SrcEntry e;
+                e.idx = g.dev_index(s.idx[j]);
+                e.are = s.amp[2 * j];
+                e.aim = s.amp[2 * j + 1];
+                e.tid = s.tid;
+                e.pad = 0;
+                tmp.push_back(e);
+              }
+            }
+            std::stable_sort(tmp.begin(), tmp.end(),
+                             [](const SrcEntry &a, const SrcEntry &b) { return a.idx < b.idx; });
+            int amin = 1 << 30, amax = -1;
+            const long long sA = (long long)g.pitch * g.nax[1];
+            for (size_t j = 0; j < tmp.size(); ++j) {
+              const int ia = (int)(tmp[j].idx / sA);
+              amin = std::min(amin, ia);
+              amax = std::max(amax, ia);
+            }
+            if (pass == 0) { R.c0 = all_src.size(); R.c1 = R.c0 + tmp.size(); R.ca0 = amin; R.ca1 = amax; }
+            else { R.i0 = all_src.size(); R.i1 = R.i0 + tmp.size(); R.ia0 = amin; R.ia1 = amax; }
+            all_src.insert(all_src.end(), tmp.begin(), tmp.end());
+          }
+        }
+      }
+    }
+    RC(upload(all_src, &d_src));
+
+    // ---- 5. per-(chunk, half, cmp) parameter blocks + tiles ----
+    std::vector<Tile> tiles[2][2], eh_tiles[2];
+    std::vector<FmpParams<T> > fmps[2];
+    const int ncmp = cfg.is_real ? 1 : 2;
+    cells = 0;
+    alg_bytes = 0;
+    for (size_t ic = 0; ic < chunks.size(); ++ic) {
+      ChunkH &ch = chunks[ic];
+      const Geom &g = ch.g;
+      long long nc = 1;
+      for (int d = 0; d < 3; ++d)
+        if (g.has[d]) nc *= g.num[d];
+      cells += nc;
+      for (int half = 0; half < 2; ++half) {
+        const int ft2 = half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF;
+        const int ft = half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF;
+        // does update_eh need f_minus_p in this chunk? (update_eh.cpp:71-112)
+        bool have_int_sources = false;
+        for (size_t is = 0; is < ch.src.size(); ++is)
+          if (ch.src[is].ft == ft2 && ch.src[is].integrated) have_int_sources = true;
+        // classify the E/H update of this chunk
+        bool general = false;
+        for (int k = 0; k < 3; ++k) {
+          const int ec = dir_comp(ft, k);
+          if (!ch.d.f[ec][0]) continue;
+          const int d1 = (k + 1) % 3, d2 = (k + 2) % 3;
+          const bool pml = ch.d.sigsize[k] > 1;
+          const void *u1 = ch.d.f[dir_comp(ft2, d1)][0] ? ch.d.chi1inv[ec][d1] : 0;
+          const void *u2 = ch.d.f[dir_comp(ft2, d2)][0] ? ch.d.chi1inv[ec][d2] : 0;
+          if (cfg.nl_mode == MEEPCU_NL_UPSTREAM_PADE) {
+            if (u1 || u2 || ch.d.chi3[ec]) general = true;
+          }
+          else if (!pml && u1 && u2 && ch.d.chi3[ec])
+            general = true;
+          for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip) {
+            const meepcu_susceptibility_desc &sd = ch.pol[ft][ip].d;
+            for (int cmp = 0; cmp < ncmp; ++cmp)
+              if (sd.P[ec][cmp] && sd.sigma[ec][k] &&
+                  ((sd.sigma[ec][d1] && ch.d.f[dir_comp(ft, d1)][cmp]) ||
+                   (sd.sigma[ec][d2] && ch.d.f[dir_comp(ft, d2)][cmp])))
+                return fail(MEEPCU_EUNSUPPORTED,
+                            "anisotropic susceptibility sigma (susceptibility.cpp:225-251) is not on the GPU path yet");
+          }
+        }
+        if (general) {
+          general_half[half] = true;
+          eager_db[half] = true;
+          if (!ch.pol[ft].empty()) eager_p[half] = true;
+        }
+        for (int cmp = 0; cmp < ncmp; ++cmp) {
+          HalfParams<T> P;
+          memset(&P, 0, sizeof P);
+          P.nA = g.nax[0]; P.nB = g.nax[1]; P.nC = g.nax[2]; P.pitch = g.pitch;
+          P.sA = (long long)g.pitch * g.nax[1];
+          P.sB = g.pitch;
+          P.is_D = half;
+          P.cmp = cmp;
+          P.dt = cfg.dt;
+          bool any = false, simple = true;
+          for (int k = 0; k < 3; ++k) {
+            CompParams<T> &c = P.comp[k];
+            c.kaxis = c.kuaxis = c.kwaxis = -1;
+            const int cc = dir_comp(ft2, k), ec = dir_comp(ft, k);
+            if (!ch.d.f[cc][cmp]) continue;
+            const bool have_p = ch.have_plus[cc], have_m = ch.have_minus[cc];
+            const T *f_p = have_p ? dev(ch.d.f[ch.plus_c[cc]][cmp]) : 0;
+            const T *f_m = have_m ? dev(ch.d.f[ch.minus_c[cc]][cmp]) : 0;
+            if (!f_p && !f_m) continue;
+            any = true;
+            long long sp = have_p ? g.ds[ch.plus_d[cc]] : 0, sm = have_m ? g.ds[ch.minus_d[cc]] : 0;
+            if (half) { sp = -sp; sm = -sm; } // step_db.cpp:81-84
+            T dtdx = (T)cfg.courant;
+            if (!f_p) { std::swap(f_p, f_m); std::swap(sp, sm); dtdx = -dtdx; } // step_generic.cpp:76-80
+            c.f = dev(ch.d.f[cc][cmp]);
+            c.g1 = f_p; c.g2 = f_m; c.s1 = sp; c.s2 = sm;
+            c.dtdx = dtdx;
+            c.dt2 = (T)((T)cfg.dt * 0.5);
+            for (int ax = 0; ax < 3; ++ax) {
+              const int d = g.dir_of_axis[ax];
+              c.lo[ax] = d < 0 ? 0 : 1 - g.yee_shift(cc, d);
+              c.hi[ax] = d < 0 ? 0 : g.num[d] - g.yee_shift(cc, d);
+            }
+            const int dsig0 = (k + 1) % 3, dsigu0 = (k + 2) % 3;
+            const bool dsig = ch.d.sigsize[dsig0] > 1, dsigu = ch.d.sigsize[dsigu0] > 1;
+            if ((dsig && !g.has[dsig0]) || (dsigu && !g.has[dsigu0]))
+              return fail(MEEPCU_EINVAL, "PML in a direction the grid does not have");
+            c.cnd = dev(ch.d.conductivity[cc][k]);
+            c.cndinv = dev(ch.d.condinv[cc][k]);
+            if (c.cnd && !c.cndinv) return fail(MEEPCU_EINVAL, "conductivity without condinv (update_condinv)");
+            if (dsig) {
+              c.kaxis = g.axis_of_dir[dsig0];
+              c.koff = g.yee_shift(cc, dsig0);
+              c.sig = dev(ch.d.sig[dsig0]); c.kap = dev(ch.d.kap[dsig0]); c.siginv = dev(ch.d.siginv[dsig0]);
+              if (c.cnd) {
+                c.fcnd = dev(ch.d.f_cond[cc][cmp]);
+                if (!c.fcnd) return fail(MEEPCU_ESTATE, "f_cond not allocated (step_db.cpp:67-70)");
+              }
+            }
+            if (dsigu) {
+              c.kuaxis = g.axis_of_dir[dsigu0];
+              c.kuoff = g.yee_shift(cc, dsigu0);
+              c.sigu = dev(ch.d.sig[dsigu0]); c.kapu = dev(ch.d.kap[dsigu0]); c.siginvu = dev(ch.d.siginv[dsigu0]);
+              c.fu = dev(ch.d.f_u[cc][cmp]);
+              if (!c.fu) return fail(MEEPCU_ESTATE, "f_u not allocated (step_db.cpp:71-75)");
+            }
+            std::map<const char *, unsigned>::iterator zm = zmask.find((const char *)ch.d.f[cc][cmp]);
+            c.zmask_db = zm == zmask.end() ? 0u : zm->second;
+            const SrcRange &R = ranges[(ic * 2 + half) * 3 + k];
+            c.csrc = d_src + R.c0; c.ncsrc = (int)(R.c1 - R.c0); c.csrc_amin = R.ca0; c.csrc_amax = R.ca1;
+            c.src_has_cndinv = c.cndinv != 0;
+            if (dsig || dsigu || c.cnd) simple = false;
+
+            // ---- E/H part ----
+            if (!ch.d.f[ec][cmp]) continue;
+            const bool pml_w = ch.d.sigsize[k] > 1;
+            bool need_fmp = have_int_sources;
+            for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip)
+              if (ch.pol[ft][ip].d.P[ec][cmp]) need_fmp = true;
+            if (ch.d.f[ec][cmp] == ch.d.f[cc][cmp]) { // H aliases B
+              if (ch.d.chi1inv[ec][k] || need_fmp || pml_w)
+                return fail(MEEPCU_ESTATE, "H aliases B where update_eh.cpp:204-209 would split them");
+              continue;
+            }
+            if (general) continue; // done by k_eh_general after the D halo exchange
+            c.e = dev(ch.d.f[ec][cmp]);
+            c.u = dev(ch.d.chi1inv[ec][k]);
+            if (pml_w) {
+              c.fw = dev(ch.d.f_w[ec][cmp]);
+              if (!c.fw) return fail(MEEPCU_ESTATE, "f_w not allocated (update_eh.cpp:212-216)");
+              c.kwaxis = g.axis_of_dir[k];
+              c.kwoff = g.yee_shift(ec, k);
+              c.sigw = dev(ch.d.sig[k]); c.kapw = dev(ch.d.kap[k]);
+              simple = false;
+            }
+            zm = zmask.find((const char *)ch.d.f[ec][cmp]);
+            c.zmask_eh = zm == zmask.end() ? 0u : zm->second;
+            c.isrc = d_src + R.i0; c.nisrc = (int)(R.i1 - R.i0); c.isrc_amin = R.ia0; c.isrc_amax = R.ia1;
+            c.npol = (int)ch.pol[ft].size();
+            if (c.npol) simple = false;
+            RC(fill_pols(ch, ft, ec, k, cmp, c.pol));
+          }
+          if (!any) continue;
+          const int pidx = (int)h_half.size();
+          h_half.push_back(P);
+          // tiles: 256 plane positions x a segment of A
+          const int plane = g.nax[1] * g.pitch;
+          int seg = 32;
+          if (g.nax[0] <= 48) seg = g.nax[0];
+          for (int a0 = 0; a0 < g.nax[0]; a0 += seg)
+            for (int p0 = 0; p0 < plane; p0 += kThreads) {
+              Tile t = {pidx, a0, std::min(a0 + seg, g.nax[0]), p0};
+              tiles[half][simple ? 0 : 1].push_back(t);
+            }
+          // algorithmic bytes: every array element once per read and once per write
+          for (int k = 0; k < 3; ++k) {
+            const CompParams<T> &c = P.comp[k];
+            if (!c.f) continue;
+            int v = 3; // R g (one compulsory read of each curl operand is counted with its own
+                       // component below: 2 operands ~ 1 per component on average), R+W f
+            if (c.fu) v += 2;
+            if (c.fcnd) v += 2;
+            if (c.cnd) v += 2;
+            if (c.e) {
+              v += 1;
+              if (c.u) v += 1;
+              if (c.fw) v += 3; // R+W fw, E becomes RMW
+              for (int ip = 0; ip < c.npol; ++ip) {
+                if (c.pol[ip].p) v += 1;
+                if (c.pol[ip].p && c.pol[ip].s) v += 4;
+              }
+            }
+            alg_bytes += (long long)v * nc * (long long)sizeof(T);
+          }
+        }
+        // ---- general E/H components of this chunk ----
+        if (general) {
+          for (int cmp = 0; cmp < ncmp; ++cmp) {
+            const T *dmp[3] = {0, 0, 0};
+            for (int k = 0; k < 3; ++k) {
+              const int dc = dir_comp(ft2, k), ec = dir_comp(ft, k);
+              if (!ch.d.f[dc][cmp]) continue;
+              bool need_fmp = false;
+              if (ch.d.f[ec][cmp]) {
+                need_fmp = have_int_sources;
+                for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip)
+                  if (ch.pol[ft][ip].d.P[ec][cmp]) need_fmp = true;
+              }
+              if (need_fmp) {
+                T *scratch = 0;
+                CU(cudaMalloc((void **)&scratch, g.ntot_dev * sizeof(T)));
+                extra_dev.push_back((char *)scratch);
+                CU(cudaMemset(scratch, 0, g.ntot_dev * sizeof(T)));
+                FmpParams<T> F;
+                memset(&F, 0, sizeof F);
+                F.fmp = scratch;
+                F.d = dev(ch.d.f[dc][cmp]);
+                F.npol = (int)ch.pol[ft].size();
+                for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip) F.p[ip] = dev(ch.pol[ft][ip].d.P[ec][cmp]);
+                F.n = (long long)g.ntot_dev;
+                const SrcRange &R = ranges[(ic * 2 + half) * 3 + k];
+                // the fused tables are sorted by index; k_fmp_src needs reference order only per
+                // index, which stable sorting preserved
+                F.isrc = d_src + R.i0;
+                F.nisrc = (int)(R.i1 - R.i0);
+                if (F.nisrc) fmp_has_src[half] = true;
+                F.is_D = half;
+                F.cmp = cmp;
+                fmps[half].push_back(F);
+                dmp[k] = scratch;
+              }
+              else
+                dmp[k] = dev(ch.d.f[dc][cmp]);
+            }
+            for (int k = 0; k < 3; ++k) {
+              const int dc = dir_comp(ft2, k), ec = dir_comp(ft, k);
+              if (!ch.d.f[ec][cmp] || ch.d.f[ec][cmp] == ch.d.f[dc][cmp]) continue;
+              EhParams<T> E;
+              memset(&E, 0, sizeof E);
+              E.nA = g.nax[0]; E.nB = g.nax[1]; E.nC = g.nax[2]; E.pitch = g.pitch;
+              E.sA = (long long)g.pitch * g.nax[1]; E.sB = g.pitch;
+              for (int ax = 0; ax < 3; ++ax) {
+                const int d = g.dir_of_axis[ax];
+                E.lo[ax] = d < 0 ? 0 : 1 - g.yee_shift(ec, d);
+                E.hi[ax] = d < 0 ? 0 : g.num[d] - g.yee_shift(ec, d);
+              }
+              const int d1 = (k + 1) % 3, d2 = (k + 2) % 3;
+              const int sgn = ft == MEEPCU_H_STUFF ? -1 : +1;
+              E.f = dev(ch.d.f[ec][cmp]);
+              E.fc = ec;
+              E.g = dmp[k]; E.g1 = dmp[d1]; E.g2 = dmp[d2];
+              E.u = dev(ch.d.chi1inv[ec][k]);
+              E.u1 = E.g1 ? dev(ch.d.chi1inv[ec][d1]) : 0;
+              E.u2 = E.g2 ? dev(ch.d.chi1inv[ec][d2]) : 0;
+              E.s = g.ds[k] * sgn; E.s1 = g.ds[d1] * sgn; E.s2 = g.ds[d2] * sgn;
+              if ((!E.g1 && E.g2) || (E.g1 && E.g2 && !E.u1 && E.u2)) { // step_generic.cpp:590-594
+                std::swap(E.g1, E.g2); std::swap(E.u1, E.u2); std::swap(E.s1, E.s2);
+              }
+              if (!E.u1 && E.u2) return fail(MEEPCU_EINVAL, "bug - didn't swap off-diagonal terms!?");
+              E.chi2 = dev(ch.d.chi2[ec]);
+              E.chi3 = dev(ch.d.chi3[ec]);
+              if ((E.u1 || E.chi3) && !E.u)
+                return fail(MEEPCU_EINVAL, "chi1inv diagonal missing where the reference dereferences it");
+              if (E.chi3 && !E.chi2 && (cfg.nl_mode == MEEPCU_NL_UPSTREAM_PADE || (E.u1 && E.u2)))
+                return fail(MEEPCU_EINVAL, "chi3 without chi2 (the reference dereferences chi2)");
+              if (cfg.nl_mode == MEEPCU_NL_FORK_LITERAL && E.u1 && E.u2 && E.chi3 && ch.d.sigsize[k] <= 1 &&
+                  !(ec == 0 || ec == 1 || ec == 4))
+                return fail(MEEPCU_EUNSUPPORTED, "NR branch reached for a non-E component (step_generic.cpp:808-811)");
+              if (ch.d.sigsize[k] > 1) {
+                E.fw = dev(ch.d.f_w[ec][cmp]);
+                if (!E.fw) return fail(MEEPCU_ESTATE, "f_w not allocated (update_eh.cpp:212-216)");
+                E.kwaxis = g.axis_of_dir[k];
+                E.kwoff = g.yee_shift(ec, k);
+                E.sigw = dev(ch.d.sig[k]); E.kapw = dev(ch.d.kap[k]);
+              }
+              E.nl_mode = cfg.nl_mode;
+              std::map<const char *, unsigned>::iterator zm = zmask.find((const char *)ch.d.f[ec][cmp]);
+              E.zmask_eh = zm == zmask.end() ? 0u : zm->second;
+              E.npol = (int)ch.pol[ft].size();
+              RC(fill_pols(ch, ft, ec, k, cmp, E.pol));
+              E.nr_fail = d_flags;
+              const int eidx = (int)h_eh.size();
+              h_eh.push_back(E);
+              const int plane = g.nax[1] * g.pitch;
+              int seg = g.nax[0] <= 48 ? g.nax[0] : 32;
+              for (int a0 = 0; a0 < g.nax[0]; a0 += seg)
+                for (int p0 = 0; p0 < plane; p0 += kThreads) {
+                  Tile t = {eidx, a0, std::min(a0 + seg, g.nax[0]), p0};
+                  eh_tiles[half].push_back(t);
+                }
+              alg_bytes += (long long)(4 + (E.fw ? 3 : 0)) * nc * (long long)sizeof(T);
+            }
+          }
+        }
+      }
+    }
+    RC(upload(h_half, &d_half));
+    RC(upload(h_eh, &d_eh));
+    for (int half = 0; half < 2; ++half) {
+      for (int cl = 0; cl < 2; ++cl) {
+        n_tiles[half][cl] = (int)tiles[half][cl].size();
+        RC(upload(tiles[half][cl], &d_tiles[half][cl]));
+      }
+      n_eh_tiles[half] = (int)eh_tiles[half].size();
+      RC(upload(eh_tiles[half], &d_eh_tiles[half]));
+      n_fmp[half] = (int)fmps[half].size();
+      RC(upload(fmps[half], &d_fmp[half]));
+    }
+
+    // ---- 6. connections ----
+    for (int ft = 0; ft < MEEPCU_NUM_FIELD_TYPES; ++ft)
+      for (int kind = 0; kind < 3; ++kind) {
+        const PtrList &L = conn[ft][kind];
+        ConnTable<T> &C = d_conn[ft][kind];
+        memset(&C, 0, sizeof C);
+        if (L.dst.empty()) continue;
+        std::vector<T *> hd(L.dst.size());
+        std::vector<const T *> hsrc(L.src.size());
+        for (size_t n = 0; n < L.dst.size(); ++n) {
+          hd[n] = dev_elem(L.dst[n]);
+          hsrc[n] = dev_elem(L.src[n]);
+          if (!hd[n] || !hsrc[n])
+            return fail(MEEPCU_EINVAL, "connection %zu of field type %d points outside the registered arrays", n, ft);
+        }
+        T **dd = 0;
+        const T **dsrc = 0;
+        RC(upload(hd, &dd));
+        RC(upload(hsrc, &dsrc));
+        C.dst = dd;
+        C.src = dsrc;
+        C.n = (long long)L.dst.size();
+        if (kind == MEEPCU_CONNECT_PHASE) {
+          std::vector<T> ph((const T *)L.phases.data(), (const T *)(L.phases.data() + L.phases.size()));
+          T *dph = 0;
+          RC(upload(ph, &dph));
+          C.phase = dph;
+        }
+      }
+    // W exchanges are only non-empty for anisotropic susceptibilities (rejected above)
+
+    // ---- 7. DFT chunks ----
+    std::vector<DftWork> work;
+    phase_row = 0;
+    for (size_t ic = 0; ic < chunks.size(); ++ic) {
+      ChunkH &ch = chunks[ic];
+      const Geom &g = ch.g;
+      for (size_t id = 0; id < ch.dft.size(); ++id) {
+        DftH &D = ch.dft[id];
+        const meepcu_dft_desc &d = D.d;
+        if (d.c < 0 || d.c >= 20 || !ch.d.f[d.c][0]) continue; // dft.cpp:266
+        if (is_D(d.c)) eager_db[1] = true;
+        if (is_B(d.c)) eager_db[0] = true;
+        const bool is_h = is_magnetic(d.c) || is_B(d.c);
+        // phase group (same omega list, scale and sampling time share one phase row)
+        int grp = -1;
+        for (size_t k = 0; k < group_omega.size(); ++k)
+          if (group_is_h[k] == (int)is_h && group_scale[k] == std::complex<double>(d.scale[0], d.scale[1]) &&
+              group_omega[k] == D.omega)
+            grp = (int)k;
+        if (grp < 0) {
+          grp = (int)group_omega.size();
+          group_omega.push_back(D.omega);
+          group_scale.push_back(std::complex<double>(d.scale[0], d.scale[1]));
+          group_is_h.push_back(is_h);
+          phase_off.push_back(phase_row);
+          phase_row += d.Nomega;
+        }
+        D.phase_group = grp;
+        DftParams<T> q;
+        memset(&q, 0, sizeof q);
+        q.f0 = dev(ch.d.f[d.c][0]);
+        q.f1 = dev(ch.d.f[d.c][1]);
+        q.dft = dev(d.dft);
+        // LOOP_OVER_IVECS in the reference's loop order (vec.hpp:151-168; yucky_dir vec.cpp:262-272)
+        long long idx0 = 0;
+        for (int k = 0; k < 3; ++k) {
+          const int dir = cfg.dim == MEEPCU_D2 ? (k + 2) % 3 : k;
+          q.dir[k] = dir;
+          if (g.has[dir]) {
+            q.n[k] = (d.ie[dir] - d.is[dir]) / 2 + 1;
+            q.st[k] = g.ds[dir];
+            idx0 += (long long)((d.is[dir] - g.io[dir]) / 2) * g.ds[dir];
+          }
+          else {
+            q.n[k] = 1;
+            q.st[k] = 0;
+          }
+        }
+        q.idx0 = idx0;
+        q.avg1 = g.dev_offset(d.avg1);
+        q.avg2 = g.dev_offset(d.avg2);
+        if (q.avg1 == ((long long)1 << 62) || q.avg2 == ((long long)1 << 62))
+          return fail(MEEPCU_EINVAL, "dft avg offsets are not sums of +-strides");
+        for (int k = 0; k < 3; ++k) { q.s0[k] = d.s0[k]; q.s1[k] = d.s1[k]; q.e0[k] = d.e0[k]; q.e1[k] = d.e1[k]; }
+        q.dV0 = d.dV0; q.dV1 = d.dV1;
+        q.include_dV = d.include_dV_and_interp_weights;
+        q.sqrt_dV = d.sqrt_dV_and_interp_weights;
+        q.Nomega = d.Nomega;
+        q.phase_group = grp;
+        q.N = (long long)D.N;
+        const int pidx = (int)h_dft.size();
+        h_dft.push_back(q);
+        dft_decim.push_back(d.decimation_factor);
+        dft_is_h.push_back(is_h);
+        const long long ne = q.N * q.Nomega;
+        for (long long e0 = 0; e0 < ne; e0 += kThreads) {
+          DftWork w = {pidx, e0};
+          work.push_back(w);
+        }
+        alg_bytes += 4LL * ne * (long long)sizeof(T) / d.decimation_factor;
+      }
+    }
+    RC(upload(h_dft, &d_dft));
+    RC(upload(work, &d_dft_work));
+    n_dft_work = (int)work.size();
+    RC(upload(phase_off, &d_phase_off));
+
+    CU(cudaStreamSynchronize(st));
+    finalized = true;
+    return MEEPCU_OK;
+  }
+
+  int fill_pols(const ChunkH &ch, int ft, int ec, int k, int cmp, PolParams<T> *out) {
+    for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip) {
+      const meepcu_susceptibility_desc &sd = ch.pol[ft][ip].d;
+      PolParams<T> &q = out[ip];
+      memset(&q, 0, sizeof q);
+      q.p = dev(sd.P[ec][cmp]);
+      q.pp = dev(sd.P_prev[ec][cmp]);
+      // update_P needs w && s (susceptibility.cpp:201); w = f_w ?: f exists since f[ec][cmp] does
+      q.s = q.p ? dev(sd.sigma[ec][k]) : 0;
+      // susceptibility.cpp:191-194, evaluated in realnum exactly like the reference
+      const double pi = 3.141592653589793238462643383276;
+      const T dt = (T)cfg.dt;
+      const T omega_0 = (T)sd.omega_0, gamma = (T)sd.gamma;
+      const T omega2pi = 2 * pi * omega_0, g2pi = gamma * 2 * pi;
+      const T omega0dtsqr = omega2pi * omega2pi * dt * dt;
+      q.gamma1inv = 1 / (1 + g2pi * dt / 2);
+      q.gamma1 = (1 - g2pi * dt / 2);
+      q.omega0dtsqr = omega0dtsqr;
+      q.omega0dtsqr_denom = sd.no_omega_0_denominator ? 0 : omega0dtsqr;
+    }
+    return MEEPCU_OK;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  int launch_conn(int ft) {
+    const ConnTable<T> &a = d_conn[ft][0], &b = d_conn[ft][1], &c = d_conn[ft][2];
+    const long long n = std::max(a.n / 2, std::max(b.n, c.n));
+    if (n == 0) return MEEPCU_OK;
+    const int grid = (int)std::min<long long>((n + kThreads - 1) / kThreads, 148 * 16);
+    k_conn<T><<<grid, kThreads, 0, st>>>(a, b, c);
+    launches++;
+    return MEEPCU_OK;
+  }
+
+  int launch_half(int half, const double *smp) {
+    if (n_tiles[half][0]) {
+      k_half<T, true><<<n_tiles[half][0], kThreads, 0, st>>>(d_half, d_tiles[half][0], smp);
+      launches++;
+    }
+    if (n_tiles[half][1]) {
+      k_half<T, false><<<n_tiles[half][1], kThreads, 0, st>>>(d_half, d_tiles[half][1], smp);
+      launches++;
+    }
+    const int ftd = half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF;
+    const int fte = half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF;
+    const int ftp = half ? MEEPCU_PE_STUFF : MEEPCU_PH_STUFF;
+    const int ftw = half ? MEEPCU_WE_STUFF : MEEPCU_WH_STUFF;
+    if (eager_db[half]) RC(launch_conn(ftd)); // step.cpp:72,104
+    if (general_half[half]) {
+      if (n_fmp[half]) {
+        dim3 grid(148 * 2, (unsigned)std::min(n_fmp[half], 64));
+        k_fmp<T><<<grid, kThreads, 0, st>>>(d_fmp[half], n_fmp[half], smp);
+        launches++;
+        if (fmp_has_src[half]) {
+          k_fmp_src<T><<<(n_fmp[half] + 63) / 64, 64, 0, st>>>(d_fmp[half], n_fmp[half], smp);
+          launches++;
+        }
+      }
+      k_eh_general<T><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
+      launches++;
+    }
+    RC(launch_conn(ftw));                    // step.cpp:81,113 (empty unless anisotropic sigma)
+    if (eager_p[half]) RC(launch_conn(ftp)); // step.cpp:87,118
+    RC(launch_conn(fte));                    // step.cpp:91,122
+    return MEEPCU_OK;
+  }
+
+  int step(int nsteps, int nsrc, const meepcu_src_sample *smp) {
+    if (!finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
+    if (nsteps <= 0) return MEEPCU_OK;
+    for (size_t ic = 0; ic < chunks.size(); ++ic)
+      for (size_t is = 0; is < chunks[ic].src.size(); ++is)
+        if (chunks[ic].src[is].tid >= nsrc || chunks[ic].src[is].tid < 0 || (nsrc > 0 && !smp))
+          return fail(MEEPCU_EINVAL, "source refers to src_time %d but only %d samples given",
+                      chunks[ic].src[is].tid, nsrc);
+    CU(cudaSetDevice(cfg.device));
+    // per-step tables: src_time samples, DFT phases (dft.cpp:269-270, host libm like the
+    // reference), DFT decimation flags (dft.cpp:259)
+    const size_t ns = (size_t)std::max(nsrc, 1) * 8;
+    RC(d_smp.reserve(ns * nsteps));
+    if (nsrc > 0)
+      CU(cudaMemcpyAsync(d_smp.p, smp, sizeof(meepcu_src_sample) * (size_t)nsrc * nsteps,
+                         cudaMemcpyHostToDevice, st));
+    const size_t ndft = h_dft.size();
+    if (ndft) {
+      std::vector<T> ph((size_t)2 * phase_row * nsteps);
+      std::vector<unsigned char> act(ndft * nsteps);
+      for (int s = 0; s < nsteps; ++s) {
+        const int tt = t + s + 1; // fields::t after the increment of step.cpp:126
+        const double timeE = tt * cfg.dt, timeH = tt * cfg.dt - 0.5 * cfg.dt; // dft.cpp:252
+        for (size_t gI = 0; gI < group_omega.size(); ++gI) {
+          const double time = group_is_h[gI] ? timeH : timeE;
+          for (size_t i = 0; i < group_omega[gI].size(); ++i) {
+            const std::complex<double> z = std::polar(1.0, group_omega[gI][i] * time) * group_scale[gI];
+            ph[2 * ((size_t)s * phase_row + phase_off[gI] + i)] = (T)z.real();
+            ph[2 * ((size_t)s * phase_row + phase_off[gI] + i) + 1] = (T)z.imag();
+          }
+        }
+        for (size_t k = 0; k < ndft; ++k) act[(size_t)s * ndft + k] = (tt % dft_decim[k]) == 0;
+      }
+      RC(d_phases.reserve(ph.size()));
+      RC(d_active.reserve(act.size()));
+      CU(cudaMemcpyAsync(d_phases.p, ph.data(), ph.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_active.p, act.data(), act.size(), cudaMemcpyHostToDevice, st));
+      CU(cudaStreamSynchronize(st)); // the staging vectors die at scope exit
+    }
+    else if (nsrc > 0)
+      CU(cudaStreamSynchronize(st));
+    CU(cudaEventRecord(ev0, st));
+    for (int s = 0; s < nsteps; ++s) {
+      const double *sm = d_smp.p + (size_t)s * ns;
+      RC(launch_half(0, sm));
+      RC(launch_half(1, sm));
+      if (n_dft_work) {
+        k_dft<T><<<n_dft_work, kThreads, 0, st>>>(d_dft, d_dft_work, d_phases.p + (size_t)2 * phase_row * s,
+                                                   d_phase_off, d_active.p + (size_t)s * ndft);
+        launches++;
+      }
+    }
+    CU(cudaEventRecord(ev1, st));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ev0, ev1));
+    last_ms = ms;
+    t += nsteps;
+    steps_done += nsteps;
+    return MEEPCU_OK;
+  }
+
+  int sync_to_host() {
+    if (!finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
+    CU(cudaSetDevice(cfg.device));
+    // halo copies the stepping kernels never consume are materialised here, so that the
+    // not-owned points of the host mirror hold what step_boundaries would have left there
+    for (int half = 0; half < 2; ++half) {
+      if (!eager_db[half]) RC(launch_conn(half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF));
+      if (!eager_p[half]) RC(launch_conn(half ? MEEPCU_PE_STUFF : MEEPCU_PH_STUFF));
+    }
+    for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it)
+      if (it->second.mut) RC(copy_array(it->second, true));
+    CU(cudaStreamSynchronize(st));
+    return MEEPCU_OK;
+  }
+  int sync_from_host() {
+    CU(cudaSetDevice(cfg.device));
+    for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it)
+      RC(copy_array(it->second, false));
+    CU(cudaStreamSynchronize(st));
+    return MEEPCU_OK;
+  }
+  int check_finite(int *ok) {
+    if (!finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
+    CU(cudaSetDevice(cfg.device));
+    CU(cudaMemsetAsync(d_flags + 1, 0, sizeof(int), st));
+    for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it)
+      if (it->second.is_field) {
+        k_nonfinite<T><<<148 * 4, kThreads, 0, st>>>((const T *)it->second.dev, (long long)it->second.n_dev,
+                                                      d_flags + 1);
+        launches++;
+      }
+    int flags[2] = {0, 0};
+    CU(cudaMemcpyAsync(flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *ok = flags[1] == 0;
+    if (flags[0])
+      return fail(MEEPCU_ENONFINITE, "%d cells exhausted the deterministic Newton-Raphson seed ladder "
+                                     "(newton_raphson.cpp:266-330); the reference would draw random seeds", flags[0]);
+    return MEEPCU_OK;
+  }
+  int read_value(const void *p, double *out) {
+    if (!finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
+    T *d = dev_elem(p);
+    if (!d) return fail(MEEPCU_EINVAL, "pointer is not inside a registered array");
+    T v;
+    CU(cudaMemcpyAsync(&v, d, sizeof(T), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *out = (double)v;
+    return MEEPCU_OK;
+  }
+  int get_stats(meepcu_stats *out) {
+    memset(out, 0, sizeof *out);
+    out->kernel_launches = launches;
+    out->steps = steps_done;
+    out->device_bytes = (int64_t)arena_bytes;
+    out->cells = cells;
+    out->algorithmic_bytes_per_step = alg_bytes;
+    out->last_step_ms = last_ms;
+    return MEEPCU_OK;
+  }
+  int get_timers(double out[22]) {
+    for (int i = 0; i < 22; ++i) out[i] = 0;
+    return MEEPCU_OK;
+  }
+};
+
+} // namespace
+
+struct meepcu_ctx {
+  CtxBase *impl;
+};
+
+extern "C" {
+
+const char *meepcu_last_error(void) { return g_err.c_str(); }
+const char *meepcu_backend(void) { return "cuda-sm_100a"; }
+int meepcu_abi_version(void) { return MEEPCU_ABI_VERSION; }
+
+int meepcu_create(const meepcu_config *cfg, meepcu_ctx **out) {
+  if (!cfg || !out) return fail(MEEPCU_EINVAL, "null argument");
+  if (cfg->abi_version != MEEPCU_ABI_VERSION) return fail(MEEPCU_EINVAL, "ABI version mismatch");
+  if (cfg->dim == MEEPCU_Dcyl) return fail(MEEPCU_EUNSUPPORTED, "cylindrical coordinates are not on the GPU path");
+  if (cfg->dim < 0 || cfg->dim > 3) return fail(MEEPCU_EINVAL, "bad dim");
+  if (cfg->nl_mode != MEEPCU_NL_FORK_LITERAL && cfg->nl_mode != MEEPCU_NL_UPSTREAM_PADE)
+    return fail(MEEPCU_EINVAL, "bad nl_mode");
+  CtxBase *impl;
+  if (cfg->realnum_bytes == 8)
+    impl = new Ctx<double>();
+  else if (cfg->realnum_bytes == 4)
+    impl = new Ctx<float>();
+  else
+    return fail(MEEPCU_EINVAL, "realnum_bytes must be 4 or 8");
+  impl->cfg = *cfg;
+  impl->t = cfg->t;
+  impl->finalized = false;
+  *out = new meepcu_ctx;
+  (*out)->impl = impl;
+  return MEEPCU_OK;
+}
+int meepcu_destroy(meepcu_ctx *ctx) {
+  if (!ctx) return MEEPCU_OK;
+  delete ctx->impl;
+  delete ctx;
+  return MEEPCU_OK;
+}
+#define CHECK_CTX                                                                                  \
+  if (!ctx || !ctx->impl) return fail(MEEPCU_EINVAL, "null context")
+int meepcu_add_chunk(meepcu_ctx *ctx, const meepcu_chunk_desc *d, int *id) {
+  CHECK_CTX;
+  if (!d) return fail(MEEPCU_EINVAL, "null chunk descriptor");
+  return ctx->impl->add_chunk(d, id);
+}
+int meepcu_add_susceptibility(meepcu_ctx *ctx, int chunk, const meepcu_susceptibility_desc *d) {
+  CHECK_CTX;
+  if (!d) return fail(MEEPCU_EINVAL, "null descriptor");
+  return ctx->impl->add_susc(chunk, d);
+}
+int meepcu_add_source(meepcu_ctx *ctx, int chunk, const meepcu_source_desc *d) {
+  CHECK_CTX;
+  if (!d) return fail(MEEPCU_EINVAL, "null descriptor");
+  return ctx->impl->add_source(chunk, d);
+}
+int meepcu_add_dft(meepcu_ctx *ctx, int chunk, const meepcu_dft_desc *d, int *id) {
+  CHECK_CTX;
+  if (!d) return fail(MEEPCU_EINVAL, "null descriptor");
+  return ctx->impl->add_dft(chunk, d, id);
+}
+int meepcu_set_metal(meepcu_ctx *ctx, int ft, size_t n, void *const *ptrs) {
+  CHECK_CTX;
+  return ctx->impl->set_metal(ft, n, ptrs);
+}
+int meepcu_add_connections(meepcu_ctx *ctx, int ft, int kind, size_t n, void *const *dst,
+                           const void *const *src, const void *phases) {
+  CHECK_CTX;
+  return ctx->impl->add_conn(ft, kind, n, dst, src, phases);
+}
+int meepcu_add_remote_send(meepcu_ctx *, int, int, int, size_t, const void *const *) {
+  return fail(MEEPCU_EUNSUPPORTED, "multi-rank halo exchange is not built in this round");
+}
+int meepcu_add_remote_recv(meepcu_ctx *, int, int, int, size_t, void *const *, const void *) {
+  return fail(MEEPCU_EUNSUPPORTED, "multi-rank halo exchange is not built in this round");
+}
+int meepcu_comm_unique_id(void *) {
+  return fail(MEEPCU_EUNSUPPORTED, "multi-rank halo exchange is not built in this round");
+}
+int meepcu_comm_init(meepcu_ctx *, int, int, const void *) {
+  return fail(MEEPCU_EUNSUPPORTED, "multi-rank halo exchange is not built in this round");
+}
+int meepcu_finalize(meepcu_ctx *ctx) {
+  CHECK_CTX;
+  return ctx->impl->finalize();
+}
+int meepcu_step(meepcu_ctx *ctx, int nsteps, int nsrc, const meepcu_src_sample *smp) {
+  CHECK_CTX;
+  return ctx->impl->step(nsteps, nsrc, smp);
+}
+int meepcu_sync_to_host(meepcu_ctx *ctx) {
+  CHECK_CTX;
+  return ctx->impl->sync_to_host();
+}
+int meepcu_sync_from_host(meepcu_ctx *ctx) {
+  CHECK_CTX;
+  if (!ctx->impl->finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
+  return ctx->impl->sync_from_host();
+}
+int meepcu_get_time(meepcu_ctx *ctx, int *t) {
+  CHECK_CTX;
+  *t = ctx->impl->t;
+  return MEEPCU_OK;
+}
+int meepcu_set_time(meepcu_ctx *ctx, int t) {
+  CHECK_CTX;
+  ctx->impl->t = t;
+  return MEEPCU_OK;
+}
+int meepcu_check_finite(meepcu_ctx *ctx, int *ok) {
+  CHECK_CTX;
+  return ctx->impl->check_finite(ok);
+}
+int meepcu_read_value(meepcu_ctx *ctx, const void *p, double *out) {
+  CHECK_CTX;
+  return ctx->impl->read_value(p, out);
+}
+int meepcu_get_timers(meepcu_ctx *ctx, double out[22]) {
+  CHECK_CTX;
+  return ctx->impl->get_timers(out);
+}
+int meepcu_get_stats(meepcu_ctx *ctx, meepcu_stats *out) {
+  CHECK_CTX;
+  return ctx->impl->get_stats(out);
+}
+}
