@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- Mcell-updates/s of the fused E+H time step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload vac3d|diel3d|lorentz3d|nr3d] [--n 256] [--dtype f64|f32]
+
+One "step" = one full `fields::step()` (B, H, D, E half-updates, boundaries, DFT) over the whole
+grid.  Default workload = BASELINE configs[1]: 3D vacuum cube 256^3, PML 1.0 on all faces
+(27 chunks), Ez point dipole, real fields; f64 (the reference's default realnum).
+
+ours:       numpy host model (meep_nl_b200/host.py) -> C ABI -> libmeepcuda.so.
+            `value`  : K steps timed on the device (CUDA events on the library's stream, recorded
+                       inside meepcu_step), inputs resident in HBM.
+            `e2e`    : the same K steps through the C ABI with HOST buffers: meepcu_sync_from_host
+                       (all arrays H2D) + meepcu_step(K) (per-step source samples H2D) + one probe
+                       read + meepcu_sync_to_host (all arrays D2H), wall clock.
+            `roofline`: dominant kernel (k_half<D/E,...>), algorithmic bytes / CUDA-event time.
+            `cpu_baseline`: the reference's own CPU code (oracle/_ref/<flavour>/ref_driver,
+                       kind "reference") or, if that did not travel, the CPU oracle (kind "port").
+reference:  times the reference's CPU implementation on the host cores, same workload/metric.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="vac3d")
+    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def build_problem(args, backend, device=0):
+    from meep_nl_b200 import host as H
+    from meep_nl_b200._cabi import Ex, Ey, Ez
+    rt = np.float64 if args.dtype == "f64" else np.float32
+    n = args.n
+    L = n / 10.0
+    gv = H.vol3d(L, L, L, 10)
+    w = args.workload
+    if w == "vac3d":
+        s = H.structure(gv, None, pml=1.0, realnum=rt)
+        f = H.fields(s, backend, device=device)
+        f.use_real_fields()
+        f.add_point_source(Ez, 0.15, 0.1, 0.0, 4.0, gv.center(), 1.0)
+    elif w == "diel3d":
+        s = H.structure(gv, lambda x, y, z: 1.0 + 1.25 * ((z > L / 3) & (z < 2 * L / 3)), pml=1.0, realnum=rt)
+        f = H.fields(s, backend, device=device)
+        f.use_real_fields()
+        f.add_point_source(Ez, 0.15, 0.1, 0.0, 4.0, gv.center(), 1.0)
+    elif w == "lorentz3d":  # BASELINE configs[3] shape
+        def ring(x, y, z):
+            r = np.sqrt((x - L / 2) ** 2 + (y - L / 2) ** 2)
+            return ((r >= 0.15 * L) & (r <= 0.3 * L) & (np.abs(z - L / 2) <= 0.1 * L)) * 1.0
+        s = H.structure(gv, lambda x, y, z: 1.0 + 10.56 * ring(x, y, z), pml=1.0, realnum=rt)
+        s.add_susceptibility(ring, H.E_stuff, H.lorentzian_susceptibility(1.1, 1e-5))
+        f = H.fields(s, backend, device=device)
+        f.use_real_fields()
+        f.add_point_source(Ez, 0.15, 0.1, 0.0, 4.0, (L / 2 + 0.22 * L, L / 2, L / 2 + 0.05), 1.0)
+        lo, hi = int(0.15 * n), int(0.85 * n)
+        fr = np.linspace(0.1, 0.2, 100)
+        for c in (Ey, Ez):
+            f.add_dft_fields(c, (hi, lo, lo), (hi, hi, hi), fr)
+            f.add_dft_fields(c, (lo, lo, lo), (lo, hi, hi), fr)
+    elif w == "nr3d":  # BASELINE configs[2] (fork Newton-Raphson chi2 slab)
+        s = H.structure(gv, lambda x, y, z: 2.25 + 0 * x, pml=1.0, realnum=rt)
+        s.set_offdiag_flags()
+        s.set_chi2(lambda x, y, z: 1e-2 * ((z > L / 3) & (z < 2 * L / 3)))
+        s.set_chi3(lambda x, y, z: 1.0 + 0 * x)
+        f = H.fields(s, backend, device=device)
+        f.use_real_fields()
+        c = gv.center()
+        f.add_point_source(Ez, 0.3, 0.2, 0.0, 4.0, c, 1.0)
+        f.add_point_source(Ex, 0.3, 0.2, 0.0, 4.0, (c[0] + 0.25, c[1] + 0.1, c[2]), 1.0)
+        f.add_point_source(Ey, 0.3, 0.2, 0.0, 4.0, (c[0], c[1] + 0.25, c[2] + 0.1), 1.0)
+    else:
+        raise SystemExit("unknown workload " + w)
+    return gv, f
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs"""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.stop = threading.Event()
+        self.samples = []
+        self.index = index
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.cmd = ["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits"]
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(self.cmd, capture_output=True, text=True, timeout=5).stdout.strip()
+                p = [x.strip() for x in out.split(",")]
+                if len(p) >= 6:
+                    self.samples.append(p)
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def workload_name(args):
+    return "%s_%d^3_%s" % (args.workload, args.n, args.dtype)
+
+
+def ref_case(args):
+    m = {"vac3d": "vac3d:%d", "lorentz3d": "lorentz3d:%d:100", "nr3d": "nrslab3d:%d"}
+    return (m.get(args.workload) or "vac3d:%d") % args.n
+
+
+def run_reference_cpu(args, steps, warmup):
+    """the reference's own CPU code on this box's host cores; returns (mcells/s, info) or None"""
+    fl = "fp64" if args.dtype == "f64" else "fp32"
+    drv = os.path.join(ROOT, "oracle", "_ref", fl, "ref_driver")
+    cores = os.cpu_count() or 1
+    if os.path.exists(drv) and args.workload in ("vac3d", "lorentz3d", "nr3d"):
+        with tempfile.NamedTemporaryFile(suffix=".json") as tf:
+            env = dict(os.environ, OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="spread")
+            subprocess.run([drv, "--mode", "ref", "--case", ref_case(args), "--steps", str(steps), "--warmup",
+                            str(warmup), "--json", tf.name], check=True, env=env, stdout=subprocess.DEVNULL,
+                           stderr=subprocess.DEVNULL, timeout=3000)
+            d = json.load(open(tf.name))
+        return d["mcells_per_s"], {"kind": "reference", "cores": d["threads"],
+                                   "sample": "%d warm-up + %d timed fields::step() of the full %s problem "
+                                             "(unmodified reference core, OpenMP, %d threads)"
+                                             % (warmup, steps, ref_case(args), d["threads"])}
+    # fall back to the CPU restatement (still the reference's algorithm, single translation unit)
+    from meep_nl_b200 import _cabi
+    lib = os.path.join(ROOT, "oracle", "liboracle_meep.so")
+    if not os.path.exists(lib):
+        return None
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    b = _cabi.Backend(lib)
+    gv, f = build_problem(args, b)
+    f.step(max(warmup, 1))
+    t0 = time.perf_counter()
+    f.step(steps)
+    dt = time.perf_counter() - t0
+    f.close()
+    return gv.cells() * steps / dt / 1e6, {"kind": "port", "cores": cores,
+                                           "sample": "%d timed steps of the full problem through the CPU oracle" % steps}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = run_reference_cpu(args, max(2, min(args.steps, args.cpu_steps)), min(args.warmup, 3))
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref nor the oracle library is built"}))
+        return
+    val, info = r
+    steps = max(2, min(args.steps, args.cpu_steps))
+    cells = args.n ** 3
+    line = {"impl": "reference", "metric": "Mcell-updates/s (fused E+H step)", "value": val, "unit": "Mcell/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
+            "ms_per_step": cells / val / 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(args)},
+            "cpu_baseline": dict(info, value=val, unit="Mcell/s"),
+            "e2e": {"value": val, "unit": "Mcell/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+        dist = dist_
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from meep_nl_b200 import _cabi
+    backend = _cabi.Backend()  # libmeepcuda.so or an exception: no fallback
+    gv, f = build_problem(args, backend, device=local)
+    K, W = args.steps, max(args.warmup, 3)
+    f.init()
+    f.step(W)
+    st0 = f.stats()
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- timed region: K steps, device time from CUDA events recorded inside meepcu_step ----
+    smp = f.samples(K)
+    backend.check(backend.set_profiling(f.ctx, 1))
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    f.step(K, samples=smp)
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop.set()
+    sampler.join()
+    st1 = f.stats()
+    dev_ms = st1.last_step_ms
+    kt = (_cabi.KernelTime * 16)()
+    nk = C.c_int(0)
+    backend.check(backend.get_kernel_times(f.ctx, kt, 16, C.byref(nk)))
+    backend.check(backend.set_profiling(f.ctx, 0))
+    kernels = [{"name": kt[i].name.decode(), "launches": kt[i].launches, "ms": kt[i].ms,
+                "bytes": kt[i].algorithmic_bytes} for i in range(nk.value) if kt[i].launches]
+    if dist is not None:
+        import torch
+        tt = torch.tensor([dev_ms], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms = float(tt.item())
+    cells = gv.cells()
+    total_cells = cells * world  # replicas: every rank steps its own copy of the workload
+    value = total_cells * K / (dev_ms * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with host buffers ----
+    smp2 = f.samples(K)
+    barrier()
+    t0 = time.perf_counter()
+    f.sync_from_host()
+    f.step(K, samples=smp2)
+    probe = f.get_field(4, gv.center())  # Ez
+    f.sync_to_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    nsrc = len(f.src_times)
+    hb = f.host_bytes()
+    e2e = {"value": total_cells * K / e2e_s / 1e6, "unit": "Mcell/s",
+           "h2d_bytes_per_step": int(st1.device_bytes / K + 64 * nsrc), "d2h_bytes_per_step": int(hb / K + 8),
+           "region": "meepcu_sync_from_host + meepcu_step(%d) + probe read + meepcu_sync_to_host, wall clock" % K}
+
+    # ---- roofline of the dominant kernel ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
+    roof = None
+    if dom:
+        per_launch_ms = dom["ms"] / dom["launches"]
+        ach = dom["bytes"] / (per_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom["name"], "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": per_launch_ms,
+                "whole_step": {"achieved": st1.algorithmic_bytes_per_step * K / (dev_ms * 1e-3) / 1e9,
+                               "frac": st1.algorithmic_bytes_per_step * K / (dev_ms * 1e-3) / 1e9 / peak,
+                               "frac_of_8TBs_nominal": st1.algorithmic_bytes_per_step * K / (dev_ms * 1e-3) / 8e12,
+                               "bytes_per_cell": st1.algorithmic_bytes_per_step / cells},
+                "kernels": kernels}
+    line = {"metric": "Mcell-updates/s (fused E+H step)", "value": value, "unit": "Mcell/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(args), "cells": cells, "chunks": len(f.chunks),
+                       "l2": "working set %.1f GB >> 126 MB L2 (no flush needed)" % (st1.device_bytes / 1e9),
+                       "parallelism": "1 GPU" if world == 1 else "%d independent replicas (halo exchange not built yet)" % world,
+                       "probe_Ez_center": probe, "wall_ms_per_step": wall / K * 1e3},
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(st1.kernel_launches - st0.kernel_launches),
+            "roofline": roof}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = run_reference_cpu(args, args.cpu_steps, 3)
+        if r is not None:
+            line["cpu_baseline"] = dict(r[1], value=r[0], unit="Mcell/s")
+    f.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

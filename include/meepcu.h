@@ -106,7 +106,7 @@ typedef struct {
   double omega_0, gamma;      /* as stored by the reference (frequency units, not angular) */
   int no_omega_0_denominator; /* 1 = Drude */
   const void *sigma[MEEPCU_NUM_COMPONENTS][5]; /* susceptibility::sigma[c][d], NULL when trivial */
-  void *P[MEEPCU_NUM_COMPONENTS][2];           /* lorentzian_data::P (NULL: device-only, zero) */
+  void *P[MEEPCU_NUM_COMPONENTS][2];           /* lorentzian_data::P (NULL: needs_P() false here) */
   void *P_prev[MEEPCU_NUM_COMPONENTS][2];      /* lorentzian_data::P_prev */
   int reserved[8];
 } meepcu_susceptibility_desc;
@@ -134,7 +134,7 @@ typedef struct {
   int Nomega;
   const double *omega;   /* dft_chunk::omega[Nomega] (angular: 2 pi f) */
   double scale[2];       /* dft_chunk::scale (re,im) */
-  void *dft;             /* dft_chunk::dft, complex<realnum>[N*Nomega]; NULL: device only */
+  void *dft;             /* dft_chunk::dft, complex<realnum>[N*Nomega] (required) */
   int reserved[8];
 } meepcu_dft_desc;
 
@@ -214,6 +214,17 @@ typedef struct {
   int64_t reserved[8];
 } meepcu_stats;
 int meepcu_get_stats(meepcu_ctx *ctx, meepcu_stats *out);
+
+/* Per-kernel device times, measured with CUDA events on the library's own stream around every
+ * launch while profiling is on (bench.py's roofline numbers come from here). */
+typedef struct {
+  char name[48];                  /* kernel (class) name, e.g. "k_half<D/E,simple>" */
+  int64_t launches;               /* launches timed so far */
+  double ms;                      /* summed device time of those launches */
+  int64_t algorithmic_bytes;      /* compulsory HBM bytes of ONE launch (DESIGN.md accounting) */
+} meepcu_kernel_time;
+int meepcu_set_profiling(meepcu_ctx *ctx, int on); /* also resets the accumulated times */
+int meepcu_get_kernel_times(meepcu_ctx *ctx, meepcu_kernel_time *out, int capacity, int *n);
 
 #ifdef __cplusplus
 }

@@ -179,6 +179,8 @@ struct CtxBase {
   virtual int read_value(const void *p, double *out) = 0;
   virtual int get_stats(meepcu_stats *out) = 0;
   virtual int get_timers(double out[22]) = 0;
+  virtual int set_profiling(int on) = 0;
+  virtual int get_kernel_times(meepcu_kernel_time *out, int cap, int *n) = 0;
 };
 
 template <class T> struct DevBuf { // simple growable device buffer
@@ -252,9 +254,25 @@ template <class T> struct Ctx : CtxBase {
   int64_t launches, steps_done, cells, alg_bytes;
   double last_ms;
 
+  // per-kernel-class profiling (CUDA events around every launch, on the library's stream)
+  enum { KC_HALF_B_SIMPLE = 0, KC_HALF_B_GENERAL, KC_HALF_D_SIMPLE, KC_HALF_D_GENERAL, KC_CONN,
+         KC_FMP, KC_EH_GENERAL, KC_DFT, KC_COUNT };
+  bool profiling;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_class;      // class of the launch between ev_pool[2k] and ev_pool[2k+1]
+  size_t ev_used;
+  double kc_ms[KC_COUNT];
+  int64_t kc_launches[KC_COUNT];
+  int64_t kc_bytes[KC_COUNT];
+  double sink_ms[22];
+
   Ctx() : arena(0), arena_bytes(0), st(0), ev0(0), ev1(0), d_half(0), d_eh(0), d_dft(0),
           d_dft_work(0), n_dft_work(0), phase_row(0), d_phase_off(0), d_flags(0), d_src(0),
-          launches(0), steps_done(0), cells(0), alg_bytes(0), last_ms(0) {
+          launches(0), steps_done(0), cells(0), alg_bytes(0), last_ms(0), profiling(false), ev_used(0) {
+    memset(kc_ms, 0, sizeof kc_ms);
+    memset(kc_launches, 0, sizeof kc_launches);
+    memset(kc_bytes, 0, sizeof kc_bytes);
+    memset(sink_ms, 0, sizeof sink_ms);
     memset(d_tiles, 0, sizeof d_tiles);
     memset(n_tiles, 0, sizeof n_tiles);
     memset(d_eh_tiles, 0, sizeof d_eh_tiles);
@@ -274,6 +292,7 @@ template <class T> struct Ctx : CtxBase {
     d_smp.release();
     d_phases.release();
     d_active.release();
+    for (size_t i = 0; i < ev_pool.size(); ++i) cudaEventDestroy(ev_pool[i]);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (st) cudaStreamDestroy(st);
@@ -865,6 +884,7 @@ template <class T> struct Ctx : CtxBase {
               }
             }
             alg_bytes += (long long)v * nc * (long long)sizeof(T);
+            kc_bytes[(half ? KC_HALF_D_SIMPLE : KC_HALF_B_SIMPLE) + (simple ? 0 : 1)] += (long long)v * nc * (long long)sizeof(T);
           }
         }
         // ---- general E/H components of this chunk ----
@@ -963,6 +983,7 @@ template <class T> struct Ctx : CtxBase {
                   eh_tiles[half].push_back(t);
                 }
               alg_bytes += (long long)(4 + (E.fw ? 3 : 0)) * nc * (long long)sizeof(T);
+              kc_bytes[KC_EH_GENERAL] += (long long)(4 + (E.fw ? 3 : 0)) * nc * (long long)sizeof(T);
             }
           }
         }
@@ -1082,6 +1103,7 @@ template <class T> struct Ctx : CtxBase {
           work.push_back(w);
         }
         alg_bytes += 4LL * ne * (long long)sizeof(T) / d.decimation_factor;
+        kc_bytes[KC_DFT] += 4LL * ne * (long long)sizeof(T) / d.decimation_factor;
       }
     }
     RC(upload(h_dft, &d_dft));
@@ -1118,23 +1140,81 @@ template <class T> struct Ctx : CtxBase {
   }
 
   // ------------------------------------------------------------------------------------------
+  int prof_begin(int kc) {
+    if (!profiling) return MEEPCU_OK;
+    if (ev_used + 2 > ev_pool.size()) {
+      for (int k = 0; k < 2; ++k) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        ev_pool.push_back(e);
+      }
+    }
+    ev_class.push_back(kc);
+    CU(cudaEventRecord(ev_pool[ev_used], st));
+    return MEEPCU_OK;
+  }
+  int prof_end() {
+    if (!profiling) return MEEPCU_OK;
+    CU(cudaEventRecord(ev_pool[ev_used + 1], st));
+    ev_used += 2;
+    return MEEPCU_OK;
+  }
+  int prof_collect() { // after a stream synchronize
+    for (size_t k = 0; k < ev_used / 2; ++k) {
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, ev_pool[2 * k], ev_pool[2 * k + 1]));
+      kc_ms[ev_class[k]] += ms;
+      kc_launches[ev_class[k]]++;
+    }
+    ev_used = 0;
+    ev_class.clear();
+    return MEEPCU_OK;
+  }
+  int set_profiling(int on) {
+    profiling = on != 0;
+    memset(kc_ms, 0, sizeof kc_ms);
+    memset(kc_launches, 0, sizeof kc_launches);
+    return MEEPCU_OK;
+  }
+  int get_kernel_times(meepcu_kernel_time *out, int cap, int *n) {
+    static const char *names[KC_COUNT] = {"k_half<B/H,simple>", "k_half<B/H,general>", "k_half<D/E,simple>",
+                                          "k_half<D/E,general>", "k_conn", "k_fmp", "k_eh_general", "k_dft"};
+    int m = 0;
+    for (int k = 0; k < KC_COUNT && m < cap; ++k) {
+      memset(&out[m], 0, sizeof out[m]);
+      snprintf(out[m].name, sizeof out[m].name, "%s", names[k]);
+      out[m].launches = kc_launches[k];
+      out[m].ms = kc_ms[k];
+      out[m].algorithmic_bytes = kc_bytes[k];
+      ++m;
+    }
+    *n = m;
+    return MEEPCU_OK;
+  }
+
   int launch_conn(int ft) {
     const ConnTable<T> &a = d_conn[ft][0], &b = d_conn[ft][1], &c = d_conn[ft][2];
     const long long n = std::max(a.n / 2, std::max(b.n, c.n));
     if (n == 0) return MEEPCU_OK;
     const int grid = (int)std::min<long long>((n + kThreads - 1) / kThreads, 148 * 16);
+    RC(prof_begin(KC_CONN));
     k_conn<T><<<grid, kThreads, 0, st>>>(a, b, c);
+    RC(prof_end());
     launches++;
     return MEEPCU_OK;
   }
 
   int launch_half(int half, const double *smp) {
     if (n_tiles[half][0]) {
+      RC(prof_begin(half ? KC_HALF_D_SIMPLE : KC_HALF_B_SIMPLE));
       k_half<T, true><<<n_tiles[half][0], kThreads, 0, st>>>(d_half, d_tiles[half][0], smp);
+      RC(prof_end());
       launches++;
     }
     if (n_tiles[half][1]) {
+      RC(prof_begin(half ? KC_HALF_D_GENERAL : KC_HALF_B_GENERAL));
       k_half<T, false><<<n_tiles[half][1], kThreads, 0, st>>>(d_half, d_tiles[half][1], smp);
+      RC(prof_end());
       launches++;
     }
     const int ftd = half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF;
@@ -1145,14 +1225,18 @@ template <class T> struct Ctx : CtxBase {
     if (general_half[half]) {
       if (n_fmp[half]) {
         dim3 grid(148 * 2, (unsigned)std::min(n_fmp[half], 64));
+        RC(prof_begin(KC_FMP));
         k_fmp<T><<<grid, kThreads, 0, st>>>(d_fmp[half], n_fmp[half], smp);
+        RC(prof_end());
         launches++;
         if (fmp_has_src[half]) {
           k_fmp_src<T><<<(n_fmp[half] + 63) / 64, 64, 0, st>>>(d_fmp[half], n_fmp[half], smp);
           launches++;
         }
       }
+      RC(prof_begin(KC_EH_GENERAL));
       k_eh_general<T><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
+      RC(prof_end());
       launches++;
     }
     RC(launch_conn(ftw));                    // step.cpp:81,113 (empty unless anisotropic sigma)
@@ -1208,8 +1292,10 @@ template <class T> struct Ctx : CtxBase {
       RC(launch_half(0, sm));
       RC(launch_half(1, sm));
       if (n_dft_work) {
+        RC(prof_begin(KC_DFT));
         k_dft<T><<<n_dft_work, kThreads, 0, st>>>(d_dft, d_dft_work, d_phases.p + (size_t)2 * phase_row * s,
                                                    d_phase_off, d_active.p + (size_t)s * ndft);
+        RC(prof_end());
         launches++;
       }
     }
@@ -1219,6 +1305,7 @@ template <class T> struct Ctx : CtxBase {
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, ev0, ev1));
     last_ms = ms;
+    RC(prof_collect());
     t += nsteps;
     steps_done += nsteps;
     return MEEPCU_OK;
@@ -1285,7 +1372,13 @@ template <class T> struct Ctx : CtxBase {
     return MEEPCU_OK;
   }
   int get_timers(double out[22]) {
+    // reference time_sink numbering (src/meep.hpp:1610-1633); seconds of device time
     for (int i = 0; i < 22; ++i) out[i] = 0;
+    out[10] = (kc_ms[KC_HALF_B_SIMPLE] + kc_ms[KC_HALF_B_GENERAL]) * 1e-3; // FieldUpdateB (+H, fused)
+    out[12] = (kc_ms[KC_HALF_D_SIMPLE] + kc_ms[KC_HALF_D_GENERAL]) * 1e-3; // FieldUpdateD (+E, fused)
+    out[13] = (kc_ms[KC_FMP] + kc_ms[KC_EH_GENERAL]) * 1e-3;               // FieldUpdateE (unfused part)
+    out[2] = kc_ms[KC_CONN] * 1e-3;                                        // Boundaries
+    out[6] = kc_ms[KC_DFT] * 1e-3;                                         // FourierTransforming
     return MEEPCU_OK;
   }
 };
@@ -1414,5 +1507,14 @@ int meepcu_get_timers(meepcu_ctx *ctx, double out[22]) {
 int meepcu_get_stats(meepcu_ctx *ctx, meepcu_stats *out) {
   CHECK_CTX;
   return ctx->impl->get_stats(out);
+}
+int meepcu_set_profiling(meepcu_ctx *ctx, int on) {
+  CHECK_CTX;
+  return ctx->impl->set_profiling(on);
+}
+int meepcu_get_kernel_times(meepcu_ctx *ctx, meepcu_kernel_time *out, int cap, int *n) {
+  CHECK_CTX;
+  if (!out || !n) return fail(MEEPCU_EINVAL, "null argument");
+  return ctx->impl->get_kernel_times(out, cap, n);
 }
 }

@@ -28,8 +28,41 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <omp.h>
+#if defined(__x86_64__) || defined(__i386__)
+#include <xmmintrin.h>
+#define ORACLE_HAVE_MXCSR 1
+#endif
 
 namespace {
+
+// The reference runs with flush-to-zero + denormals-are-zero on every thread
+// (set_zero_subnormals(true) in initialize::initialize, src/mympi.cpp:164-190,213); the oracle
+// restates that for the duration of a step call and restores the caller's mode afterwards.
+struct ZeroSubnormalsScope {
+  std::vector<unsigned> saved;
+  ZeroSubnormalsScope() {
+#ifdef ORACLE_HAVE_MXCSR
+    saved.assign(omp_get_max_threads(), 0);
+#pragma omp parallel
+    {
+      const int k = omp_get_thread_num();
+      if (k < (int)saved.size()) saved[k] = _mm_getcsr();
+      _mm_setcsr(_mm_getcsr() | 0x00008040u);
+    }
+#endif
+  }
+  ~ZeroSubnormalsScope() {
+#ifdef ORACLE_HAVE_MXCSR
+#pragma omp parallel
+    {
+      const int k = omp_get_thread_num();
+      if (k < (int)saved.size()) _mm_setcsr(saved[k]);
+    }
+#endif
+  }
+};
+
 
 thread_local std::string g_err;
 int fail(int code, const char *fmt, ...) {
@@ -1058,6 +1091,7 @@ template <class T> struct Impl : CtxBase {
   // fields::step, src/step.cpp:35-140
   int step(int nsteps, int nsrc, const meepcu_src_sample *smp) {
     int rc;
+    ZeroSubnormalsScope ftz_daz;
     for (size_t ic = 0; ic < chunks.size(); ++ic) // validate src_time ids once
       for (int ft = 0; ft < 4; ++ft)
         for (size_t is = 0; is < chunks[ic].sources[ft].size(); ++is)
@@ -1229,6 +1263,15 @@ int meepcu_get_stats(meepcu_ctx *ctx, meepcu_stats *out) {
   CHECK_CTX;
   memset(out, 0, sizeof *out);
   out->cells = ctx->impl->cells();
+  return MEEPCU_OK;
+}
+int meepcu_set_profiling(meepcu_ctx *ctx, int) {
+  CHECK_CTX;
+  return MEEPCU_OK;
+}
+int meepcu_get_kernel_times(meepcu_ctx *ctx, meepcu_kernel_time *, int, int *n) {
+  CHECK_CTX;
+  *n = 0;
   return MEEPCU_OK;
 }
 }

@@ -1,0 +1,82 @@
+"""Host-side checks that run without a GPU: the C-ABI libraries load, export every symbol that
+include/meepcu.h declares, and the product fails loudly when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import CUDA_LIB, ORACLE_LIB, ROOT
+from meep_nl_b200 import _cabi as A
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "meepcu.h")).read()
+    return sorted(set(re.findall(r"\b(meepcu_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert header_symbols() == sorted(A.SYMBOLS)
+
+
+@pytest.mark.parametrize("path", [CUDA_LIB, ORACLE_LIB])
+def test_library_exports_every_symbol(path):
+    lib = C.CDLL(path)
+    for name in header_symbols():
+        assert hasattr(lib, name), "%s lacks %s" % (path, name)
+    b = A.Backend(path)
+    assert b.lib.meepcu_abi_version() == A.ABI_VERSION
+
+
+def test_struct_sizes_match_c():
+    # sizes computed by the C compiler for include/meepcu.h (x86-64 SysV)
+    assert C.sizeof(A.Config) == 88
+    assert C.sizeof(A.SrcSample) == 64
+    assert C.sizeof(A.SourceDesc) == 40
+    assert C.sizeof(A.KernelTime) == 72
+    assert C.sizeof(A.ChunkDesc) == 24 + 8 * (4 * 40 + 100 + 20 + 20 + 100 + 100 + 18) + 24 + 32
+
+
+def test_bad_arguments_are_reported(oracle_backend, cuda_backend):
+    for b in (oracle_backend, cuda_backend):
+        cfg = A.Config()
+        cfg.abi_version = 999
+        ctx = A.vp()
+        assert b.create(C.byref(cfg), C.byref(ctx)) == A.EINVAL
+        assert b"ABI" in b.lib.meepcu_last_error()
+        cfg.abi_version = A.ABI_VERSION
+        cfg.realnum_bytes = 8
+        cfg.dim = A.Dcyl
+        assert b.create(C.byref(cfg), C.byref(ctx)) == A.EUNSUPPORTED
+        cfg.dim = A.D3
+        cfg.realnum_bytes = 2
+        assert b.create(C.byref(cfg), C.byref(ctx)) == A.EINVAL
+
+
+def test_cuda_library_has_no_cpu_fallback(cuda_backend):
+    """Without a CUDA device meepcu_finalize must fail with MEEPCU_ECUDA, never compute on the CPU."""
+    import subprocess, sys
+    code = (
+        "import sys, ctypes as C; sys.path.insert(0, %r)\n"
+        "from meep_nl_b200 import _cabi as A\n"
+        "b = A.Backend(%r)\n"
+        "cfg = A.Config(); cfg.abi_version = 1; cfg.realnum_bytes = 8; cfg.dim = A.D3; cfg.a = 10; cfg.dt = .05; cfg.courant = .5\n"
+        "ctx = A.vp(); assert b.create(C.byref(cfg), C.byref(ctx)) == 0\n"
+        "rc = b.finalize(ctx); print(rc, b.lib.meepcu_last_error().decode())\n" % (ROOT, CUDA_LIB))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.startswith("%d " % A.ECUDA), out.stdout
+    assert "no CPU fallback" in out.stdout or "failed" in out.stdout
+
+
+def test_product_package_does_not_reference_the_oracle():
+    """The product path must not import / load anything under oracle/."""
+    pkg = os.path.join(ROOT, "meep_nl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if not fn.endswith((".py", ".cu", ".cuh", ".hpp", ".h")) or "shim" in dirpath:
+                continue
+            txt = open(os.path.join(dirpath, fn)).read()
+            assert "liboracle" not in txt.replace("oracle/liboracle_meep.so, which ONLY", ""), fn
+            assert "import oracle" not in txt and "from oracle" not in txt, fn

@@ -1,0 +1,52 @@
+"""-m gpu: the drop-in path end to end.  oracle/_ref/<flavour>/ref_driver holds the UNMODIFIED
+reference core; it builds each problem twice through the reference's own C++ API, steps twin A
+with the reference's CPU code and twin B through the shim + libmeepcuda.so, syncs back and
+compares every array.  Skipped when oracle/_ref did not travel to this machine."""
+import json
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+from conftest import CUDA_LIB, ref_driver
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("fp64", "vac3d:48", 60, 3, 1e-12), ("fp32", "vac3d:48", 60, 3, 1e-5),
+         ("fp64", "vac3d_cplx:24", 40, 2, 1e-12), ("fp64", "nrslab3d:24", 30, 2, 1e-12),
+         ("fp64", "lorentz3d:32", 50, 2, 1e-12), ("fp32", "lorentz3d:32", 50, 2, 1e-5),
+         ("fp64", "phc3d:24", 60, 0, 1e-12), ("fp64", "wvg2d", 400, 5, 1e-12),
+         ("fp64", "kr_per3d_rods", 300, 0, 1e-12), ("fp64", "kr_polariton1d", 100, 0, 1e-12)]
+
+
+@pytest.mark.parametrize("flavour,case,steps,warmup,tol", CASES)
+def test_reference_twin_comparison(flavour, case, steps, warmup, tol):
+    drv = ref_driver(flavour)
+    if drv is None:
+        pytest.skip("oracle/_ref/%s not present on this machine" % flavour)
+    with tempfile.NamedTemporaryFile(suffix=".json") as tf:
+        env = dict(os.environ, OMP_NUM_THREADS="8")
+        subprocess.run([drv, "--mode", "shim", "--lib", CUDA_LIB, "--case", case, "--steps", str(steps),
+                        "--warmup", str(warmup), "--json", tf.name], check=True, env=env,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+        d = json.load(open(tf.name))
+    assert d["backend"] == "cuda-sm_100a" and d["arrays"] > 0 and d["mismatched_arrays"] <= d["arrays"]
+    assert d["finite"] == 1
+    assert d["rel_l2"] <= tol, d
+
+
+def test_known_results_on_gpu():
+    """three of the reference's own golden numbers (tests/known_results.cpp:155-169), computed by
+    the reference's objects stepping through libmeepcuda.so"""
+    drv = ref_driver("fp64")
+    if drv is None:
+        pytest.skip("oracle/_ref/fp64 not present")
+    known = {"kr_metal3d": (-41.8057, 200), "kr_pml2d": (0.883776, 600), "kr_per3d_rods": (-103.844, 600)}
+    for case, (val, steps) in known.items():
+        with tempfile.NamedTemporaryFile(suffix=".json") as tf:
+            subprocess.run([drv, "--mode", "shim", "--lib", CUDA_LIB, "--case", case, "--steps", str(steps),
+                            "--json", tf.name], check=True, stdout=subprocess.DEVNULL,
+                           stderr=subprocess.DEVNULL, timeout=900)
+            d = json.load(open(tf.name))
+        assert abs(d["probe_abi"] - val) <= 1e-5 * abs(val), (case, d["probe_abi"], val)

@@ -1,0 +1,99 @@
+"""The numpy host model (meep_nl_b200/host.py) builds the same stepping state as the reference's
+structure/fields constructors: checked through the oracle on the CPU, and (-m gpu) CUDA vs oracle
+on problems larger than the golden traces, plus size-independent properties."""
+import numpy as np
+import pytest
+
+from meep_nl_b200 import host as H
+from meep_nl_b200._cabi import Ez, Ex, Ey, Hy
+
+
+def vac3d(backend, n, rt=np.float64, pml=1.0):
+    gv = H.vol3d(n / 10.0, n / 10.0, n / 10.0, 10)
+    s = H.structure(gv, None, pml=pml, realnum=rt)
+    f = H.fields(s, backend)
+    f.use_real_fields()
+    f.add_point_source(Ez, 0.15, 0.1, 0.0, 4.0, gv.center(), 1.0)
+    return gv, f
+
+
+def test_vac3d_matches_reference_probe(oracle_backend):
+    """reference: ref_driver --mode ref --case vac3d:32 --steps 40 -> Ez(center) = 35.366206095806859
+    (27 chunks, PML 1.0, integrated Gaussian point dipole; recorded from the unmodified reference)"""
+    gv, f = vac3d(oracle_backend, 32)
+    f.step(40)
+    assert len(f.chunks) == 27
+    c = gv.center()
+    v = 0.5 * (f.get_field(Ez, (c[0], c[1], c[2] - 0.05)) + f.get_field(Ez, (c[0], c[1], c[2] + 0.05)))
+    assert abs(v - 35.366206095806859) <= 1e-12 * 35.4
+    f.close()
+
+
+def test_chunking_does_not_change_fields(oracle_backend):
+    """the reference's own invariant (tests/three_d.cpp:95-229): split == unsplit"""
+    outs = []
+    for split in (None, {0: [9, 14]}, {0: [12], 2: [7, 16]}):
+        gv = H.vol3d(2.4, 2.4, 2.4, 10)
+        s = H.structure(gv, lambda x, y, z: 1.0 + 2.0 * (x > 1.2), pml=0.5, split=split)
+        f = H.fields(s, oracle_backend)
+        f.use_real_fields()
+        f.add_point_source(Ex, 0.3, 0.2, 0.0, 4.0, (1.05, 1.2, 1.2), 1.0)
+        f.step(45)
+        outs.append([f.get_field(Ex, (1.05 + 0.1 * k, 1.2, 1.2)) for k in range(-6, 7)] +
+                    [f.get_field(Hy, (1.05, 1.2, 1.25 + 0.1 * k)) for k in range(-6, 6)])
+        f.close()
+    assert np.max(np.abs(outs[0])) > 0
+    assert outs[0] == outs[1] == outs[2]
+
+
+def test_periodic_translation_invariance(oracle_backend):
+    """with Bloch-periodic walls (k=0) and uniform eps, shifting the source shifts the field"""
+    vals = []
+    for shift in (0, 5):
+        gv = H.vol3d(1.6, 1.6, 1.6, 10)
+        s = H.structure(gv, None, pml=0.0)
+        f = H.fields(s, oracle_backend)
+        for d in range(3):
+            f.use_bloch(d, 0.0)
+        f.use_real_fields()
+        f.add_point_source(Ey, 0.25, 0.2, 0.0, 4.0, (0.3 + 0.1 * shift, 0.35, 0.4), 1.0)
+        f.step(30)
+        vals.append([f.get_field(Ey, ((((2 + shift + k) % 16) + 1) * 0.1, 0.35, 0.4)) for k in range(16)])
+        f.close()
+    assert np.max(np.abs(vals[0])) > 0 and vals[0] == vals[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rt,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
+def test_cuda_vs_oracle_vac3d_64(cuda_backend, oracle_backend, rt, tol):
+    res = []
+    for b in (cuda_backend, oracle_backend):
+        gv, f = vac3d(b, 64, rt)
+        f.step(50)
+        f.sync_to_host()
+        res.append(np.concatenate([fc.f[(Ez, 0)] for fc in f.chunks] + [fc.f[(Hy, 0)] for fc in f.chunks]).astype(np.float64))
+        assert f.finite()
+        f.close()
+    rel = np.linalg.norm(res[0] - res[1]) / np.linalg.norm(res[1])
+    assert np.linalg.norm(res[1]) > 0 and rel <= tol
+
+
+@pytest.mark.gpu
+def test_cuda_full_size_properties(cuda_backend):
+    """BASELINE config 2 at full size (256^3, fp32): chunked == differently chunked to the last
+    bit, fields finite, and the source-free region stays exactly zero until the wave arrives."""
+    outs = []
+    for split in (None, {0: [100, 180]}):
+        gv = H.vol3d(25.6, 25.6, 25.6, 10)
+        s = H.structure(gv, None, pml=1.0, realnum=np.float32, split=split)
+        f = H.fields(s, cuda_backend)
+        f.use_real_fields()
+        f.add_point_source(Ez, 0.15, 0.1, 0.0, 4.0, gv.center(), 1.0)
+        f.step(40)
+        assert f.finite()
+        c = gv.center()
+        outs.append([f.get_field(Ez, (c[0] + 0.1 * k, c[1], c[2] + 0.05)) for k in range(-15, 16)])
+        far = f.get_field(Ez, (1.5, 1.5, 1.55))  # 40 steps * c*dt = 2 units: cannot have reached
+        assert far == 0.0
+        f.close()
+    assert np.max(np.abs(outs[0])) > 0 and outs[0] == outs[1]

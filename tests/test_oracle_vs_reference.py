@@ -1,0 +1,48 @@
+"""Runs the UNMODIFIED reference (oracle/_ref/<flavour>/ref_driver, built from /root/reference by
+oracle/build_ref.sh) against the oracle through the reference-side shim, in one process, and
+requires every array (fields, PML auxiliaries, polarisations, DFT accumulators) to be identical.
+Skipped where oracle/_ref has not been built (no reference tree)."""
+import json
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+from conftest import ORACLE_LIB, ref_driver
+
+CASES = [("fp64", "vac3d:24", 25, 2), ("fp64", "kr_per3d_rods", 40, 0), ("fp64", "nr3d:10", 25, 0),
+         ("fp64", "lorentz3d:16", 30, 1), ("fp64", "wvg2d", 60, 3), ("fp32", "vac3d_cplx:14", 25, 2),
+         ("fp32", "lorentz3d:16", 30, 1), ("fp64", "vac3d:26", 25, 0)]
+
+
+@pytest.mark.parametrize("flavour,case,steps,warmup", CASES)
+def test_shim_plus_oracle_equals_reference(flavour, case, steps, warmup):
+    drv = ref_driver(flavour)
+    if drv is None:
+        pytest.skip("oracle/_ref/%s not built (reference tree absent)" % flavour)
+    with tempfile.NamedTemporaryFile(suffix=".json") as tf:
+        env = dict(os.environ, OMP_NUM_THREADS="4")
+        subprocess.run([drv, "--mode", "shim", "--lib", ORACLE_LIB, "--case", case, "--steps", str(steps),
+                        "--warmup", str(warmup), "--json", tf.name], check=True, env=env,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+        d = json.load(open(tf.name))
+    assert d["arrays"] > 0 and d["mismatched_arrays"] == 0 and d["mismatched_elements"] == 0, d
+    assert d["probe_ref"] == d["probe_abi"]
+
+
+def test_reference_known_answers_through_the_oracle():
+    """tests/known_results.cpp:155-169: three of the reference's own golden numbers, recomputed by
+    stepping through the C ABI (oracle backend) instead of fields::step."""
+    drv = ref_driver("fp64")
+    if drv is None:
+        pytest.skip("oracle/_ref/fp64 not built")
+    known = {"kr_metal3d": (-41.8057, 200), "kr_pml2d": (0.883776, 600), "kr_per3d_rods": (-103.844, 600)}
+    for case, (val, steps) in known.items():
+        with tempfile.NamedTemporaryFile(suffix=".json") as tf:
+            subprocess.run([drv, "--mode", "shim", "--lib", ORACLE_LIB, "--case", case, "--steps", str(steps),
+                            "--json", tf.name], check=True, stdout=subprocess.DEVNULL,
+                           stderr=subprocess.DEVNULL, timeout=600)
+            d = json.load(open(tf.name))
+        assert d["mismatched_elements"] == 0
+        assert abs(d["probe_abi"] - val) <= 1e-5 * abs(val), (case, d["probe_abi"], val)
