@@ -472,7 +472,10 @@ __device__ bool run_nr(T seed1, T seed2, T seed3, T out[3], const NRP<T> &p1, co
   const double tol2 = fmax(fabs(TOL * out[1]) * 0.0001, TOL);
   const double tol3 = fmax(fabs(TOL * out[2]) * 0.0001, TOL);
   double s1 = seed1, s2 = seed2, s3 = seed3;
-  for (int i = 0; i < 15; ++i) {
+  // tries 14..99: the reference draws std::random_device seeds (parity undefined); a fixed
+  // sequence, identical to oracle/oracle_meep.cpp, keeps runs reproducible
+  const double P10[40] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22, 1e23, 1e24, 1e25, 1e26, 1e27, 1e28, 1e29, 1e30, 1e31, 1e32, 1e33, 1e34, 1e35, 1e36, 1e37, 1e38, 1e39};
+  for (int i = 0; i < 100; ++i) {
     if (nr_iterate<T>((T)s1, (T)s2, (T)s3, p1, p2, p3, out, tol1, tol2, tol3, max_iter)) return true;
     switch (i) {
       case 0: s1 = seed1 * seedMax; max_iter = 600; break;
@@ -489,7 +492,12 @@ __device__ bool run_nr(T seed1, T seed2, T seed3, T out[3], const NRP<T> &p1, co
       case 11: s1 = seed1; s2 = -seed2 * seedMax; s3 = -seed3 * seedMax; break;
       case 12: s1 = seed1 * seedMax; s2 = seed2 * seedMax; s3 = seed3 * seedMax; break;
       case 13: s1 = -seed1 * seedMax; s2 = -seed2 * seedMax; s3 = -seed3 * seedMax; break;
-      default: return false;
+      default: {
+        const int r = i - 13;
+        s1 = ((r & 1) ? 1.0 : -1.0) * P10[r % 40];
+        s2 = ((r & 2) ? 1.0 : -1.0) * P10[(7 * r) % 40];
+        s3 = ((r & 4) ? 1.0 : -1.0) * P10[(13 * r) % 40];
+      }
     }
   }
   return false;

@@ -253,6 +253,7 @@ template <class T> struct Ctx : CtxBase {
 
   int64_t launches, steps_done, cells, alg_bytes;
   double last_ms;
+  int64_t nr_unconverged = 0; // cells left unchanged after 100 NR attempts (see check_finite)
 
   // per-kernel-class profiling (CUDA events around every launch, on the library's stream)
   enum { KC_HALF_B_SIMPLE = 0, KC_HALF_B_GENERAL, KC_HALF_D_SIMPLE, KC_HALF_D_GENERAL, KC_CONN,
@@ -522,6 +523,8 @@ template <class T> struct Ctx : CtxBase {
         by[(const char *)r->host].push_back((long long)e);
       }
       for (std::map<const char *, std::vector<long long> >::iterator it = by.begin(); it != by.end(); ++it) {
+        std::sort(it->second.begin(), it->second.end());
+        it->second.erase(std::unique(it->second.begin(), it->second.end()), it->second.end());
         const ArrayRec &r = arrays[it->first];
         const ChunkH &ch = chunks[r.chunk];
         const Geom &g = ch.g;
@@ -1346,9 +1349,7 @@ template <class T> struct Ctx : CtxBase {
     CU(cudaMemcpyAsync(flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     *ok = flags[1] == 0;
-    if (flags[0])
-      return fail(MEEPCU_ENONFINITE, "%d cells exhausted the deterministic Newton-Raphson seed ladder "
-                                     "(newton_raphson.cpp:266-330); the reference would draw random seeds", flags[0]);
+    nr_unconverged = flags[0];
     return MEEPCU_OK;
   }
   int read_value(const void *p, double *out) {
@@ -1369,6 +1370,7 @@ template <class T> struct Ctx : CtxBase {
     out->cells = cells;
     out->algorithmic_bytes_per_step = alg_bytes;
     out->last_step_ms = last_ms;
+    out->reserved[0] = nr_unconverged;
     return MEEPCU_OK;
   }
   int get_timers(double out[22]) {

@@ -598,7 +598,7 @@ class fields:
         conns, metals = self._connect()
         for ft, lst in metals.items():
             if not lst: continue
-            p = np.ascontiguousarray(np.concatenate(lst).astype(np.uint64))
+            p = np.ascontiguousarray(np.unique(np.concatenate(lst).astype(np.uint64)))
             b.check(b.set_metal(ctx, ft, p.size, p.ctypes.data))
         for (ft, kind), (dst, src, ph) in conns.items():
             dp = np.ascontiguousarray(np.concatenate([np.asarray(x).reshape(-1) for x in dst]).astype(np.uint64))

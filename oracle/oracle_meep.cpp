@@ -591,7 +591,12 @@ template <class T> struct Impl : CtxBase {
     double tol2 = fmax(fabs(TOLERANCE * (*fw_2)) * 0.0001, TOLERANCE);
     double tol3 = fmax(fabs(TOLERANCE * (*fw_3)) * 0.0001, TOLERANCE);
     double _seed1 = seed1, _seed2 = seed2, _seed3 = seed3;
-    for (int i = 0; i < 15; ++i) {
+    // The reference tries 14 deterministic seed variants and then up to 86 more drawn from
+    // std::random_device (parity undefined from there on).  So that runs are
+    // reproducible and CPU oracle == CUDA, tries 14..99 use the fixed sequence below instead; if
+    // all 100 fail the field value is left unchanged, as in the reference.
+    static const double P10[40] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22, 1e23, 1e24, 1e25, 1e26, 1e27, 1e28, 1e29, 1e30, 1e31, 1e32, 1e33, 1e34, 1e35, 1e36, 1e37, 1e38, 1e39};
+    for (int i = 0; i < 100; ++i) {
       if (newton_raphson(_seed1, _seed2, _seed3, p1, p2, p3, fw, fw_2, fw_3, tol1, tol2, tol3,
                          max_iterations))
         return true;
@@ -610,7 +615,12 @@ template <class T> struct Impl : CtxBase {
         case 11: _seed1 = seed1; _seed2 = -seed2 * seedMax; _seed3 = -seed3 * seedMax; break;
         case 12: _seed1 = seed1 * seedMax; _seed2 = seed2 * seedMax; _seed3 = seed3 * seedMax; break;
         case 13: _seed1 = -seed1 * seedMax; _seed2 = -seed2 * seedMax; _seed3 = -seed3 * seedMax; break;
-        default: return false;
+        default: {
+          const int r = i - 13;
+          _seed1 = ((r & 1) ? 1.0 : -1.0) * P10[r % 40];
+          _seed2 = ((r & 2) ? 1.0 : -1.0) * P10[(7 * r) % 40];
+          _seed3 = ((r & 4) ? 1.0 : -1.0) * P10[(13 * r) % 40];
+        }
       }
     }
     return false;

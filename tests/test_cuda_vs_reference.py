@@ -14,7 +14,7 @@ from conftest import CUDA_LIB, ref_driver
 pytestmark = pytest.mark.gpu
 
 CASES = [("fp64", "vac3d:48", 60, 3, 1e-12), ("fp32", "vac3d:48", 60, 3, 1e-5),
-         ("fp64", "vac3d_cplx:24", 40, 2, 1e-12), ("fp64", "nrslab3d:24", 30, 2, 1e-12),
+         ("fp64", "vac3d_cplx:24", 40, 2, 1e-12), ("fp64", "nrslab3d:20", 30, 2, 1e-12),
          ("fp64", "lorentz3d:32", 50, 2, 1e-12), ("fp32", "lorentz3d:32", 50, 2, 1e-5),
          ("fp64", "phc3d:24", 60, 0, 1e-12), ("fp64", "wvg2d", 400, 5, 1e-12),
          ("fp64", "kr_per3d_rods", 300, 0, 1e-12), ("fp64", "kr_polariton1d", 100, 0, 1e-12)]
