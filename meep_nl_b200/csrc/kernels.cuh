@@ -83,6 +83,8 @@ template <class T> struct HalfParams { // one chunk, one of {B/H, D/E}, one cmp
   long long sA, sB; // device strides of axes A and B (C is 1)
   int is_D;         // 1: D/E half (currents from current_D, dipoles from dipole_E)
   int cmp;
+  int march;        // k_halfg: 0 = CTAs march along A over a (B,C) plane, 1 = along B over (A,C)
+  int pad_;
   double dt;
   CompParams<T> comp[3];
 };
@@ -286,6 +288,371 @@ __global__ void __launch_bounds__(kThreads)
       if (act[k] && ia >= c.lo[0] && ia <= c.hi[0])
         update_point<T, SIMPLE>(c, i, ia, ib, ic, smp, P.is_D, P.cmp, P.dt);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_halfg: the general fused half step (PML / conductivity / polarisations, any dimensionality).
+// Same per-point arithmetic as update_point<T,false>, restructured for memory-level parallelism:
+// every global load of the three components of a point is issued before the first dependent
+// instruction (two-phase gather -> compute/store), read-only arrays go through the read-only
+// path, and the CTA marches along the LONGER of the two outer axes so that thin PML slabs still
+// give long, fully coalesced streams.
+//   HAS_COND: conductivity terms (cnd, cndinv, fcnd) compiled in;  HAS_POL: polarisations compiled in
+// ------------------------------------------------------------------------------------------------
+template <class T, bool HAS_COND, bool HAS_POL> struct PointVals {
+  T g1p, g1, g2, g2p, f, fu, e, fw, u;
+  T cnd, cndinv, fcnd;
+  T p[HAS_POL ? kMaxPol : 1], pp[HAS_POL ? kMaxPol : 1], s[HAS_POL ? kMaxPol : 1];
+};
+
+template <class T, bool HAS_COND, bool HAS_POL>
+__device__ __forceinline__ void gather_point(const CompParams<T> &c, long long i,
+                                             PointVals<T, HAS_COND, HAS_POL> &v) {
+  v.g1p = __ldg(c.g1 + i + c.s1);
+  v.g1 = __ldg(c.g1 + i);
+  if (c.g2) {
+    v.g2 = __ldg(c.g2 + i);
+    v.g2p = __ldg(c.g2 + i + c.s2);
+  }
+  v.f = c.f[i];
+  if (c.fu) v.fu = c.fu[i];
+  if (HAS_COND && c.cnd) {
+    v.cnd = __ldg(c.cnd + i);
+    v.cndinv = __ldg(c.cndinv + i);
+    if (c.fcnd) v.fcnd = c.fcnd[i];
+  }
+  if (c.e) {
+    if (c.u) v.u = __ldg(c.u + i);
+    if (c.fw) {
+      v.fw = c.fw[i];
+      v.e = c.e[i];
+    }
+    if (HAS_POL) {
+#pragma unroll
+      for (int ip = 0; ip < kMaxPol; ++ip)
+        if (ip < c.npol && c.pol[ip].p) {
+          v.p[ip] = c.pol[ip].p[i];
+          if (c.pol[ip].s) {
+            v.pp[ip] = c.pol[ip].pp[i];
+            v.s[ip] = __ldg(c.pol[ip].s + i);
+          }
+        }
+    }
+  }
+}
+
+template <class T, bool HAS_COND, bool HAS_POL>
+__device__ __forceinline__ void finish_point(const CompParams<T> &c, long long i, int ia, int ib, int ic,
+                                             const PointVals<T, HAS_COND, HAS_POL> &v,
+                                             const double *__restrict__ smp, int is_D, int cmp, double dt) {
+  const int idx3[3] = {ia, ib, ic};
+  // ---------------- step_curl (step_generic.cpp:89-252) ----------------
+  T curl;
+  if (c.g2)
+    curl = (v.g1p - v.g1 + v.g2 - v.g2p);
+  else
+    curl = (v.g1p - v.g1);
+  const bool cond = HAS_COND && c.cnd;
+  T fnew;
+  const T fold = v.f;
+  if (c.kaxis < 0) {
+    if (c.kuaxis < 0) {
+      if (cond)
+        fnew = ((1 - c.dt2 * v.cnd) * fold - c.dtdx * curl) * v.cndinv;
+      else
+        fnew = fold - c.dtdx * curl;
+    }
+    else {
+      const int ku = 2 * idx3[c.kuaxis] + c.kuoff;
+      const T fprev = v.fu;
+      T fun;
+      if (cond)
+        fun = ((1 - c.dt2 * v.cnd) * fprev - c.dtdx * curl) * v.cndinv;
+      else
+        fun = fprev - c.dtdx * curl;
+      c.fu[i] = fun;
+      fnew = __ldg(c.siginvu + ku) * ((__ldg(c.kapu + ku) - __ldg(c.sigu + ku)) * fold + fun - fprev);
+    }
+  }
+  else {
+    const int k = 2 * idx3[c.kaxis] + c.koff;
+    const T kap = __ldg(c.kap + k), sig = __ldg(c.sig + k), siginv = __ldg(c.siginv + k);
+    if (c.kuaxis < 0) {
+      if (cond) {
+        const T fcnd_prev = v.fcnd;
+        const T fc = ((1 - c.dt2 * v.cnd) * fcnd_prev - c.dtdx * curl) * v.cndinv;
+        c.fcnd[i] = fc;
+        fnew = ((kap - sig) * fold + (fc - fcnd_prev)) * siginv;
+      }
+      else
+        fnew = ((kap - sig) * fold - c.dtdx * curl) * siginv;
+    }
+    else {
+      const int ku = 2 * idx3[c.kuaxis] + c.kuoff;
+      const T fprev = v.fu;
+      T fun;
+      if (cond) {
+        const T fcnd_prev = v.fcnd;
+        const T fc = ((1 - c.dt2 * v.cnd) * fcnd_prev - c.dtdx * curl) * v.cndinv;
+        c.fcnd[i] = fc;
+        fun = ((kap - sig) * fprev + (fc - fcnd_prev)) * siginv;
+      }
+      else
+        fun = ((kap - sig) * fprev - c.dtdx * curl) * siginv;
+      c.fu[i] = fun;
+      fnew = __ldg(c.siginvu + ku) * ((__ldg(c.kapu + ku) - __ldg(c.sigu + ku)) * fold + fun - fprev);
+    }
+  }
+  // ---------------- step_source (step.cpp:296-319) ----------------
+  if (c.ncsrc && ia >= c.csrc_amin && ia <= c.csrc_amax) {
+    for (int j = src_lower_bound(c.csrc, c.ncsrc, i); j < c.ncsrc && c.csrc[j].idx == i; ++j) {
+      const SrcEntry e = c.csrc[j];
+      const double2 cur = sample_current(smp, e.tid, is_D);
+      double2 A = cmul(e.are, e.aim, cur.x, cur.y);
+      A.x = A.x * dt;
+      A.y = A.y * dt;
+      if (c.src_has_cndinv) {
+        const double ci = double(c.cndinv[i]);
+        A.x = A.x * ci;
+        A.y = A.y * ci;
+      }
+      fnew = (T)((double)fnew - (cmp ? A.y : A.x));
+    }
+  }
+  if (on_zero_plane<T>(c.zmask_db, c.lo, c.hi, ia, ib, ic)) fnew = 0;
+  c.f[i] = fnew;
+
+  // ---------------- update_eh / update_pols ----------------
+  if (!c.e) return;
+  T fmp = fnew;
+  if (HAS_POL) {
+#pragma unroll
+    for (int ip = 0; ip < kMaxPol; ++ip)
+      if (ip < c.npol && c.pol[ip].p) fmp -= v.p[ip];
+  }
+  if (c.nisrc && ia >= c.isrc_amin && ia <= c.isrc_amax) {
+    for (int j = src_lower_bound(c.isrc, c.nisrc, i); j < c.nisrc && c.isrc[j].idx == i; ++j) {
+      const SrcEntry e = c.isrc[j];
+      const double2 dp = sample_dipole(smp, e.tid, is_D);
+      const double2 A = cmul(e.are, e.aim, dp.x, dp.y);
+      fmp = (T)((double)fmp - (cmp ? A.y : A.x));
+    }
+  }
+  const T gu = c.u ? (fmp * v.u) : fmp;
+  T enew;
+  if (c.fw) {
+    const int kw = 2 * idx3[c.kwaxis] + c.kwoff;
+    const T kapwkw = __ldg(c.kapw + kw), sigwkw = __ldg(c.sigw + kw);
+    c.fw[i] = gu;
+    enew = v.e + ((kapwkw + sigwkw) * gu - (kapwkw - sigwkw) * v.fw);
+  }
+  else
+    enew = gu;
+  if (HAS_POL) {
+#pragma unroll
+    for (int ip = 0; ip < kMaxPol; ++ip)
+      if (ip < c.npol && c.pol[ip].p && c.pol[ip].s) {
+        const PolParams<T> &q = c.pol[ip];
+        const T pcur = v.p[ip];
+        q.p[i] = q.gamma1inv * (pcur * (2 - q.omega0dtsqr_denom) - q.gamma1 * v.pp[ip] +
+                                q.omega0dtsqr * (v.s[ip] * gu));
+        q.pp[i] = pcur;
+      }
+  }
+  if (on_zero_plane<T>(c.zmask_eh, c.lo, c.hi, ia, ib, ic)) enew = 0;
+  c.e[i] = enew;
+}
+
+template <class T, bool HAS_COND, bool HAS_POL>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_halfg(const HalfParams<T> *__restrict__ params, const Tile *__restrict__ tiles,
+            const double *__restrict__ smp) {
+  __shared__ HalfParams<T> P;
+  const Tile t = tiles[blockIdx.x];
+  {
+    const int nw = (int)(sizeof(HalfParams<T>) / 4);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(params + t.param);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&P);
+    for (int k = threadIdx.x; k < nw; k += kThreads) dst[k] = src[k];
+  }
+  __syncthreads();
+  const int p = t.p0 + threadIdx.x;
+  const int io = p / P.pitch, ic = p - io * P.pitch; // io: index on the outer axis we do NOT march
+  const int march = P.march;
+  const int n_other = march ? P.nA : P.nB;
+  if (io >= n_other || ic >= P.nC) return;
+  const int ax_o = march ? 0 : 1, ax_m = march ? 1 : 0;
+  bool act[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const CompParams<T> &c = P.comp[k];
+    act[k] = c.f != nullptr && io >= c.lo[ax_o] && io <= c.hi[ax_o] && ic >= c.lo[2] && ic <= c.hi[2];
+  }
+  if (!(act[0] || act[1] || act[2])) return;
+  const long long s_m = march ? P.sB : P.sA, s_o = march ? P.sA : P.sB;
+  long long i = (long long)t.a0 * s_m + (long long)io * s_o + ic;
+  for (int im = t.a0; im < t.a1; ++im, i += s_m) {
+    const int ia = march ? io : im, ib = march ? im : io;
+    PointVals<T, HAS_COND, HAS_POL> v[3];
+    bool on[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const CompParams<T> &c = P.comp[k];
+      on[k] = act[k] && im >= c.lo[ax_m] && im <= c.hi[ax_m];
+      if (on[k]) gather_point<T, HAS_COND, HAS_POL>(c, i, v[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      if (on[k]) finish_point<T, HAS_COND, HAS_POL>(P.comp[k], i, ia, ib, ic, v[k], smp, P.is_D, P.cmp, P.dt);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_curl3d: the interior fast path.  Same arithmetic as k_half<T,true>, specialised for 3-D chunks
+// without PML / conductivity / polarisations (78 % of the cells of BASELINE config 2):
+//   * the step plan of a Cartesian 3-D chunk (src/fields.cpp:441-469) is hard-wired:
+//       f_k -= dtdx * ( g_{k+2}[i +- s_{k+1}] - g_{k+2}[i] + g_{k+1}[i] - g_{k+1}[i +- s_{k+2}] )
+//     (+ for B from E, - for D from H; src/step_db.cpp:81-84), so the three components share their
+//     nine operand loads;
+//   * the x (= marching axis) neighbours of g_y and g_z are carried in registers from one plane to
+//     the next, so each operand element is loaded once per CTA column: 7 operand loads per cell;
+//   * operands are read through the read-only path (they are never written in the same half
+//     step), which lets the compiler keep all loads of a plane in flight together;
+//   * 32-bit indexing, <= 64 registers -> 4 CTAs / 32 warps per SM.
+// ------------------------------------------------------------------------------------------------
+template <class T> struct Curl3DParams {
+  int nA, nB, nC, pitch;
+  int sA, sB;
+  int cmp, any_src;
+  double dt;
+  T dtdx;
+  T *f[3];
+  const T *g[3];
+  T *e[3];        // all NULL: no E/H update in this chunk (H aliases B)
+  const T *u[3];  // chi1inv diagonal (NULL: trivial)
+  int lo[3][3], hi[3][3]; // [component][axis]
+  unsigned zdb[3], zeh[3];
+  const SrcEntry *csrc[3], *isrc[3];
+  int ncsrc[3], nisrc[3];
+  int ca0[3], ca1[3], ia0[3], ia1[3];
+};
+
+template <class T, bool IS_D, int K>
+__device__ __forceinline__ void curl3d_finish(const Curl3DParams<T> &P, int i, int ia, int ib, int ic,
+                                              T curl, const double *__restrict__ smp) {
+  T *__restrict__ f = P.f[K];
+  T fnew = f[i] - P.dtdx * curl; // step_generic.cpp:108
+  if (P.any_src && P.ncsrc[K] && ia >= P.ca0[K] && ia <= P.ca1[K]) { // step.cpp:296-319
+    const SrcEntry *tab = P.csrc[K];
+    for (int j = src_lower_bound(tab, P.ncsrc[K], i); j < P.ncsrc[K] && tab[j].idx == i; ++j) {
+      const SrcEntry e = tab[j];
+      const double2 cur = sample_current(smp, e.tid, IS_D);
+      double2 A = cmul(e.are, e.aim, cur.x, cur.y);
+      A.x = A.x * P.dt;
+      A.y = A.y * P.dt;
+      fnew = (T)((double)fnew - (P.cmp ? A.y : A.x));
+    }
+  }
+  if (on_zero_plane<T>(P.zdb[K], P.lo[K], P.hi[K], ia, ib, ic)) fnew = 0;
+  f[i] = fnew;
+  T *__restrict__ e = P.e[K];
+  if (!e) return;
+  T fmp = fnew;
+  if (P.any_src && P.nisrc[K] && ia >= P.ia0[K] && ia <= P.ia1[K]) { // update_eh.cpp:136-146
+    const SrcEntry *tab = P.isrc[K];
+    for (int j = src_lower_bound(tab, P.nisrc[K], i); j < P.nisrc[K] && tab[j].idx == i; ++j) {
+      const SrcEntry se = tab[j];
+      const double2 dp = sample_dipole(smp, se.tid, IS_D);
+      const double2 A = cmul(se.are, se.aim, dp.x, dp.y);
+      fmp = (T)((double)fmp - (P.cmp ? A.y : A.x));
+    }
+  }
+  const T *__restrict__ u = P.u[K];
+  T enew = u ? (fmp * __ldg(u + i)) : fmp; // step_generic.cpp:891-894,903
+  if (on_zero_plane<T>(P.zeh[K], P.lo[K], P.hi[K], ia, ib, ic)) enew = 0;
+  e[i] = enew;
+}
+
+template <class T, bool IS_D>
+__global__ void __launch_bounds__(kThreads, 4)
+    k_curl3d(const Curl3DParams<T> *__restrict__ params, const Tile *__restrict__ tiles,
+             const double *__restrict__ smp) {
+  __shared__ Curl3DParams<T> P;
+  const Tile t = tiles[blockIdx.x];
+  {
+    const int nw = (int)(sizeof(Curl3DParams<T>) / 4);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(params + t.param);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&P);
+    for (int k = threadIdx.x; k < nw; k += kThreads) dst[k] = src[k];
+  }
+  __syncthreads();
+  const int p = t.p0 + threadIdx.x;
+  const int ib = p / P.pitch, ic = p - ib * P.pitch;
+  if (ib >= P.nB || ic >= P.nC) return;
+  bool act[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    act[k] = ib >= P.lo[k][1] && ib <= P.hi[k][1] && ic >= P.lo[k][2] && ic <= P.hi[k][2];
+  if (!(act[0] || act[1] || act[2])) return;
+  const int sA = P.sA, nA = P.nA;
+  // neighbour offsets, clamped so that loads whose value no owned component consumes stay in bounds
+  int oy, oz;
+  if (!IS_D) {
+    oy = (ib + 1 < P.nB) ? P.sB : 0;
+    oz = (ic + 1 < P.nC) ? 1 : 0;
+  }
+  else {
+    oy = (ib > 0) ? -P.sB : 0;
+    oz = (ic > 0) ? -1 : 0;
+  }
+  const T *__restrict__ gx = P.g[0];
+  const T *__restrict__ gy = P.g[1];
+  const T *__restrict__ gz = P.g[2];
+  int i = t.a0 * sA + ib * P.sB + ic;
+  T ry, rz; // g_y, g_z of the plane the x-difference needs, carried between iterations
+  if (!IS_D) {
+    ry = __ldg(gy + i);
+    rz = __ldg(gz + i);
+  }
+  else {
+    const int ip = t.a0 > 0 ? i - sA : i;
+    ry = __ldg(gy + ip);
+    rz = __ldg(gz + ip);
+  }
+  const int lo0 = P.lo[0][0], hi0 = P.hi[0][0], lo1 = P.lo[1][0], hi1 = P.hi[1][0], lo2 = P.lo[2][0],
+            hi2 = P.hi[2][0];
+#pragma unroll 2
+  for (int ia = t.a0; ia < t.a1; ++ia, i += sA) {
+    T gx0 = __ldg(gx + i), gxy = __ldg(gx + i + oy), gxz = __ldg(gx + i + oz);
+    T gy0, gyz, gz0, gzy, gyx, gzx;
+    gyz = __ldg(gy + i + oz);
+    gzy = __ldg(gz + i + oy);
+    if (!IS_D) {
+      const int ox = (ia + 1 < nA) ? sA : 0;
+      gy0 = ry;
+      gz0 = rz;
+      gyx = __ldg(gy + i + ox);
+      gzx = __ldg(gz + i + ox);
+      ry = gyx;
+      rz = gzx;
+    }
+    else {
+      gy0 = __ldg(gy + i);
+      gz0 = __ldg(gz + i);
+      gyx = ry;
+      gzx = rz;
+      ry = gy0;
+      rz = gz0;
+    }
+    // component x: g1 = g_z (d/dy), g2 = g_y (d/dz);  y: g1 = g_x (d/dz), g2 = g_z (d/dx);
+    // z: g1 = g_y (d/dx), g2 = g_x (d/dy)      -- (g1[i+s1] - g1[i] + g2[i] - g2[i+s2])
+    if (act[0] && ia >= lo0 && ia <= hi0)
+      curl3d_finish<T, IS_D, 0>(P, i, ia, ib, ic, (gzy - gz0 + gy0 - gyz), smp);
+    if (act[1] && ia >= lo1 && ia <= hi1)
+      curl3d_finish<T, IS_D, 1>(P, i, ia, ib, ic, (gxz - gx0 + gz0 - gzx), smp);
+    if (act[2] && ia >= lo2 && ia <= hi2)
+      curl3d_finish<T, IS_D, 2>(P, i, ia, ib, ic, (gyx - gy0 + gx0 - gxy), smp);
   }
 }
 

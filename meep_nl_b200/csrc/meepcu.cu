@@ -219,8 +219,12 @@ template <class T> struct Ctx : CtxBase {
   // tables
   HalfParams<T> *d_half;            // [nhalf]
   std::vector<HalfParams<T> > h_half;
-  Tile *d_tiles[2][2];              // [half: 0=B/H 1=D/E][class: 0 simple 1 general]
-  int n_tiles[2][2];
+  Tile *d_tiles[2][3];              // [half: 0=B/H 1=D/E][class: 0 pml-only, 1 +polarisations, 2 +conductivity]
+  int n_tiles[2][3];
+  Curl3DParams<T> *d_c3d;           // interior fast path (k_curl3d)
+  std::vector<Curl3DParams<T> > h_c3d;
+  Tile *d_c3d_tiles[2];
+  int n_c3d_tiles[2];
   EhParams<T> *d_eh;
   std::vector<EhParams<T> > h_eh;
   Tile *d_eh_tiles[2];
@@ -257,7 +261,7 @@ template <class T> struct Ctx : CtxBase {
 
   // per-kernel-class profiling (CUDA events around every launch, on the library's stream)
   enum { KC_HALF_B_SIMPLE = 0, KC_HALF_B_GENERAL, KC_HALF_D_SIMPLE, KC_HALF_D_GENERAL, KC_CONN,
-         KC_FMP, KC_EH_GENERAL, KC_DFT, KC_COUNT };
+         KC_FMP, KC_EH_GENERAL, KC_DFT, KC_CURL3D_B, KC_CURL3D_D, KC_COUNT };
   bool profiling;
   std::vector<cudaEvent_t> ev_pool;
   std::vector<int> ev_class;      // class of the launch between ev_pool[2k] and ev_pool[2k+1]
@@ -275,6 +279,9 @@ template <class T> struct Ctx : CtxBase {
     memset(kc_bytes, 0, sizeof kc_bytes);
     memset(sink_ms, 0, sizeof sink_ms);
     memset(d_tiles, 0, sizeof d_tiles);
+    d_c3d = 0;
+    memset(d_c3d_tiles, 0, sizeof d_c3d_tiles);
+    memset(n_c3d_tiles, 0, sizeof n_c3d_tiles);
     memset(n_tiles, 0, sizeof n_tiles);
     memset(d_eh_tiles, 0, sizeof d_eh_tiles);
     memset(n_eh_tiles, 0, sizeof n_eh_tiles);
@@ -337,7 +344,13 @@ template <class T> struct Ctx : CtxBase {
       g.dir_of_axis[ax] = dirs[j];
       g.nax[ax] = g.num[dirs[j]] + 1;
     }
-    g.pitch = ((g.nax[2] + 31) / 32) * 32;
+    // fastest axis padded so that rows start on a 128-byte line (long rows) or at least on a
+    // 32-byte sector (short rows, e.g. the 12-point-thick PML slabs: padding them to 32 elements
+    // would leave most lanes of every warp idle)
+    {
+      const int q = g.nax[2] >= 64 ? 32 : (int)(32 / sizeof(T));
+      g.pitch = ((g.nax[2] + q - 1) / q) * q;
+    }
     const long long sax[3] = {(long long)g.pitch * g.nax[1], (long long)g.pitch, 1};
     for (int k = 0; k < 3; ++k)
       if (g.has[k]) g.ds[k] = sax[g.axis_of_dir[k]];
@@ -716,7 +729,7 @@ template <class T> struct Ctx : CtxBase {
     RC(upload(all_src, &d_src));
 
     // ---- 5. per-(chunk, half, cmp) parameter blocks + tiles ----
-    std::vector<Tile> tiles[2][2], eh_tiles[2];
+    std::vector<Tile> tiles[2][3], eh_tiles[2], c3d_tiles[2];
     std::vector<FmpParams<T> > fmps[2];
     const int ncmp = cfg.is_real ? 1 : 2;
     cells = 0;
@@ -857,17 +870,70 @@ template <class T> struct Ctx : CtxBase {
             RC(fill_pols(ch, ft, ec, k, cmp, c.pol));
           }
           if (!any) continue;
-          const int pidx = (int)h_half.size();
-          h_half.push_back(P);
-          // tiles: 256 plane positions x a segment of A
+          // interior fast path: full 3-D chunk, plain curl (+ optional E = u*D), 32-bit indexable
+          bool fast = simple && cfg.dim == MEEPCU_D3 && g.ntot_dev < ((size_t)1 << 31);
+          const int ftg = half ? MEEPCU_H_STUFF : MEEPCU_E_STUFF;
+          for (int k = 0; k < 3 && fast; ++k) {
+            const int cc = dir_comp(ft2, k);
+            const CompParams<T> &c = P.comp[k];
+            if (!c.f || !c.g1 || !c.g2 || !ch.have_plus[cc] || !ch.have_minus[cc] ||
+                ch.plus_c[cc] != dir_comp(ftg, (k + 2) % 3) || ch.plus_d[cc] != (k + 1) % 3 ||
+                ch.minus_c[cc] != dir_comp(ftg, (k + 1) % 3) || ch.minus_d[cc] != (k + 2) % 3 ||
+                c.dtdx != (T)cfg.courant)
+              fast = false;
+          }
           const int plane = g.nax[1] * g.pitch;
           int seg = 32;
           if (g.nax[0] <= 48) seg = g.nax[0];
-          for (int a0 = 0; a0 < g.nax[0]; a0 += seg)
-            for (int p0 = 0; p0 < plane; p0 += kThreads) {
-              Tile t = {pidx, a0, std::min(a0 + seg, g.nax[0]), p0};
-              tiles[half][simple ? 0 : 1].push_back(t);
+          if (fast) {
+            Curl3DParams<T> Q;
+            memset(&Q, 0, sizeof Q);
+            Q.nA = g.nax[0]; Q.nB = g.nax[1]; Q.nC = g.nax[2]; Q.pitch = g.pitch;
+            Q.sA = g.pitch * g.nax[1]; Q.sB = g.pitch;
+            Q.cmp = cmp;
+            Q.dt = cfg.dt;
+            Q.dtdx = (T)cfg.courant;
+            for (int k = 0; k < 3; ++k) {
+              const CompParams<T> &c = P.comp[k];
+              Q.f[k] = c.f;
+              Q.g[k] = dev(ch.d.f[dir_comp(ftg, k)][cmp]);
+              Q.e[k] = c.e;
+              Q.u[k] = c.u;
+              for (int ax = 0; ax < 3; ++ax) { Q.lo[k][ax] = c.lo[ax]; Q.hi[k][ax] = c.hi[ax]; }
+              Q.zdb[k] = c.zmask_db; Q.zeh[k] = c.zmask_eh;
+              Q.csrc[k] = c.csrc; Q.ncsrc[k] = c.ncsrc; Q.ca0[k] = c.csrc_amin; Q.ca1[k] = c.csrc_amax;
+              Q.isrc[k] = c.e ? c.isrc : 0; Q.nisrc[k] = c.e ? c.nisrc : 0; Q.ia0[k] = c.isrc_amin; Q.ia1[k] = c.isrc_amax;
+              if (Q.ncsrc[k] || Q.nisrc[k]) Q.any_src = 1;
             }
+            const int qidx = (int)h_c3d.size();
+            h_c3d.push_back(Q);
+            for (int a0 = 0; a0 < g.nax[0]; a0 += seg)
+              for (int p0 = 0; p0 < plane; p0 += kThreads) {
+                Tile t = {qidx, a0, std::min(a0 + seg, g.nax[0]), p0};
+                c3d_tiles[half].push_back(t);
+              }
+          }
+          else {
+            // class: 0 = no conductivity, no polarisations; 1 = everything compiled in
+            int heavy = 0;
+            for (int k = 0; k < 3; ++k) {
+              if (P.comp[k].f && P.comp[k].npol) heavy = std::max(heavy, 1);
+              if (P.comp[k].f && P.comp[k].cnd) heavy = 2;
+            }
+            // march along the longer outer axis: thin PML slabs still give long streams
+            P.march = (g.nax[1] > g.nax[0]) ? 1 : 0;
+            const int n_m = P.march ? g.nax[1] : g.nax[0], n_o = P.march ? g.nax[0] : g.nax[1];
+            const int pidx = (int)h_half.size();
+            h_half.push_back(P);
+            const int gplane = n_o * g.pitch;
+            const int gseg = n_m <= 48 ? n_m : 32;
+            for (int a0 = 0; a0 < n_m; a0 += gseg)
+              for (int p0 = 0; p0 < gplane; p0 += kThreads) {
+                Tile t = {pidx, a0, std::min(a0 + gseg, n_m), p0};
+                tiles[half][heavy].push_back(t);
+              }
+            simple = heavy == 0; // profiling class below
+          }
           // algorithmic bytes: every array element once per read and once per write
           for (int k = 0; k < 3; ++k) {
             const CompParams<T> &c = P.comp[k];
@@ -887,7 +953,7 @@ template <class T> struct Ctx : CtxBase {
               }
             }
             alg_bytes += (long long)v * nc * (long long)sizeof(T);
-            kc_bytes[(half ? KC_HALF_D_SIMPLE : KC_HALF_B_SIMPLE) + (simple ? 0 : 1)] += (long long)v * nc * (long long)sizeof(T);
+            kc_bytes[fast ? (half ? KC_CURL3D_D : KC_CURL3D_B) : (half ? KC_HALF_D_SIMPLE : KC_HALF_B_SIMPLE) + (simple ? 0 : 1)] += (long long)v * nc * (long long)sizeof(T);
           }
         }
         // ---- general E/H components of this chunk ----
@@ -993,9 +1059,14 @@ template <class T> struct Ctx : CtxBase {
       }
     }
     RC(upload(h_half, &d_half));
+    RC(upload(h_c3d, &d_c3d));
+    for (int half = 0; half < 2; ++half) {
+      n_c3d_tiles[half] = (int)c3d_tiles[half].size();
+      RC(upload(c3d_tiles[half], &d_c3d_tiles[half]));
+    }
     RC(upload(h_eh, &d_eh));
     for (int half = 0; half < 2; ++half) {
-      for (int cl = 0; cl < 2; ++cl) {
+      for (int cl = 0; cl < 3; ++cl) {
         n_tiles[half][cl] = (int)tiles[half][cl].size();
         RC(upload(tiles[half][cl], &d_tiles[half][cl]));
       }
@@ -1180,8 +1251,9 @@ template <class T> struct Ctx : CtxBase {
     return MEEPCU_OK;
   }
   int get_kernel_times(meepcu_kernel_time *out, int cap, int *n) {
-    static const char *names[KC_COUNT] = {"k_half<B/H,simple>", "k_half<B/H,general>", "k_half<D/E,simple>",
-                                          "k_half<D/E,general>", "k_conn", "k_fmp", "k_eh_general", "k_dft"};
+    static const char *names[KC_COUNT] = {"k_halfg<B/H,pml>", "k_halfg<B/H,cond+pol>", "k_halfg<D/E,pml>",
+                                          "k_halfg<D/E,cond+pol>", "k_conn", "k_fmp", "k_eh_general", "k_dft",
+                                          "k_curl3d<B/H>", "k_curl3d<D/E>"};
     int m = 0;
     for (int k = 0; k < KC_COUNT && m < cap; ++k) {
       memset(&out[m], 0, sizeof out[m]);
@@ -1208,15 +1280,30 @@ template <class T> struct Ctx : CtxBase {
   }
 
   int launch_half(int half, const double *smp) {
+    if (n_c3d_tiles[half]) {
+      RC(prof_begin(half ? KC_CURL3D_D : KC_CURL3D_B));
+      if (half)
+        k_curl3d<T, true><<<n_c3d_tiles[half], kThreads, 0, st>>>(d_c3d, d_c3d_tiles[half], smp);
+      else
+        k_curl3d<T, false><<<n_c3d_tiles[half], kThreads, 0, st>>>(d_c3d, d_c3d_tiles[half], smp);
+      RC(prof_end());
+      launches++;
+    }
     if (n_tiles[half][0]) {
       RC(prof_begin(half ? KC_HALF_D_SIMPLE : KC_HALF_B_SIMPLE));
-      k_half<T, true><<<n_tiles[half][0], kThreads, 0, st>>>(d_half, d_tiles[half][0], smp);
+      k_halfg<T, false, false><<<n_tiles[half][0], kThreads, 0, st>>>(d_half, d_tiles[half][0], smp);
       RC(prof_end());
       launches++;
     }
     if (n_tiles[half][1]) {
       RC(prof_begin(half ? KC_HALF_D_GENERAL : KC_HALF_B_GENERAL));
-      k_half<T, false><<<n_tiles[half][1], kThreads, 0, st>>>(d_half, d_tiles[half][1], smp);
+      k_halfg<T, false, true><<<n_tiles[half][1], kThreads, 0, st>>>(d_half, d_tiles[half][1], smp);
+      RC(prof_end());
+      launches++;
+    }
+    if (n_tiles[half][2]) {
+      RC(prof_begin(half ? KC_HALF_D_GENERAL : KC_HALF_B_GENERAL));
+      k_halfg<T, true, true><<<n_tiles[half][2], kThreads, 0, st>>>(d_half, d_tiles[half][2], smp);
       RC(prof_end());
       launches++;
     }
@@ -1376,8 +1463,8 @@ template <class T> struct Ctx : CtxBase {
   int get_timers(double out[22]) {
     // reference time_sink numbering (src/meep.hpp:1610-1633); seconds of device time
     for (int i = 0; i < 22; ++i) out[i] = 0;
-    out[10] = (kc_ms[KC_HALF_B_SIMPLE] + kc_ms[KC_HALF_B_GENERAL]) * 1e-3; // FieldUpdateB (+H, fused)
-    out[12] = (kc_ms[KC_HALF_D_SIMPLE] + kc_ms[KC_HALF_D_GENERAL]) * 1e-3; // FieldUpdateD (+E, fused)
+    out[10] = (kc_ms[KC_HALF_B_SIMPLE] + kc_ms[KC_HALF_B_GENERAL] + kc_ms[KC_CURL3D_B]) * 1e-3; // FieldUpdateB (+H, fused)
+    out[12] = (kc_ms[KC_HALF_D_SIMPLE] + kc_ms[KC_HALF_D_GENERAL] + kc_ms[KC_CURL3D_D]) * 1e-3; // FieldUpdateD (+E, fused)
     out[13] = (kc_ms[KC_FMP] + kc_ms[KC_EH_GENERAL]) * 1e-3;               // FieldUpdateE (unfused part)
     out[2] = kc_ms[KC_CONN] * 1e-3;                                        // Boundaries
     out[6] = kc_ms[KC_DFT] * 1e-3;                                         // FourierTransforming
