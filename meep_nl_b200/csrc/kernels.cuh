@@ -90,10 +90,12 @@ template <class T> struct HalfParams { // one chunk, one of {B/H, D/E}, one cmp
 };
 
 struct Tile {
-  int param; // index into the HalfParams table
+  int param; // index into the parameter table of the kernel
   int a0, a1;
-  int p0; // first position of the flattened (B,C) plane
+  int p0;    // first position of the flattened plane; bit 31 set: the tile may contain source points
+             // or metal planes (k_curl3d then runs the loop body that checks for them)
 };
+constexpr int kTileSpecial = 1 << 30;
 
 // meepcu_src_sample layout: current_B[2], dipole_H[2], current_D[2], dipole_E[2]
 __device__ __forceinline__ double2 sample_current(const double *smp, int tid, int is_D) {
@@ -538,12 +540,12 @@ template <class T> struct Curl3DParams {
   int ca0[3], ca1[3], ia0[3], ia1[3];
 };
 
-template <class T, bool IS_D, int K>
+template <class T, bool IS_D, int K, bool SPECIAL>
 __device__ __forceinline__ void curl3d_finish(const Curl3DParams<T> &P, int i, int ia, int ib, int ic,
-                                              T curl, const double *__restrict__ smp) {
-  T *__restrict__ f = P.f[K];
-  T fnew = f[i] - P.dtdx * curl; // step_generic.cpp:108
-  if (P.any_src && P.ncsrc[K] && ia >= P.ca0[K] && ia <= P.ca1[K]) { // step.cpp:296-319
+                                              T curl, T fold, T uval, T *__restrict__ f, T *__restrict__ e,
+                                              bool has_u, const double *__restrict__ smp) {
+  T fnew = fold - P.dtdx * curl; // step_generic.cpp:108
+  if (SPECIAL && P.any_src && P.ncsrc[K] && ia >= P.ca0[K] && ia <= P.ca1[K]) { // step.cpp:296-319
     const SrcEntry *tab = P.csrc[K];
     for (int j = src_lower_bound(tab, P.ncsrc[K], i); j < P.ncsrc[K] && tab[j].idx == i; ++j) {
       const SrcEntry e = tab[j];
@@ -554,12 +556,11 @@ __device__ __forceinline__ void curl3d_finish(const Curl3DParams<T> &P, int i, i
       fnew = (T)((double)fnew - (P.cmp ? A.y : A.x));
     }
   }
-  if (on_zero_plane<T>(P.zdb[K], P.lo[K], P.hi[K], ia, ib, ic)) fnew = 0;
+  if (SPECIAL && on_zero_plane<T>(P.zdb[K], P.lo[K], P.hi[K], ia, ib, ic)) fnew = 0;
   f[i] = fnew;
-  T *__restrict__ e = P.e[K];
   if (!e) return;
   T fmp = fnew;
-  if (P.any_src && P.nisrc[K] && ia >= P.ia0[K] && ia <= P.ia1[K]) { // update_eh.cpp:136-146
+  if (SPECIAL && P.any_src && P.nisrc[K] && ia >= P.ia0[K] && ia <= P.ia1[K]) { // update_eh.cpp:136-146
     const SrcEntry *tab = P.isrc[K];
     for (int j = src_lower_bound(tab, P.nisrc[K], i); j < P.nisrc[K] && tab[j].idx == i; ++j) {
       const SrcEntry se = tab[j];
@@ -568,33 +569,14 @@ __device__ __forceinline__ void curl3d_finish(const Curl3DParams<T> &P, int i, i
       fmp = (T)((double)fmp - (P.cmp ? A.y : A.x));
     }
   }
-  const T *__restrict__ u = P.u[K];
-  T enew = u ? (fmp * __ldg(u + i)) : fmp; // step_generic.cpp:891-894,903
-  if (on_zero_plane<T>(P.zeh[K], P.lo[K], P.hi[K], ia, ib, ic)) enew = 0;
+  T enew = has_u ? (fmp * uval) : fmp; // step_generic.cpp:891-894,903
+  if (SPECIAL && on_zero_plane<T>(P.zeh[K], P.lo[K], P.hi[K], ia, ib, ic)) enew = 0;
   e[i] = enew;
 }
 
-template <class T, bool IS_D>
-__global__ void __launch_bounds__(kThreads, 4)
-    k_curl3d(const Curl3DParams<T> *__restrict__ params, const Tile *__restrict__ tiles,
-             const double *__restrict__ smp) {
-  __shared__ Curl3DParams<T> P;
-  const Tile t = tiles[blockIdx.x];
-  {
-    const int nw = (int)(sizeof(Curl3DParams<T>) / 4);
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(params + t.param);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(&P);
-    for (int k = threadIdx.x; k < nw; k += kThreads) dst[k] = src[k];
-  }
-  __syncthreads();
-  const int p = t.p0 + threadIdx.x;
-  const int ib = p / P.pitch, ic = p - ib * P.pitch;
-  if (ib >= P.nB || ic >= P.nC) return;
-  bool act[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k)
-    act[k] = ib >= P.lo[k][1] && ib <= P.hi[k][1] && ic >= P.lo[k][2] && ic <= P.hi[k][2];
-  if (!(act[0] || act[1] || act[2])) return;
+template <class T, bool IS_D, bool SPECIAL>
+__device__ __forceinline__ void curl3d_loop(const Curl3DParams<T> &P, const Tile t, int ib, int ic,
+                                            const bool act[3], const double *__restrict__ smp) {
   const int sA = P.sA, nA = P.nA;
   // neighbour offsets, clamped so that loads whose value no owned component consumes stay in bounds
   int oy, oz;
@@ -609,6 +591,16 @@ __global__ void __launch_bounds__(kThreads, 4)
   const T *__restrict__ gx = P.g[0];
   const T *__restrict__ gy = P.g[1];
   const T *__restrict__ gz = P.g[2];
+  T *__restrict__ f0 = P.f[0];
+  T *__restrict__ f1 = P.f[1];
+  T *__restrict__ f2 = P.f[2];
+  T *__restrict__ e0 = P.e[0];
+  T *__restrict__ e1 = P.e[1];
+  T *__restrict__ e2 = P.e[2];
+  const T *__restrict__ u0 = P.u[0];
+  const T *__restrict__ u1 = P.u[1];
+  const T *__restrict__ u2 = P.u[2];
+  const bool hu0 = e0 && u0, hu1 = e1 && u1, hu2 = e2 && u2;
   int i = t.a0 * sA + ib * P.sB + ic;
   T ry, rz; // g_y, g_z of the plane the x-difference needs, carried between iterations
   if (!IS_D) {
@@ -624,10 +616,13 @@ __global__ void __launch_bounds__(kThreads, 4)
             hi2 = P.hi[2][0];
 #pragma unroll 2
   for (int ia = t.a0; ia < t.a1; ++ia, i += sA) {
-    T gx0 = __ldg(gx + i), gxy = __ldg(gx + i + oy), gxz = __ldg(gx + i + oz);
-    T gy0, gyz, gz0, gzy, gyx, gzx;
-    gyz = __ldg(gy + i + oz);
-    gzy = __ldg(gz + i + oy);
+    const bool on0 = act[0] && ia >= lo0 && ia <= hi0, on1 = act[1] && ia >= lo1 && ia <= hi1,
+               on2 = act[2] && ia >= lo2 && ia <= hi2;
+    // ---- every load of this plane first ----
+    const T gx0 = __ldg(gx + i), gxy = __ldg(gx + i + oy), gxz = __ldg(gx + i + oz);
+    const T gyz = __ldg(gy + i + oz);
+    const T gzy = __ldg(gz + i + oy);
+    T gy0, gz0, gyx, gzx;
     if (!IS_D) {
       const int ox = (ia + 1 < nA) ? sA : 0;
       gy0 = ry;
@@ -645,15 +640,51 @@ __global__ void __launch_bounds__(kThreads, 4)
       ry = gy0;
       rz = gz0;
     }
+    T fo0 = 0, fo1 = 0, fo2 = 0, uv0 = 0, uv1 = 0, uv2 = 0;
+    if (on0) fo0 = f0[i];
+    if (on1) fo1 = f1[i];
+    if (on2) fo2 = f2[i];
+    if (hu0 && on0) uv0 = __ldg(u0 + i);
+    if (hu1 && on1) uv1 = __ldg(u1 + i);
+    if (hu2 && on2) uv2 = __ldg(u2 + i);
     // component x: g1 = g_z (d/dy), g2 = g_y (d/dz);  y: g1 = g_x (d/dz), g2 = g_z (d/dx);
     // z: g1 = g_y (d/dx), g2 = g_x (d/dy)      -- (g1[i+s1] - g1[i] + g2[i] - g2[i+s2])
-    if (act[0] && ia >= lo0 && ia <= hi0)
-      curl3d_finish<T, IS_D, 0>(P, i, ia, ib, ic, (gzy - gz0 + gy0 - gyz), smp);
-    if (act[1] && ia >= lo1 && ia <= hi1)
-      curl3d_finish<T, IS_D, 1>(P, i, ia, ib, ic, (gxz - gx0 + gz0 - gzx), smp);
-    if (act[2] && ia >= lo2 && ia <= hi2)
-      curl3d_finish<T, IS_D, 2>(P, i, ia, ib, ic, (gyx - gy0 + gx0 - gxy), smp);
+    if (on0)
+      curl3d_finish<T, IS_D, 0, SPECIAL>(P, i, ia, ib, ic, (gzy - gz0 + gy0 - gyz), fo0, uv0, f0, e0, hu0, smp);
+    if (on1)
+      curl3d_finish<T, IS_D, 1, SPECIAL>(P, i, ia, ib, ic, (gxz - gx0 + gz0 - gzx), fo1, uv1, f1, e1, hu1, smp);
+    if (on2)
+      curl3d_finish<T, IS_D, 2, SPECIAL>(P, i, ia, ib, ic, (gyx - gy0 + gx0 - gxy), fo2, uv2, f2, e2, hu2, smp);
   }
+}
+
+template <class T, bool IS_D>
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 3 : 4)
+    k_curl3d(const Curl3DParams<T> *__restrict__ params, const Tile *__restrict__ tiles,
+             const double *__restrict__ smp) {
+  __shared__ Curl3DParams<T> P;
+  Tile t = tiles[blockIdx.x];
+  const bool special = (t.p0 & kTileSpecial) != 0;
+  t.p0 &= ~kTileSpecial;
+  {
+    const int nw = (int)(sizeof(Curl3DParams<T>) / 4);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(params + t.param);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&P);
+    for (int k = threadIdx.x; k < nw; k += kThreads) dst[k] = src[k];
+  }
+  __syncthreads();
+  const int p = t.p0 + threadIdx.x;
+  const int ib = p / P.pitch, ic = p - ib * P.pitch;
+  if (ib >= P.nB || ic >= P.nC) return;
+  bool act[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    act[k] = ib >= P.lo[k][1] && ib <= P.hi[k][1] && ic >= P.lo[k][2] && ic <= P.hi[k][2];
+  if (!(act[0] || act[1] || act[2])) return;
+  if (special)
+    curl3d_loop<T, IS_D, true>(P, t, ib, ic, act, smp);
+  else
+    curl3d_loop<T, IS_D, false>(P, t, ib, ic, act, smp);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -212,8 +212,8 @@ template <class T> struct Ctx : CtxBase {
   std::map<const char *, ArrayRec> arrays; // by host base address
   char *arena;
   size_t arena_bytes;
-  cudaStream_t st;
-  cudaEvent_t ev0, ev1;
+  cudaStream_t st, st2; // st2: the PML/general tiles run beside the interior tiles of the same half step
+  cudaEvent_t ev0, ev1, ev_fork, ev_join;
   std::vector<char *> extra_dev; // other device allocations to free
 
   // tables
@@ -271,7 +271,7 @@ template <class T> struct Ctx : CtxBase {
   int64_t kc_bytes[KC_COUNT];
   double sink_ms[22];
 
-  Ctx() : arena(0), arena_bytes(0), st(0), ev0(0), ev1(0), d_half(0), d_eh(0), d_dft(0),
+  Ctx() : arena(0), arena_bytes(0), st(0), st2(0), ev0(0), ev1(0), ev_fork(0), ev_join(0), d_half(0), d_eh(0), d_dft(0),
           d_dft_work(0), n_dft_work(0), phase_row(0), d_phase_off(0), d_flags(0), d_src(0),
           launches(0), steps_done(0), cells(0), alg_bytes(0), last_ms(0), profiling(false), ev_used(0) {
     memset(kc_ms, 0, sizeof kc_ms);
@@ -303,6 +303,9 @@ template <class T> struct Ctx : CtxBase {
     for (size_t i = 0; i < ev_pool.size(); ++i) cudaEventDestroy(ev_pool[i]);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (st2) cudaStreamDestroy(st2);
     if (st) cudaStreamDestroy(st);
   }
 
@@ -599,8 +602,11 @@ template <class T> struct Ctx : CtxBase {
       return fail(MEEPCU_ECUDA, "no CUDA device: libmeepcuda has no CPU fallback");
     CU(cudaSetDevice(cfg.device));
     CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
     CU(cudaEventCreate(&ev0));
     CU(cudaEventCreate(&ev1));
+    CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     if (cfg.dim == MEEPCU_D2 && cfg.beta != 0)
       return fail(MEEPCU_EUNSUPPORTED, "beta != 0 (step_beta) is not on the GPU path yet");
 
@@ -907,9 +913,18 @@ template <class T> struct Ctx : CtxBase {
             }
             const int qidx = (int)h_c3d.size();
             h_c3d.push_back(Q);
+            bool any_zero = false;
+            for (int k = 0; k < 3; ++k)
+              if (Q.zdb[k] || Q.zeh[k]) any_zero = true;
             for (int a0 = 0; a0 < g.nax[0]; a0 += seg)
               for (int p0 = 0; p0 < plane; p0 += kThreads) {
-                Tile t = {qidx, a0, std::min(a0 + seg, g.nax[0]), p0};
+                const int a1 = std::min(a0 + seg, g.nax[0]);
+                bool special = any_zero; // metal planes: checked per point in the special body
+                for (int k = 0; k < 3; ++k) {
+                  if (Q.ncsrc[k] && a0 <= Q.ca1[k] && a1 > Q.ca0[k]) special = true;
+                  if (Q.nisrc[k] && a0 <= Q.ia1[k] && a1 > Q.ia0[k]) special = true;
+                }
+                Tile t = {qidx, a0, a1, p0 | (special ? kTileSpecial : 0)};
                 c3d_tiles[half].push_back(t);
               }
           }
@@ -1280,6 +1295,34 @@ template <class T> struct Ctx : CtxBase {
   }
 
   int launch_half(int half, const double *smp) {
+    // The interior tiles (k_curl3d) and the PML / general tiles (k_halfg) of one half step touch
+    // disjoint chunks, so they run side by side on two streams; everything else is ordered after
+    // both.  While profiling they are serialised so that each kernel's event time is its own.
+    const bool have_g = n_tiles[half][0] || n_tiles[half][1] || n_tiles[half][2];
+    const bool fork = have_g && n_c3d_tiles[half] && !profiling;
+    cudaStream_t sg = fork ? st2 : st;
+    if (fork) {
+      CU(cudaEventRecord(ev_fork, st));
+      CU(cudaStreamWaitEvent(st2, ev_fork, 0));
+    }
+    if (n_tiles[half][0]) {
+      RC(prof_begin(half ? KC_HALF_D_SIMPLE : KC_HALF_B_SIMPLE));
+      k_halfg<T, false, false><<<n_tiles[half][0], kThreads, 0, sg>>>(d_half, d_tiles[half][0], smp);
+      RC(prof_end());
+      launches++;
+    }
+    if (n_tiles[half][1]) {
+      RC(prof_begin(half ? KC_HALF_D_GENERAL : KC_HALF_B_GENERAL));
+      k_halfg<T, false, true><<<n_tiles[half][1], kThreads, 0, sg>>>(d_half, d_tiles[half][1], smp);
+      RC(prof_end());
+      launches++;
+    }
+    if (n_tiles[half][2]) {
+      RC(prof_begin(half ? KC_HALF_D_GENERAL : KC_HALF_B_GENERAL));
+      k_halfg<T, true, true><<<n_tiles[half][2], kThreads, 0, sg>>>(d_half, d_tiles[half][2], smp);
+      RC(prof_end());
+      launches++;
+    }
     if (n_c3d_tiles[half]) {
       RC(prof_begin(half ? KC_CURL3D_D : KC_CURL3D_B));
       if (half)
@@ -1289,23 +1332,9 @@ template <class T> struct Ctx : CtxBase {
       RC(prof_end());
       launches++;
     }
-    if (n_tiles[half][0]) {
-      RC(prof_begin(half ? KC_HALF_D_SIMPLE : KC_HALF_B_SIMPLE));
-      k_halfg<T, false, false><<<n_tiles[half][0], kThreads, 0, st>>>(d_half, d_tiles[half][0], smp);
-      RC(prof_end());
-      launches++;
-    }
-    if (n_tiles[half][1]) {
-      RC(prof_begin(half ? KC_HALF_D_GENERAL : KC_HALF_B_GENERAL));
-      k_halfg<T, false, true><<<n_tiles[half][1], kThreads, 0, st>>>(d_half, d_tiles[half][1], smp);
-      RC(prof_end());
-      launches++;
-    }
-    if (n_tiles[half][2]) {
-      RC(prof_begin(half ? KC_HALF_D_GENERAL : KC_HALF_B_GENERAL));
-      k_halfg<T, true, true><<<n_tiles[half][2], kThreads, 0, st>>>(d_half, d_tiles[half][2], smp);
-      RC(prof_end());
-      launches++;
+    if (fork) {
+      CU(cudaEventRecord(ev_join, st2));
+      CU(cudaStreamWaitEvent(st, ev_join, 0));
     }
     const int ftd = half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF;
     const int fte = half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF;
