@@ -121,6 +121,8 @@ __device__ __forceinline__ double2 cmul(double a, double b, double c, double d) 
   return make_double2(a * c - b * d, a * d + b * c);
 }
 
+__device__ __forceinline__ int pick3(int axis, int a, int b, int c) { return axis == 0 ? a : (axis == 1 ? b : c); }
+
 template <class T>
 __device__ __forceinline__ bool on_zero_plane(unsigned m, const int lo[3], const int hi[3], int ia,
                                               int ib, int ic) {
@@ -145,8 +147,7 @@ __device__ __forceinline__ void update_point(const CompParams<T> &c, long long i
     fnew = c.f[i] - c.dtdx * curl; // :108,112
   }
   else {
-    const int idx3[3] = {ia, ib, ic};
-    T fold = c.f[i];
+      T fold = c.f[i];
     if (c.kaxis < 0) {
       if (c.kuaxis < 0) {
         if (c.cnd) // :95,101
@@ -155,7 +156,7 @@ __device__ __forceinline__ void update_point(const CompParams<T> &c, long long i
           fnew = fold - c.dtdx * curl;
       }
       else { // :121-154
-        const int ku = 2 * idx3[c.kuaxis] + c.kuoff;
+        const int ku = 2 * pick3(c.kuaxis, ia, ib, ic) + c.kuoff;
         T fprev = c.fu[i], fun;
         if (c.cnd)
           fun = ((1 - c.dt2 * c.cnd[i]) * fprev - c.dtdx * curl) * c.cndinv[i];
@@ -166,7 +167,7 @@ __device__ __forceinline__ void update_point(const CompParams<T> &c, long long i
       }
     }
     else {
-      const int k = 2 * idx3[c.kaxis] + c.koff;
+      const int k = 2 * pick3(c.kaxis, ia, ib, ic) + c.koff;
       if (c.kuaxis < 0) { // :164-196
         if (c.cnd) {
           T fcnd_prev = c.fcnd[i];
@@ -178,7 +179,7 @@ __device__ __forceinline__ void update_point(const CompParams<T> &c, long long i
           fnew = ((c.kap[k] - c.sig[k]) * fold - c.dtdx * curl) * c.siginv[k];
       }
       else { // :199-250
-        const int ku = 2 * idx3[c.kuaxis] + c.kuoff;
+        const int ku = 2 * pick3(c.kuaxis, ia, ib, ic) + c.kuoff;
         T fprev = c.fu[i], fun;
         if (c.cnd) {
           T fcnd_prev = c.fcnd[i];
@@ -232,8 +233,7 @@ __device__ __forceinline__ void update_point(const CompParams<T> &c, long long i
   const T gu = c.u ? (fmp * c.u[i]) : fmp;
   T enew, w;
   if (!SIMPLE && c.fw) { // PML: step_generic.cpp:708-724
-    const int idx3[3] = {ia, ib, ic};
-    const int kw = 2 * idx3[c.kwaxis] + c.kwoff;
+      const int kw = 2 * pick3(c.kwaxis, ia, ib, ic) + c.kwoff;
     const T fwprev = c.fw[i], kapwkw = c.kapw[kw], sigwkw = c.sigw[kw];
     c.fw[i] = gu;
     enew = c.e[i] + ((kapwkw + sigwkw) * gu - (kapwkw - sigwkw) * fwprev);
@@ -309,7 +309,7 @@ template <class T, bool HAS_COND, bool HAS_POL> struct PointVals {
 };
 
 template <class T, bool HAS_COND, bool HAS_POL>
-__device__ __forceinline__ void gather_point(const CompParams<T> &c, long long i,
+__device__ __forceinline__ void gather_point(const CompParams<T> &c, const PolParams<T> *pol, long long i,
                                              PointVals<T, HAS_COND, HAS_POL> &v) {
   v.g1p = __ldg(c.g1 + i + c.s1);
   v.g1 = __ldg(c.g1 + i);
@@ -333,11 +333,11 @@ __device__ __forceinline__ void gather_point(const CompParams<T> &c, long long i
     if (HAS_POL) {
 #pragma unroll
       for (int ip = 0; ip < kMaxPol; ++ip)
-        if (ip < c.npol && c.pol[ip].p) {
-          v.p[ip] = c.pol[ip].p[i];
-          if (c.pol[ip].s) {
-            v.pp[ip] = c.pol[ip].pp[i];
-            v.s[ip] = __ldg(c.pol[ip].s + i);
+        if (ip < c.npol && pol[ip].p) {
+          v.p[ip] = pol[ip].p[i];
+          if (pol[ip].s) {
+            v.pp[ip] = pol[ip].pp[i];
+            v.s[ip] = __ldg(pol[ip].s + i);
           }
         }
     }
@@ -345,10 +345,9 @@ __device__ __forceinline__ void gather_point(const CompParams<T> &c, long long i
 }
 
 template <class T, bool HAS_COND, bool HAS_POL>
-__device__ __forceinline__ void finish_point(const CompParams<T> &c, long long i, int ia, int ib, int ic,
+__device__ __forceinline__ void finish_point(const CompParams<T> &c, const PolParams<T> *pol, long long i, int ia, int ib, int ic,
                                              const PointVals<T, HAS_COND, HAS_POL> &v,
                                              const double *__restrict__ smp, int is_D, int cmp, double dt) {
-  const int idx3[3] = {ia, ib, ic};
   // ---------------- step_curl (step_generic.cpp:89-252) ----------------
   T curl;
   if (c.g2)
@@ -366,7 +365,7 @@ __device__ __forceinline__ void finish_point(const CompParams<T> &c, long long i
         fnew = fold - c.dtdx * curl;
     }
     else {
-      const int ku = 2 * idx3[c.kuaxis] + c.kuoff;
+      const int ku = 2 * pick3(c.kuaxis, ia, ib, ic) + c.kuoff;
       const T fprev = v.fu;
       T fun;
       if (cond)
@@ -378,7 +377,7 @@ __device__ __forceinline__ void finish_point(const CompParams<T> &c, long long i
     }
   }
   else {
-    const int k = 2 * idx3[c.kaxis] + c.koff;
+    const int k = 2 * pick3(c.kaxis, ia, ib, ic) + c.koff;
     const T kap = __ldg(c.kap + k), sig = __ldg(c.sig + k), siginv = __ldg(c.siginv + k);
     if (c.kuaxis < 0) {
       if (cond) {
@@ -391,7 +390,7 @@ __device__ __forceinline__ void finish_point(const CompParams<T> &c, long long i
         fnew = ((kap - sig) * fold - c.dtdx * curl) * siginv;
     }
     else {
-      const int ku = 2 * idx3[c.kuaxis] + c.kuoff;
+      const int ku = 2 * pick3(c.kuaxis, ia, ib, ic) + c.kuoff;
       const T fprev = v.fu;
       T fun;
       if (cond) {
@@ -431,7 +430,7 @@ __device__ __forceinline__ void finish_point(const CompParams<T> &c, long long i
   if (HAS_POL) {
 #pragma unroll
     for (int ip = 0; ip < kMaxPol; ++ip)
-      if (ip < c.npol && c.pol[ip].p) fmp -= v.p[ip];
+      if (ip < c.npol && pol[ip].p) fmp -= v.p[ip];
   }
   if (c.nisrc && ia >= c.isrc_amin && ia <= c.isrc_amax) {
     for (int j = src_lower_bound(c.isrc, c.nisrc, i); j < c.nisrc && c.isrc[j].idx == i; ++j) {
@@ -444,7 +443,7 @@ __device__ __forceinline__ void finish_point(const CompParams<T> &c, long long i
   const T gu = c.u ? (fmp * v.u) : fmp;
   T enew;
   if (c.fw) {
-    const int kw = 2 * idx3[c.kwaxis] + c.kwoff;
+    const int kw = 2 * pick3(c.kwaxis, ia, ib, ic) + c.kwoff;
     const T kapwkw = __ldg(c.kapw + kw), sigwkw = __ldg(c.sigw + kw);
     c.fw[i] = gu;
     enew = v.e + ((kapwkw + sigwkw) * gu - (kapwkw - sigwkw) * v.fw);
@@ -454,8 +453,8 @@ __device__ __forceinline__ void finish_point(const CompParams<T> &c, long long i
   if (HAS_POL) {
 #pragma unroll
     for (int ip = 0; ip < kMaxPol; ++ip)
-      if (ip < c.npol && c.pol[ip].p && c.pol[ip].s) {
-        const PolParams<T> &q = c.pol[ip];
+      if (ip < c.npol && pol[ip].p && pol[ip].s) {
+        const PolParams<T> &q = pol[ip];
         const T pcur = v.p[ip];
         q.p[i] = q.gamma1inv * (pcur * (2 - q.omega0dtsqr_denom) - q.gamma1 * v.pp[ip] +
                                 q.omega0dtsqr * (v.s[ip] * gu));
@@ -466,47 +465,54 @@ __device__ __forceinline__ void finish_point(const CompParams<T> &c, long long i
   c.e[i] = enew;
 }
 
+// One CTA = one COMPONENT of one tile (Tile::param = 4*HalfParams index + component): the
+// component's parameters live in registers for the whole march, and the three components of a
+// spatial tile sit next to each other in the tile table so that their shared operands meet in L2.
+template <class T> struct HalfHeader { // leading, component-independent part of HalfParams<T>
+  int nA, nB, nC, pitch;
+  long long sA, sB;
+  int is_D, cmp, march, pad_;
+  double dt;
+};
+
 template <class T, bool HAS_COND, bool HAS_POL>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
     k_halfg(const HalfParams<T> *__restrict__ params, const Tile *__restrict__ tiles,
             const double *__restrict__ smp) {
-  __shared__ HalfParams<T> P;
+  __shared__ HalfHeader<T> H;
+  __shared__ CompParams<T> Csm;
   const Tile t = tiles[blockIdx.x];
+  const int pidx = t.param >> 2, kcomp = t.param & 3;
   {
-    const int nw = (int)(sizeof(HalfParams<T>) / 4);
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(params + t.param);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(&P);
-    for (int k = threadIdx.x; k < nw; k += kThreads) dst[k] = src[k];
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(params + pidx);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&H);
+    for (int k = threadIdx.x; k < (int)(sizeof(HalfHeader<T>) / 4); k += kThreads) dst[k] = src[k];
+    const uint32_t *src2 = reinterpret_cast<const uint32_t *>(&params[pidx].comp[kcomp]);
+    uint32_t *dst2 = reinterpret_cast<uint32_t *>(&Csm);
+    for (int k = threadIdx.x; k < (int)(sizeof(CompParams<T>) / 4); k += kThreads) dst2[k] = src2[k];
   }
   __syncthreads();
   const int p = t.p0 + threadIdx.x;
-  const int io = p / P.pitch, ic = p - io * P.pitch; // io: index on the outer axis we do NOT march
-  const int march = P.march;
-  const int n_other = march ? P.nA : P.nB;
-  if (io >= n_other || ic >= P.nC) return;
-  const int ax_o = march ? 0 : 1, ax_m = march ? 1 : 0;
-  bool act[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const CompParams<T> &c = P.comp[k];
-    act[k] = c.f != nullptr && io >= c.lo[ax_o] && io <= c.hi[ax_o] && ic >= c.lo[2] && ic <= c.hi[2];
-  }
-  if (!(act[0] || act[1] || act[2])) return;
-  const long long s_m = march ? P.sB : P.sA, s_o = march ? P.sA : P.sB;
-  long long i = (long long)t.a0 * s_m + (long long)io * s_o + ic;
-  for (int im = t.a0; im < t.a1; ++im, i += s_m) {
+  const int io = p / H.pitch, ic = p - io * H.pitch; // io: index on the outer axis we do NOT march
+  const int march = H.march;
+  const int n_other = march ? H.nA : H.nB;
+  if (io >= n_other || ic >= H.nC) return;
+  const CompParams<T> c = Csm; // registers
+  const int lo_o = march ? c.lo[0] : c.lo[1], hi_o = march ? c.hi[0] : c.hi[1];
+  const int lo_m = march ? c.lo[1] : c.lo[0], hi_m = march ? c.hi[1] : c.hi[0];
+  if (!(io >= lo_o && io <= hi_o && ic >= c.lo[2] && ic <= c.hi[2])) return;
+  const long long s_m = march ? H.sB : H.sA, s_o = march ? H.sA : H.sB;
+  const int m0 = t.a0 > lo_m ? t.a0 : lo_m;
+  const int m1 = t.a1 - 1 < hi_m ? t.a1 - 1 : hi_m;
+  long long i = (long long)m0 * s_m + (long long)io * s_o + ic;
+  const int is_D = H.is_D, cmp = H.cmp;
+  const double dt = H.dt;
+#pragma unroll 2
+  for (int im = m0; im <= m1; ++im, i += s_m) {
     const int ia = march ? io : im, ib = march ? im : io;
-    PointVals<T, HAS_COND, HAS_POL> v[3];
-    bool on[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const CompParams<T> &c = P.comp[k];
-      on[k] = act[k] && im >= c.lo[ax_m] && im <= c.hi[ax_m];
-      if (on[k]) gather_point<T, HAS_COND, HAS_POL>(c, i, v[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-      if (on[k]) finish_point<T, HAS_COND, HAS_POL>(P.comp[k], i, ia, ib, ic, v[k], smp, P.is_D, P.cmp, P.dt);
+    PointVals<T, HAS_COND, HAS_POL> v;
+    gather_point<T, HAS_COND, HAS_POL>(c, Csm.pol, i, v);
+    finish_point<T, HAS_COND, HAS_POL>(c, Csm.pol, i, ia, ib, ic, v, smp, is_D, cmp, dt);
   }
 }
 
@@ -1010,8 +1016,7 @@ __device__ __forceinline__ void eh_point(const EhParams<T> &q, long long i, int 
   (void)done_nr;
   T enew, w;
   if (q.fw) {
-    const int idx3[3] = {ia, ib, ic};
-    const int kw = 2 * idx3[q.kwaxis] + q.kwoff;
+      const int kw = 2 * pick3(q.kwaxis, ia, ib, ic) + q.kwoff;
     const T fwprev = q.fw[i], kapwkw = q.kapw[kw], sigwkw = q.sigw[kw];
     q.fw[i] = val;
     enew = q.f[i] + ((kapwkw + sigwkw) * val - (kapwkw - sigwkw) * fwprev);

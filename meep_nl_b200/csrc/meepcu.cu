@@ -943,10 +943,12 @@ template <class T> struct Ctx : CtxBase {
             const int gplane = n_o * g.pitch;
             const int gseg = n_m <= 48 ? n_m : 32;
             for (int a0 = 0; a0 < n_m; a0 += gseg)
-              for (int p0 = 0; p0 < gplane; p0 += kThreads) {
-                Tile t = {pidx, a0, std::min(a0 + gseg, n_m), p0};
-                tiles[half][heavy].push_back(t);
-              }
+              for (int p0 = 0; p0 < gplane; p0 += kThreads)
+                for (int k = 0; k < 3; ++k) { // one CTA per component, neighbours in the table
+                  if (!P.comp[k].f) continue;
+                  Tile t = {pidx * 4 + k, a0, std::min(a0 + gseg, n_m), p0};
+                  tiles[half][heavy].push_back(t);
+                }
             simple = heavy == 0; // profiling class below
           }
           // algorithmic bytes: every array element once per read and once per write
