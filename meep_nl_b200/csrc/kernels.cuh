@@ -33,6 +33,13 @@ namespace mcu {
 
 constexpr int kThreads = 256;
 constexpr int kMaxPol = 4;
+#ifndef MCU_PREFETCH_PLANES
+#define MCU_PREFETCH_PLANES 2
+#endif
+
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 struct SrcEntry { // one source point, sorted by device index (stable in reference order)
   long long idx;
@@ -510,6 +517,31 @@ __global__ void __launch_bounds__(kThreads, 3)
 #pragma unroll 2
   for (int im = m0; im <= m1; ++im, i += s_m) {
     const int ia = march ? io : im, ib = march ? im : io;
+    if (MCU_PREFETCH_PLANES > 0 && im + MCU_PREFETCH_PLANES <= m1) {
+      const long long ipf = i + MCU_PREFETCH_PLANES * s_m;
+      prefetch_l2(c.g1 + ipf);
+      if (c.g2) prefetch_l2(c.g2 + ipf);
+      prefetch_l2(c.f + ipf);
+      if (c.fu) prefetch_l2(c.fu + ipf);
+      if (c.e) {
+        if (c.u) prefetch_l2(c.u + ipf);
+        if (c.fw) {
+          prefetch_l2(c.fw + ipf);
+          prefetch_l2(c.e + ipf);
+        }
+        if (HAS_POL) {
+#pragma unroll
+          for (int ip = 0; ip < kMaxPol; ++ip)
+            if (ip < c.npol && Csm.pol[ip].p) {
+              prefetch_l2(Csm.pol[ip].p + ipf);
+              if (Csm.pol[ip].s) {
+                prefetch_l2(Csm.pol[ip].pp + ipf);
+                prefetch_l2(Csm.pol[ip].s + ipf);
+              }
+            }
+        }
+      }
+    }
     PointVals<T, HAS_COND, HAS_POL> v;
     gather_point<T, HAS_COND, HAS_POL>(c, Csm.pol, i, v);
     finish_point<T, HAS_COND, HAS_POL>(c, Csm.pol, i, ia, ib, ic, v, smp, is_D, cmp, dt);
@@ -624,6 +656,20 @@ __device__ __forceinline__ void curl3d_loop(const Curl3DParams<T> &P, const Tile
   for (int ia = t.a0; ia < t.a1; ++ia, i += sA) {
     const bool on0 = act[0] && ia >= lo0 && ia <= hi0, on1 = act[1] && ia >= lo1 && ia <= hi1,
                on2 = act[2] && ia >= lo2 && ia <= hi2;
+    if (MCU_PREFETCH_PLANES > 0 && ia + MCU_PREFETCH_PLANES < nA) {
+      // pull the planes this thread will need a few iterations from now into L2: turns the
+      // DRAM latency of the marching loads into L2 latency without holding registers
+      const int ipf = i + MCU_PREFETCH_PLANES * sA;
+      prefetch_l2(gx + ipf);
+      prefetch_l2(gy + ipf);
+      prefetch_l2(gz + ipf);
+      prefetch_l2(f0 + ipf);
+      prefetch_l2(f1 + ipf);
+      prefetch_l2(f2 + ipf);
+      if (hu0) prefetch_l2(u0 + ipf);
+      if (hu1) prefetch_l2(u1 + ipf);
+      if (hu2) prefetch_l2(u2 + ipf);
+    }
     // ---- every load of this plane first ----
     const T gx0 = __ldg(gx + i), gxy = __ldg(gx + i + oy), gxz = __ldg(gx + i + oz);
     const T gyz = __ldg(gy + i + oz);
