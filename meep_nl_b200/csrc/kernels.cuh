@@ -766,6 +766,36 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// Halo exchange with another rank (replaces the MPI_Isend/Irecv pairs of src/mympi.cpp:107-135):
+// k_pack gathers the outgoing values of one field type into one contiguous buffer per peer
+// (order PHASE | NEGATE | COPY, src/step.cpp:257-268), NCCL moves the buffers over NVLink, and
+// k_unpack applies process_incoming_chunk_data (src/step.cpp:173-224) on the receiving side.
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_pack(const T *const *__restrict__ src, T *__restrict__ buf, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) buf[k] = *src[k];
+}
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+    k_unpack(T *const *__restrict__ dst, const T *__restrict__ buf, const T *__restrict__ phase,
+             const long long *__restrict__ seg, int nseg) {
+  // seg: per peer segment {offset, n_phase(realnums), n_negate, n_copy, phase_offset(complex)}
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int sgi = 0; sgi < nseg; ++sgi) {
+    const long long off = seg[5 * sgi], np = seg[5 * sgi + 1], nn = seg[5 * sgi + 2], nc = seg[5 * sgi + 3],
+                    po = seg[5 * sgi + 4];
+    for (long long k = t0; k < np / 2; k += stride) {
+      const T pr = phase[2 * (po + k)], pi = phase[2 * (po + k) + 1];
+      const T br = buf[off + 2 * k], bi = buf[off + 2 * k + 1];
+      *dst[off + 2 * k] = pr * br - pi * bi;
+      *dst[off + 2 * k + 1] = pr * bi + pi * br;
+    }
+    for (long long k = t0; k < nn; k += stride) *dst[off + np + k] = -buf[off + np + k];
+    for (long long k = t0; k < nc; k += stride) *dst[off + np + nn + k] = buf[off + np + nn + k];
+  }
+}
+
 // zero_metal for lists that are not fused into k_half (general fallback)
 template <class T> __global__ void k_zero(T *const *ptrs, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;

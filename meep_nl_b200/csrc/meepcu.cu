@@ -25,6 +25,7 @@
 #include <map>
 #include <string>
 #include <vector>
+#include <dlfcn.h>
 
 using namespace mcu;
 
@@ -51,6 +52,50 @@ int fail(int code, const char *fmt, ...) {
   do {                                                                                             \
     int rc_ = (call);                                                                              \
     if (rc_ != MEEPCU_OK) return rc_;                                                              \
+  } while (0)
+
+// ---- NCCL, bound at run time so that a single-GPU build has no dependency on it ----------------
+typedef struct { char internal[128]; } nccl_uid;
+typedef void *nccl_comm;
+struct NcclApi {
+  void *h;
+  int (*GetUniqueId)(nccl_uid *);
+  int (*CommInitRank)(nccl_comm *, int, nccl_uid, int);
+  int (*CommDestroy)(nccl_comm);
+  int (*Send)(const void *, size_t, int, int, nccl_comm, cudaStream_t);
+  int (*Recv)(void *, size_t, int, int, nccl_comm, cudaStream_t);
+  int (*GroupStart)();
+  int (*GroupEnd)();
+  const char *(*GetErrorString)(int);
+};
+NcclApi *nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    api.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.h) api.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (api.h) {
+      *(void **)&api.GetUniqueId = dlsym(api.h, "ncclGetUniqueId");
+      *(void **)&api.CommInitRank = dlsym(api.h, "ncclCommInitRank");
+      *(void **)&api.CommDestroy = dlsym(api.h, "ncclCommDestroy");
+      *(void **)&api.Send = dlsym(api.h, "ncclSend");
+      *(void **)&api.Recv = dlsym(api.h, "ncclRecv");
+      *(void **)&api.GroupStart = dlsym(api.h, "ncclGroupStart");
+      *(void **)&api.GroupEnd = dlsym(api.h, "ncclGroupEnd");
+      *(void **)&api.GetErrorString = dlsym(api.h, "ncclGetErrorString");
+      if (!api.GetUniqueId || !api.CommInitRank || !api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd)
+        api.h = 0;
+    }
+  }
+  return api.h ? &api : 0;
+}
+#define NC(call)                                                                                   \
+  do {                                                                                             \
+    int r_ = (call);                                                                               \
+    if (r_ != 0)                                                                                   \
+      return fail(MEEPCU_ENCCL, "%s failed: %s", #call,                                            \
+                  nccl_api()->GetErrorString ? nccl_api()->GetErrorString(r_) : "?");              \
   } while (0)
 
 // ---- component helpers (reference src/meep/vec.hpp:414-592, src/fields.cpp:411-425) -----------
@@ -179,6 +224,8 @@ struct CtxBase {
   virtual int read_value(const void *p, double *out) = 0;
   virtual int get_stats(meepcu_stats *out) = 0;
   virtual int get_timers(double out[22]) = 0;
+  virtual int add_remote(int ft, int kind, int peer, size_t n, const void *const *ptrs, const void *phases, bool recv) = 0;
+  virtual int comm_init(int rank, int nranks, const void *id) = 0;
   virtual int set_profiling(int on) = 0;
   virtual int get_kernel_times(meepcu_kernel_time *out, int cap, int *n) = 0;
 };
@@ -207,6 +254,19 @@ template <class T> struct Ctx : CtxBase {
   std::vector<ChunkH> chunks;
   std::vector<void *> metal[MEEPCU_NUM_FIELD_TYPES];
   PtrList conn[MEEPCU_NUM_FIELD_TYPES][3];
+  // connections whose other end lives on another rank: [ft] -> peer -> kind -> pointers
+  struct RemoteList { std::vector<const void *> ptr[3]; std::vector<char> phases; };
+  std::map<int, RemoteList> rsend[MEEPCU_NUM_FIELD_TYPES], rrecv[MEEPCU_NUM_FIELD_TYPES];
+  struct RemoteDev { // per field type, after finalize
+    const T **d_src; T *d_sendbuf; long long n_send;
+    T **d_dst; T *d_recvbuf; long long n_recv;
+    T *d_phase; long long *d_seg; int nseg;
+    std::vector<int> send_peer, recv_peer;
+    std::vector<long long> send_off, send_n, recv_off, recv_n;
+  };
+  RemoteDev rdev[MEEPCU_NUM_FIELD_TYPES];
+  nccl_comm comm;
+  int my_rank, n_ranks;
 
   // ---- device state (valid after finalize) ----
   std::map<const char *, ArrayRec> arrays; // by host base address
@@ -274,6 +334,11 @@ template <class T> struct Ctx : CtxBase {
   Ctx() : arena(0), arena_bytes(0), st(0), st2(0), ev0(0), ev1(0), ev_fork(0), ev_join(0), d_half(0), d_eh(0), d_dft(0),
           d_dft_work(0), n_dft_work(0), phase_row(0), d_phase_off(0), d_flags(0), d_src(0),
           launches(0), steps_done(0), cells(0), alg_bytes(0), last_ms(0), profiling(false), ev_used(0) {
+    comm = 0;
+    my_rank = 0;
+    n_ranks = 1;
+    memset(rdev, 0, sizeof(RemoteDev) * 0); // vectors inside: value-initialised below
+    for (int ft = 0; ft < MEEPCU_NUM_FIELD_TYPES; ++ft) { rdev[ft].d_src = 0; rdev[ft].d_sendbuf = 0; rdev[ft].n_send = 0; rdev[ft].d_dst = 0; rdev[ft].d_recvbuf = 0; rdev[ft].n_recv = 0; rdev[ft].d_phase = 0; rdev[ft].d_seg = 0; rdev[ft].nseg = 0; }
     memset(kc_ms, 0, sizeof kc_ms);
     memset(kc_launches, 0, sizeof kc_launches);
     memset(kc_bytes, 0, sizeof kc_bytes);
@@ -295,6 +360,7 @@ template <class T> struct Ctx : CtxBase {
     eager_db[0] = eager_db[1] = eager_p[0] = eager_p[1] = false;
   }
   ~Ctx() {
+    if (comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(comm);
     if (arena) cudaFree(arena);
     for (size_t i = 0; i < extra_dev.size(); ++i) cudaFree(extra_dev[i]);
     d_smp.release();
@@ -447,6 +513,106 @@ template <class T> struct Ctx : CtxBase {
       const char *p = (const char *)phases;
       c.phases.insert(c.phases.end(), p, p + (n / 2) * 2 * sizeof(T));
     }
+    return MEEPCU_OK;
+  }
+
+  int add_remote(int ft, int kind, int peer, size_t n, const void *const *ptrs, const void *phases, bool recv) {
+    if (finalized) return fail(MEEPCU_ESTATE, "context already finalized");
+    if (ft < 0 || ft >= MEEPCU_NUM_FIELD_TYPES || kind < 0 || kind > 2 || peer < 0)
+      return fail(MEEPCU_EINVAL, "bad remote connection family");
+    RemoteList &L = (recv ? rrecv : rsend)[ft][peer];
+    L.ptr[kind].insert(L.ptr[kind].end(), ptrs, ptrs + n);
+    if (recv && kind == MEEPCU_CONNECT_PHASE) {
+      if (n % 2) return fail(MEEPCU_EINVAL, "PHASE connections come in (re,im) pairs");
+      const char *p = (const char *)phases;
+      L.phases.insert(L.phases.end(), p, p + (n / 2) * 2 * sizeof(T));
+    }
+    return MEEPCU_OK;
+  }
+  int comm_init(int rank, int nranks, const void *id) {
+    NcclApi *n = nccl_api();
+    if (!n) return fail(MEEPCU_ENCCL, "libnccl.so.2 not found");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(MEEPCU_EINVAL, "bad rank");
+    CU(cudaSetDevice(cfg.device));
+    nccl_uid uid;
+    memcpy(&uid, id, sizeof uid);
+    NC(n->CommInitRank(&comm, nranks, uid, rank));
+    my_rank = rank;
+    n_ranks = nranks;
+    return MEEPCU_OK;
+  }
+  int build_remote() {
+    for (int ft = 0; ft < MEEPCU_NUM_FIELD_TYPES; ++ft) {
+      RemoteDev &R = rdev[ft];
+      if (rsend[ft].empty() && rrecv[ft].empty()) continue;
+      if (!comm) return fail(MEEPCU_ESTATE, "remote connections given but meepcu_comm_init not called");
+      std::vector<const T *> hsrc;
+      for (typename std::map<int, RemoteList>::iterator it = rsend[ft].begin(); it != rsend[ft].end(); ++it) {
+        R.send_peer.push_back(it->first);
+        R.send_off.push_back((long long)hsrc.size());
+        for (int kind = 0; kind < 3; ++kind)
+          for (size_t k = 0; k < it->second.ptr[kind].size(); ++k) {
+            const T *d = dev_elem(it->second.ptr[kind][k]);
+            if (!d) return fail(MEEPCU_EINVAL, "remote send pointer outside the registered arrays");
+            hsrc.push_back(d);
+          }
+        R.send_n.push_back((long long)hsrc.size() - R.send_off.back());
+      }
+      std::vector<T *> hdst;
+      std::vector<T> hphase;
+      std::vector<long long> seg;
+      for (typename std::map<int, RemoteList>::iterator it = rrecv[ft].begin(); it != rrecv[ft].end(); ++it) {
+        R.recv_peer.push_back(it->first);
+        R.recv_off.push_back((long long)hdst.size());
+        seg.push_back((long long)hdst.size());
+        for (int kind = 0; kind < 3; ++kind) {
+          seg.push_back((long long)it->second.ptr[kind].size());
+          for (size_t k = 0; k < it->second.ptr[kind].size(); ++k) {
+            T *d = dev_elem(it->second.ptr[kind][k]);
+            if (!d) return fail(MEEPCU_EINVAL, "remote recv pointer outside the registered arrays");
+            hdst.push_back(d);
+          }
+        }
+        seg.push_back((long long)(hphase.size() / 2));
+        const T *ph = (const T *)it->second.phases.data();
+        hphase.insert(hphase.end(), ph, ph + it->second.phases.size() / sizeof(T));
+        R.recv_n.push_back((long long)hdst.size() - R.recv_off.back());
+      }
+      R.n_send = (long long)hsrc.size();
+      R.n_recv = (long long)hdst.size();
+      R.nseg = (int)R.recv_peer.size();
+      RC(upload(hsrc, &R.d_src));
+      RC(upload(hdst, &R.d_dst));
+      RC(upload(hphase, &R.d_phase));
+      RC(upload(seg, &R.d_seg));
+      if (R.n_send) { CU(cudaMalloc((void **)&R.d_sendbuf, R.n_send * sizeof(T))); extra_dev.push_back((char *)R.d_sendbuf); }
+      if (R.n_recv) { CU(cudaMalloc((void **)&R.d_recvbuf, R.n_recv * sizeof(T))); extra_dev.push_back((char *)R.d_recvbuf); }
+    }
+    return MEEPCU_OK;
+  }
+  int launch_remote(int ft) {
+    RemoteDev &R = rdev[ft];
+    if (!R.n_send && !R.n_recv) return MEEPCU_OK;
+    NcclApi *n = nccl_api();
+    RC(prof_begin(KC_CONN));
+    if (R.n_send) {
+      const int grid = (int)std::min<long long>((R.n_send + kThreads - 1) / kThreads, 148 * 8);
+      k_pack<T><<<grid, kThreads, 0, st>>>(R.d_src, R.d_sendbuf, R.n_send);
+      launches++;
+    }
+    const int dtype = sizeof(T) == 8 ? 8 /* ncclFloat64 */ : 7 /* ncclFloat32 */;
+    NC(n->GroupStart());
+    for (size_t k = 0; k < R.recv_peer.size(); ++k)
+      NC(n->Recv(R.d_recvbuf + R.recv_off[k], (size_t)R.recv_n[k], dtype, R.recv_peer[k], comm, st));
+    for (size_t k = 0; k < R.send_peer.size(); ++k)
+      NC(n->Send(R.d_sendbuf + R.send_off[k], (size_t)R.send_n[k], dtype, R.send_peer[k], comm, st));
+    NC(n->GroupEnd());
+    if (R.n_recv) {
+      const int grid = (int)std::min<long long>((R.n_recv + kThreads - 1) / kThreads, 148 * 8);
+      k_unpack<T><<<grid, kThreads, 0, st>>>(R.d_dst, R.d_recvbuf, R.d_phase, R.d_seg, R.nseg);
+      launches++;
+    }
+    RC(prof_end());
     return MEEPCU_OK;
   }
 
@@ -1123,6 +1289,7 @@ template <class T> struct Ctx : CtxBase {
         }
       }
     // W exchanges are only non-empty for anisotropic susceptibilities (rejected above)
+    RC(build_remote());
 
     // ---- 7. DFT chunks ----
     std::vector<DftWork> work;
@@ -1287,13 +1454,13 @@ template <class T> struct Ctx : CtxBase {
   int launch_conn(int ft) {
     const ConnTable<T> &a = d_conn[ft][0], &b = d_conn[ft][1], &c = d_conn[ft][2];
     const long long n = std::max(a.n / 2, std::max(b.n, c.n));
-    if (n == 0) return MEEPCU_OK;
+    if (n == 0) return launch_remote(ft);
     const int grid = (int)std::min<long long>((n + kThreads - 1) / kThreads, 148 * 16);
     RC(prof_begin(KC_CONN));
     k_conn<T><<<grid, kThreads, 0, st>>>(a, b, c);
     RC(prof_end());
     launches++;
-    return MEEPCU_OK;
+    return launch_remote(ft);
   }
 
   int launch_half(int half, const double *smp) {
@@ -1573,17 +1740,27 @@ int meepcu_add_connections(meepcu_ctx *ctx, int ft, int kind, size_t n, void *co
   CHECK_CTX;
   return ctx->impl->add_conn(ft, kind, n, dst, src, phases);
 }
-int meepcu_add_remote_send(meepcu_ctx *, int, int, int, size_t, const void *const *) {
-  return fail(MEEPCU_EUNSUPPORTED, "multi-rank halo exchange is not built in this round");
+int meepcu_add_remote_send(meepcu_ctx *ctx, int ft, int kind, int peer, size_t n, const void *const *src) {
+  CHECK_CTX;
+  return ctx->impl->add_remote(ft, kind, peer, n, src, 0, false);
 }
-int meepcu_add_remote_recv(meepcu_ctx *, int, int, int, size_t, void *const *, const void *) {
-  return fail(MEEPCU_EUNSUPPORTED, "multi-rank halo exchange is not built in this round");
+int meepcu_add_remote_recv(meepcu_ctx *ctx, int ft, int kind, int peer, size_t n, void *const *dst,
+                           const void *phases) {
+  CHECK_CTX;
+  return ctx->impl->add_remote(ft, kind, peer, n, (const void *const *)dst, phases, true);
 }
-int meepcu_comm_unique_id(void *) {
-  return fail(MEEPCU_EUNSUPPORTED, "multi-rank halo exchange is not built in this round");
+int meepcu_comm_unique_id(void *id128) {
+  NcclApi *n = nccl_api();
+  if (!n) return fail(MEEPCU_ENCCL, "libnccl.so.2 not found");
+  nccl_uid uid;
+  NC(n->GetUniqueId(&uid));
+  memcpy(id128, &uid, sizeof uid);
+  return MEEPCU_OK;
 }
-int meepcu_comm_init(meepcu_ctx *, int, int, const void *) {
-  return fail(MEEPCU_EUNSUPPORTED, "multi-rank halo exchange is not built in this round");
+int meepcu_comm_init(meepcu_ctx *ctx, int rank, int nranks, const void *id128) {
+  CHECK_CTX;
+  if (!id128) return fail(MEEPCU_EINVAL, "null unique id");
+  return ctx->impl->comm_init(rank, nranks, id128);
 }
 int meepcu_finalize(meepcu_ctx *ctx) {
   CHECK_CTX;

@@ -283,6 +283,31 @@ class structure:
             sc.pols.append((sus, ft, arrs))
 
 
+class _Ghost:
+    """stand-in for an array that lives on another rank: same identity / aliasing behaviour as
+    a numpy array in the connection builder, but no memory"""
+
+    class _C:
+        data = 0
+
+    def __init__(self, n, itemsize):
+        self.size, self.itemsize, self.nbytes = n, itemsize, 0
+        self.ctypes = _Ghost._C()
+
+
+def slab_decomposition(gv, nranks, d=0):
+    """cuts (cells) that split direction d into nranks equal slabs, and the chunk -> rank map for a
+    structure built with split={d: cuts} (the reference's split_by_cost with equal voxel counts,
+    src/structure.cpp:66-94, restricted to one direction so that every halo is a contiguous plane)"""
+    n = gv.num[d]
+    cuts = [round(n * k / nranks) for k in range(1, nranks)]
+
+    def rank_of(sc):
+        mid = (sc.gv.io[d] - gv.io[d]) / 2.0 + sc.gv.num[d] / 2.0
+        return min(int(mid * nranks / n), nranks - 1)
+    return cuts, rank_of
+
+
 class fields_chunk:
     def __init__(self, sc, is_real):
         self.s, self.gv = sc, sc.gv
@@ -296,7 +321,14 @@ class fields:
     """fields::fields (src/fields.cpp:32-86) + the lazy allocations of the first step done
     eagerly + connect_the_chunks (src/boundaries.cpp:347-623) + fields::step."""
 
-    def __init__(self, s: structure, backend: A.Backend, nl_mode=A.NL_FORK_LITERAL, device=0):
+    def __init__(self, s: structure, backend: A.Backend, nl_mode=A.NL_FORK_LITERAL, device=0,
+                 rank=0, nranks=1, chunk_rank=None, comm_id=None):
+        """rank / nranks / chunk_rank: the reference's MPI decomposition (structure_chunk::n_proc,
+        src/structure.cpp:126-141): chunk i is time-stepped by rank chunk_rank[i]; arrays of other
+        ranks' chunks are never allocated here, and connections that cross ranks become
+        meepcu_add_remote_send / _recv lists (the MPI_Isend/Irecv pairs of src/mympi.cpp:107-135)."""
+        self.rank, self.nranks, self.comm_id = rank, nranks, comm_id
+        self.chunk_rank = list(chunk_rank) if chunk_rank is not None else [0] * len(s.chunks)
         self.s, self.gv, self.b = s, s.gv, backend
         self.a, self.dt = s.a, s.dt
         self.is_real = 0
@@ -355,30 +387,32 @@ class fields:
         comps = [c for c in range(20) if gvu.has_field(c) and comp_dir(c) < 3]
         if gvu.dim == D2:
             pass  # both TE and TM allocated (like aniso2d / 3-D); simple and always valid
-        for fc in self.chunks:
+        for ci, fc in enumerate(self.chunks):
             sc, gv = fc.s, fc.gv
             n = gv.ntot
+            fc.mine = self.chunk_rank[ci] == self.rank
+            zeros = (lambda n_, rt_: np.zeros(n_, rt_)) if fc.mine else (lambda n_, rt_: _Ghost(n_, np.dtype(rt_).itemsize))
             for cmp in range(ncmp):
                 for c in comps:
                     if is_magnetic(c): continue
-                    fc.f[(c, cmp)] = np.zeros(n, rt)
+                    fc.f[(c, cmp)] = zeros(n, rt)
                 for c in comps:  # H: alias of B unless mu / PML (fields.cpp:493-517, update_eh.cpp:204-209)
                     if not is_magnetic(c): continue
                     d = comp_dir(c)
                     bc = dir_comp(B_stuff, d)
-                    fc.f[(c, cmp)] = np.zeros(n, rt) if sc.sigsize[d] > 1 else fc.f[(bc, cmp)]
+                    fc.f[(c, cmp)] = zeros(n, rt) if sc.sigsize[d] > 1 else fc.f[(bc, cmp)]
                 for c in comps:
                     d = comp_dir(c)
                     if is_D(c) or is_B(c):  # step_db.cpp:56-75
-                        if sc.sigsize[(d + 2) % 3] > 1: fc.f_u[(c, cmp)] = np.zeros(n, rt)
+                        if sc.sigsize[(d + 2) % 3] > 1: fc.f_u[(c, cmp)] = zeros(n, rt)
                     else:                    # update_eh.cpp:199-216
-                        if sc.sigsize[d] > 1: fc.f_w[(c, cmp)] = np.zeros(n, rt)
+                        if sc.sigsize[d] > 1: fc.f_w[(c, cmp)] = zeros(n, rt)
             for (sus, ft, arrs) in sc.pols:
                 P, Pp = {}, {}
                 for (c, d) in arrs:
                     for cmp in range(ncmp):
-                        P[(c, cmp)] = np.zeros(n, rt)
-                        Pp[(c, cmp)] = np.zeros(n, rt)
+                        P[(c, cmp)] = zeros(n, rt)
+                        Pp[(c, cmp)] = zeros(n, rt)
                 fc.pol_data.append({"P": P, "P_prev": Pp})
 
     # -- sources ------------------------------------------------------------------------------
@@ -404,7 +438,7 @@ class fields:
                     for (iz, wz) in per_dir[2]:
                         g = (ix, iy, iz)  # global Yee index of component c
                         ci, idx = self._owner_index(c, g)
-                        if ci is None: continue
+                        if ci is None or not self.chunks[ci].mine: continue
                         per_chunk.setdefault(ci, []).append((idx, amp * wx * wy * wz))
             for ci, pts in per_chunk.items():
                 self.chunks[ci].sources.append(dict(ft=ft, c=c, tid=tid,
@@ -436,19 +470,31 @@ class fields:
         rt = self.s.rt
         ncmp = 1 if self.is_real else 2
         conns = {}   # (ft, kind) -> [dst ptr arrays], [src ptr arrays], [phases]
+        rsend, rrecv = {}, {}  # (ft, kind, peer) -> ([ptr arrays], [phases])
         metals = {ft: [] for ft in range(8)}
+        state = {"i": 0, "j": 0}
         bnds2 = [2 * np.asarray(self.s.bounds[d]) for d in range(3)]
         kshape = [max(len(self.s.bounds[d]) - 1, 1) for d in range(3)]
         gi = np.zeros(kshape, np.int64)
         for k, v in self.s.grid_index.items(): gi[k] = v
 
         def add(ft, kind, dst, src, phase=None):
-            e = conns.setdefault((ft, kind), ([], [], []))
-            e[0].append(dst); e[1].append(src)
-            if phase is not None: e[2].append(phase)
+            mi, mj = self.chunks[state["i"]].mine, self.chunks[state["j"]].mine
+            if mi and mj:
+                e = conns.setdefault((ft, kind), ([], [], []))
+                e[0].append(dst); e[1].append(src)
+                if phase is not None: e[2].append(phase)
+            elif mi:
+                e = rrecv.setdefault((ft, kind, self.chunk_rank[state["j"]]), ([], []))
+                e[0].append(dst)
+                if phase is not None: e[1].append(phase)
+            elif mj:
+                e = rsend.setdefault((ft, kind, self.chunk_rank[state["i"]]), ([], []))
+                e[0].append(src)
 
         for i, fc in enumerate(self.chunks):
             gv = fc.gv
+            state["i"] = i
             for c in range(20):
                 if (c, 0) not in fc.f: continue
                 ft = comp_type(c)
@@ -460,6 +506,7 @@ class fields:
                     if self.boundaries[d] != Metallic: continue
                     if gv.io[d] + 2 * gv.num[d] != gvu.io[d] + 2 * gvu.num[d]: continue
                     if gv.yee_shift(c, d): continue
+                    if not fc.mine: continue
                     idx = self._plane_indices(gv, lo, hi, d, gv.num[d])
                     for cmp in range(ncmp):
                         metals[ft].append(fc.f[(c, cmp)].ctypes.data + idx * item)
@@ -495,6 +542,8 @@ class fields:
                     ph = phase[ok]
                     for j in np.unique(owner):
                         fj = self.chunks[int(j)]
+                        state["j"] = int(j)
+                        if not (fc.mine or fj.mine): continue
                         if (c, 0) not in fj.f: continue
                         selj = owner == j
                         gj = fj.gv
@@ -526,6 +575,7 @@ class fields:
                                     if (c, cmp) in fc.pol_data[ip]["P"] and (c, cmp) in fj.pol_data[ip]["P"] and (self.is_real or np.all(p == 1.0)):
                                         add(ftp, A.CONNECT_COPY, fc.pol_data[ip]["P"][(c, cmp)].ctypes.data + n * item,
                                             fj.pol_data[ip]["P"][(c, cmp)].ctypes.data + m * item)
+        self._rsend, self._rrecv = rsend, rrecv
         return conns, metals
 
     @staticmethod
@@ -563,7 +613,15 @@ class fields:
         b.check(b.create(C.byref(cfg), C.byref(ctx)))
         self.ctx = ctx
         ncmp = 1 if self.is_real else 2
-        for i, fc in enumerate(self.chunks):
+        if self.nranks > 1:
+            if self.comm_id is None: raise ValueError("comm_id (meepcu_comm_unique_id) required for nranks > 1")
+            idbuf = (C.c_char * 128).from_buffer_copy(bytes(self.comm_id))
+            b.check(b.comm_init(ctx, self.rank, self.nranks, idbuf))
+        self.local_id = {}
+        for gi_, fc in enumerate(self.chunks):
+            if not fc.mine: continue
+            i = len(self.local_id)
+            self.local_id[gi_] = i
             sc, gv = fc.s, fc.gv
             d = A.ChunkDesc()
             for k in range(3):
@@ -578,8 +636,10 @@ class fields:
                 d.sigsize[dd] = sc.sigsize[dd]
                 if dd in sc.sig:
                     d.sig[dd], d.kap[dd], d.siginv[dd] = self._ptr(sc.sig[dd]), self._ptr(sc.kap[dd]), self._ptr(sc.siginv[dd])
+            d.rank = self.rank
             cid = C.c_int(-1)
             b.check(b.add_chunk(ctx, C.byref(d), C.byref(cid)))
+            assert cid.value == i
             for ip, (sus, ft, arrs) in enumerate(sc.pols):
                 sd = A.SusceptibilityDesc()
                 sd.ft, sd.omega_0, sd.gamma = ft, sus.omega_0, sus.gamma
@@ -606,6 +666,14 @@ class fields:
             php = np.ascontiguousarray(np.concatenate(ph)) if ph else None
             b.check(b.add_connections(ctx, ft, kind, dp.size, dp.ctypes.data, sp.ctypes.data,
                                       php.ctypes.data if php is not None else None))
+        for (ft, kind, peer), (ptrs, ph) in self._rsend.items():
+            pp = np.ascontiguousarray(np.concatenate([np.asarray(x).reshape(-1) for x in ptrs]).astype(np.uint64))
+            b.check(b.add_remote_send(ctx, ft, kind, peer, pp.size, pp.ctypes.data))
+        for (ft, kind, peer), (ptrs, ph) in self._rrecv.items():
+            pp = np.ascontiguousarray(np.concatenate([np.asarray(x).reshape(-1) for x in ptrs]).astype(np.uint64))
+            php = np.ascontiguousarray(np.concatenate(ph)) if ph else None
+            b.check(b.add_remote_recv(ctx, ft, kind, peer, pp.size, pp.ctypes.data,
+                                      php.ctypes.data if php is not None else None))
         b.check(b.finalize(ctx))
 
     def _add_dfts(self):
@@ -613,9 +681,10 @@ class fields:
         rt = self.s.rt
         ct = np.complex128 if rt.itemsize == 8 else np.complex64
         for (c, lo, hi, freqs, decim) in getattr(self, "_pending_dfts", []):
-            for i, fc in enumerate(self.chunks):
+            for gi_, fc in enumerate(self.chunks):
                 gv = fc.gv
-                if (c, 0) not in fc.f: continue
+                if (c, 0) not in fc.f or not fc.mine: continue
+                i = self.local_id[gi_]
                 is_, ie, ok = [0, 0, 0], [0, 0, 0], True
                 for d in range(3):
                     if not gv.has[d]: continue
@@ -684,6 +753,7 @@ class fields:
         g = tuple(int(round((pt[d] * 2 * self.a - gv.io[d] - gv.yee_shift(c, d)) / 2.0)) if gv.has[d] else 0 for d in range(3))
         ci, idx = self._owner_index(c, g)
         if ci is None: raise ValueError("point outside the cell")
+        if not self.chunks[ci].mine: return None
         arr = self.chunks[ci].f[(c, cmp)]
         out = C.c_double()
         self.b.check(self.b.read_value(self.ctx, arr.ctypes.data + idx * arr.itemsize, C.byref(out)))
@@ -703,6 +773,7 @@ class fields:
         n = 0
         seen = set()
         for fc in self.chunks:
+            if not fc.mine: continue
             groups = [fc.f, fc.f_u, fc.f_w]
             for g in groups:
                 for arr in g.values():

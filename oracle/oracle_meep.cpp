@@ -27,6 +27,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <map>
 #include <vector>
 #include <omp.h>
 #if defined(__x86_64__) || defined(__i386__)
@@ -179,10 +180,19 @@ struct SrcVol {
   std::vector<std::complex<double> > amp;
 };
 
+// test-only transport for world_size > 1 (tests/test_multirank_gloo.py): the oracle hands the packed
+// per-peer buffers of one field type to this callback, which exchanges them (gloo) and returns
+typedef void (*oracle_transport_fn)(void *user, int ft, int nsend, const int *send_peers,
+                                    void *const *send_bufs, const long long *send_bytes, int nrecv,
+                                    const int *recv_peers, void *const *recv_bufs,
+                                    const long long *recv_bytes);
+
 struct CtxBase {
   meepcu_config cfg;
   int t;
   bool finalized;
+  oracle_transport_fn transport;
+  void *transport_user;
   virtual ~CtxBase() {}
   virtual int add_chunk(const meepcu_chunk_desc *d, int *id) = 0;
   virtual int add_susc(int chunk, const meepcu_susceptibility_desc *d) = 0;
@@ -192,6 +202,7 @@ struct CtxBase {
   virtual int add_conn(int ft, int kind, size_t n, void *const *dst, const void *const *src,
                        const void *phases) = 0;
   virtual int step(int nsteps, int nsrc, const meepcu_src_sample *smp) = 0;
+  virtual int add_remote(int ft, int kind, int peer, size_t n, const void *const *p, const void *phases, bool recv) = 0;
   virtual int check_finite(int *ok) = 0;
   virtual int read_value(const void *p, double *out) = 0;
   virtual int64_t cells() = 0;
@@ -233,6 +244,58 @@ template <class T> struct Impl : CtxBase {
   std::vector<Chunk<T> > chunks;
   std::vector<T *> zeroes[MEEPCU_NUM_FIELD_TYPES];
   Conn<T> conn[MEEPCU_NUM_FIELD_TYPES][3];
+  struct Remote { std::vector<T *> ptr[3]; std::vector<std::complex<T> > phase; };
+  std::map<int, Remote> rsend[MEEPCU_NUM_FIELD_TYPES], rrecv[MEEPCU_NUM_FIELD_TYPES];
+
+  int add_remote(int ft, int kind, int peer, size_t n, const void *const *p, const void *phases, bool recv) {
+    if (ft < 0 || ft >= MEEPCU_NUM_FIELD_TYPES || kind < 0 || kind > 2) return fail(MEEPCU_EINVAL, "bad remote family");
+    Remote &R = (recv ? rrecv : rsend)[ft][peer];
+    for (size_t i = 0; i < n; ++i) R.ptr[kind].push_back((T *)p[i]);
+    if (recv && kind == MEEPCU_CONNECT_PHASE) {
+      const std::complex<T> *ph = (const std::complex<T> *)phases;
+      for (size_t i = 0; i < n / 2; ++i) R.phase.push_back(ph[i]);
+    }
+    return MEEPCU_OK;
+  }
+  // the cross-rank half of step_boundaries (src/step.cpp:226-288 with MPI; mympi.cpp:107-135)
+  void exchange_remote(int ft) {
+    if (rsend[ft].empty() && rrecv[ft].empty()) return;
+    std::vector<std::vector<T> > sb, rb;
+    std::vector<int> sp, rp;
+    std::vector<void *> sptr, rptr;
+    std::vector<long long> sbytes, rbytes;
+    for (typename std::map<int, Remote>::iterator it = rsend[ft].begin(); it != rsend[ft].end(); ++it) {
+      std::vector<T> b;
+      for (int k = 0; k < 3; ++k)
+        for (size_t n = 0; n < it->second.ptr[k].size(); ++n) b.push_back(*it->second.ptr[k][n]);
+      sb.push_back(b);
+      sp.push_back(it->first);
+    }
+    for (typename std::map<int, Remote>::iterator it = rrecv[ft].begin(); it != rrecv[ft].end(); ++it) {
+      size_t n = it->second.ptr[0].size() + it->second.ptr[1].size() + it->second.ptr[2].size();
+      rb.push_back(std::vector<T>(n));
+      rp.push_back(it->first);
+    }
+    for (size_t k = 0; k < sb.size(); ++k) { sptr.push_back(sb[k].data()); sbytes.push_back((long long)(sb[k].size() * sizeof(T))); }
+    for (size_t k = 0; k < rb.size(); ++k) { rptr.push_back(rb[k].data()); rbytes.push_back((long long)(rb[k].size() * sizeof(T))); }
+    transport(transport_user, ft, (int)sp.size(), sp.data(), sptr.data(), sbytes.data(), (int)rp.size(), rp.data(),
+              rptr.data(), rbytes.data());
+    size_t kk = 0;
+    for (typename std::map<int, Remote>::iterator it = rrecv[ft].begin(); it != rrecv[ft].end(); ++it, ++kk) {
+      const std::vector<T> &b = rb[kk];
+      const Remote &R = it->second;
+      size_t o = 0;
+      for (size_t n = 0; n < R.ptr[0].size() / 2; ++n) { // process_incoming_chunk_data, step.cpp:188-194
+        std::complex<T> temp = R.phase[n] * std::complex<T>(b[o + 2 * n], b[o + 2 * n + 1]);
+        *(R.ptr[0][2 * n]) = temp.real();
+        *(R.ptr[0][2 * n + 1]) = temp.imag();
+      }
+      o += R.ptr[0].size();
+      for (size_t n = 0; n < R.ptr[1].size(); ++n) *(R.ptr[1][n]) = -b[o + n];
+      o += R.ptr[1].size();
+      for (size_t n = 0; n < R.ptr[2].size(); ++n) *(R.ptr[2][n]) = b[o + n];
+    }
+  }
 
   // ---------------------------------------------------------------------------------------------
   int add_chunk(const meepcu_chunk_desc *d, int *id) {
@@ -513,6 +576,7 @@ template <class T> struct Impl : CtxBase {
       const Conn<T> &c = conn[ft][MEEPCU_CONNECT_COPY];
       for (size_t n = 0; n < c.src.size(); ++n) *(c.dst[n]) = block[MEEPCU_CONNECT_COPY][n];
     }
+    exchange_remote(ft);
   }
 
   // ---- Newton-Raphson chi2 solve, src/newton_raphson.cpp:93-359 -------------------------------
@@ -1101,6 +1165,9 @@ template <class T> struct Impl : CtxBase {
   // fields::step, src/step.cpp:35-140
   int step(int nsteps, int nsrc, const meepcu_src_sample *smp) {
     int rc;
+    for (int ft = 0; ft < MEEPCU_NUM_FIELD_TYPES; ++ft)
+      if ((!rsend[ft].empty() || !rrecv[ft].empty()) && !transport)
+        return fail(MEEPCU_ESTATE, "remote connections need oracle_set_transport");
     ZeroSubnormalsScope ftz_daz;
     for (size_t ic = 0; ic < chunks.size(); ++ic) // validate src_time ids once
       for (int ft = 0; ft < 4; ++ft)
@@ -1181,6 +1248,8 @@ int meepcu_create(const meepcu_config *cfg, meepcu_ctx **out) {
   impl->cfg = *cfg;
   impl->t = cfg->t;
   impl->finalized = false;
+  impl->transport = 0;
+  impl->transport_user = 0;
   *out = new meepcu_ctx;
   (*out)->impl = impl;
   return MEEPCU_OK;
@@ -1218,15 +1287,29 @@ int meepcu_add_connections(meepcu_ctx *ctx, int ft, int kind, size_t n, void *co
   CHECK_CTX;
   return ctx->impl->add_conn(ft, kind, n, dst, src, phases);
 }
-int meepcu_add_remote_send(meepcu_ctx *, int, int, int, size_t, const void *const *) {
-  return fail(MEEPCU_EUNSUPPORTED, "the oracle is single-process");
+int meepcu_add_remote_send(meepcu_ctx *ctx, int ft, int kind, int peer, size_t n, const void *const *src) {
+  if (!ctx || !ctx->impl) return fail(MEEPCU_EINVAL, "null context");
+  return ctx->impl->add_remote(ft, kind, peer, n, src, 0, false);
 }
-int meepcu_add_remote_recv(meepcu_ctx *, int, int, int, size_t, void *const *, const void *) {
-  return fail(MEEPCU_EUNSUPPORTED, "the oracle is single-process");
+int meepcu_add_remote_recv(meepcu_ctx *ctx, int ft, int kind, int peer, size_t n, void *const *dst,
+                           const void *phases) {
+  if (!ctx || !ctx->impl) return fail(MEEPCU_EINVAL, "null context");
+  return ctx->impl->add_remote(ft, kind, peer, n, (const void *const *)dst, phases, true);
 }
-int meepcu_comm_unique_id(void *) { return fail(MEEPCU_EUNSUPPORTED, "the oracle is single-process"); }
-int meepcu_comm_init(meepcu_ctx *, int, int, const void *) {
-  return fail(MEEPCU_EUNSUPPORTED, "the oracle is single-process");
+int meepcu_comm_unique_id(void *id) {
+  memset(id, 0, 128); // the oracle's transport is a test callback (oracle_set_transport), no NCCL
+  return MEEPCU_OK;
+}
+int meepcu_comm_init(meepcu_ctx *ctx, int, int, const void *) {
+  if (!ctx || !ctx->impl) return fail(MEEPCU_EINVAL, "null context");
+  return MEEPCU_OK;
+}
+// oracle-only (not part of include/meepcu.h): how world_size > 1 tests move the halo buffers
+int oracle_set_transport(meepcu_ctx *ctx, oracle_transport_fn fn, void *user) {
+  if (!ctx || !ctx->impl) return fail(MEEPCU_EINVAL, "null context");
+  ctx->impl->transport = fn;
+  ctx->impl->transport_user = user;
+  return MEEPCU_OK;
 }
 int meepcu_finalize(meepcu_ctx *ctx) {
   CHECK_CTX;
