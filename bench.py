@@ -2,7 +2,7 @@
 """bench.py -- Mcell-updates/s of the fused E+H time step (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload vac3d|diel3d|lorentz3d|nr3d] [--n 256] [--dtype f64|f32]
+                    [--workload vac3d|diel3d|lorentz3d|nr3d] [--size 256] [--dtype f64|f32]
 
 One "step" = one full `fields::step()` (B, H, D, E half-updates, boundaries, DFT) over the whole
 grid.  Default workload = BASELINE configs[1]: 3D vacuum cube 256^3, PML 1.0 on all faces
@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vac3d")
-    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--size", dest="n", type=int, default=256)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
