@@ -42,5 +42,7 @@ gen fp64 nrslab3d:14 30 2
 if [ -x oracle/_ref/fp64_pade/ref_driver ]; then
   gen fp64_pade kerr3d:12 30 2 1
   gen fp64_pade kerr1d 60 0 1
+  gen fp64_pade kr_per3d_rods 30 0 1
+  gen fp64_pade kr_per2d_rods 40 0 1
 fi
 ls -la $OUT | awk '{s+=$5} END {print "total bytes", s}'

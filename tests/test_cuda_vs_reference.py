@@ -17,7 +17,8 @@ CASES = [("fp64", "vac3d:48", 60, 3, 1e-12), ("fp32", "vac3d:48", 60, 3, 1e-5),
          ("fp64", "vac3d_cplx:24", 40, 2, 1e-12), ("fp64", "nrslab3d:20", 30, 2, 1e-12),
          ("fp64", "lorentz3d:32", 50, 2, 1e-12), ("fp32", "lorentz3d:32", 50, 2, 1e-5),
          ("fp64", "phc3d:24", 60, 0, 1e-12), ("fp64", "wvg2d", 400, 5, 1e-12),
-         ("fp64", "kr_per3d_rods", 300, 0, 1e-12), ("fp64", "kr_polariton1d", 100, 0, 1e-12)]
+         ("fp64", "kr_per3d_rods", 300, 0, 1e-12), ("fp64", "kr_polariton1d", 100, 0, 1e-12),
+         ("fp64_pade", "kerr3d:20", 40, 2, 1e-12), ("fp64_pade", "kr_per3d_rods", 100, 0, 1e-12)]
 
 
 @pytest.mark.parametrize("flavour,case,steps,warmup,tol", CASES)
@@ -28,7 +29,8 @@ def test_reference_twin_comparison(flavour, case, steps, warmup, tol):
     with tempfile.NamedTemporaryFile(suffix=".json") as tf:
         env = dict(os.environ, OMP_NUM_THREADS="8")
         subprocess.run([drv, "--mode", "shim", "--lib", CUDA_LIB, "--case", case, "--steps", str(steps),
-                        "--warmup", str(warmup), "--json", tf.name], check=True, env=env,
+                        "--warmup", str(warmup), "--nl", "1" if "pade" in flavour else "0", "--json", tf.name],
+                       check=True, env=env,
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
         d = json.load(open(tf.name))
     assert d["backend"] == "cuda-sm_100a" and d["arrays"] > 0 and d["mismatched_arrays"] <= d["arrays"]

@@ -13,7 +13,9 @@ from conftest import ORACLE_LIB, ref_driver
 
 CASES = [("fp64", "vac3d:24", 25, 2), ("fp64", "kr_per3d_rods", 40, 0), ("fp64", "nr3d:10", 25, 0),
          ("fp64", "lorentz3d:16", 30, 1), ("fp64", "wvg2d", 60, 3), ("fp32", "vac3d_cplx:14", 25, 2),
-         ("fp32", "lorentz3d:16", 30, 1), ("fp64", "vac3d:26", 25, 0)]
+         ("fp32", "lorentz3d:16", 30, 1), ("fp64", "vac3d:26", 25, 0),
+         # UPSTREAM_PADE against the de-blocked reference flavour (oracle/deblock_pade.py)
+         ("fp64_pade", "kerr3d:14", 40, 2), ("fp64_pade", "kerr1d", 80, 0), ("fp64_pade", "kr_per3d_rods", 40, 0)]
 
 
 @pytest.mark.parametrize("flavour,case,steps,warmup", CASES)
@@ -24,7 +26,8 @@ def test_shim_plus_oracle_equals_reference(flavour, case, steps, warmup):
     with tempfile.NamedTemporaryFile(suffix=".json") as tf:
         env = dict(os.environ, OMP_NUM_THREADS="4")
         subprocess.run([drv, "--mode", "shim", "--lib", ORACLE_LIB, "--case", case, "--steps", str(steps),
-                        "--warmup", str(warmup), "--json", tf.name], check=True, env=env,
+                        "--warmup", str(warmup), "--nl", "1" if "pade" in flavour else "0", "--json", tf.name],
+                       check=True, env=env,
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
         d = json.load(open(tf.name))
     assert d["arrays"] > 0 and d["mismatched_arrays"] == 0 and d["mismatched_elements"] == 0, d
