@@ -17,7 +17,7 @@ NVCC_FLAGS = [
     # bit-parity with the reference's x86-64 build: no FMA contraction, IEEE div/sqrt, and
     # flush-to-zero for fp32 like the FTZ/DAZ mode the reference sets (src/mympi.cpp)
     "--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=true",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared", "-lgomp",
 ]
 
 

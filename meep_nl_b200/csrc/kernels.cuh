@@ -766,6 +766,28 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// Run-length form of the COPY / NEGATE connection lists: the reference enumerates not-owned points
+// plane by plane (LOOP_OVER_VOL_NOTOWNED, src/boundaries.cpp:396), so consecutive entries advance
+// by a constant stride on both sides.  One warp copies one run: 16 bytes of pointers per RUN instead
+// of per element.
+template <class T> struct ConnRun {
+  T *dst;
+  const T *src;
+  int n, dst_stride, src_stride, negate;
+};
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_conn_runs(const ConnRun<T> *__restrict__ runs, int nruns) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nruns; r += warps_per_grid) {
+    const ConnRun<T> q = runs[r];
+    if (q.negate)
+      for (int j = lane; j < q.n; j += 32) q.dst[(long long)j * q.dst_stride] = -q.src[(long long)j * q.src_stride];
+    else
+      for (int j = lane; j < q.n; j += 32) q.dst[(long long)j * q.dst_stride] = q.src[(long long)j * q.src_stride];
+  }
+}
+
 // Halo exchange with another rank (replaces the MPI_Isend/Irecv pairs of src/mympi.cpp:107-135):
 // k_pack gathers the outgoing values of one field type into one contiguous buffer per peer
 // (order PHASE | NEGATE | COPY, src/step.cpp:257-268), NCCL moves the buffers over NVLink, and

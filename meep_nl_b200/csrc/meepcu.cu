@@ -293,6 +293,8 @@ template <class T> struct Ctx : CtxBase {
   int n_fmp[2];
   bool fmp_has_src[2];
   ConnTable<T> d_conn[MEEPCU_NUM_FIELD_TYPES][3];
+  ConnRun<T> *d_runs[MEEPCU_NUM_FIELD_TYPES]; // COPY + NEGATE lists in run-length form
+  int n_runs[MEEPCU_NUM_FIELD_TYPES];
   T **d_zero[MEEPCU_NUM_FIELD_TYPES]; // unfused metal lists (only non-plane lists; normally empty)
   long long n_zero[MEEPCU_NUM_FIELD_TYPES];
   bool general_half[2];  // some chunk needs k_eh_general in this half
@@ -334,6 +336,8 @@ template <class T> struct Ctx : CtxBase {
   Ctx() : arena(0), arena_bytes(0), st(0), st2(0), ev0(0), ev1(0), ev_fork(0), ev_join(0), d_half(0), d_eh(0), d_dft(0),
           d_dft_work(0), n_dft_work(0), phase_row(0), d_phase_off(0), d_flags(0), d_src(0),
           launches(0), steps_done(0), cells(0), alg_bytes(0), last_ms(0), profiling(false), ev_used(0) {
+    stage[0] = stage[1] = 0;
+    stage_next = 0;
     comm = 0;
     my_rank = 0;
     n_ranks = 1;
@@ -353,6 +357,8 @@ template <class T> struct Ctx : CtxBase {
     memset(d_fmp, 0, sizeof d_fmp);
     memset(n_fmp, 0, sizeof n_fmp);
     memset(d_conn, 0, sizeof d_conn);
+    memset(d_runs, 0, sizeof d_runs);
+    memset(n_runs, 0, sizeof n_runs);
     memset(d_zero, 0, sizeof d_zero);
     memset(n_zero, 0, sizeof n_zero);
     fmp_has_src[0] = fmp_has_src[1] = false;
@@ -360,6 +366,9 @@ template <class T> struct Ctx : CtxBase {
     eager_db[0] = eager_db[1] = eager_p[0] = eager_p[1] = false;
   }
   ~Ctx() {
+    for (int k = 0; k < 2; ++k) {
+      if (stage[k]) cudaFreeHost(stage[k]);
+    }
     if (comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(comm);
     if (arena) cudaFree(arena);
     for (size_t i = 0; i < extra_dev.size(); ++i) cudaFree(extra_dev[i]);
@@ -657,6 +666,90 @@ template <class T> struct Ctx : CtxBase {
     if (!r) return 0;
     if (r->kind == A_GRID) return (T *)r->dev + chunks[r->chunk].g.dev_index((long long)e);
     return (T *)r->dev + e;
+  }
+
+  // Host<->device copies go through two library-owned pinned staging buffers filled / drained by
+  // OpenMP memcpy, so that sync runs near PCIe speed although the caller's arrays are pageable
+  // (page-locking the caller's heap pages in place is not safe: neighbouring allocations that share
+  // a page would become half-pinned).
+  enum { kStageBytes = 64 << 20 };
+  char *stage[2];
+  cudaEvent_t stage_ev[2];
+  int stage_next;
+  int stage_init() {
+    if (stage[0]) return MEEPCU_OK;
+    for (int k = 0; k < 2; ++k) {
+      CU(cudaHostAlloc((void **)&stage[k], kStageBytes, cudaHostAllocDefault));
+      CU(cudaEventCreateWithFlags(&stage_ev[k], cudaEventDisableTiming));
+    }
+    stage_next = 0;
+    return MEEPCU_OK;
+  }
+  static void par_memcpy(char *dst, const char *src, size_t n) {
+    const size_t blk = 1 << 20;
+    const long nb = (long)((n + blk - 1) / blk);
+#pragma omp parallel for schedule(static)
+    for (long b = 0; b < nb; ++b) {
+      const size_t o = (size_t)b * blk;
+      memcpy(dst + o, src + o, std::min(blk, n - o));
+    }
+  }
+  // one dense host array <-> pitched device array, in row blocks that fit a staging buffer
+  int staged_copy(const ArrayRec &r, bool to_host) {
+    RC(stage_init());
+    size_t w, rows, dpitch;
+    if (r.kind == A_GRID) {
+      const Geom &g = chunks[r.chunk].g;
+      w = (size_t)g.nax[2] * sizeof(T);
+      rows = (size_t)g.nax[0] * g.nax[1];
+      dpitch = (size_t)g.pitch * sizeof(T);
+    }
+    else {
+      const size_t nb = r.n_host * sizeof(T) * (r.kind == A_DFT ? 2 : 1);
+      w = std::min<size_t>(nb, 1 << 20);
+      rows = (nb + w - 1) / w;
+      dpitch = w;
+      if (rows * w != nb) { // odd size: single pageable copy
+        if (to_host) CU(cudaMemcpyAsync((void *)r.host, r.dev, nb, cudaMemcpyDeviceToHost, st));
+        else CU(cudaMemcpyAsync(r.dev, r.host, nb, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        return MEEPCU_OK;
+      }
+    }
+    const size_t rows_per = std::max<size_t>(1, (size_t)kStageBytes / w);
+    struct Pending { int buf; size_t r0, nr; } pend[2];
+    int npend = 0;
+    for (size_t r0 = 0; r0 < rows; r0 += rows_per) {
+      const size_t nr = std::min(rows_per, rows - r0);
+      const int b = stage_next;
+      stage_next ^= 1;
+      if (to_host) {
+        // drain the buffer we are about to reuse
+        for (int k = 0; k < npend; ++k)
+          if (pend[k].buf == b) {
+            CU(cudaEventSynchronize(stage_ev[b]));
+            par_memcpy((char *)r.host + pend[k].r0 * w, stage[b], pend[k].nr * w);
+            pend[k] = pend[npend - 1];
+            --npend;
+            break;
+          }
+        CU(cudaMemcpy2DAsync(stage[b], w, r.dev + r0 * dpitch, dpitch, w, nr, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(stage_ev[b], st));
+        pend[npend].buf = b; pend[npend].r0 = r0; pend[npend].nr = nr; ++npend;
+      }
+      else {
+        CU(cudaEventSynchronize(stage_ev[b])); // previous DMA out of this buffer finished
+        par_memcpy(stage[b], (const char *)r.host + r0 * w, nr * w);
+        CU(cudaMemcpy2DAsync(r.dev + r0 * dpitch, dpitch, stage[b], w, w, nr, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(stage_ev[b], st));
+      }
+    }
+    if (to_host)
+      for (int k = 0; k < npend; ++k) {
+        CU(cudaEventSynchronize(stage_ev[pend[k].buf]));
+        par_memcpy((char *)r.host + pend[k].r0 * w, stage[pend[k].buf], pend[k].nr * w);
+      }
+    return MEEPCU_OK;
   }
 
   int copy_array(const ArrayRec &r, bool to_host) {
@@ -1260,8 +1353,46 @@ template <class T> struct Ctx : CtxBase {
     }
 
     // ---- 6. connections ----
+    for (int ft = 0; ft < MEEPCU_NUM_FIELD_TYPES; ++ft) {
+      std::vector<ConnRun<T> > runs;
+      for (int kind = MEEPCU_CONNECT_NEGATE; kind <= MEEPCU_CONNECT_COPY; ++kind) {
+        const PtrList &L = conn[ft][kind];
+        size_t k = 0;
+        while (k < L.dst.size()) {
+          T *d0 = dev_elem(L.dst[k]);
+          const T *s0 = dev_elem(L.src[k]);
+          if (!d0 || !s0)
+            return fail(MEEPCU_EINVAL, "connection %zu of field type %d points outside the registered arrays", k, ft);
+          ConnRun<T> r = {d0, s0, 1, 0, 0, kind == MEEPCU_CONNECT_NEGATE};
+          if (k + 1 < L.dst.size()) {
+            T *d1 = dev_elem(L.dst[k + 1]);
+            const T *s1 = dev_elem(L.src[k + 1]);
+            if (d1 && s1) {
+              const long long ds = d1 - d0, ss = s1 - s0;
+              if (ds != 0 && std::llabs(ds) < (1LL << 30) && std::llabs(ss) < (1LL << 30)) {
+                r.dst_stride = (int)ds;
+                r.src_stride = (int)ss;
+                T *dp = d1;
+                const T *sp = s1;
+                r.n = 2;
+                while (k + r.n < L.dst.size() && r.n < (1 << 20)) {
+                  T *dn = dev_elem(L.dst[k + r.n]);
+                  const T *sn = dev_elem(L.src[k + r.n]);
+                  if (!dn || !sn || dn - dp != ds || sn - sp != ss) break;
+                  dp = dn; sp = sn; r.n++;
+                }
+              }
+            }
+          }
+          runs.push_back(r);
+          k += r.n;
+        }
+      }
+      n_runs[ft] = (int)runs.size();
+      RC(upload(runs, &d_runs[ft]));
+    }
     for (int ft = 0; ft < MEEPCU_NUM_FIELD_TYPES; ++ft)
-      for (int kind = 0; kind < 3; ++kind) {
+      for (int kind = 0; kind < 1; ++kind) { // PHASE lists keep the per-element form
         const PtrList &L = conn[ft][kind];
         ConnTable<T> &C = d_conn[ft][kind];
         memset(&C, 0, sizeof C);
@@ -1452,14 +1583,23 @@ template <class T> struct Ctx : CtxBase {
   }
 
   int launch_conn(int ft) {
-    const ConnTable<T> &a = d_conn[ft][0], &b = d_conn[ft][1], &c = d_conn[ft][2];
-    const long long n = std::max(a.n / 2, std::max(b.n, c.n));
-    if (n == 0) return launch_remote(ft);
-    const int grid = (int)std::min<long long>((n + kThreads - 1) / kThreads, 148 * 16);
-    RC(prof_begin(KC_CONN));
-    k_conn<T><<<grid, kThreads, 0, st>>>(a, b, c);
-    RC(prof_end());
-    launches++;
+    const ConnTable<T> &a = d_conn[ft][0];
+    ConnTable<T> none;
+    memset(&none, 0, sizeof none);
+    if (a.n) {
+      const int grid = (int)std::min<long long>((a.n / 2 + kThreads - 1) / kThreads, 148 * 16);
+      RC(prof_begin(KC_CONN));
+      k_conn<T><<<grid, kThreads, 0, st>>>(a, none, none);
+      RC(prof_end());
+      launches++;
+    }
+    if (n_runs[ft]) {
+      const int grid = std::min((n_runs[ft] + 7) / 8, 148 * 16);
+      RC(prof_begin(KC_CONN));
+      k_conn_runs<T><<<grid, kThreads, 0, st>>>(d_runs[ft], n_runs[ft]);
+      RC(prof_end());
+      launches++;
+    }
     return launch_remote(ft);
   }
 
@@ -1609,14 +1749,15 @@ template <class T> struct Ctx : CtxBase {
       if (!eager_p[half]) RC(launch_conn(half ? MEEPCU_PE_STUFF : MEEPCU_PH_STUFF));
     }
     for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it)
-      if (it->second.mut) RC(copy_array(it->second, true));
+      if (it->second.mut) RC(big(it->second) ? staged_copy(it->second, true) : copy_array(it->second, true));
     CU(cudaStreamSynchronize(st));
     return MEEPCU_OK;
   }
+  bool big(const ArrayRec &r) const { return r.n_host * sizeof(T) >= (size_t)(4 << 20) && !getenv("MEEPCU_NO_STAGING"); }
   int sync_from_host() {
     CU(cudaSetDevice(cfg.device));
     for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it)
-      RC(copy_array(it->second, false));
+      RC(big(it->second) ? staged_copy(it->second, false) : copy_array(it->second, false));
     CU(cudaStreamSynchronize(st));
     return MEEPCU_OK;
   }
