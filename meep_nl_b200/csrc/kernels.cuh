@@ -740,6 +740,196 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 3 : 4)
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_curl3d_v: k_curl3d with V consecutive z points per thread (V = 2 doubles / 4 floats = 16-byte
+// loads and stores).  Only "clean" tiles (no source point, no metal plane) are routed here; the
+// arithmetic per point is the same expression sequence, so results are bit-identical.  The
+// z-neighbour of a vector is its own elements shifted by one plus ONE scalar load.
+// ------------------------------------------------------------------------------------------------
+template <class T> struct VecOf;
+template <> struct VecOf<double> { typedef double2 type; enum { V = 2 }; };
+template <> struct VecOf<float> { typedef float4 type; enum { V = 4 }; };
+
+template <class T> __device__ __forceinline__ void vload(T *out, const T *p) {
+  typedef typename VecOf<T>::type VT;
+  const VT v = __ldg(reinterpret_cast<const VT *>(p));
+  const T *e = reinterpret_cast<const T *>(&v);
+#pragma unroll
+  for (int j = 0; j < VecOf<T>::V; ++j) out[j] = e[j];
+}
+template <class T> __device__ __forceinline__ void vload_rw(T *out, const T *p) { // array we also write
+  typedef typename VecOf<T>::type VT;
+  const VT v = *reinterpret_cast<const VT *>(p);
+  const T *e = reinterpret_cast<const T *>(&v);
+#pragma unroll
+  for (int j = 0; j < VecOf<T>::V; ++j) out[j] = e[j];
+}
+template <class T> __device__ __forceinline__ void vstore(T *p, const T *in) {
+  typedef typename VecOf<T>::type VT;
+  VT v;
+  T *e = reinterpret_cast<T *>(&v);
+#pragma unroll
+  for (int j = 0; j < VecOf<T>::V; ++j) e[j] = in[j];
+  *reinterpret_cast<VT *>(p) = v;
+}
+
+template <class T, bool IS_D>
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : 3)
+    k_curl3d_v(const Curl3DParams<T> *__restrict__ params, const Tile *__restrict__ tiles) {
+  constexpr int V = VecOf<T>::V;
+  __shared__ Curl3DParams<T> P;
+  const Tile t = tiles[blockIdx.x];
+  {
+    const int nw = (int)(sizeof(Curl3DParams<T>) / 4);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(params + t.param);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&P);
+    for (int k = threadIdx.x; k < nw; k += kThreads) dst[k] = src[k];
+  }
+  __syncthreads();
+  const int pv = P.pitch / V; // vectors per row
+  const int p = t.p0 + threadIdx.x;
+  const int ib = p / pv, ic = (p - ib * pv) * V;
+  if (ib >= P.nB || ic >= P.nC) return;
+  // per component: is this row active, and which of my V elements are owned in z
+  bool rowact[3];
+  unsigned zmask[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    rowact[k] = ib >= P.lo[k][1] && ib <= P.hi[k][1];
+    unsigned m = 0;
+#pragma unroll
+    for (int j = 0; j < V; ++j)
+      if (ic + j >= P.lo[k][2] && ic + j <= P.hi[k][2]) m |= 1u << j;
+    zmask[k] = rowact[k] ? m : 0u;
+  }
+  if (!(zmask[0] | zmask[1] | zmask[2])) return;
+  const unsigned full = (1u << V) - 1u;
+  const int sA = P.sA, nA = P.nA;
+  int oy, ozs; // row offset of the y neighbour; offset of the ONE scalar z neighbour
+  if (!IS_D) {
+    oy = (ib + 1 < P.nB) ? P.sB : 0;
+    ozs = (ic + V < P.pitch) ? V : 0; // in bounds inside the padded row; value unused when not owned
+  }
+  else {
+    oy = (ib > 0) ? -P.sB : 0;
+    ozs = (ic > 0) ? -1 : 0;
+  }
+  const T *__restrict__ gx = P.g[0];
+  const T *__restrict__ gy = P.g[1];
+  const T *__restrict__ gz = P.g[2];
+  T *__restrict__ f0 = P.f[0];
+  T *__restrict__ f1 = P.f[1];
+  T *__restrict__ f2 = P.f[2];
+  T *__restrict__ e0 = P.e[0];
+  T *__restrict__ e1 = P.e[1];
+  T *__restrict__ e2 = P.e[2];
+  const T *__restrict__ u0 = P.u[0];
+  const T *__restrict__ u1 = P.u[1];
+  const T *__restrict__ u2 = P.u[2];
+  const bool hu0 = e0 && u0, hu1 = e1 && u1, hu2 = e2 && u2;
+  const T dtdx = P.dtdx;
+  int i = t.a0 * sA + ib * P.sB + ic;
+  T ry[V], rz[V];
+  if (!IS_D) {
+    vload<T>(ry, gy + i);
+    vload<T>(rz, gz + i);
+  }
+  else {
+    const int ip = t.a0 > 0 ? i - sA : i;
+    vload<T>(ry, gy + ip);
+    vload<T>(rz, gz + ip);
+  }
+  const int lo0 = P.lo[0][0], hi0 = P.hi[0][0], lo1 = P.lo[1][0], hi1 = P.hi[1][0], lo2 = P.lo[2][0],
+            hi2 = P.hi[2][0];
+  for (int ia = t.a0; ia < t.a1; ++ia, i += sA) {
+    const unsigned m0 = (ia >= lo0 && ia <= hi0) ? zmask[0] : 0u, m1 = (ia >= lo1 && ia <= hi1) ? zmask[1] : 0u,
+                   m2 = (ia >= lo2 && ia <= hi2) ? zmask[2] : 0u;
+    if (MCU_PREFETCH_PLANES > 0 && ia + MCU_PREFETCH_PLANES < nA) {
+      const int ipf = i + MCU_PREFETCH_PLANES * sA;
+      prefetch_l2(gx + ipf);
+      prefetch_l2(gy + ipf);
+      prefetch_l2(gz + ipf);
+      prefetch_l2(f0 + ipf);
+      prefetch_l2(f1 + ipf);
+      prefetch_l2(f2 + ipf);
+      if (hu0) prefetch_l2(u0 + ipf);
+      if (hu1) prefetch_l2(u1 + ipf);
+      if (hu2) prefetch_l2(u2 + ipf);
+    }
+    T gx0[V], gxy[V], gy0[V], gz0[V], gzy[V], gyx[V], gzx[V];
+    T gxs, gys; // the scalar z neighbours of g_x and g_y
+    vload<T>(gx0, gx + i);
+    vload<T>(gxy, gx + i + oy);
+    gxs = __ldg(gx + i + ozs);
+    gys = __ldg(gy + i + ozs);
+    vload<T>(gzy, gz + i + oy);
+    if (!IS_D) {
+      const int ox = (ia + 1 < nA) ? sA : 0;
+#pragma unroll
+      for (int j = 0; j < V; ++j) { gy0[j] = ry[j]; gz0[j] = rz[j]; }
+      vload<T>(gyx, gy + i + ox);
+      vload<T>(gzx, gz + i + ox);
+#pragma unroll
+      for (int j = 0; j < V; ++j) { ry[j] = gyx[j]; rz[j] = gzx[j]; }
+    }
+    else {
+      vload<T>(gy0, gy + i);
+      vload<T>(gz0, gz + i);
+#pragma unroll
+      for (int j = 0; j < V; ++j) { gyx[j] = ry[j]; gzx[j] = rz[j]; ry[j] = gy0[j]; rz[j] = gz0[j]; }
+    }
+    T fo0[V], fo1[V], fo2[V], uv0[V], uv1[V], uv2[V];
+    if (m0) vload_rw<T>(fo0, f0 + i);
+    if (m1) vload_rw<T>(fo1, f1 + i);
+    if (m2) vload_rw<T>(fo2, f2 + i);
+    if (hu0 && m0) vload<T>(uv0, u0 + i);
+    if (hu1 && m1) vload<T>(uv1, u1 + i);
+    if (hu2 && m2) vload<T>(uv2, u2 + i);
+    // z neighbours: element j of the shifted vector
+    T gxz[V], gyz[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      if (!IS_D) {
+        gxz[j] = (j + 1 < V) ? gx0[j + 1 < V ? j + 1 : j] : gxs;
+        gyz[j] = (j + 1 < V) ? gy0[j + 1 < V ? j + 1 : j] : gys;
+      }
+      else {
+        gxz[j] = (j > 0) ? gx0[j > 0 ? j - 1 : 0] : gxs;
+        gyz[j] = (j > 0) ? gy0[j > 0 ? j - 1 : 0] : gys;
+      }
+    }
+    // (g1[i+s1] - g1[i] + g2[i] - g2[i+s2]) per component, as in k_curl3d
+    T n0[V], n1[V], n2[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      n0[j] = fo0[j] - dtdx * (gzy[j] - gz0[j] + gy0[j] - gyz[j]);
+      n1[j] = fo1[j] - dtdx * (gxz[j] - gx0[j] + gz0[j] - gzx[j]);
+      n2[j] = fo2[j] - dtdx * (gyx[j] - gy0[j] + gx0[j] - gxy[j]);
+    }
+#define MCU_V_FINISH(K, m, nn, fo, ff, ee, hu, uv)                                                     \
+    if (m) {                                                                                       \
+      T ev[V];                                                                                     \
+      _Pragma("unroll") for (int j = 0; j < V; ++j) {                                              \
+        if (!((m >> j) & 1u)) nn[j] = fo[j]; /* not owned: write back what was there */            \
+        ev[j] = hu ? (nn[j] * uv[j]) : nn[j];                                                      \
+      }                                                                                            \
+      vstore<T>(ff + i, nn);                                                                       \
+      if (ee) {                                                                                    \
+        if (m == full)                                                                             \
+          vstore<T>(ee + i, ev);                                                                   \
+        else {                                                                                     \
+          _Pragma("unroll") for (int j = 0; j < V; ++j)                                            \
+            if ((m >> j) & 1u) ee[i + j] = ev[j];                                                  \
+        }                                                                                          \
+      }                                                                                            \
+    }
+    MCU_V_FINISH(0, m0, n0, fo0, f0, e0, hu0, uv0)
+    MCU_V_FINISH(1, m1, n1, fo1, f1, e1, hu1, uv1)
+    MCU_V_FINISH(2, m2, n2, fo2, f2, e2, hu2, uv2)
+#undef MCU_V_FINISH
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // step_boundaries: dst[n] = src[n] (COPY), = -src[n] (NEGATE), complex phase multiply (PHASE).
 // Sources are owned points and destinations not-owned points, so gather and scatter can be one
 // pass (the reference stages through comm_blocks only because of MPI).

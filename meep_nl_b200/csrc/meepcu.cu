@@ -285,6 +285,8 @@ template <class T> struct Ctx : CtxBase {
   std::vector<Curl3DParams<T> > h_c3d;
   Tile *d_c3d_tiles[2];
   int n_c3d_tiles[2];
+  Tile *d_c3dv_tiles[2];            // clean tiles -> vectorised kernel
+  int n_c3dv_tiles[2];
   EhParams<T> *d_eh;
   std::vector<EhParams<T> > h_eh;
   Tile *d_eh_tiles[2];
@@ -323,7 +325,7 @@ template <class T> struct Ctx : CtxBase {
 
   // per-kernel-class profiling (CUDA events around every launch, on the library's stream)
   enum { KC_HALF_B_SIMPLE = 0, KC_HALF_B_GENERAL, KC_HALF_D_SIMPLE, KC_HALF_D_GENERAL, KC_CONN,
-         KC_FMP, KC_EH_GENERAL, KC_DFT, KC_CURL3D_B, KC_CURL3D_D, KC_COUNT };
+         KC_FMP, KC_EH_GENERAL, KC_DFT, KC_CURL3D_B, KC_CURL3D_D, KC_CURL3D_SPECIAL, KC_COUNT };
   bool profiling;
   std::vector<cudaEvent_t> ev_pool;
   std::vector<int> ev_class;      // class of the launch between ev_pool[2k] and ev_pool[2k+1]
@@ -351,6 +353,8 @@ template <class T> struct Ctx : CtxBase {
     d_c3d = 0;
     memset(d_c3d_tiles, 0, sizeof d_c3d_tiles);
     memset(n_c3d_tiles, 0, sizeof n_c3d_tiles);
+    memset(d_c3dv_tiles, 0, sizeof d_c3dv_tiles);
+    memset(n_c3dv_tiles, 0, sizeof n_c3dv_tiles);
     memset(n_tiles, 0, sizeof n_tiles);
     memset(d_eh_tiles, 0, sizeof d_eh_tiles);
     memset(n_eh_tiles, 0, sizeof n_eh_tiles);
@@ -994,7 +998,7 @@ template <class T> struct Ctx : CtxBase {
     RC(upload(all_src, &d_src));
 
     // ---- 5. per-(chunk, half, cmp) parameter blocks + tiles ----
-    std::vector<Tile> tiles[2][3], eh_tiles[2], c3d_tiles[2];
+    std::vector<Tile> tiles[2][3], eh_tiles[2], c3d_tiles[2], c3dv_tiles[2];
     std::vector<FmpParams<T> > fmps[2];
     const int ncmp = cfg.is_real ? 1 : 2;
     cells = 0;
@@ -1175,17 +1179,36 @@ template <class T> struct Ctx : CtxBase {
             bool any_zero = false;
             for (int k = 0; k < 3; ++k)
               if (Q.zdb[k] || Q.zeh[k]) any_zero = true;
-            for (int a0 = 0; a0 < g.nax[0]; a0 += seg)
-              for (int p0 = 0; p0 < plane; p0 += kThreads) {
-                const int a1 = std::min(a0 + seg, g.nax[0]);
+            const int V = (int)(16 / sizeof(T));
+            const bool vec_ok = !getenv("MEEPCU_NO_VEC") && g.pitch % V == 0;
+            // device indices of every source point of this chunk half (any component)
+            std::vector<long long> spts;
+            for (int k = 0; k < 3; ++k) {
+              for (int j = 0; j < Q.ncsrc[k]; ++j) spts.push_back(all_src[(Q.csrc[k] - d_src) + j].idx);
+              for (int j = 0; j < Q.nisrc[k]; ++j) spts.push_back(all_src[(Q.isrc[k] - d_src) + j].idx);
+            }
+            const long long sAq = (long long)Q.sA;
+            const int span = vec_ok ? kThreads * V : kThreads; // elements of the plane per clean tile
+            for (int a0 = 0; a0 < g.nax[0]; a0 += seg) {
+              const int a1 = std::min(a0 + seg, g.nax[0]);
+              for (int e0 = 0; e0 < plane; e0 += span) {
                 bool special = any_zero; // metal planes: checked per point in the special body
-                for (int k = 0; k < 3; ++k) {
-                  if (Q.ncsrc[k] && a0 <= Q.ca1[k] && a1 > Q.ca0[k]) special = true;
-                  if (Q.nisrc[k] && a0 <= Q.ia1[k] && a1 > Q.ia0[k]) special = true;
+                for (size_t j = 0; j < spts.size() && !special; ++j) {
+                  const long long a = spts[j] / sAq, pos = spts[j] % sAq;
+                  if (a >= a0 && a < a1 && pos >= e0 && pos < e0 + span) special = true;
                 }
-                Tile t = {qidx, a0, a1, p0 | (special ? kTileSpecial : 0)};
-                c3d_tiles[half].push_back(t);
+                if (!special && vec_ok) { // clean: V z-points per thread
+                  Tile t = {qidx, a0, a1, e0 / V};
+                  c3dv_tiles[half].push_back(t);
+                }
+                else // few tiles: cut them into short marches so that they finish quickly
+                  for (int b0 = a0; b0 < a1; b0 += 4)
+                    for (int p0 = e0; p0 < std::min(e0 + span, plane); p0 += kThreads) {
+                      Tile t = {qidx, b0, std::min(b0 + 4, a1), p0 | (special ? kTileSpecial : 0)};
+                      c3d_tiles[half].push_back(t);
+                    }
               }
+            }
           }
           else {
             // class: 0 = no conductivity, no polarisations; 1 = everything compiled in
@@ -1339,6 +1362,8 @@ template <class T> struct Ctx : CtxBase {
     for (int half = 0; half < 2; ++half) {
       n_c3d_tiles[half] = (int)c3d_tiles[half].size();
       RC(upload(c3d_tiles[half], &d_c3d_tiles[half]));
+      n_c3dv_tiles[half] = (int)c3dv_tiles[half].size();
+      RC(upload(c3dv_tiles[half], &d_c3dv_tiles[half]));
     }
     RC(upload(h_eh, &d_eh));
     for (int half = 0; half < 2; ++half) {
@@ -1568,7 +1593,7 @@ template <class T> struct Ctx : CtxBase {
   int get_kernel_times(meepcu_kernel_time *out, int cap, int *n) {
     static const char *names[KC_COUNT] = {"k_halfg<B/H,pml>", "k_halfg<B/H,cond+pol>", "k_halfg<D/E,pml>",
                                           "k_halfg<D/E,cond+pol>", "k_conn", "k_fmp", "k_eh_general", "k_dft",
-                                          "k_curl3d<B/H>", "k_curl3d<D/E>"};
+                                          "k_curl3d_v<B/H>", "k_curl3d_v<D/E>", "k_curl3d (source/metal tiles)"};
     int m = 0;
     for (int k = 0; k < KC_COUNT && m < cap; ++k) {
       memset(&out[m], 0, sizeof out[m]);
@@ -1608,7 +1633,7 @@ template <class T> struct Ctx : CtxBase {
     // disjoint chunks, so they run side by side on two streams; everything else is ordered after
     // both.  While profiling they are serialised so that each kernel's event time is its own.
     const bool have_g = n_tiles[half][0] || n_tiles[half][1] || n_tiles[half][2];
-    const bool fork = have_g && n_c3d_tiles[half] && !profiling;
+    const bool fork = (have_g || (n_c3d_tiles[half] && n_c3dv_tiles[half])) && (n_c3d_tiles[half] || n_c3dv_tiles[half]) && !profiling;
     cudaStream_t sg = fork ? st2 : st;
     if (fork) {
       CU(cudaEventRecord(ev_fork, st));
@@ -1632,12 +1657,22 @@ template <class T> struct Ctx : CtxBase {
       RC(prof_end());
       launches++;
     }
-    if (n_c3d_tiles[half]) {
+    if (n_c3d_tiles[half]) { // tiles with source points / metal planes, or unvectorisable pitch
+      cudaStream_t ss = n_c3dv_tiles[half] ? sg : st; // beside the vector kernel when there is one
+      RC(prof_begin(KC_CURL3D_SPECIAL));
+      if (half)
+        k_curl3d<T, true><<<n_c3d_tiles[half], kThreads, 0, ss>>>(d_c3d, d_c3d_tiles[half], smp);
+      else
+        k_curl3d<T, false><<<n_c3d_tiles[half], kThreads, 0, ss>>>(d_c3d, d_c3d_tiles[half], smp);
+      RC(prof_end());
+      launches++;
+    }
+    if (n_c3dv_tiles[half]) {
       RC(prof_begin(half ? KC_CURL3D_D : KC_CURL3D_B));
       if (half)
-        k_curl3d<T, true><<<n_c3d_tiles[half], kThreads, 0, st>>>(d_c3d, d_c3d_tiles[half], smp);
+        k_curl3d_v<T, true><<<n_c3dv_tiles[half], kThreads, 0, st>>>(d_c3d, d_c3dv_tiles[half]);
       else
-        k_curl3d<T, false><<<n_c3d_tiles[half], kThreads, 0, st>>>(d_c3d, d_c3d_tiles[half], smp);
+        k_curl3d_v<T, false><<<n_c3dv_tiles[half], kThreads, 0, st>>>(d_c3d, d_c3dv_tiles[half]);
       RC(prof_end());
       launches++;
     }
