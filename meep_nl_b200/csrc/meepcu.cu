@@ -287,6 +287,8 @@ template <class T> struct Ctx : CtxBase {
   int n_c3d_tiles[2];
   Tile *d_c3dv_tiles[2];            // clean tiles -> vectorised kernel
   int n_c3dv_tiles[2];
+  Tile *d_gv_tiles[2][2];           // general vectorised: [half][0 pml, 1 +polarisations]
+  int n_gv_tiles[2][2];
   EhParams<T> *d_eh;
   std::vector<EhParams<T> > h_eh;
   Tile *d_eh_tiles[2];
@@ -325,7 +327,7 @@ template <class T> struct Ctx : CtxBase {
 
   // per-kernel-class profiling (CUDA events around every launch, on the library's stream)
   enum { KC_HALF_B_SIMPLE = 0, KC_HALF_B_GENERAL, KC_HALF_D_SIMPLE, KC_HALF_D_GENERAL, KC_CONN,
-         KC_FMP, KC_EH_GENERAL, KC_DFT, KC_CURL3D_B, KC_CURL3D_D, KC_CURL3D_SPECIAL, KC_COUNT };
+         KC_FMP, KC_EH_GENERAL, KC_DFT, KC_CURL3D_B, KC_CURL3D_D, KC_CURL3D_SPECIAL, KC_HALFG_SCALAR, KC_COUNT };
   bool profiling;
   std::vector<cudaEvent_t> ev_pool;
   std::vector<int> ev_class;      // class of the launch between ev_pool[2k] and ev_pool[2k+1]
@@ -355,6 +357,8 @@ template <class T> struct Ctx : CtxBase {
     memset(n_c3d_tiles, 0, sizeof n_c3d_tiles);
     memset(d_c3dv_tiles, 0, sizeof d_c3dv_tiles);
     memset(n_c3dv_tiles, 0, sizeof n_c3dv_tiles);
+    memset(d_gv_tiles, 0, sizeof d_gv_tiles);
+    memset(n_gv_tiles, 0, sizeof n_gv_tiles);
     memset(n_tiles, 0, sizeof n_tiles);
     memset(d_eh_tiles, 0, sizeof d_eh_tiles);
     memset(n_eh_tiles, 0, sizeof n_eh_tiles);
@@ -865,7 +869,12 @@ template <class T> struct Ctx : CtxBase {
       return fail(MEEPCU_ECUDA, "no CUDA device: libmeepcuda has no CPU fallback");
     CU(cudaSetDevice(cfg.device));
     CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+    {
+      int lo_p = 0, hi_p = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+      const int pr = getenv("MEEPCU_ST2_PRIO") ? atoi(getenv("MEEPCU_ST2_PRIO")) : 1; // 1: high (default), -1: low
+      CU(cudaStreamCreateWithPriority(&st2, cudaStreamNonBlocking, pr > 0 ? hi_p : (pr < 0 ? lo_p : 0)));
+    }
     CU(cudaEventCreate(&ev0));
     CU(cudaEventCreate(&ev1));
     CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
@@ -998,7 +1007,7 @@ template <class T> struct Ctx : CtxBase {
     RC(upload(all_src, &d_src));
 
     // ---- 5. per-(chunk, half, cmp) parameter blocks + tiles ----
-    std::vector<Tile> tiles[2][3], eh_tiles[2], c3d_tiles[2], c3dv_tiles[2];
+    std::vector<Tile> tiles[2][3], eh_tiles[2], c3d_tiles[2], c3dv_tiles[2], gv_tiles[2][2];
     std::vector<FmpParams<T> > fmps[2];
     const int ncmp = cfg.is_real ? 1 : 2;
     cells = 0;
@@ -1152,8 +1161,9 @@ template <class T> struct Ctx : CtxBase {
               fast = false;
           }
           const int plane = g.nax[1] * g.pitch;
-          int seg = 32;
-          if (g.nax[0] <= 48) seg = g.nax[0];
+          int seg = 16;
+          if (g.nax[0] <= 24) seg = g.nax[0];
+          if (getenv("MEEPCU_SEG")) seg = std::max(1, atoi(getenv("MEEPCU_SEG")));
           if (fast) {
             Curl3DParams<T> Q;
             memset(&Q, 0, sizeof Q);
@@ -1223,14 +1233,46 @@ template <class T> struct Ctx : CtxBase {
             const int pidx = (int)h_half.size();
             h_half.push_back(P);
             const int gplane = n_o * g.pitch;
-            const int gseg = n_m <= 48 ? n_m : 32;
-            for (int a0 = 0; a0 < n_m; a0 += gseg)
-              for (int p0 = 0; p0 < gplane; p0 += kThreads)
+            int gseg = n_m <= 24 ? n_m : 16;
+            if (getenv("MEEPCU_GSEG")) gseg = std::max(1, atoi(getenv("MEEPCU_GSEG")));
+            const int V = (int)(16 / sizeof(T));
+            const bool vec_ok = !getenv("MEEPCU_NO_VEC") && g.pitch % V == 0 && heavy < 2 &&
+                                (sizeof(T) == 4 || getenv("MEEPCU_GVEC64"));
+            const int span = vec_ok ? kThreads * V : kThreads;
+            const long long s_mq = P.march ? (long long)g.pitch : (long long)g.pitch * g.nax[1];
+            const long long s_oq = P.march ? (long long)g.pitch * g.nax[1] : (long long)g.pitch;
+            for (int a0 = 0; a0 < n_m; a0 += gseg) {
+              const int a1 = std::min(a0 + gseg, n_m);
+              for (int e0 = 0; e0 < gplane; e0 += span)
                 for (int k = 0; k < 3; ++k) { // one CTA per component, neighbours in the table
-                  if (!P.comp[k].f) continue;
-                  Tile t = {pidx * 4 + k, a0, std::min(a0 + gseg, n_m), p0};
-                  tiles[half][heavy].push_back(t);
+                  const CompParams<T> &c = P.comp[k];
+                  if (!c.f) continue;
+                  // does a source point of this component fall into this tile?
+                  bool special = false;
+                  for (int pass = 0; pass < 2 && !special; ++pass) {
+                    const SrcEntry *tab = pass ? c.isrc : c.csrc;
+                    const int ns = pass ? (c.e ? c.nisrc : 0) : c.ncsrc;
+                    for (int j = 0; j < ns && !special; ++j) {
+                      const long long idx = all_src[(tab - d_src) + j].idx;
+                      // decompose idx = im*s_m + io*s_o + ic on this chunk's device layout
+                      const long long big = std::max(s_mq, s_oq), small = std::min(s_mq, s_oq);
+                      const long long q1 = idx / big, r1 = idx % big, q2 = r1 / small, icz = r1 % small;
+                      const long long im = (s_mq > s_oq) ? q1 : q2, io = (s_mq > s_oq) ? q2 : q1;
+                      const long long pos = io * g.pitch + icz;
+                      if (im >= a0 && im < a1 && pos >= e0 && pos < e0 + span) special = true;
+                    }
+                  }
+                  if (vec_ok && !special) {
+                    Tile t = {pidx * 4 + k, a0, a1, e0 / V};
+                    gv_tiles[half][heavy].push_back(t);
+                  }
+                  else
+                    for (int p0 = e0; p0 < std::min(e0 + span, gplane); p0 += kThreads) {
+                      Tile t = {pidx * 4 + k, a0, a1, p0};
+                      tiles[half][heavy].push_back(t);
+                    }
                 }
+            }
             simple = heavy == 0; // profiling class below
           }
           // algorithmic bytes: every array element once per read and once per write
@@ -1364,6 +1406,10 @@ template <class T> struct Ctx : CtxBase {
       RC(upload(c3d_tiles[half], &d_c3d_tiles[half]));
       n_c3dv_tiles[half] = (int)c3dv_tiles[half].size();
       RC(upload(c3dv_tiles[half], &d_c3dv_tiles[half]));
+      for (int cl = 0; cl < 2; ++cl) {
+        n_gv_tiles[half][cl] = (int)gv_tiles[half][cl].size();
+        RC(upload(gv_tiles[half][cl], &d_gv_tiles[half][cl]));
+      }
     }
     RC(upload(h_eh, &d_eh));
     for (int half = 0; half < 2; ++half) {
@@ -1591,9 +1637,10 @@ template <class T> struct Ctx : CtxBase {
     return MEEPCU_OK;
   }
   int get_kernel_times(meepcu_kernel_time *out, int cap, int *n) {
-    static const char *names[KC_COUNT] = {"k_halfg<B/H,pml>", "k_halfg<B/H,cond+pol>", "k_halfg<D/E,pml>",
-                                          "k_halfg<D/E,cond+pol>", "k_conn", "k_fmp", "k_eh_general", "k_dft",
-                                          "k_curl3d_v<B/H>", "k_curl3d_v<D/E>", "k_curl3d (source/metal tiles)"};
+    static const char *names[KC_COUNT] = {"k_halfg_v<B/H,pml>", "k_halfg_v<B/H,pml+pol>", "k_halfg_v<D/E,pml>",
+                                          "k_halfg_v<D/E,pml+pol>", "k_conn", "k_fmp", "k_eh_general", "k_dft",
+                                          "k_curl3d_v<B/H>", "k_curl3d_v<D/E>", "k_curl3d (source/metal tiles)",
+                                          "k_halfg (scalar: sources/conductivity)"};
     int m = 0;
     for (int k = 0; k < KC_COUNT && m < cap; ++k) {
       memset(&out[m], 0, sizeof out[m]);
@@ -1632,27 +1679,54 @@ template <class T> struct Ctx : CtxBase {
     // The interior tiles (k_curl3d) and the PML / general tiles (k_halfg) of one half step touch
     // disjoint chunks, so they run side by side on two streams; everything else is ordered after
     // both.  While profiling they are serialised so that each kernel's event time is its own.
-    const bool have_g = n_tiles[half][0] || n_tiles[half][1] || n_tiles[half][2];
+    const bool have_g = n_tiles[half][0] || n_tiles[half][1] || n_tiles[half][2] || n_gv_tiles[half][0] || n_gv_tiles[half][1];
     const bool fork = (have_g || (n_c3d_tiles[half] && n_c3dv_tiles[half])) && (n_c3d_tiles[half] || n_c3dv_tiles[half]) && !profiling;
     cudaStream_t sg = fork ? st2 : st;
     if (fork) {
       CU(cudaEventRecord(ev_fork, st));
       CU(cudaStreamWaitEvent(st2, ev_fork, 0));
     }
-    if (n_tiles[half][0]) {
+    // the bandwidth-bound interior tiles are queued first; the latency-bound PML tiles (high-priority
+    // stream) take SM slots as they free up, so the two kinds of CTAs share every SM
+    static const bool interior_first = !getenv("MEEPCU_PML_FIRST");
+    if (interior_first)
+    {
+    if (n_c3dv_tiles[half]) {
+      RC(prof_begin(half ? KC_CURL3D_D : KC_CURL3D_B));
+      if (half)
+        k_curl3d_v<T, true><<<n_c3dv_tiles[half], kThreads, 0, st>>>(d_c3d, d_c3dv_tiles[half]);
+      else
+        k_curl3d_v<T, false><<<n_c3dv_tiles[half], kThreads, 0, st>>>(d_c3d, d_c3dv_tiles[half]);
+      RC(prof_end());
+      launches++;
+    }
+    }
+    if (n_gv_tiles[half][0]) {
       RC(prof_begin(half ? KC_HALF_D_SIMPLE : KC_HALF_B_SIMPLE));
+      k_halfg_v<T, false><<<n_gv_tiles[half][0], kThreads, 0, sg>>>(d_half, d_gv_tiles[half][0]);
+      RC(prof_end());
+      launches++;
+    }
+    if (n_gv_tiles[half][1]) {
+      RC(prof_begin(half ? KC_HALF_D_GENERAL : KC_HALF_B_GENERAL));
+      k_halfg_v<T, true><<<n_gv_tiles[half][1], kThreads, 0, sg>>>(d_half, d_gv_tiles[half][1]);
+      RC(prof_end());
+      launches++;
+    }
+    if (n_tiles[half][0]) {
+      RC(prof_begin(KC_HALFG_SCALAR));
       k_halfg<T, false, false><<<n_tiles[half][0], kThreads, 0, sg>>>(d_half, d_tiles[half][0], smp);
       RC(prof_end());
       launches++;
     }
     if (n_tiles[half][1]) {
-      RC(prof_begin(half ? KC_HALF_D_GENERAL : KC_HALF_B_GENERAL));
+      RC(prof_begin(KC_HALFG_SCALAR));
       k_halfg<T, false, true><<<n_tiles[half][1], kThreads, 0, sg>>>(d_half, d_tiles[half][1], smp);
       RC(prof_end());
       launches++;
     }
     if (n_tiles[half][2]) {
-      RC(prof_begin(half ? KC_HALF_D_GENERAL : KC_HALF_B_GENERAL));
+      RC(prof_begin(KC_HALFG_SCALAR));
       k_halfg<T, true, true><<<n_tiles[half][2], kThreads, 0, sg>>>(d_half, d_tiles[half][2], smp);
       RC(prof_end());
       launches++;
@@ -1667,6 +1741,8 @@ template <class T> struct Ctx : CtxBase {
       RC(prof_end());
       launches++;
     }
+    if (!interior_first)
+    {
     if (n_c3dv_tiles[half]) {
       RC(prof_begin(half ? KC_CURL3D_D : KC_CURL3D_B));
       if (half)
@@ -1675,6 +1751,7 @@ template <class T> struct Ctx : CtxBase {
         k_curl3d_v<T, false><<<n_c3dv_tiles[half], kThreads, 0, st>>>(d_c3d, d_c3dv_tiles[half]);
       RC(prof_end());
       launches++;
+    }
     }
     if (fork) {
       CU(cudaEventRecord(ev_join, st2));
