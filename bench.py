@@ -121,36 +121,69 @@ def build_problem(args, backend, device=0, rank=0, world=1, comm_id=None):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs"""
+    """SM clock / throttle reasons sampled through NVML every few ms while the timed regions run
+    (nvidia-smi as a fallback: one sample per ~100 ms)"""
+
+    HW_SLOWDOWN, SW_THERMAL, HW_THERMAL, SW_POWER_CAP = 0x8, 0x20, 0x40, 0x4
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.stop = threading.Event()
-        self.samples = []
+        self.samples = []  # (sm_mhz, reasons bitmask)
         self.index = index
+        self.sm_max = None
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         self.cmd = ["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits"]
 
+    def _reasons(self):
+        nv = self.nv
+        for fn in ("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons"):
+            if hasattr(nv, fn):
+                return int(getattr(nv, fn)(self.h))
+        return 0
+
     def run(self):
         while not self.stop.is_set():
             try:
+                if self.nv is not None:
+                    sm = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    self.samples.append((sm, self._reasons()))
+                    self.stop.wait(0.002)
+                    continue
                 out = subprocess.run(self.cmd, capture_output=True, text=True, timeout=5).stdout.strip()
                 p = [x.strip() for x in out.split(",")]
                 if len(p) >= 6:
-                    self.samples.append(p)
+                    act = [x.lower().startswith("active") for x in p[2:6]]
+                    mask = (self.HW_SLOWDOWN * act[0]) | (self.HW_THERMAL * act[1]) | (self.SW_THERMAL * act[2]) | \
+                           (self.SW_POWER_CAP * act[3])
+                    self.samples.append((float(p[0]), mask))
+                    self.sm_max = float(p[1])
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.05)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+        sm = sorted(s[0] for s in self.samples)
+        mask = 0
+        for s in self.samples:
+            mask |= s[1]
+        names = [(self.HW_SLOWDOWN, "hw_slowdown"), (self.HW_THERMAL, "hw_thermal_slowdown"),
+                 (self.SW_THERMAL, "sw_thermal_slowdown"), (self.SW_POWER_CAP, "sw_power_cap")]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.sm_max,
+                "reasons": [n for b, n in names if mask & b], "samples": len(sm),
+                "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 def workload_name(args):
@@ -308,7 +341,8 @@ def main_ours(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
+    with_bytes = [k for k in kernels if k["bytes"] > 0]
+    dom = max(with_bytes, key=lambda k: k["ms"]) if with_bytes else None
     roof = None
     if dom:
         per_launch_ms = dom["ms"] / dom["launches"]

@@ -75,7 +75,10 @@ typedef struct {
   int nl_mode;       /* MEEPCU_NL_* */
   int device;        /* CUDA device ordinal for this context (ignored by the oracle) */
   int t;             /* fields::t at attach time */
-  int reserved[7];
+  int pin_host;      /* 1: page-lock the caller's big arrays in place (cudaHostRegister) for the life of the
+                        context, so that meepcu_sync_* are plain DMA at PCIe speed; the arrays must then
+                        outlive the context.  0: copy through library-owned pinned staging buffers. */
+  int reserved[6];
 } meepcu_config;
 
 /* One fields_chunk + its structure_chunk (src/meep.hpp:590-598,1461-1485).  Array length is

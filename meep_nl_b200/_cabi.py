@@ -31,7 +31,7 @@ class Config(C.Structure):
     _fields_ = [("abi_version", C.c_int), ("realnum_bytes", C.c_int), ("is_real", C.c_int),
                 ("dim", C.c_int), ("a", C.c_double), ("dt", C.c_double), ("courant", C.c_double),
                 ("beta", C.c_double), ("nl_mode", C.c_int), ("device", C.c_int), ("t", C.c_int),
-                ("reserved", C.c_int * 7)]
+                ("pin_host", C.c_int), ("reserved", C.c_int * 6)]
 
 
 class ChunkDesc(C.Structure):

@@ -1673,6 +1673,21 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// Row re-pitching between the dense layout of the caller's arrays (row = nC elements) and the padded
+// device layout (row = pitch elements): host<->device transfers are then plain 1-D DMA at PCIe speed
+// (2-D DMA with 2 KB rows runs at a fraction of it), and the re-pitching costs one HBM pass.
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+    k_rows(T *__restrict__ dst, long long dst_pitch, const T *__restrict__ src, long long src_pitch, int w,
+           long long rows) {
+  const long long n = rows * w, stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const long long r = k / w;
+    const int c = (int)(k - r * w);
+    dst[r * dst_pitch + c] = src[r * src_pitch + c];
+  }
+}
+
 // the per-step NaN test of step.cpp:138-139, over whole arrays, on demand
 template <class T> __global__ void k_nonfinite(const T *a, long long n, int *flag) {
   const long long stride = (long long)gridDim.x * blockDim.x;

@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 #include <dlfcn.h>
@@ -124,6 +125,7 @@ struct ArrayRec {
   size_t n_dev;   // device elements
   bool mut;       // downloaded by sync_to_host
   bool is_field;  // f[c][cmp] (NaN check)
+  bool pinned;    // host array page-locked in place (meepcu_config::pin_host)
 };
 
 struct Geom { // device layout of one chunk
@@ -289,6 +291,13 @@ template <class T> struct Ctx : CtxBase {
   int n_c3dv_tiles[2];
   Tile *d_gv_tiles[2][2];           // general vectorised: [half][0 pml, 1 +polarisations]
   int n_gv_tiles[2][2];
+  // Multi-rank overlap: in every tile list the tiles that write a plane another rank receives come
+  // first (nb_* of them).  They are launched first, the halo exchange then runs on its own stream
+  // beside the remaining (interior) tiles of the same half step.
+  int nb_tiles[2][3], nb_c3d_tiles[2], nb_c3dv_tiles[2], nb_gv_tiles[2][2];
+  bool overlap_half[2];
+  cudaStream_t st_comm;
+  cudaEvent_t ev_bdone, ev_cdone;
   EhParams<T> *d_eh;
   std::vector<EhParams<T> > h_eh;
   Tile *d_eh_tiles[2];
@@ -341,6 +350,7 @@ template <class T> struct Ctx : CtxBase {
           d_dft_work(0), n_dft_work(0), phase_row(0), d_phase_off(0), d_flags(0), d_src(0),
           launches(0), steps_done(0), cells(0), alg_bytes(0), last_ms(0), profiling(false), ev_used(0) {
     stage[0] = stage[1] = 0;
+    dstage = 0;
     stage_next = 0;
     comm = 0;
     my_rank = 0;
@@ -359,6 +369,13 @@ template <class T> struct Ctx : CtxBase {
     memset(n_c3dv_tiles, 0, sizeof n_c3dv_tiles);
     memset(d_gv_tiles, 0, sizeof d_gv_tiles);
     memset(n_gv_tiles, 0, sizeof n_gv_tiles);
+    memset(nb_tiles, 0, sizeof nb_tiles);
+    memset(nb_c3d_tiles, 0, sizeof nb_c3d_tiles);
+    memset(nb_c3dv_tiles, 0, sizeof nb_c3dv_tiles);
+    memset(nb_gv_tiles, 0, sizeof nb_gv_tiles);
+    overlap_half[0] = overlap_half[1] = false;
+    st_comm = 0;
+    ev_bdone = ev_cdone = 0;
     memset(n_tiles, 0, sizeof n_tiles);
     memset(d_eh_tiles, 0, sizeof d_eh_tiles);
     memset(n_eh_tiles, 0, sizeof n_eh_tiles);
@@ -377,7 +394,10 @@ template <class T> struct Ctx : CtxBase {
     for (int k = 0; k < 2; ++k) {
       if (stage[k]) cudaFreeHost(stage[k]);
     }
+    if (dstage) cudaFree(dstage);
     if (comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(comm);
+    for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it)
+      if (it->second.pinned) cudaHostUnregister((void *)it->second.host);
     if (arena) cudaFree(arena);
     for (size_t i = 0; i < extra_dev.size(); ++i) cudaFree(extra_dev[i]);
     d_smp.release();
@@ -388,6 +408,9 @@ template <class T> struct Ctx : CtxBase {
     if (ev1) cudaEventDestroy(ev1);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    if (ev_bdone) cudaEventDestroy(ev_bdone);
+    if (ev_cdone) cudaEventDestroy(ev_cdone);
+    if (st_comm) cudaStreamDestroy(st_comm);
     if (st2) cudaStreamDestroy(st2);
     if (st) cudaStreamDestroy(st);
   }
@@ -607,29 +630,30 @@ template <class T> struct Ctx : CtxBase {
     }
     return MEEPCU_OK;
   }
-  int launch_remote(int ft) {
+  int launch_remote(int ft, cudaStream_t sx) {
     RemoteDev &R = rdev[ft];
     if (!R.n_send && !R.n_recv) return MEEPCU_OK;
     NcclApi *n = nccl_api();
-    RC(prof_begin(KC_CONN));
+    const bool prof = sx == st;
+    if (prof) RC(prof_begin(KC_CONN));
     if (R.n_send) {
       const int grid = (int)std::min<long long>((R.n_send + kThreads - 1) / kThreads, 148 * 8);
-      k_pack<T><<<grid, kThreads, 0, st>>>(R.d_src, R.d_sendbuf, R.n_send);
+      k_pack<T><<<grid, kThreads, 0, sx>>>(R.d_src, R.d_sendbuf, R.n_send);
       launches++;
     }
     const int dtype = sizeof(T) == 8 ? 8 /* ncclFloat64 */ : 7 /* ncclFloat32 */;
     NC(n->GroupStart());
     for (size_t k = 0; k < R.recv_peer.size(); ++k)
-      NC(n->Recv(R.d_recvbuf + R.recv_off[k], (size_t)R.recv_n[k], dtype, R.recv_peer[k], comm, st));
+      NC(n->Recv(R.d_recvbuf + R.recv_off[k], (size_t)R.recv_n[k], dtype, R.recv_peer[k], comm, sx));
     for (size_t k = 0; k < R.send_peer.size(); ++k)
-      NC(n->Send(R.d_sendbuf + R.send_off[k], (size_t)R.send_n[k], dtype, R.send_peer[k], comm, st));
+      NC(n->Send(R.d_sendbuf + R.send_off[k], (size_t)R.send_n[k], dtype, R.send_peer[k], comm, sx));
     NC(n->GroupEnd());
     if (R.n_recv) {
       const int grid = (int)std::min<long long>((R.n_recv + kThreads - 1) / kThreads, 148 * 8);
-      k_unpack<T><<<grid, kThreads, 0, st>>>(R.d_dst, R.d_recvbuf, R.d_phase, R.d_seg, R.nseg);
+      k_unpack<T><<<grid, kThreads, 0, sx>>>(R.d_dst, R.d_recvbuf, R.d_phase, R.d_seg, R.nseg);
       launches++;
     }
-    RC(prof_end());
+    if (prof) RC(prof_end());
     return MEEPCU_OK;
   }
 
@@ -647,7 +671,7 @@ template <class T> struct Ctx : CtxBase {
       it->second.is_field = it->second.is_field || is_field;
       return MEEPCU_OK;
     }
-    ArrayRec r = {host, 0, chunk, kind, n_host, n_dev, mut, is_field};
+    ArrayRec r = {host, 0, chunk, kind, n_host, n_dev, mut, is_field, false};
     arrays[key] = r;
     return MEEPCU_OK;
   }
@@ -702,21 +726,56 @@ template <class T> struct Ctx : CtxBase {
       memcpy(dst + o, src + o, std::min(blk, n - o));
     }
   }
-  // one dense host array <-> pitched device array, in row blocks that fit a staging buffer
+  // Device-side staging: a dense block of rows travels by 1-D DMA and k_rows moves it to / from the
+  // padded device layout (all on stream st, so one buffer is enough).
+  char *dstage;
+  int dstage_init() {
+    if (dstage) return MEEPCU_OK;
+    CU(cudaMalloc((void **)&dstage, kStageBytes));
+    return MEEPCU_OK;
+  }
+  int rows_launch(T *dst, long long dp, const T *src, long long sp, int w, long long rows) {
+    const long long n = rows * w;
+    const int grid = (int)std::min<long long>((n + kThreads - 1) / kThreads, 148 * 16);
+    k_rows<T><<<grid, kThreads, 0, st>>>(dst, dp, src, sp, w, rows);
+    launches++;
+    return MEEPCU_OK;
+  }
+  // rows [r0, r0+nr) of a grid array <-> a dense page-locked host block, asynchronously on st
+  int rows_copy(const ArrayRec &r, const Geom &g, size_t r0, size_t nr, char *hblock, bool to_host) {
+    const size_t w = (size_t)g.nax[2] * sizeof(T);
+    T *d = (T *)r.dev + r0 * (size_t)g.pitch;
+    if (g.pitch == g.nax[2]) {
+      if (to_host) CU(cudaMemcpyAsync(hblock, d, nr * w, cudaMemcpyDeviceToHost, st));
+      else CU(cudaMemcpyAsync(d, hblock, nr * w, cudaMemcpyHostToDevice, st));
+      return MEEPCU_OK;
+    }
+    RC(dstage_init());
+    if (to_host) {
+      RC(rows_launch((T *)dstage, g.nax[2], d, g.pitch, g.nax[2], (long long)nr));
+      CU(cudaMemcpyAsync(hblock, dstage, nr * w, cudaMemcpyDeviceToHost, st));
+    }
+    else {
+      CU(cudaMemcpyAsync(dstage, hblock, nr * w, cudaMemcpyHostToDevice, st));
+      RC(rows_launch(d, g.pitch, (const T *)dstage, g.nax[2], g.nax[2], (long long)nr));
+    }
+    return MEEPCU_OK;
+  }
+
+  // one dense PAGEABLE host array <-> device array, in blocks that fit a pinned staging buffer
   int staged_copy(const ArrayRec &r, bool to_host) {
     RC(stage_init());
-    size_t w, rows, dpitch;
+    size_t w, rows;
+    const Geom *g = 0;
     if (r.kind == A_GRID) {
-      const Geom &g = chunks[r.chunk].g;
-      w = (size_t)g.nax[2] * sizeof(T);
-      rows = (size_t)g.nax[0] * g.nax[1];
-      dpitch = (size_t)g.pitch * sizeof(T);
+      g = &chunks[r.chunk].g;
+      w = (size_t)g->nax[2] * sizeof(T);
+      rows = (size_t)g->nax[0] * g->nax[1];
     }
     else {
       const size_t nb = r.n_host * sizeof(T) * (r.kind == A_DFT ? 2 : 1);
       w = std::min<size_t>(nb, 1 << 20);
       rows = (nb + w - 1) / w;
-      dpitch = w;
       if (rows * w != nb) { // odd size: single pageable copy
         if (to_host) CU(cudaMemcpyAsync((void *)r.host, r.dev, nb, cudaMemcpyDeviceToHost, st));
         else CU(cudaMemcpyAsync(r.dev, r.host, nb, cudaMemcpyHostToDevice, st));
@@ -741,14 +800,16 @@ template <class T> struct Ctx : CtxBase {
             --npend;
             break;
           }
-        CU(cudaMemcpy2DAsync(stage[b], w, r.dev + r0 * dpitch, dpitch, w, nr, cudaMemcpyDeviceToHost, st));
+        if (g) RC(rows_copy(r, *g, r0, nr, stage[b], true));
+        else CU(cudaMemcpyAsync(stage[b], r.dev + r0 * w, nr * w, cudaMemcpyDeviceToHost, st));
         CU(cudaEventRecord(stage_ev[b], st));
         pend[npend].buf = b; pend[npend].r0 = r0; pend[npend].nr = nr; ++npend;
       }
       else {
         CU(cudaEventSynchronize(stage_ev[b])); // previous DMA out of this buffer finished
         par_memcpy(stage[b], (const char *)r.host + r0 * w, nr * w);
-        CU(cudaMemcpy2DAsync(r.dev + r0 * dpitch, dpitch, stage[b], w, w, nr, cudaMemcpyHostToDevice, st));
+        if (g) RC(rows_copy(r, *g, r0, nr, stage[b], false));
+        else CU(cudaMemcpyAsync(r.dev + r0 * w, stage[b], nr * w, cudaMemcpyHostToDevice, st));
         CU(cudaEventRecord(stage_ev[b], st));
       }
     }
@@ -760,10 +821,17 @@ template <class T> struct Ctx : CtxBase {
     return MEEPCU_OK;
   }
 
+  // asynchronous copy on st: small arrays (pageable is fine) and big arrays page-locked in place
   int copy_array(const ArrayRec &r, bool to_host) {
     if (r.kind == A_GRID) {
       const Geom &g = chunks[r.chunk].g;
       const size_t w = (size_t)g.nax[2] * sizeof(T), rows = (size_t)g.nax[0] * g.nax[1];
+      if (r.pinned) {
+        const size_t rows_per = std::max<size_t>(1, (size_t)kStageBytes / w);
+        for (size_t r0 = 0; r0 < rows; r0 += rows_per)
+          RC(rows_copy(r, g, r0, std::min(rows_per, rows - r0), (char *)r.host + r0 * w, to_host));
+        return MEEPCU_OK;
+      }
       if (to_host)
         CU(cudaMemcpy2DAsync((void *)r.host, w, r.dev, (size_t)g.pitch * sizeof(T), w, rows,
                              cudaMemcpyDeviceToHost, st));
@@ -874,7 +942,10 @@ template <class T> struct Ctx : CtxBase {
       CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
       const int pr = getenv("MEEPCU_ST2_PRIO") ? atoi(getenv("MEEPCU_ST2_PRIO")) : 1; // 1: high (default), -1: low
       CU(cudaStreamCreateWithPriority(&st2, cudaStreamNonBlocking, pr > 0 ? hi_p : (pr < 0 ? lo_p : 0)));
+      CU(cudaStreamCreateWithPriority(&st_comm, cudaStreamNonBlocking, hi_p));
     }
+    CU(cudaEventCreateWithFlags(&ev_bdone, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ev_cdone, cudaEventDisableTiming));
     CU(cudaEventCreate(&ev0));
     CU(cudaEventCreate(&ev1));
     CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
@@ -943,6 +1014,16 @@ template <class T> struct Ctx : CtxBase {
     CU(cudaMalloc((void **)&d_flags, 4 * sizeof(int)));
     extra_dev.push_back((char *)d_flags);
     CU(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), st));
+    if (cfg.pin_host && !getenv("MEEPCU_NO_PIN"))
+      for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it) {
+        ArrayRec &r = it->second;
+        if (!big(r)) continue;
+        const size_t nb = r.n_host * sizeof(T) * (r.kind == A_DFT ? 2 : 1);
+        // constant arrays are uploaded once: only the ones that travel at every sync are worth pinning
+        if (!r.mut) continue;
+        if (cudaHostRegister((void *)r.host, nb, cudaHostRegisterDefault) == cudaSuccess) r.pinned = true;
+        else cudaGetLastError(); // not registrable (e.g. already registered by the caller): staging path
+      }
     RC(sync_from_host());
 
     // ---- 3. metal planes ----
@@ -1009,6 +1090,7 @@ template <class T> struct Ctx : CtxBase {
     // ---- 5. per-(chunk, half, cmp) parameter blocks + tiles ----
     std::vector<Tile> tiles[2][3], eh_tiles[2], c3d_tiles[2], c3dv_tiles[2], gv_tiles[2][2];
     std::vector<FmpParams<T> > fmps[2];
+    std::vector<int> c3d_chunk, half_chunk; // owning chunk of every h_c3d / h_half entry
     const int ncmp = cfg.is_real ? 1 : 2;
     cells = 0;
     alg_bytes = 0;
@@ -1186,6 +1268,7 @@ template <class T> struct Ctx : CtxBase {
             }
             const int qidx = (int)h_c3d.size();
             h_c3d.push_back(Q);
+            c3d_chunk.push_back((int)ic);
             bool any_zero = false;
             for (int k = 0; k < 3; ++k)
               if (Q.zdb[k] || Q.zeh[k]) any_zero = true;
@@ -1232,6 +1315,7 @@ template <class T> struct Ctx : CtxBase {
             const int n_m = P.march ? g.nax[1] : g.nax[0], n_o = P.march ? g.nax[0] : g.nax[1];
             const int pidx = (int)h_half.size();
             h_half.push_back(P);
+            half_chunk.push_back((int)ic);
             const int gplane = n_o * g.pitch;
             int gseg = n_m <= 24 ? n_m : 16;
             if (getenv("MEEPCU_GSEG")) gseg = std::max(1, atoi(getenv("MEEPCU_GSEG")));
@@ -1399,6 +1483,59 @@ template <class T> struct Ctx : CtxBase {
         }
       }
     }
+    // ---- 5b. multi-rank: boundary tiles first (see nb_* above) ----
+    if (n_ranks > 1 && !getenv("MEEPCU_NO_OVERLAP"))
+      for (int half = 0; half < 2; ++half) {
+        if (general_half[half]) continue; // k_eh_general needs the D halo before E exists: ordered path
+        const int fts[2] = {half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF, half ? MEEPCU_WE_STUFF : MEEPCU_WH_STUFF};
+        // per chunk: the planes (index on device axis A) that hold points another rank receives
+        std::vector<std::set<int> > planes(chunks.size());
+        bool any_send = false;
+        for (int q = 0; q < 2; ++q)
+          for (typename std::map<int, RemoteList>::iterator it = rsend[fts[q]].begin(); it != rsend[fts[q]].end(); ++it)
+            for (int kind = 0; kind < 3; ++kind)
+              for (size_t k = 0; k < it->second.ptr[kind].size(); ++k) {
+                size_t e = 0;
+                const ArrayRec *r = find(it->second.ptr[kind][k], sizeof(T), &e);
+                if (!r || r->kind != A_GRID) return fail(MEEPCU_EINVAL, "remote send pointer outside the registered arrays");
+                const Geom &g = chunks[r->chunk].g;
+                planes[r->chunk].insert((int)(g.dev_index((long long)e) / ((long long)g.pitch * g.nax[1])));
+                any_send = true;
+              }
+        if (!any_send && rrecv[fts[0]].empty() && rrecv[fts[1]].empty()) continue;
+        struct IsBoundary {
+          const std::vector<std::set<int> > *planes;
+          const std::vector<int> *chunk_of;
+          const std::vector<HalfParams<T> > *hp; // NULL: k_curl3d tiles (always march along A)
+          int shift, V;
+          bool operator()(const Tile &t) const {
+            const int pi = t.param >> shift;
+            const std::set<int> &S = (*planes)[(*chunk_of)[pi]];
+            if (S.empty()) return false;
+            if (S.size() > 8) return true; // not a slab cut along A: no split for this chunk
+            int lo = t.a0, hi = t.a1 - 1;
+            if (hp && (*hp)[pi].march) { // tile = positions (A,C) marching along B
+              const int pitch = (*hp)[pi].pitch;
+              const long long p0 = (long long)(t.p0 & ~kTileSpecial) * V;
+              lo = (int)(p0 / pitch);
+              hi = (int)((p0 + (long long)kThreads * V - 1) / pitch);
+            }
+            std::set<int>::const_iterator f = S.lower_bound(lo);
+            return f != S.end() && *f <= hi;
+          }
+        };
+        const int V = (int)(16 / sizeof(T));
+        IsBoundary b3 = {&planes, &c3d_chunk, 0, 0, 1}, bg = {&planes, &half_chunk, &h_half, 2, 1};
+        IsBoundary b3v = b3, bgv = bg;
+        b3v.V = V; bgv.V = V;
+        nb_c3d_tiles[half] = (int)(std::stable_partition(c3d_tiles[half].begin(), c3d_tiles[half].end(), b3) - c3d_tiles[half].begin());
+        nb_c3dv_tiles[half] = (int)(std::stable_partition(c3dv_tiles[half].begin(), c3dv_tiles[half].end(), b3v) - c3dv_tiles[half].begin());
+        for (int cl = 0; cl < 3; ++cl)
+          nb_tiles[half][cl] = (int)(std::stable_partition(tiles[half][cl].begin(), tiles[half][cl].end(), bg) - tiles[half][cl].begin());
+        for (int cl = 0; cl < 2; ++cl)
+          nb_gv_tiles[half][cl] = (int)(std::stable_partition(gv_tiles[half][cl].begin(), gv_tiles[half][cl].end(), bgv) - gv_tiles[half][cl].begin());
+        overlap_half[half] = true;
+      }
     RC(upload(h_half, &d_half));
     RC(upload(h_c3d, &d_c3d));
     for (int half = 0; half < 2; ++half) {
@@ -1637,10 +1774,10 @@ template <class T> struct Ctx : CtxBase {
     return MEEPCU_OK;
   }
   int get_kernel_times(meepcu_kernel_time *out, int cap, int *n) {
-    static const char *names[KC_COUNT] = {"k_halfg_v<B/H,pml>", "k_halfg_v<B/H,pml+pol>", "k_halfg_v<D/E,pml>",
-                                          "k_halfg_v<D/E,pml+pol>", "k_conn", "k_fmp", "k_eh_general", "k_dft",
+    static const char *names[KC_COUNT] = {"k_halfg<B/H,pml>", "k_halfg<B/H,pml+pol/cond>", "k_halfg<D/E,pml>",
+                                          "k_halfg<D/E,pml+pol/cond>", "k_conn", "k_fmp", "k_eh_general", "k_dft",
                                           "k_curl3d_v<B/H>", "k_curl3d_v<D/E>", "k_curl3d (source/metal tiles)",
-                                          "k_halfg (scalar: sources/conductivity)"};
+                                          "(unused)"};
     int m = 0;
     for (int k = 0; k < KC_COUNT && m < cap; ++k) {
       memset(&out[m], 0, sizeof out[m]);
@@ -1655,6 +1792,10 @@ template <class T> struct Ctx : CtxBase {
   }
 
   int launch_conn(int ft) {
+    RC(launch_conn_local(ft));
+    return launch_remote(ft, st);
+  }
+  int launch_conn_local(int ft) {
     const ConnTable<T> &a = d_conn[ft][0];
     ConnTable<T> none;
     memset(&none, 0, sizeof none);
@@ -1672,15 +1813,28 @@ template <class T> struct Ctx : CtxBase {
       RC(prof_end());
       launches++;
     }
-    return launch_remote(ft);
+    return MEEPCU_OK;
   }
 
-  int launch_half(int half, const double *smp) {
+  // The curl / PML kernels of one half step over part of every tile list.
+  //   part 0: all tiles;  1: boundary tiles only (the first nb_* of each list);  2: the rest
+  int launch_compute(int half, const double *smp, int part) {
     // The interior tiles (k_curl3d) and the PML / general tiles (k_halfg) of one half step touch
     // disjoint chunks, so they run side by side on two streams; everything else is ordered after
     // both.  While profiling they are serialised so that each kernel's event time is its own.
-    const bool have_g = n_tiles[half][0] || n_tiles[half][1] || n_tiles[half][2] || n_gv_tiles[half][0] || n_gv_tiles[half][1];
-    const bool fork = (have_g || (n_c3d_tiles[half] && n_c3dv_tiles[half])) && (n_c3d_tiles[half] || n_c3dv_tiles[half]) && !profiling;
+#define MCU_RANGE(total, nb, off, n)                                                               \
+    const int off = part == 2 ? (nb) : 0;                                                         \
+    const int n = part == 0 ? (total) : (part == 1 ? (nb) : (total) - (nb));
+    MCU_RANGE(n_c3dv_tiles[half], nb_c3dv_tiles[half], o_cv, n_cv)
+    MCU_RANGE(n_c3d_tiles[half], nb_c3d_tiles[half], o_c, n_c)
+    MCU_RANGE(n_gv_tiles[half][0], nb_gv_tiles[half][0], o_gv0, n_gv0)
+    MCU_RANGE(n_gv_tiles[half][1], nb_gv_tiles[half][1], o_gv1, n_gv1)
+    MCU_RANGE(n_tiles[half][0], nb_tiles[half][0], o_t0, n_t0)
+    MCU_RANGE(n_tiles[half][1], nb_tiles[half][1], o_t1, n_t1)
+    MCU_RANGE(n_tiles[half][2], nb_tiles[half][2], o_t2, n_t2)
+#undef MCU_RANGE
+    const bool have_g = n_t0 || n_t1 || n_t2 || n_gv0 || n_gv1;
+    const bool fork = (have_g || (n_c && n_cv)) && (n_c || n_cv) && !profiling;
     cudaStream_t sg = fork ? st2 : st;
     if (fork) {
       CU(cudaEventRecord(ev_fork, st));
@@ -1688,79 +1842,83 @@ template <class T> struct Ctx : CtxBase {
     }
     // the bandwidth-bound interior tiles are queued first; the latency-bound PML tiles (high-priority
     // stream) take SM slots as they free up, so the two kinds of CTAs share every SM
-    static const bool interior_first = !getenv("MEEPCU_PML_FIRST");
-    if (interior_first)
-    {
-    if (n_c3dv_tiles[half]) {
+    if (n_cv) {
       RC(prof_begin(half ? KC_CURL3D_D : KC_CURL3D_B));
       if (half)
-        k_curl3d_v<T, true><<<n_c3dv_tiles[half], kThreads, 0, st>>>(d_c3d, d_c3dv_tiles[half]);
+        k_curl3d_v<T, true><<<n_cv, kThreads, 0, st>>>(d_c3d, d_c3dv_tiles[half] + o_cv);
       else
-        k_curl3d_v<T, false><<<n_c3dv_tiles[half], kThreads, 0, st>>>(d_c3d, d_c3dv_tiles[half]);
+        k_curl3d_v<T, false><<<n_cv, kThreads, 0, st>>>(d_c3d, d_c3dv_tiles[half] + o_cv);
       RC(prof_end());
       launches++;
     }
-    }
-    if (n_gv_tiles[half][0]) {
+    // one profiled region per class: the vector kernel and the scalar kernel (tiles with source points,
+    // conductivity, or rows that cannot be vectorised) of a class share its algorithmic bytes
+    if (n_gv0 || n_t0) {
       RC(prof_begin(half ? KC_HALF_D_SIMPLE : KC_HALF_B_SIMPLE));
-      k_halfg_v<T, false><<<n_gv_tiles[half][0], kThreads, 0, sg>>>(d_half, d_gv_tiles[half][0]);
+      if (n_gv0) {
+        k_halfg_v<T, false><<<n_gv0, kThreads, 0, sg>>>(d_half, d_gv_tiles[half][0] + o_gv0);
+        launches++;
+      }
+      if (n_t0) {
+        k_halfg<T, false, false><<<n_t0, kThreads, 0, sg>>>(d_half, d_tiles[half][0] + o_t0, smp);
+        launches++;
+      }
       RC(prof_end());
-      launches++;
     }
-    if (n_gv_tiles[half][1]) {
+    if (n_gv1 || n_t1 || n_t2) {
       RC(prof_begin(half ? KC_HALF_D_GENERAL : KC_HALF_B_GENERAL));
-      k_halfg_v<T, true><<<n_gv_tiles[half][1], kThreads, 0, sg>>>(d_half, d_gv_tiles[half][1]);
+      if (n_gv1) {
+        k_halfg_v<T, true><<<n_gv1, kThreads, 0, sg>>>(d_half, d_gv_tiles[half][1] + o_gv1);
+        launches++;
+      }
+      if (n_t1) {
+        k_halfg<T, false, true><<<n_t1, kThreads, 0, sg>>>(d_half, d_tiles[half][1] + o_t1, smp);
+        launches++;
+      }
+      if (n_t2) {
+        k_halfg<T, true, true><<<n_t2, kThreads, 0, sg>>>(d_half, d_tiles[half][2] + o_t2, smp);
+        launches++;
+      }
       RC(prof_end());
-      launches++;
     }
-    if (n_tiles[half][0]) {
-      RC(prof_begin(KC_HALFG_SCALAR));
-      k_halfg<T, false, false><<<n_tiles[half][0], kThreads, 0, sg>>>(d_half, d_tiles[half][0], smp);
-      RC(prof_end());
-      launches++;
-    }
-    if (n_tiles[half][1]) {
-      RC(prof_begin(KC_HALFG_SCALAR));
-      k_halfg<T, false, true><<<n_tiles[half][1], kThreads, 0, sg>>>(d_half, d_tiles[half][1], smp);
-      RC(prof_end());
-      launches++;
-    }
-    if (n_tiles[half][2]) {
-      RC(prof_begin(KC_HALFG_SCALAR));
-      k_halfg<T, true, true><<<n_tiles[half][2], kThreads, 0, sg>>>(d_half, d_tiles[half][2], smp);
-      RC(prof_end());
-      launches++;
-    }
-    if (n_c3d_tiles[half]) { // tiles with source points / metal planes, or unvectorisable pitch
-      cudaStream_t ss = n_c3dv_tiles[half] ? sg : st; // beside the vector kernel when there is one
+    if (n_c) { // tiles with source points / metal planes, or unvectorisable pitch
+      cudaStream_t ss = n_cv ? sg : st; // beside the vector kernel when there is one
       RC(prof_begin(KC_CURL3D_SPECIAL));
       if (half)
-        k_curl3d<T, true><<<n_c3d_tiles[half], kThreads, 0, ss>>>(d_c3d, d_c3d_tiles[half], smp);
+        k_curl3d<T, true><<<n_c, kThreads, 0, ss>>>(d_c3d, d_c3d_tiles[half] + o_c, smp);
       else
-        k_curl3d<T, false><<<n_c3d_tiles[half], kThreads, 0, ss>>>(d_c3d, d_c3d_tiles[half], smp);
+        k_curl3d<T, false><<<n_c, kThreads, 0, ss>>>(d_c3d, d_c3d_tiles[half] + o_c, smp);
       RC(prof_end());
       launches++;
-    }
-    if (!interior_first)
-    {
-    if (n_c3dv_tiles[half]) {
-      RC(prof_begin(half ? KC_CURL3D_D : KC_CURL3D_B));
-      if (half)
-        k_curl3d_v<T, true><<<n_c3dv_tiles[half], kThreads, 0, st>>>(d_c3d, d_c3dv_tiles[half]);
-      else
-        k_curl3d_v<T, false><<<n_c3dv_tiles[half], kThreads, 0, st>>>(d_c3d, d_c3dv_tiles[half]);
-      RC(prof_end());
-      launches++;
-    }
     }
     if (fork) {
       CU(cudaEventRecord(ev_join, st2));
       CU(cudaStreamWaitEvent(st, ev_join, 0));
     }
+    return MEEPCU_OK;
+  }
+
+  int launch_half(int half, const double *smp) {
     const int ftd = half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF;
     const int fte = half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF;
     const int ftp = half ? MEEPCU_PE_STUFF : MEEPCU_PH_STUFF;
     const int ftw = half ? MEEPCU_WE_STUFF : MEEPCU_WH_STUFF;
+    if (overlap_half[half] && !profiling) {
+      // boundary tiles -> [halo exchange on st_comm  ||  interior tiles + local halo copies] -> join.
+      // The exchange writes only not-owned points of E/H (W), which no kernel of this half reads.
+      RC(launch_compute(half, smp, 1));
+      CU(cudaEventRecord(ev_bdone, st));
+      CU(cudaStreamWaitEvent(st_comm, ev_bdone, 0));
+      RC(launch_remote(ftw, st_comm));
+      RC(launch_remote(fte, st_comm));
+      CU(cudaEventRecord(ev_cdone, st_comm));
+      RC(launch_compute(half, smp, 2));
+      RC(launch_conn_local(ftw));
+      RC(launch_conn_local(fte));
+      CU(cudaStreamWaitEvent(st, ev_cdone, 0));
+      return MEEPCU_OK;
+    }
+    RC(launch_compute(half, smp, 0));
     if (eager_db[half]) RC(launch_conn(ftd)); // step.cpp:72,104
     if (general_half[half]) {
       if (n_fmp[half]) {
@@ -1861,7 +2019,7 @@ template <class T> struct Ctx : CtxBase {
       if (!eager_p[half]) RC(launch_conn(half ? MEEPCU_PE_STUFF : MEEPCU_PH_STUFF));
     }
     for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it)
-      if (it->second.mut) RC(big(it->second) ? staged_copy(it->second, true) : copy_array(it->second, true));
+      if (it->second.mut) RC(big(it->second) && !it->second.pinned ? staged_copy(it->second, true) : copy_array(it->second, true));
     CU(cudaStreamSynchronize(st));
     return MEEPCU_OK;
   }
@@ -1869,7 +2027,7 @@ template <class T> struct Ctx : CtxBase {
   int sync_from_host() {
     CU(cudaSetDevice(cfg.device));
     for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it)
-      RC(big(it->second) ? staged_copy(it->second, false) : copy_array(it->second, false));
+      RC(big(it->second) && !it->second.pinned ? staged_copy(it->second, false) : copy_array(it->second, false));
     CU(cudaStreamSynchronize(st));
     return MEEPCU_OK;
   }
@@ -1909,6 +2067,11 @@ template <class T> struct Ctx : CtxBase {
     out->algorithmic_bytes_per_step = alg_bytes;
     out->last_step_ms = last_ms;
     out->reserved[0] = nr_unconverged;
+    for (std::map<const char *, ArrayRec>::const_iterator it = arrays.begin(); it != arrays.end(); ++it)
+      if (it->second.pinned) {
+        out->reserved[1]++; // host arrays page-locked in place (meepcu_config::pin_host)
+        out->reserved[2] += (int64_t)(it->second.n_host * sizeof(T) * (it->second.kind == A_DFT ? 2 : 1));
+      }
     return MEEPCU_OK;
   }
   int get_timers(double out[22]) {

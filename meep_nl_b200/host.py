@@ -334,6 +334,7 @@ class fields:
         self.is_real = 0
         self.t = 0
         self.nl_mode, self.device = nl_mode, device
+        self.pin_host = True  # the numpy arrays below outlive the context: sync by plain DMA (meepcu_config::pin_host)
         self.boundaries = {d: Metallic for d in range(3)}
         self.k = {d: 0.0 for d in range(3)}
         self.eikna = {d: 1 + 0j for d in range(3)}
@@ -609,6 +610,7 @@ class fields:
         cfg.a, cfg.dt, cfg.courant = self.a, self.dt, self.s.Courant
         cfg.beta = 0.0
         cfg.nl_mode, cfg.device, cfg.t = self.nl_mode, self.device, self.t
+        cfg.pin_host = 1 if self.pin_host else 0
         ctx = A.vp()
         b.check(b.create(C.byref(cfg), C.byref(ctx)))
         self.ctx = ctx
