@@ -46,7 +46,9 @@ def parse():
     ap.add_argument("--workload", default="vac3d")
     ap.add_argument("--size", dest="n", type=int, default=256)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--pml", type=float, default=0.0, help="PML thickness of the phc3d workload (default 1.0)")
     ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--cpu-size", type=int, default=0, help="grid size of the CPU baseline sample (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -60,8 +62,8 @@ def build_problem(args, backend, device=0, rank=0, world=1, comm_id=None):
     rt = np.float64 if args.dtype == "f64" else np.float32
     n = args.n
     L = n / 10.0
-    gv = H.vol3d(L * world, L, L, 10)
     w = args.workload
+    gv = H.vol3d(L * world, L, 1.5 * L if w == "phc3d" else L, 10)
     split, rank_of = None, None
     if world > 1:
         cuts, rank_of = H.slab_decomposition(gv, world, 0)
@@ -115,6 +117,15 @@ def build_problem(args, backend, device=0, rank=0, world=1, comm_id=None):
         f.add_point_source(Ez, 0.3, 0.2, 0.0, 4.0, c, amp)
         f.add_point_source(Ex, 0.3, 0.2, 0.0, 4.0, (c[0] + 0.25, c[1] + 0.1, c[2]), amp)
         f.add_point_source(Ey, 0.3, 0.2, 0.0, 4.0, (c[0], c[1] + 0.25, c[2] + 0.1), amp)
+    elif w == "phc3d":  # BASELINE configs[4] shape: eps-12 slab, PML in z only, periodic x,y (n x n x 1.5n)
+        zlo, zhi = 0.75 * L - 0.25, 0.75 * L + 0.25
+        s = H.structure(gv, lambda x, y, z: 1.0 + 11.0 * ((z > zlo) & (z < zhi)), pml=args.pml or 1.0,
+                        pml_dirs=[2], realnum=rt)
+        f = H.fields(s, backend, device=device)
+        f.use_bloch(0, 0.0)
+        f.use_bloch(1, 0.0)
+        f.use_real_fields()
+        f.add_point_source(Ey, 0.25, 0.2, 0.0, 4.0, gv.center(), 1.0)
     else:
         raise SystemExit("unknown workload " + w)
     return gv, f
@@ -186,31 +197,44 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
+def dims(args, n=None):
+    n = n or args.n
+    return (n, n, n * 3 // 2) if args.workload == "phc3d" else (n, n, n)
+
+
 def workload_name(args):
-    return "%s_%d^3_%s" % (args.workload, args.n, args.dtype)
+    d = dims(args)
+    return "%s_%dx%dx%d_%s" % (args.workload, d[0], d[1], d[2], args.dtype)
 
 
-def ref_case(args):
-    m = {"vac3d": "vac3d:%d", "lorentz3d": "lorentz3d:%d:100", "nr3d": "nrslab3d:%d"}
-    return (m.get(args.workload) or "vac3d:%d") % args.n
+# reference-driver case per workload, and the largest size the CPU arm runs in a bounded time
+REF_CASES = {"vac3d": ("vac3d:%d", 256), "lorentz3d": ("lorentz3d:%d:100", 192), "nr3d": ("nrslab3d:%d", 96),
+             "phc3d": ("phc3d:%d:1.0", 160)}
 
 
 def run_reference_cpu(args, steps, warmup):
-    """the reference's own CPU code on this box's host cores; returns (mcells/s, info) or None"""
+    """the reference's own CPU code on this box's host cores; returns (mcells/s, info) or None.
+    A bounded sample: the same workload, at most REF_CASES[..][1] points per side."""
     fl = "fp64" if args.dtype == "f64" else "fp32"
     drv = os.path.join(ROOT, "oracle", "_ref", fl, "ref_driver")
     cores = os.cpu_count() or 1
-    if os.path.exists(drv) and args.workload in ("vac3d", "lorentz3d", "nr3d"):
+    if os.path.exists(drv) and args.workload in REF_CASES:
+        tmpl, cap = REF_CASES[args.workload]
+        n = min(args.n, args.cpu_size or cap)
+        case = tmpl % n
         with tempfile.NamedTemporaryFile(suffix=".json") as tf:
             env = dict(os.environ, OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="spread")
-            subprocess.run([drv, "--mode", "ref", "--case", ref_case(args), "--steps", str(steps), "--warmup",
+            subprocess.run([drv, "--mode", "ref", "--case", case, "--steps", str(steps), "--warmup",
                             str(warmup), "--json", tf.name], check=True, env=env, stdout=subprocess.DEVNULL,
                            stderr=subprocess.DEVNULL, timeout=3000)
             d = json.load(open(tf.name))
-        return d["mcells_per_s"], {"kind": "reference", "cores": d["threads"],
-                                   "sample": "%d warm-up + %d timed fields::step() of the full %s problem "
+        dd = dims(args, n)
+        scale = "the full problem" if n == args.n else "the same problem at %dx%dx%d (the GPU arm runs %s)" % (
+            dd[0], dd[1], dd[2], workload_name(args))
+        return d["mcells_per_s"], {"kind": "reference", "cores": d["threads"], "cells": dd[0] * dd[1] * dd[2],
+                                   "sample": "%d warm-up + %d timed fields::step() of %s, case %s "
                                              "(unmodified reference core, OpenMP, %d threads)"
-                                             % (warmup, steps, ref_case(args), d["threads"])}
+                                             % (warmup, steps, scale, case, d["threads"])}
     # fall back to the CPU restatement (still the reference's algorithm, single translation unit)
     from meep_nl_b200 import _cabi
     lib = os.path.join(ROOT, "oracle", "liboracle_meep.so")
@@ -218,14 +242,17 @@ def run_reference_cpu(args, steps, warmup):
         return None
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     b = _cabi.Backend(lib)
-    gv, f = build_problem(args, b)
+    small = argparse.Namespace(**vars(args))
+    small.n = min(args.n, args.cpu_size or 128)
+    gv, f = build_problem(small, b)
     f.step(max(warmup, 1))
     t0 = time.perf_counter()
     f.step(steps)
     dt = time.perf_counter() - t0
     f.close()
-    return gv.cells() * steps / dt / 1e6, {"kind": "port", "cores": cores,
-                                           "sample": "%d timed steps of the full problem through the CPU oracle" % steps}
+    return gv.cells() * steps / dt / 1e6, {"kind": "port", "cores": cores, "cells": gv.cells(),
+                                           "sample": "%d timed steps of %s at n=%d through the CPU oracle" % (
+                                               steps, args.workload, small.n)}
 
 
 def main_reference(args):
@@ -238,10 +265,9 @@ def main_reference(args):
         return
     val, info = r
     steps = max(2, min(args.steps, args.cpu_steps))
-    cells = args.n ** 3
     line = {"impl": "reference", "metric": "Mcell-updates/s (fused E+H step)", "value": val, "unit": "Mcell/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
-            "ms_per_step": cells / val / 1e3, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": info["cells"] / val / 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(args)},
             "cpu_baseline": dict(info, value=val, unit="Mcell/s"),
@@ -271,10 +297,16 @@ def main_ours(args):
         tid = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device="cuda")
         dist.broadcast(tid, 0)
         comm_id = bytes(tid.cpu().tolist())
+    t_setup = time.perf_counter()
     gv, f = build_problem(args, backend, device=local, rank=rank, world=world, comm_id=comm_id)
     K, W = args.steps, max(args.warmup, 3)
+    t_build = time.perf_counter()
     f.init()
+    t_init = time.perf_counter()
     f.step(W)
+    if rank == 0:
+        sys.stderr.write("[bench] %s: host model %.1f s, attach (describe + upload) %.1f s, %d warm-up steps %.2f s\n"
+                         % (workload_name(args), t_build - t_setup, t_init - t_build, W, time.perf_counter() - t_init))
     st0 = f.stats()
 
     def barrier():
@@ -361,7 +393,7 @@ def main_ours(args):
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(args), "cells": cells, "chunks": len(f.chunks),
                        "l2": "working set %.1f GB >> 126 MB L2 (no flush needed)" % (st1.device_bytes / 1e9),
-                       "parallelism": "1 GPU" if world == 1 else "%d X-slabs, one rank per GPU, NCCL halo exchange (grid %dx%dx%d)" % (world, args.n * world, args.n, args.n),
+                       "parallelism": "1 GPU" if world == 1 else "%d X-slabs, one rank per GPU, NCCL halo exchange (grid %dx%dx%d)" % (world, dims(args)[0] * world, dims(args)[1], dims(args)[2]),
                        "probe_Ez_center": probe, "wall_ms_per_step": wall / K * 1e3},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(st1.kernel_launches - st0.kernel_launches),
             "roofline": roof}

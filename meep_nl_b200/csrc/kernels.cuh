@@ -482,8 +482,8 @@ template <class T> struct HalfHeader { // leading, component-independent part of
   double dt;
 };
 
-template <class T, bool HAS_COND, bool HAS_POL>
-__global__ void __launch_bounds__(kThreads, 3)
+template <class T, bool HAS_COND, bool HAS_POL, bool PIPE = false>
+__global__ void __launch_bounds__(kThreads, PIPE ? 2 : 3)
     k_halfg(const HalfParams<T> *__restrict__ params, const Tile *__restrict__ tiles,
             const double *__restrict__ smp) {
   __shared__ HalfHeader<T> H;
@@ -514,8 +514,10 @@ __global__ void __launch_bounds__(kThreads, 3)
   long long i = (long long)m0 * s_m + (long long)io * s_o + ic;
   const int is_D = H.is_D, cmp = H.cmp;
   const double dt = H.dt;
+  PointVals<T, HAS_COND, HAS_POL> v, vn;
+  if (PIPE && m0 <= m1) gather_point<T, HAS_COND, HAS_POL>(c, Csm.pol, i, v);
 #pragma unroll 2
-  for (int im = m0; im <= m1; ++im, i += s_m) {
+  for (int im = m0; im <= m1; ++im, i += s_m, PIPE ? (void)(v = vn) : (void)0) {
     const int ia = march ? io : im, ib = march ? im : io;
     if (MCU_PREFETCH_PLANES > 0 && im + MCU_PREFETCH_PLANES <= m1) {
       const long long ipf = i + MCU_PREFETCH_PLANES * s_m;
@@ -542,8 +544,11 @@ __global__ void __launch_bounds__(kThreads, 3)
         }
       }
     }
-    PointVals<T, HAS_COND, HAS_POL> v;
-    gather_point<T, HAS_COND, HAS_POL>(c, Csm.pol, i, v);
+    if (PIPE) { // operands of the next iteration first (see k_halfg_v)
+      if (im < m1) gather_point<T, HAS_COND, HAS_POL>(c, Csm.pol, i + s_m, vn);
+    }
+    else
+      gather_point<T, HAS_COND, HAS_POL>(c, Csm.pol, i, v);
     finish_point<T, HAS_COND, HAS_POL>(c, Csm.pol, i, ia, ib, ic, v, smp, is_D, cmp, dt);
   }
 }
@@ -949,8 +954,36 @@ __device__ __forceinline__ void vload_shift(T *out, const T *base, long long i, 
   }
 }
 
-template <class T, bool HAS_POL>
-__global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : 3)
+// UPML coefficients of one family (sig/kap/siginv indexed by k = 2*idx[axis] + off,
+// meep_internals.hpp:241-247) for the V points of a thread: a = kap[k] - sig[k], b = siginv[k]
+// (WFORM: a = kap + sig, b = kap - sig).  The same operations the reference does inline, done once.
+template <class T, bool WFORM>
+__device__ __forceinline__ void load_coef(const T *__restrict__ sig, const T *__restrict__ kap,
+                                          const T *__restrict__ siginv, int axis, int off, int ia, int ib,
+                                          int ic, T *a, T *b) {
+  constexpr int V = VecOf<T>::V;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    if (j == 0 || axis == 2) {
+      const int k = 2 * pick3(axis, ia, ib, ic + j) + off;
+      const T kp = __ldg(kap + k), sg = __ldg(sig + k);
+      if (WFORM) { a[j] = kp + sg; b[j] = kp - sg; }
+      else { a[j] = kp - sg; b[j] = __ldg(siginv + k); }
+    }
+    else { a[j] = a[0]; b[j] = b[0]; }
+  }
+}
+
+template <class T> struct HalfgVals { // the operands of one thread-iteration of k_halfg_v
+  T g1[VecOf<T>::V], g1p[VecOf<T>::V], g2[VecOf<T>::V], g2p[VecOf<T>::V], fo[VecOf<T>::V], fuo[VecOf<T>::V],
+      eo[VecOf<T>::V], fwo[VecOf<T>::V], uv[VecOf<T>::V];
+};
+
+// PIPE: software pipelining -- the operands of iteration n+1 are loaded into a second register set
+// before iteration n computes and stores (the compiler cannot move those loads above the stores
+// itself: nothing tells it that f, f_u, f_w and E do not alias the operand arrays).
+template <class T, bool HAS_POL, bool PIPE>
+__global__ void __launch_bounds__(kThreads, (sizeof(T) == 8 || PIPE) ? 2 : 3)
     k_halfg_v(const HalfParams<T> *__restrict__ params, const Tile *__restrict__ tiles) {
   constexpr int V = VecOf<T>::V;
   __shared__ HalfHeader<T> H;
@@ -1003,8 +1036,44 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : 3)
   long long i = (long long)m0 * s_m + (long long)io * s_o + ic;
   const bool sh1 = c.s1 == 1 || c.s1 == -1, sh2 = c.g2 && (c.s2 == 1 || c.s2 == -1);
   const T dtdx = c.dtdx;
-  for (int im = m0; im <= m1; ++im, i += s_m) {
+  // UPML coefficients: constant along the march unless the PML axis IS the march axis (thin slabs
+  // march along their long axis, so that is the rare case) -> loaded once, kept in registers
+  T cA[V], cB[V], uA[V], uB[V], wP[V], wM[V];
+  const bool has_k = c.kaxis >= 0, has_ku = c.kuaxis >= 0, has_kw = c.e && c.fw;
+  const bool var_k = has_k && c.kaxis == ax_m, var_ku = has_ku && c.kuaxis == ax_m, var_kw = has_kw && c.kwaxis == ax_m;
+  {
+    const int ia0 = march ? io : m0, ib0 = march ? m0 : io;
+    if (has_k && !var_k) load_coef<T, false>(c.sig, c.kap, c.siginv, c.kaxis, c.koff, ia0, ib0, ic, cA, cB);
+    if (has_ku && !var_ku) load_coef<T, false>(c.sigu, c.kapu, c.siginvu, c.kuaxis, c.kuoff, ia0, ib0, ic, uA, uB);
+    if (has_kw && !var_kw) load_coef<T, true>(c.sigw, c.kapw, c.kapw, c.kwaxis, c.kwoff, ia0, ib0, ic, wP, wM);
+  }
+  const int pitch = H.pitch;
+  auto gather = [&](long long ii, HalfgVals<T> &v) {
+    vload<T>(v.g1, c.g1 + ii);
+    if (sh1) vload_shift<T>(v.g1p, c.g1, ii, c.s1, v.g1, c.s1 > 0 ? (ic + V < pitch ? ii + V : ii) : (ic > 0 ? ii - 1 : ii));
+    else vload<T>(v.g1p, c.g1 + ii + c.s1);
+    if (c.g2) {
+      vload<T>(v.g2, c.g2 + ii);
+      if (sh2) vload_shift<T>(v.g2p, c.g2, ii, c.s2, v.g2, c.s2 > 0 ? (ic + V < pitch ? ii + V : ii) : (ic > 0 ? ii - 1 : ii));
+      else vload<T>(v.g2p, c.g2 + ii + c.s2);
+    }
+    vload_rw<T>(v.fo, c.f + ii);
+    if (c.fu) vload_rw<T>(v.fuo, c.fu + ii);
+    if (c.e) {
+      if (c.u) vload<T>(v.uv, c.u + ii);
+      if (c.fw) {
+        vload_rw<T>(v.fwo, c.fw + ii);
+        vload_rw<T>(v.eo, c.e + ii);
+      }
+    }
+  };
+  HalfgVals<T> cur, nxt;
+  if (PIPE && m0 <= m1) gather(i, cur);
+  for (int im = m0; im <= m1; ++im, i += s_m, PIPE ? (void)(cur = nxt) : (void)0) {
     const int ia = march ? io : im, ib = march ? im : io;
+    if (var_k) load_coef<T, false>(c.sig, c.kap, c.siginv, c.kaxis, c.koff, ia, ib, ic, cA, cB);
+    if (var_ku) load_coef<T, false>(c.sigu, c.kapu, c.siginvu, c.kuaxis, c.kuoff, ia, ib, ic, uA, uB);
+    if (var_kw) load_coef<T, true>(c.sigw, c.kapw, c.kapw, c.kwaxis, c.kwoff, ia, ib, ic, wP, wM);
     if (MCU_PREFETCH_PLANES > 0 && im + MCU_PREFETCH_PLANES <= m1) {
       const long long ipf = i + MCU_PREFETCH_PLANES * s_m;
       prefetch_l2(c.g1 + ipf);
@@ -1030,24 +1099,10 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : 3)
       }
     }
     // ---------------- gather ----------------
-    T g1[V], g1p[V], g2[V], g2p[V], fo[V], fuo[V], eo[V], fwo[V], uv[V];
-    vload<T>(g1, c.g1 + i);
-    if (sh1) vload_shift<T>(g1p, c.g1, i, c.s1, g1, c.s1 > 0 ? (ic + V < H.pitch ? i + V : i) : (ic > 0 ? i - 1 : i));
-    else vload<T>(g1p, c.g1 + i + c.s1);
-    if (c.g2) {
-      vload<T>(g2, c.g2 + i);
-      if (sh2) vload_shift<T>(g2p, c.g2, i, c.s2, g2, c.s2 > 0 ? (ic + V < H.pitch ? i + V : i) : (ic > 0 ? i - 1 : i));
-      else vload<T>(g2p, c.g2 + i + c.s2);
-    }
-    vload_rw<T>(fo, c.f + i);
-    if (c.fu) vload_rw<T>(fuo, c.fu + i);
-    if (c.e) {
-      if (c.u) vload<T>(uv, c.u + i);
-      if (c.fw) {
-        vload_rw<T>(fwo, c.fw + i);
-        vload_rw<T>(eo, c.e + i);
-      }
-    }
+    if (PIPE) { if (im < m1) gather(i + s_m, nxt); }
+    else gather(i, cur);
+    T *const g1 = cur.g1, *const g1p = cur.g1p, *const g2 = cur.g2, *const g2p = cur.g2p, *const fo = cur.fo,
+             *const fuo = cur.fuo, *const eo = cur.eo, *const fwo = cur.fwo, *const uv = cur.uv;
     // ---------------- step_curl per element (step_generic.cpp:89-252) ----------------
     const unsigned zdb = zfix_db | (((zlo_db && im == lo_m) || (zhi_db && im == hi_m)) ? full : 0u);
     const unsigned zeh = zfix_eh | (((zlo_eh && im == lo_m) || (zhi_eh && im == hi_m)) ? full : 0u);
@@ -1057,28 +1112,24 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : 3)
       const T curl = c.g2 ? (g1p[j] - g1[j] + g2[j] - g2p[j]) : (g1p[j] - g1[j]);
       const T fold = fo[j];
       T fnew;
-      if (c.kaxis < 0) {
-        if (c.kuaxis < 0)
+      if (!has_k) {
+        if (!has_ku)
           fnew = fold - dtdx * curl;
         else {
-          const int ku = 2 * pick3(c.kuaxis, ia, ib, ic + j) + c.kuoff;
           const T fprev = fuo[j];
           const T fu_ = fprev - dtdx * curl;
           fun[j] = fu_;
-          fnew = __ldg(c.siginvu + ku) * ((__ldg(c.kapu + ku) - __ldg(c.sigu + ku)) * fold + fu_ - fprev);
+          fnew = uB[j] * (uA[j] * fold + fu_ - fprev);
         }
       }
       else {
-        const int k = 2 * pick3(c.kaxis, ia, ib, ic + j) + c.koff;
-        const T kap = __ldg(c.kap + k), sig = __ldg(c.sig + k), siginv = __ldg(c.siginv + k);
-        if (c.kuaxis < 0)
-          fnew = ((kap - sig) * fold - dtdx * curl) * siginv;
+        if (!has_ku)
+          fnew = (cA[j] * fold - dtdx * curl) * cB[j];
         else {
-          const int ku = 2 * pick3(c.kuaxis, ia, ib, ic + j) + c.kuoff;
           const T fprev = fuo[j];
-          const T fu_ = ((kap - sig) * fprev - dtdx * curl) * siginv;
+          const T fu_ = (cA[j] * fprev - dtdx * curl) * cB[j];
           fun[j] = fu_;
-          fnew = __ldg(c.siginvu + ku) * ((__ldg(c.kapu + ku) - __ldg(c.sigu + ku)) * fold + fu_ - fprev);
+          fnew = uB[j] * (uA[j] * fold + fu_ - fprev);
         }
       }
       if ((zdb >> j) & 1u) fnew = 0;
@@ -1109,10 +1160,8 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : 3)
       T fwn[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        const int kw = 2 * pick3(c.kwaxis, ia, ib, ic + j) + c.kwoff;
-        const T kapwkw = __ldg(c.kapw + kw), sigwkw = __ldg(c.sigw + kw);
         const bool on = (own >> j) & 1u;
-        T enew = eo[j] + ((kapwkw + sigwkw) * gu[j] - (kapwkw - sigwkw) * fwo[j]);
+        T enew = eo[j] + (wP[j] * gu[j] - wM[j] * fwo[j]);
         if ((zeh >> j) & 1u) enew = 0;
         en[j] = on ? enew : eo[j];
         fwn[j] = on ? gu[j] : fwo[j];
@@ -1190,16 +1239,24 @@ template <class T> struct ConnRun {
   const T *src;
   int n, dst_stride, src_stride, negate;
 };
+constexpr int kConnPiece = 128; // runs are cut into pieces of at most this many elements
 template <class T>
 __global__ void __launch_bounds__(kThreads) k_conn_runs(const ConnRun<T> *__restrict__ runs, int nruns) {
+  // one warp per piece, four independent loads per lane in flight before the first store
   const int lane = threadIdx.x & 31;
-  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nruns; r += warps_per_grid) {
-    const ConnRun<T> q = runs[r];
-    if (q.negate)
-      for (int j = lane; j < q.n; j += 32) q.dst[(long long)j * q.dst_stride] = -q.src[(long long)j * q.src_stride];
-    else
-      for (int j = lane; j < q.n; j += 32) q.dst[(long long)j * q.dst_stride] = q.src[(long long)j * q.src_stride];
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= nruns) return;
+  const ConnRun<T> q = runs[r];
+  T v[kConnPiece / 32];
+#pragma unroll
+  for (int k = 0; k < kConnPiece / 32; ++k) {
+    const int j = lane + 32 * k;
+    if (j < q.n) v[k] = q.src[(long long)j * q.src_stride];
+  }
+#pragma unroll
+  for (int k = 0; k < kConnPiece / 32; ++k) {
+    const int j = lane + 32 * k;
+    if (j < q.n) q.dst[(long long)j * q.dst_stride] = q.negate ? -v[k] : v[k];
   }
 }
 

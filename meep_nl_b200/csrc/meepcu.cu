@@ -1592,7 +1592,13 @@ template <class T> struct Ctx : CtxBase {
               }
             }
           }
-          runs.push_back(r);
+          for (int o = 0; o < r.n; o += kConnPiece) { // k_conn_runs: one warp per piece
+            ConnRun<T> pc = r;
+            pc.dst = r.dst + (long long)o * r.dst_stride;
+            pc.src = r.src + (long long)o * r.src_stride;
+            pc.n = std::min(kConnPiece, r.n - o);
+            runs.push_back(pc);
+          }
           k += r.n;
         }
       }
@@ -1807,7 +1813,7 @@ template <class T> struct Ctx : CtxBase {
       launches++;
     }
     if (n_runs[ft]) {
-      const int grid = std::min((n_runs[ft] + 7) / 8, 148 * 16);
+      const int grid = (n_runs[ft] + 7) / 8;
       RC(prof_begin(KC_CONN));
       k_conn_runs<T><<<grid, kThreads, 0, st>>>(d_runs[ft], n_runs[ft]);
       RC(prof_end());
@@ -1819,6 +1825,7 @@ template <class T> struct Ctx : CtxBase {
   // The curl / PML kernels of one half step over part of every tile list.
   //   part 0: all tiles;  1: boundary tiles only (the first nb_* of each list);  2: the rest
   int launch_compute(int half, const double *smp, int part) {
+    static const bool pipe_pml = getenv("MEEPCU_PIPE") != 0;
     // The interior tiles (k_curl3d) and the PML / general tiles (k_halfg) of one half step touch
     // disjoint chunks, so they run side by side on two streams; everything else is ordered after
     // both.  While profiling they are serialised so that each kernel's event time is its own.
@@ -1856,11 +1863,13 @@ template <class T> struct Ctx : CtxBase {
     if (n_gv0 || n_t0) {
       RC(prof_begin(half ? KC_HALF_D_SIMPLE : KC_HALF_B_SIMPLE));
       if (n_gv0) {
-        k_halfg_v<T, false><<<n_gv0, kThreads, 0, sg>>>(d_half, d_gv_tiles[half][0] + o_gv0);
+        if (pipe_pml) k_halfg_v<T, false, true><<<n_gv0, kThreads, 0, sg>>>(d_half, d_gv_tiles[half][0] + o_gv0);
+        else k_halfg_v<T, false, false><<<n_gv0, kThreads, 0, sg>>>(d_half, d_gv_tiles[half][0] + o_gv0);
         launches++;
       }
       if (n_t0) {
-        k_halfg<T, false, false><<<n_t0, kThreads, 0, sg>>>(d_half, d_tiles[half][0] + o_t0, smp);
+        if (pipe_pml) k_halfg<T, false, false, true><<<n_t0, kThreads, 0, sg>>>(d_half, d_tiles[half][0] + o_t0, smp);
+        else k_halfg<T, false, false><<<n_t0, kThreads, 0, sg>>>(d_half, d_tiles[half][0] + o_t0, smp);
         launches++;
       }
       RC(prof_end());
@@ -1868,7 +1877,8 @@ template <class T> struct Ctx : CtxBase {
     if (n_gv1 || n_t1 || n_t2) {
       RC(prof_begin(half ? KC_HALF_D_GENERAL : KC_HALF_B_GENERAL));
       if (n_gv1) {
-        k_halfg_v<T, true><<<n_gv1, kThreads, 0, sg>>>(d_half, d_gv_tiles[half][1] + o_gv1);
+        if (pipe_pml) k_halfg_v<T, true, true><<<n_gv1, kThreads, 0, sg>>>(d_half, d_gv_tiles[half][1] + o_gv1);
+        else k_halfg_v<T, true, false><<<n_gv1, kThreads, 0, sg>>>(d_half, d_gv_tiles[half][1] + o_gv1);
         launches++;
       }
       if (n_t1) {

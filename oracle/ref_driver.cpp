@@ -241,7 +241,8 @@ static problem *build(const std::string &spec, int nchunks) {
     g_slab_lo = 0.75 * n / a - 0.25;
     g_slab_hi = 0.75 * n / a + 0.25;
     g_slab_eps = 12.0;
-    p->s = new structure(p->gv, slab_eps_z, pml(0.4, Z), identity(), nchunks, 0.5, false);
+    // phc3d:n:thickness -- PML thickness in z (default 0.4: the small golden case; bench.py asks for 1.0)
+    p->s = new structure(p->gv, slab_eps_z, pml(param > 0 ? param : 0.4, Z), identity(), nchunks, 0.5, false);
     p->f = new fields(p->s);
     p->f->use_bloch(X, 0.0);
     p->f->use_bloch(Y, 0.0);
