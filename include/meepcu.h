@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MEEPCU_ABI_VERSION 1
+#define MEEPCU_ABI_VERSION 2
 
 /* ---- enums: numeric values are the reference's (src/meep/vec.hpp:27-79) ---- */
 #define MEEPCU_NUM_COMPONENTS 20 /* Ex,Ey,Er,Ep,Ez,Hx..Hz,Dx..Dz,Bx..Bz           vec.hpp:31-52 */
@@ -79,6 +79,7 @@ typedef struct {
                         context, so that meepcu_sync_* are plain DMA at PCIe speed; the arrays must then
                         outlive the context.  0: copy through library-owned pinned staging buffers. */
   int reserved[6];
+  double bfast_scaled_k[3]; /* fields::bfast_scaled_k (X,Y,Z), all zero = no BFAST terms (step_db.cpp:65,129-143) */
 } meepcu_config;
 
 /* One fields_chunk + its structure_chunk (src/meep.hpp:590-598,1461-1485).  Array length is
@@ -101,6 +102,7 @@ typedef struct {
   int sigsize[6];                                     /* structure_chunk::sigsize */
   int rank;     /* owning rank (structure_chunk::n_proc()); single-GPU: 0 */
   int reserved[7];
+  void *f_bfast[MEEPCU_NUM_COMPONENTS][2]; /* fields_chunk::f_bfast (BFAST auxiliary F, step_db.cpp:76-79) */
 } meepcu_chunk_desc;
 
 /* lorentzian_susceptibility (src/susceptibility.cpp:98-281, src/meep.hpp:262-330).  */

@@ -12,7 +12,7 @@ import os
 
 NUM_COMPONENTS = 20
 NUM_FIELD_TYPES = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # component ids (reference src/meep/vec.hpp:31-52)
 Ex, Ey, Er, Ep, Ez, Hx, Hy, Hr, Hp, Hz, Dx, Dy, Dr, Dp, Dz, Bx, By, Br, Bp, Bz = range(20)
@@ -31,7 +31,8 @@ class Config(C.Structure):
     _fields_ = [("abi_version", C.c_int), ("realnum_bytes", C.c_int), ("is_real", C.c_int),
                 ("dim", C.c_int), ("a", C.c_double), ("dt", C.c_double), ("courant", C.c_double),
                 ("beta", C.c_double), ("nl_mode", C.c_int), ("device", C.c_int), ("t", C.c_int),
-                ("pin_host", C.c_int), ("reserved", C.c_int * 6)]
+                ("pin_host", C.c_int), ("reserved", C.c_int * 6),
+                ("bfast_scaled_k", C.c_double * 3)]
 
 
 class ChunkDesc(C.Structure):
@@ -42,7 +43,7 @@ class ChunkDesc(C.Structure):
                 ("chi3", vp * NUM_COMPONENTS), ("conductivity", (vp * 5) * NUM_COMPONENTS),
                 ("condinv", (vp * 5) * NUM_COMPONENTS),
                 ("sig", vp * 6), ("kap", vp * 6), ("siginv", vp * 6), ("sigsize", C.c_int * 6),
-                ("rank", C.c_int), ("reserved", C.c_int * 7)]
+                ("rank", C.c_int), ("reserved", C.c_int * 7), ("f_bfast", (vp * 2) * NUM_COMPONENTS)]
 
 
 class SusceptibilityDesc(C.Structure):

@@ -68,6 +68,12 @@ template <class T> struct CompParams {
   const T *sigu, *kapu, *siginvu;
   int kuaxis, kuoff;
   unsigned zmask_db; // metal planes: bit d -> idx[d]==lo[d], bit 3+d -> idx[d]==hi[d]
+  // ---- 2-D exp(i beta z) term (step_db.cpp:161-175, step_beta): f += betadt * gb[i] and variants ----
+  const T *gb;
+  T betadt;
+  // ---- BFAST (step_db.cpp:129-143, step_bfast): F = k1 (g1[i+s1]+g1[i]) - k2 (g2[i+s2]+g2[i]) - F ----
+  T *fb;        // fields_chunk::f_bfast (NULL: no BFAST terms)
+  T bk1, bk2;   // after the g1/g2 swap rule
   // ---- sources ----
   const SrcEntry *csrc; // currents (step_source)
   const SrcEntry *isrc; // integrated sources (update_eh.cpp:136-146)
@@ -310,7 +316,7 @@ __global__ void __launch_bounds__(kThreads)
 //   HAS_COND: conductivity terms (cnd, cndinv, fcnd) compiled in;  HAS_POL: polarisations compiled in
 // ------------------------------------------------------------------------------------------------
 template <class T, bool HAS_COND, bool HAS_POL> struct PointVals {
-  T g1p, g1, g2, g2p, f, fu, e, fw, u;
+  T g1p, g1, g2, g2p, f, fu, e, fw, u, gb, fb;
   T cnd, cndinv, fcnd;
   T p[HAS_POL ? kMaxPol : 1], pp[HAS_POL ? kMaxPol : 1], s[HAS_POL ? kMaxPol : 1];
 };
@@ -326,6 +332,8 @@ __device__ __forceinline__ void gather_point(const CompParams<T> &c, const PolPa
   }
   v.f = c.f[i];
   if (c.fu) v.fu = c.fu[i];
+  if (c.gb) v.gb = __ldg(c.gb + i);
+  if (c.fb) v.fb = c.fb[i];
   if (HAS_COND && c.cnd) {
     v.cnd = __ldg(c.cnd + i);
     v.cndinv = __ldg(c.cndinv + i);
@@ -362,7 +370,8 @@ __device__ __forceinline__ void finish_point(const CompParams<T> &c, const PolPa
   else
     curl = (v.g1p - v.g1);
   const bool cond = HAS_COND && c.cnd;
-  T fnew;
+  T fnew, fun = 0, fc = 0; // new f, f_u, f_cond (stored below, after the beta term)
+  T siginv = 0, siginvu = 0;
   const T fold = v.f;
   if (c.kaxis < 0) {
     if (c.kuaxis < 0) {
@@ -374,23 +383,22 @@ __device__ __forceinline__ void finish_point(const CompParams<T> &c, const PolPa
     else {
       const int ku = 2 * pick3(c.kuaxis, ia, ib, ic) + c.kuoff;
       const T fprev = v.fu;
-      T fun;
       if (cond)
         fun = ((1 - c.dt2 * v.cnd) * fprev - c.dtdx * curl) * v.cndinv;
       else
         fun = fprev - c.dtdx * curl;
-      c.fu[i] = fun;
-      fnew = __ldg(c.siginvu + ku) * ((__ldg(c.kapu + ku) - __ldg(c.sigu + ku)) * fold + fun - fprev);
+      siginvu = __ldg(c.siginvu + ku);
+      fnew = siginvu * ((__ldg(c.kapu + ku) - __ldg(c.sigu + ku)) * fold + fun - fprev);
     }
   }
   else {
     const int k = 2 * pick3(c.kaxis, ia, ib, ic) + c.koff;
-    const T kap = __ldg(c.kap + k), sig = __ldg(c.sig + k), siginv = __ldg(c.siginv + k);
+    const T kap = __ldg(c.kap + k), sig = __ldg(c.sig + k);
+    siginv = __ldg(c.siginv + k);
     if (c.kuaxis < 0) {
       if (cond) {
         const T fcnd_prev = v.fcnd;
-        const T fc = ((1 - c.dt2 * v.cnd) * fcnd_prev - c.dtdx * curl) * v.cndinv;
-        c.fcnd[i] = fc;
+        fc = ((1 - c.dt2 * v.cnd) * fcnd_prev - c.dtdx * curl) * v.cndinv;
         fnew = ((kap - sig) * fold + (fc - fcnd_prev)) * siginv;
       }
       else
@@ -399,19 +407,73 @@ __device__ __forceinline__ void finish_point(const CompParams<T> &c, const PolPa
     else {
       const int ku = 2 * pick3(c.kuaxis, ia, ib, ic) + c.kuoff;
       const T fprev = v.fu;
-      T fun;
       if (cond) {
         const T fcnd_prev = v.fcnd;
-        const T fc = ((1 - c.dt2 * v.cnd) * fcnd_prev - c.dtdx * curl) * v.cndinv;
-        c.fcnd[i] = fc;
+        fc = ((1 - c.dt2 * v.cnd) * fcnd_prev - c.dtdx * curl) * v.cndinv;
         fun = ((kap - sig) * fprev + (fc - fcnd_prev)) * siginv;
       }
       else
         fun = ((kap - sig) * fprev - c.dtdx * curl) * siginv;
-      c.fu[i] = fun;
-      fnew = __ldg(c.siginvu + ku) * ((__ldg(c.kapu + ku) - __ldg(c.sigu + ku)) * fold + fun - fprev);
+      siginvu = __ldg(c.siginvu + ku);
+      fnew = siginvu * ((__ldg(c.kapu + ku) - __ldg(c.sigu + ku)) * fold + fun - fprev);
     }
   }
+  // ---------------- step_bfast (step_generic.cpp:339-537) and step_beta (:259-337): both add an
+  // increment to f through the same PML / conductivity chain, bfast right after the curl of the
+  // component (step_db.cpp:129-143), beta after all curls (step_db.cpp:161-175) ----------------------
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 0 ? !c.fb : !c.gb) continue;
+    T bg;
+    if (pass == 0) {
+      const T F_prev = v.fb;
+      T Fn;
+      if (c.g2) Fn = (c.bk1 * (v.g1p + v.g1) - c.bk2 * (v.g2p + v.g2)) - F_prev;
+      else if (c.kaxis < 0 && c.kuaxis < 0 && !cond) Fn = c.bk1 * (v.g1p + v.g1); // :376, as written in the reference
+      else Fn = c.bk1 * (v.g1p + v.g1) - F_prev;
+      c.fb[i] = Fn;
+      bg = Fn - F_prev;
+    }
+    else
+      bg = c.betadt * v.gb;
+    if (c.kaxis >= 0) {
+      if (c.kuaxis >= 0) {
+        T df;
+        if (cond) {
+          const T dfcnd = bg * v.cndinv;
+          fc = fc + dfcnd;
+          fun = fun + (df = dfcnd * siginv);
+        }
+        else
+          fun = fun + (df = bg * siginv);
+        fnew = fnew + siginvu * df;
+      }
+      else {
+        if (cond) {
+          const T dfcnd = bg * v.cndinv;
+          fc = fc + dfcnd;
+          fnew = fnew + dfcnd * siginv;
+        }
+        else
+          fnew = fnew + bg * siginv;
+      }
+    }
+    else {
+      if (c.kuaxis >= 0) {
+        T df;
+        if (cond) df = bg * v.cndinv;
+        else df = bg;
+        fun = fun + df;
+        fnew = fnew + siginvu * df;
+      }
+      else {
+        if (cond) fnew = fnew + bg * v.cndinv;
+        else fnew = fnew + bg;
+      }
+    }
+  }
+  if (c.kuaxis >= 0) c.fu[i] = fun;
+  if (cond && c.kaxis >= 0) c.fcnd[i] = fc;
   // ---------------- step_source (step.cpp:296-319) ----------------
   if (c.ncsrc && ia >= c.csrc_amin && ia <= c.csrc_amax) {
     for (int j = src_lower_bound(c.csrc, c.ncsrc, i); j < c.ncsrc && c.csrc[j].idx == i; ++j) {
@@ -483,7 +545,7 @@ template <class T> struct HalfHeader { // leading, component-independent part of
 };
 
 template <class T, bool HAS_COND, bool HAS_POL, bool PIPE = false>
-__global__ void __launch_bounds__(kThreads, PIPE ? 2 : 3)
+__global__ void __launch_bounds__(kThreads, (PIPE || HAS_COND) ? 2 : 3)
     k_halfg(const HalfParams<T> *__restrict__ params, const Tile *__restrict__ tiles,
             const double *__restrict__ smp) {
   __shared__ HalfHeader<T> H;

@@ -950,8 +950,8 @@ template <class T> struct Ctx : CtxBase {
     CU(cudaEventCreate(&ev1));
     CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-    if (cfg.dim == MEEPCU_D2 && cfg.beta != 0)
-      return fail(MEEPCU_EUNSUPPORTED, "beta != 0 (step_beta) is not on the GPU path yet");
+    if (cfg.dim != MEEPCU_D2 && cfg.beta != 0)
+      return fail(MEEPCU_EINVAL, "Nonzero beta unsupported in dimensions other than 2."); // fields.cpp:559-560
 
     // ---- 1. register every array ----
     for (size_t ic = 0; ic < chunks.size(); ++ic) {
@@ -964,6 +964,7 @@ template <class T> struct Ctx : CtxBase {
           RC(reg(ch.d.f_u[c][cmp], (int)ic, A_GRID, nh, nd, true));
           RC(reg(ch.d.f_w[c][cmp], (int)ic, A_GRID, nh, nd, true));
           RC(reg(ch.d.f_cond[c][cmp], (int)ic, A_GRID, nh, nd, true));
+          RC(reg(ch.d.f_bfast[c][cmp], (int)ic, A_GRID, nh, nd, true));
         }
         for (int d = 0; d < 5; ++d) {
           RC(reg(ch.d.chi1inv[c][d], (int)ic, A_GRID, nh, nd, false));
@@ -1199,6 +1200,26 @@ template <class T> struct Ctx : CtxBase {
             c.csrc = d_src + R.c0; c.ncsrc = (int)(R.c1 - R.c0); c.csrc_amin = R.ca0; c.csrc_amax = R.ca1;
             c.src_has_cndinv = c.cndinv != 0;
             if (dsig || dsigu || c.cnd) simple = false;
+            if (cfg.bfast_scaled_k[0] || cfg.bfast_scaled_k[1] || cfg.bfast_scaled_k[2]) { // step_db.cpp:129-143
+              c.fb = dev(ch.d.f_bfast[cc][cmp]);
+              if (!c.fb) return fail(MEEPCU_ESTATE, "f_bfast not allocated (step_db.cpp:76-79)");
+              T k1 = have_m ? (T)cfg.bfast_scaled_k[comp_dir(ch.minus_c[cc])] : (T)0; // puts k1 in direction of g2
+              T k2 = have_p ? (T)cfg.bfast_scaled_k[comp_dir(ch.plus_c[cc])] : (T)0;  // puts k2 in direction of g1
+              if (half) { k1 = -k1; k2 = -k2; }
+              if (!have_p || !dev(ch.d.f[ch.plus_c[cc]][cmp])) std::swap(k1, k2); // step_generic.cpp:346-350
+              c.bk1 = k1;
+              c.bk2 = k2;
+              simple = false;
+            }
+            if (cfg.dim == MEEPCU_D2 && cfg.beta != 0 && k <= 1) { // step_db.cpp:161-175
+              const int c_g = dir_comp(half ? MEEPCU_H_STUFF : MEEPCU_E_STUFF, k == 0 ? 1 : 0);
+              const void *g_other = ch.d.f[c_g][1 - cmp];
+              c.gb = dev(g_other ? g_other : ch.d.f[c_g][cmp]);
+              const double pi = 3.141592653589793238462643383276; // src/meep.hpp:53
+              c.betadt = (T)(2 * pi * cfg.beta * cfg.dt * (k == 0 ? +1 : -1) *
+                             (g_other ? (half ? -1 : +1) * (2 * cmp - 1) : 1));
+              if (c.gb) simple = false;
+            }
 
             // ---- E/H part ----
             if (!ch.d.f[ec][cmp]) continue;
@@ -1321,7 +1342,9 @@ template <class T> struct Ctx : CtxBase {
             if (getenv("MEEPCU_GSEG")) gseg = std::max(1, atoi(getenv("MEEPCU_GSEG")));
             const int V = (int)(16 / sizeof(T));
             const bool vec_ok = !getenv("MEEPCU_NO_VEC") && g.pitch % V == 0 && heavy < 2 &&
-                                (sizeof(T) == 4 || getenv("MEEPCU_GVEC64"));
+                                (sizeof(T) == 4 || getenv("MEEPCU_GVEC64")) &&
+                                !(cfg.dim == MEEPCU_D2 && cfg.beta != 0) && // the beta and BFAST terms live in
+                                !(cfg.bfast_scaled_k[0] || cfg.bfast_scaled_k[1] || cfg.bfast_scaled_k[2]); // the scalar kernel
             const int span = vec_ok ? kThreads * V : kThreads;
             const long long s_mq = P.march ? (long long)g.pitch : (long long)g.pitch * g.nax[1];
             const long long s_oq = P.march ? (long long)g.pitch * g.nax[1] : (long long)g.pitch;

@@ -311,7 +311,7 @@ def slab_decomposition(gv, nranks, d=0):
 class fields_chunk:
     def __init__(self, sc, is_real):
         self.s, self.gv = sc, sc.gv
-        self.f, self.f_u, self.f_w, self.f_cond = {}, {}, {}, {}
+        self.f, self.f_u, self.f_w, self.f_cond, self.f_bfast = {}, {}, {}, {}, {}
         self.pol_data = []   # per susceptibility: {"P": {(c,cmp): arr}, "P_prev": {...}}
         self.sources = []    # dicts
         self.dfts = []
@@ -334,6 +334,8 @@ class fields:
         self.is_real = 0
         self.t = 0
         self.nl_mode, self.device = nl_mode, device
+        self.bfast_scaled_k = [0.0, 0.0, 0.0]  # fields::bfast_scaled_k (step_db.cpp:65,129-143)
+        self.beta = 0.0  # fields::beta: 2-D exp(i beta z) dependence (step_db.cpp:148-175)
         self.pin_host = True  # the numpy arrays below outlive the context: sync by plain DMA (meepcu_config::pin_host)
         self.boundaries = {d: Metallic for d in range(3)}
         self.k = {d: 0.0 for d in range(3)}
@@ -406,6 +408,7 @@ class fields:
                     d = comp_dir(c)
                     if is_D(c) or is_B(c):  # step_db.cpp:56-75
                         if sc.sigsize[(d + 2) % 3] > 1: fc.f_u[(c, cmp)] = zeros(n, rt)
+                        if any(self.bfast_scaled_k): fc.f_bfast[(c, cmp)] = zeros(n, rt)  # step_db.cpp:76-79
                     else:                    # update_eh.cpp:199-216
                         if sc.sigsize[d] > 1: fc.f_w[(c, cmp)] = zeros(n, rt)
             for (sus, ft, arrs) in sc.pols:
@@ -608,9 +611,10 @@ class fields:
         cfg.is_real = self.is_real
         cfg.dim = self.gv.dim
         cfg.a, cfg.dt, cfg.courant = self.a, self.dt, self.s.Courant
-        cfg.beta = 0.0
+        cfg.beta = self.beta if self.gv.dim == D2 else 0.0
         cfg.nl_mode, cfg.device, cfg.t = self.nl_mode, self.device, self.t
         cfg.pin_host = 1 if self.pin_host else 0
+        for k in range(3): cfg.bfast_scaled_k[k] = float(self.bfast_scaled_k[k])
         ctx = A.vp()
         b.check(b.create(C.byref(cfg), C.byref(ctx)))
         self.ctx = ctx
@@ -630,6 +634,7 @@ class fields:
                 d.num[k], d.io[k] = gv.num[k], gv.io[k]
             for (c, cmp), arr in fc.f.items(): d.f[c][cmp] = self._ptr(arr)
             for (c, cmp), arr in fc.f_u.items(): d.f_u[c][cmp] = self._ptr(arr)
+            for (c, cmp), arr in fc.f_bfast.items(): d.f_bfast[c][cmp] = self._ptr(arr)
             for (c, cmp), arr in fc.f_w.items(): d.f_w[c][cmp] = self._ptr(arr)
             for (c, dd), arr in sc.chi1inv.items(): d.chi1inv[c][dd] = self._ptr(arr)
             for c, arr in sc.chi2.items(): d.chi2[c] = self._ptr(arr)
@@ -776,7 +781,7 @@ class fields:
         seen = set()
         for fc in self.chunks:
             if not fc.mine: continue
-            groups = [fc.f, fc.f_u, fc.f_w]
+            groups = [fc.f, fc.f_u, fc.f_w, fc.f_bfast]
             for g in groups:
                 for arr in g.values():
                     if id(arr) in seen: continue

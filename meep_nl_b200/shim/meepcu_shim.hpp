@@ -200,6 +200,12 @@ public:
             fc->f_u[cc][cmp] = new realnum[ntot];
             memcpy(fc->f_u[cc][cmp], fc->f[cc][cmp], ntot * sizeof(realnum));
           }
+          const bool use_bfast = fc->bfast_scaled_k.size() >= 3 && // step_db.cpp:65,76-79
+                                 (fc->bfast_scaled_k[0] || fc->bfast_scaled_k[1] || fc->bfast_scaled_k[2]);
+          if (use_bfast && !fc->f_bfast[cc][cmp]) {
+            fc->f_bfast[cc][cmp] = new realnum[ntot];
+            memset(fc->f_bfast[cc][cmp], 0, sizeof(realnum) * ntot);
+          }
         }
       }
       field_type ehs[2] = {H_stuff, E_stuff};
@@ -265,8 +271,6 @@ private:
   void describe(int nl_mode, int device) {
     using namespace meep;
     if (f.gv.dim == Dcyl) meep::abort("meepcu: cylindrical coordinates are outside the GPU path");
-    if (f.bfast_scaled_k[0] || f.bfast_scaled_k[1] || f.bfast_scaled_k[2])
-      meep::abort("meepcu: BFAST is outside the GPU path");
     if (f.is_phasing()) meep::abort("meepcu: phase_material is outside the GPU path");
     for (int i = 0; i < f.num_chunks; i++)
       if (!f.chunks[i]->is_mine())
@@ -283,6 +287,7 @@ private:
     cfg.dt = f.dt;
     cfg.courant = f.num_chunks ? f.chunks[0]->Courant : f.dt * f.a;
     cfg.beta = f.beta;
+    for (int k = 0; k < 3 && k < (int)f.bfast_scaled_k.size(); ++k) cfg.bfast_scaled_k[k] = f.bfast_scaled_k[k];
     cfg.nl_mode = nl_mode;
     cfg.device = device;
     cfg.t = f.t;
@@ -313,6 +318,7 @@ private:
           d.f_u[c][cmp] = fc->f_u[c][cmp];
           d.f_w[c][cmp] = fc->f_w[c][cmp];
           d.f_cond[c][cmp] = fc->f_cond[c][cmp];
+          d.f_bfast[c][cmp] = fc->f_bfast[c][cmp];
         }
         for (int dd = 0; dd < 5; ++dd) {
           d.chi1inv[c][dd] = s->chi1inv[c][dd];

@@ -83,6 +83,7 @@ inline bool is_magnetic(int c) { return c >= Hx && c < Dx; }
 inline bool is_D(int c) { return c >= Dx && c < Bx; }
 inline bool is_B(int c) { return c >= Bx && c < 20; }
 inline int comp_type(int c) { return is_electric(c) ? 0 : is_magnetic(c) ? 1 : is_D(c) ? 2 : 3; }
+static const double kPi = 3.141592653589793238462643383276; // src/meep.hpp:53
 inline int first_comp(int ft) { return 5 * ft; } // E,H,D,B -> Ex,Hx,Dx,Bx
 inline int comp_dir(int c) {                     // component_direction
   static const int d[5] = {MEEPCU_X, MEEPCU_Y, MEEPCU_R, MEEPCU_P, MEEPCU_Z};
@@ -516,11 +517,177 @@ template <class T> struct Impl : CtxBase {
                     (const T *)ch.d.siginv[dsig], dsigu != MEEPCU_NO_DIRECTION ? fu : NULL, dsigu,
                     (const T *)ch.d.sig[dsigu], (const T *)ch.d.kap[dsigu],
                     (const T *)ch.d.siginv[dsigu], (T)cfg.dt, cnd, cndinv, fcnd);
+          if (cfg.bfast_scaled_k[0] || cfg.bfast_scaled_k[1] || cfg.bfast_scaled_k[2]) { // step_db.cpp:129-143
+            T *F = (T *)ch.d.f_bfast[cc][cmp];
+            if (!F) return fail(MEEPCU_ESTATE, "f_bfast not allocated (step_db.cpp:76-79)");
+            T k1 = have_m ? (T)cfg.bfast_scaled_k[comp_dir(ch.minus_c[cc])] : 0; // puts k1 in direction of g2
+            T k2 = have_p ? (T)cfg.bfast_scaled_k[comp_dir(ch.plus_c[cc])] : 0;  // puts k2 in direction of g1
+            if (ft == MEEPCU_D_STUFF) {
+              k1 = -k1;
+              k2 = -k2;
+            }
+            step_bfast(ch.F(cc, cmp), f_p, f_m, stride_p, stride_m, g, is, ie, dsig, (const T *)ch.d.siginv[dsig],
+                       dsigu != MEEPCU_NO_DIRECTION ? fu : NULL, dsigu, (const T *)ch.d.siginv[dsigu], cnd, cndinv,
+                       fcnd, F, k1, k2);
+          }
         }
     }
+    // In 2d with beta != 0, add the beta terms (src/step_db.cpp:148-175): after the curl loops of
+    // every component of the chunk, f += betadt * g with the PML / conductivity variants of step_beta.
     if (cfg.dim == MEEPCU_D2 && cfg.beta != 0)
-      return fail(MEEPCU_EUNSUPPORTED, "beta != 0 (step_beta) not restated in the oracle yet");
+      for (size_t ic = 0; ic < chunks.size(); ++ic) {
+        Chunk<T> &ch = chunks[ic];
+        const Grid &g = ch.g;
+        for (int cmp = 0; cmp < (cfg.is_real ? 1 : 2); ++cmp)
+          for (int d_c = MEEPCU_X; d_c <= MEEPCU_Y; ++d_c) {
+            const int cc = dir_comp(first_comp(ft), d_c);
+            const int c_g = dir_comp(ft == MEEPCU_D_STUFF ? MEEPCU_Hx : MEEPCU_Ex, d_c == MEEPCU_X ? MEEPCU_Y : MEEPCU_X);
+            T *the_f = ch.F(cc, cmp);
+            const T *gg = ch.F(c_g, 1 - cmp) ? ch.F(c_g, 1 - cmp) : ch.F(c_g, cmp);
+            if (!the_f) continue; // the reference would dereference NULL
+            const int dsig0 = cycle_dir(d_c, 1);
+            const int dsig = ch.d.sigsize[dsig0] > 1 ? dsig0 : MEEPCU_NO_DIRECTION;
+            const int dsigu0 = cycle_dir(d_c, 2);
+            const int dsigu = ch.d.sigsize[dsigu0] > 1 ? dsigu0 : MEEPCU_NO_DIRECTION;
+            const T betadt = (T)(2 * kPi * cfg.beta * cfg.dt * (d_c == MEEPCU_X ? +1 : -1) *
+                                 (ch.F(c_g, 1 - cmp) ? (ft == MEEPCU_D_STUFF ? -1 : +1) * (2 * cmp - 1) : 1));
+            int is[3], ie[3];
+            for (int d = 0; d < 3; ++d) {
+              is[d] = g.io[d] + 2 - g.yee_shift(cc, d);
+              ie[d] = g.io[d] + 2 * g.num[d];
+            }
+            step_beta(the_f, gg, g, is, ie, betadt, dsig, (const T *)ch.d.siginv[dsig], (T *)ch.d.f_u[cc][cmp],
+                      dsigu, (const T *)ch.d.siginv[dsigu], (const T *)ch.d.condinv[cc][d_c],
+                      (T *)ch.d.f_cond[cc][cmp]);
+          }
+      }
     return MEEPCU_OK;
+  }
+
+  // step_bfast, src/step_generic.cpp:339-537: F = k1 (g1[i+s1] + g1[i]) - k2 (g2[i+s2] + g2[i]) - F, then
+  // f (f_u, f_cond) += the change of F through the same PML / conductivity chain as step_beta.
+  // (One of the reference's 16 loops -- no PML, no f_u, no conductivity, no g2, :372-378 -- omits the
+  // trailing "- F[i]"; restated as written.)
+  void step_bfast(T *f, const T *g1, const T *g2, ptrdiff_t s1, ptrdiff_t s2, const Grid &g, const int is[3],
+                  const int ie[3], int dsig, const T *siginv, T *fu, int dsigu, const T *siginvu, const T *cnd,
+                  const T *cndinv, T *fcnd, T *F, T k1, T k2) {
+    if (!g1) { // :346-350
+      std::swap(g1, g2);
+      std::swap(s1, s2);
+      std::swap(k1, k2);
+    }
+    Loop L(g, is, ie);
+    KIdx K, KU;
+    if (dsig != MEEPCU_NO_DIRECTION) K = KIdx(g, dsig, is);
+    if (dsigu != MEEPCU_NO_DIRECTION) KU = KIdx(g, dsigu, is);
+    const bool plain = dsig == MEEPCU_NO_DIRECTION && dsigu == MEEPCU_NO_DIRECTION && !cnd && !g2;
+#pragma omp parallel for collapse(2)
+    OLOOP(L, i) {
+      const T F_prev = F[i];
+      if (g2)
+        F[i] = (k1 * (g1[i + s1] + g1[i]) - k2 * (g2[i + s2] + g2[i])) - F[i];
+      else if (plain)
+        F[i] = k1 * (g1[i + s1] + g1[i]); // :376, as written in the reference
+      else
+        F[i] = k1 * (g1[i + s1] + g1[i]) - F[i];
+      const T dF = F[i] - F_prev;
+      if (dsig == MEEPCU_NO_DIRECTION) {
+        if (dsigu == MEEPCU_NO_DIRECTION) {
+          if (cnd) f[i] += dF * cndinv[i];
+          else f[i] += dF;
+        }
+        else {
+          const int ku = KU.at(loop_i1, loop_i2, loop_i3);
+          T df;
+          if (cnd) fu[i] += (df = dF * cndinv[i]);
+          else fu[i] += (df = dF);
+          f[i] += siginvu[ku] * df;
+        }
+      }
+      else {
+        const int k = K.at(loop_i1, loop_i2, loop_i3);
+        if (dsigu == MEEPCU_NO_DIRECTION) {
+          if (cnd) {
+            T dfcnd = dF * cndinv[i];
+            fcnd[i] += dfcnd;
+            f[i] += dfcnd * siginv[k];
+          }
+          else
+            f[i] += dF * siginv[k];
+        }
+        else {
+          const int ku = KU.at(loop_i1, loop_i2, loop_i3);
+          T df;
+          if (cnd) {
+            T dfcnd = dF * cndinv[i];
+            fcnd[i] += dfcnd;
+            fu[i] += (df = dfcnd * siginv[k]);
+          }
+          else
+            fu[i] += (df = dF * siginv[k]);
+          f[i] += siginvu[ku] * df;
+        }
+      }
+    }
+  }
+
+  // step_beta, src/step_generic.cpp:259-337: f += betadt * g and its PML / conductivity variants
+  void step_beta(T *f, const T *gg, const Grid &g, const int is[3], const int ie[3], T betadt, int dsig,
+                 const T *siginv, T *fu, int dsigu, const T *siginvu, const T *cndinv, T *fcnd) {
+    if (!gg) return;
+    Loop L(g, is, ie);
+    KIdx K, KU;
+    if (dsig != MEEPCU_NO_DIRECTION) K = KIdx(g, dsig, is);
+    if (dsigu != MEEPCU_NO_DIRECTION) KU = KIdx(g, dsigu, is);
+#pragma omp parallel for collapse(2)
+    OLOOP(L, i) {
+      if (dsig != MEEPCU_NO_DIRECTION) {
+        const int k = K.at(loop_i1, loop_i2, loop_i3);
+        if (dsigu != MEEPCU_NO_DIRECTION) {
+          const int ku = KU.at(loop_i1, loop_i2, loop_i3);
+          T df;
+          if (cndinv) { // :271-279
+            T dfcnd = betadt * gg[i] * cndinv[i];
+            fcnd[i] += dfcnd;
+            fu[i] += (df = dfcnd * siginv[k]);
+            f[i] += siginvu[ku] * df;
+          }
+          else { // :283-289
+            fu[i] += (df = betadt * gg[i] * siginv[k]);
+            f[i] += siginvu[ku] * df;
+          }
+        }
+        else {
+          if (cndinv) { // :294-299
+            T dfcnd = betadt * gg[i] * cndinv[i];
+            fcnd[i] += dfcnd;
+            f[i] += dfcnd * siginv[k];
+          }
+          else // :302-305
+            f[i] += betadt * gg[i] * siginv[k];
+        }
+      }
+      else {
+        if (dsigu != MEEPCU_NO_DIRECTION) {
+          const int ku = KU.at(loop_i1, loop_i2, loop_i3);
+          T df;
+          if (cndinv) { // :313-318
+            fu[i] += (df = betadt * gg[i] * cndinv[i]);
+            f[i] += siginvu[ku] * df;
+          }
+          else { // :321-326
+            fu[i] += (df = betadt * gg[i]);
+            f[i] += siginvu[ku] * df;
+          }
+        }
+        else {
+          if (cndinv) // :331
+            f[i] += betadt * gg[i] * cndinv[i];
+          else // :334
+            f[i] += betadt * gg[i];
+        }
+      }
+    }
   }
 
   // fields_chunk::step_source, src/step.cpp:296-319

@@ -42,6 +42,9 @@ static double rods(const vec &r) { // tests/known_results.cpp:29-41
   return 1.0;
 }
 static double sigma763(const vec &) { return 7.63; }
+static double wvg_eps_small(const vec &p) { return fabs(p.y() - 2.0) < 0.5 ? 6.0 : 1.0; }
+static double slab_eps_y(const vec &p) { return (p.y() > g_slab_lo && p.y() < g_slab_hi) ? g_slab_eps : 1.0; }
+static double cond_fn(const vec &p) { return 0.3 + 0.2 * p.x(); }
 static double slab_eps_z(const vec &p) { return (p.z() > g_slab_lo && p.z() < g_slab_hi) ? g_slab_eps : 1.0; }
 static double ring_eps(const vec &p);
 static double ring_sigma(const vec &p);
@@ -163,6 +166,46 @@ static problem *build(const std::string &spec, int nchunks) {
     p->f->use_real_fields();
     gaussian_src_time src(0.15, 0.1);
     p->f->add_point_source(Ez, src, vec(1.0, 4.0));
+  }
+  else if (name == "beta2d" || name == "beta2d_cplx") { // 2D with exp(i beta z): step_beta (step_db.cpp:148-175)
+    p->gv = vol2d(n ? n / a : 6.0, n ? 0.75 * n / a : 4.0, a);
+    p->s = new structure(p->gv, wvg_eps_small, pml(0.8), identity(), nchunks, 0.5, false);
+    p->f = new fields(p->s, 0, param != 0 ? param : 0.35);
+    if (name == "beta2d") p->f->use_real_fields();
+    p->f->add_point_source(Ez, 0.3, 0.2, 0.0, 4.0, p->gv.center() + vec(-0.3, 0.1), 1.0);
+    p->f->add_point_source(Hz, 0.25, 0.2, 0.0, 4.0, p->gv.center() + vec(0.4, -0.2), 0.8);
+  }
+  else if (name == "bfast3d" || name == "bfast2d") { // BFAST terms (step_db.cpp:129-143, step_bfast)
+    if (!n) n = 14;
+    const bool d3 = name == "bfast3d";
+    p->gv = d3 ? vol3d(n / a, n / a, 1.5 * n / a, a) : vol2d(n / a, 1.5 * n / a, a);
+    g_slab_lo = 0.75 * n / a - 0.25;
+    g_slab_hi = 0.75 * n / a + 0.25;
+    g_slab_eps = 4.0;
+    p->s = new structure(p->gv, d3 ? slab_eps_z : slab_eps_y, pml(0.4, d3 ? Z : Y), identity(), nchunks, 0.25, false);
+    std::vector<double> bk = {param != 0 ? param : 0.2, d3 ? 0.1 : 0.0, 0.0};
+    p->f = new fields(p->s, 0, 0, true, 0, 0, bk);
+    p->f->use_bloch(X, 0.0);
+    if (d3) p->f->use_bloch(Y, 0.0);
+    p->f->add_point_source(d3 ? Ey : Ez, 0.25, 0.2, 0.0, 4.0, p->gv.center(), 1.0);
+    p->f->add_point_source(Hx, 0.3, 0.2, 0.0, 4.0, p->gv.center(), 0.6);
+  }
+  else if (name == "cond3d" || name == "cond2d") { // conductivity + PML: f_cond paths of step_curl
+    if (!n) n = 14;
+    const bool d3 = name == "cond3d";
+    p->gv = d3 ? vol3d(n / a, n / a, n / a, a) : vol2d(n / a, n / a, a);
+    g_slab_lo = 0.3 * n / a;
+    g_slab_hi = 0.7 * n / a;
+    g_slab_eps = 3.0;
+    p->s = new structure(p->gv, d3 ? slab_eps_z : slab_eps_y, pml(0.4), identity(), nchunks, 0.5, false);
+    p->s->set_conductivity(Dx, cond_fn);
+    p->s->set_conductivity(Dy, cond_fn);
+    p->s->set_conductivity(Dz, cond_fn);
+    p->s->set_conductivity(By, cond_fn);
+    p->f = new fields(p->s);
+    p->f->use_real_fields();
+    p->f->add_point_source(Ez, 0.25, 0.2, 0.0, 4.0, p->gv.center(), 1.0);
+    p->f->add_point_source(d3 ? Ex : Hz, 0.3, 0.2, 0.0, 4.0, p->gv.center(), 0.6);
   }
   else if (name == "nr3d") { // BASELINE config 3a, fork Newton-Raphson chi2
     if (!n) n = 16;
@@ -332,6 +375,10 @@ static std::vector<marray> collect(fields &f) {
       if (fc->f_cond[c][cmp]) {
         snprintf(nm, sizeof nm, "chunk%d.f_cond[%s][%d]", i, component_name(c), cmp);
         out.push_back({fc->f_cond[c][cmp], nb, nm});
+      }
+      if (fc->f_bfast[c][cmp]) {
+        snprintf(nm, sizeof nm, "chunk%d.f_bfast[%s][%d]", i, component_name(c), cmp);
+        out.push_back({fc->f_bfast[c][cmp], nb, nm});
       }
     }
     field_type ehs[2] = {E_stuff, H_stuff};

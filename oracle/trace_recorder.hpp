@@ -57,6 +57,8 @@ public:
     for (int k = 0; k < 6; ++k) ids.push_back(k < 5 ? reg(d.sig[k], d.sigsize[k], rb) : -1);
     for (int k = 0; k < 6; ++k) ids.push_back(k < 5 ? reg(d.kap[k], d.sigsize[k], rb) : -1);
     for (int k = 0; k < 6; ++k) ids.push_back(k < 5 ? reg(d.siginv[k], d.sigsize[k], rb) : -1);
+    for (int c = 0; c < 20; ++c) // ABI 2: appended, older readers stop before it
+      for (int k = 0; k < 2; ++k) ids.push_back(reg(d.f_bfast[c][k], ntot, rb));
     begin(T_CHUNK);
     put32(i);
     put(d.num, sizeof d.num);

@@ -36,6 +36,12 @@ for fl in fp64 fp32; do
   gen $fl lorentz3d:16 40 2
   gen $fl kerr3d:12 30 2
   gen $fl kerr1d 60 0
+  gen $fl beta2d 40 2
+  gen $fl bfast3d:10 40 2
+  gen $fl bfast2d 40 2
+  gen $fl cond3d:10 40 2
+  gen $fl cond2d 40 2
+  gen $fl beta2d_cplx 40 2
 done
 gen fp64 nr3d:10 30 0
 gen fp64 nrslab3d:14 30 2

@@ -30,11 +30,11 @@ def test_library_exports_every_symbol(path):
 
 def test_struct_sizes_match_c():
     # sizes computed by the C compiler for include/meepcu.h (x86-64 SysV)
-    assert C.sizeof(A.Config) == 88
+    assert C.sizeof(A.Config) == 112  # ABI 2: + bfast_scaled_k[3]
     assert C.sizeof(A.SrcSample) == 64
     assert C.sizeof(A.SourceDesc) == 40
     assert C.sizeof(A.KernelTime) == 72
-    assert C.sizeof(A.ChunkDesc) == 24 + 8 * (4 * 40 + 100 + 20 + 20 + 100 + 100 + 18) + 24 + 32
+    assert C.sizeof(A.ChunkDesc) == 24 + 8 * (4 * 40 + 100 + 20 + 20 + 100 + 100 + 18) + 24 + 32 + 8 * 40 == 4544  # ABI 2: + f_bfast
 
 
 def test_bad_arguments_are_reported(oracle_backend, cuda_backend):
@@ -60,7 +60,7 @@ def test_cuda_library_has_no_cpu_fallback(cuda_backend):
         "import sys, ctypes as C; sys.path.insert(0, %r)\n"
         "from meep_nl_b200 import _cabi as A\n"
         "b = A.Backend(%r)\n"
-        "cfg = A.Config(); cfg.abi_version = 1; cfg.realnum_bytes = 8; cfg.dim = A.D3; cfg.a = 10; cfg.dt = .05; cfg.courant = .5\n"
+        "cfg = A.Config(); cfg.abi_version = A.ABI_VERSION; cfg.realnum_bytes = 8; cfg.dim = A.D3; cfg.a = 10; cfg.dt = .05; cfg.courant = .5\n"
         "ctx = A.vp(); assert b.create(C.byref(cfg), C.byref(ctx)) == 0\n"
         "rc = b.finalize(ctx); print(rc, b.lib.meepcu_last_error().decode())\n" % (ROOT, CUDA_LIB))
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")

@@ -97,3 +97,82 @@ def test_cuda_full_size_properties(cuda_backend):
         assert far == 0.0
         f.close()
     assert np.max(np.abs(outs[0])) > 0 and outs[0] == outs[1]
+
+
+def beta2d(backend, rt=np.float64, split=None, beta=0.35):
+    """2-D cell with an exp(i beta z) dependence (fields::beta, step_db.cpp:148-175): TE and TM couple"""
+    gv = H.vol2d(4.8, 3.2, 10)
+    s = H.structure(gv, lambda x, y, z: 1.0 + 4.0 * (np.abs(y - 1.6) < 0.4), pml=0.6, realnum=rt, split=split)
+    f = H.fields(s, backend)
+    f.beta = beta
+    f.use_real_fields()
+    f.add_point_source(Ez, 0.3, 0.2, 0.0, 4.0, (2.1, 1.7, 0.0), 1.0)
+    return gv, f
+
+
+def test_beta_couples_te_and_tm_and_is_chunk_invariant(oracle_backend):
+    outs = []
+    for split, beta in ((None, 0.35), ({0: [17, 30]}, 0.35), (None, 0.0)):
+        gv, f = beta2d(oracle_backend, split=split, beta=beta)
+        f.step(60)
+        outs.append([f.get_field(Ez, (0.8 + 0.1 * k, 1.7, 0.0)) for k in range(30)] +
+                    [f.get_field(Hy, (0.85 + 0.1 * k, 1.7, 0.0)) for k in range(30)] +
+                    [f.get_field(Ex, (0.85 + 0.1 * k, 1.7, 0.0)) for k in range(30)])
+        f.close()
+    assert outs[0] == outs[1]                      # split == unsplit, bit for bit
+    assert np.max(np.abs(outs[0][60:])) > 0        # an Ez source drives Ex only through beta
+    assert np.max(np.abs(outs[2][60:])) == 0
+    assert outs[0][:30] != outs[2][:30]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rt,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
+def test_cuda_vs_oracle_beta2d(cuda_backend, oracle_backend, rt, tol):
+    res = []
+    for b in (cuda_backend, oracle_backend):
+        gv, f = beta2d(b, rt)
+        f.step(120)
+        f.sync_to_host()
+        res.append(np.concatenate([fc.f[(c, 0)] for fc in f.chunks for c in (Ez, Ex, Hy)]).astype(np.float64))
+        f.close()
+    rel = np.linalg.norm(res[0] - res[1]) / np.linalg.norm(res[1])
+    assert np.linalg.norm(res[1]) > 0 and rel <= tol
+
+
+def bfast3d(backend, rt=np.float64, split=None):
+    """BFAST terms (fields::bfast_scaled_k, step_db.cpp:129-143): periodic x,y, PML in z, complex fields"""
+    gv = H.vol3d(2.0, 1.6, 3.0, 10)
+    s = H.structure(gv, lambda x, y, z: 1.0 + 3.0 * (np.abs(z - 1.5) < 0.3), pml=0.5, pml_dirs=[2], realnum=rt,
+                    courant=0.25, split=split)
+    f = H.fields(s, backend)
+    f.bfast_scaled_k = [0.2, 0.1, 0.0]
+    f.use_bloch(0, 0.0)
+    f.use_bloch(1, 0.0)
+    f.add_point_source(Ey, 0.25, 0.2, 0.0, 4.0, gv.center(), 1.0)
+    return gv, f
+
+
+def test_bfast_is_chunk_invariant(oracle_backend):
+    outs = []
+    for split in (None, {0: [7], 2: [12, 19]}):
+        gv, f = bfast3d(oracle_backend, split=split)
+        f.step(40)
+        c = gv.center()
+        outs.append([f.get_field(Ey, (0.1 * k, c[1] + 0.05, c[2]), cmp) for k in range(1, 20) for cmp in (0, 1)])
+        f.close()
+    assert np.max(np.abs(outs[0])) > 0 and outs[0] == outs[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rt,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
+def test_cuda_vs_oracle_bfast3d(cuda_backend, oracle_backend, rt, tol):
+    res = []
+    for b in (cuda_backend, oracle_backend):
+        gv, f = bfast3d(b, rt)
+        f.step(80)
+        f.sync_to_host()
+        res.append(np.concatenate([fc.f[(c, cmp)] for fc in f.chunks for c in (Ey, Ex, Hy) for cmp in (0, 1)] +
+                                  [a for fc in f.chunks for a in fc.f_bfast.values()]).astype(np.float64))
+        f.close()
+    rel = np.linalg.norm(res[0] - res[1]) / np.linalg.norm(res[1])
+    assert np.linalg.norm(res[1]) > 0 and rel <= tol

@@ -14,6 +14,11 @@ from conftest import ORACLE_LIB, ref_driver
 CASES = [("fp64", "vac3d:24", 25, 2), ("fp64", "kr_per3d_rods", 40, 0), ("fp64", "nr3d:10", 25, 0),
          ("fp64", "lorentz3d:16", 30, 1), ("fp64", "wvg2d", 60, 3), ("fp32", "vac3d_cplx:14", 25, 2),
          ("fp32", "lorentz3d:16", 30, 1), ("fp64", "vac3d:26", 25, 0),
+         # 2-D exp(i beta z) term (step_beta), real and complex fields
+         ("fp64", "beta2d", 80, 2), ("fp64", "beta2d_cplx", 60, 2), ("fp32", "beta2d", 60, 2),
+         # BFAST terms (step_bfast) and the conductivity + PML (f_cond) variants of step_curl
+         ("fp64", "bfast3d", 60, 2), ("fp32", "bfast3d", 60, 2), ("fp64", "bfast2d", 80, 2),
+         ("fp64", "cond3d", 60, 2), ("fp32", "cond3d", 60, 2), ("fp64", "cond2d", 80, 2),
          # UPSTREAM_PADE against the de-blocked reference flavour (oracle/deblock_pade.py)
          ("fp64_pade", "kerr3d:14", 40, 2), ("fp64_pade", "kerr1d", 80, 0), ("fp64_pade", "kr_per3d_rods", 40, 0)]
 

@@ -68,7 +68,8 @@ class Trace:
         for tag, pl in self.records:
             r = Reader(pl)
             if tag == T_CONFIG:
-                self.cfg = A.Config.from_buffer_copy(pl)
+                # traces recorded with an older (shorter) meepcu_config: the appended fields are zero
+                self.cfg = A.Config.from_buffer_copy(bytes(pl) + b"\0" * max(0, C.sizeof(A.Config) - len(pl)))
                 self.rb = self.cfg.realnum_bytes
                 self.rt = np.float64 if self.rb == 8 else np.float32
             elif tag == T_ARRAY:
@@ -108,6 +109,7 @@ class Replay:
         self.arr = trace.fresh_arrays()
         self.keep = []  # ctypes objects that must outlive the calls
         cfg = A.Config.from_buffer_copy(bytes(trace.cfg))
+        cfg.abi_version = A.ABI_VERSION
         cfg.device = device
         if nl_mode is not None:
             cfg.nl_mode = nl_mode
@@ -166,6 +168,11 @@ class Replay:
             tab = getattr(d, name)
             for k in range(6):
                 tab[k] = self.addr(next(it))
+        if len(r.b) - r.o >= 8 * 40:  # ABI 2 traces: f_bfast appended
+            it = iter(r.i64(40).tolist())
+            for c in range(20):
+                for k in range(2):
+                    d.f_bfast[c][k] = self.addr(next(it))
         cid = C.c_int(-1)
         self.b.check(self.b.add_chunk(self.ctx, C.byref(d), C.byref(cid)))
         assert cid.value == i
