@@ -315,15 +315,15 @@ __global__ void __launch_bounds__(kThreads)
 // give long, fully coalesced streams.
 //   HAS_COND: conductivity terms (cnd, cndinv, fcnd) compiled in;  HAS_POL: polarisations compiled in
 // ------------------------------------------------------------------------------------------------
-template <class T, bool HAS_COND, bool HAS_POL> struct PointVals {
+template <class T, bool HAS_COND, bool HAS_POL, bool HAS_BB = false> struct PointVals {
   T g1p, g1, g2, g2p, f, fu, e, fw, u, gb, fb;
   T cnd, cndinv, fcnd;
   T p[HAS_POL ? kMaxPol : 1], pp[HAS_POL ? kMaxPol : 1], s[HAS_POL ? kMaxPol : 1];
 };
 
-template <class T, bool HAS_COND, bool HAS_POL>
+template <class T, bool HAS_COND, bool HAS_POL, bool HAS_BB>
 __device__ __forceinline__ void gather_point(const CompParams<T> &c, const PolParams<T> *pol, long long i,
-                                             PointVals<T, HAS_COND, HAS_POL> &v) {
+                                             PointVals<T, HAS_COND, HAS_POL, HAS_BB> &v) {
   v.g1p = __ldg(c.g1 + i + c.s1);
   v.g1 = __ldg(c.g1 + i);
   if (c.g2) {
@@ -332,8 +332,8 @@ __device__ __forceinline__ void gather_point(const CompParams<T> &c, const PolPa
   }
   v.f = c.f[i];
   if (c.fu) v.fu = c.fu[i];
-  if (c.gb) v.gb = __ldg(c.gb + i);
-  if (c.fb) v.fb = c.fb[i];
+  if (HAS_BB && c.gb) v.gb = __ldg(c.gb + i);
+  if (HAS_BB && c.fb) v.fb = c.fb[i];
   if (HAS_COND && c.cnd) {
     v.cnd = __ldg(c.cnd + i);
     v.cndinv = __ldg(c.cndinv + i);
@@ -359,9 +359,9 @@ __device__ __forceinline__ void gather_point(const CompParams<T> &c, const PolPa
   }
 }
 
-template <class T, bool HAS_COND, bool HAS_POL>
+template <class T, bool HAS_COND, bool HAS_POL, bool HAS_BB>
 __device__ __forceinline__ void finish_point(const CompParams<T> &c, const PolParams<T> *pol, long long i, int ia, int ib, int ic,
-                                             const PointVals<T, HAS_COND, HAS_POL> &v,
+                                             const PointVals<T, HAS_COND, HAS_POL, HAS_BB> &v,
                                              const double *__restrict__ smp, int is_D, int cmp, double dt) {
   // ---------------- step_curl (step_generic.cpp:89-252) ----------------
   T curl;
@@ -422,7 +422,7 @@ __device__ __forceinline__ void finish_point(const CompParams<T> &c, const PolPa
   // increment to f through the same PML / conductivity chain, bfast right after the curl of the
   // component (step_db.cpp:129-143), beta after all curls (step_db.cpp:161-175) ----------------------
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < (HAS_BB ? 2 : 0); ++pass) { // compiled only into the class that has these terms
     if (pass == 0 ? !c.fb : !c.gb) continue;
     T bg;
     if (pass == 0) {
@@ -544,7 +544,7 @@ template <class T> struct HalfHeader { // leading, component-independent part of
   double dt;
 };
 
-template <class T, bool HAS_COND, bool HAS_POL, bool PIPE = false>
+template <class T, bool HAS_COND, bool HAS_POL, bool PIPE = false, bool HAS_BB = false>
 __global__ void __launch_bounds__(kThreads, (PIPE || HAS_COND) ? 2 : 3)
     k_halfg(const HalfParams<T> *__restrict__ params, const Tile *__restrict__ tiles,
             const double *__restrict__ smp) {
@@ -576,8 +576,8 @@ __global__ void __launch_bounds__(kThreads, (PIPE || HAS_COND) ? 2 : 3)
   long long i = (long long)m0 * s_m + (long long)io * s_o + ic;
   const int is_D = H.is_D, cmp = H.cmp;
   const double dt = H.dt;
-  PointVals<T, HAS_COND, HAS_POL> v, vn;
-  if (PIPE && m0 <= m1) gather_point<T, HAS_COND, HAS_POL>(c, Csm.pol, i, v);
+  PointVals<T, HAS_COND, HAS_POL, HAS_BB> v, vn;
+  if (PIPE && m0 <= m1) gather_point<T, HAS_COND, HAS_POL, HAS_BB>(c, Csm.pol, i, v);
 #pragma unroll 2
   for (int im = m0; im <= m1; ++im, i += s_m, PIPE ? (void)(v = vn) : (void)0) {
     const int ia = march ? io : im, ib = march ? im : io;
@@ -607,11 +607,11 @@ __global__ void __launch_bounds__(kThreads, (PIPE || HAS_COND) ? 2 : 3)
       }
     }
     if (PIPE) { // operands of the next iteration first (see k_halfg_v)
-      if (im < m1) gather_point<T, HAS_COND, HAS_POL>(c, Csm.pol, i + s_m, vn);
+      if (im < m1) gather_point<T, HAS_COND, HAS_POL, HAS_BB>(c, Csm.pol, i + s_m, vn);
     }
     else
-      gather_point<T, HAS_COND, HAS_POL>(c, Csm.pol, i, v);
-    finish_point<T, HAS_COND, HAS_POL>(c, Csm.pol, i, ia, ib, ic, v, smp, is_D, cmp, dt);
+      gather_point<T, HAS_COND, HAS_POL, HAS_BB>(c, Csm.pol, i, v);
+    finish_point<T, HAS_COND, HAS_POL, HAS_BB>(c, Csm.pol, i, ia, ib, ic, v, smp, is_D, cmp, dt);
   }
 }
 
@@ -777,6 +777,37 @@ __device__ __forceinline__ void curl3d_loop(const Curl3DParams<T> &P, const Tile
   }
 }
 
+// hook run by a thread when it leaves a tile body (nothing today)
+struct NoExit { __device__ __forceinline__ void operator()() const {} };
+
+template <class T, bool IS_D, class OnExit = NoExit>
+__device__ __forceinline__ void curl3d_body(const Curl3DParams<T> &P, const Tile t, bool special,
+                                            const double *__restrict__ smp, const OnExit on_exit = OnExit());
+template <class T, bool IS_D, class OnExit>
+__device__ __forceinline__ void curl3d_body(const Curl3DParams<T> &P, const Tile t, bool special,
+                                            const double *__restrict__ smp, const OnExit on_exit) {
+  const int p = t.p0 + threadIdx.x;
+  const int ib = p / P.pitch, ic = p - ib * P.pitch;
+  if (ib >= P.nB || ic >= P.nC) { on_exit(); return; }
+  bool act[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    act[k] = ib >= P.lo[k][1] && ib <= P.hi[k][1] && ic >= P.lo[k][2] && ic <= P.hi[k][2];
+  if (!(act[0] || act[1] || act[2])) { on_exit(); return; }
+  if (special)
+    curl3d_loop<T, IS_D, true>(P, t, ib, ic, act, smp);
+  else
+    curl3d_loop<T, IS_D, false>(P, t, ib, ic, act, smp);
+  on_exit();
+}
+
+template <class U> __device__ __forceinline__ void block_copy_params(U *dst_, const U *src_) {
+  const int nw = (int)(sizeof(U) / 4);
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(src_);
+  uint32_t *dst = reinterpret_cast<uint32_t *>(dst_);
+  for (int k = threadIdx.x; k < nw; k += kThreads) dst[k] = src[k];
+}
+
 template <class T, bool IS_D>
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 3 : 4)
     k_curl3d(const Curl3DParams<T> *__restrict__ params, const Tile *__restrict__ tiles,
@@ -785,25 +816,9 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 3 : 4)
   Tile t = tiles[blockIdx.x];
   const bool special = (t.p0 & kTileSpecial) != 0;
   t.p0 &= ~kTileSpecial;
-  {
-    const int nw = (int)(sizeof(Curl3DParams<T>) / 4);
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(params + t.param);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(&P);
-    for (int k = threadIdx.x; k < nw; k += kThreads) dst[k] = src[k];
-  }
+  block_copy_params(&P, params + t.param);
   __syncthreads();
-  const int p = t.p0 + threadIdx.x;
-  const int ib = p / P.pitch, ic = p - ib * P.pitch;
-  if (ib >= P.nB || ic >= P.nC) return;
-  bool act[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k)
-    act[k] = ib >= P.lo[k][1] && ib <= P.hi[k][1] && ic >= P.lo[k][2] && ic <= P.hi[k][2];
-  if (!(act[0] || act[1] || act[2])) return;
-  if (special)
-    curl3d_loop<T, IS_D, true>(P, t, ib, ic, act, smp);
-  else
-    curl3d_loop<T, IS_D, false>(P, t, ib, ic, act, smp);
+  curl3d_body<T, IS_D>(P, t, special, smp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -839,23 +854,13 @@ template <class T> __device__ __forceinline__ void vstore(T *p, const T *in) {
   *reinterpret_cast<VT *>(p) = v;
 }
 
-template <class T, bool IS_D>
-__global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : 3)
-    k_curl3d_v(const Curl3DParams<T> *__restrict__ params, const Tile *__restrict__ tiles) {
+template <class T, bool IS_D, class OnExit = NoExit>
+__device__ __forceinline__ void curl3d_v_body(const Curl3DParams<T> &P, const Tile t, const OnExit on_exit = OnExit()) {
   constexpr int V = VecOf<T>::V;
-  __shared__ Curl3DParams<T> P;
-  const Tile t = tiles[blockIdx.x];
-  {
-    const int nw = (int)(sizeof(Curl3DParams<T>) / 4);
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(params + t.param);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(&P);
-    for (int k = threadIdx.x; k < nw; k += kThreads) dst[k] = src[k];
-  }
-  __syncthreads();
   const int pv = P.pitch / V; // vectors per row
   const int p = t.p0 + threadIdx.x;
   const int ib = p / pv, ic = (p - ib * pv) * V;
-  if (ib >= P.nB || ic >= P.nC) return;
+  if (ib >= P.nB || ic >= P.nC) { on_exit(); return; }
   // per component: is this row active, and which of my V elements are owned in z
   bool rowact[3];
   unsigned zmask[3];
@@ -868,7 +873,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : 3)
       if (ic + j >= P.lo[k][2] && ic + j <= P.hi[k][2]) m |= 1u << j;
     zmask[k] = rowact[k] ? m : 0u;
   }
-  if (!(zmask[0] | zmask[1] | zmask[2])) return;
+  if (!(zmask[0] | zmask[1] | zmask[2])) { on_exit(); return; }
   const unsigned full = (1u << V) - 1u;
   const int sA = P.sA, nA = P.nA;
   int oy, ozs; // row offset of the y neighbour; offset of the ONE scalar z neighbour
@@ -994,6 +999,17 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : 3)
     MCU_V_FINISH(2, m2, n2, fo2, f2, e2, hu2, uv2)
 #undef MCU_V_FINISH
   }
+  on_exit();
+}
+
+template <class T, bool IS_D>
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : 3)
+    k_curl3d_v(const Curl3DParams<T> *__restrict__ params, const Tile *__restrict__ tiles) {
+  __shared__ Curl3DParams<T> P;
+  const Tile t = tiles[blockIdx.x];
+  block_copy_params(&P, params + t.param);
+  __syncthreads();
+  curl3d_v_body<T, IS_D>(P, t);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1044,39 +1060,26 @@ template <class T> struct HalfgVals { // the operands of one thread-iteration of
 // PIPE: software pipelining -- the operands of iteration n+1 are loaded into a second register set
 // before iteration n computes and stores (the compiler cannot move those loads above the stores
 // itself: nothing tells it that f, f_u, f_w and E do not alias the operand arrays).
-template <class T, bool HAS_POL, bool PIPE>
-__global__ void __launch_bounds__(kThreads, (sizeof(T) == 8 || PIPE) ? 2 : 3)
-    k_halfg_v(const HalfParams<T> *__restrict__ params, const Tile *__restrict__ tiles) {
+template <class T, bool HAS_POL, bool PIPE, class OnExit = NoExit>
+__device__ __forceinline__ void halfg_v_body(const HalfHeader<T> &H, const CompParams<T> &Csm, const Tile t,
+                                             const OnExit on_exit = OnExit()) {
   constexpr int V = VecOf<T>::V;
-  __shared__ HalfHeader<T> H;
-  __shared__ CompParams<T> Csm;
-  const Tile t = tiles[blockIdx.x];
-  const int pidx = t.param >> 2, kcomp = t.param & 3;
-  {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(params + pidx);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(&H);
-    for (int k = threadIdx.x; k < (int)(sizeof(HalfHeader<T>) / 4); k += kThreads) dst[k] = src[k];
-    const uint32_t *src2 = reinterpret_cast<const uint32_t *>(&params[pidx].comp[kcomp]);
-    uint32_t *dst2 = reinterpret_cast<uint32_t *>(&Csm);
-    for (int k = threadIdx.x; k < (int)(sizeof(CompParams<T>) / 4); k += kThreads) dst2[k] = src2[k];
-  }
-  __syncthreads();
   const int pv = H.pitch / V;
   const int p = t.p0 + threadIdx.x;
   const int io = p / pv, ic = (p - io * pv) * V;
   const int march = H.march;
   const int n_other = march ? H.nA : H.nB;
-  if (io >= n_other || ic >= H.nC) return;
+  if (io >= n_other || ic >= H.nC) { on_exit(); return; }
   const CompParams<T> c = Csm;
   const int ax_o = march ? 0 : 1, ax_m = march ? 1 : 0;
   const int lo_o = march ? c.lo[0] : c.lo[1], hi_o = march ? c.hi[0] : c.hi[1];
   const int lo_m = march ? c.lo[1] : c.lo[0], hi_m = march ? c.hi[1] : c.hi[0];
-  if (!(io >= lo_o && io <= hi_o)) return;
+  if (!(io >= lo_o && io <= hi_o)) { on_exit(); return; }
   unsigned own = 0;
 #pragma unroll
   for (int j = 0; j < V; ++j)
     if (ic + j >= c.lo[2] && ic + j <= c.hi[2]) own |= 1u << j;
-  if (!own) return;
+  if (!own) { on_exit(); return; }
   const unsigned full = (1u << V) - 1u;
   // metal planes: the part that does not change along the march, per element
   unsigned zfix_db = 0, zfix_eh = 0;
@@ -1110,7 +1113,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 8 || PIPE) ? 2 : 3)
     if (has_kw && !var_kw) load_coef<T, true>(c.sigw, c.kapw, c.kapw, c.kwaxis, c.kwoff, ia0, ib0, ic, wP, wM);
   }
   const int pitch = H.pitch;
-  auto gather = [&](long long ii, HalfgVals<T> &v) {
+  auto gather = [&](long long ii, HalfgVals<T> &v) __attribute__((always_inline)) {
     vload<T>(v.g1, c.g1 + ii);
     if (sh1) vload_shift<T>(v.g1p, c.g1, ii, c.s1, v.g1, c.s1 > 0 ? (ic + V < pitch ? ii + V : ii) : (ic > 0 ? ii - 1 : ii));
     else vload<T>(v.g1p, c.g1 + ii + c.s1);
@@ -1263,6 +1266,20 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 8 || PIPE) ? 2 : 3)
         }
     }
   }
+  on_exit();
+}
+
+template <class T, bool HAS_POL, bool PIPE>
+__global__ void __launch_bounds__(kThreads, (sizeof(T) == 8 || PIPE) ? 2 : 3)
+    k_halfg_v(const HalfParams<T> *__restrict__ params, const Tile *__restrict__ tiles) {
+  __shared__ HalfHeader<T> H;
+  __shared__ CompParams<T> Csm;
+  const Tile t = tiles[blockIdx.x];
+  const int pidx = t.param >> 2, kcomp = t.param & 3;
+  block_copy_params(&H, reinterpret_cast<const HalfHeader<T> *>(params + pidx));
+  block_copy_params(&Csm, &params[pidx].comp[kcomp]);
+  __syncthreads();
+  halfg_v_body<T, HAS_POL, PIPE>(H, Csm, t);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1319,6 +1336,44 @@ __global__ void __launch_bounds__(kThreads) k_conn_runs(const ConnRun<T> *__rest
   for (int k = 0; k < kConnPiece / 32; ++k) {
     const int j = lane + 32 * k;
     if (j < q.n) q.dst[(long long)j * q.dst_stride] = q.negate ? -v[k] : v[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_mix: clean interior tiles (curl3d_v_body) and vectorised PML tiles (halfg_v_body, kTileGeneral)
+// in ONE grid, interleaved in the tile table in proportion to their numbers.  Launched as two
+// kernels, the latency-bound PML CTAs and the bandwidth-bound interior CTAs mostly run one after
+// the other (whichever kernel the block scheduler prefers fills every SM); in one grid every SM
+// holds both kinds at any time, so the interior tiles keep HBM busy while the PML tiles wait on
+// their dependent loads.
+// (Tried and rejected, measured: also folding the halo copies and the scalar source tiles into the
+// same grid behind a "compute CTAs done" counter -- the per-thread completion signal and the extra
+// bodies cost ~600 bytes of spills at 80 registers and the step went from 0.385 to 0.58 ms.)
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileGeneral = 1 << 29; // Tile::p0 flag inside a k_mix table
+
+template <class T, bool IS_D>
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : 3)
+    k_mix(const Curl3DParams<T> *__restrict__ cparams, const HalfParams<T> *__restrict__ hparams,
+          const Tile *__restrict__ tiles) {
+  struct G { HalfHeader<T> H; CompParams<T> C; };
+  constexpr size_t kBytes = sizeof(Curl3DParams<T>) > sizeof(G) ? sizeof(Curl3DParams<T>) : sizeof(G);
+  __shared__ __align__(16) unsigned char raw[kBytes];
+  Tile t = tiles[blockIdx.x];
+  if (t.p0 & kTileGeneral) {
+    t.p0 &= ~kTileGeneral;
+    G *g = reinterpret_cast<G *>(raw);
+    const int pidx = t.param >> 2, kcomp = t.param & 3;
+    block_copy_params(&g->H, reinterpret_cast<const HalfHeader<T> *>(hparams + pidx));
+    block_copy_params(&g->C, &hparams[pidx].comp[kcomp]);
+    __syncthreads();
+    halfg_v_body<T, false, false>(g->H, g->C, t);
+  }
+  else {
+    Curl3DParams<T> *P = reinterpret_cast<Curl3DParams<T> *>(raw);
+    block_copy_params(P, cparams + t.param);
+    __syncthreads();
+    curl3d_v_body<T, IS_D>(*P, t);
   }
 }
 

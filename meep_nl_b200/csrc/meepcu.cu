@@ -281,8 +281,8 @@ template <class T> struct Ctx : CtxBase {
   // tables
   HalfParams<T> *d_half;            // [nhalf]
   std::vector<HalfParams<T> > h_half;
-  Tile *d_tiles[2][3];              // [half: 0=B/H 1=D/E][class: 0 pml-only, 1 +polarisations, 2 +conductivity]
-  int n_tiles[2][3];
+  Tile *d_tiles[2][4];              // [half: 0=B/H 1=D/E][class: 0 pml-only, 1 +polarisations, 2 +conductivity, 3 +beta/BFAST]
+  int n_tiles[2][4];
   Curl3DParams<T> *d_c3d;           // interior fast path (k_curl3d)
   std::vector<Curl3DParams<T> > h_c3d;
   Tile *d_c3d_tiles[2];
@@ -294,7 +294,9 @@ template <class T> struct Ctx : CtxBase {
   // Multi-rank overlap: in every tile list the tiles that write a plane another rank receives come
   // first (nb_* of them).  They are launched first, the halo exchange then runs on its own stream
   // beside the remaining (interior) tiles of the same half step.
-  int nb_tiles[2][3], nb_c3d_tiles[2], nb_c3dv_tiles[2], nb_gv_tiles[2][2];
+  int nb_tiles[2][4], nb_c3d_tiles[2], nb_c3dv_tiles[2], nb_gv_tiles[2][2];
+  Tile *d_mix_tiles[2];             // k_mix: clean interior tiles and vectorised PML tiles of one half, interleaved
+  int n_mix_tiles[2], nb_mix_tiles[2]; // and how many of them are cross-rank boundary tiles
   bool overlap_half[2];
   cudaStream_t st_comm;
   cudaEvent_t ev_bdone, ev_cdone;
@@ -336,7 +338,7 @@ template <class T> struct Ctx : CtxBase {
 
   // per-kernel-class profiling (CUDA events around every launch, on the library's stream)
   enum { KC_HALF_B_SIMPLE = 0, KC_HALF_B_GENERAL, KC_HALF_D_SIMPLE, KC_HALF_D_GENERAL, KC_CONN,
-         KC_FMP, KC_EH_GENERAL, KC_DFT, KC_CURL3D_B, KC_CURL3D_D, KC_CURL3D_SPECIAL, KC_HALFG_SCALAR, KC_COUNT };
+         KC_FMP, KC_EH_GENERAL, KC_DFT, KC_CURL3D_B, KC_CURL3D_D, KC_CURL3D_SPECIAL, KC_MIX_B, KC_MIX_D, KC_COUNT };
   bool profiling;
   std::vector<cudaEvent_t> ev_pool;
   std::vector<int> ev_class;      // class of the launch between ev_pool[2k] and ev_pool[2k+1]
@@ -373,6 +375,9 @@ template <class T> struct Ctx : CtxBase {
     memset(nb_c3d_tiles, 0, sizeof nb_c3d_tiles);
     memset(nb_c3dv_tiles, 0, sizeof nb_c3dv_tiles);
     memset(nb_gv_tiles, 0, sizeof nb_gv_tiles);
+    memset(d_mix_tiles, 0, sizeof d_mix_tiles);
+    memset(n_mix_tiles, 0, sizeof n_mix_tiles);
+    memset(nb_mix_tiles, 0, sizeof nb_mix_tiles);
     overlap_half[0] = overlap_half[1] = false;
     st_comm = 0;
     ev_bdone = ev_cdone = 0;
@@ -1089,9 +1094,11 @@ template <class T> struct Ctx : CtxBase {
     RC(upload(all_src, &d_src));
 
     // ---- 5. per-(chunk, half, cmp) parameter blocks + tiles ----
-    std::vector<Tile> tiles[2][3], eh_tiles[2], c3d_tiles[2], c3dv_tiles[2], gv_tiles[2][2];
+    std::vector<Tile> tiles[2][4], eh_tiles[2], c3d_tiles[2], c3dv_tiles[2], gv_tiles[2][2];
     std::vector<FmpParams<T> > fmps[2];
     std::vector<int> c3d_chunk, half_chunk; // owning chunk of every h_c3d / h_half entry
+    // interior and PML tiles of a half in one grid (k_mix); fp64 PML tiles are vectorised only for that
+    const bool mix_want = getenv("MEEPCU_MIX") ? atoi(getenv("MEEPCU_MIX")) != 0 : true;
     const int ncmp = cfg.is_real ? 1 : 2;
     cells = 0;
     alg_bytes = 0;
@@ -1329,7 +1336,8 @@ template <class T> struct Ctx : CtxBase {
             int heavy = 0;
             for (int k = 0; k < 3; ++k) {
               if (P.comp[k].f && P.comp[k].npol) heavy = std::max(heavy, 1);
-              if (P.comp[k].f && P.comp[k].cnd) heavy = 2;
+              if (P.comp[k].f && P.comp[k].cnd) heavy = std::max(heavy, 2);
+              if (P.comp[k].f && (P.comp[k].gb || P.comp[k].fb)) heavy = 3; // beta / BFAST terms: the most general kernel
             }
             // march along the longer outer axis: thin PML slabs still give long streams
             P.march = (g.nax[1] > g.nax[0]) ? 1 : 0;
@@ -1342,7 +1350,7 @@ template <class T> struct Ctx : CtxBase {
             if (getenv("MEEPCU_GSEG")) gseg = std::max(1, atoi(getenv("MEEPCU_GSEG")));
             const int V = (int)(16 / sizeof(T));
             const bool vec_ok = !getenv("MEEPCU_NO_VEC") && g.pitch % V == 0 && heavy < 2 &&
-                                (sizeof(T) == 4 || getenv("MEEPCU_GVEC64")) &&
+                                (sizeof(T) == 4 || getenv("MEEPCU_GVEC64") || (mix_want && heavy == 0)) &&
                                 !(cfg.dim == MEEPCU_D2 && cfg.beta != 0) && // the beta and BFAST terms live in
                                 !(cfg.bfast_scaled_k[0] || cfg.bfast_scaled_k[1] || cfg.bfast_scaled_k[2]); // the scalar kernel
             const int span = vec_ok ? kThreads * V : kThreads;
@@ -1553,12 +1561,64 @@ template <class T> struct Ctx : CtxBase {
         b3v.V = V; bgv.V = V;
         nb_c3d_tiles[half] = (int)(std::stable_partition(c3d_tiles[half].begin(), c3d_tiles[half].end(), b3) - c3d_tiles[half].begin());
         nb_c3dv_tiles[half] = (int)(std::stable_partition(c3dv_tiles[half].begin(), c3dv_tiles[half].end(), b3v) - c3dv_tiles[half].begin());
-        for (int cl = 0; cl < 3; ++cl)
+        for (int cl = 0; cl < 4; ++cl)
           nb_tiles[half][cl] = (int)(std::stable_partition(tiles[half][cl].begin(), tiles[half][cl].end(), bg) - tiles[half][cl].begin());
         for (int cl = 0; cl < 2; ++cl)
           nb_gv_tiles[half][cl] = (int)(std::stable_partition(gv_tiles[half][cl].begin(), gv_tiles[half][cl].end(), bgv) - gv_tiles[half][cl].begin());
         overlap_half[half] = true;
       }
+    // ---- 5c. one grid for interior + PML tiles (k_mix) ----
+    {
+      for (int half = 0; half < 2; ++half) {
+        std::vector<Tile> &A = c3dv_tiles[half], &B = gv_tiles[half][0];
+        if ((A.empty() || !mix_want) && !B.empty() && sizeof(T) == 8 && !getenv("MEEPCU_GVEC64")) {
+          // fp64 PML tiles on their own run faster in the scalar kernel: V scalar tiles per vector tile
+          const int V = (int)(16 / sizeof(T));
+          std::vector<Tile> &S0 = tiles[half][0];
+          std::vector<Tile> bnd, rest;
+          for (size_t k = 0; k < B.size(); ++k)
+            for (int j = 0; j < V; ++j) {
+              Tile t = B[k];
+              t.p0 = B[k].p0 * V + j * kThreads;
+              ((int)k < nb_gv_tiles[half][0] ? bnd : rest).push_back(t);
+            }
+          S0.insert(S0.begin() + nb_tiles[half][0], bnd.begin(), bnd.end());
+          nb_tiles[half][0] += (int)bnd.size();
+          S0.insert(S0.end(), rest.begin(), rest.end());
+          B.clear();
+          nb_gv_tiles[half][0] = 0;
+        }
+        if (A.empty() || B.empty() || !mix_want) continue;
+        std::vector<Tile> M;
+        M.reserve(A.size() + B.size());
+        const size_t abeg[3] = {0, (size_t)nb_c3dv_tiles[half], A.size()};
+        const size_t bbeg[3] = {0, (size_t)nb_gv_tiles[half][0], B.size()};
+        for (int seg = 0; seg < 2; ++seg) { // cross-rank boundary tiles, then the rest
+          const size_t na = abeg[seg + 1] - abeg[seg], nb = bbeg[seg + 1] - bbeg[seg], tot = na + nb;
+          size_t ia = abeg[seg], ib = bbeg[seg];
+          for (size_t k = 0; k < tot; ++k) {
+            const bool pickb = nb && ((k + 1) * nb / tot > k * nb / tot);
+            if ((pickb && ib < bbeg[seg + 1]) || ia >= abeg[seg + 1]) {
+              Tile t = B[ib++];
+              t.p0 |= kTileGeneral;
+              M.push_back(t);
+            }
+            else
+              M.push_back(A[ia++]);
+          }
+          if (seg == 0) nb_mix_tiles[half] = (int)M.size();
+        }
+        n_mix_tiles[half] = (int)M.size();
+        RC(upload(M, &d_mix_tiles[half]));
+        A.clear();
+        B.clear();
+        nb_c3dv_tiles[half] = nb_gv_tiles[half][0] = 0;
+        const int km = half ? KC_MIX_D : KC_MIX_B, kc = half ? KC_CURL3D_D : KC_CURL3D_B,
+                  kh = half ? KC_HALF_D_SIMPLE : KC_HALF_B_SIMPLE;
+        kc_bytes[km] = kc_bytes[kc] + kc_bytes[kh];
+        kc_bytes[kc] = kc_bytes[kh] = 0;
+      }
+    }
     RC(upload(h_half, &d_half));
     RC(upload(h_c3d, &d_c3d));
     for (int half = 0; half < 2; ++half) {
@@ -1573,7 +1633,7 @@ template <class T> struct Ctx : CtxBase {
     }
     RC(upload(h_eh, &d_eh));
     for (int half = 0; half < 2; ++half) {
-      for (int cl = 0; cl < 3; ++cl) {
+      for (int cl = 0; cl < 4; ++cl) {
         n_tiles[half][cl] = (int)tiles[half][cl].size();
         RC(upload(tiles[half][cl], &d_tiles[half][cl]));
       }
@@ -1806,7 +1866,7 @@ template <class T> struct Ctx : CtxBase {
     static const char *names[KC_COUNT] = {"k_halfg<B/H,pml>", "k_halfg<B/H,pml+pol/cond>", "k_halfg<D/E,pml>",
                                           "k_halfg<D/E,pml+pol/cond>", "k_conn", "k_fmp", "k_eh_general", "k_dft",
                                           "k_curl3d_v<B/H>", "k_curl3d_v<D/E>", "k_curl3d (source/metal tiles)",
-                                          "(unused)"};
+                                          "k_mix<B/H> (interior + pml tiles)", "k_mix<D/E> (interior + pml tiles)"};
     int m = 0;
     for (int k = 0; k < KC_COUNT && m < cap; ++k) {
       memset(&out[m], 0, sizeof out[m]);
@@ -1862,9 +1922,11 @@ template <class T> struct Ctx : CtxBase {
     MCU_RANGE(n_tiles[half][0], nb_tiles[half][0], o_t0, n_t0)
     MCU_RANGE(n_tiles[half][1], nb_tiles[half][1], o_t1, n_t1)
     MCU_RANGE(n_tiles[half][2], nb_tiles[half][2], o_t2, n_t2)
+    MCU_RANGE(n_tiles[half][3], nb_tiles[half][3], o_t3, n_t3)
+    MCU_RANGE(n_mix_tiles[half], nb_mix_tiles[half], o_mx, n_mx)
 #undef MCU_RANGE
-    const bool have_g = n_t0 || n_t1 || n_t2 || n_gv0 || n_gv1;
-    const bool fork = (have_g || (n_c && n_cv)) && (n_c || n_cv) && !profiling;
+    const bool have_g = n_t0 || n_t1 || n_t2 || n_t3 || n_gv0 || n_gv1;
+    const bool fork = (have_g || (n_c && (n_cv || n_mx))) && (n_c || n_cv || n_mx) && !profiling;
     cudaStream_t sg = fork ? st2 : st;
     if (fork) {
       CU(cudaEventRecord(ev_fork, st));
@@ -1872,6 +1934,15 @@ template <class T> struct Ctx : CtxBase {
     }
     // the bandwidth-bound interior tiles are queued first; the latency-bound PML tiles (high-priority
     // stream) take SM slots as they free up, so the two kinds of CTAs share every SM
+    if (n_mx) {
+      RC(prof_begin(half ? KC_MIX_D : KC_MIX_B));
+      if (half)
+        k_mix<T, true><<<n_mx, kThreads, 0, st>>>(d_c3d, d_half, d_mix_tiles[half] + o_mx);
+      else
+        k_mix<T, false><<<n_mx, kThreads, 0, st>>>(d_c3d, d_half, d_mix_tiles[half] + o_mx);
+      RC(prof_end());
+      launches++;
+    }
     if (n_cv) {
       RC(prof_begin(half ? KC_CURL3D_D : KC_CURL3D_B));
       if (half)
@@ -1897,7 +1968,7 @@ template <class T> struct Ctx : CtxBase {
       }
       RC(prof_end());
     }
-    if (n_gv1 || n_t1 || n_t2) {
+    if (n_gv1 || n_t1 || n_t2 || n_t3) {
       RC(prof_begin(half ? KC_HALF_D_GENERAL : KC_HALF_B_GENERAL));
       if (n_gv1) {
         if (pipe_pml) k_halfg_v<T, true, true><<<n_gv1, kThreads, 0, sg>>>(d_half, d_gv_tiles[half][1] + o_gv1);
@@ -1912,10 +1983,14 @@ template <class T> struct Ctx : CtxBase {
         k_halfg<T, true, true><<<n_t2, kThreads, 0, sg>>>(d_half, d_tiles[half][2] + o_t2, smp);
         launches++;
       }
+      if (n_t3) {
+        k_halfg<T, true, true, false, true><<<n_t3, kThreads, 0, sg>>>(d_half, d_tiles[half][3] + o_t3, smp);
+        launches++;
+      }
       RC(prof_end());
     }
     if (n_c) { // tiles with source points / metal planes, or unvectorisable pitch
-      cudaStream_t ss = n_cv ? sg : st; // beside the vector kernel when there is one
+      cudaStream_t ss = (n_cv || n_mx) ? sg : st; // beside the vector kernel when there is one
       RC(prof_begin(KC_CURL3D_SPECIAL));
       if (half)
         k_curl3d<T, true><<<n_c, kThreads, 0, ss>>>(d_c3d, d_c3d_tiles[half] + o_c, smp);
@@ -2110,8 +2185,8 @@ template <class T> struct Ctx : CtxBase {
   int get_timers(double out[22]) {
     // reference time_sink numbering (src/meep.hpp:1610-1633); seconds of device time
     for (int i = 0; i < 22; ++i) out[i] = 0;
-    out[10] = (kc_ms[KC_HALF_B_SIMPLE] + kc_ms[KC_HALF_B_GENERAL] + kc_ms[KC_CURL3D_B]) * 1e-3; // FieldUpdateB (+H, fused)
-    out[12] = (kc_ms[KC_HALF_D_SIMPLE] + kc_ms[KC_HALF_D_GENERAL] + kc_ms[KC_CURL3D_D]) * 1e-3; // FieldUpdateD (+E, fused)
+    out[10] = (kc_ms[KC_HALF_B_SIMPLE] + kc_ms[KC_HALF_B_GENERAL] + kc_ms[KC_CURL3D_B] + kc_ms[KC_MIX_B]) * 1e-3; // FieldUpdateB (+H, fused)
+    out[12] = (kc_ms[KC_HALF_D_SIMPLE] + kc_ms[KC_HALF_D_GENERAL] + kc_ms[KC_CURL3D_D] + kc_ms[KC_MIX_D]) * 1e-3; // FieldUpdateD (+E, fused)
     out[13] = (kc_ms[KC_FMP] + kc_ms[KC_EH_GENERAL]) * 1e-3;               // FieldUpdateE (unfused part)
     out[2] = kc_ms[KC_CONN] * 1e-3;                                        // Boundaries
     out[6] = kc_ms[KC_DFT] * 1e-3;                                         // FourierTransforming
