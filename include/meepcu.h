@@ -196,6 +196,18 @@ int meepcu_finalize(meepcu_ctx *ctx);
  * samples[s*n_src_times + j] holds src_time j's values for step s (may be NULL if there are none). */
 int meepcu_step(meepcu_ctx *ctx, int nsteps, int n_src_times, const meepcu_src_sample *samples);
 
+/* fields::synchronize_magnetic_fields / restore_magnetic_fields (src/energy_and_flux.cpp:145-177) on
+ * the device: back up B and H (with their f_u, f_w, f_cond, f_bfast; fields_chunk::backup_component
+ * :97-118), advance them half a step (step_db(B), step_source(B), step_boundaries(B), update_eh(H),
+ * step_boundaries(H) with `sample[j].current_B / dipole_H` = src_time j after update(time()) /
+ * update(time()+dt/2)), and replace B, H by the average of the advanced and the backed-up arrays, so
+ * that E and H are known at the same time.  restore puts the backups back.  The reference's
+ * reference count (synchronized_magnetic_fields) stays with the caller: the library accepts
+ * synchronize only when not synchronized, restore only when synchronized, and refuses meepcu_step
+ * in between. */
+int meepcu_synchronize_magnetic_fields(meepcu_ctx *ctx, int n_src_times, const meepcu_src_sample *sample);
+int meepcu_restore_magnetic_fields(meepcu_ctx *ctx);
+
 /* ---- coherence with the host object graph -------------------------------- */
 int meepcu_sync_to_host(meepcu_ctx *ctx);   /* device -> caller's arrays (fields, aux, P, dft) */
 int meepcu_sync_from_host(meepcu_ctx *ctx); /* caller's arrays -> device (fields, aux, P, dft, materials) */

@@ -104,6 +104,8 @@ _PROTOTYPES = [
     ("meepcu_comm_init", C.c_int, [vp, C.c_int, C.c_int, vp]),
     ("meepcu_finalize", C.c_int, [vp]),
     ("meepcu_step", C.c_int, [vp, C.c_int, C.c_int, vp]),
+    ("meepcu_synchronize_magnetic_fields", C.c_int, [vp, C.c_int, vp]),
+    ("meepcu_restore_magnetic_fields", C.c_int, [vp]),
     ("meepcu_sync_to_host", C.c_int, [vp]),
     ("meepcu_sync_from_host", C.c_int, [vp]),
     ("meepcu_get_time", C.c_int, [vp, C.POINTER(C.c_int)]),

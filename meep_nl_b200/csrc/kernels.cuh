@@ -1862,6 +1862,13 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// fields_chunk::average_with_backup (energy_and_flux.cpp:135-143): fc[i] = 0.5 * (fc[i] + backup[i])
+template <class T> __global__ void __launch_bounds__(kThreads) k_average(T *__restrict__ f, const T *__restrict__ backup, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    f[i] = (T)(0.5 * (double)(f[i] + backup[i])); // the reference's promotions: realnum sum, double product
+}
+
 // the per-step NaN test of step.cpp:138-139, over whole arrays, on demand
 template <class T> __global__ void k_nonfinite(const T *a, long long n, int *flag) {
   const long long stride = (long long)gridDim.x * blockDim.x;

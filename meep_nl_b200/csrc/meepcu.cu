@@ -220,6 +220,8 @@ struct CtxBase {
                        const void *phases) = 0;
   virtual int finalize() = 0;
   virtual int step(int nsteps, int nsrc, const meepcu_src_sample *smp) = 0;
+  virtual int synchronize_magnetic_fields(int nsrc, const meepcu_src_sample *smp) = 0;
+  virtual int restore_magnetic_fields() = 0;
   virtual int sync_to_host() = 0;
   virtual int sync_from_host() = 0;
   virtual int check_finite(int *ok) = 0;
@@ -332,6 +334,12 @@ template <class T> struct Ctx : CtxBase {
   int *d_flags; // [0] nr_fail, [1] nonfinite
   SrcEntry *d_src;
 
+  // synchronize_magnetic_fields state (energy_and_flux.cpp:97-177)
+  struct MagArr { char *dev; size_t bytes, off; bool is_f, is_pol; };
+  std::vector<MagArr> mag_arrays; // B and H arrays with their f_u, f_w, f_cond, f_bfast (+ magnetic P, P_prev)
+  char *mag_backup;
+  bool mag_synced;
+
   int64_t launches, steps_done, cells, alg_bytes;
   double last_ms;
   int64_t nr_unconverged = 0; // cells left unchanged after 100 NR attempts (see check_finite)
@@ -353,6 +361,8 @@ template <class T> struct Ctx : CtxBase {
           launches(0), steps_done(0), cells(0), alg_bytes(0), last_ms(0), profiling(false), ev_used(0) {
     stage[0] = stage[1] = 0;
     dstage = 0;
+    mag_backup = 0;
+    mag_synced = false;
     stage_next = 0;
     comm = 0;
     my_rank = 0;
@@ -400,6 +410,7 @@ template <class T> struct Ctx : CtxBase {
       if (stage[k]) cudaFreeHost(stage[k]);
     }
     if (dstage) cudaFree(dstage);
+    if (mag_backup) cudaFree(mag_backup);
     if (comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(comm);
     for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it)
       if (it->second.pinned) cudaHostUnregister((void *)it->second.host);
@@ -2053,6 +2064,7 @@ template <class T> struct Ctx : CtxBase {
 
   int step(int nsteps, int nsrc, const meepcu_src_sample *smp) {
     if (!finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
+    if (mag_synced) return fail(MEEPCU_ESTATE, "magnetic fields are synchronized: meepcu_restore_magnetic_fields first (step.cpp:36-41)");
     if (nsteps <= 0) return MEEPCU_OK;
     for (size_t ic = 0; ic < chunks.size(); ++ic)
       for (size_t is = 0; is < chunks[ic].src.size(); ++is)
@@ -2114,6 +2126,89 @@ template <class T> struct Ctx : CtxBase {
     RC(prof_collect());
     t += nsteps;
     steps_done += nsteps;
+    return MEEPCU_OK;
+  }
+
+  // fields::synchronize_magnetic_fields (src/energy_and_flux.cpp:145-166) on the device
+  int collect_mag_arrays() {
+    if (!mag_arrays.empty()) return MEEPCU_OK;
+    std::set<const void *> seen;
+    size_t off = 0;
+    for (size_t ic = 0; ic < chunks.size(); ++ic) {
+      const meepcu_chunk_desc &d = chunks[ic].d;
+      for (int pass = 0; pass < 2; ++pass) // B components, then H components (aliases of B skipped)
+        for (int c = 5 * (pass ? MEEPCU_H_STUFF : MEEPCU_B_STUFF); c < 5 * (pass ? MEEPCU_H_STUFF : MEEPCU_B_STUFF) + 5; ++c)
+          for (int cmp = 0; cmp < 2; ++cmp) {
+            const void *arrs[5] = {d.f[c][cmp], d.f_u[c][cmp], d.f_w[c][cmp], d.f_cond[c][cmp], d.f_bfast[c][cmp]};
+            for (int k = 0; k < 5; ++k) {
+              if (!arrs[k] || !seen.insert(arrs[k]).second) continue;
+              std::map<const char *, ArrayRec>::iterator it = arrays.find((const char *)arrs[k]);
+              if (it == arrays.end()) continue;
+              MagArr m = {it->second.dev, it->second.n_dev * sizeof(T), off, k == 0, false};
+              off += (m.bytes + 255) & ~(size_t)255;
+              mag_arrays.push_back(m);
+            }
+          }
+      // the fused B/H pass also advances magnetic polarisations, which the reference's
+      // synchronize does not: they are put back right after the half step
+      for (size_t ip = 0; ip < chunks[ic].pol[MEEPCU_H_STUFF].size(); ++ip) {
+        const meepcu_susceptibility_desc &sd = chunks[ic].pol[MEEPCU_H_STUFF][ip].d;
+        for (int c = 0; c < 20; ++c)
+          for (int cmp = 0; cmp < 2; ++cmp) {
+            const void *arrs[2] = {sd.P[c][cmp], sd.P_prev[c][cmp]};
+            for (int k = 0; k < 2; ++k) {
+              if (!arrs[k] || !seen.insert(arrs[k]).second) continue;
+              std::map<const char *, ArrayRec>::iterator it = arrays.find((const char *)arrs[k]);
+              if (it == arrays.end()) continue;
+              MagArr m = {it->second.dev, it->second.n_dev * sizeof(T), off, false, true};
+              off += (m.bytes + 255) & ~(size_t)255;
+              mag_arrays.push_back(m);
+            }
+          }
+      }
+    }
+    if (off) CU(cudaMalloc((void **)&mag_backup, off));
+    return MEEPCU_OK;
+  }
+  int synchronize_magnetic_fields(int nsrc, const meepcu_src_sample *smp) {
+    if (!finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
+    if (mag_synced) return fail(MEEPCU_ESTATE, "magnetic fields are already synchronized");
+    for (size_t ic = 0; ic < chunks.size(); ++ic)
+      for (size_t is = 0; is < chunks[ic].src.size(); ++is)
+        if (chunks[ic].src[is].tid >= nsrc || (nsrc > 0 && !smp))
+          return fail(MEEPCU_EINVAL, "source refers to src_time %d but only %d samples given", chunks[ic].src[is].tid, nsrc);
+    CU(cudaSetDevice(cfg.device));
+    RC(collect_mag_arrays());
+    const size_t ns = (size_t)std::max(nsrc, 1) * 8;
+    RC(d_smp.reserve(ns));
+    if (nsrc > 0) CU(cudaMemcpyAsync(d_smp.p, smp, sizeof(meepcu_src_sample) * (size_t)nsrc, cudaMemcpyHostToDevice, st));
+    for (size_t k = 0; k < mag_arrays.size(); ++k) // backup_component (:97-118)
+      CU(cudaMemcpyAsync(mag_backup + mag_arrays[k].off, mag_arrays[k].dev, mag_arrays[k].bytes, cudaMemcpyDeviceToDevice, st));
+    RC(launch_half(0, d_smp.p)); // step_db(B), step_source(B), step_boundaries(B), update_eh(H), step_boundaries(H)
+    for (size_t k = 0; k < mag_arrays.size(); ++k) {
+      const MagArr &m = mag_arrays[k];
+      if (m.is_pol)
+        CU(cudaMemcpyAsync(m.dev, mag_backup + m.off, m.bytes, cudaMemcpyDeviceToDevice, st));
+      else if (m.is_f) { // average_with_backup (:135-143), every element of the array
+        const long long n = (long long)(m.bytes / sizeof(T));
+        k_average<T><<<(int)std::min<long long>((n + kThreads - 1) / kThreads, 148 * 16), kThreads, 0, st>>>(
+            (T *)m.dev, (const T *)(mag_backup + m.off), n);
+        launches++;
+      }
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    mag_synced = true;
+    return MEEPCU_OK;
+  }
+  int restore_magnetic_fields() { // src/energy_and_flux.cpp:168-177
+    if (!mag_synced) return fail(MEEPCU_ESTATE, "magnetic fields are not synchronized");
+    CU(cudaSetDevice(cfg.device));
+    for (size_t k = 0; k < mag_arrays.size(); ++k)
+      if (!mag_arrays[k].is_pol)
+        CU(cudaMemcpyAsync(mag_arrays[k].dev, mag_backup + mag_arrays[k].off, mag_arrays[k].bytes, cudaMemcpyDeviceToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    mag_synced = false;
     return MEEPCU_OK;
   }
 
@@ -2293,6 +2388,14 @@ int meepcu_finalize(meepcu_ctx *ctx) {
 int meepcu_step(meepcu_ctx *ctx, int nsteps, int nsrc, const meepcu_src_sample *smp) {
   CHECK_CTX;
   return ctx->impl->step(nsteps, nsrc, smp);
+}
+int meepcu_synchronize_magnetic_fields(meepcu_ctx *ctx, int nsrc, const meepcu_src_sample *smp) {
+  CHECK_CTX;
+  return ctx->impl->synchronize_magnetic_fields(nsrc, smp);
+}
+int meepcu_restore_magnetic_fields(meepcu_ctx *ctx) {
+  CHECK_CTX;
+  return ctx->impl->restore_magnetic_fields();
 }
 int meepcu_sync_to_host(meepcu_ctx *ctx) {
   CHECK_CTX;

@@ -335,6 +335,7 @@ class fields:
         self.t = 0
         self.nl_mode, self.device = nl_mode, device
         self.bfast_scaled_k = [0.0, 0.0, 0.0]  # fields::bfast_scaled_k (step_db.cpp:65,129-143)
+        self.synchronized_magnetic_fields = 0
         self.beta = 0.0  # fields::beta: 2-D exp(i beta z) dependence (step_db.cpp:148-175)
         self.pin_host = True  # the numpy arrays below outlive the context: sync by plain DMA (meepcu_config::pin_host)
         self.boundaries = {d: Metallic for d in range(3)}
@@ -744,9 +745,31 @@ class fields:
     def step(self, n=1, samples=None):
         """n calls of fields::step() (src/step.cpp:35-140) without leaving the device"""
         self.init()
+        saved = self.synchronized_magnetic_fields  # src/step.cpp:36-41,128-134: restore, step, synchronize again
+        if saved:
+            self.synchronized_magnetic_fields = 1
+            self.restore_magnetic_fields()
         buf, nsrc = samples if samples is not None else self.samples(n)
         self.b.check(self.b.step(self.ctx, n, nsrc, buf if nsrc else None))
         self.t += n
+        if saved:
+            self.synchronize_magnetic_fields()
+            self.synchronized_magnetic_fields = saved
+
+    def synchronize_magnetic_fields(self):
+        """fields::synchronize_magnetic_fields (src/energy_and_flux.cpp:145-166), reference-counted the
+        same way: B and H are advanced half a step and averaged with their backups on the device"""
+        self.init()
+        self.synchronized_magnetic_fields += 1
+        if self.synchronized_magnetic_fields > 1: return
+        buf, nsrc = self.samples(1)  # current_B at time(), dipole_H at time() + dt/2
+        self.b.check(self.b.synchronize_magnetic_fields(self.ctx, nsrc, buf if nsrc else None))
+
+    def restore_magnetic_fields(self):  # src/energy_and_flux.cpp:168-177
+        if not self.synchronized_magnetic_fields: return
+        self.synchronized_magnetic_fields -= 1
+        if self.synchronized_magnetic_fields: return
+        self.b.check(self.b.restore_magnetic_fields(self.ctx))
 
     def sync_to_host(self):
         self.b.check(self.b.sync_to_host(self.ctx))

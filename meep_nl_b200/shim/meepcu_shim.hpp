@@ -63,6 +63,8 @@ struct api {
   MEEPCU_FN(add_connections)
   MEEPCU_FN(finalize)
   MEEPCU_FN(step)
+  MEEPCU_FN(synchronize_magnetic_fields)
+  MEEPCU_FN(restore_magnetic_fields)
   MEEPCU_FN(sync_to_host)
   MEEPCU_FN(sync_from_host)
   MEEPCU_FN(get_time)
@@ -91,6 +93,8 @@ struct api {
     MEEPCU_FN(add_connections)
     MEEPCU_FN(finalize)
     MEEPCU_FN(step)
+    MEEPCU_FN(synchronize_magnetic_fields)
+    MEEPCU_FN(restore_magnetic_fields)
     MEEPCU_FN(sync_to_host)
     MEEPCU_FN(sync_from_host)
     MEEPCU_FN(get_time)
@@ -152,6 +156,24 @@ public:
     check(a.step(ctx, n, nsrc, nsrc ? smp.data() : 0));
     f.t += n;
   }
+  // == the body of fields::synchronize_magnetic_fields / restore_magnetic_fields
+  //    (src/energy_and_flux.cpp:145-177) on the device; the caller keeps the reference's counter
+  //    `synchronized_magnetic_fields` and calls these on its 0 -> 1 and 1 -> 0 transitions
+  void synchronize_magnetic_fields() {
+    const int nsrc = (int)src_times.size();
+    std::vector<meepcu_src_sample> smp(std::max(nsrc, 1));
+    memset(smp.data(), 0, smp.size() * sizeof(meepcu_src_sample));
+    const double tm = f.t * f.dt;
+    for (int j = 0; j < nsrc; ++j) {
+      meep::src_time *st = src_times[j];
+      st->update(tm, f.dt); // calc_sources(time()): B sources
+      put(smp[j].current_B, st->current());
+      st->update(tm + 0.5 * f.dt, f.dt); // calc_sources(time() + 0.5 dt): integrated H sources
+      put(smp[j].dipole_H, st->dipole());
+    }
+    check(a.synchronize_magnetic_fields(ctx, nsrc, nsrc ? smp.data() : 0));
+  }
+  void restore_magnetic_fields() { check(a.restore_magnetic_fields(ctx)); }
   void sync_to_host() { check(a.sync_to_host(ctx)); }
   void sync_from_host() {
     check(a.set_time(ctx, f.t));

@@ -203,6 +203,8 @@ struct CtxBase {
   virtual int add_conn(int ft, int kind, size_t n, void *const *dst, const void *const *src,
                        const void *phases) = 0;
   virtual int step(int nsteps, int nsrc, const meepcu_src_sample *smp) = 0;
+  virtual int synchronize_magnetic_fields(int nsrc, const meepcu_src_sample *smp) = 0;
+  virtual int restore_magnetic_fields() = 0;
   virtual int add_remote(int ft, int kind, int peer, size_t n, const void *const *p, const void *phases, bool recv) = 0;
   virtual int check_finite(int *ok) = 0;
   virtual int read_value(const void *p, double *out) = 0;
@@ -1339,6 +1341,7 @@ template <class T> struct Impl : CtxBase {
   // fields::step, src/step.cpp:35-140
   int step(int nsteps, int nsrc, const meepcu_src_sample *smp) {
     int rc;
+    if (mag_synced) return fail(MEEPCU_ESTATE, "magnetic fields are synchronized: meepcu_restore_magnetic_fields first (step.cpp:36-41)");
     for (int ft = 0; ft < MEEPCU_NUM_FIELD_TYPES; ++ft)
       if ((!rsend[ft].empty() || !rrecv[ft].empty()) && !transport)
         return fail(MEEPCU_ESTATE, "remote connections need oracle_set_transport");
@@ -1370,6 +1373,57 @@ template <class T> struct Impl : CtxBase {
       t += 1;
       update_dfts();
     }
+    return MEEPCU_OK;
+  }
+
+  // fields::synchronize_magnetic_fields / restore_magnetic_fields, src/energy_and_flux.cpp:97-177
+  bool mag_synced = false;
+  struct Backup { T *arr; std::vector<T> copy; bool is_f; };
+  std::vector<Backup> mag_backup;
+  int synchronize_magnetic_fields(int nsrc, const meepcu_src_sample *smp) {
+    if (mag_synced) return fail(MEEPCU_ESTATE, "magnetic fields are already synchronized");
+    int rc;
+    ZeroSubnormalsScope ftz_daz;
+    mag_backup.clear();
+    for (size_t ic = 0; ic < chunks.size(); ++ic) { // backup_component for B then H components (:97-118)
+      Chunk<T> &ch = chunks[ic];
+      const size_t ntot = ch.g.ntot;
+      for (int pass = 0; pass < 2; ++pass)
+        for (int c = first_comp(pass ? MEEPCU_H_STUFF : MEEPCU_B_STUFF); c < first_comp(pass ? MEEPCU_H_STUFF : MEEPCU_B_STUFF) + 5; ++c)
+          for (int cmp = 0; cmp < 2; ++cmp) {
+            if (!ch.F(c, cmp)) continue;
+            if (pass && ch.F(c, cmp) == ch.F(dir_comp(first_comp(MEEPCU_B_STUFF), comp_dir(c)), cmp)) continue; // H == B
+            void *arrs[5] = {ch.d.f[c][cmp], ch.d.f_u[c][cmp], ch.d.f_w[c][cmp], ch.d.f_cond[c][cmp], ch.d.f_bfast[c][cmp]};
+            for (int k = 0; k < 5; ++k)
+              if (arrs[k]) {
+                Backup b;
+                b.arr = (T *)arrs[k];
+                b.copy.assign(b.arr, b.arr + ntot);
+                b.is_f = k == 0;
+                mag_backup.push_back(b);
+              }
+          }
+    }
+    if ((rc = step_db(MEEPCU_B_STUFF))) return rc;
+    step_source(MEEPCU_B_STUFF, smp);
+    step_boundaries(MEEPCU_B_STUFF);
+    if ((rc = update_eh(MEEPCU_H_STUFF, smp))) return rc;
+    step_boundaries(MEEPCU_H_STUFF);
+    for (size_t k = 0; k < mag_backup.size(); ++k) // average_with_backup (:135-143)
+      if (mag_backup[k].is_f) {
+        T *fc = mag_backup[k].arr;
+        const T *backup = mag_backup[k].copy.data();
+        for (size_t i = 0; i < mag_backup[k].copy.size(); i++) fc[i] = 0.5 * (fc[i] + backup[i]);
+      }
+    mag_synced = true;
+    return MEEPCU_OK;
+  }
+  int restore_magnetic_fields() {
+    if (!mag_synced) return fail(MEEPCU_ESTATE, "magnetic fields are not synchronized");
+    for (size_t k = 0; k < mag_backup.size(); ++k)
+      memcpy(mag_backup[k].arr, mag_backup[k].copy.data(), mag_backup[k].copy.size() * sizeof(T));
+    mag_backup.clear();
+    mag_synced = false;
     return MEEPCU_OK;
   }
 
@@ -1494,6 +1548,15 @@ int meepcu_step(meepcu_ctx *ctx, int nsteps, int nsrc, const meepcu_src_sample *
   CHECK_CTX;
   if (!ctx->impl->finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
   return ctx->impl->step(nsteps, nsrc, smp);
+}
+int meepcu_synchronize_magnetic_fields(meepcu_ctx *ctx, int nsrc, const meepcu_src_sample *smp) {
+  CHECK_CTX;
+  if (!ctx->impl->finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
+  return ctx->impl->synchronize_magnetic_fields(nsrc, smp);
+}
+int meepcu_restore_magnetic_fields(meepcu_ctx *ctx) {
+  CHECK_CTX;
+  return ctx->impl->restore_magnetic_fields();
 }
 int meepcu_sync_to_host(meepcu_ctx *ctx) {
   CHECK_CTX;

@@ -459,7 +459,7 @@ int main(int argc, char **argv) {
 #pragma omp parallel
   { _mm_setcsr(_mm_getcsr() | 0x00008040u); }
   std::string mode = "ref", cas = "vac3d:32", lib, json, record;
-  int steps = 20, warmup = 0, nchunks = 0, nl_mode = MEEPCU_NL_FORK_LITERAL, device = 0, batch = 0;
+  int steps = 20, warmup = 0, nchunks = 0, nl_mode = MEEPCU_NL_FORK_LITERAL, device = 0, batch = 0, syncmag = 0;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     if (a == "--mode") mode = argv[++i];
@@ -473,6 +473,7 @@ int main(int argc, char **argv) {
     else if (a == "--nl") nl_mode = atoi(argv[++i]);
     else if (a == "--device") device = atoi(argv[++i]);
     else if (a == "--batch") batch = atoi(argv[++i]);
+    else if (a == "--syncmag") syncmag = atoi(argv[++i]);
     else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
   }
   if (!batch) batch = steps;
@@ -534,9 +535,34 @@ int main(int argc, char **argv) {
     for (int i = 0; i < warmup; ++i) { A->f->step(); B->f->step(); }
     meepcu::attachment *att = new meepcu::attachment(*B->f, api, nl_mode, device, rec);
     double t0 = wall_time();
-    for (int i = 0; i < steps; ++i) A->f->step();
-    double t1 = wall_time();
-    for (int done = 0; done < steps; done += batch) att->step(std::min(batch, steps - done));
+    size_t sync_bad = 0, sync_checks = 0;
+    double sync_rel = 0;
+    double t1 = t0;
+    if (syncmag > 0) {
+      // every `syncmag` steps both twins synchronize their magnetic fields (energy_and_flux.cpp:145-166:
+      // the reference on the CPU, twin B on the device), every array is compared, and both restore
+      for (int done = 0; done < steps; done += syncmag) {
+        const int n = std::min(syncmag, steps - done);
+        for (int i = 0; i < n; ++i) A->f->step();
+        att->step(n);
+        A->f->synchronize_magnetic_fields();
+        att->synchronize_magnetic_fields();
+        att->sync_to_host();
+        std::vector<marray> sa = collect(*A->f), sb = collect(*B->f);
+        cmp_result rs = compare(sa, sb);
+        sync_bad += rs.nmismatch_elems;
+        sync_rel = std::max(sync_rel, rs.sum_r2 > 0 ? sqrt(rs.sum_d2 / rs.sum_r2) : sqrt(rs.sum_d2));
+        ++sync_checks;
+        A->f->restore_magnetic_fields();
+        att->restore_magnetic_fields();
+      }
+      t1 = wall_time();
+    }
+    else {
+      for (int i = 0; i < steps; ++i) A->f->step();
+      t1 = wall_time();
+      for (int done = 0; done < steps; done += batch) att->step(std::min(batch, steps - done));
+    }
     att->sync_to_host();
     double t2 = wall_time();
     std::vector<marray> ma = collect(*A->f), mb = collect(*B->f);
@@ -552,11 +578,12 @@ int main(int argc, char **argv) {
             "\"warmup\":%d,\"threads\":%d,\"cells\":%ld,\"num_chunks\":%d,\"arrays\":%zu,\"elements\":%zu,"
             "\"mismatched_arrays\":%zu,\"mismatched_elements\":%zu,\"max_abs_diff\":%.6g,"
             "\"rel_l2\":%.6g,\"first_bad\":\"%s\",\"ref_seconds\":%.6f,\"abi_seconds\":%.6f,"
-            "\"probe_ref\":%.17g,\"probe_abi\":%.17g,\"finite\":%d,\"t\":%d}\n",
+            "\"probe_ref\":%.17g,\"probe_abi\":%.17g,\"finite\":%d,\"t\":%d,\"sync_checks\":%zu,"
+            "\"sync_mismatched_elements\":%zu,\"sync_rel_l2\":%.6g}\n",
             api.backend(), cas.c_str(), (int)sizeof(realnum), steps, warmup, nthreads, A->cells,
             A->f->num_chunks, r.narrays, r.nelems, r.nmismatch_arrays, r.nmismatch_elems, r.max_abs,
             relL2, r.first_bad.c_str(), t1 - t0, t2 - t1, probe_value(A), probe_value(B),
-            (int)att->finite(), B->f->t);
+            (int)att->finite(), B->f->t, sync_checks, sync_bad, sync_rel);
     delete att;
     delete rec;
     delete A;

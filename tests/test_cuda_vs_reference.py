@@ -55,3 +55,22 @@ def test_known_results_on_gpu():
                            stderr=subprocess.DEVNULL, timeout=900)
             d = json.load(open(tf.name))
         assert abs(d["probe_abi"] - val) <= 1e-5 * abs(val), (case, d["probe_abi"], val)
+
+
+@pytest.mark.parametrize("flavour,case,steps,tol", [("fp64", "vac3d:48", 60, 1e-12), ("fp32", "vac3d:48", 60, 1e-5),
+                                                    ("fp64", "lorentz3d:32", 50, 1e-12), ("fp64", "wvg2d", 200, 1e-12),
+                                                    ("fp64", "kr_per3d_rods", 100, 1e-12), ("fp64", "cond3d:24", 60, 1e-12)])
+def test_synchronize_magnetic_fields_on_device(flavour, case, steps, tol):
+    """fields::synchronize_magnetic_fields / restore_magnetic_fields (energy_and_flux.cpp:145-177) every 9
+    steps: twin A on the reference's CPU path, twin B through meepcu_synchronize_magnetic_fields on the GPU"""
+    drv = ref_driver(flavour)
+    if drv is None:
+        pytest.skip("oracle/_ref/%s not present on this machine" % flavour)
+    with tempfile.NamedTemporaryFile(suffix=".json") as tf:
+        env = dict(os.environ, OMP_NUM_THREADS="8")
+        subprocess.run([drv, "--mode", "shim", "--lib", CUDA_LIB, "--case", case, "--steps", str(steps),
+                        "--warmup", "2", "--syncmag", "9", "--json", tf.name], check=True, env=env,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+        d = json.load(open(tf.name))
+    assert d["backend"] == "cuda-sm_100a" and d["sync_checks"] >= 5
+    assert d["sync_rel_l2"] <= tol and d["rel_l2"] <= tol, d

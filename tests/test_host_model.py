@@ -176,3 +176,48 @@ def test_cuda_vs_oracle_bfast3d(cuda_backend, oracle_backend, rt, tol):
         f.close()
     rel = np.linalg.norm(res[0] - res[1]) / np.linalg.norm(res[1])
     assert np.linalg.norm(res[1]) > 0 and rel <= tol
+
+
+def test_synchronized_fields_are_reference_counted(oracle_backend):
+    """host.fields mirrors the reference's counter (energy_and_flux.cpp:145-177, step.cpp:36-41,128-134):
+    nested synchronize calls, stepping while synchronized, and restore give back the leap-frog state"""
+    gv, f = vac3d(oracle_backend, 24, pml=0.5)
+    gv2, g = vac3d(oracle_backend, 24, pml=0.5)
+    f.step(20)
+    g.step(20)
+    c = gv.center()
+    pt = (c[0] + 0.25, c[1] + 0.05, c[2])
+    h_leap = f.get_field(Hy, pt)
+    f.synchronize_magnetic_fields()
+    f.synchronize_magnetic_fields()
+    h_sync = f.get_field(Hy, pt)
+    assert h_sync != h_leap
+    f.step(5)  # restore, 5 steps, synchronize again: still synchronized twice
+    g.step(5)
+    assert f.synchronized_magnetic_fields == 2
+    f.restore_magnetic_fields()
+    assert f.get_field(Hy, pt) != g.get_field(Hy, pt)  # still synchronized once
+    f.restore_magnetic_fields()
+    assert f.get_field(Hy, pt) == g.get_field(Hy, pt)
+    assert f.get_field(Ez, (c[0] + 0.3, c[1], c[2] + 0.05)) == g.get_field(Ez, (c[0] + 0.3, c[1], c[2] + 0.05))
+    f.close()
+    g.close()
+
+
+@pytest.mark.gpu
+def test_cuda_synchronize_equals_oracle(cuda_backend, oracle_backend):
+    res = []
+    for b in (cuda_backend, oracle_backend):
+        gv, f = vac3d(b, 48)
+        f.step(30)
+        f.synchronize_magnetic_fields()
+        f.sync_to_host()
+        a = np.concatenate([fc.f[(Hy, 0)] for fc in f.chunks] + [fc.f[(Ez, 0)] for fc in f.chunks]).astype(np.float64)
+        f.step(10)
+        f.restore_magnetic_fields()
+        f.sync_to_host()
+        b2 = np.concatenate([fc.f[(Hy, 0)] for fc in f.chunks] + [fc.f[(Ez, 0)] for fc in f.chunks]).astype(np.float64)
+        res.append(np.concatenate([a, b2]))
+        f.close()
+    rel = np.linalg.norm(res[0] - res[1]) / np.linalg.norm(res[1])
+    assert np.linalg.norm(res[1]) > 0 and rel <= 1e-12

@@ -54,3 +54,25 @@ def test_reference_known_answers_through_the_oracle():
             d = json.load(open(tf.name))
         assert d["mismatched_elements"] == 0
         assert abs(d["probe_abi"] - val) <= 1e-5 * abs(val), (case, d["probe_abi"], val)
+
+
+SYNC_CASES = [("fp64", "vac3d:32", 40), ("fp64", "wvg2d", 60), ("fp64", "lorentz3d:16", 40), ("fp32", "vac3d_cplx:14", 30),
+              ("fp64", "kr_per3d_rods", 40), ("fp64", "cond3d:12", 40), ("fp64", "bfast3d:10", 40), ("fp32", "beta2d", 40)]
+
+
+@pytest.mark.parametrize("flavour,case,steps", SYNC_CASES)
+def test_synchronize_magnetic_fields_equals_reference(flavour, case, steps):
+    """every 7 steps both twins call synchronize_magnetic_fields (reference: energy_and_flux.cpp:145-166 on
+    the CPU; twin B: meepcu_synchronize_magnetic_fields), all arrays must be identical while synchronized,
+    after restore_magnetic_fields, and at the end of the run"""
+    drv = ref_driver(flavour)
+    if drv is None:
+        pytest.skip("oracle/_ref/%s not built (reference tree absent)" % flavour)
+    with tempfile.NamedTemporaryFile(suffix=".json") as tf:
+        env = dict(os.environ, OMP_NUM_THREADS="4")
+        subprocess.run([drv, "--mode", "shim", "--lib", ORACLE_LIB, "--case", case, "--steps", str(steps),
+                        "--warmup", "2", "--syncmag", "7", "--json", tf.name], check=True, env=env,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+        d = json.load(open(tf.name))
+    assert d["sync_checks"] >= 4 and d["sync_mismatched_elements"] == 0
+    assert d["arrays"] > 0 and d["mismatched_elements"] == 0
