@@ -211,12 +211,25 @@ int meepcu_restore_magnetic_fields(meepcu_ctx *ctx);
 /* ---- coherence with the host object graph -------------------------------- */
 int meepcu_sync_to_host(meepcu_ctx *ctx);   /* device -> caller's arrays (fields, aux, P, dft) */
 int meepcu_sync_from_host(meepcu_ctx *ctx); /* caller's arrays -> device (fields, aux, P, dft, materials) */
+/* Partial coherence: only the named groups of arrays travel.  What the reference's DFT consumers
+ * (dft_flux::flux, dft_energy, near2far, save_dft_hdf5; src/dft.cpp:444-462,533-548,630-700) need is
+ * MEEPCU_SYNC_DFT alone; energy / flux-in-box probes need FIELDS. */
+enum { MEEPCU_SYNC_FIELDS = 1,    /* fields_chunk::f */
+       MEEPCU_SYNC_AUX = 2,       /* f_u, f_w, f_cond, f_bfast */
+       MEEPCU_SYNC_POL = 4,       /* polarisation P, P_prev */
+       MEEPCU_SYNC_DFT = 8,       /* dft_chunk::dft accumulators */
+       MEEPCU_SYNC_MATERIALS = 16 /* chi1inv, chi2, chi3, conductivity, sigma, sig/kap/siginv (host -> device only) */ };
+int meepcu_sync_subset(meepcu_ctx *ctx, int to_host, unsigned groups);
 int meepcu_get_time(meepcu_ctx *ctx, int *t);
 int meepcu_set_time(meepcu_ctx *ctx, int t);
 /* the per-step NaN test of src/step.cpp:138-139, evaluated lazily on the device */
 int meepcu_check_finite(meepcu_ctx *ctx, int *ok);
 /* one element of a registered host array, read from the device mirror (fields::get_field probes) */
 int meepcu_read_value(meepcu_ctx *ctx, const void *host_ptr, double *out);
+/* n elements at once, gathered on the device and returned in one transfer: what fields::get_field's
+ * interpolation stencil, get_array_slice and integrate (src/monitor.cpp, array_slice.cpp,
+ * integrate.cpp) read, without a sync of whole arrays */
+int meepcu_read_values(meepcu_ctx *ctx, size_t n, const void *const *host_ptrs, double *out);
 
 /* ---- introspection ------------------------------------------------------------------------ */
 /* seconds accumulated per reference time_sink (src/meep.hpp:1610-1633), CUDA-event based */

@@ -13,6 +13,7 @@ import os
 NUM_COMPONENTS = 20
 NUM_FIELD_TYPES = 8
 ABI_VERSION = 2
+SYNC_FIELDS, SYNC_AUX, SYNC_POL, SYNC_DFT, SYNC_MATERIALS = 1, 2, 4, 8, 16
 
 # component ids (reference src/meep/vec.hpp:31-52)
 Ex, Ey, Er, Ep, Ez, Hx, Hy, Hr, Hp, Hz, Dx, Dy, Dr, Dp, Dz, Bx, By, Br, Bp, Bz = range(20)
@@ -108,10 +109,12 @@ _PROTOTYPES = [
     ("meepcu_restore_magnetic_fields", C.c_int, [vp]),
     ("meepcu_sync_to_host", C.c_int, [vp]),
     ("meepcu_sync_from_host", C.c_int, [vp]),
+    ("meepcu_sync_subset", C.c_int, [vp, C.c_int, C.c_uint]),
     ("meepcu_get_time", C.c_int, [vp, C.POINTER(C.c_int)]),
     ("meepcu_set_time", C.c_int, [vp, C.c_int]),
     ("meepcu_check_finite", C.c_int, [vp, C.POINTER(C.c_int)]),
     ("meepcu_read_value", C.c_int, [vp, vp, C.POINTER(C.c_double)]),
+    ("meepcu_read_values", C.c_int, [vp, C.c_size_t, vp, C.POINTER(C.c_double)]),
     ("meepcu_get_timers", C.c_int, [vp, C.POINTER(C.c_double)]),
     ("meepcu_get_stats", C.c_int, [vp, C.POINTER(Stats)]),
     ("meepcu_set_profiling", C.c_int, [vp, C.c_int]),

@@ -126,6 +126,7 @@ struct ArrayRec {
   bool mut;       // downloaded by sync_to_host
   bool is_field;  // f[c][cmp] (NaN check)
   bool pinned;    // host array page-locked in place (meepcu_config::pin_host)
+  unsigned group; // MEEPCU_SYNC_* group it travels with (meepcu_sync_subset)
 };
 
 struct Geom { // device layout of one chunk
@@ -224,6 +225,8 @@ struct CtxBase {
   virtual int restore_magnetic_fields() = 0;
   virtual int sync_to_host() = 0;
   virtual int sync_from_host() = 0;
+  virtual int sync_groups(bool to_host, unsigned groups) = 0;
+  virtual int read_values(size_t n, const void *const *ptrs, double *out) = 0;
   virtual int check_finite(int *ok) = 0;
   virtual int read_value(const void *p, double *out) = 0;
   virtual int get_stats(meepcu_stats *out) = 0;
@@ -676,7 +679,7 @@ template <class T> struct Ctx : CtxBase {
   // ------------------------------------------------------------------------------------------
   // array registry
   int reg(const void *host, int chunk, int kind, size_t n_host, size_t n_dev, bool mut,
-          bool is_field = false) {
+          bool is_field = false, unsigned group = MEEPCU_SYNC_MATERIALS) {
     if (!host) return MEEPCU_OK;
     const char *key = (const char *)host;
     std::map<const char *, ArrayRec>::iterator it = arrays.find(key);
@@ -687,7 +690,7 @@ template <class T> struct Ctx : CtxBase {
       it->second.is_field = it->second.is_field || is_field;
       return MEEPCU_OK;
     }
-    ArrayRec r = {host, 0, chunk, kind, n_host, n_dev, mut, is_field, false};
+    ArrayRec r = {host, 0, chunk, kind, n_host, n_dev, mut, is_field, false, group};
     arrays[key] = r;
     return MEEPCU_OK;
   }
@@ -976,11 +979,11 @@ template <class T> struct Ctx : CtxBase {
       const size_t nh = g.ntot_host, nd = g.ntot_dev;
       for (int c = 0; c < 20; ++c) {
         for (int cmp = 0; cmp < 2; ++cmp) {
-          RC(reg(ch.d.f[c][cmp], (int)ic, A_GRID, nh, nd, true, true));
-          RC(reg(ch.d.f_u[c][cmp], (int)ic, A_GRID, nh, nd, true));
-          RC(reg(ch.d.f_w[c][cmp], (int)ic, A_GRID, nh, nd, true));
-          RC(reg(ch.d.f_cond[c][cmp], (int)ic, A_GRID, nh, nd, true));
-          RC(reg(ch.d.f_bfast[c][cmp], (int)ic, A_GRID, nh, nd, true));
+          RC(reg(ch.d.f[c][cmp], (int)ic, A_GRID, nh, nd, true, true, MEEPCU_SYNC_FIELDS));
+          RC(reg(ch.d.f_u[c][cmp], (int)ic, A_GRID, nh, nd, true, false, MEEPCU_SYNC_AUX));
+          RC(reg(ch.d.f_w[c][cmp], (int)ic, A_GRID, nh, nd, true, false, MEEPCU_SYNC_AUX));
+          RC(reg(ch.d.f_cond[c][cmp], (int)ic, A_GRID, nh, nd, true, false, MEEPCU_SYNC_AUX));
+          RC(reg(ch.d.f_bfast[c][cmp], (int)ic, A_GRID, nh, nd, true, false, MEEPCU_SYNC_AUX));
         }
         for (int d = 0; d < 5; ++d) {
           RC(reg(ch.d.chi1inv[c][d], (int)ic, A_GRID, nh, nd, false));
@@ -1006,14 +1009,14 @@ template <class T> struct Ctx : CtxBase {
             for (int cmp = 0; cmp < 2; ++cmp) {
               if ((sd.P[c][cmp] != 0) != (sd.P_prev[c][cmp] != 0))
                 return fail(MEEPCU_EINVAL, "P and P_prev must both be given");
-              RC(reg(sd.P[c][cmp], (int)ic, A_GRID, nh, nd, true));
-              RC(reg(sd.P_prev[c][cmp], (int)ic, A_GRID, nh, nd, true));
+              RC(reg(sd.P[c][cmp], (int)ic, A_GRID, nh, nd, true, false, MEEPCU_SYNC_POL));
+              RC(reg(sd.P_prev[c][cmp], (int)ic, A_GRID, nh, nd, true, false, MEEPCU_SYNC_POL));
             }
           }
         }
       for (size_t id = 0; id < ch.dft.size(); ++id) {
         const size_t n = ch.dft[id].N * ch.dft[id].d.Nomega;
-        RC(reg(ch.dft[id].d.dft, (int)ic, A_DFT, n, n, true));
+        RC(reg(ch.dft[id].d.dft, (int)ic, A_DFT, n, n, true, false, MEEPCU_SYNC_DFT));
       }
     }
     // ---- 2. one arena ----
@@ -2212,26 +2215,55 @@ template <class T> struct Ctx : CtxBase {
     return MEEPCU_OK;
   }
 
-  int sync_to_host() {
-    if (!finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
+  int sync_to_host() { return sync_groups(true, ~0u); }
+  int sync_from_host() { return sync_groups(false, ~0u); }
+  bool big(const ArrayRec &r) const { return r.n_host * sizeof(T) >= (size_t)(4 << 20) && !getenv("MEEPCU_NO_STAGING"); }
+  int sync_groups(bool to_host, unsigned groups) {
+    if (to_host && !finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
     CU(cudaSetDevice(cfg.device));
-    // halo copies the stepping kernels never consume are materialised here, so that the
-    // not-owned points of the host mirror hold what step_boundaries would have left there
-    for (int half = 0; half < 2; ++half) {
-      if (!eager_db[half]) RC(launch_conn(half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF));
-      if (!eager_p[half]) RC(launch_conn(half ? MEEPCU_PE_STUFF : MEEPCU_PH_STUFF));
+    if (to_host) {
+      // halo copies the stepping kernels never consume are materialised here, so that the
+      // not-owned points of the host mirror hold what step_boundaries would have left there
+      for (int half = 0; half < 2; ++half) {
+        if (!eager_db[half] && (groups & MEEPCU_SYNC_FIELDS)) RC(launch_conn(half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF));
+        if (!eager_p[half] && (groups & MEEPCU_SYNC_POL)) RC(launch_conn(half ? MEEPCU_PE_STUFF : MEEPCU_PH_STUFF));
+      }
     }
-    for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it)
-      if (it->second.mut) RC(big(it->second) && !it->second.pinned ? staged_copy(it->second, true) : copy_array(it->second, true));
+    for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it) {
+      const ArrayRec &r = it->second;
+      if (!(r.group & groups) || (to_host && !r.mut)) continue;
+      RC(big(r) && !r.pinned ? staged_copy(r, to_host) : copy_array(r, to_host));
+    }
     CU(cudaStreamSynchronize(st));
     return MEEPCU_OK;
   }
-  bool big(const ArrayRec &r) const { return r.n_host * sizeof(T) >= (size_t)(4 << 20) && !getenv("MEEPCU_NO_STAGING"); }
-  int sync_from_host() {
+  // n elements gathered on the device (k_pack) and returned as doubles in one transfer
+  int read_values(size_t n, const void *const *ptrs, double *out) {
+    if (!finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
+    if (!n) return MEEPCU_OK;
+    if (!ptrs || !out) return fail(MEEPCU_EINVAL, "null argument");
     CU(cudaSetDevice(cfg.device));
-    for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it)
-      RC(big(it->second) && !it->second.pinned ? staged_copy(it->second, false) : copy_array(it->second, false));
-    CU(cudaStreamSynchronize(st));
+    std::vector<const T *> h(n);
+    for (size_t i = 0; i < n; ++i) {
+      h[i] = dev_elem(ptrs[i]);
+      if (!h[i]) return fail(MEEPCU_EINVAL, "pointer %zu is not inside a registered array", i);
+    }
+    const T **d_ptr = 0;
+    T *d_val = 0;
+    CU(cudaMalloc((void **)&d_ptr, n * sizeof(T *)));
+    if (cudaMalloc((void **)&d_val, n * sizeof(T)) != cudaSuccess) { cudaFree(d_ptr); return fail(MEEPCU_ENOMEM, "cudaMalloc"); }
+    std::vector<T> v(n);
+    cudaError_t e = cudaMemcpyAsync(d_ptr, h.data(), n * sizeof(T *), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+      k_pack<T><<<(int)std::min<size_t>((n + kThreads - 1) / kThreads, 148 * 8), kThreads, 0, st>>>(d_ptr, d_val, (long long)n);
+      launches++;
+      e = cudaMemcpyAsync(v.data(), d_val, n * sizeof(T), cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_ptr);
+    cudaFree(d_val);
+    if (e != cudaSuccess) return fail(MEEPCU_ECUDA, "%s", cudaGetErrorString(e));
+    for (size_t i = 0; i < n; ++i) out[i] = (double)v[i];
     return MEEPCU_OK;
   }
   int check_finite(int *ok) {
@@ -2405,6 +2437,15 @@ int meepcu_sync_from_host(meepcu_ctx *ctx) {
   CHECK_CTX;
   if (!ctx->impl->finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
   return ctx->impl->sync_from_host();
+}
+int meepcu_sync_subset(meepcu_ctx *ctx, int to_host, unsigned groups) {
+  CHECK_CTX;
+  if (groups & ~31u) return fail(MEEPCU_EINVAL, "unknown array group");
+  return ctx->impl->sync_groups(to_host != 0, groups);
+}
+int meepcu_read_values(meepcu_ctx *ctx, size_t n, const void *const *host_ptrs, double *out) {
+  CHECK_CTX;
+  return ctx->impl->read_values(n, host_ptrs, out);
 }
 int meepcu_get_time(meepcu_ctx *ctx, int *t) {
   CHECK_CTX;

@@ -789,6 +789,48 @@ class fields:
         self.b.check(self.b.read_value(self.ctx, arr.ctypes.data + idx * arr.itemsize, C.byref(out)))
         return out.value
 
+    def sync_subset(self, to_host=True, groups=A.SYNC_FIELDS):
+        """meepcu_sync_subset: only the named array groups travel (A.SYNC_FIELDS | SYNC_AUX | SYNC_POL |
+        SYNC_DFT | SYNC_MATERIALS)"""
+        self.b.check(self.b.sync_subset(self.ctx, 1 if to_host else 0, groups))
+
+    def sync_dft_to_host(self):
+        """all that dft_flux::flux / dft_energy / near2far read (src/dft.cpp:533-548,630-700)"""
+        self.sync_subset(True, A.SYNC_DFT)
+
+    def get_array_slice(self, c, lo, hi, cmp=0):
+        """fields::get_array_slice without interpolation (src/array_slice.cpp): the values of component c
+        at its Yee indices lo..hi (inclusive, global cells), gathered on the device by meepcu_read_values
+        -- no sync of whole arrays.  Points that no local chunk owns come back as NaN."""
+        self.init()
+        gv = self.gv
+        lo = [int(lo[d]) if gv.has[d] else 0 for d in range(3)]
+        hi = [int(hi[d]) if gv.has[d] else 0 for d in range(3)]
+        shape = [hi[d] - lo[d] + 1 for d in range(3)]
+        out = np.full(shape, np.nan)
+        for fc in self.chunks:
+            if not fc.mine or (c, cmp) not in fc.f: continue
+            cg = fc.gv
+            sl, rng = [], []
+            for d in range(3):
+                if not gv.has[d]:
+                    sl.append(slice(0, 1)); rng.append(np.zeros(1, np.int64)); continue
+                off = (cg.io[d] - gv.io[d]) // 2            # global index of this chunk's local index 0
+                o0, o1 = cg.owned_range(c, d)
+                a, b = max(lo[d], off + o0), min(hi[d], off + o1)
+                if a > b: break
+                sl.append(slice(a - lo[d], b - lo[d] + 1))
+                rng.append(np.arange(a - off, b - off + 1, dtype=np.int64) * cg.stride[d])
+            else:
+                idx = (rng[0][:, None, None] + rng[1][None, :, None] + rng[2][None, None, :]).reshape(-1)
+                arr = fc.f[(c, cmp)]
+                ptrs = np.ascontiguousarray((arr.ctypes.data + idx * arr.itemsize).astype(np.uint64))
+                vals = np.empty(ptrs.size, np.float64)
+                self.b.check(self.b.read_values(self.ctx, ptrs.size, ptrs.ctypes.data,
+                                                vals.ctypes.data_as(C.POINTER(C.c_double))))
+                out[sl[0], sl[1], sl[2]] = vals.reshape([s_.stop - s_.start for s_ in sl])
+        return out
+
     def stats(self):
         s = A.Stats()
         self.b.check(self.b.get_stats(self.ctx, C.byref(s)))

@@ -67,6 +67,8 @@ struct api {
   MEEPCU_FN(restore_magnetic_fields)
   MEEPCU_FN(sync_to_host)
   MEEPCU_FN(sync_from_host)
+  MEEPCU_FN(sync_subset)
+  MEEPCU_FN(read_values)
   MEEPCU_FN(get_time)
   MEEPCU_FN(set_time)
   MEEPCU_FN(check_finite)
@@ -97,6 +99,8 @@ struct api {
     MEEPCU_FN(restore_magnetic_fields)
     MEEPCU_FN(sync_to_host)
     MEEPCU_FN(sync_from_host)
+    MEEPCU_FN(sync_subset)
+    MEEPCU_FN(read_values)
     MEEPCU_FN(get_time)
     MEEPCU_FN(set_time)
     MEEPCU_FN(check_finite)
@@ -175,6 +179,10 @@ public:
   }
   void restore_magnetic_fields() { check(a.restore_magnetic_fields(ctx)); }
   void sync_to_host() { check(a.sync_to_host(ctx)); }
+  // only the DFT accumulators: all that dft_flux::flux / dft_energy / near2far / save_dft_hdf5 read
+  void sync_dft_to_host() { check(a.sync_subset(ctx, 1, MEEPCU_SYNC_DFT)); }
+  // fields only (get_array_slice, energy_in_box, flux_in_box ...)
+  void sync_fields_to_host() { check(a.sync_subset(ctx, 1, MEEPCU_SYNC_FIELDS)); }
   void sync_from_host() {
     check(a.set_time(ctx, f.t));
     check(a.sync_from_host(ctx));

@@ -1566,6 +1566,12 @@ int meepcu_sync_from_host(meepcu_ctx *ctx) {
   CHECK_CTX;
   return MEEPCU_OK;
 }
+int meepcu_sync_subset(meepcu_ctx *ctx, int to_host, unsigned groups) {
+  CHECK_CTX;
+  (void)to_host;
+  if (groups & ~31u) return fail(MEEPCU_EINVAL, "unknown array group");
+  return MEEPCU_OK; // the oracle works in place on the caller's arrays
+}
 int meepcu_get_time(meepcu_ctx *ctx, int *t) {
   CHECK_CTX;
   *t = ctx->impl->t;
@@ -1583,6 +1589,15 @@ int meepcu_check_finite(meepcu_ctx *ctx, int *ok) {
 int meepcu_read_value(meepcu_ctx *ctx, const void *p, double *out) {
   CHECK_CTX;
   return ctx->impl->read_value(p, out);
+}
+int meepcu_read_values(meepcu_ctx *ctx, size_t n, const void *const *host_ptrs, double *out) {
+  CHECK_CTX;
+  if (n && (!host_ptrs || !out)) return fail(MEEPCU_EINVAL, "null argument");
+  for (size_t i = 0; i < n; ++i) {
+    int rc = ctx->impl->read_value(host_ptrs[i], out + i);
+    if (rc) return rc;
+  }
+  return MEEPCU_OK;
 }
 int meepcu_get_timers(meepcu_ctx *ctx, double out[22]) {
   CHECK_CTX;

@@ -221,3 +221,41 @@ def test_cuda_synchronize_equals_oracle(cuda_backend, oracle_backend):
         f.close()
     rel = np.linalg.norm(res[0] - res[1]) / np.linalg.norm(res[1])
     assert np.linalg.norm(res[1]) > 0 and rel <= 1e-12
+
+
+def test_slices_and_partial_sync_through_the_oracle(oracle_backend):
+    """meepcu_read_values (get_array_slice) and meepcu_sync_subset agree with a full sync"""
+    from meep_nl_b200 import _cabi as A
+    gv, f = vac3d(oracle_backend, 24, pml=0.5)
+    f.step(25)
+    sl = f.get_array_slice(Ez, (3, 12, 2), (20, 12, 21))
+    assert sl.shape == (18, 1, 20) and np.isfinite(sl).all() and np.abs(sl).max() > 0
+    c = gv.center()
+    assert sl[9, 0, 10] == f.get_field(Ez, (1.2, 1.2, 1.25))
+    f.sync_subset(True, A.SYNC_FIELDS | A.SYNC_DFT)
+    f.close()
+
+
+@pytest.mark.gpu
+def test_cuda_slices_dft_and_partial_sync(cuda_backend, oracle_backend):
+    """device-side gathers and the DFT-only download against the oracle (bit-exact in fp64)"""
+    outs = []
+    for b in (cuda_backend, oracle_backend):
+        gv = H.vol3d(4.0, 4.0, 4.0, 10)
+        s = H.structure(gv, lambda x, y, z: 1.0 + 2.0 * (z > 2.0), pml=0.8)
+        f = H.fields(s, b)
+        f.use_real_fields()
+        f.add_point_source(Ez, 0.3, 0.2, 0.0, 4.0, (2.0, 2.0, 1.55), 1.0)
+        f.add_dft_fields(Ez, (10, 10, 30), (30, 30, 30), np.linspace(0.2, 0.4, 7))
+        f.step(60)
+        sl = f.get_array_slice(Ez, (2, 20, 2), (38, 20, 38))
+        # wipe the host copies of the DFT accumulators (the oracle works in place: not there), fetch ONLY them
+        dfts = [d["dft"] for fc in f.chunks for d in fc.dfts]
+        if b is cuda_backend:
+            for a in dfts: a[:] = 0
+        f.sync_dft_to_host()
+        outs.append((sl, np.concatenate([np.asarray(a).view(np.float64).ravel() for a in dfts])))
+        assert np.abs(outs[-1][1]).max() > 0
+        f.close()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
