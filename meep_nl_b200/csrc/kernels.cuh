@@ -1610,6 +1610,10 @@ __device__ bool run_nr(T seed1, T seed2, T seed3, T out[3], const NRP<T> &p1, co
   return false;
 }
 
+// susceptibility.cpp:185-186
+#define MCU_POFFDIAG(u, g, sx, s)                                                                  \
+  (0.25 * ((g[i] + g[i - sx]) * u[i] + (g[i + s] + g[(i + s) - sx]) * u[i + s]))
+
 #define MCU_OFFDIAG(u, g, sx)                                                                      \
   (0.25 * ((g[i] + g[i - sx]) * u[i] + (g[i + s] + g[(i + s) - sx]) * u[i + s]))
 
@@ -1763,6 +1767,65 @@ __global__ void __launch_bounds__(kThreads)
   const int a1 = t.a1 - 1 < P.hi[0] ? t.a1 - 1 : P.hi[0];
   long long i = (long long)a0 * P.sA + (long long)ib * P.sB + ic;
   for (int ia = a0; ia <= a1; ++ia, i += P.sA) eh_point<T>(P, i, ia, ib, ic);
+}
+
+// ------------------------------------------------------------------------------------------------
+// lorentzian_susceptibility::update_P with an anisotropic sigma tensor (susceptibility.cpp:188-262):
+// the 3x3 / 2x2 branches average the OTHER components of W over four neighbours, so they run as
+// their own pass after the E (H) update of the whole chunk and the exchange of W halos
+// (step.cpp:109-118).  Isotropic components of the same susceptibility are done here too.
+// ------------------------------------------------------------------------------------------------
+template <class T> struct PolGenParams {
+  int nA, nB, nC, pitch;
+  long long sA, sB;
+  int lo[3], hi[3];
+  T *p, *pp;
+  const T *s, *w;        // sigma[c][d], W[c]
+  const T *s1, *w1, *s2, *w2; // off-diagonal sigma rows and the W components they multiply (after the swap rule)
+  long long is, is1, is2;
+  T gamma1inv, gamma1, omega0dtsqr, omega0dtsqr_denom;
+};
+
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+    k_pol_general(const PolGenParams<T> *__restrict__ params, const Tile *__restrict__ tiles) {
+  __shared__ PolGenParams<T> P;
+  const Tile t = tiles[blockIdx.x];
+  block_copy_params(&P, params + t.param);
+  __syncthreads();
+  const int pos = t.p0 + threadIdx.x;
+  const int ib = pos / P.pitch, ic = pos - ib * P.pitch;
+  if (ib < P.lo[1] || ib > P.hi[1] || ic < P.lo[2] || ic > P.hi[2]) return;
+  const int a0 = t.a0 > P.lo[0] ? t.a0 : P.lo[0];
+  const int a1 = t.a1 - 1 < P.hi[0] ? t.a1 - 1 : P.hi[0];
+  T *p = P.p, *pp = P.pp;
+  const T *s = P.s, *w = P.w, *s1 = P.s1, *w1 = P.w1, *s2 = P.s2, *w2 = P.w2;
+  const long long is = P.is, is1 = P.is1, is2 = P.is2;
+  const T gamma1inv = P.gamma1inv, gamma1 = P.gamma1, omega0dtsqr = P.omega0dtsqr, omega0dtsqr_denom = P.omega0dtsqr_denom;
+  long long i = (long long)a0 * P.sA + (long long)ib * P.sB + ic;
+  for (int ia = a0; ia <= a1; ++ia, i += P.sA) {
+    if (s1 && s2) { // 3x3 anisotropic, :225-241
+      if (s[i] != 0) {
+        const T pcur = p[i];
+        p[i] = gamma1inv * (pcur * (2 - omega0dtsqr_denom) - gamma1 * pp[i] +
+                            omega0dtsqr * (s[i] * w[i] + MCU_POFFDIAG(s1, w1, is1, is) + MCU_POFFDIAG(s2, w2, is2, is)));
+        pp[i] = pcur;
+      }
+    }
+    else if (s1) { // 2x2 anisotropic, :243-251
+      if (s[i] != 0) {
+        const T pcur = p[i];
+        p[i] = gamma1inv * (pcur * (2 - omega0dtsqr_denom) - gamma1 * pp[i] +
+                            omega0dtsqr * (s[i] * w[i] + MCU_POFFDIAG(s1, w1, is1, is)));
+        pp[i] = pcur;
+      }
+    }
+    else { // isotropic, :253-259
+      const T pcur = p[i];
+      p[i] = gamma1inv * (pcur * (2 - omega0dtsqr_denom) - gamma1 * pp[i] + omega0dtsqr * (s[i] * w[i]));
+      pp[i] = pcur;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -317,6 +317,11 @@ template <class T> struct Ctx : CtxBase {
   int n_runs[MEEPCU_NUM_FIELD_TYPES];
   T **d_zero[MEEPCU_NUM_FIELD_TYPES]; // unfused metal lists (only non-plane lists; normally empty)
   long long n_zero[MEEPCU_NUM_FIELD_TYPES];
+  PolGenParams<T> *d_polgen;       // anisotropic-sigma polarisation updates (k_pol_general)
+  std::vector<PolGenParams<T> > h_polgen;
+  Tile *d_polgen_tiles[2];
+  int n_polgen_tiles[2];
+  std::set<std::pair<int, int> > aniso_chunk_half; // (chunk, half) whose polarisations update in k_pol_general
   bool general_half[2];  // some chunk needs k_eh_general in this half
   bool eager_db[2];      // exchange B / D halos every step
   bool eager_p[2];       // exchange PH / PE halos every step
@@ -349,7 +354,7 @@ template <class T> struct Ctx : CtxBase {
 
   // per-kernel-class profiling (CUDA events around every launch, on the library's stream)
   enum { KC_HALF_B_SIMPLE = 0, KC_HALF_B_GENERAL, KC_HALF_D_SIMPLE, KC_HALF_D_GENERAL, KC_CONN,
-         KC_FMP, KC_EH_GENERAL, KC_DFT, KC_CURL3D_B, KC_CURL3D_D, KC_CURL3D_SPECIAL, KC_MIX_B, KC_MIX_D, KC_COUNT };
+         KC_FMP, KC_EH_GENERAL, KC_DFT, KC_CURL3D_B, KC_CURL3D_D, KC_CURL3D_SPECIAL, KC_MIX_B, KC_MIX_D, KC_POL_GENERAL, KC_COUNT };
   bool profiling;
   std::vector<cudaEvent_t> ev_pool;
   std::vector<int> ev_class;      // class of the launch between ev_pool[2k] and ev_pool[2k+1]
@@ -402,6 +407,9 @@ template <class T> struct Ctx : CtxBase {
     memset(d_conn, 0, sizeof d_conn);
     memset(d_runs, 0, sizeof d_runs);
     memset(n_runs, 0, sizeof n_runs);
+    d_polgen = 0;
+    memset(d_polgen_tiles, 0, sizeof d_polgen_tiles);
+    memset(n_polgen_tiles, 0, sizeof n_polgen_tiles);
     memset(d_zero, 0, sizeof d_zero);
     memset(n_zero, 0, sizeof n_zero);
     fmp_has_src[0] = fmp_has_src[1] = false;
@@ -1110,6 +1118,7 @@ template <class T> struct Ctx : CtxBase {
     // ---- 5. per-(chunk, half, cmp) parameter blocks + tiles ----
     std::vector<Tile> tiles[2][4], eh_tiles[2], c3d_tiles[2], c3dv_tiles[2], gv_tiles[2][2];
     std::vector<FmpParams<T> > fmps[2];
+    std::vector<Tile> polgen_tiles[2];
     std::vector<int> c3d_chunk, half_chunk; // owning chunk of every h_c3d / h_half entry
     // interior and PML tiles of a half in one grid (k_mix); fp64 PML tiles are vectorised only for that
     const bool mix_want = getenv("MEEPCU_MIX") ? atoi(getenv("MEEPCU_MIX")) != 0 : true;
@@ -1150,8 +1159,7 @@ template <class T> struct Ctx : CtxBase {
               if (sd.P[ec][cmp] && sd.sigma[ec][k] &&
                   ((sd.sigma[ec][d1] && ch.d.f[dir_comp(ft, d1)][cmp]) ||
                    (sd.sigma[ec][d2] && ch.d.f[dir_comp(ft, d2)][cmp])))
-                return fail(MEEPCU_EUNSUPPORTED,
-                            "anisotropic susceptibility sigma (susceptibility.cpp:225-251) is not on the GPU path yet");
+                aniso_chunk_half.insert(std::make_pair((int)ic, half)); // susceptibility.cpp:225-251 -> k_pol_general
           }
         }
         if (general) {
@@ -1159,6 +1167,7 @@ template <class T> struct Ctx : CtxBase {
           eager_db[half] = true;
           if (!ch.pol[ft].empty()) eager_p[half] = true;
         }
+        aniso_now = aniso_chunk_half.count(std::make_pair((int)ic, half)) != 0;
         for (int cmp = 0; cmp < ncmp; ++cmp) {
           HalfParams<T> P;
           memset(&P, 0, sizeof P);
@@ -1526,12 +1535,69 @@ template <class T> struct Ctx : CtxBase {
             }
           }
         }
+        // ---- polarisations of a chunk with an anisotropic sigma: their own pass (k_pol_general) ----
+        if (aniso_now) {
+          const int sgn = ft == MEEPCU_H_STUFF ? -1 : +1;
+          for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip) {
+            const meepcu_susceptibility_desc &sd = ch.pol[ft][ip].d;
+            PolParams<T> coef[kMaxPol];
+            for (int cmp = 0; cmp < ncmp; ++cmp)
+              for (int k = 0; k < 3; ++k) {
+                const int ec = dir_comp(ft, k);
+                if (!sd.P[ec][cmp]) continue;
+                // W = f_w ?: f (update_pols.cpp:43-44)
+                const void *wh = ch.d.f_w[ec][cmp] ? ch.d.f_w[ec][cmp] : ch.d.f[ec][cmp];
+                if (!wh || !sd.sigma[ec][k]) continue; // susceptibility.cpp:201
+                const bool save = aniso_now;
+                aniso_now = false;
+                RC(fill_pols(ch, ft, ec, k, cmp, coef)); // the realnum coefficients of :191-194
+                aniso_now = save;
+                PolGenParams<T> Q;
+                memset(&Q, 0, sizeof Q);
+                Q.nA = g.nax[0]; Q.nB = g.nax[1]; Q.nC = g.nax[2]; Q.pitch = g.pitch;
+                Q.sA = (long long)g.pitch * g.nax[1]; Q.sB = g.pitch;
+                for (int ax = 0; ax < 3; ++ax) {
+                  const int d = g.dir_of_axis[ax];
+                  Q.lo[ax] = d < 0 ? 0 : 1 - g.yee_shift(ec, d);
+                  Q.hi[ax] = d < 0 ? 0 : g.num[d] - g.yee_shift(ec, d);
+                }
+                Q.p = dev(sd.P[ec][cmp]); Q.pp = dev(sd.P_prev[ec][cmp]);
+                Q.s = dev(sd.sigma[ec][k]); Q.w = dev(wh);
+                int d1 = (k + 1) % 3, d2 = (k + 2) % 3;
+                const int c1 = dir_comp(ft, d1), c2 = dir_comp(ft, d2);
+                const void *w1h = ch.d.f_w[c1][cmp] ? ch.d.f_w[c1][cmp] : ch.d.f[c1][cmp];
+                const void *w2h = ch.d.f_w[c2][cmp] ? ch.d.f_w[c2][cmp] : ch.d.f[c2][cmp];
+                Q.w1 = dev(w1h); Q.s1 = Q.w1 ? dev(sd.sigma[ec][d1]) : 0;
+                Q.w2 = dev(w2h); Q.s2 = Q.w2 ? dev(sd.sigma[ec][d2]) : 0;
+                Q.is = g.ds[k] * sgn; Q.is1 = g.ds[d1] * sgn; Q.is2 = g.ds[d2] * sgn;
+                if (Q.s2 && !Q.s1) { // :219-224
+                  std::swap(Q.w1, Q.w2); std::swap(Q.s1, Q.s2); std::swap(Q.is1, Q.is2);
+                }
+                Q.gamma1inv = coef[ip].gamma1inv; Q.gamma1 = coef[ip].gamma1;
+                Q.omega0dtsqr = coef[ip].omega0dtsqr; Q.omega0dtsqr_denom = coef[ip].omega0dtsqr_denom;
+                const int qidx = (int)h_polgen.size();
+                h_polgen.push_back(Q);
+                const int plane = g.nax[1] * g.pitch;
+                const int seg = g.nax[0] <= 48 ? g.nax[0] : 32;
+                for (int a0 = 0; a0 < g.nax[0]; a0 += seg)
+                  for (int p0 = 0; p0 < plane; p0 += kThreads) {
+                    Tile t = {qidx, a0, std::min(a0 + seg, g.nax[0]), p0};
+                    polgen_tiles[half].push_back(t);
+                  }
+                const int v = 5 + (Q.s1 ? 2 : 0) + (Q.s2 ? 2 : 0); // R,W p, R,W pp, R s (+ R s1,w1 / s2,w2; W itself counted with E)
+                alg_bytes += (long long)v * nc * (long long)sizeof(T);
+                kc_bytes[KC_POL_GENERAL] += (long long)v * nc * (long long)sizeof(T);
+              }
+          }
+        }
+        aniso_now = false;
       }
     }
     // ---- 5b. multi-rank: boundary tiles first (see nb_* above) ----
     if (n_ranks > 1 && !getenv("MEEPCU_NO_OVERLAP"))
       for (int half = 0; half < 2; ++half) {
         if (general_half[half]) continue; // k_eh_general needs the D halo before E exists: ordered path
+        if (!polgen_tiles[half].empty()) continue; // k_pol_general needs the W halo before P: ordered path
         const int fts[2] = {half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF, half ? MEEPCU_WE_STUFF : MEEPCU_WH_STUFF};
         // per chunk: the planes (index on device axis A) that hold points another rank receives
         std::vector<std::set<int> > planes(chunks.size());
@@ -1646,6 +1712,11 @@ template <class T> struct Ctx : CtxBase {
       }
     }
     RC(upload(h_eh, &d_eh));
+    RC(upload(h_polgen, &d_polgen));
+    for (int half = 0; half < 2; ++half) {
+      n_polgen_tiles[half] = (int)polgen_tiles[half].size();
+      RC(upload(polgen_tiles[half], &d_polgen_tiles[half]));
+    }
     for (int half = 0; half < 2; ++half) {
       for (int cl = 0; cl < 4; ++cl) {
         n_tiles[half][cl] = (int)tiles[half][cl].size();
@@ -1816,6 +1887,7 @@ template <class T> struct Ctx : CtxBase {
     return MEEPCU_OK;
   }
 
+  bool aniso_now = false; // set around fill_pols calls for (chunk, half) pairs in aniso_chunk_half
   int fill_pols(const ChunkH &ch, int ft, int ec, int k, int cmp, PolParams<T> *out) {
     for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip) {
       const meepcu_susceptibility_desc &sd = ch.pol[ft][ip].d;
@@ -1825,6 +1897,7 @@ template <class T> struct Ctx : CtxBase {
       q.pp = dev(sd.P_prev[ec][cmp]);
       // update_P needs w && s (susceptibility.cpp:201); w = f_w ?: f exists since f[ec][cmp] does
       q.s = q.p ? dev(sd.sigma[ec][k]) : 0;
+      if (aniso_now) q.s = 0; // updated by k_pol_general after the whole chunk has its new W
       // susceptibility.cpp:191-194, evaluated in realnum exactly like the reference
       const double pi = 3.141592653589793238462643383276;
       const T dt = (T)cfg.dt;
@@ -1880,7 +1953,8 @@ template <class T> struct Ctx : CtxBase {
     static const char *names[KC_COUNT] = {"k_halfg<B/H,pml>", "k_halfg<B/H,pml+pol/cond>", "k_halfg<D/E,pml>",
                                           "k_halfg<D/E,pml+pol/cond>", "k_conn", "k_fmp", "k_eh_general", "k_dft",
                                           "k_curl3d_v<B/H>", "k_curl3d_v<D/E>", "k_curl3d (source/metal tiles)",
-                                          "k_mix<B/H> (interior + pml tiles)", "k_mix<D/E> (interior + pml tiles)"};
+                                          "k_mix<B/H> (interior + pml tiles)", "k_mix<D/E> (interior + pml tiles)",
+                                          "k_pol_general (anisotropic sigma)"};
     int m = 0;
     for (int k = 0; k < KC_COUNT && m < cap; ++k) {
       memset(&out[m], 0, sizeof out[m]);
@@ -2060,6 +2134,12 @@ template <class T> struct Ctx : CtxBase {
       launches++;
     }
     RC(launch_conn(ftw));                    // step.cpp:81,113 (empty unless anisotropic sigma)
+    if (n_polgen_tiles[half]) {              // update_pols for anisotropic sigma, step.cpp:83-86,115-117
+      RC(prof_begin(KC_POL_GENERAL));
+      k_pol_general<T><<<n_polgen_tiles[half], kThreads, 0, st>>>(d_polgen, d_polgen_tiles[half]);
+      RC(prof_end());
+      launches++;
+    }
     if (eager_p[half]) RC(launch_conn(ftp)); // step.cpp:87,118
     RC(launch_conn(fte));                    // step.cpp:91,122
     return MEEPCU_OK;

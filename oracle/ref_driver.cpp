@@ -104,6 +104,22 @@ public:
   virtual double chi2(component c, const vec &r) { (void)c; (void)r; return chi2v; }
 };
 
+// anisotropic Lorentzian sigma (susceptibility.cpp:225-251): a material whose sigma tensor has
+// off-diagonal entries inside the ring, so that update_P reads the other components of W at neighbours
+struct aniso_sigma_mat : public material_function {
+  virtual double chi1p1(field_type ft, const vec &r) { return ft == E_stuff ? ring_eps(r) : 1.0; }
+  virtual double eps(const vec &r) { return ring_eps(r); }
+  virtual void sigma_row(component c, double sigrow[3], const vec &r) {
+    const double m = ring_mask(r);
+    sigrow[0] = sigrow[1] = sigrow[2] = 0.0;
+    if (m == 0) return;
+    const int d = component_direction(c) % 3; // X,Y,Z -> 0,1,2
+    sigrow[d] = 1.0;
+    sigrow[(d + 1) % 3] = 0.35; // 3x3 anisotropic for every E component
+    sigrow[(d + 2) % 3] = (c == Ez) ? 0.0 : -0.2; // ... except Ez: the 2x2 branch (:243-251)
+  }
+};
+
 struct problem {
   grid_volume gv;
   structure *s;
@@ -277,6 +293,22 @@ static problem *build(const std::string &spec, int nchunks) {
     p->fluxes.push_back(p->f->add_dft_flux_plane(volume(vec(lo, hi, lo), vec(hi, hi, hi)), 0.1, 0.2, nf));
     p->fluxes.push_back(p->f->add_dft_flux_plane(volume(vec(lo, lo, hi), vec(hi, hi, hi)), 0.1, 0.2, nf));
     p->fluxes.push_back(p->f->add_dft_flux_plane(volume(vec(lo, lo, lo), vec(lo, hi, hi)), 0.1, 0.2, nf));
+  }
+  else if (name == "aniso3d") { // lorentz3d with an anisotropic sigma tensor, PML around it
+    if (!n) n = 16;
+    p->gv = vol3d(n / a, n / a, n / a, a);
+    const double L = n / a;
+    g_ring_c[0] = g_ring_c[1] = g_ring_c[2] = L / 2;
+    g_ring_r0 = 0.15 * L;
+    g_ring_r1 = 0.30 * L;
+    g_ring_h = 0.2 * L;
+    p->s = new structure(p->gv, ring_eps, pml(0.1 * L > 1.0 ? 1.0 : 0.1 * L), identity(), nchunks, 0.5, false);
+    aniso_sigma_mat am;
+    p->s->add_susceptibility(am, E_stuff, lorentzian_susceptibility(1.1, 1e-5));
+    p->f = new fields(p->s);
+    p->f->use_real_fields();
+    p->f->add_point_source(Ez, 0.15, 0.1, 0.0, 4.0, vec(L / 2 + 0.22 * L, L / 2, L / 2), 1.0);
+    p->f->add_point_source(Ex, 0.2, 0.1, 0.0, 4.0, vec(L / 2, L / 2 + 0.2 * L, L / 2), 0.7);
   }
   else if (name == "phc3d") { // BASELINE config 5 shape: slab, PML in z, Bloch-periodic x,y, fp32-able
     if (!n) n = 16;
