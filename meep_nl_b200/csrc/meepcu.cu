@@ -303,8 +303,8 @@ template <class T> struct Ctx : CtxBase {
   Tile *d_mix_tiles[2];             // k_mix: clean interior tiles and vectorised PML tiles of one half, interleaved
   int n_mix_tiles[2], nb_mix_tiles[2]; // and how many of them are cross-rank boundary tiles
   bool overlap_half[2];
-  cudaStream_t st_comm;
-  cudaEvent_t ev_bdone, ev_cdone;
+  cudaStream_t st_comm, st_bnd;
+  cudaEvent_t ev_bdone, ev_cdone, ev_bstart;
   EhParams<T> *d_eh;
   std::vector<EhParams<T> > h_eh;
   Tile *d_eh_tiles[2];
@@ -397,8 +397,8 @@ template <class T> struct Ctx : CtxBase {
     memset(n_mix_tiles, 0, sizeof n_mix_tiles);
     memset(nb_mix_tiles, 0, sizeof nb_mix_tiles);
     overlap_half[0] = overlap_half[1] = false;
-    st_comm = 0;
-    ev_bdone = ev_cdone = 0;
+    st_comm = st_bnd = 0;
+    ev_bdone = ev_cdone = ev_bstart = 0;
     memset(n_tiles, 0, sizeof n_tiles);
     memset(d_eh_tiles, 0, sizeof d_eh_tiles);
     memset(n_eh_tiles, 0, sizeof n_eh_tiles);
@@ -437,7 +437,9 @@ template <class T> struct Ctx : CtxBase {
     if (ev_join) cudaEventDestroy(ev_join);
     if (ev_bdone) cudaEventDestroy(ev_bdone);
     if (ev_cdone) cudaEventDestroy(ev_cdone);
+    if (ev_bstart) cudaEventDestroy(ev_bstart);
     if (st_comm) cudaStreamDestroy(st_comm);
+    if (st_bnd) cudaStreamDestroy(st_bnd);
     if (st2) cudaStreamDestroy(st2);
     if (st) cudaStreamDestroy(st);
   }
@@ -970,9 +972,11 @@ template <class T> struct Ctx : CtxBase {
       const int pr = getenv("MEEPCU_ST2_PRIO") ? atoi(getenv("MEEPCU_ST2_PRIO")) : 1; // 1: high (default), -1: low
       CU(cudaStreamCreateWithPriority(&st2, cudaStreamNonBlocking, pr > 0 ? hi_p : (pr < 0 ? lo_p : 0)));
       CU(cudaStreamCreateWithPriority(&st_comm, cudaStreamNonBlocking, hi_p));
+      CU(cudaStreamCreateWithPriority(&st_bnd, cudaStreamNonBlocking, hi_p));
     }
     CU(cudaEventCreateWithFlags(&ev_bdone, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ev_cdone, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ev_bstart, cudaEventDisableTiming));
     CU(cudaEventCreate(&ev0));
     CU(cudaEventCreate(&ev1));
     CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
@@ -1995,7 +1999,8 @@ template <class T> struct Ctx : CtxBase {
 
   // The curl / PML kernels of one half step over part of every tile list.
   //   part 0: all tiles;  1: boundary tiles only (the first nb_* of each list);  2: the rest
-  int launch_compute(int half, const double *smp, int part) {
+  // sm: stream of the interior tiles; sside: stream of the PML / special tiles (== sm: no fork)
+  int launch_compute(int half, const double *smp, int part, cudaStream_t sm, cudaStream_t sside) {
     static const bool pipe_pml = getenv("MEEPCU_PIPE") != 0;
     // The interior tiles (k_curl3d) and the PML / general tiles (k_halfg) of one half step touch
     // disjoint chunks, so they run side by side on two streams; everything else is ordered after
@@ -2014,29 +2019,29 @@ template <class T> struct Ctx : CtxBase {
     MCU_RANGE(n_mix_tiles[half], nb_mix_tiles[half], o_mx, n_mx)
 #undef MCU_RANGE
     const bool have_g = n_t0 || n_t1 || n_t2 || n_t3 || n_gv0 || n_gv1;
-    const bool fork = (have_g || (n_c && (n_cv || n_mx))) && (n_c || n_cv || n_mx) && !profiling;
-    cudaStream_t sg = fork ? st2 : st;
+    const bool fork = (have_g || (n_c && (n_cv || n_mx))) && (n_c || n_cv || n_mx) && !profiling && sside != sm;
+    cudaStream_t sg = fork ? sside : sm;
     if (fork) {
-      CU(cudaEventRecord(ev_fork, st));
-      CU(cudaStreamWaitEvent(st2, ev_fork, 0));
+      CU(cudaEventRecord(ev_fork, sm));
+      CU(cudaStreamWaitEvent(sside, ev_fork, 0));
     }
     // the bandwidth-bound interior tiles are queued first; the latency-bound PML tiles (high-priority
     // stream) take SM slots as they free up, so the two kinds of CTAs share every SM
     if (n_mx) {
       RC(prof_begin(half ? KC_MIX_D : KC_MIX_B));
       if (half)
-        k_mix<T, true><<<n_mx, kThreads, 0, st>>>(d_c3d, d_half, d_mix_tiles[half] + o_mx);
+        k_mix<T, true><<<n_mx, kThreads, 0, sm>>>(d_c3d, d_half, d_mix_tiles[half] + o_mx);
       else
-        k_mix<T, false><<<n_mx, kThreads, 0, st>>>(d_c3d, d_half, d_mix_tiles[half] + o_mx);
+        k_mix<T, false><<<n_mx, kThreads, 0, sm>>>(d_c3d, d_half, d_mix_tiles[half] + o_mx);
       RC(prof_end());
       launches++;
     }
     if (n_cv) {
       RC(prof_begin(half ? KC_CURL3D_D : KC_CURL3D_B));
       if (half)
-        k_curl3d_v<T, true><<<n_cv, kThreads, 0, st>>>(d_c3d, d_c3dv_tiles[half] + o_cv);
+        k_curl3d_v<T, true><<<n_cv, kThreads, 0, sm>>>(d_c3d, d_c3dv_tiles[half] + o_cv);
       else
-        k_curl3d_v<T, false><<<n_cv, kThreads, 0, st>>>(d_c3d, d_c3dv_tiles[half] + o_cv);
+        k_curl3d_v<T, false><<<n_cv, kThreads, 0, sm>>>(d_c3d, d_c3dv_tiles[half] + o_cv);
       RC(prof_end());
       launches++;
     }
@@ -2078,7 +2083,7 @@ template <class T> struct Ctx : CtxBase {
       RC(prof_end());
     }
     if (n_c) { // tiles with source points / metal planes, or unvectorisable pitch
-      cudaStream_t ss = (n_cv || n_mx) ? sg : st; // beside the vector kernel when there is one
+      cudaStream_t ss = (n_cv || n_mx) ? sg : sm; // beside the vector kernel when there is one
       RC(prof_begin(KC_CURL3D_SPECIAL));
       if (half)
         k_curl3d<T, true><<<n_c, kThreads, 0, ss>>>(d_c3d, d_c3d_tiles[half] + o_c, smp);
@@ -2088,8 +2093,8 @@ template <class T> struct Ctx : CtxBase {
       launches++;
     }
     if (fork) {
-      CU(cudaEventRecord(ev_join, st2));
-      CU(cudaStreamWaitEvent(st, ev_join, 0));
+      CU(cudaEventRecord(ev_join, sside));
+      CU(cudaStreamWaitEvent(sm, ev_join, 0));
     }
     return MEEPCU_OK;
   }
@@ -2102,19 +2107,24 @@ template <class T> struct Ctx : CtxBase {
     if (overlap_half[half] && !profiling) {
       // boundary tiles -> [halo exchange on st_comm  ||  interior tiles + local halo copies] -> join.
       // The exchange writes only not-owned points of E/H (W), which no kernel of this half reads.
-      RC(launch_compute(half, smp, 1));
-      CU(cudaEventRecord(ev_bdone, st));
+      // The boundary tiles have their own high-priority stream: they are scheduled first but do not
+      // hold back the interior tiles (both sets only depend on the previous half step).
+      CU(cudaEventRecord(ev_bstart, st));
+      CU(cudaStreamWaitEvent(st_bnd, ev_bstart, 0));
+      RC(launch_compute(half, smp, 1, st_bnd, st_bnd));
+      CU(cudaEventRecord(ev_bdone, st_bnd));
       CU(cudaStreamWaitEvent(st_comm, ev_bdone, 0));
       RC(launch_remote(ftw, st_comm));
       RC(launch_remote(fte, st_comm));
       CU(cudaEventRecord(ev_cdone, st_comm));
-      RC(launch_compute(half, smp, 2));
+      RC(launch_compute(half, smp, 2, st, st2));
+      CU(cudaStreamWaitEvent(st, ev_bdone, 0)); // the local halo copies read boundary tiles' results too
       RC(launch_conn_local(ftw));
       RC(launch_conn_local(fte));
       CU(cudaStreamWaitEvent(st, ev_cdone, 0));
       return MEEPCU_OK;
     }
-    RC(launch_compute(half, smp, 0));
+    RC(launch_compute(half, smp, 0, st, st2));
     if (eager_db[half]) RC(launch_conn(ftd)); // step.cpp:72,104
     if (general_half[half]) {
       if (n_fmp[half]) {
