@@ -132,7 +132,8 @@ class MeepcuError(RuntimeError):
 
 
 def default_library_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmeepcuda.so")
+    """the in-tree build, or another build of the same ABI named by MEEPCU_LIBRARY (kernel experiments)"""
+    return os.environ.get("MEEPCU_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmeepcuda.so")
 
 
 class Backend:

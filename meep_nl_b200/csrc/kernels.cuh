@@ -109,6 +109,7 @@ struct Tile {
              // or metal planes (k_curl3d then runs the loop body that checks for them)
 };
 constexpr int kTileSpecial = 1 << 30;
+constexpr int kTileRows = 1 << 30; // k_eh_general: p0 = (row block << 12) | column block, 8 rows x 32 columns per CTA
 
 // meepcu_src_sample layout: current_B[2], dipole_H[2], current_D[2], dipole_E[2]
 __device__ __forceinline__ double2 sample_current(const double *smp, int tid, int is_D) {
@@ -1352,8 +1353,11 @@ __global__ void __launch_bounds__(kThreads) k_conn_runs(const ConnRun<T> *__rest
 // ------------------------------------------------------------------------------------------------
 constexpr int kTileGeneral = 1 << 29; // Tile::p0 flag inside a k_mix table
 
+#ifndef MCU_MIX_F32_CTAS
+#define MCU_MIX_F32_CTAS 3
+#endif
 template <class T, bool IS_D>
-__global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : 3)
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : MCU_MIX_F32_CTAS)
     k_mix(const Curl3DParams<T> *__restrict__ cparams, const HalfParams<T> *__restrict__ hparams,
           const Tile *__restrict__ tiles) {
   struct G { HalfHeader<T> H; CompParams<T> C; };
@@ -1748,8 +1752,11 @@ __device__ __forceinline__ void eh_point(const EhParams<T> &q, long long i, int 
   q.f[i] = enew;
 }
 
+#ifndef MCU_EH_CTAS
+#define MCU_EH_CTAS 4 // Newton-Raphson is latency-bound: 64 registers / 32 warps per SM beat 110 registers / 16 warps
+#endif
 template <class T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, MCU_EH_CTAS)
     k_eh_general(const EhParams<T> *__restrict__ params, const Tile *__restrict__ tiles) {
   __shared__ EhParams<T> P;
   const Tile t = tiles[blockIdx.x];
@@ -1760,8 +1767,19 @@ __global__ void __launch_bounds__(kThreads)
     for (int k = threadIdx.x; k < nw; k += kThreads) dst[k] = src[k];
   }
   __syncthreads();
-  const int p = t.p0 + threadIdx.x;
-  const int ib = p / P.pitch, ic = p - ib * P.pitch;
+  int ib, ic;
+  if (t.p0 & kTileRows) {
+    // 8 rows x 32 columns: the warps of a CTA share their range of the fastest axis, so a CTA is
+    // either all inside a nonlinear slab (every warp iterates Newton-Raphson) or all outside (done
+    // at once) -- in the flat mapping 3 warps of 8 carried the whole latency-bound solve
+    ib = ((t.p0 & ~kTileRows) >> 12) * 8 + (int)(threadIdx.x >> 5);
+    ic = (t.p0 & 4095) * 32 + (int)(threadIdx.x & 31);
+  }
+  else {
+    const int p = t.p0 + threadIdx.x;
+    ib = p / P.pitch;
+    ic = p - ib * P.pitch;
+  }
   if (ib < P.lo[1] || ib > P.hi[1] || ic < P.lo[2] || ic > P.hi[2]) return;
   const int a0 = t.a0 > P.lo[0] ? t.a0 : P.lo[0];
   const int a1 = t.a1 - 1 < P.hi[0] ? t.a1 - 1 : P.hi[0];

@@ -1529,7 +1529,16 @@ template <class T> struct Ctx : CtxBase {
               h_eh.push_back(E);
               const int plane = g.nax[1] * g.pitch;
               int seg = g.nax[0] <= 48 ? g.nax[0] : 32;
+              const bool rows2d = g.pitch % 32 == 0 && g.pitch / 32 < 4096 && !getenv("MEEPCU_EH_FLAT");
               for (int a0 = 0; a0 < g.nax[0]; a0 += seg)
+                if (rows2d) {
+                  for (int rb = 0; rb < (g.nax[1] + 7) / 8; ++rb)
+                    for (int zb = 0; zb < g.pitch / 32; ++zb) {
+                      Tile t = {eidx, a0, std::min(a0 + seg, g.nax[0]), kTileRows | (rb << 12) | zb};
+                      eh_tiles[half].push_back(t);
+                    }
+                }
+                else
                 for (int p0 = 0; p0 < plane; p0 += kThreads) {
                   Tile t = {eidx, a0, std::min(a0 + seg, g.nax[0]), p0};
                   eh_tiles[half].push_back(t);
@@ -1673,6 +1682,9 @@ template <class T> struct Ctx : CtxBase {
           nb_gv_tiles[half][0] = 0;
         }
         if (A.empty() || B.empty() || !mix_want) continue;
+        // worth it only where the PML tiles are a real share of the half step (vacuum cube with PML on
+        // six faces: 28 % of the tiles; a slab with thin PML on two faces: 2 % -> two streams are better)
+        if (B.size() * 20 < A.size() + B.size() && !getenv("MEEPCU_MIX")) continue;
         std::vector<Tile> M;
         M.reserve(A.size() + B.size());
         const size_t abeg[3] = {0, (size_t)nb_c3dv_tiles[half], A.size()};
