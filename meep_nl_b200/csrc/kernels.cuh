@@ -1753,7 +1753,7 @@ __device__ __forceinline__ void eh_point(const EhParams<T> &q, long long i, int 
 }
 
 #ifndef MCU_EH_CTAS
-#define MCU_EH_CTAS 4 // Newton-Raphson is latency-bound: 64 registers / 32 warps per SM beat 110 registers / 16 warps
+#define MCU_EH_CTAS 5 // Newton-Raphson is latency-bound: measured 2.73 / 2.13 / 2.02 / 1.65 / 1.75 ms at 2 / 3 / 4 / 5 / 6 CTAs per SM (256^3)
 #endif
 template <class T>
 __global__ void __launch_bounds__(kThreads, MCU_EH_CTAS)
