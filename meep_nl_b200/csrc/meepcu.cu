@@ -315,6 +315,10 @@ template <class T> struct Ctx : CtxBase {
   ConnTable<T> d_conn[MEEPCU_NUM_FIELD_TYPES][3];
   ConnRun<T> *d_runs[MEEPCU_NUM_FIELD_TYPES]; // COPY + NEGATE lists in run-length form
   int n_runs[MEEPCU_NUM_FIELD_TYPES];
+  // E/H halo copies no stepping kernel reads (the not-owned plane NORMAL to the component: d/dx of Ex
+  // appears in no curl): copied only when the host mirror is refreshed, like the B/D/P halos
+  ConnRun<T> *d_runs_def[MEEPCU_NUM_FIELD_TYPES];
+  int n_runs_def[MEEPCU_NUM_FIELD_TYPES];
   T **d_zero[MEEPCU_NUM_FIELD_TYPES]; // unfused metal lists (only non-plane lists; normally empty)
   long long n_zero[MEEPCU_NUM_FIELD_TYPES];
   PolGenParams<T> *d_polgen;       // anisotropic-sigma polarisation updates (k_pol_general)
@@ -407,6 +411,8 @@ template <class T> struct Ctx : CtxBase {
     memset(d_conn, 0, sizeof d_conn);
     memset(d_runs, 0, sizeof d_runs);
     memset(n_runs, 0, sizeof n_runs);
+    memset(d_runs_def, 0, sizeof d_runs_def);
+    memset(n_runs_def, 0, sizeof n_runs_def);
     d_polgen = 0;
     memset(d_polgen_tiles, 0, sizeof d_polgen_tiles);
     memset(n_polgen_tiles, 0, sizeof n_polgen_tiles);
@@ -1745,10 +1751,42 @@ template <class T> struct Ctx : CtxBase {
     }
 
     // ---- 6. connections ----
+    // which E/H connections can wait for the next host sync: 3-D, and nobody but the curl kernels reads
+    // E/H neighbours (no k_eh_general / k_pol_general / DFT averaging / cross-rank lists built from them)
+    size_t dfts_total = 0;
+    for (size_t ic = 0; ic < chunks.size(); ++ic) dfts_total += chunks[ic].dft.size();
+    const bool defer_normal = cfg.dim == MEEPCU_D3 && !general_half[0] && !general_half[1] && h_polgen.empty() &&
+                              dfts_total == 0 && !getenv("MEEPCU_NO_DEFER");
+    std::map<const char *, int> comp_of; // host base of an f array -> component (direction is what matters)
+    if (defer_normal)
+      for (size_t ic = 0; ic < chunks.size(); ++ic)
+        for (int c = 0; c < 10; ++c) // E and H components (H may alias B: same direction)
+          for (int cmp = 0; cmp < 2; ++cmp)
+            if (chunks[ic].d.f[c][cmp]) comp_of[(const char *)chunks[ic].d.f[c][cmp]] = c;
     for (int ft = 0; ft < MEEPCU_NUM_FIELD_TYPES; ++ft) {
-      std::vector<ConnRun<T> > runs;
+      std::vector<ConnRun<T> > runs[2]; // [0] every step, [1] deferred
       for (int kind = MEEPCU_CONNECT_NEGATE; kind <= MEEPCU_CONNECT_COPY; ++kind) {
-        const PtrList &L = conn[ft][kind];
+        const PtrList &L0 = conn[ft][kind];
+        PtrList part[2];
+        for (size_t k = 0; k < L0.dst.size(); ++k) {
+          int which = 0;
+          if (defer_normal && (ft == MEEPCU_E_STUFF || ft == MEEPCU_H_STUFF)) {
+            size_t e = 0;
+            const ArrayRec *r = find(L0.dst[k], sizeof(T), &e);
+            std::map<const char *, int>::iterator ci = r ? comp_of.find((const char *)r->host) : comp_of.end();
+            if (r && r->kind == A_GRID && ci != comp_of.end()) {
+              const Geom &g = chunks[r->chunk].g;
+              const int c = ci->second, d = comp_dir(c);
+              const long long coord = ((long long)e / g.hs[d]) % (g.num[d] + 1);
+              const long long notowned = g.yee_shift(c, d) ? g.num[d] : 0;
+              if (coord == notowned) which = 1;
+            }
+          }
+          part[which].dst.push_back(L0.dst[k]);
+          part[which].src.push_back(L0.src[k]);
+        }
+        for (int which = 0; which < 2; ++which) {
+        const PtrList &L = part[which];
         size_t k = 0;
         while (k < L.dst.size()) {
           T *d0 = dev_elem(L.dst[k]);
@@ -1781,13 +1819,16 @@ template <class T> struct Ctx : CtxBase {
             pc.dst = r.dst + (long long)o * r.dst_stride;
             pc.src = r.src + (long long)o * r.src_stride;
             pc.n = std::min(kConnPiece, r.n - o);
-            runs.push_back(pc);
+            runs[which].push_back(pc);
           }
           k += r.n;
         }
+        }
       }
-      n_runs[ft] = (int)runs.size();
-      RC(upload(runs, &d_runs[ft]));
+      n_runs[ft] = (int)runs[0].size();
+      RC(upload(runs[0], &d_runs[ft]));
+      n_runs_def[ft] = (int)runs[1].size();
+      RC(upload(runs[1], &d_runs_def[ft]));
     }
     for (int ft = 0; ft < MEEPCU_NUM_FIELD_TYPES; ++ft)
       for (int kind = 0; kind < 1; ++kind) { // PHASE lists keep the per-element form
@@ -2328,6 +2369,11 @@ template <class T> struct Ctx : CtxBase {
       // not-owned points of the host mirror hold what step_boundaries would have left there
       for (int half = 0; half < 2; ++half) {
         if (!eager_db[half] && (groups & MEEPCU_SYNC_FIELDS)) RC(launch_conn(half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF));
+        const int fte = half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF;
+        if (n_runs_def[fte] && (groups & MEEPCU_SYNC_FIELDS)) { // the normal-plane E/H halos
+          k_conn_runs<T><<<(n_runs_def[fte] + 7) / 8, kThreads, 0, st>>>(d_runs_def[fte], n_runs_def[fte]);
+          launches++;
+        }
         if (!eager_p[half] && (groups & MEEPCU_SYNC_POL)) RC(launch_conn(half ? MEEPCU_PE_STUFF : MEEPCU_PH_STUFF));
       }
     }
