@@ -488,11 +488,12 @@ template <class T> struct Ctx : CtxBase {
       g.dir_of_axis[ax] = dirs[j];
       g.nax[ax] = g.num[dirs[j]] + 1;
     }
-    // fastest axis padded so that rows start on a 128-byte line (long rows) or at least on a
-    // 32-byte sector (short rows, e.g. the 12-point-thick PML slabs: padding them to 32 elements
-    // would leave most lanes of every warp idle)
+    // fastest axis padded so that rows start on a 128-byte line (long rows) or on a 16-byte vector
+    // boundary (short rows, e.g. the 12-point-thick PML slabs: padding them to 32 elements would
+    // leave most lanes of every warp idle, and padding fp32 rows to a whole sector moved 16 floats of
+    // DRAM traffic for 11-12 useful ones)
     {
-      const int q = g.nax[2] >= 64 ? 32 : (int)(32 / sizeof(T));
+      const int q = g.nax[2] >= 64 ? 32 : (int)(16 / sizeof(T));
       g.pitch = ((g.nax[2] + q - 1) / q) * q;
     }
     const long long sax[3] = {(long long)g.pitch * g.nax[1], (long long)g.pitch, 1};
