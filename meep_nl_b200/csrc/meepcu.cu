@@ -488,12 +488,15 @@ template <class T> struct Ctx : CtxBase {
       g.dir_of_axis[ax] = dirs[j];
       g.nax[ax] = g.num[dirs[j]] + 1;
     }
-    // fastest axis padded so that rows start on a 128-byte line (long rows) or on a 16-byte vector
-    // boundary (short rows, e.g. the 12-point-thick PML slabs: padding them to 32 elements would
-    // leave most lanes of every warp idle, and padding fp32 rows to a whole sector moved 16 floats of
-    // DRAM traffic for 11-12 useful ones)
+    // fastest axis padded so that rows start on a 16-byte vector boundary.  Short rows (e.g. the
+    // 12-point-thick PML slabs): padding them to 32 elements would leave most lanes of every warp idle,
+    // and padding fp32 rows to a whole 32-byte sector moved 16 floats of DRAM traffic for 11-12 useful ones.
     {
-      const int q = g.nax[2] >= 64 ? 32 : (int)(16 / sizeof(T));
+      // long rows: measured at 256^3 (257-point rows) -- fp32 0.3597 / 0.3546 / 0.3527 ms per step for rows
+      // padded to 32 / 8 / 4 elements (fewer idle lanes beats line alignment), fp64 0.6329 / 0.6294 / 0.6325
+      // for 32 / 16 / 2
+      int q = g.nax[2] >= 64 ? (sizeof(T) == 4 ? 4 : 16) : (int)(16 / sizeof(T));
+      if (g.nax[2] >= 64 && getenv("MEEPCU_PITCH_Q")) q = std::max((int)(16 / sizeof(T)), atoi(getenv("MEEPCU_PITCH_Q")));
       g.pitch = ((g.nax[2] + q - 1) / q) * q;
     }
     const long long sax[3] = {(long long)g.pitch * g.nax[1], (long long)g.pitch, 1};
