@@ -388,6 +388,15 @@ def main_ours(args):
                                "bytes_per_cell": st1.algorithmic_bytes_per_step / max(cells, 1)},
                 "serialised_ms_per_step": prof_ms / K,
                 "kernels": kernels}
+    # DRAM traffic of the dominant kernel from the committed ncu capture of this same workload (or null)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if roof and workload_name(args).startswith(tr["workload"]) and world == 1:
+            roof["traffic"] = tr.get(args.dtype, {}).get(roof["kernel"])
+            if roof["traffic"]:
+                roof["traffic_source"] = "ncu --set full, profiles/r01d_ncu_full_%s.csv (bytes per launch)" % args.dtype
+    except Exception:
+        pass
     line = {"metric": "Mcell-updates/s (fused E+H step)", "value": value, "unit": "Mcell/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
