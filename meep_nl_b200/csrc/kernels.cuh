@@ -1,29 +1,32 @@
 // kernels.cuh -- sm_100a kernels of the per-timestep field update.
 //
 // Reference semantics restated here (each kernel cites the lines it replaces):
-//   k_half      : fields_chunk::step_db + step_curl        (src/step_db.cpp:44-146, step_generic.cpp:69-253)
+//   k_mix / k_curl3d_v / k_curl3d / k_halfg_v / k_halfg (one fused pass per half step):
+//                 fields_chunk::step_db + step_curl        (src/step_db.cpp:44-146, step_generic.cpp:69-253)
+//                 step_bfast, step_beta                    (src/step_generic.cpp:259-537, step_db.cpp:129-175)
 //                 fields_chunk::step_source                (src/step.cpp:296-319)
 //                 fields_chunk::zero_metal                 (src/boundaries.cpp:304-307)
 //                 fields_chunk::update_eh + step_update_EDHB, diagonal branches
 //                                                          (src/update_eh.cpp:67-283, step_generic.cpp:576-906)
 //                 lorentzian_susceptibility::subtract_P / update_P, isotropic
 //                                                          (src/susceptibility.cpp:188-281)
-//                 all fused in ONE pass over a chunk so that every array element moves once per
-//                 half step (DESIGN.md "bytes per cell").
+//                 so that every array element moves once per half step (DESIGN.md "bytes per cell").
 //   k_eh_general: step_update_EDHB branches that read neighbours of D-P: the fork's Newton-Raphson
 //                 chi2 solve (step_generic.cpp:730-816, newton_raphson.cpp:93-359) and upstream's
 //                 Pade/off-diagonal formulas (UPSTREAM_PADE mode)
+//   k_pol_general: update_P with an anisotropic sigma tensor (src/susceptibility.cpp:225-251)
 //   k_fmp       : f_minus_p = D - P - dipoles             (src/update_eh.cpp:122-146)
-//   k_conn_*    : fields::step_boundaries gather/scatter   (src/step.cpp:173-288)
+//   k_conn_*, k_pack, k_unpack : fields::step_boundaries   (src/step.cpp:173-288)
 //   k_dft       : dft_chunk::update_dft                    (src/dft.cpp:265-307)
+//   k_average   : fields_chunk::average_with_backup        (src/energy_and_flux.cpp:135-143)
 //
 // Arithmetic is written with the reference's operand order and compiled with --fmad=false so
 // that results are bit-identical to the reference's x86-64 build (no FMA contraction there).
 //
 // Thread mapping (all grid kernels): a chunk's array is [nA][nB][pitch] with the fastest axis C
-// padded to `pitch` (multiple of 32 elements, rows 128B-aligned).  A CTA owns 256 consecutive
-// positions of the flattened (B,C) plane -- fully coalesced rows -- and marches along A over
-// [a0,a1).  One launch covers every chunk: CTAs find their (chunk, cmp, plane segment, A range)
+// padded to `pitch` (rows start on a 16-byte vector boundary).  A CTA owns 256 consecutive
+// (vectors of) positions of the flattened (B,C) plane -- fully coalesced rows -- and marches along
+// A over [a0,a1).  One launch covers every chunk: CTAs find their (chunk, cmp, plane segment, A range)
 // in a tile table, and copy that chunk's parameter block to shared memory.
 #pragma once
 #include <cuda_runtime.h>
@@ -145,171 +148,9 @@ __device__ __forceinline__ bool on_zero_plane(unsigned m, const int lo[3], const
          ((m & 8u) && ia == hi[0]) || ((m & 16u) && ib == hi[1]) || ((m & 32u) && ic == hi[2]);
 }
 
-// One point of one component: curl update, sources, metal, then (optionally) E/H + polarisations.
-template <class T, bool SIMPLE>
-__device__ __forceinline__ void update_point(const CompParams<T> &c, long long i, int ia, int ib,
-                                             int ic, const double *smp, int is_D, int cmp,
-                                             double dt) {
-  // ---------------- step_curl (step_generic.cpp:89-252) ----------------
-  T curl;
-  if (c.g2)
-    curl = (c.g1[i + c.s1] - c.g1[i] + c.g2[i] - c.g2[i + c.s2]);
-  else
-    curl = (c.g1[i + c.s1] - c.g1[i]);
-  T fnew;
-  if (SIMPLE) {
-    fnew = c.f[i] - c.dtdx * curl; // :108,112
-  }
-  else {
-      T fold = c.f[i];
-    if (c.kaxis < 0) {
-      if (c.kuaxis < 0) {
-        if (c.cnd) // :95,101
-          fnew = ((1 - c.dt2 * c.cnd[i]) * fold - c.dtdx * curl) * c.cndinv[i];
-        else
-          fnew = fold - c.dtdx * curl;
-      }
-      else { // :121-154
-        const int ku = 2 * pick3(c.kuaxis, ia, ib, ic) + c.kuoff;
-        T fprev = c.fu[i], fun;
-        if (c.cnd)
-          fun = ((1 - c.dt2 * c.cnd[i]) * fprev - c.dtdx * curl) * c.cndinv[i];
-        else
-          fun = fprev - c.dtdx * curl;
-        c.fu[i] = fun;
-        fnew = c.siginvu[ku] * ((c.kapu[ku] - c.sigu[ku]) * fold + fun - fprev);
-      }
-    }
-    else {
-      const int k = 2 * pick3(c.kaxis, ia, ib, ic) + c.koff;
-      if (c.kuaxis < 0) { // :164-196
-        if (c.cnd) {
-          T fcnd_prev = c.fcnd[i];
-          T fc = ((1 - c.dt2 * c.cnd[i]) * fcnd_prev - c.dtdx * curl) * c.cndinv[i];
-          c.fcnd[i] = fc;
-          fnew = ((c.kap[k] - c.sig[k]) * fold + (fc - fcnd_prev)) * c.siginv[k];
-        }
-        else
-          fnew = ((c.kap[k] - c.sig[k]) * fold - c.dtdx * curl) * c.siginv[k];
-      }
-      else { // :199-250
-        const int ku = 2 * pick3(c.kuaxis, ia, ib, ic) + c.kuoff;
-        T fprev = c.fu[i], fun;
-        if (c.cnd) {
-          T fcnd_prev = c.fcnd[i];
-          T fc = ((1 - c.dt2 * c.cnd[i]) * fcnd_prev - c.dtdx * curl) * c.cndinv[i];
-          c.fcnd[i] = fc;
-          fun = ((c.kap[k] - c.sig[k]) * fprev + (fc - fcnd_prev)) * c.siginv[k];
-        }
-        else
-          fun = ((c.kap[k] - c.sig[k]) * fprev - c.dtdx * curl) * c.siginv[k];
-        c.fu[i] = fun;
-        fnew = c.siginvu[ku] * ((c.kapu[ku] - c.sigu[ku]) * fold + fun - fprev);
-      }
-    }
-  }
-  // ---------------- step_source (step.cpp:296-319) ----------------
-  if (c.ncsrc && ia >= c.csrc_amin && ia <= c.csrc_amax) {
-    for (int j = src_lower_bound(c.csrc, c.ncsrc, i); j < c.ncsrc && c.csrc[j].idx == i; ++j) {
-      const SrcEntry e = c.csrc[j];
-      const double2 cur = sample_current(smp, e.tid, is_D);
-      double2 A = cmul(e.are, e.aim, cur.x, cur.y);
-      A.x = A.x * dt;
-      A.y = A.y * dt;
-      if (c.src_has_cndinv) {
-        const double ci = double(c.cndinv[i]);
-        A.x = A.x * ci;
-        A.y = A.y * ci;
-      }
-      fnew = (T)((double)fnew - (cmp ? A.y : A.x));
-    }
-  }
-  // ---------------- zero_metal(D/B) inside step_boundaries (boundaries.cpp:304-307) -------------
-  if (on_zero_plane<T>(c.zmask_db, c.lo, c.hi, ia, ib, ic)) fnew = 0;
-  c.f[i] = fnew;
-
-  // ---------------- update_eh (update_eh.cpp:122-283; step_generic.cpp:706-725,888-903) ---------
-  if (!c.e) return;
-  T fmp = fnew;
-  if (!SIMPLE) {
-#pragma unroll
-    for (int ip = 0; ip < kMaxPol; ++ip)
-      if (ip < c.npol && c.pol[ip].p) fmp -= c.pol[ip].p[i]; // subtract_P, susceptibility.cpp:264-281
-  }
-  if (c.nisrc && ia >= c.isrc_amin && ia <= c.isrc_amax) {
-    for (int j = src_lower_bound(c.isrc, c.nisrc, i); j < c.nisrc && c.isrc[j].idx == i; ++j) {
-      const SrcEntry e = c.isrc[j];
-      const double2 dp = sample_dipole(smp, e.tid, is_D);
-      const double2 A = cmul(e.are, e.aim, dp.x, dp.y);
-      fmp = (T)((double)fmp - (cmp ? A.y : A.x));
-    }
-  }
-  const T gu = c.u ? (fmp * c.u[i]) : fmp;
-  T enew, w;
-  if (!SIMPLE && c.fw) { // PML: step_generic.cpp:708-724
-      const int kw = 2 * pick3(c.kwaxis, ia, ib, ic) + c.kwoff;
-    const T fwprev = c.fw[i], kapwkw = c.kapw[kw], sigwkw = c.sigw[kw];
-    c.fw[i] = gu;
-    enew = c.e[i] + ((kapwkw + sigwkw) * gu - (kapwkw - sigwkw) * fwprev);
-    w = gu;
-  }
-  else {
-    enew = gu;
-    w = gu;
-  }
-  if (!SIMPLE) {
-    // update_pols runs before zero_metal(E) (step.cpp:109-122): it sees the un-zeroed W
-#pragma unroll
-    for (int ip = 0; ip < kMaxPol; ++ip)
-      if (ip < c.npol && c.pol[ip].p && c.pol[ip].s) { // susceptibility.cpp:252-259
-        const PolParams<T> &q = c.pol[ip];
-        const T pcur = q.p[i];
-        q.p[i] = q.gamma1inv * (pcur * (2 - q.omega0dtsqr_denom) - q.gamma1 * q.pp[i] +
-                                q.omega0dtsqr * (q.s[i] * w));
-        q.pp[i] = pcur;
-      }
-  }
-  if (on_zero_plane<T>(c.zmask_eh, c.lo, c.hi, ia, ib, ic)) enew = 0;
-  c.e[i] = enew;
-}
-
-template <class T, bool SIMPLE>
-__global__ void __launch_bounds__(kThreads)
-    k_half(const HalfParams<T> *__restrict__ params, const Tile *__restrict__ tiles,
-           const double *__restrict__ smp) {
-  __shared__ HalfParams<T> P;
-  const Tile t = tiles[blockIdx.x];
-  {
-    const int nw = (int)(sizeof(HalfParams<T>) / 4);
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(params + t.param);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(&P);
-    for (int k = threadIdx.x; k < nw; k += kThreads) dst[k] = src[k];
-  }
-  __syncthreads();
-  const int p = t.p0 + threadIdx.x;
-  const int ib = p / P.pitch, ic = p - ib * P.pitch;
-  if (ib >= P.nB || ic >= P.nC) return;
-  bool act[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const CompParams<T> &c = P.comp[k];
-    act[k] = c.f != nullptr && ib >= c.lo[1] && ib <= c.hi[1] && ic >= c.lo[2] && ic <= c.hi[2];
-  }
-  if (!(act[0] || act[1] || act[2])) return;
-  long long i = (long long)t.a0 * P.sA + (long long)ib * P.sB + ic;
-  for (int ia = t.a0; ia < t.a1; ++ia, i += P.sA) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const CompParams<T> &c = P.comp[k];
-      if (act[k] && ia >= c.lo[0] && ia <= c.hi[0])
-        update_point<T, SIMPLE>(c, i, ia, ib, ic, smp, P.is_D, P.cmp, P.dt);
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // k_halfg: the general fused half step (PML / conductivity / polarisations, any dimensionality).
-// Same per-point arithmetic as update_point<T,false>, restructured for memory-level parallelism:
+// Structured for memory-level parallelism:
 // every global load of the three components of a point is issued before the first dependent
 // instruction (two-phase gather -> compute/store), read-only arrays go through the read-only
 // path, and the CTA marches along the LONGER of the two outer axes so that thin PML slabs still
@@ -545,8 +386,8 @@ template <class T> struct HalfHeader { // leading, component-independent part of
   double dt;
 };
 
-template <class T, bool HAS_COND, bool HAS_POL, bool PIPE = false, bool HAS_BB = false>
-__global__ void __launch_bounds__(kThreads, (PIPE || HAS_COND) ? 2 : 3)
+template <class T, bool HAS_COND, bool HAS_POL, bool HAS_BB = false>
+__global__ void __launch_bounds__(kThreads, HAS_COND ? 2 : 3)
     k_halfg(const HalfParams<T> *__restrict__ params, const Tile *__restrict__ tiles,
             const double *__restrict__ smp) {
   __shared__ HalfHeader<T> H;
@@ -577,10 +418,8 @@ __global__ void __launch_bounds__(kThreads, (PIPE || HAS_COND) ? 2 : 3)
   long long i = (long long)m0 * s_m + (long long)io * s_o + ic;
   const int is_D = H.is_D, cmp = H.cmp;
   const double dt = H.dt;
-  PointVals<T, HAS_COND, HAS_POL, HAS_BB> v, vn;
-  if (PIPE && m0 <= m1) gather_point<T, HAS_COND, HAS_POL, HAS_BB>(c, Csm.pol, i, v);
 #pragma unroll 2
-  for (int im = m0; im <= m1; ++im, i += s_m, PIPE ? (void)(v = vn) : (void)0) {
+  for (int im = m0; im <= m1; ++im, i += s_m) {
     const int ia = march ? io : im, ib = march ? im : io;
     if (MCU_PREFETCH_PLANES > 0 && im + MCU_PREFETCH_PLANES <= m1) {
       const long long ipf = i + MCU_PREFETCH_PLANES * s_m;
@@ -607,17 +446,14 @@ __global__ void __launch_bounds__(kThreads, (PIPE || HAS_COND) ? 2 : 3)
         }
       }
     }
-    if (PIPE) { // operands of the next iteration first (see k_halfg_v)
-      if (im < m1) gather_point<T, HAS_COND, HAS_POL, HAS_BB>(c, Csm.pol, i + s_m, vn);
-    }
-    else
-      gather_point<T, HAS_COND, HAS_POL, HAS_BB>(c, Csm.pol, i, v);
+    PointVals<T, HAS_COND, HAS_POL, HAS_BB> v;
+    gather_point<T, HAS_COND, HAS_POL, HAS_BB>(c, Csm.pol, i, v);
     finish_point<T, HAS_COND, HAS_POL, HAS_BB>(c, Csm.pol, i, ia, ib, ic, v, smp, is_D, cmp, dt);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_curl3d: the interior fast path.  Same arithmetic as k_half<T,true>, specialised for 3-D chunks
+// k_curl3d: the interior fast path.  Same arithmetic as k_halfg, specialised for 3-D chunks
 // without PML / conductivity / polarisations (78 % of the cells of BASELINE config 2):
 //   * the step plan of a Cartesian 3-D chunk (src/fields.cpp:441-469) is hard-wired:
 //       f_k -= dtdx * ( g_{k+2}[i +- s_{k+1}] - g_{k+2}[i] + g_{k+1}[i] - g_{k+1}[i +- s_{k+2}] )
@@ -1058,10 +894,9 @@ template <class T> struct HalfgVals { // the operands of one thread-iteration of
       eo[VecOf<T>::V], fwo[VecOf<T>::V], uv[VecOf<T>::V];
 };
 
-// PIPE: software pipelining -- the operands of iteration n+1 are loaded into a second register set
-// before iteration n computes and stores (the compiler cannot move those loads above the stores
-// itself: nothing tells it that f, f_u, f_w and E do not alias the operand arrays).
-template <class T, bool HAS_POL, bool PIPE, class OnExit = NoExit>
+// (Software pipelining -- loading the operands of iteration n+1 into a second register set before
+// iteration n stores -- was measured and rejected: the registers cost a resident CTA, -4...-16 %.)
+template <class T, bool HAS_POL, class OnExit = NoExit>
 __device__ __forceinline__ void halfg_v_body(const HalfHeader<T> &H, const CompParams<T> &Csm, const Tile t,
                                              const OnExit on_exit = OnExit()) {
   constexpr int V = VecOf<T>::V;
@@ -1133,9 +968,8 @@ __device__ __forceinline__ void halfg_v_body(const HalfHeader<T> &H, const CompP
       }
     }
   };
-  HalfgVals<T> cur, nxt;
-  if (PIPE && m0 <= m1) gather(i, cur);
-  for (int im = m0; im <= m1; ++im, i += s_m, PIPE ? (void)(cur = nxt) : (void)0) {
+  HalfgVals<T> cur;
+  for (int im = m0; im <= m1; ++im, i += s_m) {
     const int ia = march ? io : im, ib = march ? im : io;
     if (var_k) load_coef<T, false>(c.sig, c.kap, c.siginv, c.kaxis, c.koff, ia, ib, ic, cA, cB);
     if (var_ku) load_coef<T, false>(c.sigu, c.kapu, c.siginvu, c.kuaxis, c.kuoff, ia, ib, ic, uA, uB);
@@ -1165,8 +999,7 @@ __device__ __forceinline__ void halfg_v_body(const HalfHeader<T> &H, const CompP
       }
     }
     // ---------------- gather ----------------
-    if (PIPE) { if (im < m1) gather(i + s_m, nxt); }
-    else gather(i, cur);
+    gather(i, cur);
     T *const g1 = cur.g1, *const g1p = cur.g1p, *const g2 = cur.g2, *const g2p = cur.g2p, *const fo = cur.fo,
              *const fuo = cur.fuo, *const eo = cur.eo, *const fwo = cur.fwo, *const uv = cur.uv;
     // ---------------- step_curl per element (step_generic.cpp:89-252) ----------------
@@ -1270,8 +1103,8 @@ __device__ __forceinline__ void halfg_v_body(const HalfHeader<T> &H, const CompP
   on_exit();
 }
 
-template <class T, bool HAS_POL, bool PIPE>
-__global__ void __launch_bounds__(kThreads, (sizeof(T) == 8 || PIPE) ? 2 : 3)
+template <class T, bool HAS_POL>
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : 3)
     k_halfg_v(const HalfParams<T> *__restrict__ params, const Tile *__restrict__ tiles) {
   __shared__ HalfHeader<T> H;
   __shared__ CompParams<T> Csm;
@@ -1280,7 +1113,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 8 || PIPE) ? 2 : 3)
   block_copy_params(&H, reinterpret_cast<const HalfHeader<T> *>(params + pidx));
   block_copy_params(&Csm, &params[pidx].comp[kcomp]);
   __syncthreads();
-  halfg_v_body<T, HAS_POL, PIPE>(H, Csm, t);
+  halfg_v_body<T, HAS_POL>(H, Csm, t);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1371,7 +1204,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : MCU_MIX_F32_CTA
     block_copy_params(&g->H, reinterpret_cast<const HalfHeader<T> *>(hparams + pidx));
     block_copy_params(&g->C, &hparams[pidx].comp[kcomp]);
     __syncthreads();
-    halfg_v_body<T, false, false>(g->H, g->C, t);
+    halfg_v_body<T, false>(g->H, g->C, t);
   }
   else {
     Curl3DParams<T> *P = reinterpret_cast<Curl3DParams<T> *>(raw);

@@ -2065,7 +2065,6 @@ template <class T> struct Ctx : CtxBase {
   //   part 0: all tiles;  1: boundary tiles only (the first nb_* of each list);  2: the rest
   // sm: stream of the interior tiles; sside: stream of the PML / special tiles (== sm: no fork)
   int launch_compute(int half, const double *smp, int part, cudaStream_t sm, cudaStream_t sside) {
-    static const bool pipe_pml = getenv("MEEPCU_PIPE") != 0;
     // The interior tiles (k_curl3d) and the PML / general tiles (k_halfg) of one half step touch
     // disjoint chunks, so they run side by side on two streams; everything else is ordered after
     // both.  While profiling they are serialised so that each kernel's event time is its own.
@@ -2114,13 +2113,11 @@ template <class T> struct Ctx : CtxBase {
     if (n_gv0 || n_t0) {
       RC(prof_begin(half ? KC_HALF_D_SIMPLE : KC_HALF_B_SIMPLE));
       if (n_gv0) {
-        if (pipe_pml) k_halfg_v<T, false, true><<<n_gv0, kThreads, 0, sg>>>(d_half, d_gv_tiles[half][0] + o_gv0);
-        else k_halfg_v<T, false, false><<<n_gv0, kThreads, 0, sg>>>(d_half, d_gv_tiles[half][0] + o_gv0);
+        k_halfg_v<T, false><<<n_gv0, kThreads, 0, sg>>>(d_half, d_gv_tiles[half][0] + o_gv0);
         launches++;
       }
       if (n_t0) {
-        if (pipe_pml) k_halfg<T, false, false, true><<<n_t0, kThreads, 0, sg>>>(d_half, d_tiles[half][0] + o_t0, smp);
-        else k_halfg<T, false, false><<<n_t0, kThreads, 0, sg>>>(d_half, d_tiles[half][0] + o_t0, smp);
+        k_halfg<T, false, false><<<n_t0, kThreads, 0, sg>>>(d_half, d_tiles[half][0] + o_t0, smp);
         launches++;
       }
       RC(prof_end());
@@ -2128,8 +2125,7 @@ template <class T> struct Ctx : CtxBase {
     if (n_gv1 || n_t1 || n_t2 || n_t3) {
       RC(prof_begin(half ? KC_HALF_D_GENERAL : KC_HALF_B_GENERAL));
       if (n_gv1) {
-        if (pipe_pml) k_halfg_v<T, true, true><<<n_gv1, kThreads, 0, sg>>>(d_half, d_gv_tiles[half][1] + o_gv1);
-        else k_halfg_v<T, true, false><<<n_gv1, kThreads, 0, sg>>>(d_half, d_gv_tiles[half][1] + o_gv1);
+        k_halfg_v<T, true><<<n_gv1, kThreads, 0, sg>>>(d_half, d_gv_tiles[half][1] + o_gv1);
         launches++;
       }
       if (n_t1) {
@@ -2141,7 +2137,7 @@ template <class T> struct Ctx : CtxBase {
         launches++;
       }
       if (n_t3) {
-        k_halfg<T, true, true, false, true><<<n_t3, kThreads, 0, sg>>>(d_half, d_tiles[half][3] + o_t3, smp);
+        k_halfg<T, true, true, true><<<n_t3, kThreads, 0, sg>>>(d_half, d_tiles[half][3] + o_t3, smp);
         launches++;
       }
       RC(prof_end());
