@@ -228,10 +228,19 @@ def run_reference_cpu(args, steps, warmup):
                             str(warmup), "--json", tf.name], check=True, env=env, stdout=subprocess.DEVNULL,
                            stderr=subprocess.DEVNULL, timeout=3000)
             d = json.load(open(tf.name))
+        one = None
+        if getattr(args, "cpu_one_thread", False):  # the reference's own default is ONE thread (mympi.cpp:187-192)
+            with tempfile.NamedTemporaryFile(suffix=".json") as tf:
+                env1 = dict(os.environ, OMP_NUM_THREADS="1")
+                subprocess.run([drv, "--mode", "ref", "--case", case, "--steps", str(max(2, steps // 4)), "--warmup", "1",
+                                "--json", tf.name], check=True, env=env1, stdout=subprocess.DEVNULL,
+                               stderr=subprocess.DEVNULL, timeout=3000)
+                one = json.load(open(tf.name))["mcells_per_s"]
         dd = dims(args, n)
         scale = "the full problem" if n == args.n else "the same problem at %dx%dx%d (the GPU arm runs %s)" % (
             dd[0], dd[1], dd[2], workload_name(args))
         return d["mcells_per_s"], {"kind": "reference", "cores": d["threads"], "cells": dd[0] * dd[1] * dd[2],
+                                   "one_thread_value": one,
                                    "sample": "%d warm-up + %d timed fields::step() of %s, case %s "
                                              "(unmodified reference core, OpenMP, %d threads)"
                                              % (warmup, steps, scale, case, d["threads"])}
@@ -407,6 +416,7 @@ def main_ours(args):
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(st1.kernel_launches - st0.kernel_launches),
             "roofline": roof}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        args.cpu_one_thread = True
         r = run_reference_cpu(args, args.cpu_steps, 3)
         if r is not None:
             line["cpu_baseline"] = dict(r[1], value=r[0], unit="Mcell/s")
