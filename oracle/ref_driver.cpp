@@ -126,6 +126,9 @@ struct problem {
   fields *f;
   material_function *mat;
   std::vector<dft_flux> fluxes;
+  std::vector<dft_fields> dftfields;
+  std::vector<dft_energy> energies;
+  std::vector<dft_near2far> n2fs;
   long cells;
   problem() : s(0), f(0), mat(0), cells(0) {}
   ~problem() {
@@ -309,6 +312,36 @@ static problem *build(const std::string &spec, int nchunks) {
     p->f->use_real_fields();
     p->f->add_point_source(Ez, 0.15, 0.1, 0.0, 4.0, vec(L / 2 + 0.22 * L, L / 2, L / 2), 1.0);
     p->f->add_point_source(Ex, 0.2, 0.1, 0.0, 4.0, vec(L / 2, L / 2 + 0.2 * L, L / 2), 0.7);
+  }
+  else if (name == "dft2d" || name == "dft3d") { // every flavour of dft_chunk (src/dft.cpp:57-129): flux with
+    // decimation 1 and auto, dft_fields on the centred grid (avg1/avg2 offsets), dft_energy (D and B
+    // components), near2far (sqrt weights off, different components); complex fields with a Bloch phase
+    const bool d3 = name == "dft3d";
+    if (!n) n = d3 ? 14 : 40;
+    const double L = n / a;
+    p->gv = d3 ? vol3d(L, L, L, a) : vol2d(L, 0.8 * L, a);
+    g_slab_lo = 0.3 * L;
+    g_slab_hi = 0.5 * L;
+    g_slab_eps = 5.0;
+    p->s = new structure(p->gv, d3 ? slab_eps_z : slab_eps_y, pml(0.1 * L > 0.6 ? 0.6 : 0.1 * L, d3 ? Z : Y), identity(), nchunks, 0.5, false);
+    p->f = new fields(p->s);
+    p->f->use_bloch(X, 0.13);
+    if (d3) p->f->use_bloch(Y, 0.0);
+    p->f->add_point_source(d3 ? Ex : Ez, 0.3, 0.25, 0.0, 4.0, p->gv.center(), 1.0);
+    p->f->add_point_source(Hz, 0.25, 0.25, 0.0, 4.0, p->gv.center(), 0.5);
+    const double lo = 0.2 * L, hi = 0.7 * L;
+    volume plane = d3 ? volume(vec(lo, lo, 0.6 * L), vec(hi, hi, 0.6 * L)) : volume(vec(lo, 0.55 * L), vec(hi, 0.55 * L));
+    volume box = d3 ? volume(vec(lo, lo, lo), vec(hi, hi, hi)) : volume(vec(lo, 0.25 * L), vec(hi, 0.6 * L));
+    p->fluxes.push_back(p->f->add_dft_flux(d3 ? Z : Y, plane, 0.2, 0.4, 5, true, true, 1));
+    p->fluxes.push_back(p->f->add_dft_flux(d3 ? Z : Y, plane, 0.2, 0.4, 3, true, false, 0));
+    component cs[3] = {d3 ? Ex : Ez, Hz, d3 ? Ey : Ex};
+    p->dftfields.push_back(p->f->add_dft_fields(cs, 3, box, 0.25, 0.35, 4, true, 2));
+    p->dftfields.push_back(p->f->add_dft_fields(cs, 2, box, 0.25, 0.35, 2, false, 1));
+    volume_list vl(plane, Sx);
+    (void)vl;
+    volume_list *wl = new volume_list(box, NO_COMPONENT);
+    p->energies.push_back(p->f->add_dft_energy(wl, 0.2, 0.4, 3, 1));
+    delete wl;
   }
   else if (name == "phc3d") { // BASELINE config 5 shape: slab, PML in z, Bloch-periodic x,y, fp32-able
     if (!n) n = 16;

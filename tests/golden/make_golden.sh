@@ -42,6 +42,8 @@ for fl in fp64 fp32; do
   gen $fl cond3d:10 40 2
   gen $fl cond2d 40 2
   gen $fl aniso3d:12 40 2
+  gen $fl dft2d:24 40 2
+  gen $fl dft3d:12 40 2
   gen $fl beta2d_cplx 40 2
 done
 gen fp64 nr3d:10 30 0

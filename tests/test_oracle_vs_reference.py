@@ -21,6 +21,9 @@ CASES = [("fp64", "vac3d:24", 25, 2), ("fp64", "kr_per3d_rods", 40, 0), ("fp64",
          ("fp64", "cond3d", 60, 2), ("fp32", "cond3d", 60, 2), ("fp64", "cond2d", 80, 2),
          # anisotropic Lorentzian sigma: the 3x3 and 2x2 branches of update_P (susceptibility.cpp:225-251)
          ("fp64", "aniso3d", 60, 2), ("fp32", "aniso3d", 60, 2),
+         # every flavour of dft_chunk: flux (decimation 1 / auto), dft_fields on the centred grid, dft_energy (D, B),
+         # complex fields with a Bloch phase
+         ("fp64", "dft2d", 60, 2), ("fp32", "dft2d", 60, 2), ("fp64", "dft3d", 60, 2), ("fp32", "dft3d", 60, 2),
          # UPSTREAM_PADE against the de-blocked reference flavour (oracle/deblock_pade.py)
          ("fp64_pade", "kerr3d:14", 40, 2), ("fp64_pade", "kerr1d", 80, 0), ("fp64_pade", "kr_per3d_rods", 40, 0)]
 
