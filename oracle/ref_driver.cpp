@@ -45,6 +45,10 @@ static double sigma763(const vec &) { return 7.63; }
 static double wvg_eps_small(const vec &p) { return fabs(p.y() - 2.0) < 0.5 ? 6.0 : 1.0; }
 static double slab_eps_y(const vec &p) { return (p.y() > g_slab_lo && p.y() < g_slab_hi) ? g_slab_eps : 1.0; }
 static double cond_fn(const vec &p) { return 0.3 + 0.2 * p.x(); }
+static double slab_mu_y(const vec &p) { return (p.y() > g_slab_lo && p.y() < g_slab_hi) ? 1.5 : 1.0; }
+static double slab_mu_z(const vec &p) { return (p.z() > g_slab_lo && p.z() < g_slab_hi) ? 1.5 : 1.0; }
+static double slab_mask_y(const vec &p) { return (p.y() > g_slab_lo && p.y() < g_slab_hi) ? 1.0 : 0.0; }
+static double slab_mask_z(const vec &p) { return (p.z() > g_slab_lo && p.z() < g_slab_hi) ? 1.0 : 0.0; }
 static double slab_eps_z(const vec &p) { return (p.z() > g_slab_lo && p.z() < g_slab_hi) ? g_slab_eps : 1.0; }
 static double ring_eps(const vec &p);
 static double ring_sigma(const vec &p);
@@ -342,6 +346,24 @@ static problem *build(const std::string &spec, int nchunks) {
     volume_list *wl = new volume_list(box, NO_COMPONENT);
     p->energies.push_back(p->f->add_dft_energy(wl, 0.2, 0.4, 3, 1));
     delete wl;
+  }
+  else if (name == "magdrude3d" || name == "magdrude2d") { // mu != 1 (H split from B, chi1inv for H), a magnetic
+    // Lorentzian (pol[H_stuff]) and an electric Drude term (no_omega_0_denominator), PML around
+    const bool d3 = name == "magdrude3d";
+    if (!n) n = d3 ? 14 : 30;
+    const double L = n / a;
+    p->gv = d3 ? vol3d(L, L, L, a) : vol2d(L, L, a);
+    g_slab_lo = 0.35 * L;
+    g_slab_hi = 0.65 * L;
+    g_slab_eps = 2.5;
+    p->s = new structure(p->gv, d3 ? slab_eps_z : slab_eps_y, pml(0.1 * L > 0.5 ? 0.5 : 0.1 * L), identity(), nchunks, 0.5, false);
+    p->s->set_mu(d3 ? slab_mu_z : slab_mu_y, false);
+    p->s->add_susceptibility(d3 ? slab_mask_z : slab_mask_y, H_stuff, lorentzian_susceptibility(0.9, 1e-3));
+    p->s->add_susceptibility(d3 ? slab_mask_z : slab_mask_y, E_stuff, lorentzian_susceptibility(0.4, 0.05, true));
+    p->f = new fields(p->s);
+    p->f->use_real_fields();
+    p->f->add_point_source(Ez, 0.3, 0.25, 0.0, 4.0, p->gv.center(), 1.0);
+    p->f->add_point_source(d3 ? Hy : Hz, 0.25, 0.25, 0.0, 4.0, p->gv.center(), 0.5);
   }
   else if (name == "phc3d") { // BASELINE config 5 shape: slab, PML in z, Bloch-periodic x,y, fp32-able
     if (!n) n = 16;
