@@ -78,3 +78,21 @@ def test_synchronize_magnetic_fields_on_device(flavour, case, steps, tol):
         d = json.load(open(tf.name))
     assert d["backend"] == "cuda-sm_100a" and d["sync_checks"] >= 5
     assert d["sync_rel_l2"] <= tol and d["rel_l2"] <= tol, d
+
+
+@pytest.mark.parametrize("flavour,case,chunks,tol", [("fp64", "vac3d:48", 4, 1e-12), ("fp32", "lorentz3d:32", 3, 1e-5),
+                                                     ("fp64", "nrslab3d:20", 3, 1e-12), ("fp64", "aniso3d:24", 5, 1e-12),
+                                                     ("fp64", "dft3d:24", 3, 1e-12)])
+def test_reference_chunk_splitting_on_gpu(flavour, case, chunks, tol):
+    """the reference's own cost-based chunk splitting (structure(..., num_chunks)): 40-50 chunks instead of 27"""
+    drv = ref_driver(flavour)
+    if drv is None:
+        pytest.skip("oracle/_ref/%s not present on this machine" % flavour)
+    with tempfile.NamedTemporaryFile(suffix=".json") as tf:
+        env = dict(os.environ, OMP_NUM_THREADS="8")
+        subprocess.run([drv, "--mode", "shim", "--lib", CUDA_LIB, "--case", case, "--chunks", str(chunks), "--steps", "60",
+                        "--warmup", "2", "--json", tf.name], check=True, env=env,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+        d = json.load(open(tf.name))
+    assert d["backend"] == "cuda-sm_100a" and d["num_chunks"] > chunks and d["finite"] == 1
+    assert d["rel_l2"] <= tol, d

@@ -84,3 +84,20 @@ def test_synchronize_magnetic_fields_equals_reference(flavour, case, steps):
         d = json.load(open(tf.name))
     assert d["sync_checks"] >= 4 and d["sync_mismatched_elements"] == 0
     assert d["arrays"] > 0 and d["mismatched_elements"] == 0
+
+
+@pytest.mark.parametrize("flavour,case,chunks", [("fp64", "vac3d:32", 5), ("fp64", "lorentz3d:16", 4), ("fp32", "wvg2d", 6),
+                                                 ("fp64", "nrslab3d:14", 3), ("fp64", "aniso3d:14", 3)])
+def test_reference_chunk_splitting(flavour, case, chunks):
+    """structure(..., num_chunks) lets the reference split the cell by cost into many more chunks (40-50):
+    the description the shim hands over changes completely, the fields must not"""
+    drv = ref_driver(flavour)
+    if drv is None:
+        pytest.skip("oracle/_ref/%s not built (reference tree absent)" % flavour)
+    with tempfile.NamedTemporaryFile(suffix=".json") as tf:
+        env = dict(os.environ, OMP_NUM_THREADS="4")
+        subprocess.run([drv, "--mode", "shim", "--lib", ORACLE_LIB, "--case", case, "--chunks", str(chunks), "--steps", "40",
+                        "--warmup", "2", "--json", tf.name], check=True, env=env,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+        d = json.load(open(tf.name))
+    assert d["num_chunks"] > chunks and d["arrays"] > 0 and d["mismatched_elements"] == 0, d
