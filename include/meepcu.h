@@ -116,6 +116,20 @@ typedef struct {
   int reserved[8];
 } meepcu_susceptibility_desc;
 
+/* gyrotropic_susceptibility (src/susceptibility.cpp:350-603, src/meep.hpp:300-338): three polarisation
+ * components on EACH driving-field position (gyrotropy_data: P[c][cmp][X..Z], P_prev likewise). */
+enum { MEEPCU_GYROTROPIC_LORENTZIAN = 0, MEEPCU_GYROTROPIC_DRUDE = 1, MEEPCU_GYROTROPIC_SATURATED = 2 };
+typedef struct {
+  int ft;                     /* MEEPCU_E_STUFF or MEEPCU_H_STUFF */
+  int model;                  /* MEEPCU_GYROTROPIC_* (gyrotropy_model) */
+  double omega_0, gamma, alpha;
+  double gyro_tensor[3][3];   /* gyrotropic_susceptibility::gyro_tensor, as stored (realnum) */
+  const void *sigma[MEEPCU_NUM_COMPONENTS][5];  /* susceptibility::sigma[c][d] */
+  void *P[MEEPCU_NUM_COMPONENTS][2][3];         /* gyrotropy_data::P (NULL: needs_P() false here) */
+  void *P_prev[MEEPCU_NUM_COMPONENTS][2][3];    /* gyrotropy_data::P_prev */
+  int reserved[8];
+} meepcu_gyrotropic_desc;
+
 /* src_vol (src/meep_internals.hpp:49-82) attached to fields_chunk::sources[ft]. */
 typedef struct {
   int ft;            /* MEEPCU_D_STUFF or MEEPCU_B_STUFF: which sources[] list it is in */
@@ -163,6 +177,9 @@ int meepcu_destroy(meepcu_ctx *ctx);
 /* ---- description of the problem (called once, or again after the host re-allocates) ------ */
 int meepcu_add_chunk(meepcu_ctx *ctx, const meepcu_chunk_desc *desc, int *chunk_id);
 int meepcu_add_susceptibility(meepcu_ctx *ctx, int chunk_id, const meepcu_susceptibility_desc *desc);
+/* polarisations are updated / subtracted in the order they were added (Lorentzian and gyrotropic alike),
+ * like the reference's polarization_state list (update_eh.cpp:130-131, update_pols.cpp:46) */
+int meepcu_add_gyrotropic(meepcu_ctx *ctx, int chunk_id, const meepcu_gyrotropic_desc *desc);
 int meepcu_add_source(meepcu_ctx *ctx, int chunk_id, const meepcu_source_desc *desc);
 int meepcu_add_dft(meepcu_ctx *ctx, int chunk_id, const meepcu_dft_desc *desc, int *dft_id);
 

@@ -54,6 +54,13 @@ class SusceptibilityDesc(C.Structure):
                 ("P_prev", (vp * 2) * NUM_COMPONENTS), ("reserved", C.c_int * 8)]
 
 
+class GyrotropicDesc(C.Structure):
+    _fields_ = [("ft", C.c_int), ("model", C.c_int), ("omega_0", C.c_double), ("gamma", C.c_double),
+                ("alpha", C.c_double), ("gyro_tensor", (C.c_double * 3) * 3), ("sigma", (vp * 5) * NUM_COMPONENTS),
+                ("P", ((vp * 3) * 2) * NUM_COMPONENTS), ("P_prev", ((vp * 3) * 2) * NUM_COMPONENTS),
+                ("reserved", C.c_int * 8)]
+
+
 class SourceDesc(C.Structure):
     _fields_ = [("ft", C.c_int), ("c", C.c_int), ("src_time_id", C.c_int),
                 ("is_integrated", C.c_int), ("n", C.c_size_t), ("index", vp), ("amp", vp)]
@@ -95,6 +102,7 @@ _PROTOTYPES = [
     ("meepcu_destroy", C.c_int, [vp]),
     ("meepcu_add_chunk", C.c_int, [vp, C.POINTER(ChunkDesc), C.POINTER(C.c_int)]),
     ("meepcu_add_susceptibility", C.c_int, [vp, C.c_int, C.POINTER(SusceptibilityDesc)]),
+    ("meepcu_add_gyrotropic", C.c_int, [vp, C.c_int, C.POINTER(GyrotropicDesc)]),
     ("meepcu_add_source", C.c_int, [vp, C.c_int, C.POINTER(SourceDesc)]),
     ("meepcu_add_dft", C.c_int, [vp, C.c_int, C.POINTER(DftDesc), C.POINTER(C.c_int)]),
     ("meepcu_set_metal", C.c_int, [vp, C.c_int, C.c_size_t, vp]),

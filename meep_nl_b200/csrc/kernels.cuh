@@ -1680,6 +1680,74 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// gyrotropic_susceptibility::update_P (susceptibility.cpp:445-584): three polarisation components
+// on each driving-field position, coupled by the skew-symmetric gyration tensor; the two transverse
+// ones are driven by four-point averages of the other W components, so (like k_pol_general) this is
+// its own pass after the chunk's E (H) update and the W halo exchange.
+// ------------------------------------------------------------------------------------------------
+template <class T> struct PolGyroParams {
+  int nA, nB, nC, pitch;
+  long long sA, sB;
+  int lo[3], hi[3];
+  T *p0, *pp0, *p1, *pp1, *p2, *pp2; // P / P_prev along d0 = direction of the component, d1, d2
+  const T *s, *w0, *w1, *w2;
+  long long is, is1, is2;
+  int saturated;                      // GYROTROPIC_SATURATED (Landau-Lifshitz-Gilbert) or Lorentzian / Drude
+  T g01, g02, g10, g12, g20, g21;     // gyro_tensor[d_a][d_b]
+  T inv[3][3];                        // inv[d_a][d_b], a, b in (d0, d1, d2) order
+  T diag, gamma1, omega0dtsqr, pt;    // Lorentzian / Drude constants (:456-461)
+  T omega2pidt, g2pidt, alpha, dt2pi; // saturated-model constants (:531, :449-450)
+};
+
+#define MCU_OFFDIAGW(g, sx, s) (0.25 * (g[i] + g[i - sx] + g[i + s] + g[i + s - sx]))
+
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+    k_pol_gyro(const PolGyroParams<T> *__restrict__ params, const Tile *__restrict__ tiles) {
+  __shared__ PolGyroParams<T> P;
+  const Tile t = tiles[blockIdx.x];
+  block_copy_params(&P, params + t.param);
+  __syncthreads();
+  const int pos = t.p0 + threadIdx.x;
+  const int ib = pos / P.pitch, ic = pos - ib * P.pitch;
+  if (ib < P.lo[1] || ib > P.hi[1] || ic < P.lo[2] || ic > P.hi[2]) return;
+  const int a0 = t.a0 > P.lo[0] ? t.a0 : P.lo[0];
+  const int a1 = t.a1 - 1 < P.hi[0] ? t.a1 - 1 : P.hi[0];
+  T *p0 = P.p0, *pp0 = P.pp0, *p1 = P.p1, *pp1 = P.pp1, *p2 = P.p2, *pp2 = P.pp2;
+  const T *s = P.s, *w0 = P.w0, *w1 = P.w1, *w2 = P.w2;
+  const long long is = P.is, is1 = P.is1, is2 = P.is2;
+  const T g01 = P.g01, g02 = P.g02, g10 = P.g10, g12 = P.g12, g20 = P.g20, g21 = P.g21;
+  const T diag = P.diag, gamma1 = P.gamma1, omega0dtsqr = P.omega0dtsqr, pt = P.pt;
+  const T omega2pidt = P.omega2pidt, g2pidt = P.g2pidt, alpha = P.alpha, dt2pi = P.dt2pi;
+  long long i = (long long)a0 * P.sA + (long long)ib * P.sB + ic;
+  for (int ia = a0; ia <= a1; ++ia, i += P.sA) {
+    T r0, r1, r2;
+    if (!P.saturated) { // :484-491
+      r0 = diag * p0[i] - gamma1 * pp0[i] + omega0dtsqr * s[i] * w0[i] - pt * g01 * pp1[i] - pt * g02 * pp2[i];
+      r1 = diag * p1[i] - gamma1 * pp1[i] + (w1 ? omega0dtsqr * s[i] * MCU_OFFDIAGW(w1, is1, is) : 0) -
+           pt * g10 * pp0[i] - pt * g12 * pp2[i];
+      r2 = diag * p2[i] - gamma1 * pp2[i] + (w2 ? omega0dtsqr * s[i] * MCU_OFFDIAGW(w2, is2, is) : 0) -
+           pt * g21 * pp1[i] - pt * g20 * pp0[i];
+    }
+    else { // :560-571
+      T q0, q1, q2;
+      q0 = -omega2pidt * p0[i] + 0.5 * alpha * pp0[i] + dt2pi * s[i] * w0[i];
+      q1 = -omega2pidt * p1[i] + 0.5 * alpha * pp1[i] + dt2pi * s[i] * (w1 ? MCU_OFFDIAGW(w1, is1, is) : 0);
+      q2 = -omega2pidt * p2[i] + 0.5 * alpha * pp2[i] + dt2pi * s[i] * (w2 ? MCU_OFFDIAGW(w2, is2, is) : 0);
+      r0 = 0.5 * pp0[i] - g2pidt * p0[i] + g01 * q1 + g02 * q2;
+      r1 = 0.5 * pp1[i] - g2pidt * p1[i] + g12 * q2 + g10 * q0;
+      r2 = 0.5 * pp2[i] - g2pidt * p2[i] + g20 * q0 + g21 * q1;
+    }
+    pp0[i] = p0[i];
+    pp1[i] = p1[i];
+    pp2[i] = p2[i];
+    p0[i] = P.inv[0][0] * r0 + P.inv[0][1] * r1 + P.inv[0][2] * r2;
+    p1[i] = P.inv[1][0] * r0 + P.inv[1][1] * r1 + P.inv[1][2] * r2;
+    p2[i] = P.inv[2][0] * r0 + P.inv[2][1] * r1 + P.inv[2][2] * r2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // dft_chunk::update_dft (dft.cpp:265-307).  One thread per (point, omega) element of dft[] so the
 // read-modify-write of the accumulator -- the dominant traffic -- is fully coalesced.
 // ------------------------------------------------------------------------------------------------

@@ -179,7 +179,9 @@ struct Geom { // device layout of one chunk
 };
 
 struct SuscH {
-  meepcu_susceptibility_desc d;
+  meepcu_susceptibility_desc d; // gyrotropic: sigma, and P/P_prev = the component subtract_P uses (P[c][cmp][dir(c)])
+  bool gyro;
+  meepcu_gyrotropic_desc g;
 };
 struct SrcH {
   int ft, c, tid, integrated;
@@ -214,6 +216,7 @@ struct CtxBase {
   virtual ~CtxBase() {}
   virtual int add_chunk(const meepcu_chunk_desc *d, int *id) = 0;
   virtual int add_susc(int chunk, const meepcu_susceptibility_desc *d) = 0;
+  virtual int add_gyro(int chunk, const meepcu_gyrotropic_desc *d) = 0;
   virtual int add_source(int chunk, const meepcu_source_desc *d) = 0;
   virtual int add_dft(int chunk, const meepcu_dft_desc *d, int *id) = 0;
   virtual int set_metal(int ft, size_t n, void *const *ptrs) = 0;
@@ -319,8 +322,14 @@ template <class T> struct Ctx : CtxBase {
   // appears in no curl): copied only when the host mirror is refreshed, like the B/D/P halos
   ConnRun<T> *d_runs_def[MEEPCU_NUM_FIELD_TYPES];
   int n_runs_def[MEEPCU_NUM_FIELD_TYPES];
+  T **d_zero_late[2];                 // zero_metal(E/H) of chunks whose polarisations update in their own pass
+  long long n_zero_late[2];
   T **d_zero[MEEPCU_NUM_FIELD_TYPES]; // unfused metal lists (only non-plane lists; normally empty)
   long long n_zero[MEEPCU_NUM_FIELD_TYPES];
+  PolGyroParams<T> *d_polgyro;     // gyrotropic polarisation updates (k_pol_gyro)
+  std::vector<PolGyroParams<T> > h_polgyro;
+  Tile *d_polgyro_tiles[2];
+  int n_polgyro_tiles[2];
   PolGenParams<T> *d_polgen;       // anisotropic-sigma polarisation updates (k_pol_general)
   std::vector<PolGenParams<T> > h_polgen;
   Tile *d_polgen_tiles[2];
@@ -350,7 +359,7 @@ template <class T> struct Ctx : CtxBase {
   struct MagArr { char *dev; size_t bytes, off; bool is_f, is_pol; };
   std::vector<MagArr> mag_arrays; // B and H arrays with their f_u, f_w, f_cond, f_bfast (+ magnetic P, P_prev)
   char *mag_backup;
-  bool mag_synced;
+  bool mag_synced, in_mag_sync;
 
   int64_t launches, steps_done, cells, alg_bytes;
   double last_ms;
@@ -374,7 +383,7 @@ template <class T> struct Ctx : CtxBase {
     stage[0] = stage[1] = 0;
     dstage = 0;
     mag_backup = 0;
-    mag_synced = false;
+    mag_synced = in_mag_sync = false;
     stage_next = 0;
     comm = 0;
     my_rank = 0;
@@ -413,6 +422,11 @@ template <class T> struct Ctx : CtxBase {
     memset(n_runs, 0, sizeof n_runs);
     memset(d_runs_def, 0, sizeof d_runs_def);
     memset(n_runs_def, 0, sizeof n_runs_def);
+    memset(d_zero_late, 0, sizeof d_zero_late);
+    memset(n_zero_late, 0, sizeof n_zero_late);
+    d_polgyro = 0;
+    memset(d_polgyro_tiles, 0, sizeof d_polgyro_tiles);
+    memset(n_polgyro_tiles, 0, sizeof n_polgyro_tiles);
     d_polgen = 0;
     memset(d_polgen_tiles, 0, sizeof d_polgen_tiles);
     memset(n_polgen_tiles, 0, sizeof n_polgen_tiles);
@@ -536,7 +550,34 @@ template <class T> struct Ctx : CtxBase {
     if (d->ft != MEEPCU_E_STUFF && d->ft != MEEPCU_H_STUFF)
       return fail(MEEPCU_EINVAL, "susceptibility ft must be E_stuff or H_stuff");
     SuscH s;
+    memset(&s, 0, sizeof s);
     s.d = *d;
+    chunks[chunk].pol[d->ft].push_back(s);
+    if (chunks[chunk].pol[d->ft].size() > (size_t)kMaxPol)
+      return fail(MEEPCU_EUNSUPPORTED, "more than %d susceptibilities per chunk and field type", kMaxPol);
+    return MEEPCU_OK;
+  }
+  int add_gyro(int chunk, const meepcu_gyrotropic_desc *d) {
+    if (finalized) return fail(MEEPCU_ESTATE, "context already finalized");
+    if (chunk < 0 || chunk >= (int)chunks.size()) return fail(MEEPCU_EINVAL, "bad chunk id");
+    if (d->ft != MEEPCU_E_STUFF && d->ft != MEEPCU_H_STUFF)
+      return fail(MEEPCU_EINVAL, "susceptibility ft must be E_stuff or H_stuff");
+    if (d->model < 0 || d->model > 2) return fail(MEEPCU_EINVAL, "bad gyrotropy model");
+    if (cfg.dim != MEEPCU_D3) return fail(MEEPCU_EINVAL, "gyrotropic media require 3D Cartesian fields");
+    SuscH s;
+    memset(&s, 0, sizeof s);
+    s.gyro = true;
+    s.g = *d;
+    s.d.ft = d->ft;
+    for (int c = 0; c < 20; ++c) {
+      for (int k = 0; k < 5; ++k) s.d.sigma[c][k] = d->sigma[c][k];
+      const int d0 = comp_dir(c);
+      if (d0 < MEEPCU_R)
+        for (int cmp = 0; cmp < 2; ++cmp) { // subtract_P uses P[ec][cmp][component_direction(ec)] (:586-603)
+          s.d.P[c][cmp] = d->P[c][cmp][d0];
+          s.d.P_prev[c][cmp] = d->P_prev[c][cmp][d0];
+        }
+    }
     chunks[chunk].pol[d->ft].push_back(s);
     if (chunks[chunk].pol[d->ft].size() > (size_t)kMaxPol)
       return fail(MEEPCU_EUNSUPPORTED, "more than %d susceptibilities per chunk and field type", kMaxPol);
@@ -1033,6 +1074,11 @@ template <class T> struct Ctx : CtxBase {
                 return fail(MEEPCU_EINVAL, "P and P_prev must both be given");
               RC(reg(sd.P[c][cmp], (int)ic, A_GRID, nh, nd, true, false, MEEPCU_SYNC_POL));
               RC(reg(sd.P_prev[c][cmp], (int)ic, A_GRID, nh, nd, true, false, MEEPCU_SYNC_POL));
+              if (ch.pol[k][ip].gyro)
+                for (int dd = 0; dd < 3; ++dd) {
+                  RC(reg(ch.pol[k][ip].g.P[c][cmp][dd], (int)ic, A_GRID, nh, nd, true, false, MEEPCU_SYNC_POL));
+                  RC(reg(ch.pol[k][ip].g.P_prev[c][cmp][dd], (int)ic, A_GRID, nh, nd, true, false, MEEPCU_SYNC_POL));
+                }
             }
           }
         }
@@ -1132,7 +1178,7 @@ template <class T> struct Ctx : CtxBase {
     // ---- 5. per-(chunk, half, cmp) parameter blocks + tiles ----
     std::vector<Tile> tiles[2][4], eh_tiles[2], c3d_tiles[2], c3dv_tiles[2], gv_tiles[2][2];
     std::vector<FmpParams<T> > fmps[2];
-    std::vector<Tile> polgen_tiles[2];
+    std::vector<Tile> polgen_tiles[2], polgyro_tiles[2];
     std::vector<int> c3d_chunk, half_chunk; // owning chunk of every h_c3d / h_half entry
     // interior and PML tiles of a half in one grid (k_mix); fp64 PML tiles are vectorised only for that
     const bool mix_want = getenv("MEEPCU_MIX") ? atoi(getenv("MEEPCU_MIX")) != 0 : true;
@@ -1169,6 +1215,7 @@ template <class T> struct Ctx : CtxBase {
             general = true;
           for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip) {
             const meepcu_susceptibility_desc &sd = ch.pol[ft][ip].d;
+            if (ch.pol[ft][ip].gyro) aniso_chunk_half.insert(std::make_pair((int)ic, half)); // -> k_pol_gyro
             for (int cmp = 0; cmp < ncmp; ++cmp)
               if (sd.P[ec][cmp] && sd.sigma[ec][k] &&
                   ((sd.sigma[ec][d1] && ch.d.f[dir_comp(ft, d1)][cmp]) ||
@@ -1289,6 +1336,7 @@ template <class T> struct Ctx : CtxBase {
             }
             zm = zmask.find((const char *)ch.d.f[ec][cmp]);
             c.zmask_eh = zm == zmask.end() ? 0u : zm->second;
+            if (aniso_now) c.zmask_eh = 0; // zero_metal(E) must follow the separate polarisation pass (step.cpp:109-122)
             c.isrc = d_src + R.i0; c.nisrc = (int)(R.i1 - R.i0); c.isrc_amin = R.ia0; c.isrc_amax = R.ia1;
             c.npol = (int)ch.pol[ft].size();
             if (c.npol) simple = false;
@@ -1532,6 +1580,7 @@ template <class T> struct Ctx : CtxBase {
               E.nl_mode = cfg.nl_mode;
               std::map<const char *, unsigned>::iterator zm = zmask.find((const char *)ch.d.f[ec][cmp]);
               E.zmask_eh = zm == zmask.end() ? 0u : zm->second;
+              if (aniso_now) E.zmask_eh = 0;
               E.npol = (int)ch.pol[ft].size();
               RC(fill_pols(ch, ft, ec, k, cmp, E.pol));
               E.nr_fail = d_flags;
@@ -1563,6 +1612,10 @@ template <class T> struct Ctx : CtxBase {
           const int sgn = ft == MEEPCU_H_STUFF ? -1 : +1;
           for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip) {
             const meepcu_susceptibility_desc &sd = ch.pol[ft][ip].d;
+            if (ch.pol[ft][ip].gyro) {
+              RC(build_gyro(ch, (int)ic, ch.pol[ft][ip].g, ft, half, ncmp, nc, polgyro_tiles[half]));
+              continue;
+            }
             PolParams<T> coef[kMaxPol];
             for (int cmp = 0; cmp < ncmp; ++cmp)
               for (int k = 0; k < 3; ++k) {
@@ -1620,7 +1673,7 @@ template <class T> struct Ctx : CtxBase {
     if (n_ranks > 1 && !getenv("MEEPCU_NO_OVERLAP"))
       for (int half = 0; half < 2; ++half) {
         if (general_half[half]) continue; // k_eh_general needs the D halo before E exists: ordered path
-        if (!polgen_tiles[half].empty()) continue; // k_pol_general needs the W halo before P: ordered path
+        if (!polgen_tiles[half].empty() || !polgyro_tiles[half].empty()) continue; // k_pol_general / k_pol_gyro need the W halo before P: ordered path
         const int fts[2] = {half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF, half ? MEEPCU_WE_STUFF : MEEPCU_WH_STUFF};
         // per chunk: the planes (index on device axis A) that hold points another rank receives
         std::vector<std::set<int> > planes(chunks.size());
@@ -1745,10 +1798,24 @@ template <class T> struct Ctx : CtxBase {
       }
     }
     RC(upload(h_eh, &d_eh));
+    for (int half = 0; half < 2; ++half) { // the metal points of E (H) in those chunks, zeroed after the polarisation pass
+      const int fte = half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF;
+      std::vector<T *> late;
+      for (size_t k = 0; k < metal[fte].size(); ++k) {
+        size_t e = 0;
+        const ArrayRec *r = find(metal[fte][k], sizeof(T), &e);
+        if (r && r->kind == A_GRID && aniso_chunk_half.count(std::make_pair(r->chunk, half))) late.push_back(dev_elem(metal[fte][k]));
+      }
+      n_zero_late[half] = (long long)late.size();
+      RC(upload(late, &d_zero_late[half]));
+    }
     RC(upload(h_polgen, &d_polgen));
+    RC(upload(h_polgyro, &d_polgyro));
     for (int half = 0; half < 2; ++half) {
       n_polgen_tiles[half] = (int)polgen_tiles[half].size();
       RC(upload(polgen_tiles[half], &d_polgen_tiles[half]));
+      n_polgyro_tiles[half] = (int)polgyro_tiles[half].size();
+      RC(upload(polgyro_tiles[half], &d_polgyro_tiles[half]));
     }
     for (int half = 0; half < 2; ++half) {
       for (int cl = 0; cl < 4; ++cl) {
@@ -1766,7 +1833,7 @@ template <class T> struct Ctx : CtxBase {
     // E/H neighbours (no k_eh_general / k_pol_general / DFT averaging / cross-rank lists built from them)
     size_t dfts_total = 0;
     for (size_t ic = 0; ic < chunks.size(); ++ic) dfts_total += chunks[ic].dft.size();
-    const bool defer_normal = cfg.dim == MEEPCU_D3 && !general_half[0] && !general_half[1] && h_polgen.empty() &&
+    const bool defer_normal = cfg.dim == MEEPCU_D3 && !general_half[0] && !general_half[1] && h_polgen.empty() && h_polgyro.empty() &&
                               dfts_total == 0 && !getenv("MEEPCU_NO_DEFER");
     std::map<const char *, int> comp_of; // host base of an f array -> component (direction is what matters)
     if (defer_normal)
@@ -1952,6 +2019,98 @@ template <class T> struct Ctx : CtxBase {
 
     CU(cudaStreamSynchronize(st));
     finalized = true;
+    return MEEPCU_OK;
+  }
+
+  // parameter blocks + tiles of k_pol_gyro for one gyrotropic susceptibility of one chunk
+  // (constants evaluated in realnum exactly like susceptibility.cpp:449-478,531-546)
+  int build_gyro(const ChunkH &ch, int ic, const meepcu_gyrotropic_desc &gd_, int ft, int half, int ncmp, long long nc,
+                 std::vector<Tile> &tiles_out) {
+    const Geom &g = ch.g;
+    const double pi = 3.141592653589793238462643383276;
+    const T dt = (T)cfg.dt;
+    const T omega_0 = (T)gd_.omega_0, gamma = (T)gd_.gamma, alpha = (T)gd_.alpha;
+    T gyro_tensor[3][3];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) gyro_tensor[a][b] = (T)gd_.gyro_tensor[a][b];
+    const T omega2pidt = 2 * pi * omega_0 * dt;
+    const T g2pidt = 2 * pi * gamma * dt;
+    const int X = 0, Y = 1, Z = 2;
+    const bool sat = gd_.model == MEEPCU_GYROTROPIC_SATURATED;
+    T omega0dtsqr = 0, gamma1 = 0, diag = 0, pt = 0, dt2pi = 0, gd, gx, gy, gz;
+    if (!sat) {
+      omega0dtsqr = omega2pidt * omega2pidt;
+      gamma1 = (1 - g2pidt / 2);
+      diag = 2 - (gd_.model == MEEPCU_GYROTROPIC_DRUDE ? 0 : omega0dtsqr);
+      pt = pi * dt;
+      gd = (1 + g2pidt / 2);
+      gx = pt * gyro_tensor[Y][Z];
+      gy = pt * gyro_tensor[Z][X];
+      gz = pt * gyro_tensor[X][Y];
+    }
+    else {
+      dt2pi = 2 * pi * dt;
+      gd = 0.5;
+      gx = -0.5 * alpha * gyro_tensor[Y][Z];
+      gy = -0.5 * alpha * gyro_tensor[Z][X];
+      gz = -0.5 * alpha * gyro_tensor[X][Y];
+    }
+    const T invdet = 1.0 / gd / (gd * gd + gx * gx + gy * gy + gz * gz);
+    const T inv[3][3] = {{invdet * (gd * gd + gx * gx), invdet * (gx * gy + gd * gz), invdet * (gx * gz - gd * gy)},
+                         {invdet * (gy * gx - gd * gz), invdet * (gd * gd + gy * gy), invdet * (gy * gz + gd * gx)},
+                         {invdet * (gz * gx + gd * gy), invdet * (gz * gy - gd * gx), invdet * (gd * gd + gz * gz)}};
+    const int sgn = ft == MEEPCU_H_STUFF ? -1 : +1;
+    for (int cmp = 0; cmp < ncmp; ++cmp)
+      for (int k = 0; k < 3; ++k) {
+        const int c = dir_comp(ft, k);
+        if (!gd_.P[c][cmp][0]) continue;
+        const int d0 = k, d1 = (k + 1) % 3, d2 = (k + 2) % 3;
+        const int c1 = dir_comp(ft, d1), c2 = dir_comp(ft, d2);
+        const void *w0h = ch.d.f_w[c][cmp] ? ch.d.f_w[c][cmp] : ch.d.f[c][cmp];
+        const void *w1h = ch.d.f_w[c1][cmp] ? ch.d.f_w[c1][cmp] : ch.d.f[c1][cmp];
+        const void *w2h = ch.d.f_w[c2][cmp] ? ch.d.f_w[c2][cmp] : ch.d.f[c2][cmp];
+        PolGyroParams<T> Q;
+        memset(&Q, 0, sizeof Q);
+        Q.nA = g.nax[0]; Q.nB = g.nax[1]; Q.nC = g.nax[2]; Q.pitch = g.pitch;
+        Q.sA = (long long)g.pitch * g.nax[1]; Q.sB = g.pitch;
+        for (int ax = 0; ax < 3; ++ax) {
+          const int d = g.dir_of_axis[ax];
+          Q.lo[ax] = d < 0 ? 0 : 1 - g.yee_shift(c, d);
+          Q.hi[ax] = d < 0 ? 0 : g.num[d] - g.yee_shift(c, d);
+        }
+        Q.p0 = dev(gd_.P[c][cmp][d0]); Q.pp0 = dev(gd_.P_prev[c][cmp][d0]);
+        Q.p1 = dev(gd_.P[c][cmp][d1]); Q.pp1 = dev(gd_.P_prev[c][cmp][d1]);
+        Q.p2 = dev(gd_.P[c][cmp][d2]); Q.pp2 = dev(gd_.P_prev[c][cmp][d2]);
+        Q.s = dev(gd_.sigma[c][d0]);
+        Q.w0 = dev(w0h); Q.w1 = dev(w1h); Q.w2 = dev(w2h);
+        if (!Q.w0 || !Q.s || !Q.p0 || !Q.pp0 || !Q.p1 || !Q.pp1 || !Q.p2 || !Q.pp2)
+          return fail(MEEPCU_EINVAL, "gyrotropic media require 3D Cartesian fields");
+        if (gd_.sigma[c][d1] || gd_.sigma[c][d2])
+          return fail(MEEPCU_EINVAL, "gyrotropic media do not support anisotropic sigma");
+        Q.is = g.ds[d0] * sgn; Q.is1 = g.ds[d1] * sgn; Q.is2 = g.ds[d2] * sgn;
+        Q.saturated = sat;
+        Q.g01 = gyro_tensor[d0][d1]; Q.g02 = gyro_tensor[d0][d2];
+        Q.g10 = gyro_tensor[d1][d0]; Q.g12 = gyro_tensor[d1][d2];
+        Q.g20 = gyro_tensor[d2][d0]; Q.g21 = gyro_tensor[d2][d1];
+        const int dd[3] = {d0, d1, d2};
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b) Q.inv[a][b] = inv[dd[a]][dd[b]];
+        Q.diag = diag; Q.gamma1 = gamma1; Q.omega0dtsqr = omega0dtsqr; Q.pt = pt;
+        Q.omega2pidt = omega2pidt; Q.g2pidt = g2pidt; Q.alpha = alpha; Q.dt2pi = dt2pi;
+        const int qidx = (int)h_polgyro.size();
+        h_polgyro.push_back(Q);
+        const int plane = g.nax[1] * g.pitch;
+        const int seg = g.nax[0] <= 48 ? g.nax[0] : 32;
+        for (int a0 = 0; a0 < g.nax[0]; a0 += seg)
+          for (int p0 = 0; p0 < plane; p0 += kThreads) {
+            Tile t = {qidx, a0, std::min(a0 + seg, g.nax[0]), p0};
+            tiles_out.push_back(t);
+          }
+        alg_bytes += 13LL * nc * (long long)sizeof(T); // R,W six P arrays + R sigma (W counted with E)
+        kc_bytes[KC_POL_GENERAL] += 13LL * nc * (long long)sizeof(T);
+      }
+    (void)ic;
+    (void)half;
     return MEEPCU_OK;
   }
 
@@ -2203,11 +2362,23 @@ template <class T> struct Ctx : CtxBase {
       RC(prof_end());
       launches++;
     }
-    RC(launch_conn(ftw));                    // step.cpp:81,113 (empty unless anisotropic sigma)
-    if (n_polgen_tiles[half]) {              // update_pols for anisotropic sigma, step.cpp:83-86,115-117
+    // synchronize_magnetic_fields runs neither step_boundaries(WH) nor update_pols(H) (energy_and_flux.cpp:153-160)
+    if (!in_mag_sync) RC(launch_conn(ftw));  // step.cpp:81,113 (empty unless anisotropic sigma / gyrotropy)
+    if (n_polgen_tiles[half] && !in_mag_sync) { // update_pols for anisotropic sigma, step.cpp:83-86,115-117
       RC(prof_begin(KC_POL_GENERAL));
       k_pol_general<T><<<n_polgen_tiles[half], kThreads, 0, st>>>(d_polgen, d_polgen_tiles[half]);
       RC(prof_end());
+      launches++;
+    }
+    if (n_polgyro_tiles[half] && !in_mag_sync) { // gyrotropic update_P
+      RC(prof_begin(KC_POL_GENERAL));
+      k_pol_gyro<T><<<n_polgyro_tiles[half], kThreads, 0, st>>>(d_polgyro, d_polgyro_tiles[half]);
+      RC(prof_end());
+      launches++;
+    }
+    if (n_zero_late[half]) {                 // zero_metal(E) of step_boundaries(E_stuff), step.cpp:245-246
+      k_zero<T><<<(int)std::min<long long>((n_zero_late[half] + kThreads - 1) / kThreads, 148 * 8), kThreads, 0, st>>>(
+          d_zero_late[half], n_zero_late[half]);
       launches++;
     }
     if (eager_p[half]) RC(launch_conn(ftp)); // step.cpp:87,118
@@ -2308,8 +2479,10 @@ template <class T> struct Ctx : CtxBase {
         const meepcu_susceptibility_desc &sd = chunks[ic].pol[MEEPCU_H_STUFF][ip].d;
         for (int c = 0; c < 20; ++c)
           for (int cmp = 0; cmp < 2; ++cmp) {
-            const void *arrs[2] = {sd.P[c][cmp], sd.P_prev[c][cmp]};
-            for (int k = 0; k < 2; ++k) {
+            const meepcu_gyrotropic_desc &gg = chunks[ic].pol[MEEPCU_H_STUFF][ip].g; // all zero unless gyrotropic
+            const void *arrs[8] = {sd.P[c][cmp], sd.P_prev[c][cmp], gg.P[c][cmp][0], gg.P[c][cmp][1], gg.P[c][cmp][2],
+                                   gg.P_prev[c][cmp][0], gg.P_prev[c][cmp][1], gg.P_prev[c][cmp][2]};
+            for (int k = 0; k < 8; ++k) {
               if (!arrs[k] || !seen.insert(arrs[k]).second) continue;
               std::map<const char *, ArrayRec>::iterator it = arrays.find((const char *)arrs[k]);
               if (it == arrays.end()) continue;
@@ -2337,7 +2510,10 @@ template <class T> struct Ctx : CtxBase {
     if (nsrc > 0) CU(cudaMemcpyAsync(d_smp.p, smp, sizeof(meepcu_src_sample) * (size_t)nsrc, cudaMemcpyHostToDevice, st));
     for (size_t k = 0; k < mag_arrays.size(); ++k) // backup_component (:97-118)
       CU(cudaMemcpyAsync(mag_backup + mag_arrays[k].off, mag_arrays[k].dev, mag_arrays[k].bytes, cudaMemcpyDeviceToDevice, st));
-    RC(launch_half(0, d_smp.p)); // step_db(B), step_source(B), step_boundaries(B), update_eh(H), step_boundaries(H)
+    in_mag_sync = true;
+    const int rc_half = launch_half(0, d_smp.p); // step_db(B), step_source(B), step_boundaries(B), update_eh(H), step_boundaries(H)
+    in_mag_sync = false;
+    RC(rc_half);
     for (size_t k = 0; k < mag_arrays.size(); ++k) {
       const MagArr &m = mag_arrays[k];
       if (m.is_pol)
@@ -2526,6 +2702,11 @@ int meepcu_add_susceptibility(meepcu_ctx *ctx, int chunk, const meepcu_susceptib
   CHECK_CTX;
   if (!d) return fail(MEEPCU_EINVAL, "null descriptor");
   return ctx->impl->add_susc(chunk, d);
+}
+int meepcu_add_gyrotropic(meepcu_ctx *ctx, int chunk, const meepcu_gyrotropic_desc *d) {
+  CHECK_CTX;
+  if (!d) return fail(MEEPCU_EINVAL, "null descriptor");
+  return ctx->impl->add_gyro(chunk, d);
 }
 int meepcu_add_source(meepcu_ctx *ctx, int chunk, const meepcu_source_desc *d) {
   CHECK_CTX;

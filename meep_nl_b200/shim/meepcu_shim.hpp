@@ -57,6 +57,7 @@ struct api {
   MEEPCU_FN(destroy)
   MEEPCU_FN(add_chunk)
   MEEPCU_FN(add_susceptibility)
+  MEEPCU_FN(add_gyrotropic)
   MEEPCU_FN(add_source)
   MEEPCU_FN(add_dft)
   MEEPCU_FN(set_metal)
@@ -89,6 +90,7 @@ struct api {
     MEEPCU_FN(destroy)
     MEEPCU_FN(add_chunk)
     MEEPCU_FN(add_susceptibility)
+    MEEPCU_FN(add_gyrotropic)
     MEEPCU_FN(add_source)
     MEEPCU_FN(add_dft)
     MEEPCU_FN(set_metal)
@@ -118,6 +120,7 @@ struct observer {
   virtual void on_create(const meepcu_config &) {}
   virtual void on_chunk(int, const meepcu_chunk_desc &, size_t /*ntot*/) {}
   virtual void on_susceptibility(int, const meepcu_susceptibility_desc &, size_t /*ntot*/) {}
+  virtual void on_gyrotropic(int, const meepcu_gyrotropic_desc &, size_t /*ntot*/) {}
   virtual void on_source(int, const meepcu_source_desc &) {}
   virtual void on_dft(int, const meepcu_dft_desc &, size_t /*N*/) {}
   virtual void on_metal(int, size_t, void *const *) {}
@@ -374,10 +377,41 @@ private:
       field_type ehs[2] = {E_stuff, H_stuff};
       for (int k = 0; k < 2; ++k)
         for (polarization_state *p = fc->pol[ehs[k]]; p; p = p->next) {
+          if (typeid(*p->s) == typeid(gyrotropic_susceptibility)) {
+            const gyrotropic_susceptibility *gs = static_cast<const gyrotropic_susceptibility *>(p->s);
+            // gyrotropy_data is private to susceptibility.cpp:373-379; same layout restated here
+            struct gyrotropy_data_layout {
+              size_t sz_data, ntot;
+              realnum *P[NUM_FIELD_COMPONENTS][2][3];
+              realnum *P_prev[NUM_FIELD_COMPONENTS][2][3];
+            };
+            const gyrotropy_data_layout *gd = (const gyrotropy_data_layout *)p->data;
+            meepcu_gyrotropic_desc gdsc;
+            memset(&gdsc, 0, sizeof gdsc);
+            gdsc.ft = (int)ehs[k];
+            gdsc.model = (int)gs->model;
+            gdsc.omega_0 = gs->omega_0;
+            gdsc.gamma = gs->gamma;
+            gdsc.alpha = gs->alpha;
+            for (int r = 0; r < 3; ++r)
+              for (int q = 0; q < 3; ++q) gdsc.gyro_tensor[r][q] = gs->gyro_tensor[r][q];
+            FOR_COMPONENTS(c) {
+              for (int dd = 0; dd < 5; ++dd) gdsc.sigma[c][dd] = gs->sigma[c][dd];
+              if (gd)
+                for (int cmp = 0; cmp < 2; ++cmp)
+                  for (int dd = 0; dd < 3; ++dd) {
+                    gdsc.P[c][cmp][dd] = gd->P[c][cmp][dd];
+                    gdsc.P_prev[c][cmp][dd] = gd->P_prev[c][cmp][dd];
+                  }
+            }
+            if (obs) obs->on_gyrotropic(i, gdsc, gv.ntot());
+            check(a.add_gyrotropic(ctx, i, &gdsc));
+            continue;
+          }
           const lorentzian_susceptibility *ls =
               dynamic_cast<const lorentzian_susceptibility *>(p->s);
           if (!ls || typeid(*p->s) != typeid(lorentzian_susceptibility))
-            meep::abort("meepcu: only Lorentzian/Drude susceptibilities are on the GPU path");
+            meep::abort("meepcu: only Lorentzian/Drude and gyrotropic susceptibilities are on the GPU path");
           meepcu_susceptibility_desc sd;
           memset(&sd, 0, sizeof sd);
           sd.ft = (int)ehs[k];

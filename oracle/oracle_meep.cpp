@@ -197,6 +197,7 @@ struct CtxBase {
   virtual ~CtxBase() {}
   virtual int add_chunk(const meepcu_chunk_desc *d, int *id) = 0;
   virtual int add_susc(int chunk, const meepcu_susceptibility_desc *d) = 0;
+  virtual int add_gyro(int chunk, const meepcu_gyrotropic_desc *d) = 0;
   virtual int add_source(int chunk, const meepcu_source_desc *d) = 0;
   virtual int add_dft(int chunk, const meepcu_dft_desc *d, int *id) = 0;
   virtual int set_metal(int ft, size_t n, void *const *ptrs) = 0;
@@ -212,7 +213,9 @@ struct CtxBase {
 };
 
 template <class T> struct Susc {
-  meepcu_susceptibility_desc d;
+  meepcu_susceptibility_desc d; // gyrotropic: sigma, and P/P_prev = the component subtract_P uses (P[c][cmp][dir(c)])
+  bool gyro;
+  meepcu_gyrotropic_desc g;
 };
 
 template <class T> struct Dft {
@@ -340,7 +343,31 @@ template <class T> struct Impl : CtxBase {
     if (d->ft != MEEPCU_E_STUFF && d->ft != MEEPCU_H_STUFF)
       return fail(MEEPCU_EINVAL, "susceptibility ft must be E_stuff or H_stuff");
     Susc<T> s;
+    memset(&s, 0, sizeof s);
     s.d = *d;
+    s.gyro = false;
+    chunks[chunk].pol[d->ft].push_back(s);
+    return MEEPCU_OK;
+  }
+  int add_gyro(int chunk, const meepcu_gyrotropic_desc *d) {
+    if (chunk < 0 || chunk >= (int)chunks.size()) return fail(MEEPCU_EINVAL, "bad chunk id");
+    if (d->ft != MEEPCU_E_STUFF && d->ft != MEEPCU_H_STUFF)
+      return fail(MEEPCU_EINVAL, "susceptibility ft must be E_stuff or H_stuff");
+    if (d->model < 0 || d->model > 2) return fail(MEEPCU_EINVAL, "bad gyrotropy model");
+    Susc<T> s;
+    memset(&s, 0, sizeof s);
+    s.gyro = true;
+    s.g = *d;
+    s.d.ft = d->ft;
+    for (int c = 0; c < 20; ++c) {
+      for (int k = 0; k < 5; ++k) s.d.sigma[c][k] = d->sigma[c][k];
+      const int d0 = comp_dir(c);
+      if (d0 < MEEPCU_R)
+        for (int cmp = 0; cmp < 2; ++cmp) { // subtract_P uses P[ec][cmp][component_direction(ec)] (:586-603)
+          s.d.P[c][cmp] = d->P[c][cmp][d0];
+          s.d.P_prev[c][cmp] = d->P_prev[c][cmp][d0];
+        }
+    }
     chunks[chunk].pol[d->ft].push_back(s);
     return MEEPCU_OK;
   }
@@ -1178,12 +1205,124 @@ template <class T> struct Impl : CtxBase {
 
   // fields_chunk::update_pols, src/update_pols.cpp:40-62 -> lorentzian_susceptibility::update_P,
   // src/susceptibility.cpp:188-262
+  // gyrotropic_susceptibility::update_P, src/susceptibility.cpp:445-584
+  int update_gyro(Chunk<T> &ch, const meepcu_gyrotropic_desc &gd_) {
+    const Grid &g = ch.g;
+    const double pi = 3.141592653589793238462643383276;
+    const T dt = (T)cfg.dt;
+    const T omega_0 = (T)gd_.omega_0, gamma = (T)gd_.gamma, alpha = (T)gd_.alpha;
+    T gyro_tensor[3][3];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) gyro_tensor[a][b] = (T)gd_.gyro_tensor[a][b];
+    const T omega2pidt = 2 * pi * omega_0 * dt;
+    const T g2pidt = 2 * pi * gamma * dt;
+    const int X = 0, Y = 1, Z = 2;
+    T inv[3][3];
+    T omega0dtsqr = 0, gamma1 = 0, diag = 0, pt = 0, dt2pi = 0;
+    if (gd_.model != MEEPCU_GYROTROPIC_SATURATED) {
+      omega0dtsqr = omega2pidt * omega2pidt;
+      gamma1 = (1 - g2pidt / 2);
+      diag = 2 - (gd_.model == MEEPCU_GYROTROPIC_DRUDE ? 0 : omega0dtsqr);
+      pt = pi * dt;
+      const T gd = (1 + g2pidt / 2);
+      const T gx = pt * gyro_tensor[Y][Z];
+      const T gy = pt * gyro_tensor[Z][X];
+      const T gz = pt * gyro_tensor[X][Y];
+      const T invdet = 1.0 / gd / (gd * gd + gx * gx + gy * gy + gz * gz);
+      const T m[3][3] = {{invdet * (gd * gd + gx * gx), invdet * (gx * gy + gd * gz), invdet * (gx * gz - gd * gy)},
+                         {invdet * (gy * gx - gd * gz), invdet * (gd * gd + gy * gy), invdet * (gy * gz + gd * gx)},
+                         {invdet * (gz * gx + gd * gy), invdet * (gz * gy - gd * gx), invdet * (gd * gd + gz * gz)}};
+      memcpy(inv, m, sizeof inv);
+    }
+    else {
+      dt2pi = 2 * pi * dt;
+      const T gd = 0.5;
+      const T gx = -0.5 * alpha * gyro_tensor[Y][Z];
+      const T gy = -0.5 * alpha * gyro_tensor[Z][X];
+      const T gz = -0.5 * alpha * gyro_tensor[X][Y];
+      const T invdet = 1.0 / gd / (gd * gd + gx * gx + gy * gy + gz * gz);
+      const T m[3][3] = {{invdet * (gd * gd + gx * gx), invdet * (gx * gy + gd * gz), invdet * (gx * gz - gd * gy)},
+                         {invdet * (gy * gx - gd * gz), invdet * (gd * gd + gy * gy), invdet * (gy * gz + gd * gx)},
+                         {invdet * (gz * gx + gd * gy), invdet * (gz * gy - gd * gx), invdet * (gd * gd + gz * gz)}};
+      memcpy(inv, m, sizeof inv);
+    }
+    for (int c = 0; c < 20; ++c)
+      for (int cmp = 0; cmp < 2; ++cmp) {
+        if (!gd_.P[c][cmp][0]) continue;
+        const int d0 = comp_dir(c);
+        const T *w0 = ch.d.f_w[c][cmp] ? (const T *)ch.d.f_w[c][cmp] : ch.F(c, cmp);
+        const T *s = d0 < MEEPCU_R ? (const T *)gd_.sigma[c][d0] : NULL;
+        if (!w0 || !s || g.dim != MEEPCU_D3) return fail(MEEPCU_EINVAL, "gyrotropic media require 3D Cartesian fields");
+        const int d1 = cycle_dir(d0, 1), d2 = cycle_dir(d0, 2);
+        const int c1 = dir_comp(c, d1), c2 = dir_comp(c, d2);
+        const T *w1 = ch.d.f_w[c1][cmp] ? (const T *)ch.d.f_w[c1][cmp] : ch.F(c1, cmp);
+        const T *w2 = ch.d.f_w[c2][cmp] ? (const T *)ch.d.f_w[c2][cmp] : ch.F(c2, cmp);
+        T *p0 = (T *)gd_.P[c][cmp][d0], *pp0 = (T *)gd_.P_prev[c][cmp][d0];
+        T *p1 = (T *)gd_.P[c][cmp][d1], *pp1 = (T *)gd_.P_prev[c][cmp][d1];
+        T *p2 = (T *)gd_.P[c][cmp][d2], *pp2 = (T *)gd_.P_prev[c][cmp][d2];
+        const int sgn = is_magnetic(c) ? -1 : +1;
+        const ptrdiff_t is = g.stride[d0] * sgn, is1 = g.stride[d1] * sgn, is2 = g.stride[d2] * sgn;
+        if (!pp1 || !pp2) return fail(MEEPCU_EINVAL, "gyrotropic media require 3D Cartesian fields");
+        if (gd_.sigma[c][d1] || gd_.sigma[c][d2]) return fail(MEEPCU_EINVAL, "gyrotropic media do not support anisotropic sigma");
+        int is_[3], ie_[3]; // LOOP_OVER_VOL_OWNED
+        for (int dd = 0; dd < 3; ++dd) {
+          is_[dd] = g.io[dd] + 2 - g.yee_shift(c, dd);
+          ie_[dd] = g.io[dd] + 2 * g.num[dd];
+        }
+        Loop L(g, is_, ie_);
+#define GOFFDIAGW(gg, sx, s_) (0.25 * (gg[i] + gg[i - sx] + gg[i + s_] + gg[i + s_ - sx]))
+        if (gd_.model != MEEPCU_GYROTROPIC_SATURATED) {
+#pragma omp parallel for collapse(2)
+          OLOOP(L, i) {
+            T r0, r1, r2;
+            r0 = diag * p0[i] - gamma1 * pp0[i] + omega0dtsqr * s[i] * w0[i] - pt * gyro_tensor[d0][d1] * pp1[i] -
+                 pt * gyro_tensor[d0][d2] * pp2[i];
+            r1 = diag * p1[i] - gamma1 * pp1[i] + (w1 ? omega0dtsqr * s[i] * GOFFDIAGW(w1, is1, is) : 0) -
+                 pt * gyro_tensor[d1][d0] * pp0[i] - pt * gyro_tensor[d1][d2] * pp2[i];
+            r2 = diag * p2[i] - gamma1 * pp2[i] + (w2 ? omega0dtsqr * s[i] * GOFFDIAGW(w2, is2, is) : 0) -
+                 pt * gyro_tensor[d2][d1] * pp1[i] - pt * gyro_tensor[d2][d0] * pp0[i];
+            pp0[i] = p0[i];
+            pp1[i] = p1[i];
+            pp2[i] = p2[i];
+            p0[i] = inv[d0][d0] * r0 + inv[d0][d1] * r1 + inv[d0][d2] * r2;
+            p1[i] = inv[d1][d0] * r0 + inv[d1][d1] * r1 + inv[d1][d2] * r2;
+            p2[i] = inv[d2][d0] * r0 + inv[d2][d1] * r1 + inv[d2][d2] * r2;
+          }
+        }
+        else {
+#pragma omp parallel for collapse(2)
+          OLOOP(L, i) {
+            T r0, r1, r2, q0, q1, q2;
+            q0 = -omega2pidt * p0[i] + 0.5 * alpha * pp0[i] + dt2pi * s[i] * w0[i];
+            q1 = -omega2pidt * p1[i] + 0.5 * alpha * pp1[i] + dt2pi * s[i] * (w1 ? GOFFDIAGW(w1, is1, is) : 0);
+            q2 = -omega2pidt * p2[i] + 0.5 * alpha * pp2[i] + dt2pi * s[i] * (w2 ? GOFFDIAGW(w2, is2, is) : 0);
+            r0 = 0.5 * pp0[i] - g2pidt * p0[i] + gyro_tensor[d0][d1] * q1 + gyro_tensor[d0][d2] * q2;
+            r1 = 0.5 * pp1[i] - g2pidt * p1[i] + gyro_tensor[d1][d2] * q2 + gyro_tensor[d1][d0] * q0;
+            r2 = 0.5 * pp2[i] - g2pidt * p2[i] + gyro_tensor[d2][d0] * q0 + gyro_tensor[d2][d1] * q1;
+            pp0[i] = p0[i];
+            pp1[i] = p1[i];
+            pp2[i] = p2[i];
+            p0[i] = inv[d0][d0] * r0 + inv[d0][d1] * r1 + inv[d0][d2] * r2;
+            p1[i] = inv[d1][d0] * r0 + inv[d1][d1] * r1 + inv[d1][d2] * r2;
+            p2[i] = inv[d2][d0] * r0 + inv[d2][d1] * r1 + inv[d2][d2] * r2;
+          }
+        }
+#undef GOFFDIAGW
+      }
+    return MEEPCU_OK;
+  }
+
   int update_pols(int ft) {
     for (size_t ic = 0; ic < chunks.size(); ++ic) {
       Chunk<T> &ch = chunks[ic];
       const Grid &g = ch.g;
       const T dt = (T)cfg.dt;
       for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip) {
+        if (ch.pol[ft][ip].gyro) {
+          int rc = update_gyro(ch, ch.pol[ft][ip].g);
+          if (rc) return rc;
+          continue;
+        }
         const meepcu_susceptibility_desc &sd = ch.pol[ft][ip].d;
         const T pi = 3.141592653589793238462643383276; // src/meep.hpp:54 (const double pi)
         const double dpi = 3.141592653589793238462643383276;
@@ -1497,6 +1636,11 @@ int meepcu_add_chunk(meepcu_ctx *ctx, const meepcu_chunk_desc *d, int *id) {
 int meepcu_add_susceptibility(meepcu_ctx *ctx, int chunk, const meepcu_susceptibility_desc *d) {
   CHECK_CTX;
   return ctx->impl->add_susc(chunk, d);
+}
+int meepcu_add_gyrotropic(meepcu_ctx *ctx, int chunk, const meepcu_gyrotropic_desc *d) {
+  CHECK_CTX;
+  if (!d) return fail(MEEPCU_EINVAL, "null descriptor");
+  return ctx->impl->add_gyro(chunk, d);
 }
 int meepcu_add_source(meepcu_ctx *ctx, int chunk, const meepcu_source_desc *d) {
   CHECK_CTX;

@@ -365,6 +365,27 @@ static problem *build(const std::string &spec, int nchunks) {
     p->f->add_point_source(Ez, 0.3, 0.25, 0.0, 4.0, p->gv.center(), 1.0);
     p->f->add_point_source(d3 ? Hy : Hz, 0.25, 0.25, 0.0, 4.0, p->gv.center(), 0.5);
   }
+  else if (name == "gyro3d" || name == "gyrosat3d" || name == "gyrodrude3d") { // gyrotropic media
+    // (susceptibility.cpp:350-603): Lorentzian / Drude / saturated (Landau-Lifshitz-Gilbert) models, plus an
+    // ordinary Lorentzian in the same list so that the subtraction order matters
+    if (!n) n = 14;
+    const double L = n / a;
+    p->gv = vol3d(L, L, L, a);
+    g_slab_lo = 0.3 * L;
+    g_slab_hi = 0.7 * L;
+    g_slab_eps = 2.0;
+    p->s = new structure(p->gv, slab_eps_z, pml(0.1 * L > 0.5 ? 0.5 : 0.1 * L), identity(), nchunks, 0.5, false);
+    const vec bias(0.3, -0.2, 0.9);
+    if (name == "gyrosat3d")
+      p->s->add_susceptibility(slab_mask_z, H_stuff, gyrotropic_susceptibility(bias, 0.7, 0.02, 0.01, GYROTROPIC_SATURATED));
+    else
+      p->s->add_susceptibility(slab_mask_z, E_stuff,
+                               gyrotropic_susceptibility(bias, 0.8, 0.03, 0.0, name == "gyro3d" ? GYROTROPIC_LORENTZIAN : GYROTROPIC_DRUDE));
+    p->s->add_susceptibility(slab_mask_z, E_stuff, lorentzian_susceptibility(1.2, 0.01));
+    p->f = new fields(p->s);
+    p->f->add_point_source(Ez, 0.3, 0.25, 0.0, 4.0, p->gv.center(), 1.0);
+    p->f->add_point_source(Hx, 0.25, 0.25, 0.0, 4.0, p->gv.center(), 0.5);
+  }
   else if (name == "phc3d") { // BASELINE config 5 shape: slab, PML in z, Bloch-periodic x,y, fp32-able
     if (!n) n = 16;
     p->gv = vol3d(n / a, n / a, 1.5 * n / a, a);
@@ -473,12 +494,14 @@ static std::vector<marray> collect(fields &f) {
       int ip = 0;
       for (polarization_state *p = fc->pol[ehs[k]]; p; p = p->next, ++ip) {
         if (!p->data) continue;
-        FOR_COMPONENTS(c) for (int cmp = 0; cmp < 2; ++cmp) {
-          realnum *P = p->s->cinternal_notowned_ptr(0, c, cmp, 0, p->data);
+        // lorentzian_data: P, P_prev per (c, cmp); gyrotropy_data: (P, P_prev) for each of X, Y, Z
+        const int nsub = typeid(*p->s) == typeid(gyrotropic_susceptibility) ? 3 : 1;
+        FOR_COMPONENTS(c) for (int cmp = 0; cmp < 2; ++cmp) for (int sub = 0; sub < nsub; ++sub) {
+          realnum *P = p->s->cinternal_notowned_ptr(sub, c, cmp, 0, p->data);
           if (!P) continue;
-          snprintf(nm, sizeof nm, "chunk%d.pol%d_%d.P[%s][%d]", i, k, ip, component_name(c), cmp);
+          snprintf(nm, sizeof nm, "chunk%d.pol%d_%d.P[%s][%d][%d]", i, k, ip, component_name(c), cmp, sub);
           out.push_back({P, nb, nm});
-          snprintf(nm, sizeof nm, "chunk%d.pol%d_%d.P_prev[%s][%d]", i, k, ip, component_name(c), cmp);
+          snprintf(nm, sizeof nm, "chunk%d.pol%d_%d.P_prev[%s][%d][%d]", i, k, ip, component_name(c), cmp, sub);
           out.push_back({P + fc->gv.ntot(), nb, nm});
         }
       }

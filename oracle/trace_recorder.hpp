@@ -14,7 +14,7 @@ namespace meepcu {
 class trace_recorder : public observer {
 public:
   enum { T_CONFIG = 1, T_ARRAY, T_CHUNK, T_SUSC, T_SOURCE, T_DFT, T_METAL, T_CONN, T_FINALIZE,
-         T_STEP, T_EXPECT };
+         T_STEP, T_EXPECT, T_GYRO };
 
   explicit trace_recorder(const char *path) : rb(8) {
     fp = fopen(path, "wb");
@@ -82,6 +82,27 @@ public:
     put32(d.no_omega_0_denominator);
     putd(d.omega_0);
     putd(d.gamma);
+    put(ids.data(), ids.size() * 8);
+    end();
+  }
+  void on_gyrotropic(int i, const meepcu_gyrotropic_desc &d, size_t ntot) {
+    std::vector<int64_t> ids;
+    for (int c = 0; c < 20; ++c)
+      for (int k = 0; k < 5; ++k) ids.push_back(reg(d.sigma[c][k], ntot, rb));
+    for (int c = 0; c < 20; ++c)
+      for (int k = 0; k < 2; ++k)
+        for (int dd = 0; dd < 3; ++dd) ids.push_back(reg(d.P[c][k][dd], ntot, rb));
+    for (int c = 0; c < 20; ++c)
+      for (int k = 0; k < 2; ++k)
+        for (int dd = 0; dd < 3; ++dd) ids.push_back(reg(d.P_prev[c][k][dd], ntot, rb));
+    begin(T_GYRO);
+    put32(i);
+    put32(d.ft);
+    put32(d.model);
+    putd(d.omega_0);
+    putd(d.gamma);
+    putd(d.alpha);
+    put(d.gyro_tensor, sizeof d.gyro_tensor);
     put(ids.data(), ids.size() * 8);
     end();
   }

@@ -43,6 +43,8 @@ for fl in fp64 fp32; do
   gen $fl cond2d 40 2
   gen $fl aniso3d:12 40 2
   gen $fl dft2d:24 40 2
+  gen $fl gyro3d:10 40 2
+  gen $fl gyrosat3d:10 40 2
   gen $fl magdrude3d:12 40 2
   gen $fl magdrude2d:24 40 2
   gen $fl dft3d:12 40 2

@@ -22,6 +22,8 @@ CASES = [("fp64", "vac3d:48", 60, 3, 1e-12), ("fp32", "vac3d:48", 60, 3, 1e-5),
          ("fp64", "bfast3d:20", 100, 2, 1e-12), ("fp32", "bfast3d:20", 100, 2, 1e-5), ("fp64", "bfast2d", 150, 2, 1e-12),
          ("fp64", "cond3d:24", 100, 2, 1e-12), ("fp32", "cond3d:24", 100, 2, 1e-5), ("fp64", "cond2d", 150, 2, 1e-12),
          ("fp64", "magdrude3d:24", 100, 2, 1e-12), ("fp32", "magdrude3d:24", 100, 2, 1e-5), ("fp64", "magdrude2d:60", 200, 2, 1e-12),
+         ("fp64", "gyro3d:20", 100, 2, 1e-12), ("fp32", "gyro3d:20", 100, 2, 1e-5), ("fp64", "gyrodrude3d:20", 100, 2, 1e-12),
+         ("fp64", "gyrosat3d:20", 100, 2, 1e-12),
          ("fp64", "dft2d:60", 200, 2, 1e-12), ("fp32", "dft2d:60", 200, 2, 1e-5), ("fp64", "dft3d:24", 100, 2, 1e-12),
          ("fp64", "aniso3d:24", 100, 2, 1e-12), ("fp32", "aniso3d:24", 100, 2, 1e-5),
          ("fp64_pade", "kerr3d:20", 40, 2, 1e-12), ("fp64_pade", "kr_per3d_rods", 100, 0, 1e-12)]
@@ -63,7 +65,8 @@ def test_known_results_on_gpu():
 @pytest.mark.parametrize("flavour,case,steps,tol", [("fp64", "vac3d:48", 60, 1e-12), ("fp32", "vac3d:48", 60, 1e-5),
                                                     ("fp64", "lorentz3d:32", 50, 1e-12), ("fp64", "wvg2d", 200, 1e-12),
                                                     ("fp64", "kr_per3d_rods", 100, 1e-12), ("fp64", "cond3d:24", 60, 1e-12),
-                                                    ("fp64", "magdrude3d:24", 60, 1e-12), ("fp64", "aniso3d:24", 60, 1e-12)])
+                                                    ("fp64", "magdrude3d:24", 60, 1e-12), ("fp64", "aniso3d:24", 60, 1e-12),
+                                                    ("fp64", "gyrosat3d:20", 60, 1e-12)])
 def test_synchronize_magnetic_fields_on_device(flavour, case, steps, tol):
     """fields::synchronize_magnetic_fields / restore_magnetic_fields (energy_and_flux.cpp:145-177) every 9
     steps: twin A on the reference's CPU path, twin B through meepcu_synchronize_magnetic_fields on the GPU"""

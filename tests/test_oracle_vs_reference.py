@@ -25,6 +25,9 @@ CASES = [("fp64", "vac3d:24", 25, 2), ("fp64", "kr_per3d_rods", 40, 0), ("fp64",
          # complex fields with a Bloch phase
          # mu != 1 (H split from B), a magnetic Lorentzian (pol[H_stuff]) and an electric Drude term
          ("fp64", "magdrude3d", 60, 2), ("fp32", "magdrude3d", 60, 2), ("fp64", "magdrude2d", 80, 2),
+         # gyrotropic media: Lorentzian, Drude and saturated (Landau-Lifshitz-Gilbert) models (susceptibility.cpp:350-603)
+         ("fp64", "gyro3d", 60, 2), ("fp32", "gyro3d", 60, 2), ("fp64", "gyrodrude3d", 60, 2), ("fp64", "gyrosat3d", 60, 2),
+         ("fp32", "gyrosat3d", 60, 2),
          ("fp64", "dft2d", 60, 2), ("fp32", "dft2d", 60, 2), ("fp64", "dft3d", 60, 2), ("fp32", "dft3d", 60, 2),
          # UPSTREAM_PADE against the de-blocked reference flavour (oracle/deblock_pade.py)
          ("fp64_pade", "kerr3d:14", 40, 2), ("fp64_pade", "kerr1d", 80, 0), ("fp64_pade", "kr_per3d_rods", 40, 0)]
@@ -65,7 +68,7 @@ def test_reference_known_answers_through_the_oracle():
 
 SYNC_CASES = [("fp64", "vac3d:32", 40), ("fp64", "wvg2d", 60), ("fp64", "lorentz3d:16", 40), ("fp32", "vac3d_cplx:14", 30),
               ("fp64", "kr_per3d_rods", 40), ("fp64", "cond3d:12", 40), ("fp64", "bfast3d:10", 40), ("fp32", "beta2d", 40),
-              ("fp64", "magdrude3d", 40), ("fp32", "magdrude2d", 40)]
+              ("fp64", "magdrude3d", 40), ("fp32", "magdrude2d", 40), ("fp64", "gyrosat3d", 40)]
 
 
 @pytest.mark.parametrize("flavour,case,steps", SYNC_CASES)

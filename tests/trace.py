@@ -19,7 +19,7 @@ import numpy as np
 
 from meep_nl_b200 import _cabi as A
 
-T_CONFIG, T_ARRAY, T_CHUNK, T_SUSC, T_SOURCE, T_DFT, T_METAL, T_CONN, T_FINALIZE, T_STEP, T_EXPECT = range(1, 12)
+T_CONFIG, T_ARRAY, T_CHUNK, T_SUSC, T_SOURCE, T_DFT, T_METAL, T_CONN, T_FINALIZE, T_STEP, T_EXPECT, T_GYRO = range(1, 13)
 
 
 class Reader:
@@ -192,6 +192,27 @@ class Replay:
                 for k in range(2):
                     tab[c][k] = self.addr(next(it))
         self.b.check(self.b.add_susceptibility(self.ctx, i, C.byref(d)))
+
+    def _t12(self, r):  # GYRO
+        i, ft, model = r.i32(), r.i32(), r.i32()
+        d = A.GyrotropicDesc()
+        d.ft, d.model = ft, model
+        d.omega_0, d.gamma, d.alpha = r.f64(), r.f64(), r.f64()
+        gt = r.f64(9)
+        for a in range(3):
+            for b in range(3):
+                d.gyro_tensor[a][b] = float(gt[3 * a + b])
+        it = iter(r.i64(20 * 5 + 2 * 20 * 2 * 3).tolist())
+        for c in range(20):
+            for k in range(5):
+                d.sigma[c][k] = self.addr(next(it))
+        for name in ("P", "P_prev"):
+            tab = getattr(d, name)
+            for c in range(20):
+                for k in range(2):
+                    for dd in range(3):
+                        tab[c][k][dd] = self.addr(next(it))
+        self.b.check(self.b.add_gyrotropic(self.ctx, i, C.byref(d)))
 
     def _t5(self, r):  # SOURCE
         i = r.i32()
