@@ -373,7 +373,7 @@ def main_ours(args):
     nsrc = len(f.src_times)
     hb = f.host_bytes()
     e2e = {"value": total_cells * K / e2e_s / 1e6, "unit": "Mcell/s",
-           "h2d_bytes_per_step": int(st1.device_bytes / K + 64 * nsrc), "d2h_bytes_per_step": int(hb / K + 8),
+           "h2d_bytes_per_step": int(f.host_bytes(mutable_only=False) / K + 64 * nsrc), "d2h_bytes_per_step": int(hb / K + 8),
            "region": "meepcu_sync_from_host + meepcu_step(%d) + probe read + meepcu_sync_to_host, wall clock" % K}
 
     # ---- roofline of the dominant kernel ----

@@ -854,6 +854,16 @@ class fields:
             for pd in fc.pol_data:
                 for arr in list(pd["P"].values()) + list(pd["P_prev"].values()): n += arr.nbytes
             for dft in fc.dfts: n += dft["dft"].nbytes
+            if not mutable_only:  # what meepcu_sync_from_host uploads on top: materials, sigma, UPML profiles
+                sc = fc.s
+                for arr in list(sc.chi1inv.values()) + list(sc.chi2.values()) + list(sc.chi3.values()) + \
+                        list(sc.sig.values()) + list(sc.kap.values()) + list(sc.siginv.values()):
+                    if id(arr) in seen: continue
+                    seen.add(id(arr)); n += arr.nbytes
+                for (_sus, _ft, arrs) in sc.pols:
+                    for arr in arrs.values():
+                        if id(arr) in seen: continue
+                        seen.add(id(arr)); n += arr.nbytes
         return n
 
     def close(self):
