@@ -168,7 +168,7 @@ class ClockSampler(threading.Thread):
             try:
                 if self.nv is not None:
                     sm = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                    self.samples.append((sm, self._reasons()))
+                    self.samples.append((sm, self._reasons(), time.perf_counter()))
                     self.stop.wait(0.002)
                     continue
                 out = subprocess.run(self.cmd, capture_output=True, text=True, timeout=5).stdout.strip()
@@ -177,18 +177,23 @@ class ClockSampler(threading.Thread):
                     act = [x.lower().startswith("active") for x in p[2:6]]
                     mask = (self.HW_SLOWDOWN * act[0]) | (self.HW_THERMAL * act[1]) | (self.SW_THERMAL * act[2]) | \
                            (self.SW_POWER_CAP * act[3])
-                    self.samples.append((float(p[0]), mask))
+                    self.samples.append((float(p[0]), mask, time.perf_counter()))
                     self.sm_max = float(p[1])
             except Exception:
                 pass
             self.stop.wait(0.05)
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
+        """clocks / throttle reasons seen inside [t0, t1] (perf_counter); the sampler itself starts earlier so
+        that NVML's first-call latency on a fresh box does not eat the window"""
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(s[0] for s in self.samples)
+        inside = [s for s in self.samples if t0 is None or (t0 <= s[2] <= t1)]
+        if not inside:  # window shorter than one sampling period: the sample nearest to it
+            inside = [min(self.samples, key=lambda s: abs(s[2] - 0.5 * (t0 + t1)))]
+        sm = sorted(s[0] for s in inside)
         mask = 0
-        for s in self.samples:
+        for s in inside:
             mask |= s[1]
         names = [(self.HW_SLOWDOWN, "hw_slowdown"), (self.HW_THERMAL, "hw_thermal_slowdown"),
                  (self.SW_THERMAL, "sw_thermal_slowdown"), (self.SW_POWER_CAP, "sw_power_cap")]
@@ -306,6 +311,8 @@ def main_ours(args):
         tid = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8, device="cuda")
         dist.broadcast(tid, 0)
         comm_id = bytes(tid.cpu().tolist())
+    sampler = ClockSampler(local)
+    sampler.start()
     t_setup = time.perf_counter()
     gv, f = build_problem(args, backend, device=local, rank=rank, world=world, comm_id=comm_id)
     K, W = args.steps, max(args.warmup, 3)
@@ -326,21 +333,21 @@ def main_ours(args):
 
     # ---- timed region: K steps, device time from CUDA events recorded inside meepcu_step ----
     smp = f.samples(K)
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
     t0 = time.perf_counter()
+    t_clk0 = t0
     f.step(K, samples=smp)
     barrier()
     wall = time.perf_counter() - t0
     st1 = f.stats()
-    dev_ms = st1.last_step_ms
+    dev_ms = st1.last_step_ms or wall * 1e3  # (0 only with a backend that has no device clock: CPU dry runs)
     # ---- the same K steps again with per-kernel CUDA events (kernels serialised on one stream so
     #      that each duration is the kernel's own): feeds `roofline` ----
     smp_p = f.samples(K)
     backend.check(backend.set_profiling(f.ctx, 1))
     f.step(K, samples=smp_p)
     prof_ms = f.stats().last_step_ms
+    t_clk1 = time.perf_counter()
     sampler.stop.set()
     sampler.join()
     kt = (_cabi.KernelTime * 16)()
@@ -413,7 +420,7 @@ def main_ours(args):
                        "l2": "working set %.1f GB >> 126 MB L2 (no flush needed)" % (st1.device_bytes / 1e9),
                        "parallelism": "1 GPU" if world == 1 else "%d X-slabs, one rank per GPU, NCCL halo exchange (grid %dx%dx%d)" % (world, dims(args)[0] * world, dims(args)[1], dims(args)[2]),
                        "probe_Ez_center": probe, "wall_ms_per_step": wall / K * 1e3},
-            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(st1.kernel_launches - st0.kernel_launches),
+            "clocks": sampler.summary(t_clk0, t_clk1), "e2e": e2e, "gpu_launches": int(st1.kernel_launches - st0.kernel_launches),
             "roofline": roof}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         args.cpu_one_thread = True

@@ -160,6 +160,11 @@ class Backend:
             fn.argtypes = args
         if self.lib.meepcu_abi_version() != ABI_VERSION:
             raise RuntimeError("ABI version mismatch in %s" % self.path)
+        # the default backend (and any MEEPCU_LIBRARY override of it) is the CUDA library: the CPU oracle
+        # is test infrastructure and is only ever loaded by an explicit path from tests/, smoke() or bench's CPU arm
+        if path is None and not self.lib.meepcu_backend().decode().startswith("cuda"):
+            raise RuntimeError("%s is not a CUDA build of the ABI (%s): there is no CPU fallback"
+                               % (self.path, self.lib.meepcu_backend().decode()))
 
     @property
     def name(self) -> str:
