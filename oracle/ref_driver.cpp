@@ -699,6 +699,46 @@ int main(int argc, char **argv) {
     delete A;
     delete B;
   }
+#ifdef MEEPCU_DROPIN
+  else if (mode == "dropin") {
+    // the PATCHED reference library (oracle/_ref/*_dropin: meep_nl_b200/shim/dropin_patch.py applied):
+    // twin B is stepped by calling the reference's own fields::step(), which delegates to --lib
+    if (lib.empty()) { fprintf(stderr, "--lib required\n"); return 2; }
+    problem *A = build(cas, nchunks), *B = build(cas, nchunks);
+    for (int i = 0; i < warmup; ++i) { A->f->step(); B->f->step(); } // drop-in off: both on the CPU
+    double t0 = wall_time();
+    for (int i = 0; i < steps; ++i) A->f->step();
+    double t1 = wall_time();
+    fields::gpu_enable(lib.c_str(), nl_mode, device);
+    double mid_ref = 0, mid_abi = 0;
+    for (int i = 0; i < steps; ++i) {
+      B->f->step(); // <- the seam: unchanged caller code, device underneath
+      if (i == steps / 2) { // a host-side reader in mid-run: sync, read through the reference's own get_field
+        B->f->gpu_sync_to_host();
+        mid_abi = probe_value(B);
+      }
+    }
+    B->f->gpu_sync_to_host();
+    double t2 = wall_time();
+    const bool attached = B->f->gpu != 0;
+    std::vector<marray> ma = collect(*A->f), mb = collect(*B->f);
+    cmp_result r = compare(ma, mb);
+    double relL2 = r.sum_r2 > 0 ? sqrt(r.sum_d2 / r.sum_r2) : sqrt(r.sum_d2);
+    fields::gpu_enable(NULL);
+    (void)mid_ref;
+    fprintf(jf,
+            "{\"mode\":\"dropin\",\"backend\":\"%s\",\"case\":\"%s\",\"realnum_bytes\":%d,\"steps\":%d,"
+            "\"warmup\":%d,\"cells\":%ld,\"num_chunks\":%d,\"arrays\":%zu,\"elements\":%zu,"
+            "\"mismatched_arrays\":%zu,\"mismatched_elements\":%zu,\"max_abs_diff\":%.6g,\"rel_l2\":%.6g,"
+            "\"first_bad\":\"%s\",\"ref_seconds\":%.6f,\"abi_seconds\":%.6f,\"probe_ref\":%.17g,"
+            "\"probe_abi\":%.17g,\"probe_mid\":%.17g,\"attached\":%d,\"t_ref\":%d,\"t_abi\":%d}\n",
+            "dropin", cas.c_str(), (int)sizeof(realnum), steps, warmup, A->cells, A->f->num_chunks, r.narrays,
+            r.nelems, r.nmismatch_arrays, r.nmismatch_elems, r.max_abs, relL2, r.first_bad.c_str(), t1 - t0,
+            t2 - t1, probe_value(A), probe_value(B), mid_abi, (int)attached, A->f->t, B->f->t);
+    delete A;
+    delete B; // ~fields() -> gpu_detach()
+  }
+#endif
   else {
     fprintf(stderr, "unknown mode %s\n", mode.c_str());
     return 2;

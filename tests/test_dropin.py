@@ -1,0 +1,41 @@
+"""The drop-in seam itself: oracle/_ref/fp64_dropin is the reference library with the maintainer's patch
+(meep_nl_b200/shim/dropin_patch.py: one data member, three methods, a one-line prologue in fields::step())
+applied in the compiler's input pipe.  Twin B is stepped by the reference's OWN `fields::step()` -- unchanged
+caller code -- which delegates to the C ABI library; a host-side reader runs in mid-simulation; at the end
+every array must equal twin A's (stepped by the unpatched code path of the same library)."""
+import json
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+from conftest import CUDA_LIB, ORACLE_LIB, ref_driver
+
+
+def run(lib, case, steps, nl=0):
+    drv = ref_driver("fp64_dropin")
+    if drv is None:
+        pytest.skip("oracle/_ref/fp64_dropin not built (reference tree absent)")
+    with tempfile.NamedTemporaryFile(suffix=".json") as tf:
+        env = dict(os.environ, OMP_NUM_THREADS="4")
+        subprocess.run([drv, "--mode", "dropin", "--lib", lib, "--case", case, "--steps", str(steps), "--warmup", "2",
+                        "--nl", str(nl), "--json", tf.name], check=True, env=env, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, timeout=900)
+        return json.load(open(tf.name))
+
+
+@pytest.mark.parametrize("case", ["vac3d:32", "lorentz3d:16", "wvg2d", "nrslab3d:14", "kr_xper_ypml3d", "gyro3d:12", "dft3d:12"])
+def test_patched_reference_steps_through_the_abi(case):
+    d = run(ORACLE_LIB, case, 40)
+    assert d["attached"] == 1 and d["t_ref"] == d["t_abi"]
+    assert d["arrays"] > 0 and d["mismatched_elements"] == 0, d
+    assert d["probe_ref"] == d["probe_abi"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,tol", [("vac3d:48", 1e-12), ("lorentz3d:32", 1e-12), ("nrslab3d:20", 1e-12), ("aniso3d:24", 1e-12)])
+def test_patched_reference_steps_on_the_gpu(case, tol):
+    d = run(CUDA_LIB, case, 60)
+    assert d["attached"] == 1 and d["t_ref"] == d["t_abi"]
+    assert d["rel_l2"] <= tol, d
