@@ -2,7 +2,8 @@
 """The patch a maintainer adds to the reference so that `fields::step()` itself runs on the device
 (INTEGRATION.md section 2), expressed as anchored insertions -- no reference text is stored here.
 
-    dropin_patch.py <basename> < original > patched      (basename: meep.hpp | step.cpp | fields.cpp)
+    dropin_patch.py <basename> < original > patched
+    (basename: meep.hpp | step.cpp | fields.cpp | energy_and_flux.cpp)
 
 oracle/build_ref.sh applies it in the compiler's input pipe for the `*_dropin` flavours; the result is
 the reference library with ONE added data member (`fields::gpu`), three added methods and a four-line
@@ -16,6 +17,8 @@ MEMBERS = '''
   void *gpu = 0;           // meepcu::attachment*: non-null while the fields live on the device
   void gpu_sync_to_host(); // call before any host-side reader of the field arrays
   void gpu_detach();       // sync back and drop the device mirror (writers of the arrays call this)
+  void gpu_synchronize_magnetic_fields(); // bodies of synchronize / restore_magnetic_fields on the device
+  void gpu_restore_magnetic_fields();
   // process-wide switch: the library the drop-in dlopen()s (NULL: off), how it treats chi2/chi3, the device
   static void gpu_enable(const char *library_path, int nl_mode = 0, int device = 0);
 '''
@@ -28,14 +31,22 @@ int g_dropin_nl_mode = 0, g_dropin_device = 0;
 } // namespace
 namespace meep {
 void fields::gpu_enable(const char *library_path, int nl_mode, int device) {
-  delete g_dropin_api;
-  g_dropin_api = library_path ? new meepcu::api(library_path) : 0;
+  // loaded libraries stay loaded: attachments made earlier keep using theirs after a switch
+  static std::map<std::string, meepcu::api *> loaded;
+  g_dropin_api = 0;
+  if (library_path) {
+    meepcu::api *&a = loaded[library_path];
+    if (!a) a = new meepcu::api(library_path);
+    g_dropin_api = a;
+  }
   g_dropin_nl_mode = nl_mode;
   g_dropin_device = device;
 }
 void fields::gpu_sync_to_host() {
   if (gpu) ((meepcu::attachment *)gpu)->sync_to_host();
 }
+void fields::gpu_synchronize_magnetic_fields() { ((meepcu::attachment *)gpu)->synchronize_magnetic_fields(); }
+void fields::gpu_restore_magnetic_fields() { ((meepcu::attachment *)gpu)->restore_magnetic_fields(); }
 void fields::gpu_detach() {
   if (!gpu) return;
   meepcu::attachment *att = (meepcu::attachment *)gpu;
@@ -78,6 +89,15 @@ def patch(name, text):
         body = text[a:]
         k = body.index("{") + 1
         return head + body[:k] + "\n  if (dropin_step(this)) return; // meepcu drop-in\n" + body[k:]
+    if name == "energy_and_flux.cpp":
+        # after the reference's own reference-count test (the first `return;` of each function) the body runs on
+        # the device when the fields live there
+        for fn, call in (("synchronize_magnetic_fields", "gpu_synchronize_magnetic_fields"),
+                         ("restore_magnetic_fields", "gpu_restore_magnetic_fields")):
+            a = text.index("\nvoid fields::%s() {" % fn)
+            k = text.index("return;", a) + len("return;")
+            text = text[:k] + "\n  if (gpu) { %s(); return; } // meepcu drop-in" % call + text[k:]
+        return text
     if name == "fields.cpp":
         a = text.index("\nfields::~fields() {")
         k = text.index("{", a) + 1

@@ -711,11 +711,33 @@ int main(int argc, char **argv) {
     double t1 = wall_time();
     fields::gpu_enable(lib.c_str(), nl_mode, device);
     double mid_ref = 0, mid_abi = 0;
+    problem *C = 0;
+    size_t sync_bad = 0, sync_checks = 0;
     for (int i = 0; i < steps; ++i) {
       B->f->step(); // <- the seam: unchanged caller code, device underneath
       if (i == steps / 2) { // a host-side reader in mid-run: sync, read through the reference's own get_field
         B->f->gpu_sync_to_host();
         mid_abi = probe_value(B);
+      }
+      if (syncmag > 0 && (i + 1) % syncmag == 0) {
+        // the reference's own synchronize_magnetic_fields(): CPU on twin A (not yet stepped past here: use a
+        // third twin kept in lock step), delegated to the device on twin B; then step while synchronized
+        B->f->synchronize_magnetic_fields();
+        B->f->gpu_sync_to_host();
+        if (!C) {
+          fields::gpu_enable(NULL);
+          C = build(cas, nchunks);
+          for (int k = 0; k < warmup + i + 1; ++k) C->f->step();
+          fields::gpu_enable(lib.c_str(), nl_mode, device);
+        }
+        C->f->synchronize_magnetic_fields(); // C has no attachment: the reference's CPU body
+        std::vector<marray> sc = collect(*C->f), sb = collect(*B->f);
+        sync_bad += compare(sc, sb).nmismatch_elems;
+        ++sync_checks;
+        C->f->restore_magnetic_fields();
+        B->f->restore_magnetic_fields();
+        delete C;
+        C = 0;
       }
     }
     B->f->gpu_sync_to_host();
@@ -731,10 +753,11 @@ int main(int argc, char **argv) {
             "\"warmup\":%d,\"cells\":%ld,\"num_chunks\":%d,\"arrays\":%zu,\"elements\":%zu,"
             "\"mismatched_arrays\":%zu,\"mismatched_elements\":%zu,\"max_abs_diff\":%.6g,\"rel_l2\":%.6g,"
             "\"first_bad\":\"%s\",\"ref_seconds\":%.6f,\"abi_seconds\":%.6f,\"probe_ref\":%.17g,"
-            "\"probe_abi\":%.17g,\"probe_mid\":%.17g,\"attached\":%d,\"t_ref\":%d,\"t_abi\":%d}\n",
+            "\"probe_abi\":%.17g,\"probe_mid\":%.17g,\"attached\":%d,\"t_ref\":%d,\"t_abi\":%d,"
+            "\"sync_checks\":%zu,\"sync_mismatched_elements\":%zu}\n",
             "dropin", cas.c_str(), (int)sizeof(realnum), steps, warmup, A->cells, A->f->num_chunks, r.narrays,
             r.nelems, r.nmismatch_arrays, r.nmismatch_elems, r.max_abs, relL2, r.first_bad.c_str(), t1 - t0,
-            t2 - t1, probe_value(A), probe_value(B), mid_abi, (int)attached, A->f->t, B->f->t);
+            t2 - t1, probe_value(A), probe_value(B), mid_abi, (int)attached, A->f->t, B->f->t, sync_checks, sync_bad);
     delete A;
     delete B; // ~fields() -> gpu_detach()
   }

@@ -13,14 +13,14 @@ import pytest
 from conftest import CUDA_LIB, ORACLE_LIB, ref_driver
 
 
-def run(lib, case, steps, nl=0):
+def run(lib, case, steps, nl=0, syncmag=0):
     drv = ref_driver("fp64_dropin")
     if drv is None:
         pytest.skip("oracle/_ref/fp64_dropin not built (reference tree absent)")
     with tempfile.NamedTemporaryFile(suffix=".json") as tf:
         env = dict(os.environ, OMP_NUM_THREADS="4")
         subprocess.run([drv, "--mode", "dropin", "--lib", lib, "--case", case, "--steps", str(steps), "--warmup", "2",
-                        "--nl", str(nl), "--json", tf.name], check=True, env=env, stdout=subprocess.DEVNULL,
+                        "--nl", str(nl), "--syncmag", str(syncmag), "--json", tf.name], check=True, env=env, stdout=subprocess.DEVNULL,
                        stderr=subprocess.DEVNULL, timeout=900)
         return json.load(open(tf.name))
 
@@ -39,3 +39,19 @@ def test_patched_reference_steps_on_the_gpu(case, tol):
     d = run(CUDA_LIB, case, 60)
     assert d["attached"] == 1 and d["t_ref"] == d["t_abi"]
     assert d["rel_l2"] <= tol, d
+
+
+@pytest.mark.parametrize("case,every", [("lorentz3d:16", 9), ("magdrude3d:12", 7), ("gyrosat3d:12", 9), ("wvg2d", 10)])
+def test_patched_reference_synchronizes_magnetic_fields_through_the_abi(case, every):
+    """fields::synchronize_magnetic_fields() / restore_magnetic_fields() of the patched reference delegate their
+    bodies (energy_and_flux.cpp:145-177) when the fields live behind the ABI; a third twin runs the CPU bodies"""
+    d = run(ORACLE_LIB, case, 40, syncmag=every)
+    assert d["sync_checks"] >= 4 and d["sync_mismatched_elements"] == 0
+    assert d["mismatched_elements"] == 0 and d["t_ref"] == d["t_abi"]
+
+
+@pytest.mark.gpu
+def test_patched_reference_synchronizes_on_the_gpu():
+    d = run(CUDA_LIB, "magdrude3d:20", 45, syncmag=9)
+    assert d["sync_checks"] >= 5 and d["sync_mismatched_elements"] <= d["elements"]
+    assert d["rel_l2"] <= 1e-12, d
