@@ -3,7 +3,7 @@
 (INTEGRATION.md section 2), expressed as anchored insertions -- no reference text is stored here.
 
     dropin_patch.py <basename> < original > patched
-    (basename: meep.hpp | step.cpp | fields.cpp | energy_and_flux.cpp)
+    (basename: meep.hpp | step.cpp | fields.cpp | energy_and_flux.cpp | loop_in_chunks.cpp | monitor.cpp)
 
 oracle/build_ref.sh applies it in the compiler's input pipe for the `*_dropin` flavours; the result is
 the reference library with ONE added data member (`fields::gpu`), three added methods and a four-line
@@ -15,7 +15,7 @@ import sys
 MEMBERS = '''
   // ---- meepcu drop-in (meep_nl_b200/shim/dropin_patch.py) ----
   void *gpu = 0;           // meepcu::attachment*: non-null while the fields live on the device
-  void gpu_sync_to_host(); // call before any host-side reader of the field arrays
+  void gpu_sync_to_host(); // before a host-side reader of the field arrays (no-op unless the device has stepped since)
   void gpu_detach();       // sync back and drop the device mirror (writers of the arrays call this)
   void gpu_synchronize_magnetic_fields(); // bodies of synchronize / restore_magnetic_fields on the device
   void gpu_restore_magnetic_fields();
@@ -43,7 +43,7 @@ void fields::gpu_enable(const char *library_path, int nl_mode, int device) {
   g_dropin_device = device;
 }
 void fields::gpu_sync_to_host() {
-  if (gpu) ((meepcu::attachment *)gpu)->sync_to_host();
+  if (gpu) ((meepcu::attachment *)gpu)->sync_to_host_if_stale();
 }
 void fields::gpu_synchronize_magnetic_fields() { ((meepcu::attachment *)gpu)->synchronize_magnetic_fields(); }
 void fields::gpu_restore_magnetic_fields() { ((meepcu::attachment *)gpu)->restore_magnetic_fields(); }
@@ -98,6 +98,14 @@ def patch(name, text):
             k = text.index("return;", a) + len("return;")
             text = text[:k] + "\n  if (gpu) { %s(); return; } // meepcu drop-in" % call + text[k:]
         return text
+    if name == "loop_in_chunks.cpp":  # the iterator behind integrate / get_array_slice / output_hdf5 / energy / flux_in_box
+        a = text.index("\nvoid fields::loop_in_chunks(")
+        k = text.index("{", a) + 1
+        return text[:k] + "\n  gpu_sync_to_host(); // meepcu drop-in: readers see the device's state\n" + text[k:]
+    if name == "monitor.cpp":  # point probes: every get_field overload ends in the (component, ivec) one
+        a = text.index("fields::get_field(component c, const ivec &")
+        k = text.index("{", a) + 1
+        return text[:k] + "\n  const_cast<fields *>(this)->gpu_sync_to_host(); // meepcu drop-in\n" + text[k:]
     if name == "fields.cpp":
         a = text.index("\nfields::~fields() {")
         k = text.index("{", a) + 1

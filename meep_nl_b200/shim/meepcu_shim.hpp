@@ -162,6 +162,7 @@ public:
     if (obs) obs->on_step(n, nsrc, smp.data());
     check(a.step(ctx, n, nsrc, nsrc ? smp.data() : 0));
     f.t += n;
+    host_stale = true;
   }
   // == the body of fields::synchronize_magnetic_fields / restore_magnetic_fields
   //    (src/energy_and_flux.cpp:145-177) on the device; the caller keeps the reference's counter
@@ -179,9 +180,20 @@ public:
       put(smp[j].dipole_H, st->dipole());
     }
     check(a.synchronize_magnetic_fields(ctx, nsrc, nsrc ? smp.data() : 0));
+    host_stale = true;
   }
-  void restore_magnetic_fields() { check(a.restore_magnetic_fields(ctx)); }
-  void sync_to_host() { check(a.sync_to_host(ctx)); }
+  void restore_magnetic_fields() {
+    check(a.restore_magnetic_fields(ctx));
+    host_stale = true;
+  }
+  void sync_to_host() {
+    check(a.sync_to_host(ctx));
+    host_stale = false;
+  }
+  // for readers that may be called many times between steps (fields::get_field, loop_in_chunks ...)
+  void sync_to_host_if_stale() {
+    if (host_stale) sync_to_host();
+  }
   // only the DFT accumulators: all that dft_flux::flux / dft_energy / near2far / save_dft_hdf5 read
   void sync_dft_to_host() { check(a.sync_subset(ctx, 1, MEEPCU_SYNC_DFT)); }
   // fields only (get_array_slice, energy_in_box, flux_in_box ...)
@@ -290,6 +302,7 @@ private:
   api &a;
   meepcu_ctx *ctx;
   observer *obs;
+  bool host_stale = false; // the device has advanced since the last sync_to_host
   std::vector<meep::src_time *> src_times;
   std::vector<std::vector<double> > keep_amp; // storage handed to the ABI during description
 

@@ -707,17 +707,23 @@ int main(int argc, char **argv) {
     problem *A = build(cas, nchunks), *B = build(cas, nchunks);
     for (int i = 0; i < warmup; ++i) { A->f->step(); B->f->step(); } // drop-in off: both on the CPU
     double t0 = wall_time();
-    for (int i = 0; i < steps; ++i) A->f->step();
+    double mid_ref = 0, mid_abi = 0, mid_energy_ref = 0, mid_energy_abi = 0;
+    for (int i = 0; i < steps; ++i) {
+      A->f->step();
+      if (i == steps / 2) {
+        mid_ref = probe_value(A);
+        mid_energy_ref = A->f->electric_energy_in_box(A->gv.surroundings());
+      }
+    }
     double t1 = wall_time();
     fields::gpu_enable(lib.c_str(), nl_mode, device);
-    double mid_ref = 0, mid_abi = 0;
     problem *C = 0;
     size_t sync_bad = 0, sync_checks = 0;
     for (int i = 0; i < steps; ++i) {
       B->f->step(); // <- the seam: unchanged caller code, device underneath
-      if (i == steps / 2) { // a host-side reader in mid-run: sync, read through the reference's own get_field
-        B->f->gpu_sync_to_host();
-        mid_abi = probe_value(B);
+      if (i == steps / 2) { // host-side readers in mid-run, called like any user would: the patched get_field and
+        mid_abi = probe_value(B); // loop_in_chunks (behind electric_energy_in_box) fetch the device's state themselves
+        mid_energy_abi = B->f->electric_energy_in_box(B->gv.surroundings());
       }
       if (syncmag > 0 && (i + 1) % syncmag == 0) {
         // the reference's own synchronize_magnetic_fields(): CPU on twin A (not yet stepped past here: use a
@@ -747,17 +753,18 @@ int main(int argc, char **argv) {
     cmp_result r = compare(ma, mb);
     double relL2 = r.sum_r2 > 0 ? sqrt(r.sum_d2 / r.sum_r2) : sqrt(r.sum_d2);
     fields::gpu_enable(NULL);
-    (void)mid_ref;
     fprintf(jf,
             "{\"mode\":\"dropin\",\"backend\":\"%s\",\"case\":\"%s\",\"realnum_bytes\":%d,\"steps\":%d,"
             "\"warmup\":%d,\"cells\":%ld,\"num_chunks\":%d,\"arrays\":%zu,\"elements\":%zu,"
             "\"mismatched_arrays\":%zu,\"mismatched_elements\":%zu,\"max_abs_diff\":%.6g,\"rel_l2\":%.6g,"
             "\"first_bad\":\"%s\",\"ref_seconds\":%.6f,\"abi_seconds\":%.6f,\"probe_ref\":%.17g,"
             "\"probe_abi\":%.17g,\"probe_mid\":%.17g,\"attached\":%d,\"t_ref\":%d,\"t_abi\":%d,"
-            "\"sync_checks\":%zu,\"sync_mismatched_elements\":%zu}\n",
+            "\"sync_checks\":%zu,\"sync_mismatched_elements\":%zu,\"probe_mid_ref\":%.17g,"
+            "\"energy_mid_ref\":%.17g,\"energy_mid_abi\":%.17g}\n",
             "dropin", cas.c_str(), (int)sizeof(realnum), steps, warmup, A->cells, A->f->num_chunks, r.narrays,
             r.nelems, r.nmismatch_arrays, r.nmismatch_elems, r.max_abs, relL2, r.first_bad.c_str(), t1 - t0,
-            t2 - t1, probe_value(A), probe_value(B), mid_abi, (int)attached, A->f->t, B->f->t, sync_checks, sync_bad);
+            t2 - t1, probe_value(A), probe_value(B), mid_abi, (int)attached, A->f->t, B->f->t, sync_checks, sync_bad,
+            mid_ref, mid_energy_ref, mid_energy_abi);
     delete A;
     delete B; // ~fields() -> gpu_detach()
   }

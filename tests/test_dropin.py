@@ -31,6 +31,9 @@ def test_patched_reference_steps_through_the_abi(case):
     assert d["attached"] == 1 and d["t_ref"] == d["t_abi"]
     assert d["arrays"] > 0 and d["mismatched_elements"] == 0, d
     assert d["probe_ref"] == d["probe_abi"]
+    # mid-run readers called straight on the patched reference (no explicit sync): get_field and, through
+    # loop_in_chunks, electric_energy_in_box
+    assert d["probe_mid"] == d["probe_mid_ref"] and d["energy_mid_abi"] == d["energy_mid_ref"]
 
 
 @pytest.mark.gpu
@@ -39,6 +42,8 @@ def test_patched_reference_steps_on_the_gpu(case, tol):
     d = run(CUDA_LIB, case, 60)
     assert d["attached"] == 1 and d["t_ref"] == d["t_abi"]
     assert d["rel_l2"] <= tol, d
+    assert abs(d["probe_mid"] - d["probe_mid_ref"]) <= tol * max(1.0, abs(d["probe_mid_ref"]))
+    assert abs(d["energy_mid_abi"] - d["energy_mid_ref"]) <= 1e-9 * max(1e-30, abs(d["energy_mid_ref"]))
 
 
 @pytest.mark.parametrize("case,every", [("lorentz3d:16", 9), ("magdrude3d:12", 7), ("gyrosat3d:12", 9), ("wvg2d", 10)])
