@@ -59,6 +59,9 @@ void fields::gpu_detach() {
 // stepping phases (restore, step, re-synchronize: src/step.cpp:36-41,128-134; NaN test :138-139).
 static bool dropin_step(fields *f) {
   if (!g_dropin_api || f->is_phasing()) return false;
+  // a source / DFT monitor / polarisation added or arrays re-allocated since the last step: the host arrays
+  // become the truth again (sync back), and the object graph is described anew
+  if (f->gpu && ((meepcu::attachment *)f->gpu)->description_outdated()) f->gpu_detach();
   if (!f->gpu) f->gpu = new meepcu::attachment(*f, *g_dropin_api, g_dropin_nl_mode, g_dropin_device);
   meepcu::attachment *att = (meepcu::attachment *)f->gpu;
   const int saved = f->synchronized_magnetic_fields;

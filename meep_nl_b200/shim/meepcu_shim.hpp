@@ -190,6 +190,10 @@ public:
     check(a.sync_to_host(ctx));
     host_stale = false;
   }
+  // Has the host object graph changed since it was described (a source, DFT monitor or polarisation added,
+  // arrays re-allocated: the reference marks the latter with chunk_connections_valid = false,
+  // boundaries.cpp:171-183)?  Then the owner drops this attachment and makes a new one.
+  bool description_outdated() const { return !f.chunk_connections_valid || fingerprint() != described; }
   // for readers that may be called many times between steps (fields::get_field, loop_in_chunks ...)
   void sync_to_host_if_stale() {
     if (host_stale) sync_to_host();
@@ -298,6 +302,28 @@ public:
   }
 
 private:
+  // counts of everything the description enumerates
+  std::vector<size_t> fingerprint() const {
+    std::vector<size_t> fp;
+    size_t nst = 0;
+    for (meep::src_time *st = f.sources; st; st = st->next) ++nst;
+    fp.push_back(nst);
+    for (int i = 0; i < f.num_chunks; i++) {
+      meep::fields_chunk *fc = f.chunks[i];
+      size_t nd = 0, np = 0;
+      for (meep::dft_chunk *dc = fc->dft_chunks; dc; dc = dc->next_in_chunk) ++nd;
+      for (int ft = 0; ft < 2; ++ft)
+        for (meep::polarization_state *p = fc->pol[ft]; p; p = p->next) ++np;
+      fp.push_back(nd);
+      fp.push_back(np);
+      for (int ft = 0; ft < meep::NUM_FIELD_TYPES; ++ft) {
+        fp.push_back(fc->sources[ft].size());
+        for (const meep::src_vol &sv : fc->sources[ft]) fp.push_back(sv.num_points());
+      }
+    }
+    return fp;
+  }
+  std::vector<size_t> described;
   meep::fields &f;
   api &a;
   meepcu_ctx *ctx;
@@ -539,6 +565,7 @@ private:
     }
     if (obs) obs->on_finalize();
     check(a.finalize(ctx));
+    described = fingerprint();
   }
 };
 

@@ -554,6 +554,17 @@ static cmp_result compare(const std::vector<marray> &A, const std::vector<marray
   return r;
 }
 
+// a flux plane through the cell centre, normal to the last direction of the grid (a point in 1-D)
+static volume mid_plane(const grid_volume &gv) {
+  const vec c = gv.center();
+  const volume s = gv.surroundings();
+  const vec lo = s.get_min_corner(), hi = s.get_max_corner();
+  if (gv.dim == D3)
+    return volume(vec(0.5 * (lo.x() + c.x()), 0.5 * (lo.y() + c.y()), c.z()), vec(0.5 * (hi.x() + c.x()), 0.5 * (hi.y() + c.y()), c.z()));
+  if (gv.dim == D2) return volume(vec(0.5 * (lo.x() + c.x()), c.y()), vec(0.5 * (hi.x() + c.x()), c.y()));
+  return volume(c, c);
+}
+
 static double probe_value(problem *p) {
   component c = p->gv.dim == D1 ? Ex : Ez;
   return real(p->f->get_field(c, p->gv.center()));
@@ -569,7 +580,7 @@ int main(int argc, char **argv) {
 #pragma omp parallel
   { _mm_setcsr(_mm_getcsr() | 0x00008040u); }
   std::string mode = "ref", cas = "vac3d:32", lib, json, record;
-  int steps = 20, warmup = 0, nchunks = 0, nl_mode = MEEPCU_NL_FORK_LITERAL, device = 0, batch = 0, syncmag = 0;
+  int steps = 20, warmup = 0, nchunks = 0, nl_mode = MEEPCU_NL_FORK_LITERAL, device = 0, batch = 0, syncmag = 0, addsrc = 0;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     if (a == "--mode") mode = argv[++i];
@@ -584,6 +595,7 @@ int main(int argc, char **argv) {
     else if (a == "--device") device = atoi(argv[++i]);
     else if (a == "--batch") batch = atoi(argv[++i]);
     else if (a == "--syncmag") syncmag = atoi(argv[++i]);
+    else if (a == "--addsrc") addsrc = atoi(argv[++i]);
     else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
   }
   if (!batch) batch = steps;
@@ -714,6 +726,10 @@ int main(int argc, char **argv) {
         mid_ref = probe_value(A);
         mid_energy_ref = A->f->electric_energy_in_box(A->gv.surroundings());
       }
+      if (i == steps / 3 && addsrc) { // a source and a flux monitor added in mid-run
+        A->f->add_point_source(A->gv.dim == D1 ? Ex : Ez, 0.22, 0.2, 0.0, 4.0, A->gv.center(), 0.7);
+        A->fluxes.push_back(A->f->add_dft_flux_plane(mid_plane(A->gv), 0.15, 0.3, 3));
+      }
     }
     double t1 = wall_time();
     fields::gpu_enable(lib.c_str(), nl_mode, device);
@@ -721,6 +737,10 @@ int main(int argc, char **argv) {
     size_t sync_bad = 0, sync_checks = 0;
     for (int i = 0; i < steps; ++i) {
       B->f->step(); // <- the seam: unchanged caller code, device underneath
+      if (i == steps / 3 && addsrc) { // same calls on the twin that lives on the device: the next step re-attaches
+        B->f->add_point_source(B->gv.dim == D1 ? Ex : Ez, 0.22, 0.2, 0.0, 4.0, B->gv.center(), 0.7);
+        B->fluxes.push_back(B->f->add_dft_flux_plane(mid_plane(B->gv), 0.15, 0.3, 3));
+      }
       if (i == steps / 2) { // host-side readers in mid-run, called like any user would: the patched get_field and
         mid_abi = probe_value(B); // loop_in_chunks (behind electric_energy_in_box) fetch the device's state themselves
         mid_energy_abi = B->f->electric_energy_in_box(B->gv.surroundings());
