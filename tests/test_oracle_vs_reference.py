@@ -50,12 +50,16 @@ def test_shim_plus_oracle_equals_reference(flavour, case, steps, warmup):
 
 
 def test_reference_known_answers_through_the_oracle():
-    """tests/known_results.cpp:155-169: three of the reference's own golden numbers, recomputed by
+    """tests/known_results.cpp:155-169: the reference's own golden numbers, recomputed by
     stepping through the C ABI (oracle backend) instead of fields::step."""
     drv = ref_driver("fp64")
     if drv is None:
         pytest.skip("oracle/_ref/fp64 not built")
-    known = {"kr_metal3d": (-41.8057, 200), "kr_pml2d": (0.883776, 600), "kr_per3d_rods": (-103.844, 600)}
+    # the twelve field values of the list (the thirteenth is an energy integral, host code outside the path)
+    known = {"kr_polariton1d": (-0.0894851, 200), "kr_metal2d": (5.20605, 200), "kr_pml2d": (0.883776, 600),
+             "kr_xper2d": (0.110425, 600), "kr_per2d_rods": (-4.78767, 600), "kr_per2d": (1.12502, 600),
+             "kr_xper_ypml2d": (0.608815, 600), "kr_metal3d": (-41.8057, 200), "kr_xper3d": (-100.758, 600),
+             "kr_xper_ypml3d": (-101.398, 600), "kr_per3d_rods": (-103.844, 600), "kr_per3d": (-99.1618, 600)}
     for case, (val, steps) in known.items():
         with tempfile.NamedTemporaryFile(suffix=".json") as tf:
             subprocess.run([drv, "--mode", "shim", "--lib", ORACLE_LIB, "--case", case, "--steps", str(steps),
