@@ -2,7 +2,7 @@
 """bench.py -- Mcell-updates/s of the fused E+H time step (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload vac3d|diel3d|lorentz3d|nr3d] [--size 256] [--dtype f64|f32]
+                    [--workload vac3d|diel3d|lorentz3d|nr3d|kerr3d|phc3d] [--size 256] [--dtype f64|f32]
 
 One "step" = one full `fields::step()` (B, H, D, E half-updates, boundaries, DFT) over the whole
 grid.  Default workload = BASELINE configs[1]: 3D vacuum cube 256^3, PML 1.0 on all faces
@@ -117,6 +117,16 @@ def build_problem(args, backend, device=0, rank=0, world=1, comm_id=None):
         f.add_point_source(Ez, 0.3, 0.2, 0.0, 4.0, c, amp)
         f.add_point_source(Ex, 0.3, 0.2, 0.0, 4.0, (c[0] + 0.25, c[1] + 0.1, c[2]), amp)
         f.add_point_source(Ey, 0.3, 0.2, 0.0, 4.0, (c[0], c[1] + 0.25, c[2] + 0.1), amp)
+    elif w == "kerr3d":  # BASELINE configs[2], variant 3b: upstream's Kerr (chi3) Pade update, diagonal eps
+        from meep_nl_b200._cabi import NL_UPSTREAM_PADE
+        s = H.structure(gv, lambda x, y, z: 2.25 + 0 * x, pml=1.0, realnum=rt)
+        s.set_chi2(lambda x, y, z: 0.0 * x)
+        s.set_chi3(lambda x, y, z: 1e-2 * ((z > L / 3) & (z < 2 * L / 3)))
+        cr = [rank_of(sc) for sc in s.chunks] if rank_of else None
+        f = _fields(s, backend, nl_mode=NL_UPSTREAM_PADE, device=device, rank=rank, nranks=world, chunk_rank=cr,
+                    comm_id=comm_id)
+        f.use_real_fields()
+        f.add_point_source(Ex, 1.0 / 3.0, 0.2, 0.0, 4.0, gv.center(), 1.0)
     elif w == "phc3d":  # BASELINE configs[4] shape: eps-12 slab, PML in z only, periodic x,y (n x n x 1.5n)
         zlo, zhi = 0.75 * L - 0.25, 0.75 * L + 0.25
         s = H.structure(gv, lambda x, y, z: 1.0 + 11.0 * ((z > zlo) & (z < zhi)), pml=args.pml or 1.0,
@@ -213,6 +223,7 @@ def workload_name(args):
 
 
 # reference-driver case per workload, and the largest size the CPU arm runs in a bounded time
+# (kerr3d needs the de-blocked Pade flavour of the reference: its CPU arm falls back to the oracle port)
 REF_CASES = {"vac3d": ("vac3d:%d", 256), "lorentz3d": ("lorentz3d:%d:100", 192), "nr3d": ("nrslab3d:%d", 96),
              "phc3d": ("phc3d:%d:1.0", 160)}
 
