@@ -46,6 +46,8 @@ def make_transport():
 
 def build(backend, rank, nranks, comm_id, case, rt):
     n = (24 * max(nranks, 2), 20, 18)
+    if case.startswith("beta2d"):
+        return build_beta2d(backend, rank, nranks, comm_id, case, rt)
     gv = H.vol3d(n[0] / 10.0, n[1] / 10.0, n[2] / 10.0, 10)
     split, rank_of = None, None
     if nranks > 1:
@@ -66,6 +68,26 @@ def build(backend, rank, nranks, comm_id, case, rt):
     c = gv.center()
     f.add_point_source(A.Ez, 0.3, 0.2, 0.0, 4.0, (c[0] - 0.35, c[1], c[2] + 0.05), 1.0)
     f.add_point_source(A.Hy, 0.25, 0.2, 0.0, 4.0, (c[0] + 0.3, c[1] + 0.05, c[2] + 0.05), 0.5)
+    return gv, f
+
+
+def build_beta2d(backend, rank, nranks, comm_id, case, rt):
+    """2-D cell with exp(i beta z) dependence (TE and TM coupled), PML, split in X slabs"""
+    gv = H.vol2d(2.4 * max(nranks, 2), 2.0, 10)
+    split, rank_of = None, None
+    if nranks > 1:
+        cuts, rank_of = H.slab_decomposition(gv, nranks, 0)
+        split = {0: cuts}
+    elif case.endswith("_presplit"):
+        cuts, _ = H.slab_decomposition(gv, 2, 0)
+        split = {0: cuts}
+    s = H.structure(gv, lambda x, y, z: 1.0 + 3.0 * (np.abs(y - 1.0) < 0.3), pml=0.4, realnum=rt, split=split)
+    cr = [rank_of(sc) for sc in s.chunks] if rank_of else None
+    f = H.fields(s, backend, rank=rank, nranks=nranks, chunk_rank=cr, comm_id=comm_id)
+    f.beta = 0.3
+    f.use_real_fields()
+    c = gv.center()
+    f.add_point_source(A.Ez, 0.3, 0.2, 0.0, 4.0, (c[0] - 0.35, c[1] + 0.1, 0.0), 1.0)
     return gv, f
 
 

@@ -29,7 +29,7 @@ def run(kind, case, dtype, steps, world, port, extra_env=None):
     return vals
 
 
-@pytest.mark.parametrize("case", ["pml", "per"])
+@pytest.mark.parametrize("case", ["pml", "per", "beta2d"])
 def test_two_ranks_equal_one_rank_oracle(case):
     one = run("oracle", case + "_presplit", "f64", 40, 1, 29611)
     two = run("oracle", case, "f64", 40, 2, 29612)
