@@ -210,7 +210,17 @@ int meepcu_finalize(meepcu_ctx *ctx);
 /* ---- the hot path ------------------------------------------------------------------------- */
 /* Advance nsteps time steps == nsteps calls of fields::step() (src/step.cpp:35-140), including
  * step_db, step_source, step_boundaries, update_eh, update_pols and update_dfts.
- * samples[s*n_src_times + j] holds src_time j's values for step s (may be NULL if there are none). */
+ * samples[s*n_src_times + j] holds src_time j's values for step s (may be NULL if there are none).
+ *
+ * ASYNCHRONOUS: the call queues the work and returns; `samples` is copied before it returns.  The
+ * device is waited for only by the calls that hand data back (meepcu_sync_*, meepcu_read_value(s),
+ * meepcu_check_finite, meepcu_get_stats, meepcu_get_timers), so a caller that makes one call per time
+ * step -- the reference's `fields::step()` -- keeps the GPU fed.
+ *
+ * The reference's per-step NaN test (src/step.cpp:138-139) is evaluated lazily: every call ends with one
+ * small kernel that tests a sample of every field array and raises a flag; the NEXT meepcu_step call
+ * (no wait involved) returns MEEPCU_ENONFINITE ("simulation fields are NaN or Inf") when the flag is up.
+ * meepcu_check_finite tests every element and blocks. */
 int meepcu_step(meepcu_ctx *ctx, int nsteps, int n_src_times, const meepcu_src_sample *samples);
 
 /* fields::synchronize_magnetic_fields / restore_magnetic_fields (src/energy_and_flux.cpp:145-177) on
@@ -226,8 +236,17 @@ int meepcu_synchronize_magnetic_fields(meepcu_ctx *ctx, int n_src_times, const m
 int meepcu_restore_magnetic_fields(meepcu_ctx *ctx);
 
 /* ---- coherence with the host object graph -------------------------------- */
-int meepcu_sync_to_host(meepcu_ctx *ctx);   /* device -> caller's arrays (fields, aux, P, dft) */
-int meepcu_sync_from_host(meepcu_ctx *ctx); /* caller's arrays -> device (fields, aux, P, dft, materials) */
+/* device -> caller's arrays (fields, aux, P, dft).  The halo (not-owned) points that no stepping kernel
+ * consumes -- B/D/P, and the E/H plane normal to each component -- are brought up to date first, so the
+ * host mirror holds what step_boundaries (src/step.cpp:226-288) would have left there.
+ * With more than one rank (meepcu_comm_init) that includes halos owned by OTHER ranks: the call is then
+ * COLLECTIVE -- every rank of the communicator must make it, in the same order (like the reference's own
+ * step_boundaries).  A rank that must sync alone passes MEEPCU_SYNC_LOCAL to meepcu_sync_subset: only
+ * same-rank halos are refreshed; remote ones keep the values of the last collective sync. */
+int meepcu_sync_to_host(meepcu_ctx *ctx);
+/* caller's arrays -> device: fields, aux, P, dft.  Materials were uploaded by meepcu_finalize; after the
+ * host changes them (phase_material, set_epsilon ...) call meepcu_sync_subset(ctx, 0, MEEPCU_SYNC_MATERIALS). */
+int meepcu_sync_from_host(meepcu_ctx *ctx);
 /* Partial coherence: only the named groups of arrays travel.  What the reference's DFT consumers
  * (dft_flux::flux, dft_energy, near2far, save_dft_hdf5; src/dft.cpp:444-462,533-548,630-700) need is
  * MEEPCU_SYNC_DFT alone; energy / flux-in-box probes need FIELDS. */
@@ -235,13 +254,17 @@ enum { MEEPCU_SYNC_FIELDS = 1,    /* fields_chunk::f */
        MEEPCU_SYNC_AUX = 2,       /* f_u, f_w, f_cond, f_bfast */
        MEEPCU_SYNC_POL = 4,       /* polarisation P, P_prev */
        MEEPCU_SYNC_DFT = 8,       /* dft_chunk::dft accumulators */
-       MEEPCU_SYNC_MATERIALS = 16 /* chi1inv, chi2, chi3, conductivity, sigma, sig/kap/siginv (host -> device only) */ };
+       MEEPCU_SYNC_MATERIALS = 16,/* chi1inv, chi2, chi3, conductivity, sigma, sig/kap/siginv (host -> device only) */
+       MEEPCU_SYNC_LOCAL = 32     /* modifier: do not refresh halos owned by other ranks (not collective) */ };
 int meepcu_sync_subset(meepcu_ctx *ctx, int to_host, unsigned groups);
 int meepcu_get_time(meepcu_ctx *ctx, int *t);
 int meepcu_set_time(meepcu_ctx *ctx, int t);
-/* the per-step NaN test of src/step.cpp:138-139, evaluated lazily on the device */
+/* every element of every field array tested for NaN / Inf on the device (one launch), blocking; the
+ * per-step test of src/step.cpp:138-139 itself is the lazy one described at meepcu_step */
 int meepcu_check_finite(meepcu_ctx *ctx, int *ok);
-/* one element of a registered host array, read from the device mirror (fields::get_field probes) */
+/* one element of a registered host array, read from the device mirror (fields::get_field probes).
+ * Not-owned points are valid too: same-rank halos the stepping kernels do not need are refreshed first
+ * (halos owned by another rank are as of the last collective meepcu_sync_to_host). */
 int meepcu_read_value(meepcu_ctx *ctx, const void *host_ptr, double *out);
 /* n elements at once, gathered on the device and returned in one transfer: what fields::get_field's
  * interpolation stencil, get_array_slice and integrate (src/monitor.cpp, array_slice.cpp,
@@ -249,7 +272,9 @@ int meepcu_read_value(meepcu_ctx *ctx, const void *host_ptr, double *out);
 int meepcu_read_values(meepcu_ctx *ctx, size_t n, const void *const *host_ptrs, double *out);
 
 /* ---- introspection ------------------------------------------------------------------------ */
-/* seconds accumulated per reference time_sink (src/meep.hpp:1610-1633), CUDA-event based */
+/* seconds accumulated per reference time_sink (src/meep.hpp:1610-1633), CUDA-event based: out[1]
+ * (Stepping) is the device time of every meepcu_step call so far, always on; the per-phase sinks
+ * (FieldUpdateB/D/E, Boundaries, FourierTransforming) accumulate while meepcu_set_profiling(1) is on */
 int meepcu_get_timers(meepcu_ctx *ctx, double out[22]);
 typedef struct {
   int64_t kernel_launches;    /* kernels of this library launched so far */
@@ -257,8 +282,9 @@ typedef struct {
   int64_t device_bytes;       /* bytes of device memory owned by the context */
   int64_t cells;              /* sum over chunks of owned cells (nx*ny*nz) */
   int64_t algorithmic_bytes_per_step; /* compulsory HBM bytes per step (DESIGN.md accounting) */
-  double last_step_ms;        /* device time of the last meepcu_step call (CUDA events) */
-  int64_t reserved[8];
+  double last_step_ms;        /* device time of the last meepcu_step call (CUDA events; the query waits for it) */
+  int64_t reserved[8];        /* [0] cells the NR seed ladder left unchanged, [1],[2] host arrays / bytes page-locked in
+                                 place, [3] lazy NaN flag, [4] device microseconds of all meepcu_step calls */
 } meepcu_stats;
 int meepcu_get_stats(meepcu_ctx *ctx, meepcu_stats *out);
 

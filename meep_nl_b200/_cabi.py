@@ -13,7 +13,7 @@ import os
 NUM_COMPONENTS = 20
 NUM_FIELD_TYPES = 8
 ABI_VERSION = 2
-SYNC_FIELDS, SYNC_AUX, SYNC_POL, SYNC_DFT, SYNC_MATERIALS = 1, 2, 4, 8, 16
+SYNC_FIELDS, SYNC_AUX, SYNC_POL, SYNC_DFT, SYNC_MATERIALS, SYNC_LOCAL = 1, 2, 4, 8, 16, 32
 
 # component ids (reference src/meep/vec.hpp:31-52)
 Ex, Ey, Er, Ep, Ez, Hx, Hy, Hr, Hp, Hz, Dx, Dy, Dr, Dp, Dz, Bx, By, Br, Bp, Bz = range(20)

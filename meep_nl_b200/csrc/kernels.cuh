@@ -1851,13 +1851,24 @@ template <class T> __global__ void __launch_bounds__(kThreads) k_average(T *__re
     f[i] = (T)(0.5 * (double)(f[i] + backup[i])); // the reference's promotions: realnum sum, double product
 }
 
-// the per-step NaN test of step.cpp:138-139, over whole arrays, on demand
-template <class T> __global__ void k_nonfinite(const T *a, long long n, int *flag) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
+// the per-step NaN test of step.cpp:138-139: ONE launch over a table of all field arrays, testing `samples`
+// evenly spaced elements of each (samples >= n: every element).  blockIdx.x walks the arrays, blockIdx.y
+// splits the samples.  `flag` may live in page-locked host memory (the lazy per-call test).
+struct FinEntry { const void *p; long long n; };
+template <class T> __global__ void __launch_bounds__(kThreads) k_finite(const FinEntry *__restrict__ tab, int ntab, long long samples, int *flag) {
   int bad = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    if (!isfinite((double)a[i])) bad = 1;
-  if (bad) atomicOr(flag, 1);
+  for (int a = blockIdx.x; a < ntab; a += gridDim.x) {
+    const T *p = (const T *)tab[a].p;
+    const long long n = tab[a].n;
+    const long long stride = n > samples ? n / samples : 1;
+    const long long cnt = (n + stride - 1) / stride;
+    for (long long j = (long long)blockIdx.y * blockDim.x + threadIdx.x; j < cnt; j += (long long)gridDim.y * blockDim.x) {
+      long long i = j * stride + stride / 2;
+      if (i >= n) i = n - 1;
+      if (!isfinite((double)p[i])) bad = 1;
+    }
+  }
+  if (bad) *(volatile int *)flag = 1;
 }
 
 } // namespace mcu

@@ -67,6 +67,7 @@ struct NcclApi {
   int (*Recv)(void *, size_t, int, int, nccl_comm, cudaStream_t);
   int (*GroupStart)();
   int (*GroupEnd)();
+  int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t);
   const char *(*GetErrorString)(int);
 };
 NcclApi *nccl_api() {
@@ -84,8 +85,9 @@ NcclApi *nccl_api() {
       *(void **)&api.Recv = dlsym(api.h, "ncclRecv");
       *(void **)&api.GroupStart = dlsym(api.h, "ncclGroupStart");
       *(void **)&api.GroupEnd = dlsym(api.h, "ncclGroupEnd");
+      *(void **)&api.AllReduce = dlsym(api.h, "ncclAllReduce");
       *(void **)&api.GetErrorString = dlsym(api.h, "ncclGetErrorString");
-      if (!api.GetUniqueId || !api.CommInitRank || !api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd)
+      if (!api.GetUniqueId || !api.CommInitRank || !api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd || !api.AllReduce)
         api.h = 0;
     }
   }
@@ -335,7 +337,8 @@ template <class T> struct Ctx : CtxBase {
   Tile *d_polgen_tiles[2];
   int n_polgen_tiles[2];
   std::set<std::pair<int, int> > aniso_chunk_half; // (chunk, half) whose polarisations update in k_pol_general
-  bool general_half[2];  // some chunk needs k_eh_general in this half
+  bool general_half[2];  // some chunk (of ANY rank) needs k_eh_general in this half
+  bool aniso_half[2];    // some chunk (of any rank) updates polarisations in k_pol_general / k_pol_gyro
   bool eager_db[2];      // exchange B / D halos every step
   bool eager_p[2];       // exchange PH / PE halos every step
   DftParams<T> *d_dft;
@@ -349,10 +352,50 @@ template <class T> struct Ctx : CtxBase {
   std::vector<int> group_is_h;
   int phase_row;                   // complex elements per step
   int *d_phase_off;
-  DevBuf<double> d_smp;
-  DevBuf<T> d_phases;
-  DevBuf<unsigned char> d_active;
+  // Per-call tables (src_time samples, DFT phases, decimation flags) travel through a page-locked ring and a
+  // device ring, so that meepcu_step never waits for the device: the reference's caller makes one call per
+  // time step (src/step.cpp:35, python/simulation.py:2831-2834) and the launches of step n+1 must be queued
+  // while step n runs.
+  struct Ring { char *h, *d; size_t cap, used; } ring;
+  int ring_put(const void *src, size_t bytes, char **dptr) {
+    const size_t need = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+    if (ring.used + need > ring.cap) {
+      CU(cudaStreamSynchronize(st)); // every kernel that read earlier slots has finished (side streams join st)
+      ring.used = 0;
+      if (need > ring.cap) {
+        if (ring.h) cudaFreeHost(ring.h);
+        if (ring.d) cudaFree(ring.d);
+        ring.h = ring.d = 0;
+        ring.cap = 0;
+        const size_t cap = std::max<size_t>(2 * need, (size_t)1 << 20);
+        CU(cudaHostAlloc((void **)&ring.h, cap, cudaHostAllocDefault));
+        CU(cudaMalloc((void **)&ring.d, cap));
+        ring.cap = cap;
+      }
+    }
+    if (bytes) {
+      memcpy(ring.h + ring.used, src, bytes);
+      CU(cudaMemcpyAsync(ring.d + ring.used, ring.h + ring.used, bytes, cudaMemcpyHostToDevice, st));
+    }
+    *dptr = ring.d + ring.used;
+    ring.used += need;
+    return MEEPCU_OK;
+  }
   int *d_flags; // [0] nr_fail, [1] nonfinite
+  // the per-step NaN test (src/step.cpp:138-139), lazily: a sample of every field array is tested at the end
+  // of each meepcu_step call by one small kernel that raises a flag in page-locked host memory; the host looks
+  // at the flag when the next call comes in, never waiting for the device
+  int *h_nonfinite, *d_hnonfinite;
+  FinEntry *d_fin;
+  int n_fin;
+  long long fin_max_n;
+  bool finite_check;
+  // device time of meepcu_step calls, collected lazily (CUDA event pairs, oldest first)
+  struct StepEv { cudaEvent_t e0, e1; bool pending; };
+  std::vector<StepEv> step_ev;
+  size_t step_ev_next;
+  double total_step_ms;
+  bool halo_stale; // deferred local halo copies (B/D/P, normal-plane E/H) not materialised since the last step
   SrcEntry *d_src;
 
   // synchronize_magnetic_fields state (energy_and_flux.cpp:97-177)
@@ -382,6 +425,16 @@ template <class T> struct Ctx : CtxBase {
           launches(0), steps_done(0), cells(0), alg_bytes(0), last_ms(0), profiling(false), ev_used(0) {
     stage[0] = stage[1] = 0;
     dstage = 0;
+    ring.h = ring.d = 0;
+    ring.cap = ring.used = 0;
+    h_nonfinite = d_hnonfinite = 0;
+    d_fin = 0;
+    n_fin = 0;
+    fin_max_n = 0;
+    finite_check = true;
+    step_ev_next = 0;
+    total_step_ms = 0;
+    halo_stale = false;
     mag_backup = 0;
     mag_synced = in_mag_sync = false;
     stage_next = 0;
@@ -434,6 +487,7 @@ template <class T> struct Ctx : CtxBase {
     memset(n_zero, 0, sizeof n_zero);
     fmp_has_src[0] = fmp_has_src[1] = false;
     general_half[0] = general_half[1] = false;
+    aniso_half[0] = aniso_half[1] = false;
     eager_db[0] = eager_db[1] = eager_p[0] = eager_p[1] = false;
   }
   ~Ctx() {
@@ -447,9 +501,10 @@ template <class T> struct Ctx : CtxBase {
       if (it->second.pinned) cudaHostUnregister((void *)it->second.host);
     if (arena) cudaFree(arena);
     for (size_t i = 0; i < extra_dev.size(); ++i) cudaFree(extra_dev[i]);
-    d_smp.release();
-    d_phases.release();
-    d_active.release();
+    if (ring.h) cudaFreeHost(ring.h);
+    if (ring.d) cudaFree(ring.d);
+    if (h_nonfinite) cudaFreeHost(h_nonfinite);
+    for (size_t i = 0; i < step_ev.size(); ++i) { cudaEventDestroy(step_ev[i].e0); cudaEventDestroy(step_ev[i].e1); }
     for (size_t i = 0; i < ev_pool.size(); ++i) cudaEventDestroy(ev_pool[i]);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -1112,7 +1167,7 @@ template <class T> struct Ctx : CtxBase {
         if (cudaHostRegister((void *)r.host, nb, cudaHostRegisterDefault) == cudaSuccess) r.pinned = true;
         else cudaGetLastError(); // not registrable (e.g. already registered by the caller): staging path
       }
-    RC(sync_from_host());
+    RC(sync_groups(false, ~0u)); // everything, materials included
 
     // ---- 3. metal planes ----
     std::map<const char *, unsigned> zmask;
@@ -1669,11 +1724,38 @@ template <class T> struct Ctx : CtxBase {
         aniso_now = false;
       }
     }
+    // ---- 5a. which halo exchanges run every step.  The schedule must be the SAME on every rank: a rank that
+    // owns only PML chunks and a rank that owns nonlinear ones would otherwise post different ncclSend/ncclRecv
+    // groups (one side waiting for a D halo the other never sends).  So the flags are OR-ed over the communicator.
+    for (size_t ic = 0; ic < chunks.size(); ++ic)
+      for (size_t id = 0; id < chunks[ic].dft.size(); ++id) { // a DFT of D (B) reads its halos: dft.cpp:284-293
+        const int c = chunks[ic].dft[id].d.c;
+        if (c >= 0 && c < 20 && chunks[ic].d.f[c][0]) {
+          if (is_D(c)) eager_db[1] = true;
+          if (is_B(c)) eager_db[0] = true;
+        }
+      }
+    for (int half = 0; half < 2; ++half) aniso_half[half] = !polgen_tiles[half].empty() || !polgyro_tiles[half].empty();
+    if (n_ranks > 1) {
+      int hflag[8] = {general_half[0], general_half[1], eager_db[0], eager_db[1], eager_p[0], eager_p[1], aniso_half[0], aniso_half[1]};
+      int *dflag = 0;
+      CU(cudaMalloc((void **)&dflag, sizeof hflag));
+      extra_dev.push_back((char *)dflag);
+      CU(cudaMemcpyAsync(dflag, hflag, sizeof hflag, cudaMemcpyHostToDevice, st));
+      NC(nccl_api()->AllReduce(dflag, dflag, 8, 2 /* ncclInt32 */, 2 /* ncclMax */, comm, st));
+      CU(cudaMemcpyAsync(hflag, dflag, sizeof hflag, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      general_half[0] = hflag[0]; general_half[1] = hflag[1];
+      eager_db[0] = hflag[2]; eager_db[1] = hflag[3];
+      eager_p[0] = hflag[4]; eager_p[1] = hflag[5];
+      aniso_half[0] = hflag[6]; aniso_half[1] = hflag[7];
+    }
     // ---- 5b. multi-rank: boundary tiles first (see nb_* above) ----
     if (n_ranks > 1 && !getenv("MEEPCU_NO_OVERLAP"))
       for (int half = 0; half < 2; ++half) {
         if (general_half[half]) continue; // k_eh_general needs the D halo before E exists: ordered path
-        if (!polgen_tiles[half].empty() || !polgyro_tiles[half].empty()) continue; // k_pol_general / k_pol_gyro need the W halo before P: ordered path
+        if (aniso_half[half]) continue;   // k_pol_general / k_pol_gyro need the W halo before P: ordered path
+        if (eager_db[half] || eager_p[half]) continue; // D/B or P halos travel every step (a D/B DFT): ordered path
         const int fts[2] = {half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF, half ? MEEPCU_WE_STUFF : MEEPCU_WH_STUFF};
         // per chunk: the planes (index on device axis A) that hold points another rank receives
         std::vector<std::set<int> > planes(chunks.size());
@@ -2017,6 +2099,22 @@ template <class T> struct Ctx : CtxBase {
     n_dft_work = (int)work.size();
     RC(upload(phase_off, &d_phase_off));
 
+    // ---- 8. the lazy NaN test (step.cpp:138-139): table of the field arrays + a flag the device can raise ----
+    {
+      std::vector<FinEntry> fin;
+      for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it)
+        if (it->second.is_field) {
+          FinEntry e = {it->second.dev, (long long)it->second.n_dev};
+          fin.push_back(e);
+          fin_max_n = std::max(fin_max_n, e.n);
+        }
+      n_fin = (int)fin.size();
+      RC(upload(fin, &d_fin));
+      CU(cudaHostAlloc((void **)&h_nonfinite, 64, cudaHostAllocMapped));
+      memset(h_nonfinite, 0, 64);
+      CU(cudaHostGetDevicePointer((void **)&d_hnonfinite, h_nonfinite, 0));
+      finite_check = !getenv("MEEPCU_NO_FINITE_CHECK");
+    }
     CU(cudaStreamSynchronize(st));
     finalized = true;
     return MEEPCU_OK;
@@ -2357,10 +2455,12 @@ template <class T> struct Ctx : CtxBase {
           launches++;
         }
       }
-      RC(prof_begin(KC_EH_GENERAL));
-      k_eh_general<T><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
-      RC(prof_end());
-      launches++;
+      if (n_eh_tiles[half]) { // (the flag is global: this rank may own no such chunk)
+        RC(prof_begin(KC_EH_GENERAL));
+        k_eh_general<T><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
+        RC(prof_end());
+        launches++;
+      }
     }
     // synchronize_magnetic_fields runs neither step_boundaries(WH) nor update_pols(H) (energy_and_flux.cpp:153-160)
     if (!in_mag_sync) RC(launch_conn(ftw));  // step.cpp:81,113 (empty unless anisotropic sigma / gyrotropy)
@@ -2386,10 +2486,28 @@ template <class T> struct Ctx : CtxBase {
     return MEEPCU_OK;
   }
 
+  int collect_one(StepEv &e) {
+    if (!e.pending) return MEEPCU_OK;
+    CU(cudaEventSynchronize(e.e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e.e0, e.e1));
+    last_ms = ms;
+    total_step_ms += ms;
+    e.pending = false;
+    return MEEPCU_OK;
+  }
+  int collect_timing() { // waits for every queued meepcu_step call
+    for (size_t k = 0; k < step_ev.size(); ++k) RC(collect_one(step_ev[(step_ev_next + k) % step_ev.size()]));
+    return MEEPCU_OK;
+  }
+  int nonfinite_seen() const { return h_nonfinite ? *(volatile int *)h_nonfinite : 0; }
+
   int step(int nsteps, int nsrc, const meepcu_src_sample *smp) {
     if (!finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
     if (mag_synced) return fail(MEEPCU_ESTATE, "magnetic fields are synchronized: meepcu_restore_magnetic_fields first (step.cpp:36-41)");
     if (nsteps <= 0) return MEEPCU_OK;
+    if (nonfinite_seen()) // raised by the sampled test that followed an earlier call (step.cpp:138-139)
+      return fail(MEEPCU_ENONFINITE, "simulation fields are NaN or Inf");
     for (size_t ic = 0; ic < chunks.size(); ++ic)
       for (size_t is = 0; is < chunks[ic].src.size(); ++is)
         if (chunks[ic].src[is].tid >= nsrc || chunks[ic].src[is].tid < 0 || (nsrc > 0 && !smp))
@@ -2397,12 +2515,10 @@ template <class T> struct Ctx : CtxBase {
                       chunks[ic].src[is].tid, nsrc);
     CU(cudaSetDevice(cfg.device));
     // per-step tables: src_time samples, DFT phases (dft.cpp:269-270, host libm like the
-    // reference), DFT decimation flags (dft.cpp:259)
+    // reference), DFT decimation flags (dft.cpp:259) -- through the ring, no synchronisation
     const size_t ns = (size_t)std::max(nsrc, 1) * 8;
-    RC(d_smp.reserve(ns * nsteps));
-    if (nsrc > 0)
-      CU(cudaMemcpyAsync(d_smp.p, smp, sizeof(meepcu_src_sample) * (size_t)nsrc * nsteps,
-                         cudaMemcpyHostToDevice, st));
+    char *p_smp = 0, *p_ph = 0, *p_act = 0;
+    RC(ring_put(smp, nsrc > 0 ? sizeof(meepcu_src_sample) * (size_t)nsrc * nsteps : 0, &p_smp));
     const size_t ndft = h_dft.size();
     if (ndft) {
       std::vector<T> ph((size_t)2 * phase_row * nsteps);
@@ -2420,36 +2536,49 @@ template <class T> struct Ctx : CtxBase {
         }
         for (size_t k = 0; k < ndft; ++k) act[(size_t)s * ndft + k] = (tt % dft_decim[k]) == 0;
       }
-      RC(d_phases.reserve(ph.size()));
-      RC(d_active.reserve(act.size()));
-      CU(cudaMemcpyAsync(d_phases.p, ph.data(), ph.size() * sizeof(T), cudaMemcpyHostToDevice, st));
-      CU(cudaMemcpyAsync(d_active.p, act.data(), act.size(), cudaMemcpyHostToDevice, st));
-      CU(cudaStreamSynchronize(st)); // the staging vectors die at scope exit
+      RC(ring_put(ph.data(), ph.size() * sizeof(T), &p_ph));
+      RC(ring_put(act.data(), act.size(), &p_act));
     }
-    else if (nsrc > 0)
-      CU(cudaStreamSynchronize(st));
-    CU(cudaEventRecord(ev0, st));
+    if (step_ev.empty()) {
+      step_ev.resize(16);
+      for (size_t k = 0; k < step_ev.size(); ++k) {
+        CU(cudaEventCreate(&step_ev[k].e0));
+        CU(cudaEventCreate(&step_ev[k].e1));
+        step_ev[k].pending = false;
+      }
+    }
+    StepEv &E = step_ev[step_ev_next];
+    RC(collect_one(E)); // the oldest pair: long finished unless 16 calls are already queued
+    step_ev_next = (step_ev_next + 1) % step_ev.size();
+    CU(cudaEventRecord(E.e0, st));
     for (int s = 0; s < nsteps; ++s) {
-      const double *sm = d_smp.p + (size_t)s * ns;
+      const double *sm = (const double *)p_smp + (size_t)s * ns;
       RC(launch_half(0, sm));
       RC(launch_half(1, sm));
       if (n_dft_work) {
         RC(prof_begin(KC_DFT));
-        k_dft<T><<<n_dft_work, kThreads, 0, st>>>(d_dft, d_dft_work, d_phases.p + (size_t)2 * phase_row * s,
-                                                   d_phase_off, d_active.p + (size_t)s * ndft);
+        k_dft<T><<<n_dft_work, kThreads, 0, st>>>(d_dft, d_dft_work, (const T *)p_ph + (size_t)2 * phase_row * s,
+                                                   d_phase_off, (const unsigned char *)p_act + (size_t)s * ndft);
         RC(prof_end());
         launches++;
       }
     }
-    CU(cudaEventRecord(ev1, st));
+    CU(cudaEventRecord(E.e1, st));
+    E.pending = true;
+    if (finite_check && n_fin) { // outside the timed pair: 1024 samples of every field array
+      dim3 grid((unsigned)std::min(n_fin, 148 * 4), 1);
+      k_finite<T><<<grid, kThreads, 0, st>>>(d_fin, n_fin, 1024, d_hnonfinite);
+      launches++;
+    }
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(st));
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, ev0, ev1));
-    last_ms = ms;
-    RC(prof_collect());
     t += nsteps;
     steps_done += nsteps;
+    halo_stale = true;
+    if (profiling) { // per-kernel events are read back right away (bench.py's roofline leg)
+      CU(cudaStreamSynchronize(st));
+      RC(collect_timing());
+      RC(prof_collect());
+    }
     return MEEPCU_OK;
   }
 
@@ -2505,13 +2634,12 @@ template <class T> struct Ctx : CtxBase {
           return fail(MEEPCU_EINVAL, "source refers to src_time %d but only %d samples given", chunks[ic].src[is].tid, nsrc);
     CU(cudaSetDevice(cfg.device));
     RC(collect_mag_arrays());
-    const size_t ns = (size_t)std::max(nsrc, 1) * 8;
-    RC(d_smp.reserve(ns));
-    if (nsrc > 0) CU(cudaMemcpyAsync(d_smp.p, smp, sizeof(meepcu_src_sample) * (size_t)nsrc, cudaMemcpyHostToDevice, st));
+    char *p_smp = 0;
+    RC(ring_put(smp, nsrc > 0 ? sizeof(meepcu_src_sample) * (size_t)nsrc : 0, &p_smp));
     for (size_t k = 0; k < mag_arrays.size(); ++k) // backup_component (:97-118)
       CU(cudaMemcpyAsync(mag_backup + mag_arrays[k].off, mag_arrays[k].dev, mag_arrays[k].bytes, cudaMemcpyDeviceToDevice, st));
     in_mag_sync = true;
-    const int rc_half = launch_half(0, d_smp.p); // step_db(B), step_source(B), step_boundaries(B), update_eh(H), step_boundaries(H)
+    const int rc_half = launch_half(0, (const double *)p_smp); // step_db(B), step_source(B), step_boundaries(B), update_eh(H), step_boundaries(H)
     in_mag_sync = false;
     RC(rc_half);
     for (size_t k = 0; k < mag_arrays.size(); ++k) {
@@ -2542,23 +2670,36 @@ template <class T> struct Ctx : CtxBase {
   }
 
   int sync_to_host() { return sync_groups(true, ~0u); }
-  int sync_from_host() { return sync_groups(false, ~0u); }
+  // the caller's arrays -> device: everything that changes while stepping.  Materials (chi1inv, chi2, chi3,
+  // conductivity, sigma, sig/kap/siginv) were uploaded by meepcu_finalize and travel again only when asked for
+  // (meepcu_sync_subset(ctx, 0, MEEPCU_SYNC_MATERIALS)): re-sending them at every sync is pure PCIe time.
+  int sync_from_host() { return sync_groups(false, MEEPCU_SYNC_FIELDS | MEEPCU_SYNC_AUX | MEEPCU_SYNC_POL | MEEPCU_SYNC_DFT); }
   bool big(const ArrayRec &r) const { return r.n_host * sizeof(T) >= (size_t)(4 << 20) && !getenv("MEEPCU_NO_STAGING"); }
+  // Halo copies the stepping kernels never consume (B/D/P, the normal-plane E/H points) are materialised
+  // when somebody is about to read the device mirror.  `remote`: also the cross-rank ones (a collective:
+  // every rank of the communicator must make the same call).
+  int materialise_halos(unsigned groups, bool remote) {
+    for (int half = 0; half < 2; ++half) {
+      const int ftd = half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF, fte = half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF,
+                ftp = half ? MEEPCU_PE_STUFF : MEEPCU_PH_STUFF;
+      if (!eager_db[half] && (groups & MEEPCU_SYNC_FIELDS)) RC(remote ? launch_conn(ftd) : launch_conn_local(ftd));
+      if (n_runs_def[fte] && (groups & MEEPCU_SYNC_FIELDS)) { // the normal-plane E/H halos
+        k_conn_runs<T><<<(n_runs_def[fte] + 7) / 8, kThreads, 0, st>>>(d_runs_def[fte], n_runs_def[fte]);
+        launches++;
+      }
+      if (!eager_p[half] && (groups & MEEPCU_SYNC_POL)) RC(remote ? launch_conn(ftp) : launch_conn_local(ftp));
+    }
+    return MEEPCU_OK;
+  }
   int sync_groups(bool to_host, unsigned groups) {
     if (to_host && !finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
     CU(cudaSetDevice(cfg.device));
+    const bool local_only = (groups & MEEPCU_SYNC_LOCAL) != 0;
+    groups &= ~(unsigned)MEEPCU_SYNC_LOCAL;
     if (to_host) {
-      // halo copies the stepping kernels never consume are materialised here, so that the
-      // not-owned points of the host mirror hold what step_boundaries would have left there
-      for (int half = 0; half < 2; ++half) {
-        if (!eager_db[half] && (groups & MEEPCU_SYNC_FIELDS)) RC(launch_conn(half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF));
-        const int fte = half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF;
-        if (n_runs_def[fte] && (groups & MEEPCU_SYNC_FIELDS)) { // the normal-plane E/H halos
-          k_conn_runs<T><<<(n_runs_def[fte] + 7) / 8, kThreads, 0, st>>>(d_runs_def[fte], n_runs_def[fte]);
-          launches++;
-        }
-        if (!eager_p[half] && (groups & MEEPCU_SYNC_POL)) RC(launch_conn(half ? MEEPCU_PE_STUFF : MEEPCU_PH_STUFF));
-      }
+      // so that the not-owned points of the host mirror hold what step_boundaries would have left there
+      RC(materialise_halos(groups, n_ranks > 1 && !local_only));
+      if (n_ranks == 1 || !local_only) halo_stale = false;
     }
     for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it) {
       const ArrayRec &r = it->second;
@@ -2566,6 +2707,7 @@ template <class T> struct Ctx : CtxBase {
       RC(big(r) && !r.pinned ? staged_copy(r, to_host) : copy_array(r, to_host));
     }
     CU(cudaStreamSynchronize(st));
+    RC(collect_timing());
     return MEEPCU_OK;
   }
   // n elements gathered on the device (k_pack) and returned as doubles in one transfer
@@ -2574,6 +2716,10 @@ template <class T> struct Ctx : CtxBase {
     if (!n) return MEEPCU_OK;
     if (!ptrs || !out) return fail(MEEPCU_EINVAL, "null argument");
     CU(cudaSetDevice(cfg.device));
+    if (halo_stale) { // not-owned points may be asked for: bring the deferred LOCAL halo copies up to date
+      RC(materialise_halos(MEEPCU_SYNC_FIELDS | MEEPCU_SYNC_POL, false));
+      if (n_ranks == 1) halo_stale = false;
+    }
     std::vector<const T *> h(n);
     for (size_t i = 0; i < n; ++i) {
       h[i] = dev_elem(ptrs[i]);
@@ -2597,20 +2743,20 @@ template <class T> struct Ctx : CtxBase {
     for (size_t i = 0; i < n; ++i) out[i] = (double)v[i];
     return MEEPCU_OK;
   }
-  int check_finite(int *ok) {
+  int check_finite(int *ok) { // every element of every field array, one launch, blocking
     if (!finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
     CU(cudaSetDevice(cfg.device));
     CU(cudaMemsetAsync(d_flags + 1, 0, sizeof(int), st));
-    for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it)
-      if (it->second.is_field) {
-        k_nonfinite<T><<<148 * 4, kThreads, 0, st>>>((const T *)it->second.dev, (long long)it->second.n_dev,
-                                                      d_flags + 1);
-        launches++;
-      }
+    if (n_fin) {
+      dim3 grid((unsigned)std::min(n_fin, 64), 148 * 4 / std::min(n_fin, 64) + 1);
+      k_finite<T><<<grid, kThreads, 0, st>>>(d_fin, n_fin, fin_max_n, d_flags + 1);
+      launches++;
+    }
     int flags[2] = {0, 0};
     CU(cudaMemcpyAsync(flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    *ok = flags[1] == 0;
+    RC(collect_timing());
+    *ok = flags[1] == 0 && !nonfinite_seen();
     nr_unconverged = flags[0];
     return MEEPCU_OK;
   }
@@ -2618,6 +2764,10 @@ template <class T> struct Ctx : CtxBase {
     if (!finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
     T *d = dev_elem(p);
     if (!d) return fail(MEEPCU_EINVAL, "pointer is not inside a registered array");
+    if (halo_stale) {
+      RC(materialise_halos(MEEPCU_SYNC_FIELDS | MEEPCU_SYNC_POL, false));
+      if (n_ranks == 1) halo_stale = false;
+    }
     T v;
     CU(cudaMemcpyAsync(&v, d, sizeof(T), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -2626,6 +2776,15 @@ template <class T> struct Ctx : CtxBase {
   }
   int get_stats(meepcu_stats *out) {
     memset(out, 0, sizeof *out);
+    if (finalized) {
+      CU(cudaSetDevice(cfg.device));
+      RC(collect_timing()); // waits for the queued steps: last_step_ms is the device time of the last call
+      int fl = 0;
+      CU(cudaMemcpy(&fl, d_flags, sizeof fl, cudaMemcpyDeviceToHost));
+      nr_unconverged = fl;
+    }
+    out->reserved[3] = nonfinite_seen();
+    out->reserved[4] = (int64_t)(total_step_ms * 1e3); // device microseconds of all meepcu_step calls so far
     out->kernel_launches = launches;
     out->steps = steps_done;
     out->device_bytes = (int64_t)arena_bytes;
@@ -2643,6 +2802,9 @@ template <class T> struct Ctx : CtxBase {
   int get_timers(double out[22]) {
     // reference time_sink numbering (src/meep.hpp:1610-1633); seconds of device time
     for (int i = 0; i < 22; ++i) out[i] = 0;
+    if (finalized) RC(collect_timing());
+    out[1] = total_step_ms * 1e-3; // Stepping: device time of every meepcu_step call (always on); the per-phase
+                                   // entries below are filled while meepcu_set_profiling(1) serialises the kernels
     out[10] = (kc_ms[KC_HALF_B_SIMPLE] + kc_ms[KC_HALF_B_GENERAL] + kc_ms[KC_CURL3D_B] + kc_ms[KC_MIX_B]) * 1e-3; // FieldUpdateB (+H, fused)
     out[12] = (kc_ms[KC_HALF_D_SIMPLE] + kc_ms[KC_HALF_D_GENERAL] + kc_ms[KC_CURL3D_D] + kc_ms[KC_MIX_D]) * 1e-3; // FieldUpdateD (+E, fused)
     out[13] = (kc_ms[KC_FMP] + kc_ms[KC_EH_GENERAL]) * 1e-3;               // FieldUpdateE (unfused part)
@@ -2776,7 +2938,7 @@ int meepcu_sync_from_host(meepcu_ctx *ctx) {
 }
 int meepcu_sync_subset(meepcu_ctx *ctx, int to_host, unsigned groups) {
   CHECK_CTX;
-  if (groups & ~31u) return fail(MEEPCU_EINVAL, "unknown array group");
+  if (groups & ~63u) return fail(MEEPCU_EINVAL, "unknown array group");
   return ctx->impl->sync_groups(to_host != 0, groups);
 }
 int meepcu_read_values(meepcu_ctx *ctx, size_t n, const void *const *host_ptrs, double *out) {

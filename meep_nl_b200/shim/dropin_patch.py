@@ -3,7 +3,8 @@
 (INTEGRATION.md section 2), expressed as anchored insertions -- no reference text is stored here.
 
     dropin_patch.py <basename> < original > patched
-    (basename: meep.hpp | step.cpp | fields.cpp | energy_and_flux.cpp | loop_in_chunks.cpp | monitor.cpp)
+    (basename: meep.hpp | step.cpp | fields.cpp | energy_and_flux.cpp | loop_in_chunks.cpp | monitor.cpp |
+     initialize.cpp | fields_dump.cpp | boundaries.cpp | dft.cpp | near2far.cpp)
 
 oracle/build_ref.sh applies it in the compiler's input pipe for the `*_dropin` flavours; the result is
 the reference library with ONE added data member (`fields::gpu`), three added methods and a four-line
@@ -21,6 +22,14 @@ MEMBERS = '''
   void gpu_restore_magnetic_fields();
   // process-wide switch: the library the drop-in dlopen()s (NULL: off), how it treats chi2/chi3, the device
   static void gpu_enable(const char *library_path, int nl_mode = 0, int device = 0);
+  // DFT accumulators (dft_chunk::dft) live on the device while stepping: readers (dft_flux::flux, dft_energy,
+  // near2far, save_dft_hdf5, process_dft_component) fetch them first -- only them, not the fields; writers
+  // (scale_dft, operator-=, load_dft_hdf5) fetch them and have them sent back before the next step
+  static void gpu_dft_read();
+  static void gpu_dft_write();
+  // point probes (every fields::get_field overload ends in the (component, ivec) one) read their few values
+  // straight from the device mirror instead of downloading the whole state; false: the host arrays are current
+  bool gpu_get_field(component c, const ivec &origloc, bool parallel, std::complex<double> *out) const;
 '''
 
 STEP_HELPERS = r'''
@@ -43,8 +52,39 @@ void fields::gpu_enable(const char *library_path, int nl_mode, int device) {
   g_dropin_device = device;
 }
 void fields::gpu_sync_to_host() {
-  if (gpu) ((meepcu::attachment *)gpu)->sync_to_host_if_stale();
+  if (!gpu) return;
+  meepcu::attachment *att = (meepcu::attachment *)gpu;
+  if (!att->stale()) return;
+  am_now_working_on(Stepping); // the steps queued by step() finish here: this wait IS stepping time
+  att->wait();
+  finished_working();
+  att->sync_to_host_if_stale();
 }
+bool fields::gpu_get_field(component c, const ivec &origloc, bool parallel, std::complex<double> *out) const {
+  meepcu::attachment *att = (meepcu::attachment *)gpu;
+  if (!att || !att->stale()) return false;
+  ivec iloc = origloc; // same walk as the host version (monitor.cpp:145-157), the leaf read is the device's
+  std::complex<double> kphase = 1.0;
+  locate_point_in_user_volume(&iloc, &kphase);
+  for (int sn = 0; sn < S.multiplicity(); sn++)
+    for (int i = 0; i < num_chunks; i++)
+      if (chunks[i]->gv.owns(S.transform(iloc, sn))) {
+        const fields_chunk *fc = chunks[i];
+        const component tc = S.transform(c, sn);
+        std::complex<double> raw = 0.0;
+        if (fc->is_mine() && fc->f[tc][0]) {
+          const ptrdiff_t idx = fc->gv.index(tc, S.transform(iloc, sn));
+          raw = std::complex<double>(att->read(fc->f[tc][0] + idx), fc->f[tc][1] ? att->read(fc->f[tc][1] + idx) : 0.0);
+        }
+        const std::complex<double> val = S.phase_shift(c, sn) * kphase * raw;
+        *out = parallel ? sum_to_all(val) : val;
+        return true;
+      }
+  *out = 0.0;
+  return true;
+}
+void fields::gpu_dft_read() { meepcu::attachment::for_each_live(&meepcu::attachment::sync_dft_to_host_if_stale); }
+void fields::gpu_dft_write() { meepcu::attachment::for_each_live(&meepcu::attachment::dft_will_be_written); }
 void fields::gpu_synchronize_magnetic_fields() { ((meepcu::attachment *)gpu)->synchronize_magnetic_fields(); }
 void fields::gpu_restore_magnetic_fields() { ((meepcu::attachment *)gpu)->restore_magnetic_fields(); }
 void fields::gpu_detach() {
@@ -67,10 +107,12 @@ static bool dropin_step(fields *f) {
   const int saved = f->synchronized_magnetic_fields;
   if (saved) att->restore_magnetic_fields();
   f->am_now_working_on(Stepping);
-  att->step(1); // advances fields::t
+  // queues one time step and returns (advances fields::t).  The NaN test of step.cpp:138-139 is part of the
+  // call: a sample of every field array is tested on the device after each step and the next call aborts with
+  // the reference's message when it failed -- no per-step wait, no per-step scan of whole arrays
+  att->step(1);
   f->finished_working();
   if (saved) att->synchronize_magnetic_fields();
-  if (!att->finite()) meep::abort("simulation fields are NaN or Inf");
   return true;
 }
 } // namespace meep
@@ -108,12 +150,53 @@ def patch(name, text):
     if name == "monitor.cpp":  # point probes: every get_field overload ends in the (component, ivec) one
         a = text.index("fields::get_field(component c, const ivec &")
         k = text.index("{", a) + 1
-        return text[:k] + "\n  const_cast<fields *>(this)->gpu_sync_to_host(); // meepcu drop-in\n" + text[k:]
+        return text[:k] + ("\n  { std::complex<double> v_; if (gpu && gpu_get_field(c, origloc, parallel, &v_)) return v_; } "
+                           "// meepcu drop-in: a point probe reads the device\n") + text[k:]
     if name == "fields.cpp":
         a = text.index("\nfields::~fields() {")
         k = text.index("{", a) + 1
-        return text[:k] + "\n  gpu_detach(); // meepcu drop-in\n" + text[k:]
+        text = text[:k] + "\n  gpu_detach(); // meepcu drop-in\n" + text[k:]
+    # host-side WRITERS of the field arrays / of the set of arrays: the device mirror is synced back and dropped,
+    # the next step() describes the object graph anew (the rule the reference applies to chunk_connections_valid,
+    # boundaries.cpp:171-183)
+    for fname, sigs in WRITERS.items():
+        if name == fname:
+            for sig in sigs:
+                text = at_function_start(text, sig, "gpu_detach(); // meepcu drop-in: host-side writer")
+    for fname, sigs in DFT_READERS.items():
+        if name == fname:
+            for sig in sigs:
+                text = at_function_start(text, sig, "fields::gpu_dft_read(); // meepcu drop-in: accumulators live on the device")
+    for fname, sigs in DFT_WRITERS.items():
+        if name == fname:
+            for sig in sigs:
+                text = at_function_start(text, sig, "fields::gpu_dft_write(); // meepcu drop-in")
     return text
+
+
+def at_function_start(text, sig, line):
+    a = text.index("\n" + sig)
+    k = text.index("{", text.index(")", a)) + 1
+    return text[:k] + "\n  " + line + "\n" + text[k:]
+
+
+WRITERS = {
+    "fields.cpp": ["void fields::use_real_fields()", "void fields::_require_component(", "void fields::remove_sources()",
+                   "void fields::remove_susceptibilities()", "void fields::remove_fluxes()", "void fields::zero_fields()",
+                   "void fields::reset()"],
+    "initialize.cpp": ["void fields::initialize_field("],
+    "fields_dump.cpp": ["void fields::load(const char *filename"],
+    "boundaries.cpp": ["void fields::set_boundary(", "void fields::use_bloch(direction d"],
+}
+DFT_READERS = {
+    "dft.cpp": ["void save_dft_hdf5(dft_chunk *dft_chunks, const char *name", "double *dft_flux::flux()",
+                "double *dft_energy::electric()", "double *dft_energy::magnetic()",
+                "complex<double> fields::process_dft_component("],
+    "near2far.cpp": ["void dft_near2far::farfield_lowlevel("],
+}
+DFT_WRITERS = {
+    "dft.cpp": ["void dft_chunk::scale_dft(", "void dft_chunk::operator-=(", "void load_dft_hdf5(dft_chunk *dft_chunks, const char *name"],
+}
 
 
 if __name__ == "__main__":

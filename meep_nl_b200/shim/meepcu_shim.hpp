@@ -21,6 +21,7 @@
 #include <limits>
 #include <map>
 #include <memory>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -136,9 +137,21 @@ public:
              observer *obs_ = 0)
       : f(f_), a(a_), ctx(0), obs(obs_) {
     describe(nl_mode, device);
+    live().insert(this);
   }
   ~attachment() {
+    live().erase(this);
     if (ctx) a.destroy(ctx);
+  }
+  // every attachment alive in this process: dft_chunk objects have no way back to their `fields`, so the
+  // DFT readers / writers of the reference (dft_flux::flux, save_dft_hdf5, scale_dft ...) address all of them
+  static std::set<attachment *> &live() {
+    static std::set<attachment *> s;
+    return s;
+  }
+  static void for_each_live(void (attachment::*fn)()) {
+    std::vector<attachment *> v(live().begin(), live().end());
+    for (size_t k = 0; k < v.size(); ++k) (v[k]->*fn)();
   }
 
   // == fields::step() repeated n times (src/step.cpp:35-140), fields stay on the device
@@ -160,9 +173,26 @@ public:
       }
     }
     if (obs) obs->on_step(n, nsrc, smp.data());
-    check(a.step(ctx, n, nsrc, nsrc ? smp.data() : 0));
+    if (dft_host_dirty) { // scale_dft / operator-= / load_dft_hdf5 changed the accumulators on the host
+      check(a.sync_subset(ctx, 0, MEEPCU_SYNC_DFT));
+      dft_host_dirty = false;
+    }
+    check(a.step(ctx, n, nsrc, nsrc ? smp.data() : 0)); // queues the work and returns (include/meepcu.h)
     f.t += n;
     host_stale = true;
+    dft_stale = true;
+  }
+  // wait for the queued steps (what a blocking fields::step() would have done)
+  void wait() {
+    meepcu_stats s;
+    check(a.get_stats(ctx, &s));
+  }
+  bool stale() const { return host_stale; }
+  // one element of a registered array, read from the device mirror (waits for the queued steps)
+  double read(const meep::realnum *p) {
+    double v = 0;
+    check(a.read_value(ctx, p, &v));
+    return v;
   }
   // == the body of fields::synchronize_magnetic_fields / restore_magnetic_fields
   //    (src/energy_and_flux.cpp:145-177) on the device; the caller keeps the reference's counter
@@ -189,6 +219,7 @@ public:
   void sync_to_host() {
     check(a.sync_to_host(ctx));
     host_stale = false;
+    dft_stale = false;
   }
   // Has the host object graph changed since it was described (a source, DFT monitor or polarisation added,
   // arrays re-allocated: the reference marks the latter with chunk_connections_valid = false,
@@ -199,7 +230,17 @@ public:
     if (host_stale) sync_to_host();
   }
   // only the DFT accumulators: all that dft_flux::flux / dft_energy / near2far / save_dft_hdf5 read
-  void sync_dft_to_host() { check(a.sync_subset(ctx, 1, MEEPCU_SYNC_DFT)); }
+  void sync_dft_to_host() {
+    check(a.sync_subset(ctx, 1, MEEPCU_SYNC_DFT));
+    dft_stale = false;
+  }
+  void sync_dft_to_host_if_stale() {
+    if (dft_stale) sync_dft_to_host();
+  }
+  void dft_will_be_written() { // a host-side writer of dft_chunk::dft: fetch now, send back before the next step
+    sync_dft_to_host_if_stale();
+    dft_host_dirty = true;
+  }
   // fields only (get_array_slice, energy_in_box, flux_in_box ...)
   void sync_fields_to_host() { check(a.sync_subset(ctx, 1, MEEPCU_SYNC_FIELDS)); }
   void sync_from_host() {
@@ -329,6 +370,8 @@ private:
   meepcu_ctx *ctx;
   observer *obs;
   bool host_stale = false; // the device has advanced since the last sync_to_host
+  bool dft_stale = false;  // ... since the DFT accumulators were last fetched
+  bool dft_host_dirty = false; // the host changed the accumulators since they were last sent
   std::vector<meep::src_time *> src_times;
   std::vector<std::vector<double> > keep_amp; // storage handed to the ABI during description
 
@@ -337,6 +380,7 @@ private:
     o[1] = z.imag();
   }
   void check(int rc) {
+    if (rc == MEEPCU_ENONFINITE) meep::abort("simulation fields are NaN or Inf"); // step.cpp:138-139, the reference's words
     if (rc != MEEPCU_OK) meep::abort("meepcu (%s): %s", a.backend(), a.last_error());
   }
 

@@ -1713,7 +1713,7 @@ int meepcu_sync_from_host(meepcu_ctx *ctx) {
 int meepcu_sync_subset(meepcu_ctx *ctx, int to_host, unsigned groups) {
   CHECK_CTX;
   (void)to_host;
-  if (groups & ~31u) return fail(MEEPCU_EINVAL, "unknown array group");
+  if (groups & ~63u) return fail(MEEPCU_EINVAL, "unknown array group"); // MEEPCU_SYNC_LOCAL: nothing to refresh, the oracle works in place
   return MEEPCU_OK; // the oracle works in place on the caller's arrays
 }
 int meepcu_get_time(meepcu_ctx *ctx, int *t) {

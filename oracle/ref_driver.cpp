@@ -565,6 +565,30 @@ static volume mid_plane(const grid_volume &gv) {
   return volume(c, c);
 }
 
+// every flux spectrum of the problem, read with the reference's own dft_flux::flux() (dft.cpp:533-548)
+static std::vector<double> flux_spectra(problem *p) {
+  std::vector<double> out;
+  for (size_t k = 0; k < p->fluxes.size(); ++k) {
+    double *fl = p->fluxes[k].flux();
+    out.insert(out.end(), fl, fl + p->fluxes[k].freq.size());
+    delete[] fl;
+  }
+  return out;
+}
+static size_t count_diff(const std::vector<double> &a, const std::vector<double> &b) {
+  if (a.size() != b.size()) return a.size() + b.size() + 1;
+  size_t n = 0;
+  for (size_t k = 0; k < a.size(); ++k)
+    if (memcmp(&a[k], &b[k], sizeof(double)) != 0 && !(a[k] == b[k])) ++n;
+  return n;
+}
+static double rel_diff(const std::vector<double> &a, const std::vector<double> &b) {
+  if (a.size() != b.size()) return 1e300;
+  double d2 = 0, r2 = 0;
+  for (size_t k = 0; k < a.size(); ++k) { d2 += (a[k] - b[k]) * (a[k] - b[k]); r2 += a[k] * a[k]; }
+  return r2 > 0 ? sqrt(d2 / r2) : sqrt(d2);
+}
+
 static double probe_value(problem *p) {
   component c = p->gv.dim == D1 ? Ex : Ez;
   return real(p->f->get_field(c, p->gv.center()));
@@ -720,11 +744,14 @@ int main(int argc, char **argv) {
     for (int i = 0; i < warmup; ++i) { A->f->step(); B->f->step(); } // drop-in off: both on the CPU
     double t0 = wall_time();
     double mid_ref = 0, mid_abi = 0, mid_energy_ref = 0, mid_energy_abi = 0;
+    std::vector<double> flux_mid_ref, flux_mid_abi, flux_end_ref, flux_end_abi;
     for (int i = 0; i < steps; ++i) {
       A->f->step();
       if (i == steps / 2) {
         mid_ref = probe_value(A);
         mid_energy_ref = A->f->electric_energy_in_box(A->gv.surroundings());
+        flux_mid_ref = flux_spectra(A);
+        for (size_t k = 0; k < A->fluxes.size(); ++k) A->fluxes[k].scale_dfts(std::complex<double>(0.5, 0.25)); // a host-side WRITER of dft[]
       }
       if (i == steps / 3 && addsrc) { // a source and a flux monitor added in mid-run
         A->f->add_point_source(A->gv.dim == D1 ? Ex : Ez, 0.22, 0.2, 0.0, 4.0, A->gv.center(), 0.7);
@@ -744,6 +771,10 @@ int main(int argc, char **argv) {
       if (i == steps / 2) { // host-side readers in mid-run, called like any user would: the patched get_field and
         mid_abi = probe_value(B); // loop_in_chunks (behind electric_energy_in_box) fetch the device's state themselves
         mid_energy_abi = B->f->electric_energy_in_box(B->gv.surroundings());
+        // DFT consumers straight on the patched reference: dft_flux::flux() fetches the accumulators (only them)
+        // from the device; scale_dfts() changes them on the host and the next step() sends them back
+        flux_mid_abi = flux_spectra(B);
+        for (size_t k = 0; k < B->fluxes.size(); ++k) B->fluxes[k].scale_dfts(std::complex<double>(0.5, 0.25));
       }
       if (syncmag > 0 && (i + 1) % syncmag == 0) {
         // the reference's own synchronize_magnetic_fields(): CPU on twin A (not yet stepped past here: use a
@@ -753,7 +784,11 @@ int main(int argc, char **argv) {
         if (!C) {
           fields::gpu_enable(NULL);
           C = build(cas, nchunks);
-          for (int k = 0; k < warmup + i + 1; ++k) C->f->step();
+          for (int k = 0; k < warmup + i + 1; ++k) {
+            C->f->step();
+            if (k - warmup == steps / 2) // the mid-run scale_dfts the other twins went through
+              for (size_t q = 0; q < C->fluxes.size(); ++q) C->fluxes[q].scale_dfts(std::complex<double>(0.5, 0.25));
+          }
           fields::gpu_enable(lib.c_str(), nl_mode, device);
         }
         C->f->synchronize_magnetic_fields(); // C has no attachment: the reference's CPU body
@@ -766,8 +801,10 @@ int main(int argc, char **argv) {
         C = 0;
       }
     }
+    flux_end_abi = flux_spectra(B); // before the full sync: the reader itself must fetch what it needs
     B->f->gpu_sync_to_host();
     double t2 = wall_time();
+    flux_end_ref = flux_spectra(A);
     const bool attached = B->f->gpu != 0;
     std::vector<marray> ma = collect(*A->f), mb = collect(*B->f);
     cmp_result r = compare(ma, mb);
@@ -780,13 +817,50 @@ int main(int argc, char **argv) {
             "\"first_bad\":\"%s\",\"ref_seconds\":%.6f,\"abi_seconds\":%.6f,\"probe_ref\":%.17g,"
             "\"probe_abi\":%.17g,\"probe_mid\":%.17g,\"attached\":%d,\"t_ref\":%d,\"t_abi\":%d,"
             "\"sync_checks\":%zu,\"sync_mismatched_elements\":%zu,\"probe_mid_ref\":%.17g,"
-            "\"energy_mid_ref\":%.17g,\"energy_mid_abi\":%.17g}\n",
+            "\"energy_mid_ref\":%.17g,\"energy_mid_abi\":%.17g,\"flux_values\":%zu,\"flux_mid_mismatched\":%zu,"
+            "\"flux_end_mismatched\":%zu,\"flux_mid_rel\":%.6g,\"flux_end_rel\":%.6g}\n",
             "dropin", cas.c_str(), (int)sizeof(realnum), steps, warmup, A->cells, A->f->num_chunks, r.narrays,
             r.nelems, r.nmismatch_arrays, r.nmismatch_elems, r.max_abs, relL2, r.first_bad.c_str(), t1 - t0,
             t2 - t1, probe_value(A), probe_value(B), mid_abi, (int)attached, A->f->t, B->f->t, sync_checks, sync_bad,
-            mid_ref, mid_energy_ref, mid_energy_abi);
+            mid_ref, mid_energy_ref, mid_energy_abi, flux_end_ref.size(), count_diff(flux_mid_ref, flux_mid_abi),
+            count_diff(flux_end_ref, flux_end_abi), rel_diff(flux_mid_ref, flux_mid_abi), rel_diff(flux_end_ref, flux_end_abi));
     delete A;
     delete B; // ~fields() -> gpu_detach()
+  }
+  else if (mode == "dropin_time") {
+    // the seam as a user meets it (python/simulation.py:2831-2834): ONE fields::step() call per time step on the
+    // patched reference, nothing else.  Timed: [steps] calls + one point probe (which waits for the device and
+    // reads one value) -- the attach (describe + upload), the warm-up and the final full download separately.
+    if (lib.empty()) { fprintf(stderr, "--lib required\n"); return 2; }
+    problem *B = build(cas, nchunks);
+    fields::gpu_enable(lib.c_str(), nl_mode, device);
+    const double ta = wall_time();
+    B->f->step(); // attaches
+    const double probe0 = probe_value(B);
+    const double tb = wall_time();
+    for (int i = 0; i < warmup; ++i) B->f->step();
+    (void)probe_value(B);
+    meepcu::attachment *att = (meepcu::attachment *)B->f->gpu;
+    const meepcu_stats s0 = att->stats();
+    const double t0 = wall_time();
+    for (int i = 0; i < steps; ++i) B->f->step();
+    const double tq = wall_time();
+    const double pv = probe_value(B);
+    const double t1 = wall_time();
+    const meepcu_stats s1 = att->stats();
+    B->f->gpu_sync_to_host();
+    const double t2 = wall_time();
+    fprintf(jf,
+            "{\"mode\":\"dropin_time\",\"backend\":\"%s\",\"case\":\"%s\",\"realnum_bytes\":%d,\"steps\":%d,\"warmup\":%d,"
+            "\"cells\":%ld,\"num_chunks\":%d,\"attach_seconds\":%.6f,\"enqueue_seconds\":%.6f,\"seconds\":%.6f,"
+            "\"ms_per_step\":%.6f,\"device_ms_per_step\":%.6f,\"mcells_per_s\":%.4f,\"sync_to_host_seconds\":%.6f,"
+            "\"kernel_launches_per_step\":%.2f,\"probe_first\":%.17g,\"probe\":%.17g,\"t\":%d}\n",
+            "dropin", cas.c_str(), (int)sizeof(realnum), steps, warmup, B->cells, B->f->num_chunks, tb - ta, tq - t0, t1 - t0,
+            (t1 - t0) * 1e3 / steps, (double)(s1.reserved[4] - s0.reserved[4]) * 1e-3 / steps,
+            B->cells * (double)steps / (t1 - t0) / 1e6, t2 - t1, (double)(s1.kernel_launches - s0.kernel_launches) / steps,
+            probe0, pv, B->f->t);
+    fields::gpu_enable(NULL);
+    delete B;
   }
 #endif
   else {

@@ -34,6 +34,11 @@ def test_patched_reference_steps_through_the_abi(case):
     # mid-run readers called straight on the patched reference (no explicit sync): get_field and, through
     # loop_in_chunks, electric_energy_in_box
     assert d["probe_mid"] == d["probe_mid_ref"] and d["energy_mid_abi"] == d["energy_mid_ref"]
+    # DFT consumers called on the patched reference in mid-run and at the end (dft_flux::flux), with a
+    # scale_dfts() -- a host-side writer of the accumulators -- in between
+    assert d["flux_mid_mismatched"] == 0 and d["flux_end_mismatched"] == 0, d
+    if case in ("lorentz3d:16", "dft3d:12"):
+        assert d["flux_values"] > 0
 
 
 @pytest.mark.gpu
@@ -44,6 +49,47 @@ def test_patched_reference_steps_on_the_gpu(case, tol):
     assert d["rel_l2"] <= tol, d
     assert abs(d["probe_mid"] - d["probe_mid_ref"]) <= tol * max(1.0, abs(d["probe_mid_ref"]))
     assert abs(d["energy_mid_abi"] - d["energy_mid_ref"]) <= 1e-9 * max(1e-30, abs(d["energy_mid_ref"]))
+    # flux spectra read by the reference's own dft_flux::flux() while the accumulators live on the device
+    # (stale or zero spectra would show here), before and after a host-side scale_dfts()
+    assert d["flux_mid_rel"] <= tol and d["flux_end_rel"] <= tol, d
+    if case.startswith("lorentz3d"):
+        assert d["flux_values"] > 0
+
+
+@pytest.mark.gpu
+def test_flux_spectrum_read_from_the_device():
+    d = run(CUDA_LIB, "dft3d:16", 60)
+    assert d["flux_values"] > 0 and d["flux_mid_rel"] <= 1e-12 and d["flux_end_rel"] <= 1e-12, d
+    assert d["rel_l2"] <= 1e-12
+
+
+def run_time(lib, case, steps):
+    drv = ref_driver("fp64_dropin")
+    if drv is None:
+        pytest.skip("oracle/_ref/fp64_dropin not built (reference tree absent)")
+    with tempfile.NamedTemporaryFile(suffix=".json") as tf:
+        env = dict(os.environ, OMP_NUM_THREADS="4")
+        subprocess.run([drv, "--mode", "dropin_time", "--lib", lib, "--case", case, "--steps", str(steps), "--warmup", "3",
+                        "--json", tf.name], check=True, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
+                       timeout=900)
+        return json.load(open(tf.name))
+
+
+def test_dropin_timing_mode_runs_one_step_per_call():
+    """bench.py's e2e_dropin leg: fields::step() of the patched reference called once per time step"""
+    d = run_time(ORACLE_LIB, "vac3d:24", 10)
+    assert d["t"] == 14 and d["steps"] == 10 and d["ms_per_step"] > 0 and d["probe"] != 0
+
+
+@pytest.mark.gpu
+def test_dropin_step_does_not_wait_for_the_device():
+    """one fields::step() call per time step must cost about one device step: the call only queues work
+    (no per-step scan of whole arrays, no per-step synchronisation)"""
+    d = run_time(CUDA_LIB, "vac3d:128", 200)
+    assert d["t"] == 204 and d["probe"] != 0
+    assert d["kernel_launches_per_step"] <= 12, d
+    assert d["enqueue_seconds"] < d["seconds"]
+    assert d["ms_per_step"] <= 1.5 * d["device_ms_per_step"] + 0.05, d
 
 
 @pytest.mark.parametrize("case,every", [("lorentz3d:16", 9), ("magdrude3d:12", 7), ("gyrosat3d:12", 9), ("wvg2d", 10)])
