@@ -835,10 +835,11 @@ template <class T> struct Ctx : CtxBase {
     return (T *)r->dev + e;
   }
 
-  // Host<->device copies go through two library-owned pinned staging buffers filled / drained by
-  // OpenMP memcpy, so that sync runs near PCIe speed although the caller's arrays are pageable
-  // (page-locking the caller's heap pages in place is not safe: neighbouring allocations that share
-  // a page would become half-pinned).
+  // Host<->device copies of big PAGEABLE arrays go through two library-owned pinned staging buffers filled /
+  // drained by OpenMP memcpy, so that sync runs near PCIe speed.  With meepcu_config::pin_host the caller's big
+  // mutable arrays are instead page-locked IN PLACE at finalize (cudaHostRegister) and copied by plain DMA: the
+  // caller then promises that those arrays outlive the context (they are unregistered in ~Ctx); arrays that
+  // cannot be registered (e.g. already registered by the caller) silently take the staging path.
   enum { kStageBytes = 64 << 20 };
   char *stage[2];
   cudaEvent_t stage_ev[2];

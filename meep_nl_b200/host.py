@@ -261,17 +261,23 @@ class structure:
                     if d != comp_dir(c) and sc.gv.has[d]:
                         sc.chi1inv[(c, d)] = np.full(sc.gv.ntot, value, self.rt)
 
-    def set_chi2(self, fn):  # structure_chunk::set_chi2, structure.cpp:832-866
-        self._set_chi(fn, "chi2")
+    def set_chi2(self, fn, elide_trivial=False):  # structure_chunk::set_chi2, structure.cpp:832-866
+        self._set_chi(fn, "chi2", elide_trivial)
 
-    def set_chi3(self, fn):
-        self._set_chi(fn, "chi3")
+    def set_chi3(self, fn, elide_trivial=False):
+        self._set_chi(fn, "chi3", elide_trivial)
 
-    def _set_chi(self, fn, which):
+    def _set_chi(self, fn, which, elide_trivial=False):
+        """elide_trivial: like the reference, a chunk where the function vanishes everywhere gets no array
+        (structure.cpp:818-827,851-862) -- chunks of one structure then differ in which update they need"""
         for sc in self.chunks:
             for c in (Ex, Ey, Ez):
                 if not sc.gv.has_field(c): continue
-                getattr(sc, which)[c] = np.ascontiguousarray(self._eval(sc, c, fn).astype(self.rt)).reshape(-1)
+                v = np.ascontiguousarray(self._eval(sc, c, fn).astype(self.rt)).reshape(-1)
+                if elide_trivial and not np.any(v):
+                    getattr(sc, which).pop(c, None)
+                    continue
+                getattr(sc, which)[c] = v
 
     def add_susceptibility(self, sigma, ft, sus):  # anisotropic_averaging.cpp:300-370 (diagonal)
         assert ft == E_stuff
@@ -866,7 +872,43 @@ class fields:
                         seen.add(id(arr)); n += arr.nbytes
         return n
 
+    def owned_arrays(self):
+        """every mutable array of the chunks this rank steps, as (name, ndarray) in a deterministic order that
+        does not depend on the rank decomposition (names carry the GLOBAL chunk index): what the N-rank ==
+        1-rank comparisons hash (the reference's own invariant, tests/three_d.cpp:95-229)"""
+        out = []
+        for gi_, fc in enumerate(self.chunks):
+            if not fc.mine: continue
+            seen = set()
+            for kind, g in (("f", fc.f), ("f_u", fc.f_u), ("f_w", fc.f_w), ("f_bfast", fc.f_bfast)):
+                for (c, cmp) in sorted(g):
+                    arr = g[(c, cmp)]
+                    if id(arr) in seen: continue  # H aliasing B
+                    seen.add(id(arr))
+                    out.append(("chunk%d.%s[%d][%d]" % (gi_, kind, c, cmp), arr))
+            for ip, pd in enumerate(fc.pol_data):
+                for kind in ("P", "P_prev"):
+                    for (c, cmp) in sorted(pd[kind]):
+                        out.append(("chunk%d.pol%d.%s[%d][%d]" % (gi_, ip, kind, c, cmp), pd[kind][(c, cmp)]))
+            for k, d in enumerate(fc.dfts):
+                out.append(("chunk%d.dft%d[%d]" % (gi_, k, d["c"]), d["dft"]))
+        return out
+
     def close(self):
         if self.ctx is not None:
             self.b.destroy(self.ctx)
             self.ctx = None
+
+    # the context page-locks the numpy arrays in place (pin_host) and keeps their addresses: it must go before they do
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -168,7 +168,8 @@ static problem *build(const std::string &spec, int nchunks) {
   problem *p = new problem;
   if (name == "vac3d") { // BASELINE config 2
     if (!n) n = 32;
-    p->gv = vol3d(n / a, n / a, n / a, a);
+    // vac3d:n:m -- the weak-scaling grid of m GPUs (m*n x n x n), for the reference arm of `bench.py --gpus m`
+    p->gv = vol3d((param > 1 ? param : 1.0) * n / a, n / a, n / a, a);
     p->s = new structure(p->gv, one, pml(1.0), identity(), nchunks);
     p->f = new fields(p->s);
     p->f->use_real_fields();

@@ -46,6 +46,29 @@ def test_reference_twin_comparison(flavour, case, steps, warmup, tol):
     assert d["rel_l2"] <= tol, d
 
 
+# BASELINE.json sizes (or the largest the reference's CPU twin finishes in seconds): the long-row 128-byte-pitch
+# layout, the k_mix tile ordering and the 16-plane march are exercised where they are benchmarked
+BASELINE_SIZE = [("fp64", "vac3d:256", 30, 1e-12), ("fp32", "vac3d:256", 30, 1e-5),
+                 ("fp64", "lorentz3d:192:100", 30, 1e-12), ("fp64", "nrslab3d:64", 12, 1e-12),  # (the reference's NR twin: ~3 s per step at 96^3)
+                 ("fp64", "phc3d:160:1.0", 30, 1e-12), ("fp32", "phc3d:160:1.0", 30, 1e-5)]
+
+
+@pytest.mark.parametrize("flavour,case,steps,tol", BASELINE_SIZE)
+def test_baseline_size_twins(flavour, case, steps, tol):
+    """every array of the reference's CPU twin against the GPU twin at benchmark sizes"""
+    drv = ref_driver(flavour)
+    if drv is None:
+        pytest.skip("oracle/_ref/%s not present on this machine" % flavour)
+    with tempfile.NamedTemporaryFile(suffix=".json") as tf:
+        env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 8), OMP_PROC_BIND="spread")
+        subprocess.run([drv, "--mode", "shim", "--lib", CUDA_LIB, "--case", case, "--steps", str(steps),
+                        "--warmup", "2", "--json", tf.name], check=True, env=env,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=1800)
+        d = json.load(open(tf.name))
+    assert d["backend"] == "cuda-sm_100a" and d["arrays"] > 0 and d["elements"] > 3e6 and d["finite"] == 1
+    assert d["probe_ref"] != 0 and d["rel_l2"] <= tol, d
+
+
 def test_known_results_on_gpu():
     """three of the reference's own golden numbers (tests/known_results.cpp:155-169), computed by
     the reference's objects stepping through libmeepcuda.so"""
