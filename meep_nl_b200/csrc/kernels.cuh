@@ -480,6 +480,19 @@ template <class T> struct Curl3DParams {
   const SrcEntry *csrc[3], *isrc[3];
   int ncsrc[3], nisrc[3];
   int ca0[3], ca1[3], ia0[3], ia1[3];
+  // ---- virtual E (B/H half of a chunk whose E arrays are not kept up to date while stepping) ----
+  // Where E = chi1inv * (D - dipoles) is a pure function of D (no PML, no polarisation, diagonal eps), storing E
+  // in the D/E half and reading it back in the B/H half moves 6 of the 21-24 values per cell for nothing
+  // (step_generic.cpp:891-894,903 write what :108 of the next half reads).  In virtual mode the D/E half of such a
+  // chunk writes no E, and the B/H half recomputes each operand from D (x chi1inv) as it loads it -- the same
+  // multiplication the reference did when it stored E, so every bit is the same.  Not-owned points: the E halo
+  // copies of step_boundaries land in the D array's not-owned points (nobody reads those while stepping) and
+  // the device copy of chi1inv is 1 there.
+  int virt;            // 1: operands of the B/H half may be read as vu * vg (launch argument vmode selects)
+  const T *vg[3];      // D components
+  const T *vu[3];      // chi1inv diagonal of the E components (NULL: E = D)
+  const SrcEntry *vsrc[3]; // integrated E sources of the chunk (update_eh.cpp:136-146): subtracted before the multiply
+  int nvsrc[3], va0[3], va1[3];
 };
 
 template <class T, bool IS_D, int K, bool SPECIAL>
@@ -516,10 +529,34 @@ __device__ __forceinline__ void curl3d_finish(const Curl3DParams<T> &P, int i, i
   e[i] = enew;
 }
 
+// one operand of the B/H curl in virtual-E mode: E_K[idx] recomputed as the D/E half would have stored it
+// (curl3d_finish: fmp = D - dipoles, enew = fmp * u), dipoles from the PREVIOUS step's dipole_E sample
+template <class T, int K, bool SPECIAL>
+__device__ __forceinline__ T virt_e_load(const Curl3DParams<T> &P, const T *__restrict__ d, const T *__restrict__ u, int idx,
+                                         const double *__restrict__ smp_prev) {
+  T v = __ldg(d + idx);
+  if (SPECIAL && P.nvsrc[K]) {
+    const int pa = idx / P.sA;
+    if (pa >= P.va0[K] && pa <= P.va1[K]) {
+      const SrcEntry *tab = P.vsrc[K];
+      for (int j = src_lower_bound(tab, P.nvsrc[K], idx); j < P.nvsrc[K] && tab[j].idx == idx; ++j) {
+        const SrcEntry se = tab[j];
+        const double2 dp = sample_dipole(smp_prev, se.tid, 1);
+        const double2 A = cmul(se.are, se.aim, dp.x, dp.y);
+        v = (T)((double)v - (P.cmp ? A.y : A.x));
+      }
+    }
+  }
+  if (u) v = v * __ldg(u + idx);
+  return v;
+}
+
 template <class T, bool IS_D, bool SPECIAL>
 __device__ __forceinline__ void curl3d_loop(const Curl3DParams<T> &P, const Tile t, int ib, int ic,
-                                            const bool act[3], const double *__restrict__ smp) {
+                                            const bool act[3], const double *__restrict__ smp,
+                                            const double *__restrict__ smp_prev = 0, int vmode = 0) {
   const int sA = P.sA, nA = P.nA;
+  const bool virt = !IS_D && vmode && P.virt;
   // neighbour offsets, clamped so that loads whose value no owned component consumes stay in bounds
   int oy, oz;
   if (!IS_D) {
@@ -530,9 +567,12 @@ __device__ __forceinline__ void curl3d_loop(const Curl3DParams<T> &P, const Tile
     oy = (ib > 0) ? -P.sB : 0;
     oz = (ic > 0) ? -1 : 0;
   }
-  const T *__restrict__ gx = P.g[0];
-  const T *__restrict__ gy = P.g[1];
-  const T *__restrict__ gz = P.g[2];
+  const T *__restrict__ gx = virt ? P.vg[0] : P.g[0];
+  const T *__restrict__ gy = virt ? P.vg[1] : P.g[1];
+  const T *__restrict__ gz = virt ? P.vg[2] : P.g[2];
+  const T *__restrict__ wx = virt ? P.vu[0] : 0; // multipliers of the operands (virtual E only)
+  const T *__restrict__ wy = virt ? P.vu[1] : 0;
+  const T *__restrict__ wz = virt ? P.vu[2] : 0;
   T *__restrict__ f0 = P.f[0];
   T *__restrict__ f1 = P.f[1];
   T *__restrict__ f2 = P.f[2];
@@ -544,10 +584,13 @@ __device__ __forceinline__ void curl3d_loop(const Curl3DParams<T> &P, const Tile
   const T *__restrict__ u2 = P.u[2];
   const bool hu0 = e0 && u0, hu1 = e1 && u1, hu2 = e2 && u2;
   int i = t.a0 * sA + ib * P.sB + ic;
+#define MCU_LDX(idx) (virt ? virt_e_load<T, 0, SPECIAL>(P, gx, wx, (idx), smp_prev) : __ldg(gx + (idx)))
+#define MCU_LDY(idx) (virt ? virt_e_load<T, 1, SPECIAL>(P, gy, wy, (idx), smp_prev) : __ldg(gy + (idx)))
+#define MCU_LDZ(idx) (virt ? virt_e_load<T, 2, SPECIAL>(P, gz, wz, (idx), smp_prev) : __ldg(gz + (idx)))
   T ry, rz; // g_y, g_z of the plane the x-difference needs, carried between iterations
   if (!IS_D) {
-    ry = __ldg(gy + i);
-    rz = __ldg(gz + i);
+    ry = MCU_LDY(i);
+    rz = MCU_LDZ(i);
   }
   else {
     const int ip = t.a0 > 0 ? i - sA : i;
@@ -575,16 +618,16 @@ __device__ __forceinline__ void curl3d_loop(const Curl3DParams<T> &P, const Tile
       if (hu2) prefetch_l2(u2 + ipf);
     }
     // ---- every load of this plane first ----
-    const T gx0 = __ldg(gx + i), gxy = __ldg(gx + i + oy), gxz = __ldg(gx + i + oz);
-    const T gyz = __ldg(gy + i + oz);
-    const T gzy = __ldg(gz + i + oy);
+    const T gx0 = MCU_LDX(i), gxy = MCU_LDX(i + oy), gxz = MCU_LDX(i + oz);
+    const T gyz = MCU_LDY(i + oz);
+    const T gzy = MCU_LDZ(i + oy);
     T gy0, gz0, gyx, gzx;
     if (!IS_D) {
       const int ox = (ia + 1 < nA) ? sA : 0;
       gy0 = ry;
       gz0 = rz;
-      gyx = __ldg(gy + i + ox);
-      gzx = __ldg(gz + i + ox);
+      gyx = MCU_LDY(i + ox);
+      gzx = MCU_LDZ(i + ox);
       ry = gyx;
       rz = gzx;
     }
@@ -612,6 +655,9 @@ __device__ __forceinline__ void curl3d_loop(const Curl3DParams<T> &P, const Tile
     if (on2)
       curl3d_finish<T, IS_D, 2, SPECIAL>(P, i, ia, ib, ic, (gyx - gy0 + gx0 - gxy), fo2, uv2, f2, e2, hu2, smp);
   }
+#undef MCU_LDX
+#undef MCU_LDY
+#undef MCU_LDZ
 }
 
 // hook run by a thread when it leaves a tile body (nothing today)
@@ -619,10 +665,12 @@ struct NoExit { __device__ __forceinline__ void operator()() const {} };
 
 template <class T, bool IS_D, class OnExit = NoExit>
 __device__ __forceinline__ void curl3d_body(const Curl3DParams<T> &P, const Tile t, bool special,
-                                            const double *__restrict__ smp, const OnExit on_exit = OnExit());
+                                            const double *__restrict__ smp, const double *__restrict__ smp_prev, int vmode,
+                                            const OnExit on_exit = OnExit());
 template <class T, bool IS_D, class OnExit>
 __device__ __forceinline__ void curl3d_body(const Curl3DParams<T> &P, const Tile t, bool special,
-                                            const double *__restrict__ smp, const OnExit on_exit) {
+                                            const double *__restrict__ smp, const double *__restrict__ smp_prev, int vmode,
+                                            const OnExit on_exit) {
   const int p = t.p0 + threadIdx.x;
   const int ib = p / P.pitch, ic = p - ib * P.pitch;
   if (ib >= P.nB || ic >= P.nC) { on_exit(); return; }
@@ -632,9 +680,9 @@ __device__ __forceinline__ void curl3d_body(const Curl3DParams<T> &P, const Tile
     act[k] = ib >= P.lo[k][1] && ib <= P.hi[k][1] && ic >= P.lo[k][2] && ic <= P.hi[k][2];
   if (!(act[0] || act[1] || act[2])) { on_exit(); return; }
   if (special)
-    curl3d_loop<T, IS_D, true>(P, t, ib, ic, act, smp);
+    curl3d_loop<T, IS_D, true>(P, t, ib, ic, act, smp, smp_prev, vmode);
   else
-    curl3d_loop<T, IS_D, false>(P, t, ib, ic, act, smp);
+    curl3d_loop<T, IS_D, false>(P, t, ib, ic, act, smp, smp_prev, vmode);
   on_exit();
 }
 
@@ -648,14 +696,14 @@ template <class U> __device__ __forceinline__ void block_copy_params(U *dst_, co
 template <class T, bool IS_D>
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 3 : 4)
     k_curl3d(const Curl3DParams<T> *__restrict__ params, const Tile *__restrict__ tiles,
-             const double *__restrict__ smp) {
+             const double *__restrict__ smp, const double *__restrict__ smp_prev, int vmode) {
   __shared__ Curl3DParams<T> P;
   Tile t = tiles[blockIdx.x];
   const bool special = (t.p0 & kTileSpecial) != 0;
   t.p0 &= ~kTileSpecial;
   block_copy_params(&P, params + t.param);
   __syncthreads();
-  curl3d_body<T, IS_D>(P, t, special, smp);
+  curl3d_body<T, IS_D>(P, t, special, smp, smp_prev, vmode);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -691,9 +739,27 @@ template <class T> __device__ __forceinline__ void vstore(T *p, const T *in) {
   *reinterpret_cast<VT *>(p) = v;
 }
 
-template <class T, bool IS_D, class OnExit = NoExit>
-__device__ __forceinline__ void curl3d_v_body(const Curl3DParams<T> &P, const Tile t, const OnExit on_exit = OnExit()) {
+// operand vector of the B/H curl: g[idx..idx+V), times u[idx..idx+V) in virtual-E mode with a chi1inv array
+template <class T, bool VU> __device__ __forceinline__ void vload_e(T *out, const T *g, const T *u, int idx) {
+  vload<T>(out, g + idx);
+  if (VU && u) {
+    T w[VecOf<T>::V];
+    vload<T>(w, u + idx);
+#pragma unroll
+    for (int j = 0; j < VecOf<T>::V; ++j) out[j] = out[j] * w[j];
+  }
+}
+template <class T, bool VU> __device__ __forceinline__ T sload_e(const T *g, const T *u, int idx) {
+  const T v = __ldg(g + idx);
+  return (VU && u) ? v * __ldg(u + idx) : v;
+}
+
+// VU: compiled with the chi1inv multiplication of virtual-E operands (only launched when some chunk needs it, so
+// that the plain kernel keeps its register count)
+template <class T, bool IS_D, bool VU = false, class OnExit = NoExit>
+__device__ __forceinline__ void curl3d_v_body(const Curl3DParams<T> &P, const Tile t, int vmode = 0, const OnExit on_exit = OnExit()) {
   constexpr int V = VecOf<T>::V;
+  const bool virt = !IS_D && vmode && P.virt;
   const int pv = P.pitch / V; // vectors per row
   const int p = t.p0 + threadIdx.x;
   const int ib = p / pv, ic = (p - ib * pv) * V;
@@ -722,9 +788,12 @@ __device__ __forceinline__ void curl3d_v_body(const Curl3DParams<T> &P, const Ti
     oy = (ib > 0) ? -P.sB : 0;
     ozs = (ic > 0) ? -1 : 0;
   }
-  const T *__restrict__ gx = P.g[0];
-  const T *__restrict__ gy = P.g[1];
-  const T *__restrict__ gz = P.g[2];
+  const T *__restrict__ gx = virt ? P.vg[0] : P.g[0];
+  const T *__restrict__ gy = virt ? P.vg[1] : P.g[1];
+  const T *__restrict__ gz = virt ? P.vg[2] : P.g[2];
+  const T *__restrict__ wx = (VU && virt) ? P.vu[0] : 0;
+  const T *__restrict__ wy = (VU && virt) ? P.vu[1] : 0;
+  const T *__restrict__ wz = (VU && virt) ? P.vu[2] : 0;
   T *__restrict__ f0 = P.f[0];
   T *__restrict__ f1 = P.f[1];
   T *__restrict__ f2 = P.f[2];
@@ -739,8 +808,8 @@ __device__ __forceinline__ void curl3d_v_body(const Curl3DParams<T> &P, const Ti
   int i = t.a0 * sA + ib * P.sB + ic;
   T ry[V], rz[V];
   if (!IS_D) {
-    vload<T>(ry, gy + i);
-    vload<T>(rz, gz + i);
+    vload_e<T, VU>(ry, gy, wy, i);
+    vload_e<T, VU>(rz, gz, wz, i);
   }
   else {
     const int ip = t.a0 > 0 ? i - sA : i;
@@ -763,20 +832,23 @@ __device__ __forceinline__ void curl3d_v_body(const Curl3DParams<T> &P, const Ti
       if (hu0) prefetch_l2(u0 + ipf);
       if (hu1) prefetch_l2(u1 + ipf);
       if (hu2) prefetch_l2(u2 + ipf);
+      if (VU && wx) prefetch_l2(wx + ipf);
+      if (VU && wy) prefetch_l2(wy + ipf);
+      if (VU && wz) prefetch_l2(wz + ipf);
     }
     T gx0[V], gxy[V], gy0[V], gz0[V], gzy[V], gyx[V], gzx[V];
     T gxs, gys; // the scalar z neighbours of g_x and g_y
-    vload<T>(gx0, gx + i);
-    vload<T>(gxy, gx + i + oy);
-    gxs = __ldg(gx + i + ozs);
-    gys = __ldg(gy + i + ozs);
-    vload<T>(gzy, gz + i + oy);
+    vload_e<T, VU>(gx0, gx, wx, i);
+    vload_e<T, VU>(gxy, gx, wx, i + oy);
+    gxs = sload_e<T, VU>(gx, wx, i + ozs);
+    gys = sload_e<T, VU>(gy, wy, i + ozs);
+    vload_e<T, VU>(gzy, gz, wz, i + oy);
     if (!IS_D) {
       const int ox = (ia + 1 < nA) ? sA : 0;
 #pragma unroll
       for (int j = 0; j < V; ++j) { gy0[j] = ry[j]; gz0[j] = rz[j]; }
-      vload<T>(gyx, gy + i + ox);
-      vload<T>(gzx, gz + i + ox);
+      vload_e<T, VU>(gyx, gy, wy, i + ox);
+      vload_e<T, VU>(gzx, gz, wz, i + ox);
 #pragma unroll
       for (int j = 0; j < V; ++j) { ry[j] = gyx[j]; rz[j] = gzx[j]; }
     }
@@ -839,14 +911,14 @@ __device__ __forceinline__ void curl3d_v_body(const Curl3DParams<T> &P, const Ti
   on_exit();
 }
 
-template <class T, bool IS_D>
+template <class T, bool IS_D, bool VU = false>
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : 3)
-    k_curl3d_v(const Curl3DParams<T> *__restrict__ params, const Tile *__restrict__ tiles) {
+    k_curl3d_v(const Curl3DParams<T> *__restrict__ params, const Tile *__restrict__ tiles, int vmode) {
   __shared__ Curl3DParams<T> P;
   const Tile t = tiles[blockIdx.x];
   block_copy_params(&P, params + t.param);
   __syncthreads();
-  curl3d_v_body<T, IS_D>(P, t);
+  curl3d_v_body<T, IS_D, VU>(P, t, vmode);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1126,7 +1198,12 @@ template <class T> struct ConnTable {
   const T *const *src;
   const T *phase; // (re,im) per complex transfer, PHASE only
   long long n;    // number of realnum transfers (PHASE: 2 per complex)
+  const T *const *mul; // per transfer: chi1inv element the source is multiplied by (virtual-E sources), or NULL table
 };
+template <class T> __device__ __forceinline__ T conn_value(const T *src, const T *mul) {
+  const T v = *src;
+  return mul ? v * *mul : v; // E = chi1inv * D of a chunk that does not store E (see Curl3DParams::virt)
+}
 
 template <class T>
 __global__ void __launch_bounds__(kThreads)
@@ -1137,7 +1214,8 @@ __global__ void __launch_bounds__(kThreads)
   for (long long n = t0; n < negate.n; n += stride) *negate.dst[n] = -*negate.src[n];
   for (long long n = t0; n < phase.n / 2; n += stride) { // step.cpp:188-194
     const T pr = phase.phase[2 * n], pi = phase.phase[2 * n + 1];
-    const T br = *phase.src[2 * n], bi = *phase.src[2 * n + 1];
+    const T br = conn_value<T>(phase.src[2 * n], phase.mul ? phase.mul[2 * n] : 0),
+            bi = conn_value<T>(phase.src[2 * n + 1], phase.mul ? phase.mul[2 * n + 1] : 0);
     *phase.dst[2 * n] = pr * br - pi * bi;
     *phase.dst[2 * n + 1] = pr * bi + pi * br;
   }
@@ -1151,6 +1229,7 @@ template <class T> struct ConnRun {
   T *dst;
   const T *src;
   int n, dst_stride, src_stride, negate;
+  const T *mul; // NULL, or the chi1inv element of src[0] (same stride as src): virtual-E sources
 };
 constexpr int kConnPiece = 128; // runs are cut into pieces of at most this many elements
 template <class T>
@@ -1164,7 +1243,10 @@ __global__ void __launch_bounds__(kThreads) k_conn_runs(const ConnRun<T> *__rest
 #pragma unroll
   for (int k = 0; k < kConnPiece / 32; ++k) {
     const int j = lane + 32 * k;
-    if (j < q.n) v[k] = q.src[(long long)j * q.src_stride];
+    if (j < q.n) {
+      v[k] = q.src[(long long)j * q.src_stride];
+      if (q.mul) v[k] = v[k] * q.mul[(long long)j * q.src_stride];
+    }
   }
 #pragma unroll
   for (int k = 0; k < kConnPiece / 32; ++k) {
@@ -1189,10 +1271,10 @@ constexpr int kTileGeneral = 1 << 29; // Tile::p0 flag inside a k_mix table
 #ifndef MCU_MIX_F32_CTAS
 #define MCU_MIX_F32_CTAS 3
 #endif
-template <class T, bool IS_D>
+template <class T, bool IS_D, bool VU = false>
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : MCU_MIX_F32_CTAS)
     k_mix(const Curl3DParams<T> *__restrict__ cparams, const HalfParams<T> *__restrict__ hparams,
-          const Tile *__restrict__ tiles) {
+          const Tile *__restrict__ tiles, int vmode) {
   struct G { HalfHeader<T> H; CompParams<T> C; };
   constexpr size_t kBytes = sizeof(Curl3DParams<T>) > sizeof(G) ? sizeof(Curl3DParams<T>) : sizeof(G);
   __shared__ __align__(16) unsigned char raw[kBytes];
@@ -1210,7 +1292,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : MCU_MIX_F32_CTA
     Curl3DParams<T> *P = reinterpret_cast<Curl3DParams<T> *>(raw);
     block_copy_params(P, cparams + t.param);
     __syncthreads();
-    curl3d_v_body<T, IS_D>(*P, t);
+    curl3d_v_body<T, IS_D, VU>(*P, t, vmode);
   }
 }
 
@@ -1219,9 +1301,50 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : MCU_MIX_F32_CTA
 // (order PHASE | NEGATE | COPY, src/step.cpp:257-268), NCCL moves the buffers over NVLink, and
 // k_unpack applies process_incoming_chunk_data (src/step.cpp:173-224) on the receiving side.
 template <class T>
-__global__ void __launch_bounds__(kThreads) k_pack(const T *const *__restrict__ src, T *__restrict__ buf, long long n) {
+__global__ void __launch_bounds__(kThreads) k_pack(const T *const *__restrict__ src, T *__restrict__ buf, long long n,
+                                                   const T *const *__restrict__ mul = 0) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) buf[k] = *src[k];
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+    buf[k] = conn_value<T>(src[k], mul ? mul[k] : 0);
+}
+
+// virtual E made real again (host syncs): e = u * d over the whole array (u is 1 at not-owned points, where d holds
+// the E halo), then the dipoles of the integrated sources (k_virt_src)
+template <class T> __global__ void __launch_bounds__(kThreads) k_virt_materialise(T *__restrict__ e, const T *__restrict__ d, const T *__restrict__ u, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) e[i] = u ? d[i] * u[i] : d[i];
+}
+template <class T> __global__ void k_virt_src(T *__restrict__ e, const T *__restrict__ d, const T *__restrict__ u, const SrcEntry *__restrict__ tab, int n,
+                                              int cmp, const double *__restrict__ smp_prev) {
+  // one thread: the sources of a point are applied in list order (tab is sorted by index, stable)
+  if (blockIdx.x || threadIdx.x) return;
+  int j = 0;
+  while (j < n) {
+    const long long idx = tab[j].idx;
+    T v = d[idx];
+    for (; j < n && tab[j].idx == idx; ++j) {
+      const double2 dp = sample_dipole(smp_prev, tab[j].tid, 1);
+      const double2 A = cmul(tab[j].are, tab[j].aim, dp.x, dp.y);
+      v = (T)((double)v - (cmp ? A.y : A.x));
+    }
+    e[idx] = u ? v * u[idx] : v;
+  }
+}
+// device copy of a chi1inv array: 1 at the not-owned points of its component (see Curl3DParams::virt)
+template <class T> __global__ void __launch_bounds__(kThreads) k_virt_patch_u(T *__restrict__ u, int nA, int nB, int pitch, int lo0, int hi0, int lo1, int hi1, int lo2, int hi2) {
+  const long long n = (long long)nA * nB * pitch, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int c = (int)(i % pitch);
+    const long long r = i / pitch;
+    const int b = (int)(r % nB), a = (int)(r / nB);
+    if (a < lo0 || a > hi0 || b < lo1 || b > hi1 || c < lo2 || c > hi2) u[i] = (T)1;
+  }
+}
+// gather with the same rule (meepcu_read_values on a virtual E array)
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_gather(const T *const *__restrict__ src, const T *const *__restrict__ mul, T *__restrict__ buf, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) buf[k] = conn_value<T>(src[k], mul[k]);
 }
 template <class T>
 __global__ void __launch_bounds__(kThreads)

@@ -129,6 +129,7 @@ struct ArrayRec {
   bool is_field;  // f[c][cmp] (NaN check)
   bool pinned;    // host array page-locked in place (meepcu_config::pin_host)
   unsigned group; // MEEPCU_SYNC_* group it travels with (meepcu_sync_subset)
+  int comp;       // field component of an f[c][cmp] array (-1: something else)
 };
 
 struct Geom { // device layout of one chunk
@@ -270,7 +271,7 @@ template <class T> struct Ctx : CtxBase {
   struct RemoteList { std::vector<const void *> ptr[3]; std::vector<char> phases; };
   std::map<int, RemoteList> rsend[MEEPCU_NUM_FIELD_TYPES], rrecv[MEEPCU_NUM_FIELD_TYPES];
   struct RemoteDev { // per field type, after finalize
-    const T **d_src; T *d_sendbuf; long long n_send;
+    const T **d_src; const T **d_mul; T *d_sendbuf; long long n_send;
     T **d_dst; T *d_recvbuf; long long n_recv;
     T *d_phase; long long *d_seg; int nseg;
     std::vector<int> send_peer, recv_peer;
@@ -396,6 +397,17 @@ template <class T> struct Ctx : CtxBase {
   size_t step_ev_next;
   double total_step_ms;
   bool halo_stale; // deferred local halo copies (B/D/P, normal-plane E/H) not materialised since the last step
+  // ---- virtual E (kernels.cuh, Curl3DParams::virt): chunks whose E arrays are not stored while stepping ----
+  struct VirtComp { T *e; const T *d; T *u; const SrcEntry *src; int nsrc, cmp, chunk, comp; long long n; };
+  std::vector<VirtComp> virt_comps;
+  std::map<const char *, const char *> virt_alias; // host base of a virtual E array -> host base of its D array
+  std::map<const char *, const char *> virt_mul;   // ... -> host base of its chi1inv array (absent: E = D)
+  std::set<int> virt_chunks;
+  bool virt_any;        // some chunk of SOME rank is virtual (the sync sequence is then the same on every rank)
+  bool virt_vu;         // some virtual chunk of this rank multiplies by chi1inv
+  bool e_virtual;       // stepped since the E arrays were last uploaded: those of virtual chunks are out of date
+  std::vector<double> last_row; // src_time samples of the last step taken (its dipole_E is in the stored E)
+  std::vector<long long> h_src_idx; // device index of every entry of d_src
   SrcEntry *d_src;
 
   // synchronize_magnetic_fields state (energy_and_flux.cpp:97-177)
@@ -435,6 +447,7 @@ template <class T> struct Ctx : CtxBase {
     step_ev_next = 0;
     total_step_ms = 0;
     halo_stale = false;
+    virt_any = virt_vu = e_virtual = false;
     mag_backup = 0;
     mag_synced = in_mag_sync = false;
     stage_next = 0;
@@ -442,7 +455,7 @@ template <class T> struct Ctx : CtxBase {
     my_rank = 0;
     n_ranks = 1;
     memset(rdev, 0, sizeof(RemoteDev) * 0); // vectors inside: value-initialised below
-    for (int ft = 0; ft < MEEPCU_NUM_FIELD_TYPES; ++ft) { rdev[ft].d_src = 0; rdev[ft].d_sendbuf = 0; rdev[ft].n_send = 0; rdev[ft].d_dst = 0; rdev[ft].d_recvbuf = 0; rdev[ft].n_recv = 0; rdev[ft].d_phase = 0; rdev[ft].d_seg = 0; rdev[ft].nseg = 0; }
+    for (int ft = 0; ft < MEEPCU_NUM_FIELD_TYPES; ++ft) { rdev[ft].d_src = 0; rdev[ft].d_mul = 0; rdev[ft].d_sendbuf = 0; rdev[ft].n_send = 0; rdev[ft].d_dst = 0; rdev[ft].d_recvbuf = 0; rdev[ft].n_recv = 0; rdev[ft].d_phase = 0; rdev[ft].d_seg = 0; rdev[ft].nseg = 0; }
     memset(kc_ms, 0, sizeof kc_ms);
     memset(kc_launches, 0, sizeof kc_launches);
     memset(kc_bytes, 0, sizeof kc_bytes);
@@ -721,15 +734,19 @@ template <class T> struct Ctx : CtxBase {
       RemoteDev &R = rdev[ft];
       if (rsend[ft].empty() && rrecv[ft].empty()) continue;
       if (!comm) return fail(MEEPCU_ESTATE, "remote connections given but meepcu_comm_init not called");
-      std::vector<const T *> hsrc;
+      std::vector<const T *> hsrc, hmul;
+      bool any_mul = false;
       for (typename std::map<int, RemoteList>::iterator it = rsend[ft].begin(); it != rsend[ft].end(); ++it) {
         R.send_peer.push_back(it->first);
         R.send_off.push_back((long long)hsrc.size());
         for (int kind = 0; kind < 3; ++kind)
           for (size_t k = 0; k < it->second.ptr[kind].size(); ++k) {
-            const T *d = dev_elem(it->second.ptr[kind][k]);
+            const T *m = 0;
+            const T *d = dev_elem_v(it->second.ptr[kind][k], ft, &m);
             if (!d) return fail(MEEPCU_EINVAL, "remote send pointer outside the registered arrays");
             hsrc.push_back(d);
+            hmul.push_back(m);
+            if (m) any_mul = true;
           }
         R.send_n.push_back((long long)hsrc.size() - R.send_off.back());
       }
@@ -743,7 +760,8 @@ template <class T> struct Ctx : CtxBase {
         for (int kind = 0; kind < 3; ++kind) {
           seg.push_back((long long)it->second.ptr[kind].size());
           for (size_t k = 0; k < it->second.ptr[kind].size(); ++k) {
-            T *d = dev_elem(it->second.ptr[kind][k]);
+            const T *mx = 0;
+            T *d = dev_elem_v(it->second.ptr[kind][k], ft, &mx);
             if (!d) return fail(MEEPCU_EINVAL, "remote recv pointer outside the registered arrays");
             hdst.push_back(d);
           }
@@ -757,6 +775,7 @@ template <class T> struct Ctx : CtxBase {
       R.n_recv = (long long)hdst.size();
       R.nseg = (int)R.recv_peer.size();
       RC(upload(hsrc, &R.d_src));
+      if (any_mul) RC(upload(hmul, &R.d_mul));
       RC(upload(hdst, &R.d_dst));
       RC(upload(hphase, &R.d_phase));
       RC(upload(seg, &R.d_seg));
@@ -773,7 +792,7 @@ template <class T> struct Ctx : CtxBase {
     if (prof) RC(prof_begin(KC_CONN));
     if (R.n_send) {
       const int grid = (int)std::min<long long>((R.n_send + kThreads - 1) / kThreads, 148 * 8);
-      k_pack<T><<<grid, kThreads, 0, sx>>>(R.d_src, R.d_sendbuf, R.n_send);
+      k_pack<T><<<grid, kThreads, 0, sx>>>(R.d_src, R.d_sendbuf, R.n_send, R.d_mul);
       launches++;
     }
     const int dtype = sizeof(T) == 8 ? 8 /* ncclFloat64 */ : 7 /* ncclFloat32 */;
@@ -795,7 +814,7 @@ template <class T> struct Ctx : CtxBase {
   // ------------------------------------------------------------------------------------------
   // array registry
   int reg(const void *host, int chunk, int kind, size_t n_host, size_t n_dev, bool mut,
-          bool is_field = false, unsigned group = MEEPCU_SYNC_MATERIALS) {
+          bool is_field = false, unsigned group = MEEPCU_SYNC_MATERIALS, int comp = -1) {
     if (!host) return MEEPCU_OK;
     const char *key = (const char *)host;
     std::map<const char *, ArrayRec>::iterator it = arrays.find(key);
@@ -804,9 +823,9 @@ template <class T> struct Ctx : CtxBase {
         return fail(MEEPCU_EINVAL, "host array registered twice with different shapes");
       it->second.mut = it->second.mut || mut;
       it->second.is_field = it->second.is_field || is_field;
-      return MEEPCU_OK;
+      return MEEPCU_OK; // (H aliasing B keeps the B component: same Yee position)
     }
-    ArrayRec r = {host, 0, chunk, kind, n_host, n_dev, mut, is_field, false, group};
+    ArrayRec r = {host, 0, chunk, kind, n_host, n_dev, mut, is_field, false, group, comp};
     arrays[key] = r;
     return MEEPCU_OK;
   }
@@ -833,6 +852,111 @@ template <class T> struct Ctx : CtxBase {
     if (!r) return 0;
     if (r->kind == A_GRID) return (T *)r->dev + chunks[r->chunk].g.dev_index((long long)e);
     return (T *)r->dev + e;
+  }
+
+  // device address of one element as the STEPPING kernels see it: an element of an E array that is not stored
+  // while stepping is the same element of the D array (*mul: the chi1inv element a reader multiplies it by)
+  T *dev_elem_v(const void *p, int ft, const T **mul) const {
+    *mul = 0;
+    size_t e = 0;
+    const ArrayRec *r = find(p, sizeof(T), &e);
+    if (!r) return 0;
+    if (ft == MEEPCU_E_STUFF && r->kind == A_GRID && !virt_alias.empty()) {
+      std::map<const char *, const char *>::const_iterator it = virt_alias.find((const char *)r->host);
+      if (it != virt_alias.end()) {
+        const long long di = chunks[r->chunk].g.dev_index((long long)e);
+        std::map<const char *, const char *>::const_iterator mu = virt_mul.find((const char *)r->host);
+        if (mu != virt_mul.end()) *mul = dev(mu->second) + di;
+        return dev(it->second) + di;
+      }
+    }
+    if (r->kind == A_GRID) return (T *)r->dev + chunks[r->chunk].g.dev_index((long long)e);
+    return (T *)r->dev + e;
+  }
+  // Is the E update of this chunk a pure function of D (E = chi1inv_diag * (D - dipoles)), and does nobody but the
+  // B/H curl kernels and the halo copies read its E arrays?  (3-D, no PML / conductivity / polarisation / BFAST,
+  // no off-diagonal or nonlinear update, no metal plane, no DFT of E or D, dipoles away from the chunk's faces)
+  bool virt_eligible(size_t ic, const std::map<const char *, unsigned> &zmask) const {
+    const ChunkH &ch = chunks[ic];
+    const Geom &g = ch.g;
+    if (cfg.dim != MEEPCU_D3 || g.ntot_dev >= ((size_t)1 << 31)) return false;
+    if (cfg.bfast_scaled_k[0] || cfg.bfast_scaled_k[1] || cfg.bfast_scaled_k[2]) return false;
+    for (int d = 0; d < 3; ++d)
+      if (!g.has[d] || ch.d.sigsize[d] > 1 || g.num[d] < 6) return false;
+    if (!ch.pol[0].empty() || !ch.pol[1].empty()) return false;
+    const int ncmp = cfg.is_real ? 1 : 2;
+    for (int k = 0; k < 3; ++k) {
+      const int ec = dir_comp(MEEPCU_E_STUFF, k), dc = dir_comp(MEEPCU_D_STUFF, k), hc = dir_comp(MEEPCU_H_STUFF, k),
+                bc = dir_comp(MEEPCU_B_STUFF, k);
+      const int cs[4] = {ec, dc, hc, bc};
+      for (int q = 0; q < 4; ++q)
+        for (int d = 0; d < 5; ++d)
+          if (ch.d.conductivity[cs[q]][d]) return false;
+      for (int cmp = 0; cmp < ncmp; ++cmp) {
+        if (!ch.d.f[ec][cmp] || !ch.d.f[dc][cmp] || !ch.d.f[hc][cmp] || !ch.d.f[bc][cmp] || ch.d.f[ec][cmp] == ch.d.f[dc][cmp])
+          return false;
+        if (zmask.count((const char *)ch.d.f[ec][cmp]) || zmask.count((const char *)ch.d.f[dc][cmp])) return false;
+      }
+      const int d1 = (k + 1) % 3, d2 = (k + 2) % 3;
+      const void *u1 = ch.d.chi1inv[ec][d1], *u2 = ch.d.chi1inv[ec][d2];
+      if (cfg.nl_mode == MEEPCU_NL_UPSTREAM_PADE) {
+        if (u1 || u2 || ch.d.chi3[ec]) return false;
+      }
+      else if (u1 && u2 && ch.d.chi3[ec])
+        return false;
+      for (int half = 0; half < 2; ++half) { // the hard-wired step plan of the interior kernels (k_curl3d)
+        const int cc = dir_comp(half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF, k), ftg = half ? MEEPCU_H_STUFF : MEEPCU_E_STUFF;
+        if (!ch.have_plus[cc] || !ch.have_minus[cc] || ch.plus_c[cc] != dir_comp(ftg, (k + 2) % 3) || ch.plus_d[cc] != (k + 1) % 3 ||
+            ch.minus_c[cc] != dir_comp(ftg, (k + 1) % 3) || ch.minus_d[cc] != (k + 2) % 3)
+          return false;
+      }
+    }
+    for (size_t id = 0; id < ch.dft.size(); ++id)
+      if (is_electric(ch.dft[id].d.c) || is_D(ch.dft[id].d.c)) return false;
+    for (size_t is = 0; is < ch.src.size(); ++is) {
+      const SrcH &sr = ch.src[is];
+      if (sr.ft != MEEPCU_D_STUFF || !sr.integrated) continue;
+      for (size_t j = 0; j < sr.idx.size(); ++j) {
+        long long rem = sr.idx[j];
+        for (int d = 0; d < 3; ++d) {
+          const long long q = rem / g.hs[d];
+          rem -= q * g.hs[d];
+          if (q < 2 || q > g.num[d] - 2) return false;
+        }
+      }
+    }
+    return true;
+  }
+  int virt_patch_u() { // after every upload of the materials
+    for (size_t k = 0; k < virt_comps.size(); ++k) {
+      const VirtComp &vc = virt_comps[k];
+      if (!vc.u || vc.cmp != 0) continue;
+      const Geom &g = chunks[vc.chunk].g;
+      int lo[3], hi[3];
+      for (int ax = 0; ax < 3; ++ax) {
+        const int d = g.dir_of_axis[ax];
+        lo[ax] = 1 - g.yee_shift(vc.comp, d);
+        hi[ax] = g.num[d] - g.yee_shift(vc.comp, d);
+      }
+      k_virt_patch_u<T><<<148 * 8, kThreads, 0, st>>>(vc.u, g.nax[0], g.nax[1], g.pitch, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]);
+      launches++;
+    }
+    return MEEPCU_OK;
+  }
+  // E arrays of the virtual chunks := what the D/E half would have stored (before the host reads them)
+  int virt_materialise() {
+    char *p_prev = 0;
+    RC(ring_put(last_row.data(), last_row.size() * sizeof(double), &p_prev));
+    for (size_t k = 0; k < virt_comps.size(); ++k) {
+      const VirtComp &vc = virt_comps[k];
+      k_virt_materialise<T><<<148 * 8, kThreads, 0, st>>>(vc.e, vc.d, vc.u, vc.n);
+      launches++;
+      if (vc.nsrc) {
+        k_virt_src<T><<<1, 32, 0, st>>>(vc.e, vc.d, vc.u, vc.src, vc.nsrc, vc.cmp, (const double *)p_prev);
+        launches++;
+      }
+    }
+    return MEEPCU_OK;
   }
 
   // Host<->device copies of big PAGEABLE arrays go through two library-owned pinned staging buffers filled /
@@ -1098,7 +1222,7 @@ template <class T> struct Ctx : CtxBase {
       const size_t nh = g.ntot_host, nd = g.ntot_dev;
       for (int c = 0; c < 20; ++c) {
         for (int cmp = 0; cmp < 2; ++cmp) {
-          RC(reg(ch.d.f[c][cmp], (int)ic, A_GRID, nh, nd, true, true, MEEPCU_SYNC_FIELDS));
+          RC(reg(ch.d.f[c][cmp], (int)ic, A_GRID, nh, nd, true, true, MEEPCU_SYNC_FIELDS, c));
           RC(reg(ch.d.f_u[c][cmp], (int)ic, A_GRID, nh, nd, true, false, MEEPCU_SYNC_AUX));
           RC(reg(ch.d.f_w[c][cmp], (int)ic, A_GRID, nh, nd, true, false, MEEPCU_SYNC_AUX));
           RC(reg(ch.d.f_cond[c][cmp], (int)ic, A_GRID, nh, nd, true, false, MEEPCU_SYNC_AUX));
@@ -1230,6 +1354,13 @@ template <class T> struct Ctx : CtxBase {
       }
     }
     RC(upload(all_src, &d_src));
+    h_src_idx.resize(all_src.size());
+    for (size_t k = 0; k < all_src.size(); ++k) h_src_idx[k] = all_src[k].idx;
+
+    // ---- 4b. chunks whose E arrays are not stored while stepping (Curl3DParams::virt) ----
+    if (!getenv("MEEPCU_NO_VIRTUAL_E"))
+      for (size_t ic = 0; ic < chunks.size(); ++ic)
+        if (virt_eligible(ic, zmask)) virt_chunks.insert((int)ic);
 
     // ---- 5. per-(chunk, half, cmp) parameter blocks + tiles ----
     std::vector<Tile> tiles[2][4], eh_tiles[2], c3d_tiles[2], c3dv_tiles[2], gv_tiles[2][2];
@@ -1415,6 +1546,10 @@ template <class T> struct Ctx : CtxBase {
           int seg = 16;
           if (g.nax[0] <= 24) seg = g.nax[0];
           if (getenv("MEEPCU_SEG")) seg = std::max(1, atoi(getenv("MEEPCU_SEG")));
+          const bool virt = virt_chunks.count((int)ic) != 0;
+          if (virt && !fast) return fail(MEEPCU_ESTATE, "internal: virtual-E chunk off the interior fast path");
+          if (virt && half == 1) // the D/E half of such a chunk stores no E
+            for (int k = 0; k < 3; ++k) { P.comp[k].e = 0; P.comp[k].u = 0; P.comp[k].nisrc = 0; P.comp[k].zmask_eh = 0; }
           if (fast) {
             Curl3DParams<T> Q;
             memset(&Q, 0, sizeof Q);
@@ -1434,6 +1569,20 @@ template <class T> struct Ctx : CtxBase {
               Q.csrc[k] = c.csrc; Q.ncsrc[k] = c.ncsrc; Q.ca0[k] = c.csrc_amin; Q.ca1[k] = c.csrc_amax;
               Q.isrc[k] = c.e ? c.isrc : 0; Q.nisrc[k] = c.e ? c.nisrc : 0; Q.ia0[k] = c.isrc_amin; Q.ia1[k] = c.isrc_amax;
               if (Q.ncsrc[k] || Q.nisrc[k]) Q.any_src = 1;
+              if (virt && half == 0) { // the B/H half reads E_k = chi1inv_k * (D_k - dipoles) as it loads its operands
+                const int ecv = dir_comp(MEEPCU_E_STUFF, k), dcv = dir_comp(MEEPCU_D_STUFF, k);
+                const SrcRange &RE = ranges[(ic * 2 + 1) * 3 + k];
+                Q.virt = 1;
+                Q.vg[k] = dev(ch.d.f[dcv][cmp]);
+                Q.vu[k] = dev(ch.d.chi1inv[ecv][k]);
+                Q.vsrc[k] = d_src + RE.i0; Q.nvsrc[k] = (int)(RE.i1 - RE.i0); Q.va0[k] = RE.ia0; Q.va1[k] = RE.ia1;
+                if (Q.vu[k]) virt_vu = true;
+                VirtComp vc = {dev(ch.d.f[ecv][cmp]), Q.vg[k], dev(ch.d.chi1inv[ecv][k]), Q.vsrc[k], Q.nvsrc[k], cmp, (int)ic, ecv,
+                               (long long)g.ntot_dev};
+                virt_comps.push_back(vc);
+                virt_alias[(const char *)ch.d.f[ecv][cmp]] = (const char *)ch.d.f[dcv][cmp];
+                if (ch.d.chi1inv[ecv][k]) virt_mul[(const char *)ch.d.f[ecv][cmp]] = (const char *)ch.d.chi1inv[ecv][k];
+              }
             }
             const int qidx = (int)h_c3d.size();
             h_c3d.push_back(Q);
@@ -1445,9 +1594,11 @@ template <class T> struct Ctx : CtxBase {
             const bool vec_ok = !getenv("MEEPCU_NO_VEC") && g.pitch % V == 0;
             // device indices of every source point of this chunk half (any component)
             std::vector<long long> spts;
+            std::vector<long long> vpts; // dipole points of a virtual E: special for every B/H tile that READS them
             for (int k = 0; k < 3; ++k) {
               for (int j = 0; j < Q.ncsrc[k]; ++j) spts.push_back(all_src[(Q.csrc[k] - d_src) + j].idx);
               for (int j = 0; j < Q.nisrc[k]; ++j) spts.push_back(all_src[(Q.isrc[k] - d_src) + j].idx);
+              for (int j = 0; j < Q.nvsrc[k]; ++j) vpts.push_back(all_src[(Q.vsrc[k] - d_src) + j].idx);
             }
             const long long sAq = (long long)Q.sA;
             const int span = vec_ok ? kThreads * V : kThreads; // elements of the plane per clean tile
@@ -1458,6 +1609,10 @@ template <class T> struct Ctx : CtxBase {
                 for (size_t j = 0; j < spts.size() && !special; ++j) {
                   const long long a = spts[j] / sAq, pos = spts[j] % sAq;
                   if (a >= a0 && a < a1 && pos >= e0 && pos < e0 + span) special = true;
+                }
+                for (size_t j = 0; j < vpts.size() && !special; ++j) { // footprint of the tile's loads: +1 in x, y, z
+                  const long long a = vpts[j] / sAq, pos = vpts[j] % sAq;
+                  if (a >= a0 && a <= a1 && pos >= e0 && pos <= e0 + span + g.pitch) special = true;
                 }
                 if (!special && vec_ok) { // clean: V z-points per thread
                   Tile t = {qidx, a0, a1, e0 / V};
@@ -1537,6 +1692,7 @@ template <class T> struct Ctx : CtxBase {
             if (!c.f) continue;
             int v = 3; // R g (one compulsory read of each curl operand is counted with its own
                        // component below: 2 operands ~ 1 per component on average), R+W f
+            if (virt && half == 0 && ch.d.chi1inv[dir_comp(MEEPCU_E_STUFF, k)][k]) v += 1; // virtual E: R chi1inv with the operand
             if (c.fu) v += 2;
             if (c.fcnd) v += 2;
             if (c.cnd) v += 2;
@@ -1737,20 +1893,24 @@ template <class T> struct Ctx : CtxBase {
         }
       }
     for (int half = 0; half < 2; ++half) aniso_half[half] = !polgen_tiles[half].empty() || !polgyro_tiles[half].empty();
+    virt_any = !virt_comps.empty();
     if (n_ranks > 1) {
-      int hflag[8] = {general_half[0], general_half[1], eager_db[0], eager_db[1], eager_p[0], eager_p[1], aniso_half[0], aniso_half[1]};
+      int hflag[9] = {general_half[0], general_half[1], eager_db[0], eager_db[1], eager_p[0], eager_p[1], aniso_half[0], aniso_half[1],
+                      virt_any};
       int *dflag = 0;
       CU(cudaMalloc((void **)&dflag, sizeof hflag));
       extra_dev.push_back((char *)dflag);
       CU(cudaMemcpyAsync(dflag, hflag, sizeof hflag, cudaMemcpyHostToDevice, st));
-      NC(nccl_api()->AllReduce(dflag, dflag, 8, 2 /* ncclInt32 */, 2 /* ncclMax */, comm, st));
+      NC(nccl_api()->AllReduce(dflag, dflag, 9, 2 /* ncclInt32 */, 2 /* ncclMax */, comm, st));
       CU(cudaMemcpyAsync(hflag, dflag, sizeof hflag, cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
       general_half[0] = hflag[0]; general_half[1] = hflag[1];
       eager_db[0] = hflag[2]; eager_db[1] = hflag[3];
       eager_p[0] = hflag[4]; eager_p[1] = hflag[5];
       aniso_half[0] = hflag[6]; aniso_half[1] = hflag[7];
+      virt_any = hflag[8];
     }
+    RC(virt_patch_u());
     // ---- 5b. multi-rank: boundary tiles first (see nb_* above) ----
     if (n_ranks > 1 && !getenv("MEEPCU_NO_OVERLAP"))
       for (int half = 0; half < 2; ++half) {
@@ -1950,26 +2110,29 @@ template <class T> struct Ctx : CtxBase {
         const PtrList &L = part[which];
         size_t k = 0;
         while (k < L.dst.size()) {
-          T *d0 = dev_elem(L.dst[k]);
-          const T *s0 = dev_elem(L.src[k]);
+          const T *m0 = 0, *mx = 0;
+          T *d0 = dev_elem_v(L.dst[k], ft, &mx);
+          const T *s0 = dev_elem_v(L.src[k], ft, &m0);
           if (!d0 || !s0)
             return fail(MEEPCU_EINVAL, "connection %zu of field type %d points outside the registered arrays", k, ft);
-          ConnRun<T> r = {d0, s0, 1, 0, 0, kind == MEEPCU_CONNECT_NEGATE};
+          ConnRun<T> r = {d0, s0, 1, 0, 0, kind == MEEPCU_CONNECT_NEGATE, m0};
           if (k + 1 < L.dst.size()) {
-            T *d1 = dev_elem(L.dst[k + 1]);
-            const T *s1 = dev_elem(L.src[k + 1]);
+            const T *m1 = 0;
+            T *d1 = dev_elem_v(L.dst[k + 1], ft, &mx);
+            const T *s1 = dev_elem_v(L.src[k + 1], ft, &m1);
             if (d1 && s1) {
               const long long ds = d1 - d0, ss = s1 - s0;
-              if (ds != 0 && std::llabs(ds) < (1LL << 30) && std::llabs(ss) < (1LL << 30)) {
+              if (ds != 0 && std::llabs(ds) < (1LL << 30) && std::llabs(ss) < (1LL << 30) && m1 == (m0 ? m0 + ss : 0)) {
                 r.dst_stride = (int)ds;
                 r.src_stride = (int)ss;
                 T *dp = d1;
                 const T *sp = s1;
                 r.n = 2;
                 while (k + r.n < L.dst.size() && r.n < (1 << 20)) {
-                  T *dn = dev_elem(L.dst[k + r.n]);
-                  const T *sn = dev_elem(L.src[k + r.n]);
-                  if (!dn || !sn || dn - dp != ds || sn - sp != ss) break;
+                  const T *mn = 0;
+                  T *dn = dev_elem_v(L.dst[k + r.n], ft, &mx);
+                  const T *sn = dev_elem_v(L.src[k + r.n], ft, &mn);
+                  if (!dn || !sn || dn - dp != ds || sn - sp != ss || mn != (m0 ? m0 + (sn - s0) : 0)) break;
                   dp = dn; sp = sn; r.n++;
                 }
               }
@@ -1979,6 +2142,7 @@ template <class T> struct Ctx : CtxBase {
             ConnRun<T> pc = r;
             pc.dst = r.dst + (long long)o * r.dst_stride;
             pc.src = r.src + (long long)o * r.src_stride;
+            if (r.mul) pc.mul = r.mul + (long long)o * r.src_stride;
             pc.n = std::min(kConnPiece, r.n - o);
             runs[which].push_back(pc);
           }
@@ -1998,19 +2162,24 @@ template <class T> struct Ctx : CtxBase {
         memset(&C, 0, sizeof C);
         if (L.dst.empty()) continue;
         std::vector<T *> hd(L.dst.size());
-        std::vector<const T *> hsrc(L.src.size());
+        std::vector<const T *> hsrc(L.src.size()), hmul(L.src.size());
+        bool any_mul = false;
         for (size_t n = 0; n < L.dst.size(); ++n) {
-          hd[n] = dev_elem(L.dst[n]);
-          hsrc[n] = dev_elem(L.src[n]);
+          const T *mx = 0;
+          hd[n] = dev_elem_v(L.dst[n], ft, &mx);
+          hsrc[n] = dev_elem_v(L.src[n], ft, &hmul[n]);
+          if (hmul[n]) any_mul = true;
           if (!hd[n] || !hsrc[n])
             return fail(MEEPCU_EINVAL, "connection %zu of field type %d points outside the registered arrays", n, ft);
         }
         T **dd = 0;
-        const T **dsrc = 0;
+        const T **dsrc = 0, **dmul = 0;
         RC(upload(hd, &dd));
         RC(upload(hsrc, &dsrc));
+        if (any_mul) RC(upload(hmul, &dmul));
         C.dst = dd;
         C.src = dsrc;
+        C.mul = dmul;
         C.n = (long long)L.dst.size();
         if (kind == MEEPCU_CONNECT_PHASE) {
           std::vector<T> ph((const T *)L.phases.data(), (const T *)(L.phases.data() + L.phases.size()));
@@ -2322,7 +2491,11 @@ template <class T> struct Ctx : CtxBase {
   // The curl / PML kernels of one half step over part of every tile list.
   //   part 0: all tiles;  1: boundary tiles only (the first nb_* of each list);  2: the rest
   // sm: stream of the interior tiles; sside: stream of the PML / special tiles (== sm: no fork)
+  const double *cur_prev = 0; // previous step's sample row (virtual-E dipoles), set by the callers of launch_half
+  int cur_vmode = 0;          // 1: B/H half of virtual chunks reads D (x chi1inv) instead of E
   int launch_compute(int half, const double *smp, int part, cudaStream_t sm, cudaStream_t sside) {
+    const int vmode = half == 0 ? cur_vmode : 0;
+    const double *smp_prev = cur_prev;
     // The interior tiles (k_curl3d) and the PML / general tiles (k_halfg) of one half step touch
     // disjoint chunks, so they run side by side on two streams; everything else is ordered after
     // both.  While profiling they are serialised so that each kernel's event time is its own.
@@ -2351,18 +2524,22 @@ template <class T> struct Ctx : CtxBase {
     if (n_mx) {
       RC(prof_begin(half ? KC_MIX_D : KC_MIX_B));
       if (half)
-        k_mix<T, true><<<n_mx, kThreads, 0, sm>>>(d_c3d, d_half, d_mix_tiles[half] + o_mx);
+        k_mix<T, true><<<n_mx, kThreads, 0, sm>>>(d_c3d, d_half, d_mix_tiles[half] + o_mx, 0);
+      else if (vmode && virt_vu)
+        k_mix<T, false, true><<<n_mx, kThreads, 0, sm>>>(d_c3d, d_half, d_mix_tiles[half] + o_mx, vmode);
       else
-        k_mix<T, false><<<n_mx, kThreads, 0, sm>>>(d_c3d, d_half, d_mix_tiles[half] + o_mx);
+        k_mix<T, false><<<n_mx, kThreads, 0, sm>>>(d_c3d, d_half, d_mix_tiles[half] + o_mx, vmode);
       RC(prof_end());
       launches++;
     }
     if (n_cv) {
       RC(prof_begin(half ? KC_CURL3D_D : KC_CURL3D_B));
       if (half)
-        k_curl3d_v<T, true><<<n_cv, kThreads, 0, sm>>>(d_c3d, d_c3dv_tiles[half] + o_cv);
+        k_curl3d_v<T, true><<<n_cv, kThreads, 0, sm>>>(d_c3d, d_c3dv_tiles[half] + o_cv, 0);
+      else if (vmode && virt_vu)
+        k_curl3d_v<T, false, true><<<n_cv, kThreads, 0, sm>>>(d_c3d, d_c3dv_tiles[half] + o_cv, vmode);
       else
-        k_curl3d_v<T, false><<<n_cv, kThreads, 0, sm>>>(d_c3d, d_c3dv_tiles[half] + o_cv);
+        k_curl3d_v<T, false><<<n_cv, kThreads, 0, sm>>>(d_c3d, d_c3dv_tiles[half] + o_cv, vmode);
       RC(prof_end());
       launches++;
     }
@@ -2404,9 +2581,9 @@ template <class T> struct Ctx : CtxBase {
       cudaStream_t ss = (n_cv || n_mx) ? sg : sm; // beside the vector kernel when there is one
       RC(prof_begin(KC_CURL3D_SPECIAL));
       if (half)
-        k_curl3d<T, true><<<n_c, kThreads, 0, ss>>>(d_c3d, d_c3d_tiles[half] + o_c, smp);
+        k_curl3d<T, true><<<n_c, kThreads, 0, ss>>>(d_c3d, d_c3d_tiles[half] + o_c, smp, smp_prev, 0);
       else
-        k_curl3d<T, false><<<n_c, kThreads, 0, ss>>>(d_c3d, d_c3d_tiles[half] + o_c, smp);
+        k_curl3d<T, false><<<n_c, kThreads, 0, ss>>>(d_c3d, d_c3d_tiles[half] + o_c, smp, smp_prev, vmode);
       RC(prof_end());
       launches++;
     }
@@ -2519,7 +2696,14 @@ template <class T> struct Ctx : CtxBase {
     // reference), DFT decimation flags (dft.cpp:259) -- through the ring, no synchronisation
     const size_t ns = (size_t)std::max(nsrc, 1) * 8;
     char *p_smp = 0, *p_ph = 0, *p_act = 0;
-    RC(ring_put(smp, nsrc > 0 ? sizeof(meepcu_src_sample) * (size_t)nsrc * nsteps : 0, &p_smp));
+    {
+      // row 0: the samples of the last step taken before this call (a virtual E holds ITS dipole_E), rows 1..: this call's
+      std::vector<double> tab((size_t)(nsteps + 1) * ns, 0.0);
+      if (last_row.size() == ns) memcpy(tab.data(), last_row.data(), ns * sizeof(double));
+      if (nsrc > 0) memcpy(tab.data() + ns, smp, sizeof(meepcu_src_sample) * (size_t)nsrc * nsteps);
+      RC(ring_put(tab.data(), tab.size() * sizeof(double), &p_smp));
+      last_row.assign(tab.end() - ns, tab.end());
+    }
     const size_t ndft = h_dft.size();
     if (ndft) {
       std::vector<T> ph((size_t)2 * phase_row * nsteps);
@@ -2553,9 +2737,12 @@ template <class T> struct Ctx : CtxBase {
     step_ev_next = (step_ev_next + 1) % step_ev.size();
     CU(cudaEventRecord(E.e0, st));
     for (int s = 0; s < nsteps; ++s) {
-      const double *sm = (const double *)p_smp + (size_t)s * ns;
+      const double *sm = (const double *)p_smp + (size_t)(s + 1) * ns;
+      cur_prev = (const double *)p_smp + (size_t)s * ns;
+      cur_vmode = (!virt_comps.empty() && e_virtual) ? 1 : 0;
       RC(launch_half(0, sm));
       RC(launch_half(1, sm));
+      e_virtual = true; // the D/E half of a virtual chunk has not stored E: from now on it is read through D
       if (n_dft_work) {
         RC(prof_begin(KC_DFT));
         k_dft<T><<<n_dft_work, kThreads, 0, st>>>(d_dft, d_dft_work, (const T *)p_ph + (size_t)2 * phase_row * s,
@@ -2636,7 +2823,16 @@ template <class T> struct Ctx : CtxBase {
     CU(cudaSetDevice(cfg.device));
     RC(collect_mag_arrays());
     char *p_smp = 0;
-    RC(ring_put(smp, nsrc > 0 ? sizeof(meepcu_src_sample) * (size_t)nsrc : 0, &p_smp));
+    {
+      const size_t ns = (size_t)std::max(nsrc, 1) * 8;
+      std::vector<double> tab(2 * ns, 0.0);
+      if (last_row.size() == ns) memcpy(tab.data(), last_row.data(), ns * sizeof(double));
+      if (nsrc > 0) memcpy(tab.data() + ns, smp, sizeof(meepcu_src_sample) * (size_t)nsrc);
+      RC(ring_put(tab.data(), tab.size() * sizeof(double), &p_smp));
+      cur_prev = (const double *)p_smp;
+      cur_vmode = (!virt_comps.empty() && e_virtual) ? 1 : 0;
+      p_smp += ns * sizeof(double);
+    }
     for (size_t k = 0; k < mag_arrays.size(); ++k) // backup_component (:97-118)
       CU(cudaMemcpyAsync(mag_backup + mag_arrays[k].off, mag_arrays[k].dev, mag_arrays[k].bytes, cudaMemcpyDeviceToDevice, st));
     in_mag_sync = true;
@@ -2678,18 +2874,42 @@ template <class T> struct Ctx : CtxBase {
   bool big(const ArrayRec &r) const { return r.n_host * sizeof(T) >= (size_t)(4 << 20) && !getenv("MEEPCU_NO_STAGING"); }
   // Halo copies the stepping kernels never consume (B/D/P, the normal-plane E/H points) are materialised
   // when somebody is about to read the device mirror.  `remote`: also the cross-rank ones (a collective:
-  // every rank of the communicator must make the same call).
-  int materialise_halos(unsigned groups, bool remote) {
+  // every rank of the communicator must make the same call).  With virtual-E chunks the order matters:
+  //   A  normal-plane E/H halos (for a virtual chunk they land in its D array, like every E halo)
+  //   V  (make_e_real) the E arrays of virtual chunks := chi1inv * (D - dipoles), halos included
+  //   B  B / D / P halos -- this overwrites the E halos parked in the D arrays of virtual chunks, so
+  //   R  (after the reads) the every-step E halo copies are run again
+  int halos_A(unsigned groups) {
     for (int half = 0; half < 2; ++half) {
-      const int ftd = half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF, fte = half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF,
-                ftp = half ? MEEPCU_PE_STUFF : MEEPCU_PH_STUFF;
-      if (!eager_db[half] && (groups & MEEPCU_SYNC_FIELDS)) RC(remote ? launch_conn(ftd) : launch_conn_local(ftd));
-      if (n_runs_def[fte] && (groups & MEEPCU_SYNC_FIELDS)) { // the normal-plane E/H halos
+      const int fte = half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF;
+      if (n_runs_def[fte] && (groups & MEEPCU_SYNC_FIELDS)) {
         k_conn_runs<T><<<(n_runs_def[fte] + 7) / 8, kThreads, 0, st>>>(d_runs_def[fte], n_runs_def[fte]);
         launches++;
       }
+    }
+    return MEEPCU_OK;
+  }
+  int halos_B(unsigned groups, bool remote) {
+    for (int half = 0; half < 2; ++half) {
+      const int ftd = half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF, ftp = half ? MEEPCU_PE_STUFF : MEEPCU_PH_STUFF;
+      if (!eager_db[half] && (groups & MEEPCU_SYNC_FIELDS)) RC(remote ? launch_conn(ftd) : launch_conn_local(ftd));
       if (!eager_p[half] && (groups & MEEPCU_SYNC_POL)) RC(remote ? launch_conn(ftp) : launch_conn_local(ftp));
     }
+    return MEEPCU_OK;
+  }
+  bool virt_now(unsigned groups) const { return virt_any && e_virtual && (groups & MEEPCU_SYNC_FIELDS); }
+  int halos_R(unsigned groups, bool remote) {
+    if (!virt_now(groups)) return MEEPCU_OK;
+    return remote ? launch_conn(MEEPCU_E_STUFF) : launch_conn_local(MEEPCU_E_STUFF);
+  }
+  // before a gather of values that may be lazily copied not-owned points, read through the virtual-E aliases:
+  // B and R first, A last (B would overwrite the normal-plane E halos A parks in the D arrays of virtual chunks)
+  int refresh_for_read() {
+    const unsigned groups = MEEPCU_SYNC_FIELDS | MEEPCU_SYNC_POL;
+    RC(halos_B(groups, false));
+    RC(halos_R(groups, false));
+    RC(halos_A(groups));
+    if (n_ranks == 1) halo_stale = false;
     return MEEPCU_OK;
   }
   int sync_groups(bool to_host, unsigned groups) {
@@ -2697,9 +2917,12 @@ template <class T> struct Ctx : CtxBase {
     CU(cudaSetDevice(cfg.device));
     const bool local_only = (groups & MEEPCU_SYNC_LOCAL) != 0;
     groups &= ~(unsigned)MEEPCU_SYNC_LOCAL;
+    const bool remote = n_ranks > 1 && !local_only;
     if (to_host) {
       // so that the not-owned points of the host mirror hold what step_boundaries would have left there
-      RC(materialise_halos(groups, n_ranks > 1 && !local_only));
+      RC(halos_A(groups));
+      if (virt_now(groups)) RC(virt_materialise());
+      RC(halos_B(groups, remote));
       if (n_ranks == 1 || !local_only) halo_stale = false;
     }
     for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it) {
@@ -2707,33 +2930,92 @@ template <class T> struct Ctx : CtxBase {
       if (!(r.group & groups) || (to_host && !r.mut)) continue;
       RC(big(r) && !r.pinned ? staged_copy(r, to_host) : copy_array(r, to_host));
     }
+    if (to_host) {
+      RC(halos_R(groups, remote));
+      if (virt_now(groups) && n_runs_def[MEEPCU_E_STUFF]) halo_stale = true; // (the normal-plane E halos parked in D arrays: next A)
+    }
+    else {
+      if (groups & MEEPCU_SYNC_FIELDS) e_virtual = false; // every E array on the device is the host's again
+      if (groups & MEEPCU_SYNC_MATERIALS) RC(virt_patch_u());
+    }
     CU(cudaStreamSynchronize(st));
     RC(collect_timing());
     return MEEPCU_OK;
   }
-  // n elements gathered on the device (k_pack) and returned as doubles in one transfer
+  // How one requested element is read from the device.  0: as it is.  1: it is a not-owned point whose halo copy is
+  // lazy (B / D / P): refresh_for_read first.  2: it needs the real E array of a virtual chunk (a dipole point) or
+  // a not-owned D point of such a chunk (parked E halo): refresh_for_read(make_e_real).  Virtual E elements are
+  // otherwise read as D (x chi1inv) -- *src / *mul.
+  int classify_read(const void *p, const T **src, const T **mul) const {
+    *src = *mul = 0;
+    size_t e = 0;
+    const ArrayRec *r = find(p, sizeof(T), &e);
+    if (!r) return -1;
+    if (r->kind != A_GRID) { *src = (const T *)r->dev + e; return 0; }
+    const Geom &g = chunks[r->chunk].g;
+    const long long di = g.dev_index((long long)e);
+    *src = (const T *)r->dev + di;
+    bool owned = true;
+    if (r->comp >= 0) {
+      long long rem = (long long)e;
+      for (int d = 0; d < 3; ++d)
+        if (g.has[d]) {
+          const long long q = rem / g.hs[d];
+          rem -= q * g.hs[d];
+          if (q < 1 - g.yee_shift(r->comp, d) || q > g.num[d] - g.yee_shift(r->comp, d)) owned = false;
+        }
+    }
+    const bool virt_on = !virt_comps.empty() && e_virtual;
+    if (virt_on && r->comp >= 0 && virt_chunks.count(r->chunk)) {
+      if (is_electric(r->comp)) {
+        for (size_t k = 0; k < virt_comps.size(); ++k)
+          if ((const char *)virt_comps[k].e == r->dev)
+            for (int j = 0; j < virt_comps[k].nsrc; ++j)
+              if (h_src_idx[(virt_comps[k].src - d_src) + j] == di) return 2; // E = chi1inv * (D - dipole): the real array
+        const T *m = 0;
+        *src = dev_elem_v(p, MEEPCU_E_STUFF, &m);
+        *mul = m;
+        // (halos of E are parked in D and chi1inv is 1 there: the product is right for them too; the normal-plane
+        //  ones are copied lazily)
+        return (!owned && n_runs_def[MEEPCU_E_STUFF]) ? 1 : 0;
+      }
+      if (is_D(r->comp) && !owned) return 2;
+    }
+    if (!owned && (is_D(r->comp) || is_B(r->comp)) ) return 1;
+    if (r->group == MEEPCU_SYNC_POL) return 1; // polarisation halos are lazy too (which points are owned is not recorded)
+    if (!owned && r->comp >= 0 && n_runs_def[is_electric(r->comp) ? MEEPCU_E_STUFF : MEEPCU_H_STUFF]) return 1; // normal-plane E/H halos
+    return 0;
+  }
+  // n elements gathered on the device and returned as doubles in one transfer
   int read_values(size_t n, const void *const *ptrs, double *out) {
     if (!finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
     if (!n) return MEEPCU_OK;
     if (!ptrs || !out) return fail(MEEPCU_EINVAL, "null argument");
     CU(cudaSetDevice(cfg.device));
-    if (halo_stale) { // not-owned points may be asked for: bring the deferred LOCAL halo copies up to date
-      RC(materialise_halos(MEEPCU_SYNC_FIELDS | MEEPCU_SYNC_POL, false));
-      if (n_ranks == 1) halo_stale = false;
-    }
-    std::vector<const T *> h(n);
+    std::vector<const T *> h(2 * n);
+    int worst = 0;
     for (size_t i = 0; i < n; ++i) {
-      h[i] = dev_elem(ptrs[i]);
-      if (!h[i]) return fail(MEEPCU_EINVAL, "pointer %zu is not inside a registered array", i);
+      const int c = classify_read(ptrs[i], &h[i], &h[n + i]);
+      if (c < 0) return fail(MEEPCU_EINVAL, "pointer %zu is not inside a registered array", i);
+      worst = std::max(worst, c);
     }
+    const unsigned fp = MEEPCU_SYNC_FIELDS | MEEPCU_SYNC_POL;
+    if (worst == 2) { // rare: every element from the REAL arrays, between B and R (the order of meepcu_sync_to_host)
+      RC(halos_A(fp));
+      RC(virt_materialise());
+      RC(halos_B(fp, false));
+      for (size_t i = 0; i < n; ++i) { h[i] = dev_elem(ptrs[i]); h[n + i] = 0; }
+    }
+    else if (worst == 1 && halo_stale)
+      RC(refresh_for_read());
     const T **d_ptr = 0;
     T *d_val = 0;
-    CU(cudaMalloc((void **)&d_ptr, n * sizeof(T *)));
+    CU(cudaMalloc((void **)&d_ptr, 2 * n * sizeof(T *)));
     if (cudaMalloc((void **)&d_val, n * sizeof(T)) != cudaSuccess) { cudaFree(d_ptr); return fail(MEEPCU_ENOMEM, "cudaMalloc"); }
     std::vector<T> v(n);
-    cudaError_t e = cudaMemcpyAsync(d_ptr, h.data(), n * sizeof(T *), cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaMemcpyAsync(d_ptr, h.data(), 2 * n * sizeof(T *), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
-      k_pack<T><<<(int)std::min<size_t>((n + kThreads - 1) / kThreads, 148 * 8), kThreads, 0, st>>>(d_ptr, d_val, (long long)n);
+      k_gather<T><<<(int)std::min<size_t>((n + kThreads - 1) / kThreads, 148 * 8), kThreads, 0, st>>>(d_ptr, d_ptr + n, d_val, (long long)n);
       launches++;
       e = cudaMemcpyAsync(v.data(), d_val, n * sizeof(T), cudaMemcpyDeviceToHost, st);
     }
@@ -2741,6 +3023,10 @@ template <class T> struct Ctx : CtxBase {
     cudaFree(d_ptr);
     cudaFree(d_val);
     if (e != cudaSuccess) return fail(MEEPCU_ECUDA, "%s", cudaGetErrorString(e));
+    if (worst == 2) {
+      RC(halos_R(fp, false));
+      halo_stale = true; // the normal-plane E halos parked in D arrays are gone until the next A
+    }
     for (size_t i = 0; i < n; ++i) out[i] = (double)v[i];
     return MEEPCU_OK;
   }
@@ -2761,20 +3047,7 @@ template <class T> struct Ctx : CtxBase {
     nr_unconverged = flags[0];
     return MEEPCU_OK;
   }
-  int read_value(const void *p, double *out) {
-    if (!finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
-    T *d = dev_elem(p);
-    if (!d) return fail(MEEPCU_EINVAL, "pointer is not inside a registered array");
-    if (halo_stale) {
-      RC(materialise_halos(MEEPCU_SYNC_FIELDS | MEEPCU_SYNC_POL, false));
-      if (n_ranks == 1) halo_stale = false;
-    }
-    T v;
-    CU(cudaMemcpyAsync(&v, d, sizeof(T), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    *out = (double)v;
-    return MEEPCU_OK;
-  }
+  int read_value(const void *p, double *out) { return read_values(1, &p, out); }
   int get_stats(meepcu_stats *out) {
     memset(out, 0, sizeof *out);
     if (finalized) {
@@ -2784,6 +3057,7 @@ template <class T> struct Ctx : CtxBase {
       CU(cudaMemcpy(&fl, d_flags, sizeof fl, cudaMemcpyDeviceToHost));
       nr_unconverged = fl;
     }
+    out->reserved[5] = (int64_t)virt_comps.size(); // E arrays of this rank that are not stored while stepping (virtual E)
     out->reserved[3] = nonfinite_seen();
     out->reserved[4] = (int64_t)(total_step_ms * 1e3); // device microseconds of all meepcu_step calls so far
     out->kernel_launches = launches;

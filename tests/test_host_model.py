@@ -259,3 +259,113 @@ def test_cuda_slices_dft_and_partial_sync(cuda_backend, oracle_backend):
         f.close()
     assert np.array_equal(outs[0][0], outs[1][0])
     assert np.array_equal(outs[0][1], outs[1][1])
+
+
+# ---- virtual E (kernels.cuh, Curl3DParams::virt): chunks without PML / polarisations do not store E while
+# stepping; the B/H half reads chi1inv * (D - dipoles) instead.  Everything a host can observe must be unchanged. ----
+def virt_problem(backend, kind, rt=np.float64, split=None):
+    if kind == "vacuum":      # E = D; dipole (integrated source) inside the interior chunk
+        gv = H.vol3d(4.8, 4.0, 4.4, 10)
+        s = H.structure(gv, None, pml=0.8, realnum=rt, split=split)
+        f = H.fields(s, backend)
+        f.use_real_fields()
+    elif kind == "dielectric":  # E = chi1inv * D, block of eps = 6 crossing chunk boundaries
+        gv = H.vol3d(4.8, 4.0, 4.4, 10)
+        s = H.structure(gv, lambda x, y, z: 1.0 + 5.0 * ((x > 1.0) & (x < 3.3) & (y > 0.5) & (z > 1.7)), pml=0.8, realnum=rt, split=split)
+        f = H.fields(s, backend)
+        f.use_real_fields()
+    else:                       # periodic slab, PML in z only, complex fields with a Bloch phase
+        gv = H.vol3d(3.2, 2.4, 4.8, 10)
+        s = H.structure(gv, lambda x, y, z: 1.0 + 11.0 * (np.abs(z - 2.4) < 0.3), pml=0.8, pml_dirs=[2], realnum=rt, split=split)
+        f = H.fields(s, backend)
+        f.use_bloch(0, 0.21)
+        f.use_bloch(1, 0.0)
+    c = gv.center()
+    f.add_point_source(Ez, 0.3, 0.2, 0.0, 4.0, (c[0] - 0.3, c[1] + 0.1, c[2] + 0.05), 1.0)
+    f.add_point_source(Ex, 0.35, 0.2, 0.0, 4.0, (c[0] + 0.25, c[1], c[2] - 0.2), 0.7)
+    f.add_point_source(Hy, 0.25, 0.2, 0.0, 4.0, (c[0] + 0.05, c[1] - 0.2, c[2] + 0.05), 0.5)
+    return gv, f
+
+
+def run_virt_sequence(gv, f):
+    """steps in several calls with every kind of reader in between; returns what a host observed"""
+    obs = []
+    c = gv.center()
+    f.step(7)
+    obs.append(f.get_field(Ez, (c[0] - 0.3, c[1] + 0.1, c[2] + 0.05)))          # a dipole point itself
+    f.step(1)
+    obs.append(f.get_array_slice(Ez, (1, 1, 1), (gv.num[0] - 1, 12, gv.num[2] - 1)).copy())   # owned + chunk-boundary points
+    f.step(9)
+    f.sync_to_host()
+    obs.append({k: a.copy() for k, a in f.owned_arrays()})
+    f.step(5)
+    f.synchronize_magnetic_fields()
+    obs.append(f.get_array_slice(Hy, (2, 2, 2), (20, 20, 20)).copy())
+    obs.append(f.get_array_slice(Ex, (2, 2, 2), (20, 20, 20)).copy())
+    f.restore_magnetic_fields()
+    f.step(6)
+    obs.append(f.get_array_slice(Dz, (1, 1, 1), (gv.num[0] - 1, 10, 10)).copy())
+    f.sync_to_host()
+    obs.append({k: a.copy() for k, a in f.owned_arrays()})
+    # the host changes E alone (no longer chi1inv * D), uploads, and goes on: the uploaded E is what the next B/H half must use
+    for fc in f.chunks:
+        for (cc, cmp), arr in fc.f.items():
+            if cc == Ez: arr *= 0.5
+    f.sync_from_host()
+    f.step(11)
+    f.sync_to_host()
+    obs.append({k: a.copy() for k, a in f.owned_arrays()})
+    return obs
+
+
+def same_observations(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        if isinstance(x, dict):
+            assert x.keys() == y.keys()
+            bad = [k for k in x if not np.array_equal(x[k].view(np.uint8), y[k].view(np.uint8))]
+            assert not bad, bad[:6]
+            assert sum(1 for v in x.values() if np.any(v)) > len(x) // 2
+        else:
+            assert np.array_equal(np.asarray(x), np.asarray(y)), (np.asarray(x).shape,)
+
+
+from meep_nl_b200._cabi import Dz  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,rt,split", [("vacuum", np.float64, None), ("vacuum", np.float32, {0: [20]}),
+                                           ("dielectric", np.float64, {1: [17]}), ("dielectric", np.float32, None),
+                                           ("bloch_slab", np.float64, {0: [14]}), ("bloch_slab", np.float32, None)])
+def test_virtual_e_is_invisible(cuda_backend, kind, rt, split, monkeypatch):
+    """the same run with E stored every step (MEEPCU_NO_VIRTUAL_E=1) and with virtual E: every probe, slice, synchronized
+    field and every array of every sync must be bit-identical"""
+    monkeypatch.setenv("MEEPCU_NO_VIRTUAL_E", "1")
+    gv, f = virt_problem(cuda_backend, kind, rt, split)
+    f.init()
+    stored = run_virt_sequence(gv, f)
+    f.close()
+    monkeypatch.delenv("MEEPCU_NO_VIRTUAL_E")
+    gv, f = virt_problem(cuda_backend, kind, rt, split)
+    f.init()
+    virt = run_virt_sequence(gv, f)
+    st = f.stats()
+    f.close()
+    same_observations(stored, virt)
+    assert st.reserved[5] > 0, "no chunk ran with a virtual E: the test tested nothing"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["vacuum", "dielectric", "bloch_slab"])
+def test_virtual_e_equals_oracle(cuda_backend, oracle_backend, kind):
+    res = []
+    for b in (cuda_backend, oracle_backend):
+        gv, f = virt_problem(b, kind)
+        f.step(13)
+        f.sync_to_host()
+        f.step(30)
+        f.sync_to_host()
+        res.append(np.concatenate([np.asarray(a).view(np.float64).ravel() for _, a in f.owned_arrays()]))
+        f.close()
+    rel = np.linalg.norm(res[0] - res[1]) / np.linalg.norm(res[1])
+    assert np.linalg.norm(res[1]) > 0 and rel <= 1e-12
