@@ -283,9 +283,10 @@ typedef struct {
   int64_t cells;              /* sum over chunks of owned cells (nx*ny*nz) */
   int64_t algorithmic_bytes_per_step; /* compulsory HBM bytes per step (DESIGN.md accounting) */
   double last_step_ms;        /* device time of the last meepcu_step call (CUDA events; the query waits for it) */
-  int64_t reserved[8];        /* [0] cells the NR seed ladder left unchanged, [1],[2] host arrays / bytes page-locked in
-                                 place, [3] lazy NaN flag, [4] device microseconds of all meepcu_step calls, [5] E arrays not stored
-                                 while stepping (virtual E) */
+  int64_t reserved[8];        /* [0] cells the NR seed ladder left unchanged; [1], [2], [6] Newton-Raphson solves, their
+                                 iterations and the longest solve, counted while meepcu_set_profiling is on; [3] lazy NaN
+                                 flag; [4] device microseconds of all meepcu_step calls; [5] E arrays not stored while
+                                 stepping (virtual E); [7] bytes of host arrays page-locked in place */
 } meepcu_stats;
 int meepcu_get_stats(meepcu_ctx *ctx, meepcu_stats *out);
 

@@ -1438,7 +1438,8 @@ template <class T> struct EhParams {
   unsigned zmask_eh;
   int npol;
   PolParams<T> pol[kMaxPol];
-  int *nr_fail; // device counter of cells whose NR seed ladder was exhausted
+  int *nr_fail; // device flags: [0] cells whose NR seed ladder was exhausted, [2] count solves?, [3] longest solve (iterations),
+                // [4..7] as two 64-bit counters: solves, iterations
 };
 
 template <class T>
@@ -1473,10 +1474,11 @@ template <> __device__ __forceinline__ bool bits_equal<float>(float a, float b) 
 
 template <class T>
 __device__ bool nr_iterate(T x, T y, T z, const NRP<T> &p1, const NRP<T> &p2, const NRP<T> &p3,
-                           T out[3], double tol1, double tol2, double tol3, int max_iter) {
+                           T out[3], double tol1, double tol2, double tol3, int max_iter, int &iters) {
   T px1 = x, py1 = y, pz1 = z, px2 = x, py2 = y, pz2 = z;
   bool dead = false;
   for (int iter = 0; iter < max_iter && !dead; iter++) { // newton_raphson.cpp:93-142
+    ++iters;
     double F[3], J[3][3], b[3], d[3];
     nr_equations<T>(x, y, z, p1, p2, p3, F);
     J[0][0] = -p1.B - p1.G * z - p1.H * y;
@@ -1536,7 +1538,7 @@ __device__ bool nr_iterate(T x, T y, T z, const NRP<T> &p1, const NRP<T> &p2, co
 // runNR :209-359 with the deterministic part of the seed ladder
 template <class T>
 __device__ bool run_nr(T seed1, T seed2, T seed3, T out[3], const NRP<T> &p1, const NRP<T> &p2,
-                       const NRP<T> &p3) {
+                       const NRP<T> &p3, int &iters) {
   const double TOL = 1e-8, seedMax = 1e33;
   int max_iter = 250;
   const double tol1 = fmax(fabs(TOL * out[0]) * 0.0001, TOL);
@@ -1548,7 +1550,7 @@ __device__ bool run_nr(T seed1, T seed2, T seed3, T out[3], const NRP<T> &p1, co
   // spurious large-field roots of the quadratic system).  We stop here and leave the field value
   // unchanged, which is also what the reference does when all of its attempts fail.
   for (int i = 0; i < 15; ++i) {
-    if (nr_iterate<T>((T)s1, (T)s2, (T)s3, p1, p2, p3, out, tol1, tol2, tol3, max_iter)) return true;
+    if (nr_iterate<T>((T)s1, (T)s2, (T)s3, p1, p2, p3, out, tol1, tol2, tol3, max_iter, iters)) return true;
     switch (i) {
       case 0: s1 = seed1 * seedMax; max_iter = 600; break;
       case 1: s1 = seed1; s2 = seed2 * seedMax; break;
@@ -1628,10 +1630,17 @@ __device__ __forceinline__ void eh_point(const EhParams<T> &q, long long i, int 
         out[0] = own == 0 ? fprev_ : (T)0; // *fw of this component = previous field; the dummies are 0
         out[1] = own == 1 ? fprev_ : (T)0;
         out[2] = own == 2 ? fprev_ : (T)0;
-        const bool ok = run_nr<T>(sd1, sd2, sd3, out, p1, p2, p3);
+        int iters = 0;
+        const bool ok = run_nr<T>(sd1, sd2, sd3, out, p1, p2, p3, iters);
         if (!ok) {
           atomicAdd(q.nr_fail, 1);
           out[0] = out[1] = out[2] = fprev_;
+        }
+        if (q.nr_fail[2]) { // counting is on (meepcu_set_profiling): solves, iterations, longest solve
+          unsigned long long *cnt = reinterpret_cast<unsigned long long *>(q.nr_fail + 4);
+          atomicAdd(cnt, 1ull);
+          atomicAdd(cnt + 1, (unsigned long long)iters);
+          atomicMax(q.nr_fail + 3, iters);
         }
         val = own == 0 ? out[0] : (own == 1 ? out[1] : out[2]);
       }

@@ -1279,9 +1279,9 @@ template <class T> struct Ctx : CtxBase {
     CU(cudaMemsetAsync(arena, 0, arena_bytes, st));
     for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it)
       it->second.dev = arena + (size_t)it->second.dev;
-    CU(cudaMalloc((void **)&d_flags, 4 * sizeof(int)));
+    CU(cudaMalloc((void **)&d_flags, 8 * sizeof(int)));
     extra_dev.push_back((char *)d_flags);
-    CU(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), st));
+    CU(cudaMemsetAsync(d_flags, 0, 8 * sizeof(int), st));
     if (cfg.pin_host && !getenv("MEEPCU_NO_PIN"))
       for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it) {
         ArrayRec &r = it->second;
@@ -2440,6 +2440,13 @@ template <class T> struct Ctx : CtxBase {
   }
   int set_profiling(int on) {
     profiling = on != 0;
+    if (finalized) { // Newton-Raphson solves / iterations are counted while profiling is on (kernels.cuh, eh_point)
+      CU(cudaSetDevice(cfg.device));
+      CU(cudaStreamSynchronize(st));
+      const int z[6] = {on != 0, 0, 0, 0, 0, 0};
+      if (on) CU(cudaMemcpy(d_flags + 2, z, sizeof z, cudaMemcpyHostToDevice));
+      else CU(cudaMemcpy(d_flags + 2, z, sizeof(int), cudaMemcpyHostToDevice));
+    }
     memset(kc_ms, 0, sizeof kc_ms);
     memset(kc_launches, 0, sizeof kc_launches);
     return MEEPCU_OK;
@@ -3053,9 +3060,14 @@ template <class T> struct Ctx : CtxBase {
     if (finalized) {
       CU(cudaSetDevice(cfg.device));
       RC(collect_timing()); // waits for the queued steps: last_step_ms is the device time of the last call
-      int fl = 0;
-      CU(cudaMemcpy(&fl, d_flags, sizeof fl, cudaMemcpyDeviceToHost));
-      nr_unconverged = fl;
+      int fl[8];
+      CU(cudaMemcpy(fl, d_flags, sizeof fl, cudaMemcpyDeviceToHost));
+      nr_unconverged = fl[0];
+      unsigned long long cnt[2];
+      memcpy(cnt, fl + 4, sizeof cnt);
+      out->reserved[1] = (int64_t)cnt[0]; // Newton-Raphson solves counted while profiling was on
+      out->reserved[2] = (int64_t)cnt[1]; // ... their iterations
+      out->reserved[6] = fl[3];           // ... the longest of them
     }
     out->reserved[5] = (int64_t)virt_comps.size(); // E arrays of this rank that are not stored while stepping (virtual E)
     out->reserved[3] = nonfinite_seen();
@@ -3068,10 +3080,8 @@ template <class T> struct Ctx : CtxBase {
     out->last_step_ms = last_ms;
     out->reserved[0] = nr_unconverged;
     for (std::map<const char *, ArrayRec>::const_iterator it = arrays.begin(); it != arrays.end(); ++it)
-      if (it->second.pinned) {
-        out->reserved[1]++; // host arrays page-locked in place (meepcu_config::pin_host)
-        out->reserved[2] += (int64_t)(it->second.n_host * sizeof(T) * (it->second.kind == A_DFT ? 2 : 1));
-      }
+      if (it->second.pinned) // bytes of host arrays page-locked in place (meepcu_config::pin_host)
+        out->reserved[7] += (int64_t)(it->second.n_host * sizeof(T) * (it->second.kind == A_DFT ? 2 : 1));
     return MEEPCU_OK;
   }
   int get_timers(double out[22]) {
