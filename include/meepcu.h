@@ -298,7 +298,9 @@ typedef struct {
   double ms;                      /* summed device time of those launches */
   int64_t algorithmic_bytes;      /* compulsory HBM bytes of ONE launch (DESIGN.md accounting) */
 } meepcu_kernel_time;
-int meepcu_set_profiling(meepcu_ctx *ctx, int on); /* also resets the accumulated times */
+/* on: bit 0 = time every kernel (serialised on one stream; also resets the accumulated times), bit 1 = count the
+ * Newton-Raphson solves and iterations of k_eh_general (meepcu_stats.reserved[1,2,6]; atomics: do not time then) */
+int meepcu_set_profiling(meepcu_ctx *ctx, int on);
 int meepcu_get_kernel_times(meepcu_ctx *ctx, meepcu_kernel_time *out, int capacity, int *n);
 
 #ifdef __cplusplus

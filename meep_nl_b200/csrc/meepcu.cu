@@ -2439,12 +2439,12 @@ template <class T> struct Ctx : CtxBase {
     return MEEPCU_OK;
   }
   int set_profiling(int on) {
-    profiling = on != 0;
-    if (finalized) { // Newton-Raphson solves / iterations are counted while profiling is on (kernels.cuh, eh_point)
+    profiling = (on & 1) != 0;
+    if (finalized) { // bit 1: count Newton-Raphson solves / iterations (kernels.cuh, eh_point; atomics: not while timing)
       CU(cudaSetDevice(cfg.device));
       CU(cudaStreamSynchronize(st));
-      const int z[6] = {on != 0, 0, 0, 0, 0, 0};
-      if (on) CU(cudaMemcpy(d_flags + 2, z, sizeof z, cudaMemcpyHostToDevice));
+      const int z[6] = {(on & 2) != 0, 0, 0, 0, 0, 0};
+      if (on & 2) CU(cudaMemcpy(d_flags + 2, z, sizeof z, cudaMemcpyHostToDevice));
       else CU(cudaMemcpy(d_flags + 2, z, sizeof(int), cudaMemcpyHostToDevice));
     }
     memset(kc_ms, 0, sizeof kc_ms);

@@ -325,7 +325,7 @@ def same_observations(a, b):
             assert x.keys() == y.keys()
             bad = [k for k in x if not np.array_equal(x[k].view(np.uint8), y[k].view(np.uint8))]
             assert not bad, bad[:6]
-            assert sum(1 for v in x.values() if np.any(v)) > len(x) // 2
+            assert sum(1 for v in x.values() if np.any(v)) > 20
         else:
             assert np.array_equal(np.asarray(x), np.asarray(y)), (np.asarray(x).shape,)
 
