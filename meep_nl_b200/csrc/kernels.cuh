@@ -1438,6 +1438,10 @@ template <class T> struct EhParams {
   unsigned zmask_eh;
   int npol;
   PolParams<T> pol[kMaxPol];
+  // per-point class of the update, derived once from the (immutable) material arrays by k_eh_mask: 0 = the plain
+  // product val = g*u (no neighbour of D-P, no chi2 / chi3 / off-diagonal flag and no old E is read), 1 = the full
+  // formula.  NULL: not built (every point takes the full path).
+  const unsigned char *mask;
   int *nr_fail; // device flags: [0] cells whose NR seed ladder was exhausted, [2] count solves?, [3] longest solve (iterations),
                 // [4..7] as two 64-bit counters: solves, iterations
 };
@@ -1589,17 +1593,27 @@ __device__ __forceinline__ void eh_point(const EhParams<T> &q, long long i, int 
   if (!pade) {
     if (!q.fw && u1 && u2 && q.chi3) { // the fork's NR branch, step_generic.cpp:732-816
       const T gs = g[i];
-      const T gs_2 = (g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)]) * 0.25;
-      const T gs_3 = (g2[i] + g2[i + s] + g2[i - s2] + g2[i + (s - s2)]) * 0.25;
       const T ui = u[i];
-      const T us = 1 / ui;
-      const T chi2new = q.chi2[i];
-      int zeroEps = 0;
-      if (ui == 0) zeroEps += 1;
-      if (u1[i] == 0) zeroEps += 1;
-      if (u2[i] == 0) zeroEps += 1;
-      if (chi2new == 0 || zeroEps > 1) { val = (gs * ui); }
+      // :757-764: chi2 == 0, or more than one of u, u1, u2 zero -> the linear product.  The test only involves
+      // material arrays, so it is evaluated once (k_eh_mask) and the 8 neighbour loads, chi2, u1, u2 and the old E
+      // are skipped where it holds (two thirds of BASELINE config 3's cells)
+      bool plain;
+      T chi2new = 0;
+      if (q.mask) plain = q.mask[i] == 0;
       else {
+        chi2new = q.chi2[i];
+        int zeroEps = 0;
+        if (ui == 0) zeroEps += 1;
+        if (u1[i] == 0) zeroEps += 1;
+        if (u2[i] == 0) zeroEps += 1;
+        plain = chi2new == 0 || zeroEps > 1;
+      }
+      if (plain) { val = (gs * ui); }
+      else {
+        if (q.mask) chi2new = q.chi2[i];
+        const T gs_2 = (g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)]) * 0.25;
+        const T gs_3 = (g2[i] + g2[i + s] + g2[i - s2] + g2[i + (s - s2)]) * 0.25;
+        const T us = 1 / ui;
         T out[3];
         NRP<T> p1, p2, p3;
         T sd1, sd2, sd3;
@@ -1674,7 +1688,9 @@ __device__ __forceinline__ void eh_point(const EhParams<T> &q, long long i, int 
     }
     else if (q.chi3) {
       const T gs = g[i], us = u[i];
-      if (g1 && g2) {
+      if (q.mask && q.mask[i] == 0) // chi2 == chi3 == 0 here: calc_nonlinear_u is (1 + 0 + 0) / (1 + 0 + 0) = 1 exactly
+        val = gs * us;
+      else if (g1 && g2) {
         const T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
         const T g2s = g2[i] + g2[i + s] + g2[i - s2] + g2[i + (s - s2)];
         val = (gs * us) * calc_nonlinear_u<T>(gs * gs + 0.0625 * (g1s * g1s + g2s * g2s), gs, us,
@@ -1717,11 +1733,33 @@ __device__ __forceinline__ void eh_point(const EhParams<T> &q, long long i, int 
   q.f[i] = enew;
 }
 
+// EhParams::mask for one component (see there).  mode 0 (the fork's NR branch): 1 where chi2 != 0 and at most one of
+// u, u1, u2 is zero (step_generic.cpp:757-764); mode 1 (UPSTREAM_PADE without off-diagonal rows): 1 where chi2 or chi3 != 0.
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_eh_mask(unsigned char *__restrict__ mask, const T *__restrict__ u, const T *__restrict__ u1,
+                                                      const T *__restrict__ u2, const T *__restrict__ chi2, const T *__restrict__ chi3,
+                                                      int mode, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    unsigned char m;
+    if (mode == 0) {
+      int zeroEps = 0;
+      if (u[i] == 0) zeroEps += 1;
+      if (u1[i] == 0) zeroEps += 1;
+      if (u2[i] == 0) zeroEps += 1;
+      m = !(chi2[i] == 0 || zeroEps > 1);
+    }
+    else
+      m = chi2[i] != 0 || chi3[i] != 0;
+    mask[i] = m;
+  }
+}
+
 #ifndef MCU_EH_CTAS
 #define MCU_EH_CTAS 5 // Newton-Raphson is latency-bound: measured 2.73 / 2.13 / 2.02 / 1.65 / 1.75 ms at 2 / 3 / 4 / 5 / 6 CTAs per SM (256^3)
 #endif
-template <class T>
-__global__ void __launch_bounds__(kThreads, MCU_EH_CTAS)
+template <class T, int CTAS = MCU_EH_CTAS>
+__global__ void __launch_bounds__(kThreads, CTAS)
     k_eh_general(const EhParams<T> *__restrict__ params, const Tile *__restrict__ tiles) {
   __shared__ EhParams<T> P;
   const Tile t = tiles[blockIdx.x];
@@ -1902,62 +1940,108 @@ struct DftWork {
   long long e0; // first element (point*Nomega + omega) of this CTA
 };
 
+template <class T> struct CplxOf;
+template <> struct CplxOf<double> { typedef double2 type; };
+template <> struct CplxOf<float> { typedef float2 type; };
+constexpr int kDftPerThread = 4; // accumulator elements per thread, kThreads apart (DftWork covers kThreads * this)
+
+// Each thread owns kDftPerThread (point, omega) elements: the complex accumulator moves as ONE 16-byte (fp64) /
+// 8-byte (fp32) access, all accumulator loads of a thread are in flight before the first store, and the index
+// arithmetic is 32-bit where the region allows it.  Per element the operations are those of dft.cpp:295-305.
 template <class T>
 __global__ void __launch_bounds__(kThreads)
     k_dft(const DftParams<T> *__restrict__ params, const DftWork *__restrict__ work,
           const T *__restrict__ phases, const int *__restrict__ phase_off,
           const unsigned char *__restrict__ active) {
+  typedef typename CplxOf<T>::type CT;
   const DftWork wk = work[blockIdx.x];
   if (!active[wk.param]) return; // decimation: dft.cpp:259
   const DftParams<T> &q = params[wk.param];
-  const long long e = wk.e0 + threadIdx.x;
-  if (e >= q.N * q.Nomega) return;
-  const long long pt = e / q.Nomega;
-  const int iw = (int)(e - pt * q.Nomega);
-  const int n2 = q.n[1], n3 = q.n[2];
-  const int i3 = (int)(pt % n3);
-  const long long r = pt / n3;
-  const int i2 = (int)(r % n2), i1 = (int)(r / n2);
-  const long long idx = q.idx0 + i1 * q.st[0] + i2 * q.st[1] + i3 * q.st[2];
-  double w;
-  if (q.include_dV) { // IVEC_LOOP_WEIGHT, vec.hpp:372-383
-    const int li[3] = {i1, i2, i3};
-    double w1[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int i = li[k], n = q.n[k], dir = q.dir[k];
-      w1[k] = (i > 1 && i < n - 2)
-                  ? 1.0
-                  : (i == 0 ? q.s0[dir]
-                            : (i == 1 ? q.s1[dir]
-                                      : i == n - 1 ? q.e0[dir] : (i == n - 2 ? q.e1[dir] : 1.0)));
-    }
-    w = (w1[2] * (w1[1] * ((q.dV0 + q.dV1 * i2) * w1[0])));
-    if (q.sqrt_dV) w = sqrt(w);
-  }
-  else
-    w = 1.0;
-  T f[2];
+  const long long total = q.N * q.Nomega;
+  const int Nw = q.Nomega, n2 = q.n[1], n3 = q.n[2];
   const int numcmp = q.f1 ? 2 : 1;
-  for (int cmp = 0; cmp < numcmp; ++cmp) {
-    const T *ff = cmp ? q.f1 : q.f0;
-    if (q.avg2)
-      f[cmp] = (w * 0.25) * (ff[idx] + ff[idx + q.avg1] + ff[idx + q.avg2] + ff[idx + (q.avg1 + q.avg2)]);
-    else if (q.avg1)
-      f[cmp] = (w * 0.5) * (ff[idx] + ff[idx + q.avg1]);
+  const T *phb = phases + 2 * phase_off[q.phase_group];
+  CT acc[kDftPerThread];
+  T f0[kDftPerThread], f1[kDftPerThread], pr[kDftPerThread], pi[kDftPerThread];
+  bool on[kDftPerThread];
+#pragma unroll
+  for (int k = 0; k < kDftPerThread; ++k) {
+    const long long e = wk.e0 + threadIdx.x + (long long)k * kThreads;
+    on[k] = e < total;
+    if (!on[k]) continue;
+    acc[k] = *reinterpret_cast<const CT *>(q.dft + 2 * e); // the dominant traffic: issued first
+    long long pt;
+    int iw;
+    if (total < (1LL << 31)) {
+      const unsigned eu = (unsigned)e;
+      pt = eu / (unsigned)Nw;
+      iw = (int)(eu - (unsigned)pt * (unsigned)Nw);
+    }
+    else {
+      pt = e / Nw;
+      iw = (int)(e - pt * Nw);
+    }
+    int i1, i2, i3;
+    if (q.N < (1LL << 31)) {
+      const unsigned p = (unsigned)pt, r = p / (unsigned)n3;
+      i3 = (int)(p - r * (unsigned)n3);
+      i1 = (int)(r / (unsigned)n2);
+      i2 = (int)(r - (unsigned)i1 * (unsigned)n2);
+    }
+    else {
+      i3 = (int)(pt % n3);
+      const long long r = pt / n3;
+      i2 = (int)(r % n2);
+      i1 = (int)(r / n2);
+    }
+    const long long idx = q.idx0 + i1 * q.st[0] + i2 * q.st[1] + i3 * q.st[2];
+    double w;
+    if (q.include_dV) { // IVEC_LOOP_WEIGHT, vec.hpp:372-383
+      const int li[3] = {i1, i2, i3};
+      double w1[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int i = li[d], n = q.n[d], dir = q.dir[d];
+        w1[d] = (i > 1 && i < n - 2)
+                    ? 1.0
+                    : (i == 0 ? q.s0[dir]
+                              : (i == 1 ? q.s1[dir]
+                                        : i == n - 1 ? q.e0[dir] : (i == n - 2 ? q.e1[dir] : 1.0)));
+      }
+      w = (w1[2] * (w1[1] * ((q.dV0 + q.dV1 * i2) * w1[0])));
+      if (q.sqrt_dV) w = sqrt(w);
+    }
     else
-      f[cmp] = w * ff[idx];
+      w = 1.0;
+    T f[2] = {0, 0};
+    for (int cmp = 0; cmp < numcmp; ++cmp) {
+      const T *ff = cmp ? q.f1 : q.f0;
+      if (q.avg2)
+        f[cmp] = (w * 0.25) * (ff[idx] + ff[idx + q.avg1] + ff[idx + q.avg2] + ff[idx + (q.avg1 + q.avg2)]);
+      else if (q.avg1)
+        f[cmp] = (w * 0.5) * (ff[idx] + ff[idx + q.avg1]);
+      else
+        f[cmp] = w * ff[idx];
+    }
+    f0[k] = f[0];
+    f1[k] = f[1];
+    pr[k] = phb[2 * iw];
+    pi[k] = phb[2 * iw + 1];
   }
-  const T *ph = phases + 2 * (phase_off[q.phase_group] + iw);
-  const T pr = ph[0], pi = ph[1];
-  T *d = q.dft + 2 * e;
-  if (numcmp == 2) { // complex<realnum> product, dft.cpp:295-299
-    d[0] = d[0] + (pr * f[0] - pi * f[1]);
-    d[1] = d[1] + (pr * f[1] + pi * f[0]);
-  }
-  else { // :300-305
-    d[0] = d[0] + f[0] * pr;
-    d[1] = d[1] + f[0] * pi;
+#pragma unroll
+  for (int k = 0; k < kDftPerThread; ++k) {
+    if (!on[k]) continue;
+    const long long e = wk.e0 + threadIdx.x + (long long)k * kThreads;
+    CT d = acc[k];
+    if (numcmp == 2) { // complex<realnum> product, dft.cpp:295-299
+      d.x = d.x + (pr[k] * f0[k] - pi[k] * f1[k]);
+      d.y = d.y + (pr[k] * f1[k] + pi[k] * f0[k]);
+    }
+    else { // :300-305
+      d.x = d.x + f0[k] * pr[k];
+      d.y = d.y + f0[k] * pi[k];
+    }
+    *reinterpret_cast<CT *>(q.dft + 2 * e) = d;
   }
 }
 

@@ -927,6 +927,16 @@ template <class T> struct Ctx : CtxBase {
     }
     return true;
   }
+  struct EhMask { unsigned char *mask; const T *u, *u1, *u2, *chi2, *chi3; int mode; long long n; };
+  std::vector<EhMask> eh_masks;
+  int build_eh_masks() { // after every upload of the materials
+    for (size_t k = 0; k < eh_masks.size(); ++k) {
+      const EhMask &m = eh_masks[k];
+      k_eh_mask<T><<<148 * 8, kThreads, 0, st>>>(m.mask, m.u, m.u1, m.u2, m.chi2, m.chi3, m.mode, m.n);
+      launches++;
+    }
+    return MEEPCU_OK;
+  }
   int virt_patch_u() { // after every upload of the materials
     for (size_t k = 0; k < virt_comps.size(); ++k) {
       const VirtComp &vc = virt_comps[k];
@@ -1796,6 +1806,17 @@ template <class T> struct Ctx : CtxBase {
               E.npol = (int)ch.pol[ft].size();
               RC(fill_pols(ch, ft, ec, k, cmp, E.pol));
               E.nr_fail = d_flags;
+              // per-point class of the update from the material arrays (EhParams::mask)
+              const bool nr_branch = cfg.nl_mode == MEEPCU_NL_FORK_LITERAL && !E.fw && E.u1 && E.u2 && E.chi3;
+              const bool pade_diag = cfg.nl_mode == MEEPCU_NL_UPSTREAM_PADE && !E.u1 && !E.u2 && E.chi3;
+              if ((nr_branch || pade_diag) && !getenv("MEEPCU_NO_EH_MASK")) {
+                unsigned char *mk = 0;
+                CU(cudaMalloc((void **)&mk, g.ntot_dev));
+                extra_dev.push_back((char *)mk);
+                E.mask = mk;
+                EhMask em = {mk, E.u, E.u1, E.u2, E.chi2, E.chi3, nr_branch ? 0 : 1, (long long)g.ntot_dev};
+                eh_masks.push_back(em);
+              }
               const int eidx = (int)h_eh.size();
               h_eh.push_back(E);
               const int plane = g.nax[1] * g.pitch;
@@ -1911,6 +1932,7 @@ template <class T> struct Ctx : CtxBase {
       virt_any = hflag[8];
     }
     RC(virt_patch_u());
+    RC(build_eh_masks());
     // ---- 5b. multi-rank: boundary tiles first (see nb_* above) ----
     if (n_ranks > 1 && !getenv("MEEPCU_NO_OVERLAP"))
       for (int half = 0; half < 2; ++half) {
@@ -2256,7 +2278,7 @@ template <class T> struct Ctx : CtxBase {
         dft_decim.push_back(d.decimation_factor);
         dft_is_h.push_back(is_h);
         const long long ne = q.N * q.Nomega;
-        for (long long e0 = 0; e0 < ne; e0 += kThreads) {
+        for (long long e0 = 0; e0 < ne; e0 += (long long)kThreads * kDftPerThread) {
           DftWork w = {pidx, e0};
           work.push_back(w);
         }
@@ -2642,7 +2664,13 @@ template <class T> struct Ctx : CtxBase {
       }
       if (n_eh_tiles[half]) { // (the flag is global: this rank may own no such chunk)
         RC(prof_begin(KC_EH_GENERAL));
-        k_eh_general<T><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
+        // resident CTAs per SM (= registers per thread): 5 x 48 registers measured best while every point paid the
+        // neighbour loads; MEEPCU_EH_CTAS = 2 / 3 / 4 select builds with 128 / 80 / 64 registers
+        static const int eh_ctas = getenv("MEEPCU_EH_CTAS") ? atoi(getenv("MEEPCU_EH_CTAS")) : MCU_EH_CTAS;
+        if (eh_ctas == 2) k_eh_general<T, 2><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
+        else if (eh_ctas == 3) k_eh_general<T, 3><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
+        else if (eh_ctas == 4) k_eh_general<T, 4><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
+        else k_eh_general<T, MCU_EH_CTAS><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
         RC(prof_end());
         launches++;
       }
@@ -2943,7 +2971,7 @@ template <class T> struct Ctx : CtxBase {
     }
     else {
       if (groups & MEEPCU_SYNC_FIELDS) e_virtual = false; // every E array on the device is the host's again
-      if (groups & MEEPCU_SYNC_MATERIALS) RC(virt_patch_u());
+      if (groups & MEEPCU_SYNC_MATERIALS) { RC(virt_patch_u()); RC(build_eh_masks()); }
     }
     CU(cudaStreamSynchronize(st));
     RC(collect_timing());
