@@ -271,6 +271,37 @@ int meepcu_read_value(meepcu_ctx *ctx, const void *host_ptr, double *out);
  * integrate.cpp) read, without a sync of whole arrays */
 int meepcu_read_values(meepcu_ctx *ctx, size_t n, const void *const *host_ptrs, double *out);
 
+/* ---- reductions for the host-side readers: no array travels ------------ */
+/* out[i] = sum over the listed pairs p and their points k < N_p of
+ *   Re(a_p.dft[k*Nomega+i] * conj(b_p.dft[k*Nomega+i]))        (each term in realnum, the sum in double)
+ * for i < Nomega: dft_flux::flux (src/dft.cpp:533-548; a = the E list, b = the H list, in list order) and the
+ * sums of dft_energy::electric / magnetic (src/dft.cpp:657-687; the caller multiplies by 0.5).  a[p], b[p] are
+ * dft_chunk::dft host pointers as given to meepcu_add_dft; both chunks of a pair have the same N and Nomega.
+ * The accumulators stay on the device. */
+int meepcu_dft_dot(meepcu_ctx *ctx, size_t npairs, const void *const *a, const void *const *b, int Nomega,
+                   double *out);
+
+/* One piece of fields::integrate (src/integrate.cpp:47-131) with two field components: what
+ * integrate_chunkloop receives from loop_in_chunks for one (chunk, symmetry copy, periodic shift). */
+typedef struct {
+  const void *f[2][2];   /* fields_chunk::f[cS[i]][cmp] of the two components (cmp 1 NULL: real fields) */
+  ptrdiff_t off[2][2];   /* grid_volume::yee2cent_offsets of each component in host elements (0,0: own grid) */
+  double ph[2][2];       /* shift_phase * S.phase_shift(cS[i], sn) as (re,im) */
+  int is[3], ie[3];      /* loop bounds (ivec, X,Y,Z) */
+  double s0[3], s1[3], e0[3], e1[3]; /* IVEC_LOOP_WEIGHT end weights (X,Y,Z) */
+  double dV0, dV1;
+  int reserved[4];
+} meepcu_integrate_desc;
+/* *sum    = sum over the pieces and their points of  w * Re(conj(F_0) F_1),
+ * *maxabs = max |Re(conj(F_0) F_1)|  (may be NULL),
+ * F_i = complex<realnum>(ph_i * 0.25 (f_i[idx] + f_i[idx+off0] + f_i[idx+off1] + f_i[idx+off0+off1])), w =
+ * IVEC_LOOP_WEIGHT: fields::integrate(2, cs, dot_integrand, 0, where) of src/energy_and_flux.cpp:61-85,189-215
+ * -- field_energy_in_box, electric / magnetic_energy_in_box, flux_in_box_wrongH -- evaluated on the device mirror
+ * (E and H at the times the device holds them: call meepcu_synchronize_magnetic_fields around it like the
+ * reference does).  Single rank: the caller adds the ranks' sums (sum_to_all), as the reference does. */
+int meepcu_integrate_dot(meepcu_ctx *ctx, size_t npieces, const meepcu_integrate_desc *pieces, double *sum,
+                         double *maxabs);
+
 /* ---- introspection ------------------------------------------------------------------------ */
 /* seconds accumulated per reference time_sink (src/meep.hpp:1610-1633), CUDA-event based: out[1]
  * (Stepping) is the device time of every meepcu_step call so far, always on; the per-phase sinks
@@ -301,6 +332,12 @@ typedef struct {
 /* on: bit 0 = time every kernel (serialised on one stream; also resets the accumulated times), bit 1 = count the
  * Newton-Raphson solves and iterations of k_eh_general (meepcu_stats.reserved[1,2,6]; atomics: do not time then) */
 int meepcu_set_profiling(meepcu_ctx *ctx, int on);
+/* The same byte counts with SURVEY.md 8(d)'s per-cell figures, i.e. with every array of the reference's update moved once
+ * per half step in which it is read and once where it is written (21 values per vacuum cell, 24 with a diagonal
+ * epsilon: E is stored by the D/E half and read back by the B/H half).  meepcu_stats.algorithmic_bytes_per_step and
+ * meepcu_kernel_time.algorithmic_bytes count what THIS implementation has to move, which is less where a chunk does
+ * not store E while stepping (18 / 21).  per_kernel[i] belongs to entry i of meepcu_get_kernel_times. */
+int meepcu_get_compulsory_bytes(meepcu_ctx *ctx, int64_t *per_step, int64_t *per_kernel, int capacity, int *n);
 int meepcu_get_kernel_times(meepcu_ctx *ctx, meepcu_kernel_time *out, int capacity, int *n);
 
 #ifdef __cplusplus

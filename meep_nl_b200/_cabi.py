@@ -77,6 +77,13 @@ class DftDesc(C.Structure):
                 ("reserved", C.c_int * 8)]
 
 
+class IntegrateDesc(C.Structure):  # meepcu_integrate_desc
+    _fields_ = [("f", (vp * 2) * 2), ("off", (C.c_ssize_t * 2) * 2), ("ph", (C.c_double * 2) * 2),
+                ("is_", C.c_int * 3), ("ie", C.c_int * 3),
+                ("s0", C.c_double * 3), ("s1", C.c_double * 3), ("e0", C.c_double * 3), ("e1", C.c_double * 3),
+                ("dV0", C.c_double), ("dV1", C.c_double), ("reserved", C.c_int * 4)]
+
+
 class SrcSample(C.Structure):
     _fields_ = [("current_B", C.c_double * 2), ("dipole_H", C.c_double * 2),
                 ("current_D", C.c_double * 2), ("dipole_E", C.c_double * 2)]
@@ -123,10 +130,13 @@ _PROTOTYPES = [
     ("meepcu_check_finite", C.c_int, [vp, C.POINTER(C.c_int)]),
     ("meepcu_read_value", C.c_int, [vp, vp, C.POINTER(C.c_double)]),
     ("meepcu_read_values", C.c_int, [vp, C.c_size_t, vp, C.POINTER(C.c_double)]),
+    ("meepcu_dft_dot", C.c_int, [vp, C.c_size_t, vp, vp, C.c_int, C.POINTER(C.c_double)]),
+    ("meepcu_integrate_dot", C.c_int, [vp, C.c_size_t, C.POINTER(IntegrateDesc), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("meepcu_get_timers", C.c_int, [vp, C.POINTER(C.c_double)]),
     ("meepcu_get_stats", C.c_int, [vp, C.POINTER(Stats)]),
     ("meepcu_set_profiling", C.c_int, [vp, C.c_int]),
     ("meepcu_get_kernel_times", C.c_int, [vp, C.POINTER(KernelTime), C.c_int, C.POINTER(C.c_int)]),
+    ("meepcu_get_compulsory_bytes", C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int)]),
 ]
 SYMBOLS = [p[0] for p in _PROTOTYPES]
 

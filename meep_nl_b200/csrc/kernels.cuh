@@ -1787,7 +1787,21 @@ __global__ void __launch_bounds__(kThreads, CTAS)
   const int a0 = t.a0 > P.lo[0] ? t.a0 : P.lo[0];
   const int a1 = t.a1 - 1 < P.hi[0] ? t.a1 - 1 : P.hi[0];
   long long i = (long long)a0 * P.sA + (long long)ib * P.sB + ic;
-  for (int ia = a0; ia <= a1; ++ia, i += P.sA) eh_point<T>(P, i, ia, ib, ic);
+  for (int ia = a0; ia <= a1; ++ia, i += P.sA) {
+    if (MCU_PREFETCH_PLANES > 0 && ia + MCU_PREFETCH_PLANES <= a1) {
+      // the operands of this thread's point two planes ahead, into L2 (r02d ncu: 45 % of the kernel's stall samples
+      // were the first dependent instructions after the loads of a point -- DRAM latency, once per point)
+      const long long ipf = i + MCU_PREFETCH_PLANES * P.sA;
+      prefetch_l2(P.g + ipf);
+      if (P.u) prefetch_l2(P.u + ipf);
+      if (P.mask) prefetch_l2(P.mask + ipf);
+      if (P.g1) prefetch_l2(P.g1 + ipf);
+      if (P.g2) prefetch_l2(P.g2 + ipf);
+      if (P.chi2) prefetch_l2(P.chi2 + ipf);
+      if (P.fw || (P.u1 && P.u2 && P.chi3)) prefetch_l2(P.f + ipf);
+    }
+    eh_point<T>(P, i, ia, ib, ic);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2042,6 +2056,119 @@ __global__ void __launch_bounds__(kThreads)
       d.y = d.y + f0[k] * pi[k];
     }
     *reinterpret_cast<CT *>(q.dft + 2 * e) = d;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reductions for the host-side readers: the arrays stay on the device, a few
+// kilobytes of per-CTA partial sums travel.  Every partial is formed in a fixed order (no atomics), and
+// the host adds the partials in work-item order, so a result does not depend on scheduling.
+// ------------------------------------------------------------------------------------------------
+// dft_flux::flux / dft_energy::electric, magnetic (dft.cpp:533-548,657-687):
+//   out[i] += Re(a[k*Nw+i] * conj(b[k*Nw+i])) = a.re*b.re + a.im*b.im   (term in realnum, sum in double)
+// A CTA = (kThreads / W) point lanes x W frequency lanes (W = power of two >= min(Nw, kThreads)): consecutive
+// threads read consecutive frequencies of one point -- the layout of dft[] -- and walk the points of the work item.
+template <class T> struct DftDotWork {
+  const T *a, *b;   // complex<T> arrays as (re,im) pairs
+  long long k0, k1; // points [k0, k1) of this pair
+};
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+    k_dft_dot(const DftDotWork<T> *__restrict__ work, int Nw, int W, double *__restrict__ partial) {
+  typedef typename CplxOf<T>::type CT;
+  __shared__ double red[kThreads];
+  const DftDotWork<T> wk = work[blockIdx.x];
+  const int wi = threadIdx.x % W, lk = threadIdx.x / W, lanes = kThreads / W;
+  const int i = blockIdx.y * W + wi;
+  double acc = 0;
+  if (i < Nw) {
+    const CT *a = reinterpret_cast<const CT *>(wk.a), *b = reinterpret_cast<const CT *>(wk.b);
+    for (long long k = wk.k0 + lk; k < wk.k1; k += lanes) {
+      const CT x = a[k * Nw + i], y = b[k * Nw + i];
+      const T term = x.x * y.x + x.y * y.y;
+      acc += (double)term;
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (lk == 0 && i < Nw) {
+    double s = acc;
+    for (int l = 1; l < lanes; ++l) s += red[l * W + wi];
+    partial[(size_t)blockIdx.x * Nw + i] = s;
+  }
+}
+
+// fields::integrate with two components and dot_integrand (integrate.cpp:47-131, energy_and_flux.cpp:61-65):
+// per point  F_i = complex<realnum>(complex<double>(f_re, f_im) * ph_i),  f = 0.25 * (four-point sum in realnum),
+//            v = Re(conj(F_0) F_1) = F0.re*F1.re + F0.im*F1.im in double,  sum += v * IVEC_LOOP_WEIGHT, max |v|.
+template <class T> struct IntgParams {
+  const T *f[2][2];
+  long long off[2][2]; // device offsets of the yee2cent averages
+  double ph[2][2];
+  long long idx0, st[3];
+  int n[3], dir[3];
+  double s0[3], s1[3], e0[3], e1[3], dV0, dV1;
+  long long N;
+};
+struct IntgWork {
+  int param;
+  long long p0; // first point (loop counter) of this CTA
+};
+constexpr int kIntgPerThread = 8;
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+    k_integrate_dot(const IntgParams<T> *__restrict__ params, const IntgWork *__restrict__ work, double *__restrict__ partial) {
+  __shared__ double rs[kThreads], rm[kThreads];
+  const IntgWork wk = work[blockIdx.x];
+  const IntgParams<T> &q = params[wk.param];
+  const int n2 = q.n[1], n3 = q.n[2];
+  double sum = 0, mx = 0;
+  for (int r = 0; r < kIntgPerThread; ++r) {
+    const long long pt = wk.p0 + threadIdx.x + (long long)r * kThreads;
+    if (pt >= q.N) break;
+    const int i3 = (int)(pt % n3);
+    const long long rr = pt / n3;
+    const int i2 = (int)(rr % n2), i1 = (int)(rr / n2);
+    const long long idx = q.idx0 + i1 * q.st[0] + i2 * q.st[1] + i3 * q.st[2];
+    const int li[3] = {i1, i2, i3};
+    double w1[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { // IVEC_LOOP_WEIGHT1x, vec.hpp:372-383
+      const int i = li[d], n = q.n[d], dir = q.dir[d];
+      w1[d] = (i > 1 && i < n - 2) ? 1.0
+                                   : (i == 0 ? q.s0[dir] : (i == 1 ? q.s1[dir] : i == n - 1 ? q.e0[dir] : (i == n - 2 ? q.e1[dir] : 1.0)));
+    }
+    const double w = (w1[2] * (w1[1] * ((q.dV0 + q.dV1 * i2) * w1[0])));
+    T F[2][2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      double f[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const T *p = q.f[c][k];
+        f[k] = p ? 0.25 * (p[idx] + p[idx + q.off[c][0]] + p[idx + q.off[c][1]] + p[idx + (q.off[c][0] + q.off[c][1])]) : 0.0;
+      }
+      const double2 z = cmul(f[0], f[1], q.ph[c][0], q.ph[c][1]);
+      F[c][0] = (T)z.x;
+      F[c][1] = (T)z.y;
+    }
+    const double v = (double)F[0][0] * (double)F[1][0] + (double)F[0][1] * (double)F[1][1];
+    sum += v * w;
+    mx = fmax(mx, fabs(v));
+  }
+  rs[threadIdx.x] = sum;
+  rm[threadIdx.x] = mx;
+  __syncthreads();
+  for (int s = kThreads / 2; s > 0; s >>= 1) { // fixed-shape tree: the same partial whatever the scheduling
+    if ((int)threadIdx.x < s) {
+      rs[threadIdx.x] += rs[threadIdx.x + s];
+      rm[threadIdx.x] = fmax(rm[threadIdx.x], rm[threadIdx.x + s]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[2 * (size_t)blockIdx.x] = rs[0];
+    partial[2 * (size_t)blockIdx.x + 1] = rm[0];
   }
 }
 

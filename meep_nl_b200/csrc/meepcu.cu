@@ -241,6 +241,9 @@ struct CtxBase {
   virtual int comm_init(int rank, int nranks, const void *id) = 0;
   virtual int set_profiling(int on) = 0;
   virtual int get_kernel_times(meepcu_kernel_time *out, int cap, int *n) = 0;
+  virtual int get_compulsory_bytes(int64_t *per_step, int64_t *per_kernel, int cap, int *n) = 0;
+  virtual int dft_dot(size_t npairs, const void *const *a, const void *const *b, int Nomega, double *out) = 0;
+  virtual int integrate_dot(size_t n, const meepcu_integrate_desc *pc, double *sum, double *maxabs) = 0;
 };
 
 template <class T> struct DevBuf { // simple growable device buffer
@@ -430,6 +433,10 @@ template <class T> struct Ctx : CtxBase {
   double kc_ms[KC_COUNT];
   int64_t kc_launches[KC_COUNT];
   int64_t kc_bytes[KC_COUNT];
+  // the same accounting with SURVEY.md 8(d)'s per-cell figures (E stored in the D/E half and read back in the B/H half:
+  // 21 / 24 values per vacuum / dielectric cell) -- what `roofline.achieved` is quoted on; kc_bytes / alg_bytes count
+  // what the kernels really have to move (virtual-E chunks: 18 / 21)
+  int64_t kc_bytes_sv[KC_COUNT], alg_bytes_sv;
   double sink_ms[22];
 
   Ctx() : arena(0), arena_bytes(0), st(0), st2(0), ev0(0), ev1(0), ev_fork(0), ev_join(0), d_half(0), d_eh(0), d_dft(0),
@@ -459,6 +466,8 @@ template <class T> struct Ctx : CtxBase {
     memset(kc_ms, 0, sizeof kc_ms);
     memset(kc_launches, 0, sizeof kc_launches);
     memset(kc_bytes, 0, sizeof kc_bytes);
+    memset(kc_bytes_sv, 0, sizeof kc_bytes_sv);
+    alg_bytes_sv = 0;
     memset(sink_ms, 0, sizeof sink_ms);
     memset(d_tiles, 0, sizeof d_tiles);
     d_c3d = 0;
@@ -1382,6 +1391,8 @@ template <class T> struct Ctx : CtxBase {
     const int ncmp = cfg.is_real ? 1 : 2;
     cells = 0;
     alg_bytes = 0;
+    alg_bytes_sv = 0;
+    memset(kc_bytes_sv, 0, sizeof kc_bytes_sv);
     for (size_t ic = 0; ic < chunks.size(); ++ic) {
       ChunkH &ch = chunks[ic];
       const Geom &g = ch.g;
@@ -1716,7 +1727,16 @@ template <class T> struct Ctx : CtxBase {
               }
             }
             alg_bytes += (long long)v * nc * (long long)sizeof(T);
-            kc_bytes[fast ? (half ? KC_CURL3D_D : KC_CURL3D_B) : (half ? KC_HALF_D_SIMPLE : KC_HALF_B_SIMPLE) + (simple ? 0 : 1)] += (long long)v * nc * (long long)sizeof(T);
+            const int kcl = fast ? (half ? KC_CURL3D_D : KC_CURL3D_B) : (half ? KC_HALF_D_SIMPLE : KC_HALF_B_SIMPLE) + (simple ? 0 : 1);
+            kc_bytes[kcl] += (long long)v * nc * (long long)sizeof(T);
+            int vs = v; // the E array is written (with its chi1inv read) in the D/E half, read in the B/H half
+            if (virt) {
+              const bool has_u = ch.d.chi1inv[dir_comp(MEEPCU_E_STUFF, k)][k] != 0;
+              if (half == 0 && has_u) vs -= 1;
+              if (half == 1) vs += 1 + (has_u ? 1 : 0);
+            }
+            alg_bytes_sv += (long long)vs * nc * (long long)sizeof(T);
+            kc_bytes_sv[kcl] += (long long)vs * nc * (long long)sizeof(T);
           }
         }
         // ---- general E/H components of this chunk ----
@@ -1837,6 +1857,8 @@ template <class T> struct Ctx : CtxBase {
                 }
               alg_bytes += (long long)(4 + (E.fw ? 3 : 0)) * nc * (long long)sizeof(T);
               kc_bytes[KC_EH_GENERAL] += (long long)(4 + (E.fw ? 3 : 0)) * nc * (long long)sizeof(T);
+              alg_bytes_sv += (long long)(4 + (E.fw ? 3 : 0)) * nc * (long long)sizeof(T);
+              kc_bytes_sv[KC_EH_GENERAL] += (long long)(4 + (E.fw ? 3 : 0)) * nc * (long long)sizeof(T);
             }
           }
         }
@@ -1896,6 +1918,8 @@ template <class T> struct Ctx : CtxBase {
                 const int v = 5 + (Q.s1 ? 2 : 0) + (Q.s2 ? 2 : 0); // R,W p, R,W pp, R s (+ R s1,w1 / s2,w2; W itself counted with E)
                 alg_bytes += (long long)v * nc * (long long)sizeof(T);
                 kc_bytes[KC_POL_GENERAL] += (long long)v * nc * (long long)sizeof(T);
+                alg_bytes_sv += (long long)v * nc * (long long)sizeof(T);
+                kc_bytes_sv[KC_POL_GENERAL] += (long long)v * nc * (long long)sizeof(T);
               }
           }
         }
@@ -2048,6 +2072,8 @@ template <class T> struct Ctx : CtxBase {
                   kh = half ? KC_HALF_D_SIMPLE : KC_HALF_B_SIMPLE;
         kc_bytes[km] = kc_bytes[kc] + kc_bytes[kh];
         kc_bytes[kc] = kc_bytes[kh] = 0;
+        kc_bytes_sv[km] = kc_bytes_sv[kc] + kc_bytes_sv[kh];
+        kc_bytes_sv[kc] = kc_bytes_sv[kh] = 0;
       }
     }
     RC(upload(h_half, &d_half));
@@ -2284,6 +2310,8 @@ template <class T> struct Ctx : CtxBase {
         }
         alg_bytes += 4LL * ne * (long long)sizeof(T) / d.decimation_factor;
         kc_bytes[KC_DFT] += 4LL * ne * (long long)sizeof(T) / d.decimation_factor;
+        alg_bytes_sv += 4LL * ne * (long long)sizeof(T) / d.decimation_factor;
+        kc_bytes_sv[KC_DFT] += 4LL * ne * (long long)sizeof(T) / d.decimation_factor;
       }
     }
     RC(upload(h_dft, &d_dft));
@@ -2398,6 +2426,8 @@ template <class T> struct Ctx : CtxBase {
           }
         alg_bytes += 13LL * nc * (long long)sizeof(T); // R,W six P arrays + R sigma (W counted with E)
         kc_bytes[KC_POL_GENERAL] += 13LL * nc * (long long)sizeof(T);
+        alg_bytes_sv += 13LL * nc * (long long)sizeof(T);
+        kc_bytes_sv[KC_POL_GENERAL] += 13LL * nc * (long long)sizeof(T);
       }
     (void)ic;
     (void)half;
@@ -2901,7 +2931,9 @@ template <class T> struct Ctx : CtxBase {
     return MEEPCU_OK;
   }
 
-  int sync_to_host() { return sync_groups(true, ~0u); }
+  // every group, and NOT the MEEPCU_SYNC_LOCAL modifier: with several ranks the call is collective and refreshes the
+  // halos owned by other ranks too (r02e: passing ~0u made every full sync local-only -- stale D/B halos across cuts)
+  int sync_to_host() { return sync_groups(true, ~0u & ~(unsigned)MEEPCU_SYNC_LOCAL); }
   // the caller's arrays -> device: everything that changes while stepping.  Materials (chi1inv, chi2, chi3,
   // conductivity, sigma, sig/kap/siginv) were uploaded by meepcu_finalize and travel again only when asked for
   // (meepcu_sync_subset(ctx, 0, MEEPCU_SYNC_MATERIALS)): re-sending them at every sync is pure PCIe time.
@@ -3063,6 +3095,170 @@ template <class T> struct Ctx : CtxBase {
       halo_stale = true; // the normal-plane E halos parked in D arrays are gone until the next A
     }
     for (size_t i = 0; i < n; ++i) out[i] = (double)v[i];
+    return MEEPCU_OK;
+  }
+
+  // ---- reductions for the host-side readers: dft_flux::flux / dft_energy (dft.cpp:533-548,657-687) ----
+  int get_compulsory_bytes(int64_t *per_step, int64_t *per_kernel, int cap, int *n) {
+    if (per_step) *per_step = alg_bytes_sv;
+    int m = 0;
+    for (int k = 0; k < KC_COUNT && m < cap; ++k) per_kernel[m++] = kc_bytes_sv[k];
+    if (n) *n = m;
+    return MEEPCU_OK;
+  }
+  int dft_dot(size_t npairs, const void *const *a, const void *const *b, int Nomega, double *out) {
+    if (!finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
+    if (Nomega <= 0 || !out || (npairs && (!a || !b))) return fail(MEEPCU_EINVAL, "bad argument");
+    for (int i = 0; i < Nomega; ++i) out[i] = 0;
+    if (!npairs) return MEEPCU_OK;
+    CU(cudaSetDevice(cfg.device));
+    int W = 1;
+    while (W < Nomega && W < kThreads) W <<= 1;
+    const int lanes = kThreads / W;
+    const long long per = std::max<long long>(lanes, ((long long)1 << 15) / W); // points per work item
+    std::vector<DftDotWork<T> > work;
+    for (size_t p = 0; p < npairs; ++p) {
+      size_t ea = 0, eb = 0;
+      const ArrayRec *ra = find(a[p], sizeof(T), &ea), *rb = find(b[p], sizeof(T), &eb);
+      if (!ra || !rb || ra->kind != A_DFT || rb->kind != A_DFT || ea || eb)
+        return fail(MEEPCU_EINVAL, "pair %zu: not dft_chunk::dft arrays registered by meepcu_add_dft", p);
+      if (ra->n_host != rb->n_host || ra->n_host % (size_t)Nomega)
+        return fail(MEEPCU_EINVAL, "pair %zu: the two dft chunks differ in size, or Nomega does not divide it", p);
+      const long long N = (long long)(ra->n_host / (size_t)Nomega);
+      for (long long k0 = 0; k0 < N; k0 += per) {
+        DftDotWork<T> w = {(const T *)ra->dev, (const T *)rb->dev, k0, std::min(N, k0 + per)};
+        work.push_back(w);
+      }
+    }
+    if (work.empty()) return MEEPCU_OK;
+    DftDotWork<T> *d_work = 0;
+    double *d_part = 0;
+    const size_t np = work.size() * (size_t)Nomega;
+    CU(cudaMalloc((void **)&d_work, work.size() * sizeof(DftDotWork<T>)));
+    if (cudaMalloc((void **)&d_part, np * sizeof(double)) != cudaSuccess) { cudaFree(d_work); return fail(MEEPCU_ENOMEM, "cudaMalloc"); }
+    std::vector<double> part(np);
+    cudaError_t e = cudaMemcpyAsync(d_work, work.data(), work.size() * sizeof(DftDotWork<T>), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+      dim3 grid((unsigned)work.size(), (unsigned)((Nomega + W - 1) / W));
+      k_dft_dot<T><<<grid, kThreads, 0, st>>>(d_work, Nomega, W, d_part);
+      launches++;
+      e = cudaMemcpyAsync(part.data(), d_part, np * sizeof(double), cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_work);
+    cudaFree(d_part);
+    if (e != cudaSuccess) return fail(MEEPCU_ECUDA, "%s", cudaGetErrorString(e));
+    RC(collect_timing());
+    for (size_t w = 0; w < work.size(); ++w)
+      for (int i = 0; i < Nomega; ++i) out[i] += part[w * (size_t)Nomega + i];
+    return MEEPCU_OK;
+  }
+
+  // ---- fields::integrate(2, cs, dot_integrand, ...) (integrate.cpp:47-131, energy_and_flux.cpp:61-85,189-215) ----
+  int integrate_dot(size_t n, const meepcu_integrate_desc *pc, double *sum, double *maxabs) {
+    if (!finalized) return fail(MEEPCU_ESTATE, "meepcu_finalize not called");
+    if (!sum || (n && !pc)) return fail(MEEPCU_EINVAL, "null argument");
+    *sum = 0;
+    if (maxabs) *maxabs = 0;
+    if (!n) return MEEPCU_OK;
+    CU(cudaSetDevice(cfg.device));
+    std::vector<IntgParams<T> > par;
+    std::vector<IntgWork> work;
+    for (size_t ip = 0; ip < n; ++ip) {
+      const meepcu_integrate_desc &d = pc[ip];
+      if (!d.f[0][0] || !d.f[1][0]) continue; // a component this chunk does not have: the integrand is 0 (integrate.cpp:110-116)
+      size_t e0 = 0;
+      const ArrayRec *r0 = find(d.f[0][0], sizeof(T), &e0);
+      if (!r0 || r0->kind != A_GRID || e0) return fail(MEEPCU_EINVAL, "piece %zu: f[0][0] is not a registered field array", ip);
+      const Geom &g = chunks[r0->chunk].g;
+      IntgParams<T> q;
+      memset(&q, 0, sizeof q);
+      for (int c = 0; c < 2; ++c)
+        for (int k = 0; k < 2; ++k) {
+          if (!d.f[c][k]) continue;
+          size_t e = 0;
+          const ArrayRec *r = find(d.f[c][k], sizeof(T), &e);
+          if (!r || r->kind != A_GRID || e || r->chunk != r0->chunk)
+            return fail(MEEPCU_EINVAL, "piece %zu: f[%d][%d] is not a field array of the same chunk", ip, c, k);
+          q.f[c][k] = (const T *)r->dev;
+        }
+      long long idx0 = 0, N = 1;
+      for (int k = 0; k < 3; ++k) { // LOOP_OVER_IVECS in the reference's loop order (vec.hpp:151-168)
+        const int dir = cfg.dim == MEEPCU_D2 ? (k + 2) % 3 : k;
+        q.dir[k] = dir;
+        if (g.has[dir]) {
+          if (d.ie[dir] < d.is[dir]) { N = 0; break; }
+          q.n[k] = (d.ie[dir] - d.is[dir]) / 2 + 1;
+          q.st[k] = g.ds[dir];
+          idx0 += (long long)((d.is[dir] - g.io[dir]) / 2) * g.ds[dir];
+          N *= q.n[k];
+        }
+        else {
+          q.n[k] = 1;
+          q.st[k] = 0;
+        }
+      }
+      if (N <= 0) continue;
+      q.idx0 = idx0;
+      q.N = N;
+      for (int c = 0; c < 2; ++c)
+        for (int k = 0; k < 2; ++k) {
+          q.off[c][k] = g.dev_offset((long long)d.off[c][k]);
+          if (q.off[c][k] == ((long long)1 << 62)) return fail(MEEPCU_EINVAL, "piece %zu: yee2cent offsets are not sums of +-strides", ip);
+          q.ph[c][k] = d.ph[c][k];
+        }
+      for (int k = 0; k < 3; ++k) { q.s0[k] = d.s0[k]; q.s1[k] = d.s1[k]; q.e0[k] = d.e0[k]; q.e1[k] = d.e1[k]; }
+      q.dV0 = d.dV0;
+      q.dV1 = d.dV1;
+      const int pidx = (int)par.size();
+      par.push_back(q);
+      for (long long p0 = 0; p0 < N; p0 += (long long)kThreads * kIntgPerThread) {
+        IntgWork w = {pidx, p0};
+        work.push_back(w);
+      }
+    }
+    if (work.empty()) return MEEPCU_OK;
+    // the device mirror as a host reader would see it: lazy halos materialised, virtual E arrays made real
+    const unsigned fp = MEEPCU_SYNC_FIELDS | MEEPCU_SYNC_POL;
+    const bool virt = virt_now(fp);
+    if (virt) {
+      RC(halos_A(fp));
+      RC(virt_materialise());
+      RC(halos_B(fp, false));
+    }
+    else if (halo_stale)
+      RC(refresh_for_read());
+    IntgParams<T> *d_par = 0;
+    IntgWork *d_work = 0;
+    double *d_part = 0;
+    CU(cudaMalloc((void **)&d_par, par.size() * sizeof(IntgParams<T>)));
+    if (cudaMalloc((void **)&d_work, work.size() * sizeof(IntgWork)) != cudaSuccess) { cudaFree(d_par); return fail(MEEPCU_ENOMEM, "cudaMalloc"); }
+    if (cudaMalloc((void **)&d_part, 2 * work.size() * sizeof(double)) != cudaSuccess) { cudaFree(d_par); cudaFree(d_work); return fail(MEEPCU_ENOMEM, "cudaMalloc"); }
+    std::vector<double> part(2 * work.size());
+    cudaError_t e = cudaMemcpyAsync(d_par, par.data(), par.size() * sizeof(IntgParams<T>), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_work, work.data(), work.size() * sizeof(IntgWork), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+      k_integrate_dot<T><<<(unsigned)work.size(), kThreads, 0, st>>>(d_par, d_work, d_part);
+      launches++;
+      e = cudaMemcpyAsync(part.data(), d_part, part.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_par);
+    cudaFree(d_work);
+    cudaFree(d_part);
+    if (e != cudaSuccess) return fail(MEEPCU_ECUDA, "%s", cudaGetErrorString(e));
+    if (virt) {
+      RC(halos_R(fp, false));
+      halo_stale = true; // the normal-plane E halos parked in D arrays are gone until the next A
+    }
+    RC(collect_timing());
+    double s = 0, m = 0;
+    for (size_t w = 0; w < work.size(); ++w) {
+      s += part[2 * w];
+      m = std::max(m, part[2 * w + 1]);
+    }
+    *sum = s;
+    if (maxabs) *maxabs = m;
     return MEEPCU_OK;
   }
   int check_finite(int *ok) { // every element of every field array, one launch, blocking
@@ -3275,6 +3471,19 @@ int meepcu_check_finite(meepcu_ctx *ctx, int *ok) {
 int meepcu_read_value(meepcu_ctx *ctx, const void *p, double *out) {
   CHECK_CTX;
   return ctx->impl->read_value(p, out);
+}
+int meepcu_get_compulsory_bytes(meepcu_ctx *ctx, int64_t *per_step, int64_t *per_kernel, int capacity, int *n) {
+  if (!ctx || !ctx->impl) return fail(MEEPCU_EINVAL, "null context");
+  if (capacity > 0 && !per_kernel) return fail(MEEPCU_EINVAL, "null argument");
+  return ctx->impl->get_compulsory_bytes(per_step, per_kernel, capacity, n);
+}
+int meepcu_dft_dot(meepcu_ctx *ctx, size_t npairs, const void *const *a, const void *const *b, int Nomega, double *out) {
+  if (!ctx || !ctx->impl) return fail(MEEPCU_EINVAL, "null context");
+  return ctx->impl->dft_dot(npairs, a, b, Nomega, out);
+}
+int meepcu_integrate_dot(meepcu_ctx *ctx, size_t npieces, const meepcu_integrate_desc *pieces, double *sum, double *maxabs) {
+  if (!ctx || !ctx->impl) return fail(MEEPCU_EINVAL, "null context");
+  return ctx->impl->integrate_dot(npieces, pieces, sum, maxabs);
 }
 int meepcu_get_timers(meepcu_ctx *ctx, double out[22]) {
   CHECK_CTX;

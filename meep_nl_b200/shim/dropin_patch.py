@@ -30,6 +30,13 @@ MEMBERS = '''
   // point probes (every fields::get_field overload ends in the (component, ivec) one) read their few values
   // straight from the device mirror instead of downloading the whole state; false: the host arrays are current
   bool gpu_get_field(component c, const ivec &origloc, bool parallel, std::complex<double> *out) const;
+  // reductions on the device (no array travels): fields::integrate(2, cs, dot_integrand, 0, where) -- what
+  // field_energy_in_box / electric_energy_in_box / magnetic_energy_in_box / flux_in_box_wrongH compute -- and the
+  // sums of dft_flux::flux / dft_energy::electric, magnetic.  false: not on the device, the host code runs as before
+  bool gpu_integrate_dot(const component *cs, const volume &where, double *out);
+  static bool gpu_dft_dot(dft_chunk *a, dft_chunk *b, size_t Nfreq, double *F);
+  bool gpu_collecting = false; // loop_in_chunks is being used to enumerate pieces only
+#define MEEPCU_DROPIN_PATCHED 1
 '''
 
 STEP_HELPERS = r'''
@@ -82,6 +89,14 @@ bool fields::gpu_get_field(component c, const ivec &origloc, bool parallel, std:
       }
   *out = 0.0;
   return true;
+}
+bool fields::gpu_integrate_dot(const component *cs, const volume &where, double *out) {
+  meepcu::attachment *att = (meepcu::attachment *)gpu;
+  if (!att || !att->stale()) return false;
+  return att->integrate_dot(cs, where, out);
+}
+bool fields::gpu_dft_dot(dft_chunk *a, dft_chunk *b, size_t Nfreq, double *F) {
+  return meepcu::attachment::dft_dot_on_device(a, b, Nfreq, F);
 }
 void fields::gpu_dft_read() { meepcu::attachment::for_each_live(&meepcu::attachment::sync_dft_to_host_if_stale); }
 void fields::gpu_dft_write() { meepcu::attachment::for_each_live(&meepcu::attachment::dft_will_be_written); }
@@ -142,11 +157,17 @@ def patch(name, text):
             a = text.index("\nvoid fields::%s() {" % fn)
             k = text.index("return;", a) + len("return;")
             text = text[:k] + "\n  if (gpu) { %s(); return; } // meepcu drop-in" % call + text[k:]
+        # field_energy_in_box(c, where) and flux_in_box_wrongH: the integral is formed on the device
+        a = text.index("return real(integrate(2, cs, dot_integrand, 0, where)) * 0.5;")
+        text = text[:a] + "{ double v_; if (gpu_integrate_dot(cs, where, &v_)) return v_ * 0.5; } // meepcu drop-in\n  " + text[a:]
+        a = text.index("sum += real(integrate(2, cs, dot_integrand, 0, where)) * (1 - 2 * i);")
+        text = text[:a] + ("{ double v_; if (gpu_integrate_dot(cs, where, &v_)) { sum += v_ * (1 - 2 * i); continue; } } "
+                           "// meepcu drop-in\n    ") + text[a:]
         return text
     if name == "loop_in_chunks.cpp":  # the iterator behind integrate / get_array_slice / output_hdf5 / energy / flux_in_box
         a = text.index("\nvoid fields::loop_in_chunks(")
         k = text.index("{", a) + 1
-        return text[:k] + "\n  gpu_sync_to_host(); // meepcu drop-in: readers see the device's state\n" + text[k:]
+        return text[:k] + "\n  if (!gpu_collecting) gpu_sync_to_host(); // meepcu drop-in: readers see the device's state\n" + text[k:]
     if name == "monitor.cpp":  # point probes: every get_field overload ends in the (component, ivec) one
         a = text.index("fields::get_field(component c, const ivec &")
         k = text.index("{", a) + 1
@@ -171,6 +192,15 @@ def patch(name, text):
         if name == fname:
             for sig in sigs:
                 text = at_function_start(text, sig, "fields::gpu_dft_write(); // meepcu drop-in")
+    # (inserted last, so that it runs FIRST: a spectrum that can be summed on the device fetches nothing)
+    if name == "dft.cpp":
+        for sig, la, lb, fac in (("double *dft_flux::flux()", "E", "H", ""), ("double *dft_energy::electric()", "E", "D", "0.5 * "),
+                                 ("double *dft_energy::magnetic()", "H", "B", "0.5 * ")):
+            text = at_function_start(text, sig,
+                "{ const size_t Nf_ = freq.size(); double *F_ = new double[Nf_]; // meepcu drop-in: summed on the device\n"
+                "    if (fields::gpu_dft_dot(%s, %s, Nf_, F_)) { double *Fs_ = new double[Nf_]; for (size_t i_ = 0; i_ < Nf_; ++i_) F_[i_] = %sF_[i_];\n"
+                "      sum_to_all(F_, Fs_, int(Nf_)); delete[] F_; return Fs_; }\n"
+                "    delete[] F_; }" % (la, lb, fac))
     return text
 
 

@@ -77,6 +77,8 @@ struct api {
   MEEPCU_FN(read_value)
   MEEPCU_FN(get_timers)
   MEEPCU_FN(get_stats)
+  MEEPCU_FN(dft_dot)
+  MEEPCU_FN(integrate_dot)
 #undef MEEPCU_FN
   explicit api(const char *path) {
     handle = dlopen(path, RTLD_NOW | RTLD_LOCAL);
@@ -110,6 +112,8 @@ struct api {
     MEEPCU_FN(read_value)
     MEEPCU_FN(get_timers)
     MEEPCU_FN(get_stats)
+    MEEPCU_FN(dft_dot)
+    MEEPCU_FN(integrate_dot)
 #undef MEEPCU_FN
     if (abi_version() != MEEPCU_ABI_VERSION) meep::abort("meepcu: ABI version mismatch in %s", path);
   }
@@ -193,6 +197,94 @@ public:
     double v = 0;
     check(a.read_value(ctx, p, &v));
     return v;
+  }
+  // ---- reductions on the device for the reference's readers (include/meepcu.h) ----------------------------
+  // dft_flux::flux / dft_energy::electric, magnetic (dft.cpp:533-548,657-687): F[i] = sum over the chunk pairs of the
+  // two lists of Re(a.dft * conj(b.dft)).  true: computed on the device (the accumulators live there and the host
+  // copy is out of date); false: the host arrays are current (or belong to no attachment) -- the caller runs its loop.
+  static size_t &device_reductions(int which) { // [0] dft_dot, [1] integrate_dot calls answered by the device (tests)
+    static size_t n[2] = {0, 0};
+    return n[which];
+  }
+  static bool dft_dot_on_device(meep::dft_chunk *A, meep::dft_chunk *B, size_t Nfreq, double *F) {
+    if (!A || !B) return false;
+    for (std::set<attachment *>::iterator it = live().begin(); it != live().end(); ++it) {
+      attachment *att = *it;
+      if (!att->dft_ptrs.count(A->dft)) continue;
+      if (!att->dft_stale || att->dft_host_dirty) return false;
+      std::vector<const void *> pa, pb;
+      for (meep::dft_chunk *ca = A, *cb = B; ca && cb; ca = ca->next_in_dft, cb = cb->next_in_dft) {
+        if (!att->dft_ptrs.count(ca->dft) || !att->dft_ptrs.count(cb->dft) || ca->N != cb->N ||
+            ca->omega.size() != Nfreq || cb->omega.size() != Nfreq)
+          return false;
+        pa.push_back(ca->dft);
+        pb.push_back(cb->dft);
+      }
+      att->check(att->a.dft_dot(att->ctx, pa.size(), pa.data(), pb.data(), (int)Nfreq, F));
+      ++device_reductions(0);
+      return true;
+    }
+    return false;
+  }
+  // fields::integrate(2, cs, dot_integrand, 0, where) (integrate.cpp:133-206, energy_and_flux.cpp:61-85,189-215):
+  // loop_in_chunks enumerates the pieces exactly as it does for integrate_chunkloop, the sums are formed on the device
+  struct integrate_collect {
+    const meep::component *cs;
+    std::vector<meepcu_integrate_desc> pieces;
+  };
+  static void integrate_collect_chunkloop(meep::fields_chunk *fc, int, meep::component cgrid, meep::ivec is, meep::ivec ie,
+                                          meep::vec s0, meep::vec s1, meep::vec e0, meep::vec e1, double dV0, double dV1,
+                                          meep::ivec, std::complex<double> shift_phase, const meep::symmetry &S, int sn,
+                                          void *data_) {
+    using namespace meep;
+    integrate_collect *data = (integrate_collect *)data_;
+    static const direction xyz[3] = {X, Y, Z};
+    meepcu_integrate_desc d;
+    memset(&d, 0, sizeof d);
+    for (int i = 0; i < 2; ++i) {
+      const component c = S.transform(data->cs[i], -sn);
+      ptrdiff_t o0 = 0, o1 = 0;
+      if (cgrid == Centered) fc->gv.yee2cent_offsets(c, o0, o1);
+      d.off[i][0] = o0;
+      d.off[i][1] = o1;
+      const std::complex<double> ph = shift_phase * S.phase_shift(c, sn);
+      d.ph[i][0] = ph.real();
+      d.ph[i][1] = ph.imag();
+      d.f[i][0] = fc->f[c][0];
+      d.f[i][1] = fc->f[c][1];
+    }
+    for (int k = 0; k < 3; ++k) {
+      const bool has = has_direction(fc->gv.dim, xyz[k]);
+      d.is[k] = has ? is.in_direction(xyz[k]) : 0;
+      d.ie[k] = has ? ie.in_direction(xyz[k]) : 0;
+      d.s0[k] = s0.in_direction(xyz[k]);
+      d.s1[k] = s1.in_direction(xyz[k]);
+      d.e0[k] = e0.in_direction(xyz[k]);
+      d.e1[k] = e1.in_direction(xyz[k]);
+    }
+    d.dV0 = dV0;
+    d.dV1 = dV1;
+    data->pieces.push_back(d);
+  }
+  // false: Dcyl (not on the device) -- the caller integrates on the host as before
+  bool integrate_dot(const meep::component *cs, const meep::volume &where, double *out) {
+    using namespace meep;
+    if (f.gv.dim == Dcyl) return false;
+    bool same_grid = f.gv.iyee_shift(cs[1]) == f.gv.iyee_shift(cs[0]); // integrate.cpp:136-146
+    integrate_collect data;
+    data.cs = cs;
+#ifdef MEEPCU_DROPIN_PATCHED
+    f.gpu_collecting = true; // the patched loop_in_chunks only enumerates here: no fetch of the device's state
+#endif
+    f.loop_in_chunks(integrate_collect_chunkloop, (void *)&data, where, same_grid ? cs[0] : Centered);
+#ifdef MEEPCU_DROPIN_PATCHED
+    f.gpu_collecting = false;
+#endif
+    double sum = 0;
+    check(a.integrate_dot(ctx, data.pieces.size(), data.pieces.data(), &sum, 0));
+    *out = sum_to_all(sum);
+    ++device_reductions(1);
+    return true;
   }
   // == the body of fields::synchronize_magnetic_fields / restore_magnetic_fields
   //    (src/energy_and_flux.cpp:145-177) on the device; the caller keeps the reference's counter
@@ -372,6 +464,7 @@ private:
   bool host_stale = false; // the device has advanced since the last sync_to_host
   bool dft_stale = false;  // ... since the DFT accumulators were last fetched
   bool dft_host_dirty = false; // the host changed the accumulators since they were last sent
+  std::set<const void *> dft_ptrs; // dft_chunk::dft arrays registered with the context
   std::vector<meep::src_time *> src_times;
   std::vector<std::vector<double> > keep_amp; // storage handed to the ABI during description
 
@@ -565,6 +658,7 @@ private:
         dd.scale[0] = dc->scale.real();
         dd.scale[1] = dc->scale.imag();
         dd.dft = dc->dft;
+        dft_ptrs.insert(dc->dft);
         if (obs) obs->on_dft(i, dd, dc->N);
         check(a.add_dft(ctx, i, &dd, 0));
       }

@@ -210,6 +210,8 @@ struct CtxBase {
   virtual int check_finite(int *ok) = 0;
   virtual int read_value(const void *p, double *out) = 0;
   virtual int64_t cells() = 0;
+  virtual int dft_dot(size_t npairs, const void *const *a, const void *const *b, int Nomega, double *out) = 0;
+  virtual int integrate_dot(size_t n, const meepcu_integrate_desc *pc, double *sum, double *maxabs) = 0;
 };
 
 template <class T> struct Susc {
@@ -1566,6 +1568,86 @@ template <class T> struct Impl : CtxBase {
     return MEEPCU_OK;
   }
 
+
+  // dft_flux::flux, src/dft.cpp:533-548 (and the sums of dft_energy::electric / magnetic, :657-687): the
+  // reference's loop nest and accumulation order (pairs in list order, points, frequencies; double accumulators)
+  int dft_dot(size_t npairs, const void *const *a, const void *const *b, int Nomega, double *out) {
+    if (Nomega <= 0 || !out || (npairs && (!a || !b))) return fail(MEEPCU_EINVAL, "bad argument");
+    for (int i = 0; i < Nomega; ++i) out[i] = 0;
+    for (size_t p = 0; p < npairs; ++p) {
+      size_t N = 0;
+      bool found_a = false, found_b = false;
+      for (size_t ic = 0; ic < chunks.size(); ++ic)
+        for (size_t id = 0; id < chunks[ic].dfts.size(); ++id) {
+          const Dft<T> &D = chunks[ic].dfts[id];
+          if ((const void *)D.dft == a[p] && D.d.Nomega == Nomega) { N = D.N; found_a = true; }
+          if ((const void *)D.dft == b[p] && D.d.Nomega == Nomega) found_b = found_b || true;
+        }
+      if (!found_a || !found_b) return fail(MEEPCU_EINVAL, "pair %zu: not dft_chunk::dft arrays registered by meepcu_add_dft", p);
+      const std::complex<T> *ea = (const std::complex<T> *)a[p], *eb = (const std::complex<T> *)b[p];
+      for (size_t k = 0; k < N; ++k)
+        for (int i = 0; i < Nomega; ++i) out[i] += real(ea[k * Nomega + i] * conj(eb[k * Nomega + i]));
+    }
+    return MEEPCU_OK;
+  }
+
+  // integrate_chunkloop with two components and dot_integrand, src/integrate.cpp:47-131,
+  // src/energy_and_flux.cpp:61-65: one long double sum per piece, added to the double total piece by piece
+  int integrate_dot(size_t n, const meepcu_integrate_desc *pc, double *sum_out, double *maxabs_out) {
+    if (!sum_out || (n && !pc)) return fail(MEEPCU_EINVAL, "null argument");
+    std::complex<double> total = 0.0;
+    double total_max = 0;
+    for (size_t ip = 0; ip < n; ++ip) {
+      const meepcu_integrate_desc &d = pc[ip];
+      const Chunk<T> *chp = 0;
+      for (size_t ic = 0; ic < chunks.size() && !chp; ++ic)
+        for (int c = 0; c < 20 && !chp; ++c)
+          for (int cmp = 0; cmp < 2; ++cmp) {
+            const void *probe = d.f[0][0] ? d.f[0][0] : d.f[1][0];
+            if (probe && chunks[ic].d.f[c][cmp] == probe) chp = &chunks[ic];
+          }
+      if (!chp) {
+        if (!d.f[0][0] && !d.f[1][0]) continue;
+        return fail(MEEPCU_EINVAL, "piece %zu: not field arrays of a registered chunk", ip);
+      }
+      const Grid &g = chp->g;
+      Loop L(g, d.is, d.ie);
+      std::complex<long double> sum = 0.0;
+      double maxabs = 0;
+      std::complex<double> ph[2] = {std::complex<double>(d.ph[0][0], d.ph[0][1]), std::complex<double>(d.ph[1][0], d.ph[1][1])};
+      std::complex<T> fvals[2];
+      OLOOP(L, idx) {
+        for (int i = 0; i < 2; ++i) {
+          double f[2];
+          for (int k = 0; k < 2; ++k) {
+            const T *ff = (const T *)d.f[i][k];
+            if (ff)
+              f[k] = 0.25 * (ff[idx] + ff[idx + d.off[i][0]] + ff[idx + d.off[i][1]] + ff[idx + d.off[i][0] + d.off[i][1]]);
+            else
+              f[k] = 0;
+          }
+          fvals[i] = std::complex<double>(f[0], f[1]) * ph[i];
+        }
+        const std::complex<double> integrand =
+            real(conj(std::complex<double>(fvals[0])) * std::complex<double>(fvals[1]));
+        maxabs = std::max(maxabs, abs(integrand));
+        const ptrdiff_t li[3] = {loop_i1, loop_i2, loop_i3};
+        double w1[3];
+        for (int k = 0; k < 3; ++k) { // IVEC_LOOP_WEIGHT, src/meep/vec.hpp:372-383
+          const ptrdiff_t i = li[k], nn = L.n[k];
+          const int dir = L.dir[k];
+          w1[k] = (i > 1 && i < nn - 2) ? 1.0
+                                        : (i == 0 ? d.s0[dir] : (i == 1 ? d.s1[dir] : i == nn - 1 ? d.e0[dir] : (i == nn - 2 ? d.e1[dir] : 1.0)));
+        }
+        sum += integrand * (w1[2] * (w1[1] * ((d.dV0 + d.dV1 * loop_i2) * w1[0])));
+      }
+      total_max = std::max(total_max, maxabs);
+      total += sum;
+    }
+    *sum_out = total.real();
+    if (maxabs_out) *maxabs_out = total_max;
+    return MEEPCU_OK;
+  }
   int check_finite(int *ok) {
     *ok = 1;
     for (size_t ic = 0; ic < chunks.size(); ++ic)
@@ -1742,6 +1824,20 @@ int meepcu_read_values(meepcu_ctx *ctx, size_t n, const void *const *host_ptrs, 
     if (rc) return rc;
   }
   return MEEPCU_OK;
+}
+int meepcu_get_compulsory_bytes(meepcu_ctx *ctx, int64_t *per_step, int64_t *, int, int *n) {
+  CHECK_CTX;
+  if (per_step) *per_step = 0;
+  if (n) *n = 0;
+  return MEEPCU_OK;
+}
+int meepcu_dft_dot(meepcu_ctx *ctx, size_t npairs, const void *const *a, const void *const *b, int Nomega, double *out) {
+  CHECK_CTX;
+  return ctx->impl->dft_dot(npairs, a, b, Nomega, out);
+}
+int meepcu_integrate_dot(meepcu_ctx *ctx, size_t npieces, const meepcu_integrate_desc *pieces, double *sum, double *maxabs) {
+  CHECK_CTX;
+  return ctx->impl->integrate_dot(npieces, pieces, sum, maxabs);
 }
 int meepcu_get_timers(meepcu_ctx *ctx, double out[22]) {
   CHECK_CTX;

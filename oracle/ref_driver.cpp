@@ -574,6 +574,23 @@ static std::vector<double> flux_spectra(problem *p) {
     out.insert(out.end(), fl, fl + p->fluxes[k].freq.size());
     delete[] fl;
   }
+  for (size_t k = 0; k < p->energies.size(); ++k) { // dft_energy::electric / magnetic (dft.cpp:657-687)
+    double *el = p->energies[k].electric(), *mg = p->energies[k].magnetic();
+    out.insert(out.end(), el, el + p->energies[k].freq.size());
+    out.insert(out.end(), mg, mg + p->energies[k].freq.size());
+    delete[] el;
+    delete[] mg;
+  }
+  return out;
+}
+// the energy / flux integrals of energy_and_flux.cpp on the whole cell and through its mid plane
+static std::vector<double> box_integrals(problem *p) {
+  std::vector<double> out;
+  out.push_back(p->f->electric_energy_in_box(p->gv.surroundings()));
+  out.push_back(p->f->magnetic_energy_in_box(p->gv.surroundings()));
+  out.push_back(p->f->field_energy_in_box(p->gv.surroundings())); // synchronizes the magnetic fields around the H part
+  const direction dn = p->gv.dim == D3 ? Z : (p->gv.dim == D2 ? Y : Z);
+  out.push_back(p->f->flux_in_box(dn, mid_plane(p->gv)));
   return out;
 }
 static size_t count_diff(const std::vector<double> &a, const std::vector<double> &b) {
@@ -745,12 +762,13 @@ int main(int argc, char **argv) {
     for (int i = 0; i < warmup; ++i) { A->f->step(); B->f->step(); } // drop-in off: both on the CPU
     double t0 = wall_time();
     double mid_ref = 0, mid_abi = 0, mid_energy_ref = 0, mid_energy_abi = 0;
-    std::vector<double> flux_mid_ref, flux_mid_abi, flux_end_ref, flux_end_abi;
+    std::vector<double> flux_mid_ref, flux_mid_abi, flux_end_ref, flux_end_abi, box_ref, box_abi;
     for (int i = 0; i < steps; ++i) {
       A->f->step();
       if (i == steps / 2) {
         mid_ref = probe_value(A);
         mid_energy_ref = A->f->electric_energy_in_box(A->gv.surroundings());
+        box_ref = box_integrals(A);
         flux_mid_ref = flux_spectra(A);
         for (size_t k = 0; k < A->fluxes.size(); ++k) A->fluxes[k].scale_dfts(std::complex<double>(0.5, 0.25)); // a host-side WRITER of dft[]
       }
@@ -772,6 +790,7 @@ int main(int argc, char **argv) {
       if (i == steps / 2) { // host-side readers in mid-run, called like any user would: the patched get_field and
         mid_abi = probe_value(B); // loop_in_chunks (behind electric_energy_in_box) fetch the device's state themselves
         mid_energy_abi = B->f->electric_energy_in_box(B->gv.surroundings());
+        box_abi = box_integrals(B); // the integrals are formed on the device (meepcu_integrate_dot): nothing is downloaded
         // DFT consumers straight on the patched reference: dft_flux::flux() fetches the accumulators (only them)
         // from the device; scale_dfts() changes them on the host and the next step() sends them back
         flux_mid_abi = flux_spectra(B);
@@ -819,12 +838,15 @@ int main(int argc, char **argv) {
             "\"probe_abi\":%.17g,\"probe_mid\":%.17g,\"attached\":%d,\"t_ref\":%d,\"t_abi\":%d,"
             "\"sync_checks\":%zu,\"sync_mismatched_elements\":%zu,\"probe_mid_ref\":%.17g,"
             "\"energy_mid_ref\":%.17g,\"energy_mid_abi\":%.17g,\"flux_values\":%zu,\"flux_mid_mismatched\":%zu,"
-            "\"flux_end_mismatched\":%zu,\"flux_mid_rel\":%.6g,\"flux_end_rel\":%.6g}\n",
+            "\"flux_end_mismatched\":%zu,\"flux_mid_rel\":%.6g,\"flux_end_rel\":%.6g,\"box_values\":%zu,"
+            "\"box_mismatched\":%zu,\"box_rel\":%.6g,\"device_dft_dots\":%zu,\"device_integrals\":%zu,\"launches_abi\":%ld}\n",
             "dropin", cas.c_str(), (int)sizeof(realnum), steps, warmup, A->cells, A->f->num_chunks, r.narrays,
             r.nelems, r.nmismatch_arrays, r.nmismatch_elems, r.max_abs, relL2, r.first_bad.c_str(), t1 - t0,
             t2 - t1, probe_value(A), probe_value(B), mid_abi, (int)attached, A->f->t, B->f->t, sync_checks, sync_bad,
             mid_ref, mid_energy_ref, mid_energy_abi, flux_end_ref.size(), count_diff(flux_mid_ref, flux_mid_abi),
-            count_diff(flux_end_ref, flux_end_abi), rel_diff(flux_mid_ref, flux_mid_abi), rel_diff(flux_end_ref, flux_end_abi));
+            count_diff(flux_end_ref, flux_end_abi), rel_diff(flux_mid_ref, flux_mid_abi), rel_diff(flux_end_ref, flux_end_abi),
+            box_ref.size(), count_diff(box_ref, box_abi), rel_diff(box_ref, box_abi), meepcu::attachment::device_reductions(0),
+            meepcu::attachment::device_reductions(1), 0L);
     delete A;
     delete B; // ~fields() -> gpu_detach()
   }

@@ -27,11 +27,12 @@ int main(int argc, char **argv) {
   meepcu_src_sample smp;
   meepcu_stats st;
   meepcu_kernel_time kt;
+  meepcu_integrate_desc idsc;
   int (*abi_version)(void);
   if (argc < 2) return 2;
   memset(&cfg, 0, sizeof cfg); memset(&cd, 0, sizeof cd); memset(&sd, 0, sizeof sd); memset(&gd, 0, sizeof gd);
   memset(&src, 0, sizeof src); memset(&dd, 0, sizeof dd); memset(&smp, 0, sizeof smp); memset(&st, 0, sizeof st);
-  memset(&kt, 0, sizeof kt);
+  memset(&kt, 0, sizeof kt); memset(&idsc, 0, sizeof idsc);
   h = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);
   if (!h) { fprintf(stderr, "%s\n", dlerror()); return 3; }
   SYM(meepcu_last_error); SYM(meepcu_backend); SYM(meepcu_abi_version); SYM(meepcu_create); SYM(meepcu_destroy);
@@ -42,6 +43,7 @@ int main(int argc, char **argv) {
   SYM(meepcu_sync_to_host); SYM(meepcu_sync_from_host); SYM(meepcu_sync_subset); SYM(meepcu_get_time);
   SYM(meepcu_set_time); SYM(meepcu_check_finite); SYM(meepcu_read_value); SYM(meepcu_read_values);
   SYM(meepcu_get_timers); SYM(meepcu_get_stats); SYM(meepcu_set_profiling); SYM(meepcu_get_kernel_times);
+  SYM(meepcu_dft_dot); SYM(meepcu_integrate_dot); SYM(meepcu_get_compulsory_bytes);
   *(void **)(&abi_version) = dlsym(h, "meepcu_abi_version");
   printf("{\"symbols\": %d, \"missing\": %d, \"abi\": %d, \"header_abi\": %d, \"sizeof_config\": %d, "
          "\"sizeof_chunk_desc\": %d, \"sizeof_gyrotropic_desc\": %d}\n",

@@ -39,6 +39,11 @@ def test_patched_reference_steps_through_the_abi(case):
     assert d["flux_mid_mismatched"] == 0 and d["flux_end_mismatched"] == 0, d
     if case in ("lorentz3d:16", "dft3d:12"):
         assert d["flux_values"] > 0
+        # ... and they were SUMMED behind the ABI (meepcu_dft_dot), not fetched: dft_flux::flux, dft_energy::electric/magnetic
+        assert d["device_dft_dots"] > 0
+    # energy_and_flux.cpp's integrals (electric / magnetic / field_energy_in_box, flux_in_box with its synchronize /
+    # restore pair) were formed behind the ABI too (meepcu_integrate_dot): same bits as the reference's own loops
+    assert d["box_values"] == 4 and d["box_mismatched"] == 0 and d["device_integrals"] >= 10, d
 
 
 @pytest.mark.gpu
@@ -53,13 +58,16 @@ def test_patched_reference_steps_on_the_gpu(case, tol):
     # (stale or zero spectra would show here), before and after a host-side scale_dfts()
     assert d["flux_mid_rel"] <= tol and d["flux_end_rel"] <= tol, d
     if case.startswith("lorentz3d"):
-        assert d["flux_values"] > 0
+        assert d["flux_values"] > 0 and d["device_dft_dots"] > 0
+    # the box integrals are reduced on the GPU (k_integrate_dot): double tree sums against the reference's long double loop
+    assert d["box_values"] == 4 and d["device_integrals"] >= 10 and d["box_rel"] <= tol, d
 
 
 @pytest.mark.gpu
 def test_flux_spectrum_read_from_the_device():
     d = run(CUDA_LIB, "dft3d:16", 60)
     assert d["flux_values"] > 0 and d["flux_mid_rel"] <= 1e-12 and d["flux_end_rel"] <= 1e-12, d
+    assert d["device_dft_dots"] > 0 and d["box_rel"] <= 1e-12  # k_dft_dot / k_integrate_dot, incl. the centred-grid averages of flux_in_box
     assert d["rel_l2"] <= 1e-12
 
 
