@@ -67,7 +67,7 @@ typedef struct {
   int abi_version;   /* MEEPCU_ABI_VERSION */
   int realnum_bytes; /* sizeof(realnum): 8, or 4 for the --enable-single build (meep.hpp:42-46) */
   int is_real;       /* fields::is_real: 1 = only cmp 0 exists */
-  int dim;           /* grid_volume::dim (D1/D2/D3; Dcyl -> MEEPCU_EUNSUPPORTED) */
+  int dim;           /* grid_volume::dim (D1/D2/D3/Dcyl) */
   double a;          /* resolution */
   double dt;         /* fields::dt = Courant/a */
   double courant;    /* fields_chunk::Courant: the dt/dx factor passed to step_curl (step_db.cpp:125) */
@@ -78,7 +78,9 @@ typedef struct {
   int pin_host;      /* 1: page-lock the caller's big arrays in place (cudaHostRegister) for the life of the
                         context, so that meepcu_sync_* are plain DMA at PCIe speed; the arrays must then
                         outlive the context.  0: copy through library-owned pinned staging buffers. */
-  int reserved[6];
+  double m;          /* fields::m, the exp(i m phi) order of a cylindrical (Dcyl) simulation (step_db.cpp:178-290) */
+  int zero_fields_near_cylorigin; /* fields::zero_fields_near_cylorigin (step_db.cpp:404-440) */
+  int reserved[3];
   double bfast_scaled_k[3]; /* fields::bfast_scaled_k (X,Y,Z), all zero = no BFAST terms (step_db.cpp:65,129-143) */
 } meepcu_config;
 
@@ -87,8 +89,9 @@ typedef struct {
  * (src/vec.cpp:293-296,482-494).  A NULL pointer means "not allocated" exactly as in the
  * reference; f[Hc]==f[Bc] means H aliases B (src/fields.cpp:493-517). */
 typedef struct {
-  int num[3];   /* grid_volume::num_direction(X,Y,Z); 0 for absent directions */
-  int io[3];    /* grid_volume::little_corner(), half-pixel units, X,Y,Z */
+  int num[3];   /* grid_volume::num_direction(X,Y,Z); 0 for absent directions.  Dcyl: slot 0 = R, slot 2 = Z (the
+                   reference's own num[d % 3] layout, vec.hpp:1014-1020), here and in every is/ie/s0.. triple below */
+  int io[3];    /* grid_volume::little_corner(), half-pixel units, X,Y,Z (Dcyl: R,-,Z) */
   void *f[MEEPCU_NUM_COMPONENTS][2];      /* fields_chunk::f        */
   void *f_u[MEEPCU_NUM_COMPONENTS][2];    /* fields_chunk::f_u      (PML, integrated from D/B) */
   void *f_w[MEEPCU_NUM_COMPONENTS][2];    /* fields_chunk::f_w      (PML, E/H integrated from W) */

@@ -32,7 +32,8 @@ class Config(C.Structure):
     _fields_ = [("abi_version", C.c_int), ("realnum_bytes", C.c_int), ("is_real", C.c_int),
                 ("dim", C.c_int), ("a", C.c_double), ("dt", C.c_double), ("courant", C.c_double),
                 ("beta", C.c_double), ("nl_mode", C.c_int), ("device", C.c_int), ("t", C.c_int),
-                ("pin_host", C.c_int), ("reserved", C.c_int * 6),
+                ("pin_host", C.c_int), ("m", C.c_double), ("zero_fields_near_cylorigin", C.c_int),
+                ("reserved", C.c_int * 3),
                 ("bfast_scaled_k", C.c_double * 3)]
 
 

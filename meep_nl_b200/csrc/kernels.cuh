@@ -1756,7 +1756,7 @@ __global__ void __launch_bounds__(kThreads) k_eh_mask(unsigned char *__restrict_
 }
 
 #ifndef MCU_EH_CTAS
-#define MCU_EH_CTAS 5 // Newton-Raphson is latency-bound: measured 2.73 / 2.13 / 2.02 / 1.65 / 1.75 ms at 2 / 3 / 4 / 5 / 6 CTAs per SM (256^3)
+#define MCU_EH_CTAS 4 // Newton-Raphson is latency-bound.  With the L2 prefetch of the operands (r02g, 384^3, ms per launch): 5.13 / 4.34 / 4.81 at 3 / 4 / 5 CTAs per SM (before the prefetch 5 CTAs were best: 4.56)
 #endif
 template <class T, int CTAS = MCU_EH_CTAS>
 __global__ void __launch_bounds__(kThreads, CTAS)
@@ -1951,50 +1951,38 @@ template <class T> struct DftParams {
 };
 struct DftWork {
   int param;
-  long long e0; // first element (point*Nomega + omega) of this CTA
+  int npts;      // points of this CTA (<= kDftMaxPts)
+  long long pt0; // first point (IVEC_LOOP_COUNTER) of this CTA
 };
 
 template <class T> struct CplxOf;
 template <> struct CplxOf<double> { typedef double2 type; };
 template <> struct CplxOf<float> { typedef float2 type; };
-constexpr int kDftPerThread = 4; // accumulator elements per thread, kThreads apart (DftWork covers kThreads * this)
+constexpr int kDftMaxPts = 1024;     // points per CTA at most (their weighted field values live in shared memory)
+constexpr int kDftElemsPerCta = 4096; // accumulator elements per CTA aimed at: npts = clamp(kDftElemsPerCta / Nomega, 1, kDftMaxPts)
+constexpr int kDftUnroll = 4;         // accumulator loads in flight per thread
 
-// Each thread owns kDftPerThread (point, omega) elements: the complex accumulator moves as ONE 16-byte (fp64) /
-// 8-byte (fp32) access, all accumulator loads of a thread are in flight before the first store, and the index
-// arithmetic is 32-bit where the region allows it.  Per element the operations are those of dft.cpp:295-305.
+// A CTA owns `npts` consecutive points = npts * Nomega CONSECUTIVE complex accumulators.  Phase 1: one thread per point
+// evaluates the weighted (and averaged) field value once -- index decomposition, IVEC_LOOP_WEIGHT, up to four field
+// loads -- and parks it in shared memory.  Phase 2: the threads stream the accumulator block with 16-byte (fp64) /
+// 8-byte (fp32) accesses, kDftUnroll loads in flight, (point, omega) of an element advanced incrementally -- per
+// element two multiplies, two adds, one load and one store.  (Until r02 every (point, omega) element recomputed the
+// point's weight and field value: Nomega times the arithmetic, issue-bound at half the HBM rate.)  Per element the
+// operations are those of dft.cpp:295-305, so the accumulators are bit-identical.
 template <class T>
 __global__ void __launch_bounds__(kThreads)
     k_dft(const DftParams<T> *__restrict__ params, const DftWork *__restrict__ work,
           const T *__restrict__ phases, const int *__restrict__ phase_off,
           const unsigned char *__restrict__ active) {
   typedef typename CplxOf<T>::type CT;
+  __shared__ T sf[2][kDftMaxPts];
   const DftWork wk = work[blockIdx.x];
   if (!active[wk.param]) return; // decimation: dft.cpp:259
   const DftParams<T> &q = params[wk.param];
-  const long long total = q.N * q.Nomega;
   const int Nw = q.Nomega, n2 = q.n[1], n3 = q.n[2];
   const int numcmp = q.f1 ? 2 : 1;
-  const T *phb = phases + 2 * phase_off[q.phase_group];
-  CT acc[kDftPerThread];
-  T f0[kDftPerThread], f1[kDftPerThread], pr[kDftPerThread], pi[kDftPerThread];
-  bool on[kDftPerThread];
-#pragma unroll
-  for (int k = 0; k < kDftPerThread; ++k) {
-    const long long e = wk.e0 + threadIdx.x + (long long)k * kThreads;
-    on[k] = e < total;
-    if (!on[k]) continue;
-    acc[k] = *reinterpret_cast<const CT *>(q.dft + 2 * e); // the dominant traffic: issued first
-    long long pt;
-    int iw;
-    if (total < (1LL << 31)) {
-      const unsigned eu = (unsigned)e;
-      pt = eu / (unsigned)Nw;
-      iw = (int)(eu - (unsigned)pt * (unsigned)Nw);
-    }
-    else {
-      pt = e / Nw;
-      iw = (int)(e - pt * Nw);
-    }
+  for (int t = threadIdx.x; t < wk.npts; t += kThreads) {
+    const long long pt = wk.pt0 + t;
     int i1, i2, i3;
     if (q.N < (1LL << 31)) {
       const unsigned p = (unsigned)pt, r = p / (unsigned)n3;
@@ -2037,25 +2025,48 @@ __global__ void __launch_bounds__(kThreads)
       else
         f[cmp] = w * ff[idx];
     }
-    f0[k] = f[0];
-    f1[k] = f[1];
-    pr[k] = phb[2 * iw];
-    pi[k] = phb[2 * iw + 1];
+    sf[0][t] = f[0];
+    sf[1][t] = f[1];
   }
+  __syncthreads();
+  const T *__restrict__ phb = phases + 2 * phase_off[q.phase_group];
+  CT *__restrict__ acc0 = reinterpret_cast<CT *>(q.dft) + wk.pt0 * Nw;
+  const int n = wk.npts * Nw;
+  const int dp = kThreads / Nw, dw = kThreads - dp * Nw; // (point, omega) advance of one stride of kThreads elements
+  int e = threadIdx.x;
+  int pt = e / Nw, iw = e - pt * Nw;
+  while (e < n) {
+    CT a[kDftUnroll];
+    int pts[kDftUnroll], iws[kDftUnroll];
 #pragma unroll
-  for (int k = 0; k < kDftPerThread; ++k) {
-    if (!on[k]) continue;
-    const long long e = wk.e0 + threadIdx.x + (long long)k * kThreads;
-    CT d = acc[k];
-    if (numcmp == 2) { // complex<realnum> product, dft.cpp:295-299
-      d.x = d.x + (pr[k] * f0[k] - pi[k] * f1[k]);
-      d.y = d.y + (pr[k] * f1[k] + pi[k] * f0[k]);
+    for (int k = 0; k < kDftUnroll; ++k) {
+      const int ek = e + k * kThreads;
+      pts[k] = pt;
+      iws[k] = iw;
+      if (ek < n) a[k] = acc0[ek]; // the dominant traffic: every load of the batch before the first store
+      pt += dp;
+      iw += dw;
+      if (iw >= Nw) { iw -= Nw; ++pt; }
     }
-    else { // :300-305
-      d.x = d.x + f0[k] * pr[k];
-      d.y = d.y + f0[k] * pi[k];
+#pragma unroll
+    for (int k = 0; k < kDftUnroll; ++k) {
+      const int ek = e + k * kThreads;
+      if (ek >= n) break;
+      const T pr = phb[2 * iws[k]], pi = phb[2 * iws[k] + 1];
+      const T f0 = sf[0][pts[k]];
+      CT d = a[k];
+      if (numcmp == 2) { // complex<realnum> product, dft.cpp:295-299
+        const T f1 = sf[1][pts[k]];
+        d.x = d.x + (pr * f0 - pi * f1);
+        d.y = d.y + (pr * f1 + pi * f0);
+      }
+      else { // :300-305
+        d.x = d.x + f0 * pr;
+        d.y = d.y + f0 * pi;
+      }
+      acc0[ek] = d;
     }
-    *reinterpret_cast<CT *>(q.dft + 2 * e) = d;
+    e += kDftUnroll * kThreads;
   }
 }
 

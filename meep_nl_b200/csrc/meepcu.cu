@@ -2304,8 +2304,9 @@ template <class T> struct Ctx : CtxBase {
         dft_decim.push_back(d.decimation_factor);
         dft_is_h.push_back(is_h);
         const long long ne = q.N * q.Nomega;
-        for (long long e0 = 0; e0 < ne; e0 += (long long)kThreads * kDftPerThread) {
-          DftWork w = {pidx, e0};
+        const long long per = std::max<long long>(1, std::min<long long>(kDftMaxPts, kDftElemsPerCta / std::max(1, d.Nomega)));
+        for (long long p0 = 0; p0 < q.N; p0 += per) {
+          DftWork w = {pidx, (int)std::min<long long>(per, q.N - p0), p0};
           work.push_back(w);
         }
         alg_bytes += 4LL * ne * (long long)sizeof(T) / d.decimation_factor;
@@ -2694,13 +2695,13 @@ template <class T> struct Ctx : CtxBase {
       }
       if (n_eh_tiles[half]) { // (the flag is global: this rank may own no such chunk)
         RC(prof_begin(KC_EH_GENERAL));
-        // resident CTAs per SM (= registers per thread): 5 x 48 registers measured best while every point paid the
-        // neighbour loads; MEEPCU_EH_CTAS = 2 / 3 / 4 select builds with 128 / 80 / 64 registers
+        // resident CTAs per SM (= registers per thread): MEEPCU_EH_CTAS = 2 / 3 / 4 / 5 select builds with 128 / 80 / 64 /
+        // 48 registers (measurements at MCU_EH_CTAS in kernels.cuh)
         static const int eh_ctas = getenv("MEEPCU_EH_CTAS") ? atoi(getenv("MEEPCU_EH_CTAS")) : MCU_EH_CTAS;
         if (eh_ctas == 2) k_eh_general<T, 2><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
         else if (eh_ctas == 3) k_eh_general<T, 3><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
-        else if (eh_ctas == 4) k_eh_general<T, 4><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
-        else k_eh_general<T, MCU_EH_CTAS><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
+        else if (eh_ctas == 5) k_eh_general<T, 5><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
+        else k_eh_general<T, 4><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
         RC(prof_end());
         launches++;
       }

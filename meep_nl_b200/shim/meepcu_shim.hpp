@@ -48,6 +48,17 @@
 namespace meepcu {
 
 // ---- the ABI, resolved at run time so that libmeep does not link against CUDA ----------------
+// direction of slot k of every X,Y,Z triple of the ABI: Cartesian X,Y,Z; cylindrical R,-,Z (grid_volume keeps
+// num[d % 3], vec.hpp:1014-1020)
+inline meep::direction slot_direction(meep::ndim dim, int k) {
+  if (dim == meep::Dcyl) return k == 0 ? meep::R : (k == 2 ? meep::Z : meep::NO_DIRECTION);
+  return (meep::direction)k;
+}
+inline bool slot_present(meep::ndim dim, int k) {
+  const meep::direction d = slot_direction(dim, k);
+  return d != meep::NO_DIRECTION && meep::has_direction(dim, d);
+}
+
 struct api {
   void *handle;
 #define MEEPCU_FN(name) decltype(&::meepcu_##name) name;
@@ -238,7 +249,8 @@ public:
                                           void *data_) {
     using namespace meep;
     integrate_collect *data = (integrate_collect *)data_;
-    static const direction xyz[3] = {X, Y, Z};
+    direction xyz[3];
+    for (int k = 0; k < 3; ++k) xyz[k] = slot_direction(fc->gv.dim, k);
     meepcu_integrate_desc d;
     memset(&d, 0, sizeof d);
     for (int i = 0; i < 2; ++i) {
@@ -254,22 +266,20 @@ public:
       d.f[i][1] = fc->f[c][1];
     }
     for (int k = 0; k < 3; ++k) {
-      const bool has = has_direction(fc->gv.dim, xyz[k]);
+      const bool has = slot_present(fc->gv.dim, k);
       d.is[k] = has ? is.in_direction(xyz[k]) : 0;
       d.ie[k] = has ? ie.in_direction(xyz[k]) : 0;
-      d.s0[k] = s0.in_direction(xyz[k]);
-      d.s1[k] = s1.in_direction(xyz[k]);
-      d.e0[k] = e0.in_direction(xyz[k]);
-      d.e1[k] = e1.in_direction(xyz[k]);
+      d.s0[k] = has ? s0.in_direction(xyz[k]) : 0;
+      d.s1[k] = has ? s1.in_direction(xyz[k]) : 0;
+      d.e0[k] = has ? e0.in_direction(xyz[k]) : 0;
+      d.e1[k] = has ? e1.in_direction(xyz[k]) : 0;
     }
     d.dV0 = dV0;
     d.dV1 = dV1;
     data->pieces.push_back(d);
   }
-  // false: Dcyl (not on the device) -- the caller integrates on the host as before
   bool integrate_dot(const meep::component *cs, const meep::volume &where, double *out) {
     using namespace meep;
-    if (f.gv.dim == Dcyl) return false;
     bool same_grid = f.gv.iyee_shift(cs[1]) == f.gv.iyee_shift(cs[0]); // integrate.cpp:136-146
     integrate_collect data;
     data.cs = cs;
@@ -479,7 +489,6 @@ private:
 
   void describe(int nl_mode, int device) {
     using namespace meep;
-    if (f.gv.dim == Dcyl) meep::abort("meepcu: cylindrical coordinates are outside the GPU path");
     if (f.is_phasing()) meep::abort("meepcu: phase_material is outside the GPU path");
     for (int i = 0; i < f.num_chunks; i++)
       if (!f.chunks[i]->is_mine())
@@ -496,6 +505,8 @@ private:
     cfg.dt = f.dt;
     cfg.courant = f.num_chunks ? f.chunks[0]->Courant : f.dt * f.a;
     cfg.beta = f.beta;
+    cfg.m = f.m;
+    cfg.zero_fields_near_cylorigin = f.num_chunks ? f.chunks[0]->zero_fields_near_cylorigin : 1; // a fields_chunk member (meep.hpp:1504)
     for (int k = 0; k < 3 && k < (int)f.bfast_scaled_k.size(); ++k) cfg.bfast_scaled_k[k] = f.bfast_scaled_k[k];
     cfg.nl_mode = nl_mode;
     cfg.device = device;
@@ -516,10 +527,11 @@ private:
       const grid_volume &gv = fc->gv;
       meepcu_chunk_desc d;
       memset(&d, 0, sizeof d);
-      const direction xyz[3] = {X, Y, Z};
+      direction xyz[3];
       for (int k = 0; k < 3; ++k) {
-        d.num[k] = has_direction(gv.dim, xyz[k]) ? gv.num_direction(xyz[k]) : 0;
-        d.io[k] = has_direction(gv.dim, xyz[k]) ? gv.little_corner().in_direction(xyz[k]) : 0;
+        xyz[k] = slot_direction(gv.dim, k);
+        d.num[k] = slot_present(gv.dim, k) ? gv.num_direction(xyz[k]) : 0;
+        d.io[k] = slot_present(gv.dim, k) ? gv.little_corner().in_direction(xyz[k]) : 0;
       }
       FOR_COMPONENTS(c) {
         for (int cmp = 0; cmp < 2; ++cmp) {
@@ -638,13 +650,13 @@ private:
         memset(&dd, 0, sizeof dd);
         dd.c = (int)dc->c;
         for (int k = 0; k < 3; ++k) {
-          const bool has = has_direction(gv.dim, xyz[k]);
+          const bool has = slot_present(gv.dim, k);
           dd.is[k] = has ? dc->is.in_direction(xyz[k]) : 0;
           dd.ie[k] = has ? dc->ie.in_direction(xyz[k]) : 0;
-          dd.s0[k] = dc->s0.in_direction(xyz[k]);
-          dd.s1[k] = dc->s1.in_direction(xyz[k]);
-          dd.e0[k] = dc->e0.in_direction(xyz[k]);
-          dd.e1[k] = dc->e1.in_direction(xyz[k]);
+          dd.s0[k] = has ? dc->s0.in_direction(xyz[k]) : 0;
+          dd.s1[k] = has ? dc->s1.in_direction(xyz[k]) : 0;
+          dd.e0[k] = has ? dc->e0.in_direction(xyz[k]) : 0;
+          dd.e1[k] = has ? dc->e1.in_direction(xyz[k]) : 0;
         }
         dd.dV0 = dc->dV0;
         dd.dV1 = dc->dV1;

@@ -93,9 +93,25 @@ inline int dir_comp(int c, int d) { // direction_component(c, d)
   static const int off[5] = {0, 1, 4, 2, 3};
   return (c / 5) * 5 + off[d];
 }
-inline int cycle_dir(int d, int shift) { return (d + shift + 99) % 3; } // cartesian only
-inline bool cross_negative(int a, int b) { return ((3 + b - a) % 3) == 2; }
-inline int cross(int a, int b) { return (3 + 2 * a - b) % 3; }
+inline int cycle_dir(int dim, int d, int shift) { // cycle_direction, src/meep/vec.hpp:586-589 (R -> P -> Z -> R in Dcyl)
+  const int start = dim == MEEPCU_Dcyl ? 2 : 0;
+  return (d - start + shift + 99) % 3 + start;
+}
+inline bool cross_negative(int a, int b) { // src/fields.cpp:411-415
+  if (a >= MEEPCU_R) a -= 3;
+  if (b >= MEEPCU_R) b -= 3;
+  return ((3 + b - a) % 3) == 2;
+}
+inline int cross(int a, int b) { // src/fields.cpp:417-425
+  const bool dcyl = a >= MEEPCU_R || b >= MEEPCU_R;
+  if (a >= MEEPCU_R) a -= 3;
+  if (b >= MEEPCU_R) b -= 3;
+  const int c = (3 + 2 * a - b) % 3;
+  return (dcyl && c < MEEPCU_Z) ? c + 3 : c;
+}
+// Grid arrays are indexed by SLOT = direction % 3 (X,R -> 0; Y,P -> 1; Z -> 2), the reference's own num[d % 3]
+// (src/meep/vec.hpp:1014-1020); in Dcyl slot 1 (P) has no extent
+inline int slot(int d) { return d % 3; }
 
 struct Grid { // the parts of grid_volume the hot path uses (src/meep/vec.hpp:1014-1178)
   int dim;
@@ -104,10 +120,15 @@ struct Grid { // the parts of grid_volume the hot path uses (src/meep/vec.hpp:10
   bool has[3];         // has_direction(dim, d)
   ptrdiff_t stride[3]; // set_strides, src/vec.cpp:482-494
   size_t ntot;         // update_ntot, src/vec.cpp:293-296
+  int sdir[3];         // the direction each slot stands for (Dcyl: R, P, Z)
   void init(int dim_, const int num_[3], const int io_[3]) {
     dim = dim_;
-    has[0] = has[1] = (dim == MEEPCU_D2 || dim == MEEPCU_D3);
-    has[2] = (dim == MEEPCU_D1 || dim == MEEPCU_D3);
+    has[0] = (dim == MEEPCU_D2 || dim == MEEPCU_D3 || dim == MEEPCU_Dcyl);
+    has[1] = (dim == MEEPCU_D2 || dim == MEEPCU_D3);
+    has[2] = (dim == MEEPCU_D1 || dim == MEEPCU_D3 || dim == MEEPCU_Dcyl);
+    sdir[0] = dim == MEEPCU_Dcyl ? MEEPCU_R : MEEPCU_X;
+    sdir[1] = dim == MEEPCU_Dcyl ? MEEPCU_P : MEEPCU_Y;
+    sdir[2] = MEEPCU_Z;
     for (int d = 0; d < 3; ++d) {
       num[d] = has[d] ? num_[d] : 0;
       io[d] = has[d] ? io_[d] : 0;
@@ -123,16 +144,21 @@ struct Grid { // the parts of grid_volume the hot path uses (src/meep/vec.hpp:10
   bool has_field(int c) const { // grid_volume::has_field
     if (dim == MEEPCU_D1) return c == 0 || c == 6 || c == 10 || c == 16; // Ex,Hy,Dx,By
     int d = comp_dir(c);
+    if (dim == MEEPCU_Dcyl) return d >= MEEPCU_Z; // Z, R, P
     return d < MEEPCU_R;
   }
-  int yee_shift(int c, int d) const { // iyee_shift(c).in_direction(d)
-    if (!has[d]) return 0;
-    int dc = comp_dir(c);
+  int yee_shift(int c, int sl) const { // iyee_shift(c).in_direction(direction of slot sl)
+    if (!has[sl]) return 0;
+    int dc = comp_dir(c), d = sdir[sl];
     if ((is_electric(c) || is_D(c)) && d == dc) return 1;
     if ((is_magnetic(c) || is_B(c)) && d != dc) return 1;
     return 0;
   }
-  int yucky_dir(int n) const { return dim == MEEPCU_D2 ? (n + 2) % 3 : n; } // src/vec.cpp:262-272
+  // slot of the n-th loop level, src/vec.cpp:262-272 (Dcyl: P, R, Z -- the P level has one iteration)
+  int yucky_dir(int n) const {
+    if (dim == MEEPCU_Dcyl) return n == 0 ? 1 : (n == 1 ? 0 : 2);
+    return dim == MEEPCU_D2 ? (n + 2) % 3 : n;
+  }
 };
 
 // LOOP_OVER_IVECS restated (src/meep/vec.hpp:151-168)
@@ -164,7 +190,8 @@ struct Loop {
 struct KIdx {
   int k0, s1, s2, s3;
   KIdx() : k0(0), s1(0), s2(0), s3(0) {}
-  KIdx(const Grid &g, int dsig, const int is[3]) {
+  KIdx(const Grid &g, int dsig_dir, const int is[3]) {
+    const int dsig = slot(dsig_dir);
     k0 = is[dsig] - g.io[dsig];
     s1 = g.yucky_dir(0) == dsig ? 2 : 0;
     s2 = g.yucky_dir(1) == dsig ? 2 : 0;
@@ -235,6 +262,7 @@ template <class T> struct Chunk {
   std::vector<SrcVol> sources[4]; // indexed by ft (only D_STUFF, B_STUFF used)
   std::vector<Dft<T> > dfts;    // in list order (newest first, like the reference's linked list)
   std::vector<T> fmp_store[MEEPCU_NUM_COMPONENTS][2]; // f_minus_p scratch (update_eh.cpp:94-103)
+  std::vector<T> rderiv;                              // fields_chunk::f_rderiv_int (step_db.cpp:93-118)
   // step plan (src/fields.cpp:441-469)
   bool have_plus[20], have_minus[20];
   int plus_c[20], minus_c[20], plus_d[20], minus_d[20];
@@ -320,8 +348,8 @@ template <class T> struct Impl : CtxBase {
               (is_magnetic(c1) && is_electric(c2)) || (is_B(c1) && is_electric(c2))))
           continue;
         int dc2 = comp_dir(c2);
-        if (dc1 >= MEEPCU_R || dc2 >= MEEPCU_R) continue; // no cylindrical support
-        if (dc1 != dc2 && ch.g.has_field(c2) && ch.g.has_field(c1) && ch.g.has[cross(dc1, dc2)]) {
+        if (dc1 != dc2 && ch.g.has_field(c2) && ch.g.has_field(c1) &&
+            (ch.g.has[slot(cross(dc1, dc2))] || cfg.dim == MEEPCU_Dcyl)) { // (every R, P, Z is a field direction in Dcyl)
           int dd = cross(dc1, dc2);
           if (cross_negative(dc2, dc1)) {
             ch.minus_c[c1] = c2;
@@ -441,6 +469,14 @@ template <class T> struct Impl : CtxBase {
     return tot;
   }
 
+  // gv.origin_r() * gv.a with the reference's roundings: origin = io * (0.5 * inva), inva = 1 / a
+  // (src/vec.cpp:38-41, src/meep/vec.hpp:1055)
+  double origin_r_times_a(const Grid &g) const {
+    const double inva = 1.0 / cfg.a;
+    const double origin_r = g.io[0] * (0.5 * inva);
+    return origin_r * cfg.a;
+  }
+
   // ---------------------------------------------------------------------------------------------
   // step_curl, src/step_generic.cpp:69-253.  The 16 hand-specialised loops of the reference are
   // the four stages below with absent terms dropped; each retained expression is written with
@@ -517,14 +553,39 @@ template <class T> struct Impl : CtxBase {
           if (!ch.F(cc, cmp)) continue;
           const int d_c = comp_dir(cc);
           const bool have_p = ch.have_plus[cc], have_m = ch.have_minus[cc];
-          const int dsig0 = cycle_dir(d_c, 1);
+          const int dsig0 = cycle_dir(cfg.dim, d_c, 1);
           const int dsig = ch.d.sigsize[dsig0] > 1 ? dsig0 : MEEPCU_NO_DIRECTION;
-          const int dsigu0 = cycle_dir(d_c, 2);
+          const int dsigu0 = cycle_dir(cfg.dim, d_c, 2);
           const int dsigu = ch.d.sigsize[dsigu0] > 1 ? dsigu0 : MEEPCU_NO_DIRECTION;
-          ptrdiff_t stride_p = have_p ? g.stride[ch.plus_d[cc]] : 0;
-          ptrdiff_t stride_m = have_m ? g.stride[ch.minus_d[cc]] : 0;
+          ptrdiff_t stride_p = have_p ? g.stride[slot(ch.plus_d[cc])] : 0;
+          ptrdiff_t stride_m = have_m ? g.stride[slot(ch.minus_d[cc])] : 0;
           const T *f_p = have_p ? ch.F(ch.plus_c[cc], cmp) : NULL;
           const T *f_m = have_m ? ch.F(ch.minus_c[cc], cmp) : NULL;
+          if (cfg.dim == MEEPCU_Dcyl) { // step_db.cpp:86-122
+            if (d_c == MEEPCU_R)
+              f_p = NULL; // im/r Fz term will be handled separately
+            else if (d_c == MEEPCU_Z) {
+              f_m = NULL; // im/r Fr term will be handled separately
+              // f_rderiv_int: the running sum over r of 1/r d(r Fp)/dr, so that the unmodified step_curl difference
+              // gives the cylindrical derivative (:93-118); realnum arithmetic, row by row like the reference
+              if (f_p) {
+                const int nr = g.num[0], nz = g.num[2];
+                std::vector<T> &S = ch.rderiv;
+                S.resize(g.ntot);
+                const T ir0 = (T)(origin_r_times_a(g) + 0.5 * g.yee_shift(ch.plus_c[cc], 0));
+                for (int iz = 0; iz <= nz; ++iz) S[iz] = 0;
+                const int sr = nz + 1;
+                for (int ir = 1; ir <= nr; ++ir) {
+                  const T rinv = 1.0 / ((ir + ir0) - 0.5);
+                  for (int iz = 0; iz <= nz; ++iz) {
+                    const ptrdiff_t idx = (ptrdiff_t)ir * sr + iz;
+                    S[idx] = S[idx - sr] + rinv * (f_p[idx] * (ir + ir0) - f_p[idx - sr] * ((ir - 1) + ir0));
+                  }
+                }
+                f_p = S.data();
+              }
+            }
+          }
           if (!f_p && !f_m) continue; // nothing to curl from (reference would dereference NULL)
           const T *cnd = (const T *)ch.d.conductivity[cc][d_c];
           const T *cndinv = (const T *)ch.d.condinv[cc][d_c];
@@ -576,9 +637,9 @@ template <class T> struct Impl : CtxBase {
             T *the_f = ch.F(cc, cmp);
             const T *gg = ch.F(c_g, 1 - cmp) ? ch.F(c_g, 1 - cmp) : ch.F(c_g, cmp);
             if (!the_f) continue; // the reference would dereference NULL
-            const int dsig0 = cycle_dir(d_c, 1);
+            const int dsig0 = cycle_dir(cfg.dim, d_c, 1);
             const int dsig = ch.d.sigsize[dsig0] > 1 ? dsig0 : MEEPCU_NO_DIRECTION;
-            const int dsigu0 = cycle_dir(d_c, 2);
+            const int dsigu0 = cycle_dir(cfg.dim, d_c, 2);
             const int dsigu = ch.d.sigsize[dsigu0] > 1 ? dsigu0 : MEEPCU_NO_DIRECTION;
             const T betadt = (T)(2 * kPi * cfg.beta * cfg.dt * (d_c == MEEPCU_X ? +1 : -1) *
                                  (ch.F(c_g, 1 - cmp) ? (ft == MEEPCU_D_STUFF ? -1 : +1) * (2 * cmp - 1) : 1));
@@ -591,6 +652,180 @@ template <class T> struct Impl : CtxBase {
                       dsigu, (const T *)ch.d.siginv[dsigu], (const T *)ch.d.condinv[cc][d_c],
                       (T *)ch.d.f_cond[cc][cmp]);
           }
+      }
+
+    // in cylindrical coordinates, add the i*m/r terms (src/step_db.cpp:177-290): f += (the_m / r) * g through the
+    // same PML / conductivity chain as step_beta, g = the OTHER cmp of the component the dropped derivative acted on
+    if (cfg.dim == MEEPCU_Dcyl && cfg.m != 0)
+      for (size_t ic = 0; ic < chunks.size(); ++ic) {
+        Chunk<T> &ch = chunks[ic];
+        const Grid &g = ch.g;
+        for (int cmp = 0; cmp < (cfg.is_real ? 1 : 2); ++cmp)
+          for (int cc = first_comp(ft); cc < first_comp(ft) + 5; ++cc) {
+            const int d_c = comp_dir(cc);
+            if (!ch.F(cc, cmp) || !(d_c == MEEPCU_R || d_c == MEEPCU_Z)) continue;
+            const int c_g = d_c == MEEPCU_R ? ch.plus_c[cc] : ch.minus_c[cc];
+            const T *gg = ch.F(c_g, 1 - cmp);
+            if (!gg) return fail(MEEPCU_EINVAL, "m != 0 needs complex fields (step_db.cpp:183)");
+            T *the_f = ch.F(cc, cmp);
+            const T *cndinv = (const T *)ch.d.condinv[cc][d_c];
+            T *fcnd = (T *)ch.d.f_cond[cc][cmp];
+            T *fu = (T *)ch.d.f_u[cc][cmp];
+            const int dsig = cycle_dir(cfg.dim, d_c, 1);
+            const T *siginv = ch.d.sigsize[dsig] > 1 ? (const T *)ch.d.siginv[dsig] : 0;
+            const int dsigu = cycle_dir(cfg.dim, d_c, 2);
+            const T *siginvu = ch.d.sigsize[dsigu] > 1 ? (const T *)ch.d.siginv[dsigu] : 0;
+            int is[3], ie[3];
+            for (int d = 0; d < 3; ++d) { // LOOP_OVER_VOL_OWNED0
+              is[d] = g.io[d] + 2 - g.yee_shift(cc, d);
+              ie[d] = g.io[d] + 2 * g.num[d];
+            }
+            const T the_m = 2 * cfg.m * (1 - 2 * cmp) * (1 - 2 * (ft == MEEPCU_B_STUFF)) * (1 - 2 * (d_c == MEEPCU_R)) * cfg.courant;
+            Loop L(g, is, ie);
+            KIdx K, KU;
+            if (siginv) K = KIdx(g, dsig, is);
+            if (siginvu) KU = KIdx(g, dsigu, is);
+            OLOOP(L, i) {
+              const int here_r = is[0] + 2 * (int)loop_i2; // IVEC_LOOP_ILOC: R is the second loop level in Dcyl
+              const T rinv = the_m / here_r;
+              if (siginv) {
+                const int k = K.at(loop_i1, loop_i2, loop_i3);
+                if (siginvu) {
+                  const int ku = KU.at(loop_i1, loop_i2, loop_i3);
+                  T df, dfcnd;
+                  if (cndinv) {
+                    dfcnd = rinv * gg[i] * cndinv[i];
+                    fcnd[i] += dfcnd;
+                  }
+                  else
+                    dfcnd = rinv * gg[i];
+                  fu[i] += (df = dfcnd * siginv[k]);
+                  the_f[i] += siginvu[ku] * df;
+                }
+                else {
+                  T dfcnd;
+                  if (cndinv) {
+                    dfcnd = rinv * gg[i] * cndinv[i];
+                    fcnd[i] += dfcnd;
+                  }
+                  else
+                    dfcnd = rinv * gg[i];
+                  the_f[i] += dfcnd * siginv[k];
+                }
+              }
+              else {
+                if (siginvu) {
+                  const int ku = KU.at(loop_i1, loop_i2, loop_i3);
+                  const T df = cndinv ? rinv * gg[i] * cndinv[i] : rinv * gg[i];
+                  fu[i] += df;
+                  the_f[i] += siginvu[ku] * df;
+                }
+                else {
+                  if (cndinv) the_f[i] += rinv * gg[i] * cndinv[i];
+                  else the_f[i] += rinv * gg[i];
+                }
+              }
+            }
+          }
+      }
+    // the r = 0 boundary conditions for m = 0, |m| = 1 and the other m (src/step_db.cpp:292-457)
+    if (cfg.dim == MEEPCU_Dcyl)
+      for (size_t ic = 0; ic < chunks.size(); ++ic) {
+        Chunk<T> &ch = chunks[ic];
+        const Grid &g = ch.g;
+        if (g.io[0] != 0) continue; // gv.origin_r() == 0.0
+        const int nz = g.num[2];
+        const double m = cfg.m;
+        const int Dz = MEEPCU_Dz, Dp = MEEPCU_Dp, Br = MEEPCU_Br, Hp = MEEPCU_Hp, Hr = MEEPCU_Hr, Hz = MEEPCU_Hz, Ep = MEEPCU_Ep,
+                  Ez = MEEPCU_Ez;
+#define ZERO_Z(arr) memset((arr), 0, sizeof(T) * (nz + 1))
+        for (int cmp = 0; cmp < (cfg.is_real ? 1 : 2); ++cmp) {
+          if ((m == 0 && ft == MEEPCU_D_STUFF && ch.F(Dz, cmp)) || (fabs(m) == 1 && !(m == 0 && ft == MEEPCU_B_STUFF && ch.F(Br, cmp)))) {
+            // the two explicit row updates share their structure (:296-330 and :341-386)
+            const bool m0 = (m == 0);
+            const int cc = m0 ? Dz : (ft == MEEPCU_D_STUFF ? Dp : Br);
+            const int d_c = comp_dir(cc);
+            if (!ch.F(cc, cmp)) continue;
+            const T *f_p = m0 ? ch.F(Hp, cmp) : ch.F(ft == MEEPCU_D_STUFF ? Hr : Ep, cmp);
+            const T *f_m = m0 ? 0 : (ft == MEEPCU_D_STUFF ? ch.F(Hz, cmp) : (ch.F(Ez, 1 - cmp) ? ch.F(Ez, 1 - cmp) + (nz + 1) : 0));
+            const T *cndinv = (const T *)ch.d.condinv[cc][d_c];
+            const T *cnd = (const T *)ch.d.conductivity[cc][d_c];
+            T *fcnd = (T *)ch.d.f_cond[cc][cmp];
+            const int dsig = cycle_dir(cfg.dim, d_c, 1);
+            const bool hs = ch.d.sigsize[dsig] > 1;
+            const T *siginv = hs ? (const T *)ch.d.siginv[dsig] : 0, *sig = hs ? (const T *)ch.d.sig[dsig] : 0,
+                    *kap = hs ? (const T *)ch.d.kap[dsig] : 0;
+            const int dsigu = cycle_dir(cfg.dim, d_c, 2);
+            const bool hu = ch.d.sigsize[dsigu] > 1;
+            const T *siginvu = hu ? (const T *)ch.d.siginv[dsigu] : 0, *sigu = hu ? (const T *)ch.d.sig[dsigu] : 0,
+                    *kapu = hu ? (const T *)ch.d.kap[dsigu] : 0;
+            T *fu = siginvu && ch.d.f_u[cc][cmp] ? ch.F(cc, cmp) : 0;
+            T *the_f = fu ? (T *)ch.d.f_u[cc][cmp] : ch.F(cc, cmp);
+            const int sd = ft == MEEPCU_D_STUFF ? +1 : -1;
+            const T f_m_mult = ft == MEEPCU_D_STUFF ? 2 : (1 - 2 * cmp) * m;
+            const T dt2 = cfg.dt * 0.5;
+            int is[3], ie[3];
+            for (int d = 0; d < 3; ++d) { // little_owned_corner(cc) (r index 0 at the origin), big_owned_corner(cc) with r = 0
+              is[d] = g.io[d] + 2 - g.yee_shift(cc, d);
+              ie[d] = g.io[d] + 2 * g.num[d] - g.yee_shift(cc, d);
+            }
+            if (is[0] == 2) is[0] = 0; // vec.cpp:432-436
+            ie[0] = 0;
+            if (ie[0] < is[0]) continue; // (a component that does not sit on the axis)
+            Loop L(g, is, ie);
+            KIdx K, KU;
+            if (hs) K = KIdx(g, dsig, is);
+            if (hu) KU = KIdx(g, dsigu, is);
+            OLOOP(L, i) {
+              const T fprev = the_f[i];
+              T dfcnd;
+              // (Courant is a double in the reference: the products are formed in double and rounded to realnum once)
+              if (m0) dfcnd = (T)(f_p[i] * (cfg.courant * 4));
+              else dfcnd = (T)((sd * cfg.courant) * (f_p[i] - f_p[i - sd] - f_m_mult * f_m[i]));
+              if (fcnd) {
+                const T fcnd_prev = fcnd[i];
+                fcnd[i] = ((1 - dt2 * cnd[i]) * fcnd[i] + dfcnd) * cndinv[i];
+                dfcnd = fcnd[i] - fcnd_prev;
+              }
+              const int k = hs ? K.at(loop_i1, loop_i2, loop_i3) : 0, ku = hu ? KU.at(loop_i1, loop_i2, loop_i3) : 0;
+              the_f[i] = ((kap ? kap[k] - sig[k] : 1) * the_f[i] + dfcnd) * (siginv ? siginv[k] : 1);
+              if (fu) fu[i] = siginvu[ku] * ((kapu ? kapu[ku] - sigu[ku] : 1) * fu[i] + the_f[i] - fprev);
+            }
+            if (m0) { // :331-333
+              if (ch.F(Dp, cmp)) ZERO_Z(ch.F(Dp, cmp));
+              if (ch.d.f_cond[Dp][cmp]) ZERO_Z((T *)ch.d.f_cond[Dp][cmp]);
+              if (ch.d.f_u[Dp][cmp]) ZERO_Z((T *)ch.d.f_u[Dp][cmp]);
+            }
+            else if (ft == MEEPCU_D_STUFF) { // :387-391
+              if (ch.F(Dz, cmp)) ZERO_Z(ch.F(Dz, cmp));
+              if (ch.d.f_cond[Dz][cmp]) ZERO_Z((T *)ch.d.f_cond[Dz][cmp]);
+              if (ch.d.f_u[Dz][cmp]) ZERO_Z((T *)ch.d.f_u[Dz][cmp]);
+            }
+          }
+          else if (m == 0 && ft == MEEPCU_B_STUFF && ch.F(Br, cmp)) { // :335-339
+            ZERO_Z(ch.F(Br, cmp));
+            if (ch.d.f_cond[Br][cmp]) ZERO_Z((T *)ch.d.f_cond[Br][cmp]);
+            if (ch.d.f_u[Br][cmp]) ZERO_Z((T *)ch.d.f_u[Br][cmp]);
+          }
+          else if (m != 0) { // m != {0,+1,-1}: :393-455
+            const int nrows = cfg.zero_fields_near_cylorigin ? g.num[0] + 1 : 1;
+            const double rmax = cfg.zero_fields_near_cylorigin ? fabs(m) - int(origin_r_times_a(g) + 0.5) : 1;
+            for (int r = 0; r < nrows && r < rmax; r++) {
+              const ptrdiff_t ir = (ptrdiff_t)r * (nz + 1);
+              const int list_d[2] = {Dp, Dz}, list_b[1] = {Br};
+              const int *list = ft == MEEPCU_D_STUFF ? list_d : list_b;
+              const int nl = ft == MEEPCU_D_STUFF ? 2 : 1;
+              for (int q = 0; q < nl; ++q) {
+                const int c = list[q];
+                // (the reference writes through f[c][cmp] unconditionally; the arrays exist whenever the chunk has the component)
+                if (ch.F(c, cmp)) ZERO_Z(ch.F(c, cmp) + ir);
+                if (ch.d.f_cond[c][cmp]) ZERO_Z((T *)ch.d.f_cond[c][cmp] + ir);
+                if (ch.d.f_u[c][cmp]) ZERO_Z((T *)ch.d.f_u[c][cmp] + ir);
+              }
+            }
+          }
+        }
+#undef ZERO_Z
       }
     return MEEPCU_OK;
   }
@@ -1172,15 +1407,14 @@ template <class T> struct Impl : CtxBase {
           if (!ch.F(ec, cmp)) continue;
           const int dc = dir_comp(first_comp(ft2), comp_dir(ec));
           const int d_ec = comp_dir(ec);
-          if (d_ec >= MEEPCU_R) continue;
           const int sgn = ft == MEEPCU_H_STUFF ? -1 : +1;
-          const ptrdiff_t s_ec = g.stride[d_ec] * sgn;
-          const int d_1 = cycle_dir(d_ec, 1);
+          const ptrdiff_t s_ec = g.stride[slot(d_ec)] * sgn;
+          const int d_1 = cycle_dir(cfg.dim, d_ec, 1);
           const int dc_1 = dir_comp(dc, d_1);
-          const ptrdiff_t s_1 = g.stride[d_1] * sgn;
-          const int d_2 = cycle_dir(d_ec, 2);
+          const ptrdiff_t s_1 = g.stride[slot(d_1)] * sgn;
+          const int d_2 = cycle_dir(cfg.dim, d_ec, 2);
           const int dc_2 = dir_comp(dc, d_2);
-          const ptrdiff_t s_2 = g.stride[d_2] * sgn;
+          const ptrdiff_t s_2 = g.stride[slot(d_2)] * sgn;
           const int dsigw = ch.d.sigsize[d_ec] > 1 ? d_ec : MEEPCU_NO_DIRECTION;
           if (ch.F(ec, cmp) == ch.F(dc, cmp)) {
             if (ch.d.chi1inv[ec][d_ec] || have_f_minus_p || dsigw != MEEPCU_NO_DIRECTION)
@@ -1255,7 +1489,7 @@ template <class T> struct Impl : CtxBase {
         const T *w0 = ch.d.f_w[c][cmp] ? (const T *)ch.d.f_w[c][cmp] : ch.F(c, cmp);
         const T *s = d0 < MEEPCU_R ? (const T *)gd_.sigma[c][d0] : NULL;
         if (!w0 || !s || g.dim != MEEPCU_D3) return fail(MEEPCU_EINVAL, "gyrotropic media require 3D Cartesian fields");
-        const int d1 = cycle_dir(d0, 1), d2 = cycle_dir(d0, 2);
+        const int d1 = cycle_dir(cfg.dim, d0, 1), d2 = cycle_dir(cfg.dim, d0, 2);
         const int c1 = dir_comp(c, d1), c2 = dir_comp(c, d2);
         const T *w1 = ch.d.f_w[c1][cmp] ? (const T *)ch.d.f_w[c1][cmp] : ch.F(c1, cmp);
         const T *w2 = ch.d.f_w[c2][cmp] ? (const T *)ch.d.f_w[c2][cmp] : ch.F(c2, cmp);
@@ -1263,7 +1497,7 @@ template <class T> struct Impl : CtxBase {
         T *p1 = (T *)gd_.P[c][cmp][d1], *pp1 = (T *)gd_.P_prev[c][cmp][d1];
         T *p2 = (T *)gd_.P[c][cmp][d2], *pp2 = (T *)gd_.P_prev[c][cmp][d2];
         const int sgn = is_magnetic(c) ? -1 : +1;
-        const ptrdiff_t is = g.stride[d0] * sgn, is1 = g.stride[d1] * sgn, is2 = g.stride[d2] * sgn;
+        const ptrdiff_t is = g.stride[slot(d0)] * sgn, is1 = g.stride[slot(d1)] * sgn, is2 = g.stride[slot(d2)] * sgn;
         if (!pp1 || !pp2) return fail(MEEPCU_EINVAL, "gyrotropic media require 3D Cartesian fields");
         if (gd_.sigma[c][d1] || gd_.sigma[c][d2]) return fail(MEEPCU_EINVAL, "gyrotropic media do not support anisotropic sigma");
         int is_[3], ie_[3]; // LOOP_OVER_VOL_OWNED
@@ -1340,15 +1574,14 @@ template <class T> struct Impl : CtxBase {
             if (!sd.P[c][cmp]) continue;
             const T *w = ch.d.f_w[c][cmp] ? (const T *)ch.d.f_w[c][cmp] : ch.F(c, cmp); // :43-44
             const int d = comp_dir(c);
-            if (d >= MEEPCU_R) continue;
             const T *s = (const T *)sd.sigma[c][d];
             if (!(w && s)) continue;
             T *p = (T *)sd.P[c][cmp], *pp = (T *)sd.P_prev[c][cmp];
             const int sgn = is_magnetic(c) ? -1 : +1;
-            const ptrdiff_t is_ = g.stride[d] * sgn;
-            int d1 = cycle_dir(d, 1), d2 = cycle_dir(d, 2);
+            const ptrdiff_t is_ = g.stride[slot(d)] * sgn;
+            int d1 = cycle_dir(cfg.dim, d, 1), d2 = cycle_dir(cfg.dim, d, 2);
             int c1 = dir_comp(c, d1), c2 = dir_comp(c, d2);
-            ptrdiff_t is1 = g.stride[d1] * sgn, is2 = g.stride[d2] * sgn;
+            ptrdiff_t is1 = g.stride[slot(d1)] * sgn, is2 = g.stride[slot(d2)] * sgn;
             const T *w1 = ch.d.f_w[c1][cmp] ? (const T *)ch.d.f_w[c1][cmp] : ch.F(c1, cmp);
             const T *s1 = w1 ? (const T *)sd.sigma[c][d1] : NULL;
             const T *w2 = ch.d.f_w[c2][cmp] ? (const T *)ch.d.f_w[c2][cmp] : ch.F(c2, cmp);
@@ -1685,7 +1918,6 @@ int meepcu_abi_version(void) { return MEEPCU_ABI_VERSION; }
 int meepcu_create(const meepcu_config *cfg, meepcu_ctx **out) {
   if (!cfg || !out) return fail(MEEPCU_EINVAL, "null argument");
   if (cfg->abi_version != MEEPCU_ABI_VERSION) return fail(MEEPCU_EINVAL, "ABI version mismatch");
-  if (cfg->dim == MEEPCU_Dcyl) return fail(MEEPCU_EUNSUPPORTED, "cylindrical coordinates");
   if (cfg->dim < 0 || cfg->dim > 3) return fail(MEEPCU_EINVAL, "bad dim");
   CtxBase *impl;
   if (cfg->realnum_bytes == 8)

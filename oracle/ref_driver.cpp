@@ -142,6 +142,9 @@ struct problem {
   }
 };
 
+static double cond_fn_r(const vec &p) { return 0.3 + 0.2 * p.r(); }
+static double rod_eps_r(const vec &p) { return (p.r() >= g_slab_lo && p.r() <= g_slab_hi) ? g_slab_eps : 1.0; }
+
 static vec kvec_for(const grid_volume &gv) { // tests/known_results.cpp:97-103
   switch (gv.dim) {
     case D1: return vec(0.3);
@@ -230,6 +233,34 @@ static problem *build(const std::string &spec, int nchunks) {
     p->f->use_real_fields();
     p->f->add_point_source(Ez, 0.25, 0.2, 0.0, 4.0, p->gv.center(), 1.0);
     p->f->add_point_source(d3 ? Ex : Hz, 0.3, 0.2, 0.0, 4.0, p->gv.center(), 0.6);
+  }
+  else if (name.compare(0, 3, "cyl") == 0) {
+    // cylindrical coordinates (step_db.cpp:86-122,178-457; tests/cylindrical.cpp physics): name[:nr[:m]] with
+    //   cyl      metallic walls            cylper   periodic in z (Bloch k = 0)
+    //   cylpml   PML in r and z around a dielectric rod          cylpmlnz  the same without zero_fields_near_cylorigin
+    //   cylcond  cylpml + conductivity (f_cond paths of the i m / r terms)
+    if (!n) n = 15;
+    p->gv = volcyl(n / a, (2 * n / 3) / a, a);
+    const bool with_pml = name.compare(0, 6, "cylpml") == 0 || name == "cylcond";
+    g_slab_lo = 0.0;
+    g_slab_hi = 0.4 * n / a;
+    g_slab_eps = 4.0;
+    if (with_pml)
+      p->s = new structure(p->gv, rod_eps_r, pml(0.4), identity(), nchunks, 0.5, false);
+    else
+      p->s = new structure(p->gv, rod_eps_r, no_pml(), identity(), nchunks, 0.4, false);
+    if (name == "cylcond") {
+      p->s->set_conductivity(Dr, cond_fn_r);
+      p->s->set_conductivity(Dp, cond_fn_r);
+      p->s->set_conductivity(Dz, cond_fn_r);
+      p->s->set_conductivity(Bp, cond_fn_r);
+    }
+    p->f = new fields(p->s, param, 0, name != "cylpmlnz");
+    if (name == "cylper") p->f->use_bloch(0.0);
+    const double R = n / a, Zs = (2 * n / 3) / a;
+    p->f->add_point_source(Ep, 0.7, 2.5, 0.0, 4.0, veccyl(0.33 * R, 0.5 * Zs), 1.0);
+    p->f->add_point_source(Ez, 0.8, 0.6, 0.0, 4.0, veccyl(0.267 * R + 0.001, 0.376 * Zs + 0.001), 1.0);
+    p->f->add_point_source(Hr, 0.6, 0.8, 0.0, 4.0, veccyl(0.45 * R + 0.003, 0.45 * Zs), 0.5);
   }
   else if (name == "nr3d") { // BASELINE config 3a, fork Newton-Raphson chi2
     if (!n) n = 16;
@@ -539,7 +570,11 @@ static cmp_result compare(const std::vector<marray> &A, const std::vector<marray
     size_t bad = 0;
     for (size_t i = 0; i < n; ++i) {
       double d = (double)a[i] - (double)b[i];
-      if (memcmp(&a[i], &b[i], sizeof(realnum)) != 0 && !(a[i] == b[i])) bad++; // -0 == +0 ok
+      if (memcmp(&a[i], &b[i], sizeof(realnum)) != 0 && !(a[i] == b[i])) { // -0 == +0 ok
+        bad++;
+        static const char *dbg = getenv("MEEPCU_DEBUG_COMPARE");
+        if (dbg && bad <= (size_t)atoi(dbg)) fprintf(stderr, "  %s[%zu]: ref %.17g abi %.17g\n", A[k].name.c_str(), i, (double)a[i], (double)b[i]);
+      }
       if (fabs(d) > r.max_abs) r.max_abs = fabs(d);
       r.sum_d2 += d * d;
       r.sum_r2 += (double)a[i] * (double)a[i];
