@@ -2198,6 +2198,30 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// The same for MANY small arrays at once (meepcu_sync_*: the edge / corner PML chunks of a 3-D cell are hundreds of
+// arrays of a few hundred KB): their dense rows travel packed in one staging block, one launch re-pitches them all.
+template <class T> struct RowsEntry {
+  T *dev;
+  long long dpitch; // elements
+  long long off;    // first element in the staging block
+  int w;            // elements per dense row
+  long long rows;
+};
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+    k_rows_batch(const RowsEntry<T> *__restrict__ tab, int n, T *__restrict__ stage, int to_stage) {
+  for (int e = blockIdx.y; e < n; e += gridDim.y) {
+    const RowsEntry<T> q = tab[e];
+    const long long tot = q.rows * q.w, stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < tot; k += stride) {
+      const long long r = k / q.w;
+      const int c = (int)(k - r * q.w);
+      if (to_stage) stage[q.off + k] = q.dev[r * q.dpitch + c];
+      else q.dev[r * q.dpitch + c] = stage[q.off + k];
+    }
+  }
+}
+
 // fields_chunk::average_with_backup (energy_and_flux.cpp:135-143): fc[i] = 0.5 * (fc[i] + backup[i])
 template <class T> __global__ void __launch_bounds__(kThreads) k_average(T *__restrict__ f, const T *__restrict__ backup, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;

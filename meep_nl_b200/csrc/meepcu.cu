@@ -1100,6 +1100,87 @@ template <class T> struct Ctx : CtxBase {
     return MEEPCU_OK;
   }
 
+  // Small arrays that are not page-locked in place (pageable copies of 2 KB rows ran at 5-7 GB/s, and a 3-D cell with
+  // PML on every face has ~500 of them, ~100 MB): packed by the host cores into the pinned staging buffers, ONE DMA
+  // per 64 MB block, ONE k_rows_batch launch per block.
+  bool batchable(const ArrayRec &r) const {
+    const size_t nb = r.n_host * sizeof(T) * (r.kind == A_DFT ? 2 : 1);
+    return !r.pinned && nb <= (size_t)kStageBytes / 8 && nb > 0 && !getenv("MEEPCU_NO_BATCH");
+  }
+  int batch_copy(const std::vector<const ArrayRec *> &list, bool to_host) {
+    if (list.empty()) return MEEPCU_OK;
+    RC(stage_init());
+    RC(dstage_init());
+    struct Item { const ArrayRec *r; size_t off, nb; };
+    struct Pending { int buf; std::vector<Item> items; };
+    std::vector<Pending> pend;
+    auto drain = [&](Pending &P) -> int { // D2H: the block has landed in stage[buf]: hand the rows to their arrays
+      CU(cudaEventSynchronize(stage_ev[P.buf]));
+      const long ni = (long)P.items.size();
+#pragma omp parallel for schedule(dynamic, 4)
+      for (long k = 0; k < ni; ++k) memcpy((void *)P.items[k].r->host, stage[P.buf] + P.items[k].off, P.items[k].nb);
+      return MEEPCU_OK;
+    };
+    size_t i = 0;
+    while (i < list.size()) {
+      const int b = stage_next;
+      stage_next ^= 1;
+      for (size_t k = 0; k < pend.size(); ++k) // the buffer we are about to reuse
+        if (pend[k].buf == b) { RC(drain(pend[k])); pend.erase(pend.begin() + k); break; }
+      if (!to_host) CU(cudaEventSynchronize(stage_ev[b])); // the previous DMA out of this buffer has finished
+      Pending P;
+      P.buf = b;
+      std::vector<RowsEntry<T> > tab;
+      size_t used = 0;
+      for (; i < list.size(); ++i) {
+        const ArrayRec &r = *list[i];
+        const size_t esz = sizeof(T), ne = r.n_host * (r.kind == A_DFT ? 2 : 1), nb = ne * esz;
+        if (used + nb > (size_t)kStageBytes) break;
+        RowsEntry<T> e;
+        e.dev = (T *)r.dev;
+        e.off = (long long)(used / esz);
+        if (r.kind == A_GRID) {
+          const Geom &g = chunks[r.chunk].g;
+          e.w = g.nax[2];
+          e.rows = (long long)g.nax[0] * g.nax[1];
+          e.dpitch = g.pitch;
+        }
+        else {
+          e.w = (int)std::min<size_t>(ne, (size_t)1 << 20);
+          e.rows = (long long)((ne + e.w - 1) / e.w);
+          e.dpitch = e.w;
+          if ((size_t)e.rows * e.w != ne) { e.w = 1; e.rows = (long long)ne; e.dpitch = 1; }
+        }
+        tab.push_back(e);
+        Item it = {&r, used, nb};
+        P.items.push_back(it);
+        used += (nb + 15) & ~(size_t)15;
+      }
+      if (tab.empty()) return fail(MEEPCU_EINVAL, "array too large for the batched path");
+      char *d_tab = 0;
+      RC(ring_put(tab.data(), tab.size() * sizeof(RowsEntry<T>), &d_tab));
+      dim3 grid(8, (unsigned)std::min<size_t>(tab.size(), 148 * 2));
+      if (to_host) {
+        k_rows_batch<T><<<grid, kThreads, 0, st>>>((const RowsEntry<T> *)d_tab, (int)tab.size(), (T *)dstage, 1);
+        launches++;
+        CU(cudaMemcpyAsync(stage[b], dstage, used, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(stage_ev[b], st));
+        pend.push_back(P);
+      }
+      else {
+        const long ni = (long)P.items.size();
+#pragma omp parallel for schedule(dynamic, 4)
+        for (long k = 0; k < ni; ++k) memcpy(stage[b] + P.items[k].off, P.items[k].r->host, P.items[k].nb);
+        CU(cudaMemcpyAsync(dstage, stage[b], used, cudaMemcpyHostToDevice, st));
+        k_rows_batch<T><<<grid, kThreads, 0, st>>>((const RowsEntry<T> *)d_tab, (int)tab.size(), (T *)dstage, 0);
+        launches++;
+        CU(cudaEventRecord(stage_ev[b], st));
+      }
+    }
+    for (size_t k = 0; k < pend.size(); ++k) RC(drain(pend[k]));
+    return MEEPCU_OK;
+  }
+
   // asynchronous copy on st: small arrays (pageable is fine) and big arrays page-locked in place
   int copy_array(const ArrayRec &r, bool to_host) {
     if (r.kind == A_GRID) {
@@ -2993,11 +3074,14 @@ template <class T> struct Ctx : CtxBase {
       RC(halos_B(groups, remote));
       if (n_ranks == 1 || !local_only) halo_stale = false;
     }
+    std::vector<const ArrayRec *> small;
     for (std::map<const char *, ArrayRec>::iterator it = arrays.begin(); it != arrays.end(); ++it) {
       const ArrayRec &r = it->second;
       if (!(r.group & groups) || (to_host && !r.mut)) continue;
+      if (batchable(r)) { small.push_back(&r); continue; }
       RC(big(r) && !r.pinned ? staged_copy(r, to_host) : copy_array(r, to_host));
     }
+    RC(batch_copy(small, to_host));
     if (to_host) {
       RC(halos_R(groups, remote));
       if (virt_now(groups) && n_runs_def[MEEPCU_E_STUFF]) halo_stale = true; // (the normal-plane E halos parked in D arrays: next A)

@@ -51,12 +51,11 @@ namespace meepcu {
 // direction of slot k of every X,Y,Z triple of the ABI: Cartesian X,Y,Z; cylindrical R,-,Z (grid_volume keeps
 // num[d % 3], vec.hpp:1014-1020)
 inline meep::direction slot_direction(meep::ndim dim, int k) {
-  if (dim == meep::Dcyl) return k == 0 ? meep::R : (k == 2 ? meep::Z : meep::NO_DIRECTION);
+  if (dim == meep::Dcyl) return k == 0 ? meep::R : (k == 2 ? meep::Z : meep::P); // (P: no extent, one loop iteration)
   return (meep::direction)k;
 }
 inline bool slot_present(meep::ndim dim, int k) {
-  const meep::direction d = slot_direction(dim, k);
-  return d != meep::NO_DIRECTION && meep::has_direction(dim, d);
+  return meep::has_direction(dim, slot_direction(dim, k));
 }
 
 struct api {
@@ -269,10 +268,12 @@ public:
       const bool has = slot_present(fc->gv.dim, k);
       d.is[k] = has ? is.in_direction(xyz[k]) : 0;
       d.ie[k] = has ? ie.in_direction(xyz[k]) : 0;
-      d.s0[k] = has ? s0.in_direction(xyz[k]) : 0;
-      d.s1[k] = has ? s1.in_direction(xyz[k]) : 0;
-      d.e0[k] = has ? e0.in_direction(xyz[k]) : 0;
-      d.e1[k] = has ? e1.in_direction(xyz[k]) : 0;
+      // (every slot: the loop level of an absent direction has one iteration whose IVEC_LOOP_WEIGHT factor is
+      //  s0.in_direction(that direction), vec.hpp:372-383)
+      d.s0[k] = s0.in_direction(xyz[k]);
+      d.s1[k] = s1.in_direction(xyz[k]);
+      d.e0[k] = e0.in_direction(xyz[k]);
+      d.e1[k] = e1.in_direction(xyz[k]);
     }
     d.dV0 = dV0;
     d.dV1 = dV1;
@@ -653,10 +654,10 @@ private:
           const bool has = slot_present(gv.dim, k);
           dd.is[k] = has ? dc->is.in_direction(xyz[k]) : 0;
           dd.ie[k] = has ? dc->ie.in_direction(xyz[k]) : 0;
-          dd.s0[k] = has ? dc->s0.in_direction(xyz[k]) : 0;
-          dd.s1[k] = has ? dc->s1.in_direction(xyz[k]) : 0;
-          dd.e0[k] = has ? dc->e0.in_direction(xyz[k]) : 0;
-          dd.e1[k] = has ? dc->e1.in_direction(xyz[k]) : 0;
+          dd.s0[k] = dc->s0.in_direction(xyz[k]); // (every slot: see integrate_collect_chunkloop)
+          dd.s1[k] = dc->s1.in_direction(xyz[k]);
+          dd.e0[k] = dc->e0.in_direction(xyz[k]);
+          dd.e1[k] = dc->e1.in_direction(xyz[k]);
         }
         dd.dV0 = dc->dV0;
         dd.dV1 = dc->dV1;

@@ -143,6 +143,7 @@ struct problem {
 };
 
 static double cond_fn_r(const vec &p) { return 0.3 + 0.2 * p.r(); }
+static double rod_sigma_r(const vec &p) { return (p.r() >= g_slab_lo && p.r() <= g_slab_hi) ? 1.5 : 0.0; }
 static double rod_eps_r(const vec &p) { return (p.r() >= g_slab_lo && p.r() <= g_slab_hi) ? g_slab_eps : 1.0; }
 
 static vec kvec_for(const grid_volume &gv) { // tests/known_results.cpp:97-103
@@ -241,7 +242,8 @@ static problem *build(const std::string &spec, int nchunks) {
     //   cylcond  cylpml + conductivity (f_cond paths of the i m / r terms)
     if (!n) n = 15;
     p->gv = volcyl(n / a, (2 * n / 3) / a, a);
-    const bool with_pml = name.compare(0, 6, "cylpml") == 0 || name == "cylcond";
+    //   cyllor   cylpml + a Lorentzian rod + DFT flux planes (r = const and z = const) + dft_fields
+    const bool with_pml = name.compare(0, 6, "cylpml") == 0 || name == "cylcond" || name == "cyllor";
     g_slab_lo = 0.0;
     g_slab_hi = 0.4 * n / a;
     g_slab_eps = 4.0;
@@ -255,12 +257,19 @@ static problem *build(const std::string &spec, int nchunks) {
       p->s->set_conductivity(Dz, cond_fn_r);
       p->s->set_conductivity(Bp, cond_fn_r);
     }
+    if (name == "cyllor") p->s->add_susceptibility(rod_sigma_r, E_stuff, lorentzian_susceptibility(0.9, 0.02));
     p->f = new fields(p->s, param, 0, name != "cylpmlnz");
     if (name == "cylper") p->f->use_bloch(0.0);
     const double R = n / a, Zs = (2 * n / 3) / a;
     p->f->add_point_source(Ep, 0.7, 2.5, 0.0, 4.0, veccyl(0.33 * R, 0.5 * Zs), 1.0);
     p->f->add_point_source(Ez, 0.8, 0.6, 0.0, 4.0, veccyl(0.267 * R + 0.001, 0.376 * Zs + 0.001), 1.0);
     p->f->add_point_source(Hr, 0.6, 0.8, 0.0, 4.0, veccyl(0.45 * R + 0.003, 0.45 * Zs), 0.5);
+    if (name == "cyllor") {
+      p->fluxes.push_back(p->f->add_dft_flux_plane(volume(veccyl(0.6 * R, 0.2 * Zs), veccyl(0.6 * R, 0.8 * Zs)), 0.5, 0.9, 4));
+      p->fluxes.push_back(p->f->add_dft_flux_plane(volume(veccyl(0.0, 0.7 * Zs), veccyl(0.6 * R, 0.7 * Zs)), 0.5, 0.9, 3));
+      component cs[2] = {Ep, Hz};
+      p->dftfields.push_back(p->f->add_dft_fields(cs, 2, volume(veccyl(0.1 * R, 0.3 * Zs), veccyl(0.5 * R, 0.6 * Zs)), 0.6, 0.8, 2));
+    }
   }
   else if (name == "nr3d") { // BASELINE config 3a, fork Newton-Raphson chi2
     if (!n) n = 16;

@@ -29,6 +29,14 @@ CASES = [("fp64", "vac3d:24", 25, 2), ("fp64", "kr_per3d_rods", 40, 0), ("fp64",
          ("fp64", "gyro3d", 60, 2), ("fp32", "gyro3d", 60, 2), ("fp64", "gyrodrude3d", 60, 2), ("fp64", "gyrosat3d", 60, 2),
          ("fp32", "gyrosat3d", 60, 2),
          ("fp64", "dft2d", 60, 2), ("fp32", "dft2d", 60, 2), ("fp64", "dft3d", 60, 2), ("fp32", "dft3d", 60, 2),
+         # cylindrical coordinates (step_db.cpp:86-122,178-457): metallic / periodic-in-z / PML cells, m = -1 .. 3 (the
+         # r = 0 rules of m = 0, |m| = 1 and the zeroed rows of larger |m|, with and without zero_fields_near_cylorigin),
+         # conductivity (f_cond paths of the i m / r terms), a Lorentzian rod with DFT flux planes and dft_fields
+         ("fp64", "cyl:15:0", 120, 0), ("fp64", "cyl:15:1", 120, 0), ("fp32", "cyl:15:-1", 120, 0), ("fp64", "cylper:15:2", 120, 2),
+         ("fp32", "cylper:16:0", 120, 0), ("fp64", "cylpml:18:0", 120, 2), ("fp64", "cylpml:18:1", 120, 0),
+         ("fp32", "cylpml:18:1", 120, 0), ("fp64", "cylpml:18:3", 120, 0), ("fp64", "cylpmlnz:18:3", 120, 0),
+         ("fp64", "cylcond:18:1", 120, 2), ("fp32", "cylcond:18:2", 120, 0), ("fp64", "cyllor:20:1", 150, 2),
+         ("fp32", "cyllor:20:0", 150, 0), ("fp64", "cyllor:18:2", 150, 0),
          # UPSTREAM_PADE against the de-blocked reference flavour (oracle/deblock_pade.py)
          ("fp64_pade", "kerr3d:14", 40, 2), ("fp64_pade", "kerr1d", 80, 0), ("fp64_pade", "kr_per3d_rods", 40, 0)]
 
@@ -72,7 +80,8 @@ def test_reference_known_answers_through_the_oracle():
 
 SYNC_CASES = [("fp64", "vac3d:32", 40), ("fp64", "wvg2d", 60), ("fp64", "lorentz3d:16", 40), ("fp32", "vac3d_cplx:14", 30),
               ("fp64", "kr_per3d_rods", 40), ("fp64", "cond3d:12", 40), ("fp64", "bfast3d:10", 40), ("fp32", "beta2d", 40),
-              ("fp64", "magdrude3d", 40), ("fp32", "magdrude2d", 40), ("fp64", "gyrosat3d", 40)]
+              ("fp64", "magdrude3d", 40), ("fp32", "magdrude2d", 40), ("fp64", "gyrosat3d", 40),
+              ("fp64", "cylpml:18:1", 40), ("fp64", "cyllor:18:0", 40), ("fp32", "cylcond:18:2", 40)]
 
 
 @pytest.mark.parametrize("flavour,case,steps", SYNC_CASES)
@@ -94,7 +103,8 @@ def test_synchronize_magnetic_fields_equals_reference(flavour, case, steps):
 
 
 @pytest.mark.parametrize("flavour,case,chunks", [("fp64", "vac3d:32", 5), ("fp64", "lorentz3d:16", 4), ("fp32", "wvg2d", 6),
-                                                 ("fp64", "nrslab3d:14", 3), ("fp64", "aniso3d:14", 3)])
+                                                 ("fp64", "nrslab3d:14", 3), ("fp64", "aniso3d:14", 3),
+                                                 ("fp64", "cyllor:24:1", 3), ("fp32", "cylpml:24:2", 4)])
 def test_reference_chunk_splitting(flavour, case, chunks):
     """structure(..., num_chunks) lets the reference split the cell by cost into many more chunks (40-50):
     the description the shim hands over changes completely, the fields must not"""
