@@ -92,6 +92,11 @@ template <class T> struct CompParams {
   unsigned zmask_eh;
   int npol;
   PolParams<T> pol[kMaxPol];
+  // ---- cylindrical coordinates (step_db.cpp:177-290,393-455) ----
+  const T *gm; // the OTHER cmp of the component whose phi-derivative became the i m / r term (NULL: none)
+  T the_m;     // 2 m (1 - 2 cmp) (+-1 by field type) (+-1 by direction) Courant
+  int r0;      // here.r() = r0 + 2 * (index along R), R being device axis B
+  int zrows;   // rows r < zrows of this component (and its f_u, f_cond) are zeroed after the curl: |m| > 1 next to the axis
 };
 
 template <class T> struct HalfParams { // one chunk, one of {B/H, D/E}, one cmp
@@ -158,7 +163,7 @@ __device__ __forceinline__ bool on_zero_plane(unsigned m, const int lo[3], const
 //   HAS_COND: conductivity terms (cnd, cndinv, fcnd) compiled in;  HAS_POL: polarisations compiled in
 // ------------------------------------------------------------------------------------------------
 template <class T, bool HAS_COND, bool HAS_POL, bool HAS_BB = false> struct PointVals {
-  T g1p, g1, g2, g2p, f, fu, e, fw, u, gb, fb;
+  T g1p, g1, g2, g2p, f, fu, e, fw, u, gb, fb, gm;
   T cnd, cndinv, fcnd;
   T p[HAS_POL ? kMaxPol : 1], pp[HAS_POL ? kMaxPol : 1], s[HAS_POL ? kMaxPol : 1];
 };
@@ -176,6 +181,7 @@ __device__ __forceinline__ void gather_point(const CompParams<T> &c, const PolPa
   if (c.fu) v.fu = c.fu[i];
   if (HAS_BB && c.gb) v.gb = __ldg(c.gb + i);
   if (HAS_BB && c.fb) v.fb = c.fb[i];
+  if (HAS_BB && c.gm) v.gm = __ldg(c.gm + i);
   if (HAS_COND && c.cnd) {
     v.cnd = __ldg(c.cnd + i);
     v.cndinv = __ldg(c.cndinv + i);
@@ -264,8 +270,8 @@ __device__ __forceinline__ void finish_point(const CompParams<T> &c, const PolPa
   // increment to f through the same PML / conductivity chain, bfast right after the curl of the
   // component (step_db.cpp:129-143), beta after all curls (step_db.cpp:161-175) ----------------------
 #pragma unroll
-  for (int pass = 0; pass < (HAS_BB ? 2 : 0); ++pass) { // compiled only into the class that has these terms
-    if (pass == 0 ? !c.fb : !c.gb) continue;
+  for (int pass = 0; pass < (HAS_BB ? 3 : 0); ++pass) { // compiled only into the class that has these terms
+    if (pass == 0 ? !c.fb : (pass == 1 ? !c.gb : !c.gm)) continue;
     T bg;
     if (pass == 0) {
       const T F_prev = v.fb;
@@ -276,8 +282,12 @@ __device__ __forceinline__ void finish_point(const CompParams<T> &c, const PolPa
       c.fb[i] = Fn;
       bg = Fn - F_prev;
     }
-    else
+    else if (pass == 1)
       bg = c.betadt * v.gb;
+    else { // cylindrical i m / r term (step_db.cpp:177-290): rinv = the_m / here.r(), increment rinv * g[i]
+      const T rinv = c.the_m / (T)(c.r0 + 2 * ib);
+      bg = rinv * v.gm;
+    }
     if (c.kaxis >= 0) {
       if (c.kuaxis >= 0) {
         T df;
@@ -313,6 +323,11 @@ __device__ __forceinline__ void finish_point(const CompParams<T> &c, const PolPa
         else fnew = fnew + bg;
       }
     }
+  }
+  if (HAS_BB && ib < c.zrows) { // |m| > 1: the rows next to the axis are zeroed at the end of step_db (:393-455)
+    fnew = 0;
+    fun = 0;
+    fc = 0;
   }
   if (c.kuaxis >= 0) c.fu[i] = fun;
   if (cond && c.kaxis >= 0) c.fcnd[i] = fc;
@@ -2180,6 +2195,82 @@ __global__ void __launch_bounds__(kThreads)
   if (threadIdx.x == 0) {
     partial[2 * (size_t)blockIdx.x] = rs[0];
     partial[2 * (size_t)blockIdx.x + 1] = rm[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cylindrical coordinates (step_db.cpp:86-122): the update of a z component needs (1/r) d(r F_phi)/dr; the reference
+// builds the running sum over r of that expression (f_rderiv_int) so that the plain difference of step_curl yields
+// it.  The sum is sequential in r by construction -- every partial sum is rounded -- so one thread owns one z
+// column and walks r; consecutive threads hold consecutive z (coalesced rows).  Same expressions, same roundings.
+// ------------------------------------------------------------------------------------------------
+template <class T> struct CylRderiv {
+  T *S;        // f_rderiv_int, device layout of the chunk
+  const T *fp; // the phi component (E_p or H_p) of this cmp
+  int nr, nz, pitch;
+  T ir0;       // origin_r * a + 0.5 * iyee_shift(c_p).r
+};
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_cyl_rderiv(const CylRderiv<T> *__restrict__ tab, int n) {
+  for (int e = blockIdx.y; e < n; e += gridDim.y) {
+    const CylRderiv<T> q = tab[e];
+    for (int iz = blockIdx.x * blockDim.x + threadIdx.x; iz <= q.nz; iz += gridDim.x * blockDim.x) {
+      T acc = 0, prev = q.fp[iz];
+      q.S[iz] = 0;
+      for (int ir = 1; ir <= q.nr; ++ir) {
+        const T rinv = 1.0 / ((ir + q.ir0) - 0.5);
+        const long long idx = (long long)ir * q.pitch + iz;
+        const T cur = q.fp[idx];
+        acc = acc + rinv * (cur * (ir + q.ir0) - prev * ((ir - 1) + q.ir0));
+        q.S[idx] = acc;
+        prev = cur;
+      }
+    }
+  }
+}
+
+// The r = 0 rules of step_db.cpp:292-457 for a chunk that contains the axis: the explicit update of the one
+// component that lives on the axis (m = 0: D_z from H_phi; |m| = 1: D_phi from H_r, H_z / B_r from E_phi, E_z) with
+// its PML / conductivity chain, and the rows that are cleared.  One thread per z.
+template <class T> struct CylOrigin {
+  int lo, hi, nzp1;         // z index range of the row update (inclusive); elements per row
+  T *the_f, *fu;            // after the role swap of step_db.cpp:311-312 (the_f NULL: no row update)
+  const T *f_p, *f_m;       // f_m: already points at the row it is read from
+  int sd, m0;
+  T f_m_mult, dt2;
+  double courant;
+  T *fcnd;
+  const T *cnd, *cndinv;
+  const T *sig, *kap, *siginv;
+  int k_z, koff;            // k = k_z * 2 * iz + koff
+  const T *sigu, *kapu, *siginvu;
+  int ku_z, kuoff;
+  T *zero[6];               // rows (first nzp1 elements) that are cleared
+  int nzero;
+};
+template <class T>
+__global__ void __launch_bounds__(kThreads) k_cyl_origin(const CylOrigin<T> *__restrict__ tab, int n) {
+  for (int e = blockIdx.y; e < n; e += gridDim.y) {
+    const CylOrigin<T> q = tab[e];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q.nzp1; i += gridDim.x * blockDim.x) {
+      if (q.the_f && i >= q.lo && i <= q.hi) {
+        const T fprev = q.the_f[i];
+        T dfcnd;
+        if (q.m0) dfcnd = (T)(q.f_p[i] * (q.courant * 4));
+        else dfcnd = (T)((q.sd * q.courant) * (q.f_p[i] - q.f_p[i - q.sd] - q.f_m_mult * q.f_m[i]));
+        if (q.fcnd) {
+          const T fcnd_prev = q.fcnd[i];
+          const T fcn = ((1 - q.dt2 * q.cnd[i]) * fcnd_prev + dfcnd) * q.cndinv[i];
+          q.fcnd[i] = fcn;
+          dfcnd = fcn - fcnd_prev;
+        }
+        const int k = q.k_z * 2 * i + q.koff, ku = q.ku_z * 2 * i + q.kuoff;
+        const T fn = ((q.kap ? q.kap[k] - q.sig[k] : (T)1) * fprev + dfcnd) * (q.siginv ? q.siginv[k] : (T)1);
+        q.the_f[i] = fn;
+        if (q.fu) q.fu[i] = q.siginvu[ku] * ((q.kapu ? q.kapu[ku] - q.sigu[ku] : (T)1) * q.fu[i] + fn - fprev);
+      }
+      for (int z = 0; z < q.nzero; ++z) q.zero[z][i] = 0;
+    }
   }
 }
 

@@ -116,6 +116,63 @@ inline int dir_comp(int ft, int d) { // direction_component(first_field_componen
   return 5 * ft + off[d];
 }
 
+// Cylindrical coordinates are handled in CANONICAL form: (R, P, Z) -> the slots of (X, Y, Z) -- which is the
+// reference's own convention for everything it indexes by direction % 3 (src/meep/vec.hpp:1014-1020,
+// src/fields.cpp:411-425) -- so that the library sees a Cartesian-like grid with extents in slots 0 and 2 and none
+// in slot 1.  The descriptions are rewritten once, on entry; host pointers (the keys of everything) are untouched.
+inline int canon_comp(int c) { // Er -> the Ex slot, Ep -> the Ey slot, Ez stays
+  const int o = c % 5;
+  return c - o + (o == 2 ? 0 : (o == 3 ? 1 : o));
+}
+inline void canon_chunk_desc(meepcu_chunk_desc &d) {
+  const meepcu_chunk_desc o = d;
+  static const int cyl_dir[3] = {MEEPCU_R, MEEPCU_P, MEEPCU_Z};
+  for (int c = 0; c < 20; ++c) {
+    for (int cmp = 0; cmp < 2; ++cmp) d.f[c][cmp] = d.f_u[c][cmp] = d.f_w[c][cmp] = d.f_cond[c][cmp] = d.f_bfast[c][cmp] = 0;
+    for (int k = 0; k < 5; ++k) d.chi1inv[c][k] = d.conductivity[c][k] = d.condinv[c][k] = 0;
+    d.chi2[c] = d.chi3[c] = 0;
+  }
+  for (int c = 0; c < 20; ++c) {
+    if (c % 5 < 2) continue; // no Cartesian components in a cylindrical cell
+    const int cc = canon_comp(c);
+    for (int cmp = 0; cmp < 2; ++cmp) {
+      d.f[cc][cmp] = o.f[c][cmp];
+      d.f_u[cc][cmp] = o.f_u[c][cmp];
+      d.f_w[cc][cmp] = o.f_w[c][cmp];
+      d.f_cond[cc][cmp] = o.f_cond[c][cmp];
+      d.f_bfast[cc][cmp] = o.f_bfast[c][cmp];
+    }
+    for (int k = 0; k < 3; ++k) {
+      d.chi1inv[cc][k] = o.chi1inv[c][cyl_dir[k]];
+      d.conductivity[cc][k] = o.conductivity[c][cyl_dir[k]];
+      d.condinv[cc][k] = o.condinv[c][cyl_dir[k]];
+    }
+    d.chi2[cc] = o.chi2[c];
+    d.chi3[cc] = o.chi3[c];
+  }
+  for (int k = 0; k < 6; ++k) { d.sig[k] = d.kap[k] = d.siginv[k] = 0; d.sigsize[k] = 0; }
+  for (int k = 0; k < 3; ++k) {
+    d.sig[k] = o.sig[cyl_dir[k]];
+    d.kap[k] = o.kap[cyl_dir[k]];
+    d.siginv[k] = o.siginv[cyl_dir[k]];
+    d.sigsize[k] = o.sigsize[cyl_dir[k]];
+  }
+}
+inline void canon_susc_desc(meepcu_susceptibility_desc &d) {
+  const meepcu_susceptibility_desc o = d;
+  static const int cyl_dir[3] = {MEEPCU_R, MEEPCU_P, MEEPCU_Z};
+  for (int c = 0; c < 20; ++c) {
+    for (int k = 0; k < 5; ++k) d.sigma[c][k] = 0;
+    for (int cmp = 0; cmp < 2; ++cmp) d.P[c][cmp] = d.P_prev[c][cmp] = 0;
+  }
+  for (int c = 0; c < 20; ++c) {
+    if (c % 5 < 2) continue;
+    const int cc = canon_comp(c);
+    for (int k = 0; k < 3; ++k) d.sigma[cc][k] = o.sigma[c][cyl_dir[k]];
+    for (int cmp = 0; cmp < 2; ++cmp) { d.P[cc][cmp] = o.P[c][cmp]; d.P_prev[cc][cmp] = o.P_prev[c][cmp]; }
+  }
+}
+
 enum ArrKind { A_GRID = 0, A_VEC = 1, A_DFT = 2 };
 
 struct ArrayRec {
@@ -328,6 +385,7 @@ template <class T> struct Ctx : CtxBase {
   // appears in no curl): copied only when the host mirror is refreshed, like the B/D/P halos
   ConnRun<T> *d_runs_def[MEEPCU_NUM_FIELD_TYPES];
   int n_runs_def[MEEPCU_NUM_FIELD_TYPES];
+  std::vector<T *> metal_axis[MEEPCU_NUM_FIELD_TYPES]; // cylindrical: metal points on the axis row (see metal_masks)
   T **d_zero_late[2];                 // zero_metal(E/H) of chunks whose polarisations update in their own pass
   long long n_zero_late[2];
   T **d_zero[MEEPCU_NUM_FIELD_TYPES]; // unfused metal lists (only non-plane lists; normally empty)
@@ -340,6 +398,11 @@ template <class T> struct Ctx : CtxBase {
   std::vector<PolGenParams<T> > h_polgen;
   Tile *d_polgen_tiles[2];
   int n_polgen_tiles[2];
+  // cylindrical coordinates: per half, the f_rderiv_int pre-pass and the r = 0 rules (kernels.cuh)
+  CylRderiv<T> *d_cyl_rd[2];
+  int n_cyl_rd[2];
+  CylOrigin<T> *d_cyl_org[2];
+  int n_cyl_org[2];
   std::set<std::pair<int, int> > aniso_chunk_half; // (chunk, half) whose polarisations update in k_pol_general
   bool general_half[2];  // some chunk (of ANY rank) needs k_eh_general in this half
   bool aniso_half[2];    // some chunk (of any rank) updates polarisations in k_pol_general / k_pol_gyro
@@ -505,6 +568,10 @@ template <class T> struct Ctx : CtxBase {
     d_polgen = 0;
     memset(d_polgen_tiles, 0, sizeof d_polgen_tiles);
     memset(n_polgen_tiles, 0, sizeof n_polgen_tiles);
+    memset(d_cyl_rd, 0, sizeof d_cyl_rd);
+    memset(n_cyl_rd, 0, sizeof n_cyl_rd);
+    memset(d_cyl_org, 0, sizeof d_cyl_org);
+    memset(n_cyl_org, 0, sizeof n_cyl_org);
     memset(d_zero, 0, sizeof d_zero);
     memset(n_zero, 0, sizeof n_zero);
     fmp_has_src[0] = fmp_has_src[1] = false;
@@ -541,15 +608,30 @@ template <class T> struct Ctx : CtxBase {
     if (st) cudaStreamDestroy(st);
   }
 
+  // gv.origin_r() * gv.a with the reference's roundings: origin = io * (0.5 * inva), inva = 1 / a (vec.cpp:38-41)
+  double origin_r_times_a(const Geom &g) const {
+    const double inva = 1.0 / cfg.a;
+    const double origin_r = g.io[0] * (0.5 * inva);
+    return origin_r * cfg.a;
+  }
+  // slot of the k-th loop level of LOOP_OVER_IVECS (yucky_dir, vec.cpp:262-272): X,Y,Z; 2-D: Z,X,Y; Dcyl: P,R,Z
+  int loop_slot(int k) const {
+    if (cfg.dim == MEEPCU_Dcyl) return k == 0 ? 1 : (k == 1 ? 0 : 2);
+    return cfg.dim == MEEPCU_D2 ? (k + 2) % 3 : k;
+  }
+
   // ------------------------------------------------------------------------------------------
   int add_chunk(const meepcu_chunk_desc *d, int *id) {
     if (finalized) return fail(MEEPCU_ESTATE, "context already finalized");
     ChunkH ch;
     ch.d = *d;
+    if (cfg.dim == MEEPCU_Dcyl) canon_chunk_desc(ch.d);
+    d = &ch.d;
     Geom &g = ch.g;
     g.dim = cfg.dim;
-    g.has[0] = g.has[1] = (cfg.dim == MEEPCU_D2 || cfg.dim == MEEPCU_D3);
-    g.has[2] = (cfg.dim == MEEPCU_D1 || cfg.dim == MEEPCU_D3);
+    g.has[0] = (cfg.dim == MEEPCU_D2 || cfg.dim == MEEPCU_D3 || cfg.dim == MEEPCU_Dcyl);
+    g.has[1] = (cfg.dim == MEEPCU_D2 || cfg.dim == MEEPCU_D3);
+    g.has[2] = (cfg.dim == MEEPCU_D1 || cfg.dim == MEEPCU_D3 || cfg.dim == MEEPCU_Dcyl);
     for (int k = 0; k < 3; ++k) {
       g.num[k] = g.has[k] ? d->num[k] : 0;
       g.io[k] = g.has[k] ? d->io[k] : 0;
@@ -629,6 +711,7 @@ template <class T> struct Ctx : CtxBase {
     SuscH s;
     memset(&s, 0, sizeof s);
     s.d = *d;
+    if (cfg.dim == MEEPCU_Dcyl) canon_susc_desc(s.d);
     chunks[chunk].pol[d->ft].push_back(s);
     if (chunks[chunk].pol[d->ft].size() > (size_t)kMaxPol)
       return fail(MEEPCU_EUNSUPPORTED, "more than %d susceptibilities per chunk and field type", kMaxPol);
@@ -667,7 +750,7 @@ template <class T> struct Ctx : CtxBase {
       return fail(MEEPCU_EINVAL, "source ft must be D_stuff or B_stuff");
     SrcH s;
     s.ft = d->ft;
-    s.c = d->c;
+    s.c = cfg.dim == MEEPCU_Dcyl ? canon_comp(d->c) : d->c;
     s.tid = d->src_time_id;
     s.integrated = d->is_integrated;
     s.idx.assign(d->index, d->index + d->n);
@@ -682,6 +765,7 @@ template <class T> struct Ctx : CtxBase {
     if (d->decimation_factor < 1) return fail(MEEPCU_EINVAL, "decimation_factor must be >= 1");
     DftH f;
     f.d = *d;
+    if (cfg.dim == MEEPCU_Dcyl && f.d.c >= 0 && f.d.c < 20) f.d.c = canon_comp(f.d.c);
     f.omega.assign(d->omega, d->omega + d->Nomega);
     f.N = 1;
     for (int k = 0; k < 3; ++k)
@@ -1252,14 +1336,26 @@ template <class T> struct Ctx : CtxBase {
         }
         long long cnt[6] = {0, 0, 0, 0, 0, 0};
         std::vector<int> xyz(3 * it->second.size());
+        std::vector<char> outside(it->second.size(), 0);
         for (size_t k = 0; k < it->second.size(); ++k) {
           long long rem = it->second[k];
           for (int d = 0; d < 3; ++d) {
             int q = 0;
             if (g.has[d]) { q = (int)(rem / g.hs[d]); rem -= q * g.hs[d]; }
             xyz[3 * k + d] = q;
-            if (g.has[d] && q == lo[d]) cnt[d]++;
-            if (g.has[d] && q == hi[d]) cnt[3 + d]++;
+            if (g.has[d] && (q < lo[d] || q > hi[d])) outside[k] = 1;
+          }
+          // Cylindrical cells: find_metals loops over LOOP_OVER_VOL_OWNED, whose range includes the r = 0 row of the
+          // components that live on the axis (vec.cpp:432-436) -- outside the range the stepping kernels own.  Those
+          // points are only ever written by k_cyl_origin; they are cleared by the late k_zero list of the half step.
+          if (outside[k]) {
+            if (cfg.dim != MEEPCU_Dcyl) return fail(MEEPCU_EUNSUPPORTED, "metal point outside the owned range");
+            metal_axis[ft].push_back((T *)r.dev + g.dev_index(it->second[k]));
+            continue;
+          }
+          for (int d = 0; d < 3; ++d) {
+            if (g.has[d] && xyz[3 * k + d] == lo[d]) cnt[d]++;
+            if (g.has[d] && xyz[3 * k + d] == hi[d]) cnt[3 + d]++;
           }
         }
         unsigned m = 0;
@@ -1273,7 +1369,7 @@ template <class T> struct Ctx : CtxBase {
           if (cnt[3 + d] == face) m |= 1u << (3 + ax);
         }
         for (size_t k = 0; k < it->second.size(); ++k) {
-          bool covered = false;
+          bool covered = outside[k] != 0;
           for (int d = 0; d < 3; ++d) {
             if (!g.has[d]) continue;
             const int ax = g.axis_of_dir[d];
@@ -1464,6 +1560,8 @@ template <class T> struct Ctx : CtxBase {
 
     // ---- 5. per-(chunk, half, cmp) parameter blocks + tiles ----
     std::vector<Tile> tiles[2][4], eh_tiles[2], c3d_tiles[2], c3dv_tiles[2], gv_tiles[2][2];
+    std::vector<CylRderiv<T> > cyl_rd[2];
+    std::vector<CylOrigin<T> > cyl_org[2];
     std::vector<FmpParams<T> > fmps[2];
     std::vector<Tile> polgen_tiles[2], polgyro_tiles[2];
     std::vector<int> c3d_chunk, half_chunk; // owning chunk of every h_c3d / h_half entry
@@ -1536,6 +1634,17 @@ template <class T> struct Ctx : CtxBase {
             const bool have_p = ch.have_plus[cc], have_m = ch.have_minus[cc];
             const T *f_p = have_p ? dev(ch.d.f[ch.plus_c[cc]][cmp]) : 0;
             const T *f_m = have_m ? dev(ch.d.f[ch.minus_c[cc]][cmp]) : 0;
+            if (cfg.dim == MEEPCU_Dcyl && k == 2 && f_p) { // step_db.cpp:93-118: f_p := f_rderiv_int (k_cyl_rderiv, every step)
+              if (ch.plus_d[cc] != 0 || f_m) return fail(MEEPCU_ESTATE, "internal: cylindrical step plan");
+              T *S = 0;
+              CU(cudaMalloc((void **)&S, g.ntot_dev * sizeof(T)));
+              extra_dev.push_back((char *)S);
+              CU(cudaMemsetAsync(S, 0, g.ntot_dev * sizeof(T), st));
+              CylRderiv<T> rd = {S, f_p, g.num[0], g.num[2], g.pitch,
+                                 (T)(origin_r_times_a(g) + 0.5 * g.yee_shift(ch.plus_c[cc], 0))};
+              cyl_rd[half].push_back(rd);
+              f_p = S;
+            }
             if (!f_p && !f_m) continue;
             any = true;
             long long sp = have_p ? g.ds[ch.plus_d[cc]] : 0, sm = have_m ? g.ds[ch.minus_d[cc]] : 0;
@@ -1600,6 +1709,21 @@ template <class T> struct Ctx : CtxBase {
                              (g_other ? (half ? -1 : +1) * (2 * cmp - 1) : 1));
               if (c.gb) simple = false;
             }
+            if (cfg.dim == MEEPCU_Dcyl) simple = false; // one code path for cylindrical cells: the most general scalar kernel
+            if (cfg.dim == MEEPCU_Dcyl && cfg.m != 0 && (k == 0 || k == 2)) { // step_db.cpp:177-290
+              const int c_g = dir_comp(half ? MEEPCU_H_STUFF : MEEPCU_E_STUFF, k == 0 ? 2 : 0);
+              c.gm = dev(ch.d.f[c_g][1 - cmp]);
+              if (!c.gm) return fail(MEEPCU_EINVAL, "m != 0 needs complex fields (step_db.cpp:183)");
+              c.the_m = (T)(2 * cfg.m * (1 - 2 * cmp) * (1 - 2 * (half == 0)) * (1 - 2 * (k == 0)) * cfg.courant);
+              c.r0 = g.io[0] + g.yee_shift(cc, 0);
+            }
+            if (cfg.dim == MEEPCU_Dcyl && cfg.m != 0 && fabs(cfg.m) != 1 && g.io[0] == 0 &&
+                ((half == 1 && k >= 1) || (half == 0 && k == 0))) { // step_db.cpp:393-455: rows cleared next to the axis
+              const double rmax = cfg.zero_fields_near_cylorigin ? fabs(cfg.m) - int(origin_r_times_a(g) + 0.5) : 1;
+              int zr = 0;
+              for (int r = 0; r <= g.num[0] && r < rmax; r++) ++zr;
+              c.zrows = zr; // (row 0 itself is not in the owned range of these components: k_cyl_origin clears it)
+            }
 
             // ---- E/H part ----
             if (!ch.d.f[ec][cmp]) continue;
@@ -1630,6 +1754,66 @@ template <class T> struct Ctx : CtxBase {
             c.npol = (int)ch.pol[ft].size();
             if (c.npol) simple = false;
             RC(fill_pols(ch, ft, ec, k, cmp, c.pol));
+          }
+          if (cfg.dim == MEEPCU_Dcyl && g.io[0] == 0) { // the r = 0 rules of step_db.cpp:292-457 -> k_cyl_origin
+            const double m = cfg.m;
+            const int ftg = half ? MEEPCU_H_STUFF : MEEPCU_E_STUFF;
+            const int cR = dir_comp(ft2, 0), cP = dir_comp(ft2, 1), cZ = dir_comp(ft2, 2);
+            CylOrigin<T> O;
+            memset(&O, 0, sizeof O);
+            O.nzp1 = g.num[2] + 1;
+            O.hi = -1;
+            auto clear_rows = [&](int c) { // ZERO_Z of f, f_cond, f_u
+              const void *arrs[3] = {ch.d.f[c][cmp], ch.d.f_cond[c][cmp], ch.d.f_u[c][cmp]};
+              for (int q = 0; q < 3; ++q)
+                if (arrs[q] && O.nzero < 6) O.zero[O.nzero++] = dev(arrs[q]);
+            };
+            int upd = -1; // canonical direction of the component with an explicit row update
+            if (m == 0 && half == 1 && ch.d.f[cZ][cmp]) { upd = 2; clear_rows(cP); }
+            else if (m == 0 && half == 0 && ch.d.f[cR][cmp]) clear_rows(cR);
+            else if (fabs(m) == 1) {
+              if (ch.d.f[half ? cP : cR][cmp]) {
+                upd = half ? 1 : 0;
+                if (half) clear_rows(cZ);
+              }
+            }
+            else if (m != 0) {
+              if (half) { clear_rows(cP); clear_rows(cZ); }
+              else clear_rows(cR);
+            }
+            if (upd >= 0) {
+              const int cc = dir_comp(ft2, upd);
+              const int dsig0 = (upd + 1) % 3, dsigu0 = (upd + 2) % 3;
+              const bool hs = ch.d.sigsize[dsig0] > 1, hu = ch.d.sigsize[dsigu0] > 1;
+              O.cnd = dev(ch.d.conductivity[cc][upd]);
+              O.cndinv = dev(ch.d.condinv[cc][upd]);
+              O.fcnd = dev(ch.d.f_cond[cc][cmp]);
+              if (hs) { O.sig = dev(ch.d.sig[dsig0]); O.kap = dev(ch.d.kap[dsig0]); O.siginv = dev(ch.d.siginv[dsig0]); }
+              if (hu) { O.sigu = dev(ch.d.sig[dsigu0]); O.kapu = dev(ch.d.kap[dsigu0]); O.siginvu = dev(ch.d.siginv[dsigu0]); }
+              O.k_z = dsig0 == 2; O.koff = hs ? g.yee_shift(cc, dsig0) : 0;
+              O.ku_z = dsigu0 == 2; O.kuoff = hu ? g.yee_shift(cc, dsigu0) : 0;
+              T *fmain = dev(ch.d.f[cc][cmp]), *fuarr = dev(ch.d.f_u[cc][cmp]);
+              O.fu = (O.siginvu && fuarr) ? fmain : 0; // step_db.cpp:311-312: the roles of f and f_u are swapped
+              O.the_f = O.fu ? fuarr : fmain;
+              O.lo = 1 - g.yee_shift(cc, 2);
+              O.hi = g.num[2] - g.yee_shift(cc, 2);
+              O.courant = cfg.courant;
+              O.dt2 = (T)(cfg.dt * 0.5);
+              if (m == 0) {
+                O.m0 = 1;
+                O.f_p = dev(ch.d.f[dir_comp(ftg, 1)][cmp]); // H_phi
+                if (!O.f_p) O.the_f = 0;
+              }
+              else {
+                O.sd = half ? +1 : -1;
+                O.f_m_mult = half ? (T)2 : (T)((1 - 2 * cmp) * m);
+                O.f_p = dev(ch.d.f[dir_comp(ftg, half ? 0 : 1)][cmp]); // H_r / E_phi
+                const T *fm = half ? dev(ch.d.f[dir_comp(ftg, 2)][cmp]) : dev(ch.d.f[dir_comp(ftg, 2)][1 - cmp]);
+                O.f_m = fm ? (half ? fm : fm + g.pitch) : 0; // (B: E_z of the other cmp, row r = 1)
+                if (!O.f_p || !O.f_m) return fail(MEEPCU_EINVAL, "|m| = 1 needs complex fields and all components (step_db.cpp:341-386)");
+              }
+            }
+            if (O.the_f || O.nzero) cyl_org[half].push_back(O);
           }
           if (!any) continue;
           // interior fast path: full 3-D chunk, plain curl (+ optional E = u*D), 32-bit indexable
@@ -1736,6 +1920,7 @@ template <class T> struct Ctx : CtxBase {
               if (P.comp[k].f && P.comp[k].npol) heavy = std::max(heavy, 1);
               if (P.comp[k].f && P.comp[k].cnd) heavy = std::max(heavy, 2);
               if (P.comp[k].f && (P.comp[k].gb || P.comp[k].fb)) heavy = 3; // beta / BFAST terms: the most general kernel
+              if (cfg.dim == MEEPCU_Dcyl) heavy = 3;                            // ... and the cylindrical i m / r terms
             }
             // march along the longer outer axis: thin PML slabs still give long streams
             P.march = (g.nax[1] > g.nax[0]) ? 1 : 0;
@@ -1747,7 +1932,7 @@ template <class T> struct Ctx : CtxBase {
             int gseg = n_m <= 24 ? n_m : 16;
             if (getenv("MEEPCU_GSEG")) gseg = std::max(1, atoi(getenv("MEEPCU_GSEG")));
             const int V = (int)(16 / sizeof(T));
-            const bool vec_ok = !getenv("MEEPCU_NO_VEC") && g.pitch % V == 0 && heavy < 2 &&
+            const bool vec_ok = !getenv("MEEPCU_NO_VEC") && g.pitch % V == 0 && heavy < 2 && cfg.dim != MEEPCU_Dcyl &&
                                 (sizeof(T) == 4 || getenv("MEEPCU_GVEC64") || (mix_want && heavy == 0)) &&
                                 !(cfg.dim == MEEPCU_D2 && cfg.beta != 0) && // the beta and BFAST terms live in
                                 !(cfg.bfast_scaled_k[0] || cfg.bfast_scaled_k[1] || cfg.bfast_scaled_k[2]); // the scalar kernel
@@ -2042,6 +2227,7 @@ template <class T> struct Ctx : CtxBase {
     if (n_ranks > 1 && !getenv("MEEPCU_NO_OVERLAP"))
       for (int half = 0; half < 2; ++half) {
         if (general_half[half]) continue; // k_eh_general needs the D halo before E exists: ordered path
+        if (cfg.dim == MEEPCU_Dcyl) continue; // the axis rules (k_cyl_origin, late zero list) live on the ordered path
         if (aniso_half[half]) continue;   // k_pol_general / k_pol_gyro need the W halo before P: ordered path
         if (eager_db[half] || eager_p[half]) continue; // D/B or P halos travel every step (a D/B DFT): ordered path
         const int fts[2] = {half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF, half ? MEEPCU_WE_STUFF : MEEPCU_WH_STUFF};
@@ -2157,6 +2343,12 @@ template <class T> struct Ctx : CtxBase {
         kc_bytes_sv[kc] = kc_bytes_sv[kh] = 0;
       }
     }
+    for (int half = 0; half < 2; ++half) {
+      n_cyl_rd[half] = (int)cyl_rd[half].size();
+      RC(upload(cyl_rd[half], &d_cyl_rd[half]));
+      n_cyl_org[half] = (int)cyl_org[half].size();
+      RC(upload(cyl_org[half], &d_cyl_org[half]));
+    }
     RC(upload(h_half, &d_half));
     RC(upload(h_c3d, &d_c3d));
     for (int half = 0; half < 2; ++half) {
@@ -2178,6 +2370,9 @@ template <class T> struct Ctx : CtxBase {
         const ArrayRec *r = find(metal[fte][k], sizeof(T), &e);
         if (r && r->kind == A_GRID && aniso_chunk_half.count(std::make_pair(r->chunk, half))) late.push_back(dev_elem(metal[fte][k]));
       }
+      const int ftd = half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF;
+      late.insert(late.end(), metal_axis[ftd].begin(), metal_axis[ftd].end());
+      late.insert(late.end(), metal_axis[fte].begin(), metal_axis[fte].end());
       n_zero_late[half] = (long long)late.size();
       RC(upload(late, &d_zero_late[half]));
     }
@@ -2356,7 +2551,7 @@ template <class T> struct Ctx : CtxBase {
         // LOOP_OVER_IVECS in the reference's loop order (vec.hpp:151-168; yucky_dir vec.cpp:262-272)
         long long idx0 = 0;
         for (int k = 0; k < 3; ++k) {
-          const int dir = cfg.dim == MEEPCU_D2 ? (k + 2) % 3 : k;
+          const int dir = loop_slot(k);
           q.dir[k] = dir;
           if (g.has[dir]) {
             q.n[k] = (d.ie[dir] - d.is[dir]) / 2 + 1;
@@ -2735,11 +2930,21 @@ template <class T> struct Ctx : CtxBase {
     return MEEPCU_OK;
   }
 
+  int launch_cyl_origin(int half) { // the r = 0 rules of step_db.cpp:292-457, after the curls of the half step
+    if (!n_cyl_org[half]) return MEEPCU_OK;
+    k_cyl_origin<T><<<dim3(4, (unsigned)std::min(n_cyl_org[half], 1024)), kThreads, 0, st>>>(d_cyl_org[half], n_cyl_org[half]);
+    launches++;
+    return MEEPCU_OK;
+  }
   int launch_half(int half, const double *smp) {
     const int ftd = half ? MEEPCU_D_STUFF : MEEPCU_B_STUFF;
     const int fte = half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF;
     const int ftp = half ? MEEPCU_PE_STUFF : MEEPCU_PH_STUFF;
     const int ftw = half ? MEEPCU_WE_STUFF : MEEPCU_WH_STUFF;
+    if (n_cyl_rd[half]) { // cylindrical: f_rderiv_int of this half's phi operand (step_db.cpp:93-118), before the curls
+      k_cyl_rderiv<T><<<dim3(4, (unsigned)std::min(n_cyl_rd[half], 1024)), kThreads, 0, st>>>(d_cyl_rd[half], n_cyl_rd[half]);
+      launches++;
+    }
     if (overlap_half[half] && !profiling) {
       // boundary tiles -> [halo exchange on st_comm  ||  interior tiles + local halo copies] -> join.
       // The exchange writes only not-owned points of E/H (W), which no kernel of this half reads.
@@ -2755,12 +2960,14 @@ template <class T> struct Ctx : CtxBase {
       CU(cudaEventRecord(ev_cdone, st_comm));
       RC(launch_compute(half, smp, 2, st, st2));
       CU(cudaStreamWaitEvent(st, ev_bdone, 0)); // the local halo copies read boundary tiles' results too
+      RC(launch_cyl_origin(half));
       RC(launch_conn_local(ftw));
       RC(launch_conn_local(fte));
       CU(cudaStreamWaitEvent(st, ev_cdone, 0));
       return MEEPCU_OK;
     }
     RC(launch_compute(half, smp, 0, st, st2));
+    RC(launch_cyl_origin(half));
     if (eager_db[half]) RC(launch_conn(ftd)); // step.cpp:72,104
     if (general_half[half]) {
       if (n_fmp[half]) {
@@ -3269,7 +3476,7 @@ template <class T> struct Ctx : CtxBase {
         }
       long long idx0 = 0, N = 1;
       for (int k = 0; k < 3; ++k) { // LOOP_OVER_IVECS in the reference's loop order (vec.hpp:151-168)
-        const int dir = cfg.dim == MEEPCU_D2 ? (k + 2) % 3 : k;
+        const int dir = loop_slot(k);
         q.dir[k] = dir;
         if (g.has[dir]) {
           if (d.ie[dir] < d.is[dir]) { N = 0; break; }
@@ -3423,7 +3630,6 @@ int meepcu_abi_version(void) { return MEEPCU_ABI_VERSION; }
 int meepcu_create(const meepcu_config *cfg, meepcu_ctx **out) {
   if (!cfg || !out) return fail(MEEPCU_EINVAL, "null argument");
   if (cfg->abi_version != MEEPCU_ABI_VERSION) return fail(MEEPCU_EINVAL, "ABI version mismatch");
-  if (cfg->dim == MEEPCU_Dcyl) return fail(MEEPCU_EUNSUPPORTED, "cylindrical coordinates are not on the GPU path");
   if (cfg->dim < 0 || cfg->dim > 3) return fail(MEEPCU_EINVAL, "bad dim");
   if (cfg->nl_mode != MEEPCU_NL_FORK_LITERAL && cfg->nl_mode != MEEPCU_NL_UPSTREAM_PADE)
     return fail(MEEPCU_EINVAL, "bad nl_mode");

@@ -26,6 +26,12 @@ CASES = [("fp64", "vac3d:48", 60, 3, 1e-12), ("fp32", "vac3d:48", 60, 3, 1e-5),
          ("fp64", "gyrosat3d:20", 100, 2, 1e-12),
          ("fp64", "dft2d:60", 200, 2, 1e-12), ("fp32", "dft2d:60", 200, 2, 1e-5), ("fp64", "dft3d:24", 100, 2, 1e-12),
          ("fp64", "aniso3d:24", 100, 2, 1e-12), ("fp32", "aniso3d:24", 100, 2, 1e-5),
+         # cylindrical coordinates: f_rderiv_int pre-pass, i m / r terms through the PML / conductivity chain, r = 0 rules
+         ("fp64", "cyl:30:0", 200, 0, 1e-12), ("fp64", "cyl:30:1", 200, 0, 1e-12), ("fp32", "cyl:30:-1", 200, 0, 1e-5),
+         ("fp64", "cylper:30:2", 200, 2, 1e-12), ("fp64", "cylpml:40:0", 200, 2, 1e-12), ("fp64", "cylpml:40:1", 200, 0, 1e-12),
+         ("fp32", "cylpml:40:1", 200, 0, 1e-5), ("fp64", "cylpml:40:3", 200, 0, 1e-12), ("fp64", "cylpmlnz:40:3", 200, 0, 1e-12),
+         ("fp64", "cylcond:40:1", 200, 2, 1e-12), ("fp32", "cylcond:40:2", 200, 0, 1e-5), ("fp64", "cyllor:40:1", 200, 2, 1e-12),
+         ("fp32", "cyllor:40:0", 200, 0, 1e-5), ("fp64", "cyllor:36:2", 200, 0, 1e-12), ("fp64", "cylpml:600:1", 60, 0, 1e-12),
          ("fp64_pade", "kerr3d:20", 40, 2, 1e-12), ("fp64_pade", "kr_per3d_rods", 100, 0, 1e-12)]
 
 
@@ -89,7 +95,8 @@ def test_known_results_on_gpu():
                                                     ("fp64", "lorentz3d:32", 50, 1e-12), ("fp64", "wvg2d", 200, 1e-12),
                                                     ("fp64", "kr_per3d_rods", 100, 1e-12), ("fp64", "cond3d:24", 60, 1e-12),
                                                     ("fp64", "magdrude3d:24", 60, 1e-12), ("fp64", "aniso3d:24", 60, 1e-12),
-                                                    ("fp64", "gyrosat3d:20", 60, 1e-12)])
+                                                    ("fp64", "gyrosat3d:20", 60, 1e-12), ("fp64", "cylpml:40:1", 60, 1e-12),
+                                                    ("fp64", "cyllor:40:0", 60, 1e-12)])
 def test_synchronize_magnetic_fields_on_device(flavour, case, steps, tol):
     """fields::synchronize_magnetic_fields / restore_magnetic_fields (energy_and_flux.cpp:145-177) every 9
     steps: twin A on the reference's CPU path, twin B through meepcu_synchronize_magnetic_fields on the GPU"""
@@ -108,7 +115,8 @@ def test_synchronize_magnetic_fields_on_device(flavour, case, steps, tol):
 
 @pytest.mark.parametrize("flavour,case,chunks,tol", [("fp64", "vac3d:48", 4, 1e-12), ("fp32", "lorentz3d:32", 3, 1e-5),
                                                      ("fp64", "nrslab3d:20", 3, 1e-12), ("fp64", "aniso3d:24", 5, 1e-12),
-                                                     ("fp64", "dft3d:24", 3, 1e-12)])
+                                                     ("fp64", "dft3d:24", 3, 1e-12), ("fp64", "cyllor:48:1", 3, 1e-12),
+                                                     ("fp32", "cylpml:48:2", 4, 1e-5)])
 def test_reference_chunk_splitting_on_gpu(flavour, case, chunks, tol):
     """the reference's own cost-based chunk splitting (structure(..., num_chunks)): 40-50 chunks instead of 27"""
     drv = ref_driver(flavour)
