@@ -572,13 +572,17 @@ def measure(args, backend, rank, world, local, dist, comm_id, sampler, with_pari
         ach_moved = dom["bytes_moved"] / (per_launch_ms * 1e-3) / 1e9
         step_bytes = int(sv_step.value) or st1.algorithmic_bytes_per_step
         step_moved = st1.algorithmic_bytes_per_step
-        roof = {"bound": "hbm", "kernel": dom["name"], "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": per_launch_ms,
-                "accounting": "achieved = SURVEY.md 8(d) bytes (every array of the reference's update once per read and once per "
-                              "write per half step: 21 values per vacuum cell, 24 with eps) / launch time; `moved` = the bytes this "
-                              "implementation has to move (chunks that do not store E while stepping: 18 / 21) / the same time",
-                "moved": {"bytes_per_launch": dom["bytes_moved"], "achieved": ach_moved, "frac": ach_moved / peak},
+        roof = {"bound": "hbm", "kernel": dom["name"], "achieved": ach_moved, "peak": peak, "unit": "GB/s",
+                "frac": ach_moved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom["bytes_moved"], "ms_per_launch": per_launch_ms,
+                "accounting": "per kernel: achieved = the bytes this launch has to move (every array element once per read and once "
+                              "per write; chunks that do not store E while stepping move 18 values per vacuum cell and step, 21 "
+                              "with eps) / its CUDA-event time -- comparable with `traffic` (ncu DRAM bytes).  `survey` = the same "
+                              "launch credited with SURVEY.md 8(d)'s figures (21 / 24 values: E written by the D/E half, read back "
+                              "by the B/H half) -- an effective bandwidth, which exceeds the moved one for the D/E half and falls "
+                              "below it for the B/H half of such chunks; over the whole step (`whole_step.frac`) it is the "
+                              "metric's own byte count per cell update",
+                "survey": {"bytes_per_launch": dom["bytes"], "achieved": ach, "frac": ach / peak},
                 "whole_step": {"achieved": step_bytes * K / (dev_ms * 1e-3) / 1e9,
                                "frac": step_bytes * K / (dev_ms * 1e-3) / 1e9 / peak,
                                "frac_of_8TBs_nominal": step_bytes * K / (dev_ms * 1e-3) / 8e12,

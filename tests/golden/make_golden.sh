@@ -49,7 +49,11 @@ for fl in fp64 fp32; do
   gen $fl magdrude2d:24 40 2
   gen $fl dft3d:12 40 2
   gen $fl beta2d_cplx 40 2
+  gen $fl cylpml:14:1 40 0
+  gen $fl cyllor:14:0 40 0
 done
+gen fp64 cylper:12:2 40 0
+gen fp64 cylpmlnz:14:3 40 0
 gen fp64 nr3d:10 30 0
 gen fp64 nrslab3d:14 30 2
 if [ -x oracle/_ref/fp64_pade/ref_driver ]; then
