@@ -36,8 +36,14 @@ namespace mcu {
 
 constexpr int kThreads = 256;
 constexpr int kMaxPol = 4;
-#ifndef MCU_PREFETCH_PLANES
-#define MCU_PREFETCH_PLANES 2
+// How many planes ahead of the march the operands are pulled into L2 (prefetch.global.L2).  What matters is the
+// distance in bytes: measured on the B200 (r02o, ms per step at 0 / 1 / 2 planes) -- fp64: vacuum 256^3 0.717 / 0.591 /
+// 0.563, eps slab 384^2 x 576 2.93 / 2.63 / 2.45, Lorentzian 256^3 1.357 / 1.157 / 1.137; fp32: vacuum 256^3 0.374 /
+// 0.308 / 0.311, eps slab 512^2 x 768 3.20 / 2.82 / 2.98 (3 and 4 planes: 3.31 / 3.71).  -DMCU_PREFETCH_PLANES=n forces n.
+#ifdef MCU_PREFETCH_PLANES
+template <class T> __host__ __device__ constexpr int pf_planes() { return MCU_PREFETCH_PLANES; }
+#else
+template <class T> __host__ __device__ constexpr int pf_planes() { return sizeof(T) == 4 ? 1 : 2; }
 #endif
 
 __device__ __forceinline__ void prefetch_l2(const void *p) {
@@ -436,8 +442,8 @@ __global__ void __launch_bounds__(kThreads, HAS_COND ? 2 : 3)
 #pragma unroll 2
   for (int im = m0; im <= m1; ++im, i += s_m) {
     const int ia = march ? io : im, ib = march ? im : io;
-    if (MCU_PREFETCH_PLANES > 0 && im + MCU_PREFETCH_PLANES <= m1) {
-      const long long ipf = i + MCU_PREFETCH_PLANES * s_m;
+    if (pf_planes<T>() > 0 && im + pf_planes<T>() <= m1) {
+      const long long ipf = i + pf_planes<T>() * s_m;
       prefetch_l2(c.g1 + ipf);
       if (c.g2) prefetch_l2(c.g2 + ipf);
       prefetch_l2(c.f + ipf);
@@ -618,10 +624,10 @@ __device__ __forceinline__ void curl3d_loop(const Curl3DParams<T> &P, const Tile
   for (int ia = t.a0; ia < t.a1; ++ia, i += sA) {
     const bool on0 = act[0] && ia >= lo0 && ia <= hi0, on1 = act[1] && ia >= lo1 && ia <= hi1,
                on2 = act[2] && ia >= lo2 && ia <= hi2;
-    if (MCU_PREFETCH_PLANES > 0 && ia + MCU_PREFETCH_PLANES < nA) {
+    if (pf_planes<T>() > 0 && ia + pf_planes<T>() < nA) {
       // pull the planes this thread will need a few iterations from now into L2: turns the
       // DRAM latency of the marching loads into L2 latency without holding registers
-      const int ipf = i + MCU_PREFETCH_PLANES * sA;
+      const int ipf = i + pf_planes<T>() * sA;
       prefetch_l2(gx + ipf);
       prefetch_l2(gy + ipf);
       prefetch_l2(gz + ipf);
@@ -836,8 +842,8 @@ __device__ __forceinline__ void curl3d_v_body(const Curl3DParams<T> &P, const Ti
   for (int ia = t.a0; ia < t.a1; ++ia, i += sA) {
     const unsigned m0 = (ia >= lo0 && ia <= hi0) ? zmask[0] : 0u, m1 = (ia >= lo1 && ia <= hi1) ? zmask[1] : 0u,
                    m2 = (ia >= lo2 && ia <= hi2) ? zmask[2] : 0u;
-    if (MCU_PREFETCH_PLANES > 0 && ia + MCU_PREFETCH_PLANES < nA) {
-      const int ipf = i + MCU_PREFETCH_PLANES * sA;
+    if (pf_planes<T>() > 0 && ia + pf_planes<T>() < nA) {
+      const int ipf = i + pf_planes<T>() * sA;
       prefetch_l2(gx + ipf);
       prefetch_l2(gy + ipf);
       prefetch_l2(gz + ipf);
@@ -1061,8 +1067,8 @@ __device__ __forceinline__ void halfg_v_body(const HalfHeader<T> &H, const CompP
     if (var_k) load_coef<T, false>(c.sig, c.kap, c.siginv, c.kaxis, c.koff, ia, ib, ic, cA, cB);
     if (var_ku) load_coef<T, false>(c.sigu, c.kapu, c.siginvu, c.kuaxis, c.kuoff, ia, ib, ic, uA, uB);
     if (var_kw) load_coef<T, true>(c.sigw, c.kapw, c.kapw, c.kwaxis, c.kwoff, ia, ib, ic, wP, wM);
-    if (MCU_PREFETCH_PLANES > 0 && im + MCU_PREFETCH_PLANES <= m1) {
-      const long long ipf = i + MCU_PREFETCH_PLANES * s_m;
+    if (pf_planes<T>() > 0 && im + pf_planes<T>() <= m1) {
+      const long long ipf = i + pf_planes<T>() * s_m;
       prefetch_l2(c.g1 + ipf);
       if (c.g2) prefetch_l2(c.g2 + ipf);
       prefetch_l2(c.f + ipf);
@@ -1429,6 +1435,34 @@ __global__ void k_fmp_src(const FmpParams<T> *__restrict__ tab, int ntab,
     const double2 dp = sample_dipole(smp, e.tid, q.is_D);
     const double2 A = cmul(e.are, e.aim, dp.x, dp.y);
     q.fmp[e.idx] = (T)((double)q.fmp[e.idx] - (q.cmp ? A.y : A.x));
+  }
+}
+
+// Where f_minus_p would be D minus dipoles only (no polarisation), it is not materialised: the E update reads D
+// itself and the handful of dipole points are patched in place around it -- saved, replaced by
+// (T)((double)D - dipoles) in list order like update_eh.cpp:136-146, and put back bit for bit afterwards.
+template <class T> struct DipPatch {
+  T *d;
+  const SrcEntry *isrc; // sorted by index (stable in reference order)
+  int n, is_D, cmp;
+  T *saved;             // n slots; the slot of the first entry of an index holds the original value
+};
+template <class T>
+__global__ void k_dip_patch(const DipPatch<T> *__restrict__ tab, int ntab, const double *__restrict__ smp, int restore) {
+  const int it = blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= ntab) return;
+  const DipPatch<T> q = tab[it];
+  for (int j = 0; j < q.n; ++j) {
+    const SrcEntry e = q.isrc[j];
+    const bool first = j == 0 || q.isrc[j - 1].idx != e.idx;
+    if (restore) {
+      if (first) q.d[e.idx] = q.saved[j];
+      continue;
+    }
+    if (first) q.saved[j] = q.d[e.idx];
+    const double2 dp = sample_dipole(smp, e.tid, q.is_D);
+    const double2 A = cmul(e.are, e.aim, dp.x, dp.y);
+    q.d[e.idx] = (T)((double)q.d[e.idx] - (q.cmp ? A.y : A.x));
   }
 }
 
@@ -1803,10 +1837,10 @@ __global__ void __launch_bounds__(kThreads, CTAS)
   const int a1 = t.a1 - 1 < P.hi[0] ? t.a1 - 1 : P.hi[0];
   long long i = (long long)a0 * P.sA + (long long)ib * P.sB + ic;
   for (int ia = a0; ia <= a1; ++ia, i += P.sA) {
-    if (MCU_PREFETCH_PLANES > 0 && ia + MCU_PREFETCH_PLANES <= a1) {
+    if (pf_planes<T>() > 0 && ia + pf_planes<T>() <= a1) {
       // the operands of this thread's point two planes ahead, into L2 (r02d ncu: 45 % of the kernel's stall samples
       // were the first dependent instructions after the loads of a point -- DRAM latency, once per point)
-      const long long ipf = i + MCU_PREFETCH_PLANES * P.sA;
+      const long long ipf = i + pf_planes<T>() * P.sA;
       prefetch_l2(P.g + ipf);
       if (P.u) prefetch_l2(P.u + ipf);
       if (P.mask) prefetch_l2(P.mask + ipf);

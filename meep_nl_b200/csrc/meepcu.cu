@@ -377,6 +377,8 @@ template <class T> struct Ctx : CtxBase {
   int n_eh_tiles[2];
   FmpParams<T> *d_fmp[2];
   int n_fmp[2];
+  DipPatch<T> *d_dip[2]; // dipole points patched in place around k_eh_general (kernels.cuh, DipPatch)
+  int n_dip[2];
   bool fmp_has_src[2];
   ConnTable<T> d_conn[MEEPCU_NUM_FIELD_TYPES][3];
   ConnRun<T> *d_runs[MEEPCU_NUM_FIELD_TYPES]; // COPY + NEGATE lists in run-length form
@@ -553,6 +555,8 @@ template <class T> struct Ctx : CtxBase {
     memset(n_tiles, 0, sizeof n_tiles);
     memset(d_eh_tiles, 0, sizeof d_eh_tiles);
     memset(n_eh_tiles, 0, sizeof n_eh_tiles);
+    memset(d_dip, 0, sizeof d_dip);
+    memset(n_dip, 0, sizeof n_dip);
     memset(d_fmp, 0, sizeof d_fmp);
     memset(n_fmp, 0, sizeof n_fmp);
     memset(d_conn, 0, sizeof d_conn);
@@ -1563,6 +1567,7 @@ template <class T> struct Ctx : CtxBase {
     std::vector<CylRderiv<T> > cyl_rd[2];
     std::vector<CylOrigin<T> > cyl_org[2];
     std::vector<FmpParams<T> > fmps[2];
+    std::vector<DipPatch<T> > dips[2];
     std::vector<Tile> polgen_tiles[2], polgyro_tiles[2];
     std::vector<int> c3d_chunk, half_chunk; // owning chunk of every h_c3d / h_half entry
     // interior and PML tiles of a half in one grid (k_mix); fp64 PML tiles are vectorised only for that
@@ -2018,7 +2023,28 @@ template <class T> struct Ctx : CtxBase {
                 for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip)
                   if (ch.pol[ft][ip].d.P[ec][cmp]) need_fmp = true;
               }
-              if (need_fmp) {
+              bool has_pol = false;
+              for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip)
+                if (ch.d.f[ec][cmp] && ch.pol[ft][ip].d.P[ec][cmp]) has_pol = true;
+              if (need_fmp && !has_pol && !getenv("MEEPCU_FMP_ALWAYS")) {
+                // f_minus_p = D - dipoles: not materialised (a whole-array pass for a handful of points); the dipole
+                // points of this component are patched in place around k_eh_general instead (DipPatch)
+                const SrcRange &R = ranges[(ic * 2 + half) * 3 + k];
+                if (R.i1 > R.i0) {
+                  DipPatch<T> dp;
+                  memset(&dp, 0, sizeof dp);
+                  dp.d = dev(ch.d.f[dc][cmp]);
+                  dp.isrc = d_src + R.i0;
+                  dp.n = (int)(R.i1 - R.i0);
+                  dp.is_D = half;
+                  dp.cmp = cmp;
+                  CU(cudaMalloc((void **)&dp.saved, (size_t)dp.n * sizeof(T)));
+                  extra_dev.push_back((char *)dp.saved);
+                  dips[half].push_back(dp);
+                }
+                dmp[k] = dev(ch.d.f[dc][cmp]);
+              }
+              else if (need_fmp) {
                 T *scratch = 0;
                 CU(cudaMalloc((void **)&scratch, g.ntot_dev * sizeof(T)));
                 extra_dev.push_back((char *)scratch);
@@ -2393,6 +2419,8 @@ template <class T> struct Ctx : CtxBase {
       RC(upload(eh_tiles[half], &d_eh_tiles[half]));
       n_fmp[half] = (int)fmps[half].size();
       RC(upload(fmps[half], &d_fmp[half]));
+      n_dip[half] = (int)dips[half].size();
+      RC(upload(dips[half], &d_dip[half]));
     }
 
     // ---- 6. connections ----
@@ -2981,16 +3009,26 @@ template <class T> struct Ctx : CtxBase {
           launches++;
         }
       }
+      if (n_dip[half]) { // dipole points: D := D - dipoles in place (originals saved), put back after the E update
+        k_dip_patch<T><<<(n_dip[half] + 63) / 64, 64, 0, st>>>(d_dip[half], n_dip[half], smp, 0);
+        launches++;
+      }
       if (n_eh_tiles[half]) { // (the flag is global: this rank may own no such chunk)
         RC(prof_begin(KC_EH_GENERAL));
         // resident CTAs per SM (= registers per thread): MEEPCU_EH_CTAS = 2 / 3 / 4 / 5 select builds with 128 / 80 / 64 /
         // 48 registers (measurements at MCU_EH_CTAS in kernels.cuh)
-        static const int eh_ctas = getenv("MEEPCU_EH_CTAS") ? atoi(getenv("MEEPCU_EH_CTAS")) : MCU_EH_CTAS;
+        // (the Pade update has no iteration to keep in registers: 5 CTAs, 2.55 vs 2.83 ms at 384^3; NR: 4, 4.34 vs 4.81)
+        const int eh_ctas = getenv("MEEPCU_EH_CTAS") ? atoi(getenv("MEEPCU_EH_CTAS"))
+                                                     : (cfg.nl_mode == MEEPCU_NL_UPSTREAM_PADE ? 5 : MCU_EH_CTAS);
         if (eh_ctas == 2) k_eh_general<T, 2><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
         else if (eh_ctas == 3) k_eh_general<T, 3><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
         else if (eh_ctas == 5) k_eh_general<T, 5><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
         else k_eh_general<T, 4><<<n_eh_tiles[half], kThreads, 0, st>>>(d_eh, d_eh_tiles[half]);
         RC(prof_end());
+        launches++;
+      }
+      if (n_dip[half]) {
+        k_dip_patch<T><<<(n_dip[half] + 63) / 64, 64, 0, st>>>(d_dip[half], n_dip[half], smp, 1);
         launches++;
       }
     }
