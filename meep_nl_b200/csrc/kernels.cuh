@@ -34,6 +34,9 @@
 
 namespace mcu {
 
+#ifndef MCU_C3DV_F64_CTAS
+#define MCU_C3DV_F64_CTAS 2 // resident CTAs per SM of the fp64 interior vector kernel (128 registers)
+#endif
 constexpr int kThreads = 256;
 constexpr int kMaxPol = 4;
 // How many planes ahead of the march the operands are pulled into L2 (prefetch.global.L2).  What matters is the
@@ -933,7 +936,7 @@ __device__ __forceinline__ void curl3d_v_body(const Curl3DParams<T> &P, const Ti
 }
 
 template <class T, bool IS_D, bool VU = false>
-__global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : 3)
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? MCU_C3DV_F64_CTAS : 3)
     k_curl3d_v(const Curl3DParams<T> *__restrict__ params, const Tile *__restrict__ tiles, int vmode) {
   __shared__ Curl3DParams<T> P;
   const Tile t = tiles[blockIdx.x];
@@ -1292,8 +1295,11 @@ constexpr int kTileGeneral = 1 << 29; // Tile::p0 flag inside a k_mix table
 #ifndef MCU_MIX_F32_CTAS
 #define MCU_MIX_F32_CTAS 3
 #endif
+#ifndef MCU_MIX_F64_CTAS
+#define MCU_MIX_F64_CTAS 2
+#endif
 template <class T, bool IS_D, bool VU = false>
-__global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? 2 : MCU_MIX_F32_CTAS)
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 8 ? MCU_MIX_F64_CTAS : MCU_MIX_F32_CTAS)
     k_mix(const Curl3DParams<T> *__restrict__ cparams, const HalfParams<T> *__restrict__ hparams,
           const Tile *__restrict__ tiles, int vmode) {
   struct G { HalfHeader<T> H; CompParams<T> C; };

@@ -27,6 +27,7 @@
 #include <string>
 #include <vector>
 #include <dlfcn.h>
+#include <omp.h>
 
 using namespace mcu;
 
@@ -1415,6 +1416,15 @@ template <class T> struct Ctx : CtxBase {
     if (cfg.dim != MEEPCU_D2 && cfg.beta != 0)
       return fail(MEEPCU_EINVAL, "Nonzero beta unsupported in dimensions other than 2."); // fields.cpp:559-560
 
+    const bool tm_on = getenv("MEEPCU_TIMING") != 0;
+    double tm_last = omp_get_wtime();
+    auto tm_mark = [&](const char *what) {
+      if (!tm_on) return;
+      cudaStreamSynchronize(st);
+      const double now = omp_get_wtime();
+      fprintf(stderr, "[meepcu_finalize] %-28s %8.3f s\n", what, now - tm_last);
+      tm_last = now;
+    };
     // ---- 1. register every array ----
     for (size_t ic = 0; ic < chunks.size(); ++ic) {
       ChunkH &ch = chunks[ic];
@@ -1494,10 +1504,12 @@ template <class T> struct Ctx : CtxBase {
       }
     RC(sync_groups(false, ~0u)); // everything, materials included
 
+    tm_mark("register + arena + upload");
     // ---- 3. metal planes ----
     std::map<const char *, unsigned> zmask;
     RC(metal_masks(zmask));
 
+    tm_mark("metal masks");
     // ---- 4. sources -> sorted device tables ----
     std::vector<SrcEntry> all_src;
     struct SrcRange { size_t c0, c1, i0, i1; int ca0, ca1, ia0, ia1; };
@@ -1562,6 +1574,7 @@ template <class T> struct Ctx : CtxBase {
       for (size_t ic = 0; ic < chunks.size(); ++ic)
         if (virt_eligible(ic, zmask)) virt_chunks.insert((int)ic);
 
+    tm_mark("sources, virtual chunks");
     // ---- 5. per-(chunk, half, cmp) parameter blocks + tiles ----
     std::vector<Tile> tiles[2][4], eh_tiles[2], c3d_tiles[2], c3dv_tiles[2], gv_tiles[2][2];
     std::vector<CylRderiv<T> > cyl_rd[2];
@@ -2220,6 +2233,7 @@ template <class T> struct Ctx : CtxBase {
         aniso_now = false;
       }
     }
+    tm_mark("parameter blocks + tiles");
     // ---- 5a. which halo exchanges run every step.  The schedule must be the SAME on every rank: a rank that
     // owns only PML chunks and a rank that owns nonlinear ones would otherwise post different ncclSend/ncclRecv
     // groups (one side waiting for a D halo the other never sends).  So the flags are OR-ed over the communicator.
@@ -2425,6 +2439,7 @@ template <class T> struct Ctx : CtxBase {
       RC(upload(dips[half], &d_dip[half]));
     }
 
+    tm_mark("schedule, boundary tiles, mix");
     // ---- 6. connections ----
     // which E/H connections can wait for the next host sync: 3-D, and nobody but the curl kernels reads
     // E/H neighbours (no k_eh_general / k_pol_general / DFT averaging / cross-rank lists built from them)
@@ -2545,6 +2560,7 @@ template <class T> struct Ctx : CtxBase {
     // W exchanges are only non-empty for anisotropic susceptibilities (rejected above)
     RC(build_remote());
 
+    tm_mark("connections");
     // ---- 7. DFT chunks ----
     std::vector<DftWork> work;
     phase_row = 0;
@@ -2626,6 +2642,7 @@ template <class T> struct Ctx : CtxBase {
     n_dft_work = (int)work.size();
     RC(upload(phase_off, &d_phase_off));
 
+    tm_mark("dft");
     // ---- 8. the lazy NaN test (step.cpp:138-139): table of the field arrays + a flag the device can raise ----
     {
       std::vector<FinEntry> fin;
