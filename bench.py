@@ -102,8 +102,12 @@ def workload_name(args, nslabs=1):
 def config_of(args, nslabs=1):
     """identical in both arms (ours / reference)"""
     d = grid_dims(args, nslabs)
+    note = None
+    if nslabs > 1 and args.workload != "phc3d":
+        note = ("PML on all six faces of the WHOLE grid: an end rank has one X-PML face, a middle rank none, the single GPU "
+                "two -- per-GPU work is not constant (efficiency can exceed 1); constant per-GPU work: configs.config5_weak")
     return {"workload": workload_name(args, nslabs), "grid": list(d), "cells": d[0] * d[1] * d[2],
-            "scaling": args.scaling if nslabs > 1 else "single GPU",
+            "scaling": args.scaling if nslabs > 1 else "single GPU", **({"note": note} if note else {}),
             "l2": "working set >> 126 MB L2, every array streamed once per half step (no flush needed)"}
 
 

@@ -694,7 +694,7 @@ class fields:
         b, ctx = self.b, self.ctx
         rt = self.s.rt
         ct = np.complex128 if rt.itemsize == 8 else np.complex64
-        for (c, lo, hi, freqs, decim) in getattr(self, "_pending_dfts", []):
+        for mon, (c, lo, hi, freqs, decim) in enumerate(getattr(self, "_pending_dfts", [])):
             for gi_, fc in enumerate(self.chunks):
                 gv = fc.gv
                 if (c, 0) not in fc.f or not fc.mine: continue
@@ -727,7 +727,7 @@ class fields:
                 arr = np.zeros(N * om.size, ct)
                 dd.dft = arr.ctypes.data
                 self._keep += [om]
-                fc.dfts.append(dict(c=c, dft=arr, N=N, nomega=om.size))
+                fc.dfts.append(dict(c=c, dft=arr, N=N, nomega=om.size, mon=mon))
                 b.check(b.add_dft(ctx, i, C.byref(dd), None))
 
     # -- stepping -------------------------------------------------------------------------------
@@ -803,6 +803,61 @@ class fields:
     def sync_dft_to_host(self):
         """all that dft_flux::flux / dft_energy / near2far read (src/dft.cpp:533-548,630-700)"""
         self.sync_subset(True, A.SYNC_DFT)
+
+    def dft_dot(self, mon_a, mon_b):
+        """out[i] = sum over the chunks and points of monitors mon_a, mon_b (indices in add_dft_fields order; same box,
+        components on the same Yee grid) of Re(a.dft * conj(b.dft)), summed on the device (meepcu_dft_dot): the loop of
+        dft_flux::flux / dft_energy::electric, magnetic (src/dft.cpp:533-548,657-687) without fetching an accumulator"""
+        self.init()
+        pa, pb, nom = [], [], None
+        for fc in self.chunks:
+            if not fc.mine: continue
+            da = [d for d in fc.dfts if d["mon"] == mon_a]
+            db = [d for d in fc.dfts if d["mon"] == mon_b]
+            if not da and not db: continue
+            assert len(da) == 1 and len(db) == 1 and da[0]["N"] == db[0]["N"], "monitors do not cover the same points"
+            pa.append(da[0]["dft"].ctypes.data); pb.append(db[0]["dft"].ctypes.data)
+            nom = da[0]["nomega"]
+        out = np.zeros(nom or 0, np.float64)
+        if pa:
+            a = np.asarray(pa, np.uint64); b = np.asarray(pb, np.uint64)
+            self.b.check(self.b.dft_dot(self.ctx, len(pa), a.ctypes.data, b.ctypes.data, nom,
+                                        out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def integrate_dot(self, c0, c1, lo, hi):
+        """sum over the Yee indices lo..hi (inclusive, global cells; c0 and c1 on the same Yee grid, e.g. Ex and Dx) of
+        Re(conj(f_c0) f_c1) with unit weights, and max |.|, reduced on the device (meepcu_integrate_dot): the loop of
+        fields::integrate(2, cs, dot_integrand, ...) (src/integrate.cpp:47-131) with the weights of an interior box"""
+        self.init()
+        gv = self.gv
+        pieces = []
+        for fc in self.chunks:
+            if not fc.mine or (c0, 0) not in fc.f or (c1, 0) not in fc.f: continue
+            cg = fc.gv
+            d = A.IntegrateDesc()
+            ok = True
+            for k in range(3):
+                d.s0[k] = d.s1[k] = d.e0[k] = d.e1[k] = 1.0
+                if not gv.has[k]: continue
+                off = (cg.io[k] - gv.io[k]) // 2
+                o0, o1 = cg.owned_range(c0, k)
+                a, b = max(int(lo[k]), off + o0), min(int(hi[k]), off + o1)
+                if a > b: ok = False; break
+                d.is_[k] = cg.io[k] + 2 * (a - off) + cg.yee_shift(c0, k)
+                d.ie[k] = cg.io[k] + 2 * (b - off) + cg.yee_shift(c0, k)
+            if not ok: continue
+            for i, c in enumerate((c0, c1)):
+                d.f[i][0] = fc.f[(c, 0)].ctypes.data
+                d.f[i][1] = fc.f[(c, 1)].ctypes.data if (c, 1) in fc.f else None
+                d.ph[i][0], d.ph[i][1] = 1.0, 0.0
+            d.dV0, d.dV1 = 1.0, 0.0
+            pieces.append(d)
+        s_, m_ = C.c_double(0), C.c_double(0)
+        if pieces:
+            arr = (A.IntegrateDesc * len(pieces))(*pieces)
+            self.b.check(self.b.integrate_dot(self.ctx, len(pieces), arr, C.byref(s_), C.byref(m_)))
+        return s_.value, m_.value
 
     def get_array_slice(self, c, lo, hi, cmp=0):
         """fields::get_array_slice without interpolation (src/array_slice.cpp): the values of component c

@@ -261,6 +261,62 @@ def test_cuda_slices_dft_and_partial_sync(cuda_backend, oracle_backend):
     assert np.array_equal(outs[0][1], outs[1][1])
 
 
+def reductions_problem(backend, rt=np.float64):
+    gv = H.vol3d(4.0, 3.6, 4.4, 10)
+    s = H.structure(gv, lambda x, y, z: 1.0 + 2.0 * (z > 2.0), pml=0.8, realnum=rt)
+    f = H.fields(s, backend)
+    f.add_point_source(Ez, 0.3, 0.2, 0.0, 4.0, (2.0, 1.8, 1.55), 1.0)  # complex fields
+    f.add_dft_fields(Ez, (6, 6, 6), (33, 29, 37), np.linspace(0.2, 0.4, 5))   # a box that crosses chunk boundaries
+    f.add_dft_fields(Ez, (6, 6, 6), (33, 29, 37), np.linspace(0.2, 0.4, 5), decimation_factor=2)
+    return gv, f
+
+
+def reductions_on_the_host(f):
+    """the same sums from the synced arrays (numpy)"""
+    f.sync_to_host()
+    dots = np.zeros(5)
+    for fc in f.chunks:
+        da = [d for d in fc.dfts if d["mon"] == 0]
+        db = [d for d in fc.dfts if d["mon"] == 1]
+        if da:
+            a = da[0]["dft"].reshape(-1, 5).astype(np.complex128)
+            b = db[0]["dft"].reshape(-1, 5).astype(np.complex128)
+            dots += np.sum((a * np.conj(b)).real, axis=0)
+    return dots
+
+
+@pytest.mark.parametrize("which", ["oracle", pytest.param("cuda", marks=pytest.mark.gpu)])
+def test_device_reductions_through_the_host_model(which, oracle_backend, request):
+    """meepcu_dft_dot and meepcu_integrate_dot against numpy sums over the synced arrays (dft_flux::flux /
+    fields::integrate loops, src/dft.cpp:533-548, src/integrate.cpp:47-131); the CUDA sums equal the oracle's to 1e-13"""
+    from meep_nl_b200._cabi import Dz
+    backend = oracle_backend if which == "oracle" else request.getfixturevalue("cuda_backend")
+    gv, f = reductions_problem(backend)
+    f.step(50)
+    dev_dots = f.dft_dot(0, 1)
+    dev_sum, dev_max = f.integrate_dot(Ez, Dz, (3, 3, 3), (36, 32, 40))
+    host_dots = reductions_on_the_host(f)
+    assert np.abs(host_dots).max() > 0
+    assert np.allclose(dev_dots, host_dots, rtol=1e-12, atol=1e-13 * np.abs(host_dots).max())
+    tot, mx = 0.0, 0.0
+    for fc in f.chunks:
+        cg = fc.gv
+        sl = []
+        for k in range(3):
+            off = (cg.io[k] - gv.io[k]) // 2
+            o0, o1 = cg.owned_range(Ez, k)
+            a, b = max((3, 3, 3)[k], off + o0), min((36, 32, 40)[k], off + o1)
+            sl.append(slice(a - off, b - off + 1) if a <= b else slice(0, 0))
+        shp = tuple(n + 1 for n in cg.num)
+        e = (fc.f[(Ez, 0)].reshape(shp)[tuple(sl)] + 1j * fc.f[(Ez, 1)].reshape(shp)[tuple(sl)]).astype(np.complex128)
+        d = (fc.f[(Dz, 0)].reshape(shp)[tuple(sl)] + 1j * fc.f[(Dz, 1)].reshape(shp)[tuple(sl)]).astype(np.complex128)
+        v = (np.conj(e) * d).real
+        tot += float(v.sum())
+        mx = max(mx, float(np.abs(v).max()) if v.size else 0.0)
+    assert mx > 0 and abs(dev_sum - tot) <= 1e-12 * max(abs(tot), mx) and abs(dev_max - mx) <= 1e-15 * mx
+    f.close()
+
+
 # ---- virtual E (kernels.cuh, Curl3DParams::virt): chunks without PML / polarisations do not store E while
 # stepping; the B/H half reads chi1inv * (D - dipoles) instead.  Everything a host can observe must be unchanged. ----
 def virt_problem(backend, kind, rt=np.float64, split=None):
