@@ -116,7 +116,9 @@ typedef struct {
   const void *sigma[MEEPCU_NUM_COMPONENTS][5]; /* susceptibility::sigma[c][d], NULL when trivial */
   void *P[MEEPCU_NUM_COMPONENTS][2];           /* lorentzian_data::P (NULL: needs_P() false here) */
   void *P_prev[MEEPCU_NUM_COMPONENTS][2];      /* lorentzian_data::P_prev */
-  int reserved[8];
+  double noise_amp;           /* noisy_lorentzian_susceptibility::noise_amp (src/meep.hpp:282-299); 0 = no noise term.
+                                 Occupies the first two of the former reserved[8] ints: binary compatible. */
+  int reserved[6];
 } meepcu_susceptibility_desc;
 
 /* gyrotropic_susceptibility (src/susceptibility.cpp:350-603, src/meep.hpp:300-338): three polarisation
@@ -132,6 +134,33 @@ typedef struct {
   void *P_prev[MEEPCU_NUM_COMPONENTS][2][3];    /* gyrotropy_data::P_prev */
   int reserved[8];
 } meepcu_gyrotropic_desc;
+
+/* multilevel_susceptibility (src/multilevel-atom.cpp:28-407, src/meep.hpp:340-386): L atomic levels with populations
+ * N on the CENTRED grid, T radiative transitions, each with its own polarisation P[c][cmp][t] on the field's Yee
+ * positions.  update_P (:240-374) first advances N at every owned centred point from the eight-point sums of W, W_prev
+ * and of P, P_prev around it, then every P as an oscillator driven by sigma * W * (population inversion averaged back
+ * to the Yee position); subtract_P (:376-394) takes every P[.][.][t] off D.  The small arrays are copied at the call.
+ * The reference adds the medium to EVERY chunk (structure_chunk::add_susceptibility, anisotropic_averaging.cpp:300-372;
+ * sigma stays trivial where the medium is absent), so N relaxes and W is saved to W_prev everywhere: describe it for
+ * every chunk, as the shim does.  E_stuff only (H_stuff: MEEPCU_EUNSUPPORTED). */
+typedef struct {
+  int ft;                /* MEEPCU_E_STUFF */
+  int L, T;              /* multilevel_susceptibility::L, T */
+  const void *Gamma;     /* realnum[L*L]  relaxation rates                                      (meep.hpp:380) */
+  const void *GammaInv;  /* realnum[L*L]  multilevel_data::GammaInv = inv(1 + Gamma dt/2), as the reference's set-up
+                            computed it with LAPACK (multilevel-atom.cpp:156-162): an input of the stepping path */
+  const void *alpha;     /* realnum[L*T]  transition coefficients                               (meep.hpp:382) */
+  const void *omega;     /* realnum[T]    transition frequencies                                (meep.hpp:383) */
+  const void *gamma;     /* realnum[T]    optical loss rates                                    (meep.hpp:384) */
+  const void *sigmat;    /* realnum[5*T]  per-transition sigma factors by direction             (meep.hpp:385) */
+  const void *sigma[MEEPCU_NUM_COMPONENTS][5];  /* susceptibility::sigma[c][d] */
+  void *const *P[MEEPCU_NUM_COMPONENTS][2];     /* multilevel_data::P[c][cmp]: T pointers (NULL: needs_P() false) */
+  void *const *P_prev[MEEPCU_NUM_COMPONENTS][2];/* multilevel_data::P_prev[c][cmp] */
+  void *N;               /* multilevel_data::N, realnum[ntot*L]: N[i*L + level], i on the centred grid */
+  void *W_prev[MEEPCU_NUM_COMPONENTS][2];       /* fields_chunk::f_w_prev (update_eh.cpp:221-226): W = f_w ?: f of the
+                                                   previous time step, saved before every E update of the chunk */
+  int reserved[8];
+} meepcu_multilevel_desc;
 
 /* src_vol (src/meep_internals.hpp:49-82) attached to fields_chunk::sources[ft]. */
 typedef struct {
@@ -183,6 +212,7 @@ int meepcu_add_susceptibility(meepcu_ctx *ctx, int chunk_id, const meepcu_suscep
 /* polarisations are updated / subtracted in the order they were added (Lorentzian and gyrotropic alike),
  * like the reference's polarization_state list (update_eh.cpp:130-131, update_pols.cpp:46) */
 int meepcu_add_gyrotropic(meepcu_ctx *ctx, int chunk_id, const meepcu_gyrotropic_desc *desc);
+int meepcu_add_multilevel(meepcu_ctx *ctx, int chunk_id, const meepcu_multilevel_desc *desc);
 int meepcu_add_source(meepcu_ctx *ctx, int chunk_id, const meepcu_source_desc *desc);
 int meepcu_add_dft(meepcu_ctx *ctx, int chunk_id, const meepcu_dft_desc *desc, int *dft_id);
 
@@ -225,6 +255,22 @@ int meepcu_finalize(meepcu_ctx *ctx);
  * (no wait involved) returns MEEPCU_ENONFINITE ("simulation fields are NaN or Inf") when the flag is up.
  * meepcu_check_finite tests every element and blocks. */
 int meepcu_step(meepcu_ctx *ctx, int nsteps, int n_src_times, const meepcu_src_sample *samples);
+
+/* noisy_lorentzian_susceptibility::update_P (src/susceptibility.cpp:317-339) adds, after the Lorentzian update,
+ *   p[i] += gaussian_random(0, amp * sqrt(sigma[i]))
+ * at every owned point of every polarisation component, drawing from the process-global Mersenne twister
+ * (src/random.cpp:57-69: Knuth's polar method, libm log) in loop order.  Bit parity therefore needs the CALLER's
+ * generator: before each meepcu_step the caller draws the unit Gaussians g = gaussian_random(0, 1) in the reference's
+ * own order and hands them over; the device forms p[i] = (realnum)(p[i] + (0.0 + g * (double)(amp * sqrt(sigma[i])))),
+ * the same roundings as gaussian_random's `mean + v1 * sqrt(-2 log s / s) * stddev`.
+ * Order of one time step's n_per_step values: update_pols(H_stuff) then update_pols(E_stuff) (step.cpp:83-86,115-117);
+ * in each, chunks in index order, their susceptibilities in the order they were added, FOR_COMPONENTS(c), cmp 0 then 1
+ * where P[c][cmp] and sigma[c][direction(c)] exist, LOOP_OVER_VOL_OWNED(gv, c, i).
+ * meepcu_get_noise_count: n_per_step of the finalized context (0: no noisy medium).  meepcu_set_noise: the values
+ * for the steps of the NEXT meepcu_step call (nsteps * n_per_step doubles, copied before the call returns); a
+ * context with noisy media refuses meepcu_step(nsteps) unless exactly that many steps of noise are waiting. */
+int meepcu_get_noise_count(meepcu_ctx *ctx, size_t *n_per_step);
+int meepcu_set_noise(meepcu_ctx *ctx, int nsteps, size_t n_per_step, const double *unit_gaussians);
 
 /* fields::synchronize_magnetic_fields / restore_magnetic_fields (src/energy_and_flux.cpp:145-177) on
  * the device: back up B and H (with their f_u, f_w, f_cond, f_bfast; fields_chunk::backup_component

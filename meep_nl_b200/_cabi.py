@@ -52,7 +52,15 @@ class SusceptibilityDesc(C.Structure):
     _fields_ = [("ft", C.c_int), ("omega_0", C.c_double), ("gamma", C.c_double),
                 ("no_omega_0_denominator", C.c_int),
                 ("sigma", (vp * 5) * NUM_COMPONENTS), ("P", (vp * 2) * NUM_COMPONENTS),
-                ("P_prev", (vp * 2) * NUM_COMPONENTS), ("reserved", C.c_int * 8)]
+                ("P_prev", (vp * 2) * NUM_COMPONENTS), ("noise_amp", C.c_double), ("reserved", C.c_int * 6)]
+
+
+class MultilevelDesc(C.Structure):  # meepcu_multilevel_desc
+    _fields_ = [("ft", C.c_int), ("L", C.c_int), ("T", C.c_int),
+                ("Gamma", vp), ("GammaInv", vp), ("alpha", vp), ("omega", vp), ("gamma", vp), ("sigmat", vp),
+                ("sigma", (vp * 5) * NUM_COMPONENTS), ("P", (vp * 2) * NUM_COMPONENTS),
+                ("P_prev", (vp * 2) * NUM_COMPONENTS), ("N", vp), ("W_prev", (vp * 2) * NUM_COMPONENTS),
+                ("reserved", C.c_int * 8)]
 
 
 class GyrotropicDesc(C.Structure):
@@ -111,6 +119,9 @@ _PROTOTYPES = [
     ("meepcu_add_chunk", C.c_int, [vp, C.POINTER(ChunkDesc), C.POINTER(C.c_int)]),
     ("meepcu_add_susceptibility", C.c_int, [vp, C.c_int, C.POINTER(SusceptibilityDesc)]),
     ("meepcu_add_gyrotropic", C.c_int, [vp, C.c_int, C.POINTER(GyrotropicDesc)]),
+    ("meepcu_add_multilevel", C.c_int, [vp, C.c_int, C.POINTER(MultilevelDesc)]),
+    ("meepcu_get_noise_count", C.c_int, [vp, C.POINTER(C.c_size_t)]),
+    ("meepcu_set_noise", C.c_int, [vp, C.c_int, C.c_size_t, vp]),
     ("meepcu_add_source", C.c_int, [vp, C.c_int, C.POINTER(SourceDesc)]),
     ("meepcu_add_dft", C.c_int, [vp, C.c_int, C.POINTER(DftDesc), C.POINTER(C.c_int)]),
     ("meepcu_set_metal", C.c_int, [vp, C.c_int, C.c_size_t, vp]),

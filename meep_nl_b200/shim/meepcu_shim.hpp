@@ -69,6 +69,9 @@ struct api {
   MEEPCU_FN(add_chunk)
   MEEPCU_FN(add_susceptibility)
   MEEPCU_FN(add_gyrotropic)
+  MEEPCU_FN(add_multilevel)
+  MEEPCU_FN(get_noise_count)
+  MEEPCU_FN(set_noise)
   MEEPCU_FN(add_source)
   MEEPCU_FN(add_dft)
   MEEPCU_FN(set_metal)
@@ -104,6 +107,9 @@ struct api {
     MEEPCU_FN(add_chunk)
     MEEPCU_FN(add_susceptibility)
     MEEPCU_FN(add_gyrotropic)
+    MEEPCU_FN(add_multilevel)
+    MEEPCU_FN(get_noise_count)
+    MEEPCU_FN(set_noise)
     MEEPCU_FN(add_source)
     MEEPCU_FN(add_dft)
     MEEPCU_FN(set_metal)
@@ -136,6 +142,8 @@ struct observer {
   virtual void on_chunk(int, const meepcu_chunk_desc &, size_t /*ntot*/) {}
   virtual void on_susceptibility(int, const meepcu_susceptibility_desc &, size_t /*ntot*/) {}
   virtual void on_gyrotropic(int, const meepcu_gyrotropic_desc &, size_t /*ntot*/) {}
+  virtual void on_multilevel(int, const meepcu_multilevel_desc &, size_t /*ntot*/) {}
+  virtual void on_noise(int /*nsteps*/, size_t /*n_per_step*/, const double *) {}
   virtual void on_source(int, const meepcu_source_desc &) {}
   virtual void on_dft(int, const meepcu_dft_desc &, size_t /*N*/) {}
   virtual void on_metal(int, size_t, void *const *) {}
@@ -185,6 +193,12 @@ public:
         st->update(tm + f.dt, f.dt); // step.cpp:106
         put(o.dipole_E, st->dipole());
       }
+    }
+    if (n_noise) { // noisy Lorentzian media: this process's generator, the reference's draw order (include/meepcu.h)
+      std::vector<double> g((size_t)n * n_noise);
+      for (size_t k = 0; k < g.size(); ++k) g[k] = meep::gaussian_random(0, 1);
+      if (obs) obs->on_noise(n, n_noise, g.data());
+      check(a.set_noise(ctx, n, n_noise, g.data()));
     }
     if (obs) obs->on_step(n, nsrc, smp.data());
     if (dft_host_dirty) { // scale_dft / operator-= / load_dft_hdf5 changed the accumulators on the host
@@ -430,8 +444,13 @@ public:
             fc->f_w[ec][cmp] = new realnum[ntot];
             memcpy(fc->f_w[ec][cmp], fc->f[ec][cmp], ntot * sizeof(realnum));
           }
-          if (fc->needs_W_prev(ec))
-            meep::abort("meepcu: susceptibilities that need W_prev are outside the GPU path");
+          if (fc->needs_W_prev(ec)) { // update_eh.cpp:221-226 (multilevel atoms; every chunk of such a structure)
+            if (ft == H_stuff) meep::abort("meepcu: magnetic multilevel media are outside the GPU path");
+            if (!fc->f_w_prev[ec][cmp]) {
+              fc->f_w_prev[ec][cmp] = new realnum[ntot];
+              memcpy(fc->f_w_prev[ec][cmp], fc->f_w[ec][cmp] ? fc->f_w[ec][cmp] : fc->f[ec][cmp], sizeof(realnum) * ntot);
+            }
+          }
         }
         for (polarization_state *p = fc->pol[ft]; p; p = p->next) { // update_pols.cpp:49-55
           if (!p->data) {
@@ -477,6 +496,7 @@ private:
   bool dft_host_dirty = false; // the host changed the accumulators since they were last sent
   std::set<const void *> dft_ptrs; // dft_chunk::dft arrays registered with the context
   std::vector<meep::src_time *> src_times;
+  size_t n_noise = 0; // unit Gaussians the context wants per time step (noisy Lorentzian media)
   std::vector<std::vector<double> > keep_amp; // storage handed to the ABI during description
 
   static void put(double o[2], std::complex<double> z) {
@@ -597,13 +617,51 @@ private:
             check(a.add_gyrotropic(ctx, i, &gdsc));
             continue;
           }
+          if (typeid(*p->s) == typeid(multilevel_susceptibility)) {
+            const multilevel_susceptibility *ms = static_cast<const multilevel_susceptibility *>(p->s);
+            // multilevel_data is private to multilevel-atom.cpp:118-128; same layout restated here
+            struct multilevel_data_layout {
+              size_t sz_data, ntot;
+              realnum *GammaInv;
+              realnum **P[NUM_FIELD_COMPONENTS][2];
+              realnum **P_prev[NUM_FIELD_COMPONENTS][2];
+              realnum *N, *Ntmp;
+            };
+            const multilevel_data_layout *md = (const multilevel_data_layout *)p->data;
+            if (!md) meep::abort("meepcu: multilevel medium without internal data");
+            meepcu_multilevel_desc mdsc;
+            memset(&mdsc, 0, sizeof mdsc);
+            mdsc.ft = (int)ehs[k];
+            mdsc.L = ms->L;
+            mdsc.T = ms->T;
+            mdsc.Gamma = ms->Gamma;
+            mdsc.GammaInv = md->GammaInv;
+            mdsc.alpha = ms->alpha;
+            mdsc.omega = ms->omega;
+            mdsc.gamma = ms->gamma;
+            mdsc.sigmat = ms->sigmat;
+            mdsc.N = md->N;
+            FOR_COMPONENTS(c) {
+              for (int dd = 0; dd < 5; ++dd) mdsc.sigma[c][dd] = ms->sigma[c][dd];
+              for (int cmp = 0; cmp < 2; ++cmp) {
+                mdsc.P[c][cmp] = (void *const *)md->P[c][cmp];
+                mdsc.P_prev[c][cmp] = (void *const *)md->P_prev[c][cmp];
+                mdsc.W_prev[c][cmp] = fc->f_w_prev[c][cmp];
+              }
+            }
+            if (obs) obs->on_multilevel(i, mdsc, gv.ntot());
+            check(a.add_multilevel(ctx, i, &mdsc));
+            continue;
+          }
           const lorentzian_susceptibility *ls =
               dynamic_cast<const lorentzian_susceptibility *>(p->s);
-          if (!ls || typeid(*p->s) != typeid(lorentzian_susceptibility))
-            meep::abort("meepcu: only Lorentzian/Drude and gyrotropic susceptibilities are on the GPU path");
+          const bool noisy = typeid(*p->s) == typeid(noisy_lorentzian_susceptibility);
+          if (!ls || (typeid(*p->s) != typeid(lorentzian_susceptibility) && !noisy))
+            meep::abort("meepcu: only Lorentzian/Drude (plain or noisy), gyrotropic and multilevel susceptibilities are on the GPU path");
           meepcu_susceptibility_desc sd;
           memset(&sd, 0, sizeof sd);
           sd.ft = (int)ehs[k];
+          if (noisy) sd.noise_amp = static_cast<const noisy_lorentzian_susceptibility *>(p->s)->noise_amp;
           sd.omega_0 = ls->omega_0;
           sd.gamma = ls->gamma;
           sd.no_omega_0_denominator = ls->no_omega_0_denominator;
@@ -716,6 +774,7 @@ private:
     }
     if (obs) obs->on_finalize();
     check(a.finalize(ctx));
+    check(a.get_noise_count(ctx, &n_noise));
     described = fingerprint();
   }
 };

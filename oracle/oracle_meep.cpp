@@ -225,6 +225,9 @@ struct CtxBase {
   virtual int add_chunk(const meepcu_chunk_desc *d, int *id) = 0;
   virtual int add_susc(int chunk, const meepcu_susceptibility_desc *d) = 0;
   virtual int add_gyro(int chunk, const meepcu_gyrotropic_desc *d) = 0;
+  virtual int add_multilevel(int chunk, const meepcu_multilevel_desc *d) = 0;
+  virtual size_t noise_count() = 0;
+  virtual int set_noise(int nsteps, size_t n_per_step, const double *g) = 0;
   virtual int add_source(int chunk, const meepcu_source_desc *d) = 0;
   virtual int add_dft(int chunk, const meepcu_dft_desc *d, int *id) = 0;
   virtual int set_metal(int ft, size_t n, void *const *ptrs) = 0;
@@ -245,6 +248,18 @@ template <class T> struct Susc {
   meepcu_susceptibility_desc d; // gyrotropic: sigma, and P/P_prev = the component subtract_P uses (P[c][cmp][dir(c)])
   bool gyro;
   meepcu_gyrotropic_desc g;
+  // multilevel atoms: one entry per transition t (what subtract_P takes off D, in t order, multilevel-atom.cpp:376-394);
+  // the entry of transition 0 runs the whole update_P
+  int ml, ml_t; // index into Chunk::ml (-1: not a multilevel entry), transition
+};
+
+// multilevel_susceptibility + multilevel_data (src/multilevel-atom.cpp:118-128, src/meep.hpp:377-386)
+template <class T> struct MlAtom {
+  int L, Tn;
+  std::vector<T> Gamma, GammaInv, alpha, omega, gamma, sigmat;
+  const void *sigma[MEEPCU_NUM_COMPONENTS][5];
+  std::vector<T *> P[MEEPCU_NUM_COMPONENTS][2], P_prev[MEEPCU_NUM_COMPONENTS][2]; // [t]
+  T *N;
 };
 
 template <class T> struct Dft {
@@ -263,6 +278,8 @@ template <class T> struct Chunk {
   std::vector<Dft<T> > dfts;    // in list order (newest first, like the reference's linked list)
   std::vector<T> fmp_store[MEEPCU_NUM_COMPONENTS][2]; // f_minus_p scratch (update_eh.cpp:94-103)
   std::vector<T> rderiv;                              // fields_chunk::f_rderiv_int (step_db.cpp:93-118)
+  std::vector<MlAtom<T> > ml;                         // multilevel media of the chunk
+  T *w_prev[MEEPCU_NUM_COMPONENTS][2];                // fields_chunk::f_w_prev (update_eh.cpp:221-226)
   // step plan (src/fields.cpp:441-469)
   bool have_plus[20], have_minus[20];
   int plus_c[20], minus_c[20], plus_d[20], minus_d[20];
@@ -338,6 +355,7 @@ template <class T> struct Impl : CtxBase {
     Chunk<T> ch;
     ch.d = *d;
     ch.g.init(cfg.dim, d->num, d->io);
+    memset(ch.w_prev, 0, sizeof ch.w_prev);
     // figure_out_step_plan, src/fields.cpp:441-469
     for (int c = 0; c < 20; ++c) ch.have_plus[c] = ch.have_minus[c] = false;
     for (int c1 = 0; c1 < 20; ++c1) {
@@ -368,6 +386,89 @@ template <class T> struct Impl : CtxBase {
     if (id) *id = (int)chunks.size() - 1;
     return MEEPCU_OK;
   }
+  int add_multilevel(int chunk, const meepcu_multilevel_desc *d) {
+    if (chunk < 0 || chunk >= (int)chunks.size()) return fail(MEEPCU_EINVAL, "bad chunk id");
+    if (d->ft != MEEPCU_E_STUFF)
+      return fail(MEEPCU_EUNSUPPORTED, "multilevel media are supported for E_stuff only");
+    if (cfg.dim == MEEPCU_Dcyl) return fail(MEEPCU_EUNSUPPORTED, "multilevel media in cylindrical coordinates");
+    if (d->L < 1 || d->L > 8 || d->T < 1 || d->T > 4) return fail(MEEPCU_EUNSUPPORTED, "multilevel medium: 1..8 levels, 1..4 transitions");
+    if (!d->Gamma || !d->GammaInv || !d->alpha || !d->omega || !d->gamma || !d->sigmat || !d->N)
+      return fail(MEEPCU_EINVAL, "multilevel medium: Gamma, GammaInv, alpha, omega, gamma, sigmat and N are required");
+    Chunk<T> &ch = chunks[chunk];
+    MlAtom<T> M;
+    M.L = d->L;
+    M.Tn = d->T;
+    const int L = d->L, Tn = d->T;
+    M.Gamma.assign((const T *)d->Gamma, (const T *)d->Gamma + L * L);
+    M.GammaInv.assign((const T *)d->GammaInv, (const T *)d->GammaInv + L * L);
+    M.alpha.assign((const T *)d->alpha, (const T *)d->alpha + L * Tn);
+    M.omega.assign((const T *)d->omega, (const T *)d->omega + Tn);
+    M.gamma.assign((const T *)d->gamma, (const T *)d->gamma + Tn);
+    M.sigmat.assign((const T *)d->sigmat, (const T *)d->sigmat + 5 * Tn);
+    M.N = (T *)d->N;
+    for (int c = 0; c < 20; ++c) {
+      for (int k = 0; k < 5; ++k) M.sigma[c][k] = d->sigma[c][k];
+      for (int cmp = 0; cmp < 2; ++cmp) {
+        if ((d->P[c][cmp] != NULL) != (d->P_prev[c][cmp] != NULL)) return fail(MEEPCU_EINVAL, "P and P_prev must both be given");
+        if (d->P[c][cmp])
+          for (int t = 0; t < Tn; ++t) {
+            if (!d->P[c][cmp][t] || !d->P_prev[c][cmp][t]) return fail(MEEPCU_EINVAL, "multilevel medium: NULL transition array");
+            M.P[c][cmp].push_back((T *)d->P[c][cmp][t]);
+            M.P_prev[c][cmp].push_back((T *)d->P_prev[c][cmp][t]);
+          }
+        if (d->W_prev[c][cmp]) ch.w_prev[c][cmp] = (T *)d->W_prev[c][cmp];
+      }
+    }
+    for (int t = 0; t < Tn; ++t) {
+      Susc<T> s;
+      memset(&s, 0, sizeof s);
+      s.d.ft = d->ft;
+      s.ml = (int)ch.ml.size();
+      s.ml_t = t;
+      for (int c = 0; c < 20; ++c)
+        for (int cmp = 0; cmp < 2; ++cmp)
+          if (d->P[c][cmp]) {
+            s.d.P[c][cmp] = d->P[c][cmp][t];
+            s.d.P_prev[c][cmp] = d->P_prev[c][cmp][t];
+          }
+      ch.pol[d->ft].push_back(s);
+    }
+    ch.ml.push_back(M);
+    return MEEPCU_OK;
+  }
+  // noisy Lorentzian media (susceptibility.cpp:317-339): the caller's unit Gaussians, include/meepcu.h
+  std::vector<double> noise;
+  int noise_steps = 0;
+  const double *noise_cur = 0;
+  size_t noise_points(const Chunk<T> &ch, int ft) const {
+    size_t n = 0;
+    for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip) {
+      const meepcu_susceptibility_desc &sd = ch.pol[ft][ip].d;
+      if (ch.pol[ft][ip].gyro || ch.pol[ft][ip].ml >= 0 || sd.noise_amp == 0) continue;
+      for (int c = 0; c < 20; ++c)
+        for (int cmp = 0; cmp < 2; ++cmp)
+          if (sd.P[c][cmp] && sd.sigma[c][comp_dir(c)]) {
+            size_t m = 1;
+            for (int dd = 0; dd < 3; ++dd)
+              if (ch.g.has[dd]) m *= (size_t)ch.g.num[dd]; // (ie - is) / 2 + 1 of LOOP_OVER_VOL_OWNED, either Yee shift
+            n += m;
+          }
+    }
+    return n;
+  }
+  size_t noise_count() {
+    size_t n = 0;
+    for (int ft = MEEPCU_H_STUFF; ft >= MEEPCU_E_STUFF; --ft) // H_stuff first (step.cpp:83-86), then E_stuff (:115-117)
+      for (size_t ic = 0; ic < chunks.size(); ++ic) n += noise_points(chunks[ic], ft);
+    return n;
+  }
+  int set_noise(int nsteps, size_t n_per_step, const double *g) {
+    if (n_per_step != noise_count()) return fail(MEEPCU_EINVAL, "meepcu_set_noise: %zu values per step given, the context needs %zu", n_per_step, noise_count());
+    if (nsteps < 0 || (nsteps > 0 && n_per_step > 0 && !g)) return fail(MEEPCU_EINVAL, "meepcu_set_noise: bad arguments");
+    noise.assign(g, g + (size_t)nsteps * n_per_step);
+    noise_steps = nsteps;
+    return MEEPCU_OK;
+  }
   int add_susc(int chunk, const meepcu_susceptibility_desc *d) {
     if (chunk < 0 || chunk >= (int)chunks.size()) return fail(MEEPCU_EINVAL, "bad chunk id");
     if (d->ft != MEEPCU_E_STUFF && d->ft != MEEPCU_H_STUFF)
@@ -376,6 +477,8 @@ template <class T> struct Impl : CtxBase {
     memset(&s, 0, sizeof s);
     s.d = *d;
     s.gyro = false;
+    s.ml = -1;
+    if (d->noise_amp != 0 && cfg.dim == MEEPCU_Dcyl) return fail(MEEPCU_EUNSUPPORTED, "noisy Lorentzian media in cylindrical coordinates");
     chunks[chunk].pol[d->ft].push_back(s);
     return MEEPCU_OK;
   }
@@ -387,6 +490,7 @@ template <class T> struct Impl : CtxBase {
     Susc<T> s;
     memset(&s, 0, sizeof s);
     s.gyro = true;
+    s.ml = -1;
     s.g = *d;
     s.d.ft = d->ft;
     for (int c = 0; c < 20; ++c) {
@@ -1416,6 +1520,8 @@ template <class T> struct Impl : CtxBase {
           const int dc_2 = dir_comp(dc, d_2);
           const ptrdiff_t s_2 = g.stride[slot(d_2)] * sgn;
           const int dsigw = ch.d.sigsize[d_ec] > 1 ? d_ec : MEEPCU_NO_DIRECTION;
+          if (ch.w_prev[ec][cmp]) // :221-226 save W of this time step where a polarisation needs W_prev
+            memcpy(ch.w_prev[ec][cmp], ch.d.f_w[ec][cmp] ? (const T *)ch.d.f_w[ec][cmp] : ch.F(ec, cmp), sizeof(T) * g.ntot);
           if (ch.F(ec, cmp) == ch.F(dc, cmp)) {
             if (ch.d.chi1inv[ec][d_ec] || have_f_minus_p || dsigw != MEEPCU_NO_DIRECTION)
               return fail(MEEPCU_ESTATE, "H aliases B where update_eh.cpp:204-209 would split them");
@@ -1559,6 +1665,13 @@ template <class T> struct Impl : CtxBase {
           if (rc) return rc;
           continue;
         }
+        if (ch.pol[ft][ip].ml >= 0) {
+          if (ch.pol[ft][ip].ml_t == 0) {
+            int rc = update_multilevel(ch, ch.ml[ch.pol[ft][ip].ml]);
+            if (rc) return rc;
+          }
+          continue;
+        }
         const meepcu_susceptibility_desc &sd = ch.pol[ft][ip].d;
         const T pi = 3.141592653589793238462643383276; // src/meep.hpp:54 (const double pi)
         const double dpi = 3.141592653589793238462643383276;
@@ -1635,9 +1748,187 @@ template <class T> struct Impl : CtxBase {
             }
 #undef POFFDIAG
           }
+        if (sd.noise_amp != 0) { // noisy_lorentzian_susceptibility::update_P, susceptibility.cpp:321-337
+          const T noise_amp = (T)sd.noise_amp;
+          const T g2pi_n = gamma * 2 * dpi;
+          const T w2pi = omega_0 * 2 * dpi;
+          const T amp = w2pi * noise_amp * std::sqrt(g2pi_n) * dt * dt / (1 + g2pi_n * dt / 2);
+          for (int c = 0; c < 20; ++c)
+            for (int cmp = 0; cmp < 2; ++cmp) {
+              if (!sd.P[c][cmp]) continue;
+              const T *sg = (const T *)sd.sigma[c][comp_dir(c)];
+              if (!sg) continue;
+              T *p = (T *)sd.P[c][cmp];
+              int is[3], ie[3];
+              for (int dd = 0; dd < 3; ++dd) {
+                is[dd] = g.io[dd] + 2 - g.yee_shift(c, dd);
+                ie[dd] = g.io[dd] + 2 * g.num[dd];
+              }
+              Loop L(g, is, ie);
+              if (!noise_cur) return fail(MEEPCU_ESTATE, "noisy medium stepped without noise");
+              // gaussian_random(0, stddev) = 0 + v1 sqrt(-2 log s / s) * stddev (random.cpp:57-69); the caller drew
+              // g = v1 sqrt(-2 log s / s) from its generator in this very order (one at a time: no OpenMP here)
+              OLOOP(L, i) { p[i] += 0.0 + *noise_cur++ * (amp * std::sqrt(sg[i])); }
+            }
+        }
       }
     }
     return MEEPCU_OK;
+  }
+
+  // multilevel_susceptibility::update_P, src/multilevel-atom.cpp:240-374
+  int update_multilevel(Chunk<T> &ch, MlAtom<T> &M) {
+    const Grid &g = ch.g;
+    const int L = M.L, Tn = M.Tn;
+    const T dt = (T)cfg.dt;
+    const T dt2 = 0.5 * dt;
+    const T *Gamma = M.Gamma.data(), *alpha = M.alpha.data(), *omega = M.omega.data(), *gamma = M.gamma.data();
+    const T *sigmat = M.sigmat.data();
+    // field directions and offsets for the E * dP dot product (:247-258)
+    int cdot[3] = {-1, -1, -1}, ndot = 0;
+    ptrdiff_t o1[3] = {0, 0, 0}, o2[3] = {0, 0, 0};
+    for (int c = 0; c < 20; ++c)
+      if (!M.P[c][0].empty()) {
+        if (ndot == 3) return fail(MEEPCU_EINVAL, "bug in meep: too many polarization components");
+        yee2cent_offsets(g, c, o1[ndot], o2[ndot]);
+        cdot[ndot++] = c;
+      }
+    const T *W[3][2], *Wp[3][2];
+    for (int k = 0; k < ndot; ++k)
+      for (int cmp = 0; cmp < 2; ++cmp) {
+        const int c = cdot[k];
+        W[k][cmp] = ch.d.f_w[c][cmp] ? (const T *)ch.d.f_w[c][cmp] : ch.F(c, cmp); // update_pols.cpp:43-44
+        Wp[k][cmp] = ch.w_prev[c][cmp];
+        if (cmp == 0 && (!W[k][0] || !Wp[k][0])) return fail(MEEPCU_EINVAL, "multilevel medium: W / W_prev missing");
+        if (W[k][cmp] && !Wp[k][cmp]) return fail(MEEPCU_EINVAL, "multilevel medium: W_prev missing");
+      }
+    { // update N from W and P (:260-329), LOOP_OVER_VOL_OWNED(gv, Centered, i)
+      const T *GammaInv = M.GammaInv.data();
+      int is[3], ie[3];
+      for (int dd = 0; dd < 3; ++dd) {
+        is[dd] = g.io[dd] + 1;
+        ie[dd] = g.io[dd] + 2 * g.num[dd];
+      }
+      Loop Lp(g, is, ie);
+#pragma omp parallel for collapse(2)
+      OLOOP(Lp, i) {
+        T Ntmp[8]; // multilevel_data::Ntmp (shared scratch in the reference, whose loop is serial)
+        T *N = M.N + i * L;
+        for (int l1 = 0; l1 < L; ++l1) {
+          Ntmp[l1] = 0;
+          for (int l2 = 0; l2 < L; ++l2) Ntmp[l1] += ((l1 == l2) - Gamma[l1 * L + l2] * dt2) * N[l2];
+        }
+        T E8[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+        for (int idot = 0; idot < ndot; ++idot) {
+          const T *w = W[idot][0], *wp = Wp[idot][0];
+          E8[idot][0] = w[i] + w[i + o1[idot]] + w[i + o2[idot]] + w[i + o1[idot] + o2[idot]] + wp[i] +
+                        wp[i + o1[idot]] + wp[i + o2[idot]] + wp[i + o1[idot] + o2[idot]];
+          if (W[idot][1]) {
+            w = W[idot][1];
+            wp = Wp[idot][1];
+            E8[idot][1] = w[i] + w[i + o1[idot]] + w[i + o2[idot]] + w[i + o1[idot] + o2[idot]] + wp[i] +
+                          wp[i + o1[idot]] + wp[i + o2[idot]] + wp[i + o1[idot] + o2[idot]];
+          }
+          else
+            E8[idot][1] = 0;
+        }
+        for (int t = 0; t < Tn; ++t) {
+          T EdP32 = 0;
+          T EPave64 = 0;
+          T gperpdt = gamma[t] * kPi * dt;
+          for (int idot = 0; idot < ndot; ++idot) {
+            const int c = cdot[idot];
+            const T *p = M.P[c][0][t], *pp = M.P_prev[c][0][t];
+            T dP = p[i] + p[i + o1[idot]] + p[i + o2[idot]] + p[i + o1[idot] + o2[idot]] -
+                   (pp[i] + pp[i + o1[idot]] + pp[i + o2[idot]] + pp[i + o1[idot] + o2[idot]]);
+            T Pave2 = p[i] + p[i + o1[idot]] + p[i + o2[idot]] + p[i + o1[idot] + o2[idot]] +
+                      (pp[i] + pp[i + o1[idot]] + pp[i + o2[idot]] + pp[i + o1[idot] + o2[idot]]);
+            EdP32 += dP * E8[idot][0];
+            EPave64 += Pave2 * E8[idot][0];
+            if (!M.P[c][1].empty()) {
+              p = M.P[c][1][t];
+              pp = M.P_prev[c][1][t];
+              dP = p[i] + p[i + o1[idot]] + p[i + o2[idot]] + p[i + o1[idot] + o2[idot]] -
+                   (pp[i] + pp[i + o1[idot]] + pp[i + o2[idot]] + pp[i + o1[idot] + o2[idot]]);
+              Pave2 = p[i] + p[i + o1[idot]] + p[i + o2[idot]] + p[i + o1[idot] + o2[idot]] +
+                      (pp[i] + pp[i + o1[idot]] + pp[i + o2[idot]] + pp[i + o1[idot] + o2[idot]]);
+              EdP32 += dP * E8[idot][1];
+              EPave64 += Pave2 * E8[idot][1];
+            }
+          }
+          EdP32 *= 0.03125;
+          EPave64 *= 0.015625;
+          for (int l = 0; l < L; ++l) Ntmp[l] += alpha[l * Tn + t] * EdP32 + alpha[l * Tn + t] * gperpdt * EPave64;
+        }
+        for (int l1 = 0; l1 < L; ++l1) {
+          N[l1] = 0;
+          for (int l2 = 0; l2 < L; ++l2) N[l1] += GammaInv[l1 * L + l2] * Ntmp[l2];
+        }
+      }
+    }
+    // each P is updated as a damped harmonic oscillator (:331-373)
+    for (int t = 0; t < Tn; ++t) {
+      const T omega2pi = 2 * kPi * omega[t], g2pi = gamma[t] * 2 * kPi, gperp = gamma[t] * kPi;
+      const T omega0dtsqrCorrected = omega2pi * omega2pi * dt * dt + gperp * gperp * dt * dt;
+      const T gamma1inv = 1 / (1 + g2pi * dt2), gamma1 = (1 - g2pi * dt2);
+      const T dtsqr = dt * dt;
+      int lp = -1, lm = -1;
+      for (int l = 0; l < L; ++l) {
+        if (alpha[l * Tn + t] > 0) lp = l;
+        if (alpha[l * Tn + t] < 0) lm = l;
+      }
+      if (lp < 0 || lm < 0) return fail(MEEPCU_EINVAL, "invalid alpha array for transition %d", t);
+      for (int c = 0; c < 20; ++c)
+        for (int cmp = 0; cmp < 2; ++cmp) {
+          if (M.P[c][cmp].empty()) continue;
+          const int d0 = comp_dir(c);
+          const T *w = ch.d.f_w[c][cmp] ? (const T *)ch.d.f_w[c][cmp] : ch.F(c, cmp);
+          const T *s = (const T *)M.sigma[c][d0];
+          const T st = sigmat[5 * t + d0];
+          if (!(w && s)) continue;
+          T *p = M.P[c][cmp][t], *pp = M.P_prev[c][cmp][t];
+          ptrdiff_t oa, ob;
+          yee2cent_offsets(g, c, oa, ob); // cent2yee_offsets = the negatives (vec.cpp:347-351)
+          oa = -oa * L;
+          ob = -ob * L;
+          const T *N = M.N;
+          const int d1 = cycle_dir(cfg.dim, d0, 1), d2 = cycle_dir(cfg.dim, d0, 2);
+          const int c1 = dir_comp(c, d1), c2 = dir_comp(c, d2);
+          const T *w1 = ch.d.f_w[c1][cmp] ? (const T *)ch.d.f_w[c1][cmp] : ch.F(c1, cmp);
+          const T *w2 = ch.d.f_w[c2][cmp] ? (const T *)ch.d.f_w[c2][cmp] : ch.F(c2, cmp);
+          if ((w1 && M.sigma[c][d1]) || (w2 && M.sigma[c][d2]))
+            return fail(MEEPCU_EUNSUPPORTED, "nondiagonal saturable gain is not yet supported"); // the reference's words (:362)
+          int is[3], ie[3];
+          for (int dd = 0; dd < 3; ++dd) {
+            is[dd] = g.io[dd] + 2 - g.yee_shift(c, dd);
+            ie[dd] = g.io[dd] + 2 * g.num[dd];
+          }
+          Loop Lc(g, is, ie);
+#pragma omp parallel for collapse(2)
+          OLOOP(Lc, i) {
+            T pcur = p[i];
+            const T *Ni = N + i * L;
+            T dNi = 0.25 * (Ni[lp] + Ni[lp + oa] + Ni[lp + ob] + Ni[lp + oa + ob] - Ni[lm] - Ni[lm + oa] - Ni[lm + ob] -
+                            Ni[lm + oa + ob]);
+            p[i] = gamma1inv * (pcur * (2 - omega0dtsqrCorrected) - gamma1 * pp[i] - dtsqr * (st * s[i] * w[i]) * dNi);
+            pp[i] = pcur;
+          }
+        }
+    }
+    return MEEPCU_OK;
+  }
+  // grid_volume::yee2cent_offsets, src/vec.cpp:333-344
+  static void yee2cent_offsets(const Grid &g, int c, ptrdiff_t &offset1, ptrdiff_t &offset2) {
+    offset1 = offset2 = 0;
+    for (int dd = 0; dd < 3; ++dd) {
+      if (!g.has[dd]) continue;
+      if (!g.yee_shift(c, dd)) {
+        if (offset1)
+          offset2 = g.stride[dd];
+        else
+          offset1 = g.stride[dd];
+      }
+    }
   }
 
   // fields::update_dfts / dft_chunk::update_dft, src/dft.cpp:249-307
@@ -1726,6 +2017,11 @@ template <class T> struct Impl : CtxBase {
           if (chunks[ic].sources[ft][is].src_time_id >= nsrc || (nsrc > 0 && !smp))
             return fail(MEEPCU_EINVAL, "source refers to src_time %d but only %d samples given",
                         chunks[ic].sources[ft][is].src_time_id, nsrc);
+    const size_t n_noise = noise_count();
+    if (n_noise && noise_steps != nsteps)
+      return fail(MEEPCU_ESTATE, "noisy Lorentzian media: meepcu_set_noise must provide the %d steps of this call (%d waiting)", nsteps, noise_steps);
+    noise_cur = n_noise ? noise.data() : 0;
+    noise_steps = 0;
     for (int s = 0; s < nsteps; ++s) {
       const meepcu_src_sample *sm = smp ? smp + (size_t)s * nsrc : NULL;
       if ((rc = step_db(MEEPCU_B_STUFF))) return rc;
@@ -1955,6 +2251,21 @@ int meepcu_add_gyrotropic(meepcu_ctx *ctx, int chunk, const meepcu_gyrotropic_de
   CHECK_CTX;
   if (!d) return fail(MEEPCU_EINVAL, "null descriptor");
   return ctx->impl->add_gyro(chunk, d);
+}
+int meepcu_add_multilevel(meepcu_ctx *ctx, int chunk, const meepcu_multilevel_desc *d) {
+  CHECK_CTX;
+  if (!d) return fail(MEEPCU_EINVAL, "null descriptor");
+  return ctx->impl->add_multilevel(chunk, d);
+}
+int meepcu_get_noise_count(meepcu_ctx *ctx, size_t *n) {
+  CHECK_CTX;
+  if (!n) return fail(MEEPCU_EINVAL, "null argument");
+  *n = ctx->impl->noise_count();
+  return MEEPCU_OK;
+}
+int meepcu_set_noise(meepcu_ctx *ctx, int nsteps, size_t n_per_step, const double *g) {
+  CHECK_CTX;
+  return ctx->impl->set_noise(nsteps, n_per_step, g);
 }
 int meepcu_add_source(meepcu_ctx *ctx, int chunk, const meepcu_source_desc *d) {
   CHECK_CTX;

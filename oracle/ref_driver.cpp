@@ -29,6 +29,9 @@ using std::complex;
 // ------------------------------------------------------------------------------------------
 // test problems
 // ------------------------------------------------------------------------------------------
+// The twins of one run share the process-global Mersenne twister (src/random.cpp) that noisy Lorentzian media
+// draw from: it is re-seeded from the index of the time step about to run, before each twin steps it
+static void reseed(int step_index) { meep::set_random_seed(0x5eed1UL + 7919UL * (unsigned long)step_index); }
 static double one(const vec &) { return 1.0; }
 static double g_slab_lo, g_slab_hi, g_slab_eps;
 static double wvg_eps(const vec &p) { return fabs(p.y() - 4.0) < 0.5 ? 12.0 : 1.0; }
@@ -427,6 +430,70 @@ static problem *build(const std::string &spec, int nchunks) {
     p->f->add_point_source(Ez, 0.3, 0.25, 0.0, 4.0, p->gv.center(), 1.0);
     p->f->add_point_source(Hx, 0.25, 0.25, 0.0, 4.0, p->gv.center(), 0.5);
   }
+  else if (name == "mlatom3d" || name == "mlatom2d") { // multilevel-atom gain medium (multilevel-atom.cpp)
+    // mlatom3d: two levels, one radiative transition, real fields (python/tests/test_multilevel_atom.py physics);
+    // mlatom2d: three levels, two radiative transitions with different sigma factors, complex fields, plus an
+    // ordinary Lorentzian in the same list.  The medium fills a slab; N relaxes in every chunk (PML ones too)
+    if (!n) n = 14;
+    const bool d3 = name == "mlatom3d";
+    const double L = n / a;
+    p->gv = d3 ? vol3d(L, L, L, a) : vol2d(L, 1.5 * L, a);
+    g_slab_lo = (d3 ? 0.3 : 0.45) * L;
+    g_slab_hi = (d3 ? 0.7 : 1.05) * L;
+    g_slab_eps = 2.25;
+    p->s = new structure(p->gv, d3 ? slab_eps_z : slab_eps_y, pml(0.1 * L > 0.5 ? 0.5 : 0.1 * L), identity(), nchunks, 0.5, false);
+    const double pi_ = 3.14159265358979323846264338327950288;
+    if (d3) { // make_multilevel_sus (meepgeom.cpp:1711-1788) for t1 = 1->2 pumped + radiative, t2 = 2->1 decay
+      const double f21 = 0.3, g21 = 0.06, Rp = 0.051, r21 = 0.05;
+      realnum Gamma[4] = {(realnum)Rp, (realnum)-r21, (realnum)-Rp, (realnum)r21};
+      realnum N0[2] = {1.0, (realnum)(param != 0 ? param : 0.25)};
+      realnum alpha[2] = {(realnum)(-1.0 / (2 * pi_ * f21)), (realnum)(+1.0 / (2 * pi_ * f21))};
+      realnum omega[1] = {(realnum)f21}, gam[1] = {(realnum)g21};
+      realnum sigmat[5] = {1.5, 1.5, 1.5, 0, 0};
+      p->s->add_susceptibility(slab_mask_z, E_stuff, multilevel_susceptibility(2, 1, Gamma, N0, alpha, omega, gam, sigmat));
+    }
+    else {
+      const double fa = 0.3, fb = 0.22, ga = 0.05, gb = 0.08;
+      realnum Gamma[9] = {0.04, -0.03, 0, -0.04, 0.03 + 0.02, -0.01, 0, -0.02, 0.01};
+      realnum N0[3] = {0.9, 0.3, 0.1};
+      realnum alpha[6] = {0, 0, 0, 0, 0, 0}; // alpha[l*T + t]
+      alpha[0 * 2 + 0] = -1.0 / (2 * pi_ * fa); // transition 0 couples levels 0 -> 1
+      alpha[1 * 2 + 0] = +1.0 / (2 * pi_ * fa);
+      alpha[1 * 2 + 1] = -1.0 / (2 * pi_ * fb); // transition 1 couples levels 1 -> 2
+      alpha[2 * 2 + 1] = +1.0 / (2 * pi_ * fb);
+      realnum omega[2] = {(realnum)fa, (realnum)fb}, gam[2] = {(realnum)ga, (realnum)gb};
+      realnum sigmat[10] = {1.0, 1.2, 0.8, 0, 0, 0.7, 0.9, 1.1, 0, 0};
+      p->s->add_susceptibility(slab_mask_y, E_stuff, multilevel_susceptibility(3, 2, Gamma, N0, alpha, omega, gam, sigmat));
+      p->s->add_susceptibility(slab_mask_y, E_stuff, lorentzian_susceptibility(1.2, 0.01));
+    }
+    p->f = new fields(p->s);
+    if (d3) p->f->use_real_fields();
+    p->f->add_point_source(Ez, 0.3, 0.25, 0.0, 4.0, p->gv.center(), 1.0);
+    p->f->add_point_source(d3 ? Ex : Hz, 0.25, 0.25, 0.0, 4.0, p->gv.center(), 0.5);
+  }
+  else if (name == "noisy3d" || name == "noisy2d") { // noisy_lorentzian_susceptibility (susceptibility.cpp:317-339)
+    // noisy3d: electric noisy Lorentzian slab, real fields; noisy2d: a magnetic noisy Drude term AND an electric
+    // noisy Lorentzian (the draws of one step: H_stuff first, then E_stuff), complex fields.  The twins share the
+    // process-global generator: main() re-seeds it before each twin's stepping (reseed())
+    if (!n) n = 14;
+    const bool d3 = name == "noisy3d";
+    const double L = n / a;
+    p->gv = d3 ? vol3d(L, L, L, a) : vol2d(L, 1.5 * L, a);
+    g_slab_lo = (d3 ? 0.3 : 0.45) * L;
+    g_slab_hi = (d3 ? 0.7 : 1.05) * L;
+    g_slab_eps = 2.0;
+    p->s = new structure(p->gv, d3 ? slab_eps_z : slab_eps_y, pml(0.1 * L > 0.5 ? 0.5 : 0.1 * L), identity(), nchunks, 0.5, false);
+    const double amp = param != 0 ? param : 0.05;
+    p->s->add_susceptibility(d3 ? slab_mask_z : slab_mask_y, E_stuff, noisy_lorentzian_susceptibility(amp, 1.1, 0.05));
+    if (!d3) {
+      p->s->add_susceptibility(slab_mask_y, H_stuff, noisy_lorentzian_susceptibility(0.5 * amp, 0.7, 0.02, true));
+      p->s->add_susceptibility(slab_mask_y, E_stuff, lorentzian_susceptibility(1.3, 0.01));
+    }
+    p->f = new fields(p->s);
+    if (d3) p->f->use_real_fields();
+    p->f->add_point_source(Ez, 0.3, 0.25, 0.0, 4.0, p->gv.center(), 1.0);
+    p->f->add_point_source(d3 ? Ex : Hz, 0.25, 0.25, 0.0, 4.0, p->gv.center(), 0.5);
+  }
   else if (name == "phc3d") { // BASELINE config 5 shape: slab, PML in z, Bloch-periodic x,y, fp32-able
     if (!n) n = 16;
     p->gv = vol3d(n / a, n / a, 1.5 * n / a, a);
@@ -521,6 +588,10 @@ static std::vector<marray> collect(fields &f) {
         snprintf(nm, sizeof nm, "chunk%d.f_w[%s][%d]", i, component_name(c), cmp);
         out.push_back({fc->f_w[c][cmp], nb, nm});
       }
+      if (fc->f_w_prev[c][cmp]) {
+        snprintf(nm, sizeof nm, "chunk%d.f_w_prev[%s][%d]", i, component_name(c), cmp);
+        out.push_back({fc->f_w_prev[c][cmp], nb, nm});
+      }
       if (fc->f_cond[c][cmp]) {
         snprintf(nm, sizeof nm, "chunk%d.f_cond[%s][%d]", i, component_name(c), cmp);
         out.push_back({fc->f_cond[c][cmp], nb, nm});
@@ -536,7 +607,17 @@ static std::vector<marray> collect(fields &f) {
       for (polarization_state *p = fc->pol[ehs[k]]; p; p = p->next, ++ip) {
         if (!p->data) continue;
         // lorentzian_data: P, P_prev per (c, cmp); gyrotropy_data: (P, P_prev) for each of X, Y, Z
-        const int nsub = typeid(*p->s) == typeid(gyrotropic_susceptibility) ? 3 : 1;
+        // multilevel_data: (P, P_prev) for each transition, and the populations N (ntot x L)
+        const bool ml = typeid(*p->s) == typeid(multilevel_susceptibility);
+        const int nsub = typeid(*p->s) == typeid(gyrotropic_susceptibility) ? 3
+                         : ml ? static_cast<const multilevel_susceptibility *>(p->s)->T : 1;
+        if (ml) {
+          struct ml_layout { size_t sz_data, ntot; realnum *GammaInv; realnum **P[NUM_FIELD_COMPONENTS][2];
+                             realnum **P_prev[NUM_FIELD_COMPONENTS][2]; realnum *N, *Ntmp; };
+          const ml_layout *md = (const ml_layout *)p->data;
+          snprintf(nm, sizeof nm, "chunk%d.pol%d_%d.N", i, k, ip);
+          out.push_back({md->N, nb * static_cast<const multilevel_susceptibility *>(p->s)->L, nm});
+        }
         FOR_COMPONENTS(c) for (int cmp = 0; cmp < 2; ++cmp) for (int sub = 0; sub < nsub; ++sub) {
           realnum *P = p->s->cinternal_notowned_ptr(sub, c, cmp, 0, p->data);
           if (!P) continue;
@@ -697,6 +778,7 @@ int main(int argc, char **argv) {
 
   if (mode == "ref") {
     problem *p = build(cas, nchunks);
+    reseed(0);
     for (int i = 0; i < warmup; ++i) p->f->step();
     double t0 = wall_time();
     for (int i = 0; i < steps; ++i) p->f->step();
@@ -740,7 +822,7 @@ int main(int argc, char **argv) {
     meepcu::trace_recorder *rec = record.empty() ? 0 : new meepcu::trace_recorder(record.c_str());
     // warm-up steps run on the reference CPU path on BOTH twins: the attach then happens in
     // mid-simulation, with every lazily allocated array already live
-    for (int i = 0; i < warmup; ++i) { A->f->step(); B->f->step(); }
+    for (int i = 0; i < warmup; ++i) { reseed(i); A->f->step(); reseed(i); B->f->step(); }
     meepcu::attachment *att = new meepcu::attachment(*B->f, api, nl_mode, device, rec);
     double t0 = wall_time();
     size_t sync_bad = 0, sync_checks = 0;
@@ -751,7 +833,9 @@ int main(int argc, char **argv) {
       // the reference on the CPU, twin B on the device), every array is compared, and both restore
       for (int done = 0; done < steps; done += syncmag) {
         const int n = std::min(syncmag, steps - done);
+        reseed(warmup + done);
         for (int i = 0; i < n; ++i) A->f->step();
+        reseed(warmup + done);
         att->step(n);
         A->f->synchronize_magnetic_fields();
         att->synchronize_magnetic_fields();
@@ -767,9 +851,15 @@ int main(int argc, char **argv) {
       t1 = wall_time();
     }
     else {
-      for (int i = 0; i < steps; ++i) A->f->step();
+      for (int i = 0; i < steps; ++i) {
+        if (i % batch == 0) reseed(warmup + i);
+        A->f->step();
+      }
       t1 = wall_time();
-      for (int done = 0; done < steps; done += batch) att->step(std::min(batch, steps - done));
+      for (int done = 0; done < steps; done += batch) {
+        reseed(warmup + done);
+        att->step(std::min(batch, steps - done));
+      }
     }
     att->sync_to_host();
     double t2 = wall_time();
@@ -803,11 +893,12 @@ int main(int argc, char **argv) {
     // twin B is stepped by calling the reference's own fields::step(), which delegates to --lib
     if (lib.empty()) { fprintf(stderr, "--lib required\n"); return 2; }
     problem *A = build(cas, nchunks), *B = build(cas, nchunks);
-    for (int i = 0; i < warmup; ++i) { A->f->step(); B->f->step(); } // drop-in off: both on the CPU
+    for (int i = 0; i < warmup; ++i) { reseed(i); A->f->step(); reseed(i); B->f->step(); } // drop-in off: both on the CPU
     double t0 = wall_time();
     double mid_ref = 0, mid_abi = 0, mid_energy_ref = 0, mid_energy_abi = 0;
     std::vector<double> flux_mid_ref, flux_mid_abi, flux_end_ref, flux_end_abi, box_ref, box_abi;
     for (int i = 0; i < steps; ++i) {
+      reseed(warmup + i);
       A->f->step();
       if (i == steps / 2) {
         mid_ref = probe_value(A);
@@ -826,6 +917,7 @@ int main(int argc, char **argv) {
     problem *C = 0;
     size_t sync_bad = 0, sync_checks = 0;
     for (int i = 0; i < steps; ++i) {
+      reseed(warmup + i);
       B->f->step(); // <- the seam: unchanged caller code, device underneath
       if (i == steps / 3 && addsrc) { // same calls on the twin that lives on the device: the next step re-attaches
         B->f->add_point_source(B->gv.dim == D1 ? Ex : Ez, 0.22, 0.2, 0.0, 4.0, B->gv.center(), 0.7);
@@ -849,6 +941,7 @@ int main(int argc, char **argv) {
           fields::gpu_enable(NULL);
           C = build(cas, nchunks);
           for (int k = 0; k < warmup + i + 1; ++k) {
+            reseed(k);
             C->f->step();
             if (k - warmup == steps / 2) // the mid-run scale_dfts the other twins went through
               for (size_t q = 0; q < C->fluxes.size(); ++q) C->fluxes[q].scale_dfts(std::complex<double>(0.5, 0.25));

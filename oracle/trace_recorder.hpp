@@ -14,7 +14,7 @@ namespace meepcu {
 class trace_recorder : public observer {
 public:
   enum { T_CONFIG = 1, T_ARRAY, T_CHUNK, T_SUSC, T_SOURCE, T_DFT, T_METAL, T_CONN, T_FINALIZE,
-         T_STEP, T_EXPECT, T_GYRO };
+         T_STEP, T_EXPECT, T_GYRO, T_MLATOM, T_NOISE };
 
   explicit trace_recorder(const char *path) : rb(8) {
     fp = fopen(path, "wb");
@@ -83,6 +83,41 @@ public:
     putd(d.omega_0);
     putd(d.gamma);
     put(ids.data(), ids.size() * 8);
+    if (d.noise_amp != 0) putd(d.noise_amp); // appended (noisy Lorentzian): older readers stop before it
+    end();
+  }
+  void on_multilevel(int i, const meepcu_multilevel_desc &d, size_t ntot) {
+    std::vector<int64_t> ids;
+    ids.push_back(reg(d.Gamma, (size_t)d.L * d.L, rb));
+    ids.push_back(reg(d.GammaInv, (size_t)d.L * d.L, rb));
+    ids.push_back(reg(d.alpha, (size_t)d.L * d.T, rb));
+    ids.push_back(reg(d.omega, d.T, rb));
+    ids.push_back(reg(d.gamma, d.T, rb));
+    ids.push_back(reg(d.sigmat, 5 * (size_t)d.T, rb));
+    ids.push_back(reg(d.N, ntot * d.L, rb));
+    for (int c = 0; c < 20; ++c)
+      for (int k = 0; k < 5; ++k) ids.push_back(reg(d.sigma[c][k], ntot, rb));
+    for (int c = 0; c < 20; ++c)
+      for (int k = 0; k < 2; ++k) ids.push_back(reg(d.W_prev[c][k], ntot, rb));
+    for (int c = 0; c < 20; ++c)
+      for (int k = 0; k < 2; ++k)
+        for (int t = 0; t < d.T; ++t) ids.push_back(d.P[c][k] ? reg(d.P[c][k][t], ntot, rb) : -1);
+    for (int c = 0; c < 20; ++c)
+      for (int k = 0; k < 2; ++k)
+        for (int t = 0; t < d.T; ++t) ids.push_back(d.P_prev[c][k] ? reg(d.P_prev[c][k][t], ntot, rb) : -1);
+    begin(T_MLATOM);
+    put32(i);
+    put32(d.ft);
+    put32(d.L);
+    put32(d.T);
+    put(ids.data(), ids.size() * 8);
+    end();
+  }
+  void on_noise(int nsteps, size_t n_per_step, const double *g) { // the values of the NEXT T_STEP record
+    begin(T_NOISE);
+    put32(nsteps);
+    put64((int64_t)n_per_step);
+    put(g, 8 * (size_t)nsteps * n_per_step);
     end();
   }
   void on_gyrotropic(int i, const meepcu_gyrotropic_desc &d, size_t ntot) {

@@ -73,7 +73,7 @@ def test_step_batching_is_invisible(cuda_backend):
     path = [p for p in GOLDEN if "lorentz3d_16_fp64" in p][0]
     t = tr.Trace(path)
     r = tr.Replay(t, cuda_backend)
-    for ns, nsrc, raw in t.steps:
+    for ns, nsrc, raw, _noise in t.steps:
         sz = C.sizeof(A.SrcSample) * nsrc
         for s in range(ns):
             chunk = raw[s * sz:(s + 1) * sz]
@@ -90,7 +90,7 @@ def test_sync_roundtrip_is_lossless(cuda_backend):
     path = [p for p in GOLDEN if "kr_xper_ypml3d_fp64" in p][0]
     t = tr.Trace(path)
     r = tr.Replay(t, cuda_backend)
-    ns, nsrc, raw = t.steps[0]
+    ns, nsrc, raw, _noise = t.steps[0]
     sz = C.sizeof(A.SrcSample) * nsrc
     half = ns // 2
     a = raw[:half * sz]

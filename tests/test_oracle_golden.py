@@ -37,7 +37,7 @@ def test_split_run_equals_single_run(oracle_backend):
     t = tr.Trace(path)
     r = tr.Replay(t, oracle_backend)
     done = 0
-    for ns, nsrc, raw in t.steps:
+    for ns, nsrc, raw, _noise in t.steps:
         import ctypes as C
         from meep_nl_b200 import _cabi as A
         sz = C.sizeof(A.SrcSample) * nsrc

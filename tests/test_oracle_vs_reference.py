@@ -37,6 +37,14 @@ CASES = [("fp64", "vac3d:24", 25, 2), ("fp64", "kr_per3d_rods", 40, 0), ("fp64",
          ("fp32", "cylpml:18:1", 120, 0), ("fp64", "cylpml:18:3", 120, 0), ("fp64", "cylpmlnz:18:3", 120, 0),
          ("fp64", "cylcond:18:1", 120, 2), ("fp32", "cylcond:18:2", 120, 0), ("fp64", "cyllor:20:1", 150, 2),
          ("fp32", "cyllor:20:0", 150, 0), ("fp64", "cyllor:18:2", 150, 0),
+         # multilevel-atom gain media (multilevel-atom.cpp: populations on the centred grid, one polarisation per
+         # transition, W_prev) -- two levels / one transition with real fields, three levels / two transitions with
+         # complex fields next to an ordinary Lorentzian
+         ("fp64", "mlatom3d", 60, 2), ("fp32", "mlatom3d", 60, 2), ("fp64", "mlatom2d", 80, 2), ("fp32", "mlatom2d", 80, 2),
+         ("fp64", "mlatom3d:18:0.6", 100, 0),
+         # noisy Lorentzian media (susceptibility.cpp:317-339): the reference's own generator draws the unit Gaussians in
+         # its loop order for both twins; electric, and magnetic Drude + electric in one step with complex fields
+         ("fp64", "noisy3d", 60, 2), ("fp32", "noisy3d", 60, 2), ("fp64", "noisy2d", 80, 2), ("fp32", "noisy2d", 80, 2),
          # UPSTREAM_PADE against the de-blocked reference flavour (oracle/deblock_pade.py)
          ("fp64_pade", "kerr3d:14", 40, 2), ("fp64_pade", "kerr1d", 80, 0), ("fp64_pade", "kr_per3d_rods", 40, 0)]
 
@@ -81,7 +89,8 @@ def test_reference_known_answers_through_the_oracle():
 SYNC_CASES = [("fp64", "vac3d:32", 40), ("fp64", "wvg2d", 60), ("fp64", "lorentz3d:16", 40), ("fp32", "vac3d_cplx:14", 30),
               ("fp64", "kr_per3d_rods", 40), ("fp64", "cond3d:12", 40), ("fp64", "bfast3d:10", 40), ("fp32", "beta2d", 40),
               ("fp64", "magdrude3d", 40), ("fp32", "magdrude2d", 40), ("fp64", "gyrosat3d", 40),
-              ("fp64", "cylpml:18:1", 40), ("fp64", "cyllor:18:0", 40), ("fp32", "cylcond:18:2", 40)]
+              ("fp64", "cylpml:18:1", 40), ("fp64", "cyllor:18:0", 40), ("fp32", "cylcond:18:2", 40),
+              ("fp64", "mlatom3d", 40), ("fp32", "noisy2d", 40)]
 
 
 @pytest.mark.parametrize("flavour,case,steps", SYNC_CASES)
@@ -104,7 +113,8 @@ def test_synchronize_magnetic_fields_equals_reference(flavour, case, steps):
 
 @pytest.mark.parametrize("flavour,case,chunks", [("fp64", "vac3d:32", 5), ("fp64", "lorentz3d:16", 4), ("fp32", "wvg2d", 6),
                                                  ("fp64", "nrslab3d:14", 3), ("fp64", "aniso3d:14", 3),
-                                                 ("fp64", "cyllor:24:1", 3), ("fp32", "cylpml:24:2", 4)])
+                                                 ("fp64", "cyllor:24:1", 3), ("fp32", "cylpml:24:2", 4),
+                                                 ("fp64", "mlatom3d:16", 3), ("fp64", "noisy3d:16", 3)])
 def test_reference_chunk_splitting(flavour, case, chunks):
     """structure(..., num_chunks) lets the reference split the cell by cost into many more chunks (40-50):
     the description the shim hands over changes completely, the fields must not"""

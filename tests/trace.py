@@ -19,7 +19,7 @@ import numpy as np
 
 from meep_nl_b200 import _cabi as A
 
-T_CONFIG, T_ARRAY, T_CHUNK, T_SUSC, T_SOURCE, T_DFT, T_METAL, T_CONN, T_FINALIZE, T_STEP, T_EXPECT, T_GYRO = range(1, 13)
+T_CONFIG, T_ARRAY, T_CHUNK, T_SUSC, T_SOURCE, T_DFT, T_METAL, T_CONN, T_FINALIZE, T_STEP, T_EXPECT, T_GYRO, T_MLATOM, T_NOISE = range(1, 15)
 
 
 class Reader:
@@ -63,7 +63,8 @@ class Trace:
         self.cfg = None
         self.arrays = {}
         self.expect = {}
-        self.steps = []  # list of (nsteps, nsrc, bytes)
+        self.steps = []  # list of (nsteps, nsrc, bytes, noise of those steps or None)
+        noise = None
         self.calls = []  # description calls in order
         for tag, pl in self.records:
             r = Reader(pl)
@@ -85,7 +86,12 @@ class Trace:
                 self.expect[aid] = (n, pl[r.o:])
             elif tag == T_STEP:
                 ns, nsrc = r.i32(), r.i32()
-                self.steps.append((ns, nsrc, pl[r.o:]))
+                self.steps.append((ns, nsrc, pl[r.o:], noise))
+                noise = None
+            elif tag == T_NOISE:  # unit Gaussians of the next T_STEP record (noisy Lorentzian media)
+                ns = r.i32()
+                npst = r.i64()
+                noise = (npst, np.frombuffer(r.take(8 * ns * npst), dtype=np.float64).copy())
             else:
                 self.calls.append((tag, pl))
         # expected arrays get the dtype of the array they shadow
@@ -191,7 +197,33 @@ class Replay:
             for c in range(20):
                 for k in range(2):
                     tab[c][k] = self.addr(next(it))
+        if len(r.b) - r.o >= 8:  # appended: noisy Lorentzian
+            d.noise_amp = r.f64()
         self.b.check(self.b.add_susceptibility(self.ctx, i, C.byref(d)))
+
+    def _t13(self, r):  # MLATOM
+        i, ft, L, T = r.i32(), r.i32(), r.i32(), r.i32()
+        d = A.MultilevelDesc()
+        d.ft, d.L, d.T = ft, L, T
+        it = iter(r.i64(7 + 20 * 5 + 20 * 2 + 2 * 20 * 2 * T).tolist())
+        for name in ("Gamma", "GammaInv", "alpha", "omega", "gamma", "sigmat", "N"):
+            setattr(d, name, self.addr(next(it)))
+        for c in range(20):
+            for k in range(5):
+                d.sigma[c][k] = self.addr(next(it))
+        for c in range(20):
+            for k in range(2):
+                d.W_prev[c][k] = self.addr(next(it))
+        for name in ("P", "P_prev"):
+            tab = getattr(d, name)
+            for c in range(20):
+                for k in range(2):
+                    ptrs = [self.addr(next(it)) for _ in range(T)]
+                    if ptrs[0]:
+                        arr = (A.vp * T)(*ptrs)
+                        self.keep.append(arr)
+                        tab[c][k] = C.cast(arr, A.vp)
+        self.b.check(self.b.add_multilevel(self.ctx, i, C.byref(d)))
 
     def _t12(self, r):  # GYRO
         i, ft, model = r.i32(), r.i32(), r.i32()
@@ -274,11 +306,15 @@ class Replay:
     def run(self, max_steps=None):
         """Issue the recorded meepcu_step calls (optionally only the first max_steps steps)."""
         done = 0
-        for ns, nsrc, raw in self.tr.steps:
+        for ns, nsrc, raw, noise in self.tr.steps:
             if max_steps is not None:
                 ns = min(ns, max_steps - done)
                 if ns <= 0:
                     break
+            if noise is not None:
+                npst, g = noise
+                g = np.ascontiguousarray(g[:ns * npst])
+                self.b.check(self.b.set_noise(self.ctx, ns, npst, g.ctypes.data))
             buf = C.create_string_buffer(raw, len(raw)) if raw else None
             self.b.check(self.b.step(self.ctx, ns, nsrc, buf))
             done += ns
