@@ -1987,6 +1987,186 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// multilevel_susceptibility::update_P (multilevel-atom.cpp:240-374), two passes after the chunk's E update and the W
+// halo exchange:
+//   k_ml_levels  the populations N of the L levels at every owned point of the CENTRED grid (:260-329): relaxation
+//                (I - Gamma dt/2) N, plus alpha * (E . dP/dt + gamma_perp E . P) from the eight-point sums of W, W_prev
+//                and of every transition's P, P_prev around the point, then N = GammaInv * that.  N keeps the
+//                reference's layout N[i_host * L + level] (the L values of a point are contiguous: one thread, one point).
+//   k_ml_pol     every transition's polarisation at the owned Yee points of its component (:331-373): an oscillator
+//                driven by sigma_t * sigma * W times the population inversion averaged back from four centred points.
+// Every expression keeps the reference's operand order; the point-independent factors ((l1 == l2) - Gamma dt/2,
+// gamma pi dt, 2 - omega0^2 dt^2 ...) are formed once on the host in realnum, as the reference forms them per point.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMlMaxL = 8, kMlMaxT = 4;
+template <class T> struct MlLevelParams {
+  int nA, nB, nC, pitch;
+  long long sA, sB;       // device strides of the field / polarisation arrays
+  long long hA, hB, hC;   // host strides by device axis (the layout of N)
+  int hi[3];              // owned centred points: 0 .. hi[axis]
+  int L, Tn, ndot;
+  T *N;
+  const T *w[3][2], *wp[3][2];  // W = f_w ?: f and f_w_prev of the (up to three) polarised components, cmp 0 / 1
+  long long o1[3], o2[3];       // grid_volume::yee2cent_offsets of those components, device elements
+  const T *p[3][2][kMlMaxT], *pp[3][2][kMlMaxT];
+  T A[kMlMaxL * kMlMaxL];       // (l1 == l2) - Gamma[l1 L + l2] dt/2   (:265-270)
+  T Ginv[kMlMaxL * kMlMaxL];    // multilevel_data::GammaInv
+  T alpha[kMlMaxL * kMlMaxT];   // alpha[l Tn + t]
+  T gperpdt[kMlMaxT];           // gamma[t] pi dt                        (:297)
+};
+
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+    k_ml_levels(const MlLevelParams<T> *__restrict__ params, const Tile *__restrict__ tiles) {
+  __shared__ MlLevelParams<T> P;
+  const Tile t = tiles[blockIdx.x];
+  block_copy_params(&P, params + t.param);
+  __syncthreads();
+  const int pos = t.p0 + threadIdx.x;
+  const int ib = pos / P.pitch, ic = pos - ib * P.pitch;
+  if (ib > P.hi[1] || ic > P.hi[2]) return;
+  const int a1 = t.a1 - 1 < P.hi[0] ? t.a1 - 1 : P.hi[0];
+  const int L = P.L, Tn = P.Tn, ndot = P.ndot;
+  for (int ia = t.a0; ia <= a1; ++ia) {
+    const long long i = (long long)ia * P.sA + (long long)ib * P.sB + ic;
+    T *N = P.N + ((long long)ia * P.hA + (long long)ib * P.hB + (long long)ic * P.hC) * L;
+    T Nv[kMlMaxL], Ntmp[kMlMaxL];
+    for (int l = 0; l < L; ++l) Nv[l] = N[l];
+    for (int l1 = 0; l1 < L; ++l1) { // Ntmp = (I - Gamma * dt/2) * N
+      T a = 0;
+      for (int l2 = 0; l2 < L; ++l2) a += P.A[l1 * L + l2] * Nv[l2];
+      Ntmp[l1] = a;
+    }
+    T E8[3][2] = {{0, 0}, {0, 0}, {0, 0}}; // E*8 at point i (:273-288)
+    for (int k = 0; k < ndot; ++k) {
+      const long long o1 = P.o1[k], o2 = P.o2[k];
+      const T *w = P.w[k][0], *wp = P.wp[k][0];
+      E8[k][0] = w[i] + w[i + o1] + w[i + o2] + w[i + o1 + o2] + wp[i] + wp[i + o1] + wp[i + o2] + wp[i + o1 + o2];
+      if (P.w[k][1]) {
+        w = P.w[k][1];
+        wp = P.wp[k][1];
+        E8[k][1] = w[i] + w[i + o1] + w[i + o2] + w[i + o1 + o2] + wp[i] + wp[i + o1] + wp[i + o2] + wp[i + o1 + o2];
+      }
+    }
+    for (int tr = 0; tr < Tn; ++tr) { // Ntmp = Ntmp + alpha * E * dP (:291-321)
+      T EdP32 = 0, EPave64 = 0;
+      const T gperpdt = P.gperpdt[tr];
+      for (int k = 0; k < ndot; ++k) {
+        const long long o1 = P.o1[k], o2 = P.o2[k];
+        for (int cmp = 0; cmp < 2; ++cmp) {
+          const T *p = P.p[k][cmp][tr], *pp = P.pp[k][cmp][tr];
+          if (!p) continue;
+          const T sp = p[i] + p[i + o1] + p[i + o2] + p[i + o1 + o2];
+          const T spp = pp[i] + pp[i + o1] + pp[i + o2] + pp[i + o1 + o2];
+          const T dP = sp - spp, Pave2 = sp + spp;
+          EdP32 += dP * E8[k][cmp];
+          EPave64 += Pave2 * E8[k][cmp];
+        }
+      }
+      EdP32 *= 0.03125;
+      EPave64 *= 0.015625;
+      for (int l = 0; l < L; ++l) Ntmp[l] += P.alpha[l * Tn + tr] * EdP32 + P.alpha[l * Tn + tr] * gperpdt * EPave64;
+    }
+    for (int l1 = 0; l1 < L; ++l1) { // N = GammaInv * Ntmp
+      T a = 0;
+      for (int l2 = 0; l2 < L; ++l2) a += P.Ginv[l1 * L + l2] * Ntmp[l2];
+      N[l1] = a;
+    }
+  }
+}
+
+template <class T> struct MlPolParams {
+  int nA, nB, nC, pitch;
+  long long sA, sB;
+  long long hA, hB, hC;
+  int lo[3], hi[3];     // owned points of the component
+  int L, lp, lm;        // the two levels the transition couples (alpha > 0 / alpha < 0, :341-347)
+  T *p, *pp;
+  const T *s, *w, *N;
+  long long oa, ob;     // grid_volume::cent2yee_offsets in elements of N (host strides times L, negative)
+  T gamma1inv, gamma1, two_minus, dtsqr, st; // :332-336,351
+};
+
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+    k_ml_pol(const MlPolParams<T> *__restrict__ params, const Tile *__restrict__ tiles) {
+  __shared__ MlPolParams<T> P;
+  const Tile t = tiles[blockIdx.x];
+  block_copy_params(&P, params + t.param);
+  __syncthreads();
+  const int pos = t.p0 + threadIdx.x;
+  const int ib = pos / P.pitch, ic = pos - ib * P.pitch;
+  if (ib < P.lo[1] || ib > P.hi[1] || ic < P.lo[2] || ic > P.hi[2]) return;
+  const int a0 = t.a0 > P.lo[0] ? t.a0 : P.lo[0];
+  const int a1 = t.a1 - 1 < P.hi[0] ? t.a1 - 1 : P.hi[0];
+  T *p = P.p, *pp = P.pp;
+  const T *s = P.s, *w = P.w;
+  const int lp = P.lp, lm = P.lm;
+  const long long oa = P.oa, ob = P.ob;
+  const T gamma1inv = P.gamma1inv, gamma1 = P.gamma1, two_minus = P.two_minus, dtsqr = P.dtsqr, st = P.st;
+  for (int ia = a0; ia <= a1; ++ia) {
+    const long long i = (long long)ia * P.sA + (long long)ib * P.sB + ic;
+    const T *Ni = P.N + ((long long)ia * P.hA + (long long)ib * P.hB + (long long)ic * P.hC) * P.L;
+    const T pcur = p[i];
+    // dNi is the population inversion for this transition (:366-368)
+    const T dNi = 0.25 * (Ni[lp] + Ni[lp + oa] + Ni[lp + ob] + Ni[lp + oa + ob] - Ni[lm] - Ni[lm + oa] - Ni[lm + ob] -
+                          Ni[lm + oa + ob]);
+    p[i] = gamma1inv * (pcur * two_minus - gamma1 * pp[i] - dtsqr * (st * s[i] * w[i]) * dNi);
+    pp[i] = pcur;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// noisy_lorentzian_susceptibility::update_P (susceptibility.cpp:317-339), the part after the Lorentzian update:
+// p[i] += gaussian_random(0, amp sqrt(sigma[i])) at every owned point, in the reference's loop order.  The unit
+// Gaussians g come from the CALLER's generator (include/meepcu.h, meepcu_set_noise): gaussian_random(0, stddev) is
+// 0 + g stddev in double (random.cpp:57-69), so the value stored is the reference's, bit for bit.
+// ------------------------------------------------------------------------------------------------
+// whole-array device copies from a table (fields_chunk::f_w_prev = W before the E update, update_eh.cpp:221-226)
+template <class T> struct CopyItem {
+  T *dst;
+  const T *src;
+  long long n;
+};
+template <class T> __global__ void __launch_bounds__(kThreads) k_copy_arrays(const CopyItem<T> *__restrict__ items) {
+  const CopyItem<T> it = items[blockIdx.y];
+  for (long long k = (long long)blockIdx.x * kThreads + threadIdx.x; k < it.n; k += (long long)gridDim.x * kThreads)
+    it.dst[k] = it.src[k];
+}
+
+template <class T> struct NoiseSeg {
+  T *p;
+  const T *s;
+  T amp;            // w2pi noise_amp sqrt(g2pi) dt dt / (1 + g2pi dt / 2), in realnum (:325)
+  long long first;  // index of the segment's first value within the half step's sequence
+  long long base;   // device index of its first owned point
+  long long ds[3];  // device strides X, Y, Z
+  int n[3];         // owned points per direction (1: absent), X outermost = LOOP_OVER_VOL_OWNED's order
+};
+
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+    k_pol_noise(const NoiseSeg<T> *__restrict__ segs, int nseg, long long total, const double *__restrict__ g) {
+  for (long long k = (long long)blockIdx.x * kThreads + threadIdx.x; k < total; k += (long long)gridDim.x * kThreads) {
+    int lo = 0, hi = nseg - 1; // last segment with first <= k
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (segs[mid].first <= k) lo = mid;
+      else hi = mid - 1;
+    }
+    const NoiseSeg<T> &S = segs[lo];
+    long long r = k - S.first;
+    const int iz = (int)(r % S.n[2]);
+    r /= S.n[2];
+    const int iy = (int)(r % S.n[1]);
+    const int ix = (int)(r / S.n[1]);
+    const long long i = S.base + ix * S.ds[0] + iy * S.ds[1] + iz * S.ds[2];
+    const T stddev = S.amp * sqrt(S.s[i]);
+    S.p[i] = (T)((double)S.p[i] + (0.0 + g[k] * (double)stddev));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // dft_chunk::update_dft (dft.cpp:265-307).  One thread per (point, omega) element of dft[] so the
 // read-modify-write of the accumulator -- the dominant traffic -- is fully coalesced.
 // ------------------------------------------------------------------------------------------------

@@ -243,6 +243,18 @@ struct SuscH {
   meepcu_susceptibility_desc d; // gyrotropic: sigma, and P/P_prev = the component subtract_P uses (P[c][cmp][dir(c)])
   bool gyro;
   meepcu_gyrotropic_desc g;
+  // multilevel atoms: one entry per transition t, holding P[c][cmp][t] with NO sigma: subtract-only entries, in the order
+  // subtract_P takes them off D (multilevel-atom.cpp:376-394); the update itself is k_ml_levels / k_ml_pol
+  int ml, ml_t; // index into ChunkH::ml (-1: not a multilevel entry), transition
+};
+// multilevel_susceptibility + multilevel_data (src/multilevel-atom.cpp:118-128, src/meep.hpp:377-386); the small
+// arrays are kept as double (exact for either realnum)
+struct MlH {
+  int L, Tn;
+  std::vector<double> Gamma, GammaInv, alpha, omega, gamma, sigmat;
+  const void *sigma[MEEPCU_NUM_COMPONENTS][5];
+  std::vector<const void *> P[MEEPCU_NUM_COMPONENTS][2], P_prev[MEEPCU_NUM_COMPONENTS][2]; // [t]
+  const void *N;
 };
 struct SrcH {
   int ft, c, tid, integrated;
@@ -259,6 +271,8 @@ struct ChunkH {
   meepcu_chunk_desc d;
   Geom g;
   std::vector<SuscH> pol[2];
+  std::vector<MlH> ml;                                // multilevel media (E_stuff)
+  const void *w_prev[MEEPCU_NUM_COMPONENTS][2];       // fields_chunk::f_w_prev (update_eh.cpp:221-226)
   std::vector<SrcH> src;
   std::vector<DftH> dft;
   bool have_plus[20], have_minus[20];
@@ -278,6 +292,9 @@ struct CtxBase {
   virtual int add_chunk(const meepcu_chunk_desc *d, int *id) = 0;
   virtual int add_susc(int chunk, const meepcu_susceptibility_desc *d) = 0;
   virtual int add_gyro(int chunk, const meepcu_gyrotropic_desc *d) = 0;
+  virtual int add_multilevel(int chunk, const meepcu_multilevel_desc *d) = 0;
+  virtual size_t noise_count() = 0;
+  virtual int set_noise(int nsteps, size_t n_per_step, const double *g) = 0;
   virtual int add_source(int chunk, const meepcu_source_desc *d) = 0;
   virtual int add_dft(int chunk, const meepcu_dft_desc *d, int *id) = 0;
   virtual int set_metal(int ft, size_t n, void *const *ptrs) = 0;
@@ -393,6 +410,21 @@ template <class T> struct Ctx : CtxBase {
   long long n_zero_late[2];
   T **d_zero[MEEPCU_NUM_FIELD_TYPES]; // unfused metal lists (only non-plane lists; normally empty)
   long long n_zero[MEEPCU_NUM_FIELD_TYPES];
+  MlLevelParams<T> *d_mllev;       // multilevel atoms: populations (k_ml_levels) and polarisations (k_ml_pol)
+  std::vector<MlLevelParams<T> > h_mllev;
+  MlPolParams<T> *d_mlpol;
+  std::vector<MlPolParams<T> > h_mlpol;
+  Tile *d_mllev_tiles, *d_mlpol_tiles;
+  int n_mllev_tiles, n_mlpol_tiles;
+  CopyItem<T> *d_wprev;            // W -> W_prev copies at the start of the D/E half (update_eh.cpp:221-226)
+  int n_wprev;
+  long long wprev_max;
+  NoiseSeg<T> *d_noise_seg[2];     // noisy Lorentzian media, per half (k_pol_noise)
+  int n_noise_seg[2];
+  long long noise_total[2];        // unit Gaussians per time step: [0] update_pols(H_stuff), [1] update_pols(E_stuff)
+  std::vector<double> noise_host;  // meepcu_set_noise: the values of the next meepcu_step call
+  int noise_steps;
+  const double *cur_noise;         // device address of the current step's values
   PolGyroParams<T> *d_polgyro;     // gyrotropic polarisation updates (k_pol_gyro)
   std::vector<PolGyroParams<T> > h_polgyro;
   Tile *d_polgyro_tiles[2];
@@ -567,6 +599,18 @@ template <class T> struct Ctx : CtxBase {
     memset(n_runs_def, 0, sizeof n_runs_def);
     memset(d_zero_late, 0, sizeof d_zero_late);
     memset(n_zero_late, 0, sizeof n_zero_late);
+    d_mllev = 0;
+    d_mlpol = 0;
+    d_mllev_tiles = d_mlpol_tiles = 0;
+    n_mllev_tiles = n_mlpol_tiles = 0;
+    d_wprev = 0;
+    n_wprev = 0;
+    wprev_max = 0;
+    memset(d_noise_seg, 0, sizeof d_noise_seg);
+    memset(n_noise_seg, 0, sizeof n_noise_seg);
+    memset(noise_total, 0, sizeof noise_total);
+    noise_steps = 0;
+    cur_noise = 0;
     d_polgyro = 0;
     memset(d_polgyro_tiles, 0, sizeof d_polgyro_tiles);
     memset(n_polgyro_tiles, 0, sizeof n_polgyro_tiles);
@@ -630,6 +674,7 @@ template <class T> struct Ctx : CtxBase {
     if (finalized) return fail(MEEPCU_ESTATE, "context already finalized");
     ChunkH ch;
     ch.d = *d;
+    memset(ch.w_prev, 0, sizeof ch.w_prev);
     if (cfg.dim == MEEPCU_Dcyl) canon_chunk_desc(ch.d);
     d = &ch.d;
     Geom &g = ch.g;
@@ -713,8 +758,11 @@ template <class T> struct Ctx : CtxBase {
     if (chunk < 0 || chunk >= (int)chunks.size()) return fail(MEEPCU_EINVAL, "bad chunk id");
     if (d->ft != MEEPCU_E_STUFF && d->ft != MEEPCU_H_STUFF)
       return fail(MEEPCU_EINVAL, "susceptibility ft must be E_stuff or H_stuff");
+    if (d->noise_amp != 0 && cfg.dim == MEEPCU_Dcyl)
+      return fail(MEEPCU_EUNSUPPORTED, "noisy Lorentzian media in cylindrical coordinates");
     SuscH s;
     memset(&s, 0, sizeof s);
+    s.ml = -1;
     s.d = *d;
     if (cfg.dim == MEEPCU_Dcyl) canon_susc_desc(s.d);
     chunks[chunk].pol[d->ft].push_back(s);
@@ -731,6 +779,7 @@ template <class T> struct Ctx : CtxBase {
     if (cfg.dim != MEEPCU_D3) return fail(MEEPCU_EINVAL, "gyrotropic media require 3D Cartesian fields");
     SuscH s;
     memset(&s, 0, sizeof s);
+    s.ml = -1;
     s.gyro = true;
     s.g = *d;
     s.d.ft = d->ft;
@@ -746,6 +795,91 @@ template <class T> struct Ctx : CtxBase {
     chunks[chunk].pol[d->ft].push_back(s);
     if (chunks[chunk].pol[d->ft].size() > (size_t)kMaxPol)
       return fail(MEEPCU_EUNSUPPORTED, "more than %d susceptibilities per chunk and field type", kMaxPol);
+    return MEEPCU_OK;
+  }
+  int add_multilevel(int chunk, const meepcu_multilevel_desc *d) {
+    if (finalized) return fail(MEEPCU_ESTATE, "context already finalized");
+    if (chunk < 0 || chunk >= (int)chunks.size()) return fail(MEEPCU_EINVAL, "bad chunk id");
+    if (d->ft != MEEPCU_E_STUFF) return fail(MEEPCU_EUNSUPPORTED, "multilevel media are supported for E_stuff only");
+    if (cfg.dim == MEEPCU_Dcyl) return fail(MEEPCU_EUNSUPPORTED, "multilevel media in cylindrical coordinates");
+    if (d->L < 1 || d->L > kMlMaxL || d->T < 1 || d->T > kMlMaxT)
+      return fail(MEEPCU_EUNSUPPORTED, "multilevel medium: 1..%d levels, 1..%d transitions", kMlMaxL, kMlMaxT);
+    if (!d->Gamma || !d->GammaInv || !d->alpha || !d->omega || !d->gamma || !d->sigmat || !d->N)
+      return fail(MEEPCU_EINVAL, "multilevel medium: Gamma, GammaInv, alpha, omega, gamma, sigmat and N are required");
+    ChunkH &ch = chunks[chunk];
+    if (ch.pol[d->ft].size() + (size_t)d->T > (size_t)kMaxPol)
+      return fail(MEEPCU_EUNSUPPORTED, "more than %d polarisations per chunk and field type (a multilevel medium counts once per transition)", kMaxPol);
+    MlH M;
+    const int L = d->L, Tn = d->T;
+    M.L = L;
+    M.Tn = Tn;
+    M.Gamma.assign((const T *)d->Gamma, (const T *)d->Gamma + L * L);
+    M.GammaInv.assign((const T *)d->GammaInv, (const T *)d->GammaInv + L * L);
+    M.alpha.assign((const T *)d->alpha, (const T *)d->alpha + L * Tn);
+    M.omega.assign((const T *)d->omega, (const T *)d->omega + Tn);
+    M.gamma.assign((const T *)d->gamma, (const T *)d->gamma + Tn);
+    M.sigmat.assign((const T *)d->sigmat, (const T *)d->sigmat + 5 * Tn);
+    M.N = d->N;
+    for (int c = 0; c < 20; ++c) {
+      for (int k = 0; k < 5; ++k) M.sigma[c][k] = d->sigma[c][k];
+      for (int cmp = 0; cmp < 2; ++cmp) {
+        if ((d->P[c][cmp] != 0) != (d->P_prev[c][cmp] != 0)) return fail(MEEPCU_EINVAL, "P and P_prev must both be given");
+        if (d->P[c][cmp])
+          for (int t = 0; t < Tn; ++t) {
+            if (!d->P[c][cmp][t] || !d->P_prev[c][cmp][t]) return fail(MEEPCU_EINVAL, "multilevel medium: NULL transition array");
+            M.P[c][cmp].push_back(d->P[c][cmp][t]);
+            M.P_prev[c][cmp].push_back(d->P_prev[c][cmp][t]);
+          }
+        if (d->W_prev[c][cmp]) ch.w_prev[c][cmp] = d->W_prev[c][cmp];
+      }
+    }
+    for (int t = 0; t < Tn; ++t) {
+      SuscH s;
+      memset(&s, 0, sizeof s);
+      s.d.ft = d->ft;
+      s.ml = (int)ch.ml.size();
+      s.ml_t = t;
+      for (int c = 0; c < 20; ++c)
+        for (int cmp = 0; cmp < 2; ++cmp)
+          if (d->P[c][cmp]) {
+            s.d.P[c][cmp] = d->P[c][cmp][t];
+            s.d.P_prev[c][cmp] = d->P_prev[c][cmp][t];
+          }
+      ch.pol[d->ft].push_back(s);
+    }
+    ch.ml.push_back(M);
+    return MEEPCU_OK;
+  }
+  // noisy Lorentzian media: the owned points of every noisy polarisation component, in the reference's draw order
+  // (include/meepcu.h at meepcu_set_noise)
+  size_t noise_points(const ChunkH &ch, int ft) const {
+    size_t n = 0;
+    for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip) {
+      const meepcu_susceptibility_desc &sd = ch.pol[ft][ip].d;
+      if (ch.pol[ft][ip].gyro || ch.pol[ft][ip].ml >= 0 || sd.noise_amp == 0) continue;
+      for (int c = 0; c < 20; ++c)
+        for (int cmp = 0; cmp < 2; ++cmp)
+          if (sd.P[c][cmp] && comp_dir(c) < MEEPCU_R && sd.sigma[c][comp_dir(c)]) {
+            size_t m = 1;
+            for (int dd = 0; dd < 3; ++dd)
+              if (ch.g.has[dd]) m *= (size_t)ch.g.num[dd];
+            n += m;
+          }
+    }
+    return n;
+  }
+  size_t noise_count() {
+    size_t n = 0;
+    for (int ft = MEEPCU_H_STUFF; ft >= MEEPCU_E_STUFF; --ft)
+      for (size_t ic = 0; ic < chunks.size(); ++ic) n += noise_points(chunks[ic], ft);
+    return n;
+  }
+  int set_noise(int nsteps, size_t n_per_step, const double *g) {
+    if (n_per_step != noise_count())
+      return fail(MEEPCU_EINVAL, "meepcu_set_noise: %zu values per step given, the context needs %zu", n_per_step, noise_count());
+    if (nsteps < 0 || (nsteps > 0 && n_per_step > 0 && !g)) return fail(MEEPCU_EINVAL, "meepcu_set_noise: bad arguments");
+    noise_host.assign(g, g + (size_t)nsteps * n_per_step);
+    noise_steps = nsteps;
     return MEEPCU_OK;
   }
   int add_source(int chunk, const meepcu_source_desc *d) {
@@ -1472,6 +1606,13 @@ template <class T> struct Ctx : CtxBase {
             }
           }
         }
+      for (size_t im = 0; im < ch.ml.size(); ++im) { // multilevel atoms: sigma, the populations (host layout, not pitched)
+        for (int c = 0; c < 20; ++c)
+          for (int d = 0; d < 5; ++d) RC(reg(ch.ml[im].sigma[c][d], (int)ic, A_GRID, nh, nd, false));
+        RC(reg(ch.ml[im].N, (int)ic, A_VEC, nh * ch.ml[im].L, nh * ch.ml[im].L, true, false, MEEPCU_SYNC_POL));
+      }
+      for (int c = 0; c < 20; ++c)
+        for (int cmp = 0; cmp < 2; ++cmp) RC(reg(ch.w_prev[c][cmp], (int)ic, A_GRID, nh, nd, true, false, MEEPCU_SYNC_AUX));
       for (size_t id = 0; id < ch.dft.size(); ++id) {
         const size_t n = ch.dft[id].N * ch.dft[id].d.Nomega;
         RC(reg(ch.dft[id].d.dft, (int)ic, A_DFT, n, n, true, false, MEEPCU_SYNC_DFT));
@@ -1581,7 +1722,8 @@ template <class T> struct Ctx : CtxBase {
     std::vector<CylOrigin<T> > cyl_org[2];
     std::vector<FmpParams<T> > fmps[2];
     std::vector<DipPatch<T> > dips[2];
-    std::vector<Tile> polgen_tiles[2], polgyro_tiles[2];
+    std::vector<Tile> polgen_tiles[2], polgyro_tiles[2], mllev_tiles, mlpol_tiles;
+    std::vector<CopyItem<T> > wprev_items;
     std::vector<int> c3d_chunk, half_chunk; // owning chunk of every h_c3d / h_half entry
     // interior and PML tiles of a half in one grid (k_mix); fp64 PML tiles are vectorised only for that
     const bool mix_want = getenv("MEEPCU_MIX") ? atoi(getenv("MEEPCU_MIX")) != 0 : true;
@@ -1621,6 +1763,10 @@ template <class T> struct Ctx : CtxBase {
           for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip) {
             const meepcu_susceptibility_desc &sd = ch.pol[ft][ip].d;
             if (ch.pol[ft][ip].gyro) aniso_chunk_half.insert(std::make_pair((int)ic, half)); // -> k_pol_gyro
+            if (ch.pol[ft][ip].ml >= 0 && sd.P[ec][0]) { // -> k_ml_levels reads W around every centred point before
+              aniso_chunk_half.insert(std::make_pair((int)ic, half)); // zero_metal(E), and P halos every step
+              eager_p[half] = true;
+            }
             for (int cmp = 0; cmp < ncmp; ++cmp)
               if (sd.P[ec][cmp] && sd.sigma[ec][k] &&
                   ((sd.sigma[ec][d1] && ch.d.f[dir_comp(ft, d1)][cmp]) ||
@@ -2231,8 +2377,25 @@ template <class T> struct Ctx : CtxBase {
           }
         }
         aniso_now = false;
+        if (half == 1) {
+          for (size_t im = 0; im < ch.ml.size(); ++im) RC(build_ml(ch, ch.ml[im], ncmp, nc, mllev_tiles, mlpol_tiles));
+          for (int k = 0; k < 3; ++k) // W -> W_prev before the chunk's E update
+            for (int cmp = 0; cmp < ncmp; ++cmp) {
+              const int ec = dir_comp(MEEPCU_E_STUFF, k);
+              if (!ch.w_prev[ec][cmp] || !ch.d.f[ec][cmp]) continue;
+              CopyItem<T> it = {dev(ch.w_prev[ec][cmp]), dev(ch.d.f_w[ec][cmp] ? ch.d.f_w[ec][cmp] : ch.d.f[ec][cmp]),
+                                (long long)g.ntot_dev};
+              wprev_items.push_back(it);
+              wprev_max = std::max(wprev_max, it.n);
+              alg_bytes += 2LL * nc * (long long)sizeof(T);
+              alg_bytes_sv += 2LL * nc * (long long)sizeof(T);
+            }
+        }
       }
     }
+    n_wprev = (int)wprev_items.size();
+    RC(upload(wprev_items, &d_wprev));
+    RC(build_noise());
     tm_mark("parameter blocks + tiles");
     // ---- 5a. which halo exchanges run every step.  The schedule must be the SAME on every rank: a rank that
     // owns only PML chunks and a rank that owns nonlinear ones would otherwise post different ncclSend/ncclRecv
@@ -2246,6 +2409,7 @@ template <class T> struct Ctx : CtxBase {
         }
       }
     for (int half = 0; half < 2; ++half) aniso_half[half] = !polgen_tiles[half].empty() || !polgyro_tiles[half].empty();
+    if (!mllev_tiles.empty() || n_wprev) aniso_half[1] = true; // multilevel atoms: ordered path (W, P halos around the passes)
     virt_any = !virt_comps.empty();
     if (n_ranks > 1) {
       int hflag[9] = {general_half[0], general_half[1], eager_db[0], eager_db[1], eager_p[0], eager_p[1], aniso_half[0], aniso_half[1],
@@ -2420,6 +2584,12 @@ template <class T> struct Ctx : CtxBase {
     }
     RC(upload(h_polgen, &d_polgen));
     RC(upload(h_polgyro, &d_polgyro));
+    RC(upload(h_mllev, &d_mllev));
+    RC(upload(h_mlpol, &d_mlpol));
+    n_mllev_tiles = (int)mllev_tiles.size();
+    RC(upload(mllev_tiles, &d_mllev_tiles));
+    n_mlpol_tiles = (int)mlpol_tiles.size();
+    RC(upload(mlpol_tiles, &d_mlpol_tiles));
     for (int half = 0; half < 2; ++half) {
       n_polgen_tiles[half] = (int)polgen_tiles[half].size();
       RC(upload(polgen_tiles[half], &d_polgen_tiles[half]));
@@ -2446,7 +2616,7 @@ template <class T> struct Ctx : CtxBase {
     size_t dfts_total = 0;
     for (size_t ic = 0; ic < chunks.size(); ++ic) dfts_total += chunks[ic].dft.size();
     const bool defer_normal = cfg.dim == MEEPCU_D3 && !general_half[0] && !general_half[1] && h_polgen.empty() && h_polgyro.empty() &&
-                              dfts_total == 0 && !getenv("MEEPCU_NO_DEFER");
+                              h_mllev.empty() && dfts_total == 0 && !getenv("MEEPCU_NO_DEFER");
     std::map<const char *, int> comp_of; // host base of an f array -> component (direction is what matters)
     if (defer_normal)
       for (size_t ic = 0; ic < chunks.size(); ++ic)
@@ -2661,6 +2831,194 @@ template <class T> struct Ctx : CtxBase {
     }
     CU(cudaStreamSynchronize(st));
     finalized = true;
+    return MEEPCU_OK;
+  }
+
+  // parameter blocks + tiles of k_ml_levels / k_ml_pol for one multilevel medium of one chunk (constants evaluated in
+  // realnum exactly like multilevel-atom.cpp:244,265-270,297,332-336)
+  int build_ml(const ChunkH &ch, const MlH &M, int ncmp, long long nc, std::vector<Tile> &lev_tiles, std::vector<Tile> &pol_tiles) {
+    const Geom &g = ch.g;
+    const double pi = 3.141592653589793238462643383276;
+    const int L = M.L, Tn = M.Tn;
+    const T dt = (T)cfg.dt;
+    const T dt2 = 0.5 * dt;
+    std::vector<T> Gamma(M.Gamma.begin(), M.Gamma.end()), alpha(M.alpha.begin(), M.alpha.end()), omega(M.omega.begin(), M.omega.end()),
+        gamma(M.gamma.begin(), M.gamma.end()), sigmat(M.sigmat.begin(), M.sigmat.end());
+    long long hax[3];
+    for (int ax = 0; ax < 3; ++ax) hax[ax] = g.dir_of_axis[ax] < 0 ? 0 : g.hs[g.dir_of_axis[ax]];
+    T *Ndev = dev(M.N);
+    if (!Ndev) return fail(MEEPCU_EINVAL, "multilevel medium: N not registered");
+    const int plane = g.nax[1] * g.pitch;
+    const int seg = g.nax[0] <= 48 ? g.nax[0] : 32;
+    { // ---- the populations ----
+      MlLevelParams<T> Q;
+      memset(&Q, 0, sizeof Q);
+      Q.nA = g.nax[0]; Q.nB = g.nax[1]; Q.nC = g.nax[2]; Q.pitch = g.pitch;
+      Q.sA = (long long)g.pitch * g.nax[1]; Q.sB = g.pitch;
+      Q.hA = hax[0]; Q.hB = hax[1]; Q.hC = hax[2];
+      for (int ax = 0; ax < 3; ++ax) { // LOOP_OVER_VOL_OWNED(gv, Centered, i): num points per direction, from index 0
+        const int d = g.dir_of_axis[ax];
+        Q.hi[ax] = d < 0 ? 0 : g.num[d] - 1;
+      }
+      Q.L = L; Q.Tn = Tn;
+      Q.N = Ndev;
+      int ndot = 0;
+      for (int c = 0; c < 20; ++c) {
+        if (M.P[c][0].empty()) continue;
+        if (ndot == 3) return fail(MEEPCU_EINVAL, "bug in meep: too many polarization components");
+        long long o1 = 0, o2 = 0; // grid_volume::yee2cent_offsets (vec.cpp:333-344)
+        for (int dd = 0; dd < 3; ++dd)
+          if (g.has[dd] && !g.yee_shift(c, dd)) {
+            if (o1) o2 = g.ds[dd];
+            else o1 = g.ds[dd];
+          }
+        Q.o1[ndot] = o1; Q.o2[ndot] = o2;
+        for (int cmp = 0; cmp < ncmp; ++cmp) {
+          const void *wh = ch.d.f_w[c][cmp] ? ch.d.f_w[c][cmp] : ch.d.f[c][cmp]; // update_pols.cpp:43-44
+          Q.w[ndot][cmp] = dev(wh);
+          Q.wp[ndot][cmp] = dev(ch.w_prev[c][cmp]);
+          if (Q.w[ndot][cmp] && !Q.wp[ndot][cmp]) return fail(MEEPCU_EINVAL, "multilevel medium: W_prev missing");
+          if (cmp == 0 && !Q.w[ndot][0]) return fail(MEEPCU_EINVAL, "multilevel medium: W missing");
+          if (!M.P[c][cmp].empty())
+            for (int t = 0; t < Tn; ++t) {
+              Q.p[ndot][cmp][t] = dev(M.P[c][cmp][t]);
+              Q.pp[ndot][cmp][t] = dev(M.P_prev[c][cmp][t]);
+              if (!Q.p[ndot][cmp][t] || !Q.pp[ndot][cmp][t]) return fail(MEEPCU_EINVAL, "multilevel medium: P not registered");
+            }
+        }
+        ++ndot;
+      }
+      Q.ndot = ndot;
+      for (int l1 = 0; l1 < L; ++l1)
+        for (int l2 = 0; l2 < L; ++l2) {
+          Q.A[l1 * L + l2] = ((l1 == l2) - Gamma[l1 * L + l2] * dt2);
+          Q.Ginv[l1 * L + l2] = (T)M.GammaInv[l1 * L + l2];
+        }
+      for (int l = 0; l < L; ++l)
+        for (int t = 0; t < Tn; ++t) Q.alpha[l * Tn + t] = alpha[l * Tn + t];
+      for (int t = 0; t < Tn; ++t) Q.gperpdt[t] = gamma[t] * pi * dt;
+      const int qidx = (int)h_mllev.size();
+      h_mllev.push_back(Q);
+      for (int a0 = 0; a0 < g.nax[0]; a0 += seg)
+        for (int p0 = 0; p0 < plane; p0 += kThreads) {
+          Tile t = {qidx, a0, std::min(a0 + seg, g.nax[0]), p0};
+          lev_tiles.push_back(t);
+        }
+      const long long v = 2LL * L + (long long)ndot * ncmp * (2 + 2 * Tn); // R,W N; R W, W_prev, P, P_prev of every transition
+      alg_bytes += v * nc * (long long)sizeof(T);
+      kc_bytes[KC_POL_GENERAL] += v * nc * (long long)sizeof(T);
+      alg_bytes_sv += v * nc * (long long)sizeof(T);
+      kc_bytes_sv[KC_POL_GENERAL] += v * nc * (long long)sizeof(T);
+    }
+    // ---- each P is updated as a damped harmonic oscillator (:331-373) ----
+    for (int t = 0; t < Tn; ++t) {
+      const T omega2pi = 2 * pi * omega[t], g2pi = gamma[t] * 2 * pi, gperp = gamma[t] * pi;
+      const T omega0dtsqrCorrected = omega2pi * omega2pi * dt * dt + gperp * gperp * dt * dt;
+      const T gamma1inv = 1 / (1 + g2pi * dt2), gamma1 = (1 - g2pi * dt2);
+      const T dtsqr = dt * dt;
+      int lp = -1, lm = -1;
+      for (int l = 0; l < L; ++l) {
+        if (alpha[l * Tn + t] > 0) lp = l;
+        if (alpha[l * Tn + t] < 0) lm = l;
+      }
+      if (lp < 0 || lm < 0) return fail(MEEPCU_EINVAL, "invalid alpha array for transition %d", t);
+      for (int c = 0; c < 20; ++c)
+        for (int cmp = 0; cmp < ncmp; ++cmp) {
+          if (M.P[c][cmp].empty()) continue;
+          const int d0 = comp_dir(c);
+          if (d0 >= MEEPCU_R) continue;
+          const void *wh = ch.d.f_w[c][cmp] ? ch.d.f_w[c][cmp] : ch.d.f[c][cmp];
+          if (!wh || !M.sigma[c][d0]) continue; // :352
+          const int d1 = (d0 + 1) % 3, d2 = (d0 + 2) % 3;
+          const int c1 = dir_comp(MEEPCU_E_STUFF, d1), c2 = dir_comp(MEEPCU_E_STUFF, d2);
+          const bool w1 = g.has_field(c1) && (ch.d.f_w[c1][cmp] || ch.d.f[c1][cmp]);
+          const bool w2 = g.has_field(c2) && (ch.d.f_w[c2][cmp] || ch.d.f[c2][cmp]);
+          if ((w1 && M.sigma[c][d1]) || (w2 && M.sigma[c][d2]))
+            return fail(MEEPCU_EUNSUPPORTED, "nondiagonal saturable gain is not yet supported"); // the reference's words (:362)
+          MlPolParams<T> Q;
+          memset(&Q, 0, sizeof Q);
+          Q.nA = g.nax[0]; Q.nB = g.nax[1]; Q.nC = g.nax[2]; Q.pitch = g.pitch;
+          Q.sA = (long long)g.pitch * g.nax[1]; Q.sB = g.pitch;
+          Q.hA = hax[0]; Q.hB = hax[1]; Q.hC = hax[2];
+          for (int ax = 0; ax < 3; ++ax) {
+            const int d = g.dir_of_axis[ax];
+            Q.lo[ax] = d < 0 ? 0 : 1 - g.yee_shift(c, d);
+            Q.hi[ax] = d < 0 ? 0 : g.num[d] - g.yee_shift(c, d);
+          }
+          Q.L = L; Q.lp = lp; Q.lm = lm;
+          Q.p = dev(M.P[c][cmp][t]); Q.pp = dev(M.P_prev[c][cmp][t]);
+          Q.s = dev(M.sigma[c][d0]); Q.w = dev(wh); Q.N = Ndev;
+          if (!Q.p || !Q.pp || !Q.s || !Q.w) return fail(MEEPCU_EINVAL, "multilevel medium: array not registered");
+          long long oa = 0, ob = 0; // cent2yee_offsets = -yee2cent_offsets (vec.cpp:347-351), in elements of N
+          for (int dd = 0; dd < 3; ++dd)
+            if (g.has[dd] && !g.yee_shift(c, dd)) {
+              if (oa) ob = g.hs[dd];
+              else oa = g.hs[dd];
+            }
+          Q.oa = -oa * L; Q.ob = -ob * L;
+          Q.gamma1inv = gamma1inv; Q.gamma1 = gamma1; Q.two_minus = (2 - omega0dtsqrCorrected); Q.dtsqr = dtsqr;
+          Q.st = sigmat[5 * t + d0];
+          const int qidx = (int)h_mlpol.size();
+          h_mlpol.push_back(Q);
+          for (int a0 = 0; a0 < g.nax[0]; a0 += seg)
+            for (int p0 = 0; p0 < plane; p0 += kThreads) {
+              Tile tl = {qidx, a0, std::min(a0 + seg, g.nax[0]), p0};
+              pol_tiles.push_back(tl);
+            }
+          const long long v = 5 + 2LL * L; // R,W p, R,W pp, R sigma (+ the levels around the point; W counted with E)
+          alg_bytes += v * nc * (long long)sizeof(T);
+          kc_bytes[KC_POL_GENERAL] += v * nc * (long long)sizeof(T);
+          alg_bytes_sv += v * nc * (long long)sizeof(T);
+          kc_bytes_sv[KC_POL_GENERAL] += v * nc * (long long)sizeof(T);
+        }
+    }
+    return MEEPCU_OK;
+  }
+
+  // segments of k_pol_noise, per half, in the reference's draw order (susceptibility.cpp:327-336)
+  int build_noise() {
+    const double pi = 3.141592653589793238462643383276;
+    const T dt = (T)cfg.dt;
+    for (int half = 0; half < 2; ++half) {
+      const int ft = half ? MEEPCU_E_STUFF : MEEPCU_H_STUFF;
+      std::vector<NoiseSeg<T> > segs;
+      long long total = 0;
+      for (size_t ic = 0; ic < chunks.size(); ++ic) {
+        const ChunkH &ch = chunks[ic];
+        const Geom &g = ch.g;
+        for (size_t ip = 0; ip < ch.pol[ft].size(); ++ip) {
+          const meepcu_susceptibility_desc &sd = ch.pol[ft][ip].d;
+          if (ch.pol[ft][ip].gyro || ch.pol[ft][ip].ml >= 0 || sd.noise_amp == 0) continue;
+          const T noise_amp = (T)sd.noise_amp, omega_0 = (T)sd.omega_0, gamma = (T)sd.gamma;
+          const T g2pi = gamma * 2 * pi;
+          const T w2pi = omega_0 * 2 * pi;
+          const T amp = w2pi * noise_amp * std::sqrt(g2pi) * dt * dt / (1 + g2pi * dt / 2); // :325
+          for (int c = 0; c < 20; ++c)
+            for (int cmp = 0; cmp < 2; ++cmp) {
+              if (!sd.P[c][cmp] || comp_dir(c) >= MEEPCU_R || !sd.sigma[c][comp_dir(c)]) continue;
+              NoiseSeg<T> S;
+              memset(&S, 0, sizeof S);
+              S.p = dev(sd.P[c][cmp]);
+              S.s = dev(sd.sigma[c][comp_dir(c)]);
+              if (!S.p || !S.s) return fail(MEEPCU_EINVAL, "noisy medium: array not registered");
+              S.amp = amp;
+              S.first = total;
+              long long m = 1;
+              for (int dd = 0; dd < 3; ++dd) {
+                S.n[dd] = g.has[dd] ? g.num[dd] : 1;
+                S.ds[dd] = g.has[dd] ? g.ds[dd] : 0;
+                if (g.has[dd]) S.base += (long long)(1 - g.yee_shift(c, dd)) * g.ds[dd]; // little_owned_corner(c)
+                m *= S.n[dd];
+              }
+              total += m;
+              segs.push_back(S);
+            }
+        }
+      }
+      n_noise_seg[half] = (int)segs.size();
+      noise_total[half] = total;
+      RC(upload(segs, &d_noise_seg[half]));
+    }
     return MEEPCU_OK;
   }
 
@@ -2992,6 +3350,11 @@ template <class T> struct Ctx : CtxBase {
       k_cyl_rderiv<T><<<dim3(4, (unsigned)std::min(n_cyl_rd[half], 1024)), kThreads, 0, st>>>(d_cyl_rd[half], n_cyl_rd[half]);
       launches++;
     }
+    if (half == 1 && n_wprev && !in_mag_sync) { // f_w_prev = W of this time step, before the E update (update_eh.cpp:221-226)
+      dim3 grid((unsigned)std::min<long long>((wprev_max + kThreads * 4 - 1) / (kThreads * 4), 148 * 4), (unsigned)n_wprev);
+      k_copy_arrays<T><<<grid, kThreads, 0, st>>>(d_wprev);
+      launches++;
+    }
     if (overlap_half[half] && !profiling) {
       // boundary tiles -> [halo exchange on st_comm  ||  interior tiles + local halo copies] -> join.
       // The exchange writes only not-owned points of E/H (W), which no kernel of this half reads.
@@ -3065,6 +3428,23 @@ template <class T> struct Ctx : CtxBase {
       RC(prof_end());
       launches++;
     }
+    if (half == 1 && n_mllev_tiles && !in_mag_sync) { // multilevel atoms: populations, then every transition's P
+      RC(prof_begin(KC_POL_GENERAL));
+      k_ml_levels<T><<<n_mllev_tiles, kThreads, 0, st>>>(d_mllev, d_mllev_tiles);
+      launches++;
+      if (n_mlpol_tiles) {
+        k_ml_pol<T><<<n_mlpol_tiles, kThreads, 0, st>>>(d_mlpol, d_mlpol_tiles);
+        launches++;
+      }
+      RC(prof_end());
+    }
+    if (n_noise_seg[half] && !in_mag_sync) { // noisy Lorentzian media: the caller's Gaussians, after the Lorentzian update
+      if (!cur_noise) return fail(MEEPCU_ESTATE, "noisy medium stepped without noise");
+      const int grid = (int)std::min<long long>((noise_total[half] + kThreads - 1) / kThreads, 148 * 8);
+      k_pol_noise<T><<<grid, kThreads, 0, st>>>(d_noise_seg[half], n_noise_seg[half], noise_total[half],
+                                                cur_noise + (half ? noise_total[0] : 0));
+      launches++;
+    }
     if (n_zero_late[half]) {                 // zero_metal(E) of step_boundaries(E_stuff), step.cpp:245-246
       k_zero<T><<<(int)std::min<long long>((n_zero_late[half] + kThreads - 1) / kThreads, 148 * 8), kThreads, 0, st>>>(
           d_zero_late[half], n_zero_late[half]);
@@ -3115,6 +3495,14 @@ template <class T> struct Ctx : CtxBase {
       RC(ring_put(tab.data(), tab.size() * sizeof(double), &p_smp));
       last_row.assign(tab.end() - ns, tab.end());
     }
+    const size_t npst = (size_t)(noise_total[0] + noise_total[1]);
+    char *p_noise = 0;
+    if (npst) { // noisy Lorentzian media: the unit Gaussians meepcu_set_noise left for exactly these steps
+      if (noise_steps != nsteps)
+        return fail(MEEPCU_ESTATE, "noisy Lorentzian media: meepcu_set_noise must provide the %d steps of this call (%d waiting)", nsteps, noise_steps);
+      RC(ring_put(noise_host.data(), noise_host.size() * sizeof(double), &p_noise));
+      noise_steps = 0;
+    }
     const size_t ndft = h_dft.size();
     if (ndft) {
       std::vector<T> ph((size_t)2 * phase_row * nsteps);
@@ -3151,6 +3539,7 @@ template <class T> struct Ctx : CtxBase {
       const double *sm = (const double *)p_smp + (size_t)(s + 1) * ns;
       cur_prev = (const double *)p_smp + (size_t)s * ns;
       cur_vmode = (!virt_comps.empty() && e_virtual) ? 1 : 0;
+      cur_noise = npst ? (const double *)p_noise + (size_t)s * npst : 0;
       RC(launch_half(0, sm));
       RC(launch_half(1, sm));
       e_virtual = true; // the D/E half of a virtual chunk has not stored E: from now on it is read through D
@@ -3726,6 +4115,21 @@ int meepcu_add_gyrotropic(meepcu_ctx *ctx, int chunk, const meepcu_gyrotropic_de
   CHECK_CTX;
   if (!d) return fail(MEEPCU_EINVAL, "null descriptor");
   return ctx->impl->add_gyro(chunk, d);
+}
+int meepcu_add_multilevel(meepcu_ctx *ctx, int chunk, const meepcu_multilevel_desc *d) {
+  CHECK_CTX;
+  if (!d) return fail(MEEPCU_EINVAL, "null descriptor");
+  return ctx->impl->add_multilevel(chunk, d);
+}
+int meepcu_get_noise_count(meepcu_ctx *ctx, size_t *n) {
+  CHECK_CTX;
+  if (!n) return fail(MEEPCU_EINVAL, "null argument");
+  *n = ctx->impl->noise_count();
+  return MEEPCU_OK;
+}
+int meepcu_set_noise(meepcu_ctx *ctx, int nsteps, size_t n_per_step, const double *g) {
+  CHECK_CTX;
+  return ctx->impl->set_noise(nsteps, n_per_step, g);
 }
 int meepcu_add_source(meepcu_ctx *ctx, int chunk, const meepcu_source_desc *d) {
   CHECK_CTX;

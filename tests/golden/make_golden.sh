@@ -49,6 +49,10 @@ for fl in fp64 fp32; do
   gen $fl magdrude2d:24 40 2
   gen $fl dft3d:12 40 2
   gen $fl beta2d_cplx 40 2
+  gen $fl mlatom3d:10 40 2
+  gen $fl mlatom2d:24 40 2
+  gen $fl noisy3d:10 24 2
+  gen $fl noisy2d:16 24 2
   gen $fl cylpml:14:1 40 0
   gen $fl cyllor:14:0 40 0
 done

@@ -84,7 +84,7 @@ def test_product_package_does_not_reference_the_oracle():
 
 def test_header_is_plain_c_and_every_symbol_has_c_linkage(tmp_path):
     """include/meepcu.h compiled by a C99 compiler (-pedantic -Werror); the C client dlopen()s libmeepcuda.so and
-    the oracle and finds all 35 entry points; struct sizes agree with the ctypes mirror"""
+    the oracle and finds all 38 entry points; struct sizes agree with the ctypes mirror"""
     import json, subprocess
     exe = str(tmp_path / "abi_c_client")
     subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
@@ -93,7 +93,10 @@ def test_header_is_plain_c_and_every_symbol_has_c_linkage(tmp_path):
         r = subprocess.run([exe, lib], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         d = json.loads(r.stdout)
-        assert d["missing"] == 0 and d["symbols"] == len(A.SYMBOLS) == 35
+        assert d["missing"] == 0 and d["symbols"] == len(A.SYMBOLS) == 38
         assert d["abi"] == d["header_abi"] == A.ABI_VERSION
         assert d["sizeof_config"] == C.sizeof(A.Config) and d["sizeof_chunk_desc"] == C.sizeof(A.ChunkDesc)
         assert d["sizeof_gyrotropic_desc"] == C.sizeof(A.GyrotropicDesc)
+        # noise_amp took the place of two reserved ints: the size of the descriptor did not change
+        assert d["sizeof_susceptibility_desc"] == C.sizeof(A.SusceptibilityDesc) == 24 + 8 + 8 * (100 + 40 + 40) + 32
+        assert d["sizeof_multilevel_desc"] == C.sizeof(A.MultilevelDesc)

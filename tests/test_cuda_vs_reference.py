@@ -32,6 +32,12 @@ CASES = [("fp64", "vac3d:48", 60, 3, 1e-12), ("fp32", "vac3d:48", 60, 3, 1e-5),
          ("fp32", "cylpml:40:1", 200, 0, 1e-5), ("fp64", "cylpml:40:3", 200, 0, 1e-12), ("fp64", "cylpmlnz:40:3", 200, 0, 1e-12),
          ("fp64", "cylcond:40:1", 200, 2, 1e-12), ("fp32", "cylcond:40:2", 200, 0, 1e-5), ("fp64", "cyllor:40:1", 200, 2, 1e-12),
          ("fp32", "cyllor:40:0", 200, 0, 1e-5), ("fp64", "cyllor:36:2", 200, 0, 1e-12), ("fp64", "cylpml:600:1", 60, 0, 1e-12),
+         # multilevel-atom gain media (k_ml_levels, k_ml_pol, W_prev copies) and noisy Lorentzian media (k_pol_noise fed by
+         # the reference's own generator)
+         ("fp64", "mlatom3d:24", 100, 2, 1e-12), ("fp32", "mlatom3d:24", 100, 2, 1e-5), ("fp64", "mlatom2d:60", 200, 2, 1e-12),
+         ("fp32", "mlatom2d:60", 200, 2, 1e-5), ("fp64", "mlatom3d:40:0.6", 60, 0, 1e-12),
+         ("fp64", "noisy3d:24", 100, 2, 1e-12), ("fp32", "noisy3d:24", 100, 2, 1e-5), ("fp64", "noisy2d:60", 200, 2, 1e-12),
+         ("fp32", "noisy2d:60", 200, 2, 1e-5),
          ("fp64_pade", "kerr3d:20", 40, 2, 1e-12), ("fp64_pade", "kr_per3d_rods", 100, 0, 1e-12)]
 
 
