@@ -101,6 +101,24 @@ class lorentzian_susceptibility:  # src/meep.hpp:246-278
         self.omega_0, self.gamma, self.drude = omega_0, gamma, no_omega_0_denominator
 
 
+class noisy_lorentzian_susceptibility(lorentzian_susceptibility):  # src/meep.hpp:282-299
+    def __init__(self, noise_amp, omega_0, gamma, no_omega_0_denominator=False):
+        super().__init__(omega_0, gamma, no_omega_0_denominator)
+        self.noise_amp = noise_amp
+
+
+class multilevel_susceptibility:  # src/meep.hpp:340-386, src/multilevel-atom.cpp:28-47
+    """L levels, T radiative transitions: Gamma[L*L] relaxation rates, N0[L] initial populations, alpha[L*T]
+    transition coefficients, omega[T], gamma[T], sigmat[5*T] (per-transition sigma factors by direction)."""
+
+    def __init__(self, L, T, Gamma, N0, alpha, omega, gamma, sigmat):
+        self.L, self.T = int(L), int(T)
+        self.Gamma, self.N0, self.alpha = np.asarray(Gamma, float), np.asarray(N0, float), np.asarray(alpha, float)
+        self.omega, self.gamma, self.sigmat = np.asarray(omega, float), np.asarray(gamma, float), np.asarray(sigmat, float)
+        assert self.Gamma.size == L * L and self.N0.size == L and self.alpha.size == L * T
+        assert self.omega.size == T and self.gamma.size == T and self.sigmat.size == 5 * T
+
+
 class gaussian_src_time:
     """src/sources.cpp:72-108 (4-argument constructor), integrated by default"""
 
@@ -318,7 +336,8 @@ class fields_chunk:
     def __init__(self, sc, is_real):
         self.s, self.gv = sc, sc.gv
         self.f, self.f_u, self.f_w, self.f_cond, self.f_bfast = {}, {}, {}, {}, {}
-        self.pol_data = []   # per susceptibility: {"P": {(c,cmp): arr}, "P_prev": {...}}
+        self.f_w_prev = {}   # fields_chunk::f_w_prev (update_eh.cpp:221-226): only where a multilevel medium needs it
+        self.pol_data = []   # per susceptibility: {"P": {(c,cmp): arr}, "P_prev": {...}}; multilevel: + "ml" (below)
         self.sources = []    # dicts
         self.dfts = []
 
@@ -419,6 +438,25 @@ class fields:
                     else:                    # update_eh.cpp:199-216
                         if sc.sigsize[d] > 1: fc.f_w[(c, cmp)] = zeros(n, rt)
             for (sus, ft, arrs) in sc.pols:
+                if isinstance(sus, multilevel_susceptibility):
+                    # multilevel_data (multilevel-atom.cpp:118-181): GammaInv = inv(1 + Gamma dt/2), P / P_prev per
+                    # transition, the populations N[i * L + level] = N0 everywhere; and W_prev for every E component
+                    Pt = [{(c, cmp): zeros(n, rt) for (c, d) in arrs for cmp in range(ncmp)} for _ in range(sus.T)]
+                    Ppt = [{(c, cmp): zeros(n, rt) for (c, d) in arrs for cmp in range(ncmp)} for _ in range(sus.T)]
+                    ml = {"P": Pt, "P_prev": Ppt}
+                    if fc.mine:
+                        L = sus.L
+                        G = (np.eye(L) + sus.Gamma.reshape(L, L) * float(np.asarray(self.dt, rt)) / 2).astype(rt)
+                        ml["GammaInv"] = np.ascontiguousarray(np.linalg.inv(G.astype(np.float64)).astype(rt)).reshape(-1)
+                        ml["N"] = np.ascontiguousarray(np.tile(sus.N0.astype(rt), n))
+                        ml["small"] = {k: np.ascontiguousarray(getattr(sus, k).astype(rt)).reshape(-1)
+                                       for k in ("Gamma", "alpha", "omega", "gamma", "sigmat")}
+                        for c in comps:
+                            if is_electric(c):
+                                for cmp in range(ncmp):
+                                    if (c, cmp) not in fc.f_w_prev: fc.f_w_prev[(c, cmp)] = zeros(n, rt)
+                    fc.pol_data.append({"P": Pt[0], "P_prev": Ppt[0], "ml": ml})
+                    continue
                 P, Pp = {}, {}
                 for (c, d) in arrs:
                     for cmp in range(ncmp):
@@ -582,10 +620,14 @@ class fields:
                             ftp = PE_stuff if is_electric(c) else PH_stuff
                             for ip in range(len(fc.pol_data)):
                                 if ip >= len(fj.pol_data): break
-                                for cmp in range(ncmp):
-                                    if (c, cmp) in fc.pol_data[ip]["P"] and (c, cmp) in fj.pol_data[ip]["P"] and (self.is_real or np.all(p == 1.0)):
-                                        add(ftp, A.CONNECT_COPY, fc.pol_data[ip]["P"][(c, cmp)].ctypes.data + n * item,
-                                            fj.pol_data[ip]["P"][(c, cmp)].ctypes.data + m * item)
+                                # (a multilevel medium: one P per transition, cinternal_notowned_ptr of multilevel-atom.cpp:228-238)
+                                pi_ = fc.pol_data[ip]["ml"]["P"] if "ml" in fc.pol_data[ip] else [fc.pol_data[ip]["P"]]
+                                pj_ = fj.pol_data[ip]["ml"]["P"] if "ml" in fj.pol_data[ip] else [fj.pol_data[ip]["P"]]
+                                for Pi, Pj in zip(pi_, pj_):
+                                    for cmp in range(ncmp):
+                                        if (c, cmp) in Pi and (c, cmp) in Pj and (self.is_real or np.all(p == 1.0)):
+                                            add(ftp, A.CONNECT_COPY, Pi[(c, cmp)].ctypes.data + n * item,
+                                                Pj[(c, cmp)].ctypes.data + m * item)
         self._rsend, self._rrecv = rsend, rrecv
         return conns, metals
 
@@ -655,9 +697,28 @@ class fields:
             b.check(b.add_chunk(ctx, C.byref(d), C.byref(cid)))
             assert cid.value == i
             for ip, (sus, ft, arrs) in enumerate(sc.pols):
+                if isinstance(sus, multilevel_susceptibility):
+                    ml = fc.pol_data[ip]["ml"]
+                    md = A.MultilevelDesc()
+                    md.ft, md.L, md.T = ft, sus.L, sus.T
+                    md.Gamma, md.GammaInv = self._ptr(ml["small"]["Gamma"]), self._ptr(ml["GammaInv"])
+                    md.alpha, md.omega = self._ptr(ml["small"]["alpha"]), self._ptr(ml["small"]["omega"])
+                    md.gamma, md.sigmat = self._ptr(ml["small"]["gamma"]), self._ptr(ml["small"]["sigmat"])
+                    md.N = self._ptr(ml["N"])
+                    for (c, dd), arr in arrs.items(): md.sigma[c][dd] = self._ptr(arr)
+                    for name in ("P", "P_prev"):
+                        tab = getattr(md, name)
+                        for (c, cmp) in ml[name][0]:
+                            ptrs = (A.vp * sus.T)(*[ml[name][t][(c, cmp)].ctypes.data for t in range(sus.T)])
+                            self._keep.append(ptrs)
+                            tab[c][cmp] = C.cast(ptrs, A.vp)
+                    for (c, cmp), arr in fc.f_w_prev.items(): md.W_prev[c][cmp] = self._ptr(arr)
+                    b.check(b.add_multilevel(ctx, i, C.byref(md)))
+                    continue
                 sd = A.SusceptibilityDesc()
                 sd.ft, sd.omega_0, sd.gamma = ft, sus.omega_0, sus.gamma
                 sd.no_omega_0_denominator = int(sus.drude)
+                sd.noise_amp = float(getattr(sus, "noise_amp", 0.0))
                 for (c, dd), arr in arrs.items(): sd.sigma[c][dd] = self._ptr(arr)
                 for (c, cmp), arr in fc.pol_data[ip]["P"].items(): sd.P[c][cmp] = self._ptr(arr)
                 for (c, cmp), arr in fc.pol_data[ip]["P_prev"].items(): sd.P_prev[c][cmp] = self._ptr(arr)
@@ -689,6 +750,35 @@ class fields:
             b.check(b.add_remote_recv(ctx, ft, kind, peer, pp.size, pp.ctypes.data,
                                       php.ctypes.data if php is not None else None))
         b.check(b.finalize(ctx))
+        nn = C.c_size_t(0)
+        b.check(b.get_noise_count(ctx, C.byref(nn)))
+        self.n_noise = nn.value
+
+    def _noise(self, nsteps):
+        """unit Gaussians for noisy Lorentzian media in the order include/meepcu.h states: per step, update_pols(H_stuff)
+        then update_pols(E_stuff); in each, this rank's chunks in index order, their susceptibilities, components, cmp,
+        owned points.  Drawn per (time step, field type, GLOBAL chunk), so that a point sees the same value whatever
+        the rank decomposition (the reference's MPI ranks each have their own generator: there the decomposition
+        changes the noise; here it is the one property the N-rank == 1-rank tests need)."""
+        ncmp = 1 if self.is_real else 2
+        out = []
+        for s in range(nsteps):
+            for ft in (H_stuff, E_stuff):
+                for gi_, fc in enumerate(self.chunks):
+                    if not fc.mine: continue
+                    cnt = 0
+                    for ip, (sus, sft, arrs) in enumerate(fc.s.pols):
+                        if sft != ft or not getattr(sus, "noise_amp", 0.0) or isinstance(sus, multilevel_susceptibility): continue
+                        for c in range(20):
+                            for cmp in range(ncmp):
+                                if (c, cmp) in fc.pol_data[ip]["P"] and (c, comp_dir(c)) in arrs:
+                                    cnt += int(np.prod([fc.gv.num[d] for d in fc.gv.dirs]))
+                    if cnt:
+                        rng = np.random.default_rng([getattr(self, "noise_seed", 1234), self.t + s, ft, gi_])
+                        out.append(rng.standard_normal(cnt))
+        g = np.ascontiguousarray(np.concatenate(out)) if out else np.zeros(0)
+        assert g.size == nsteps * self.n_noise, (g.size, nsteps, self.n_noise)
+        return g
 
     def _add_dfts(self):
         b, ctx = self.b, self.ctx
@@ -756,6 +846,9 @@ class fields:
             self.synchronized_magnetic_fields = 1
             self.restore_magnetic_fields()
         buf, nsrc = samples if samples is not None else self.samples(n)
+        if self.n_noise:
+            g = self._noise(n)
+            self.b.check(self.b.set_noise(self.ctx, n, self.n_noise, g.ctypes.data))
         self.b.check(self.b.step(self.ctx, n, nsrc, buf if nsrc else None))
         self.t += n
         if saved:
@@ -914,6 +1007,11 @@ class fields:
                     seen.add(id(arr)); n += arr.nbytes
             for pd in fc.pol_data:
                 for arr in list(pd["P"].values()) + list(pd["P_prev"].values()): n += arr.nbytes
+                if "ml" in pd:
+                    n += pd["ml"]["N"].nbytes
+                    for t in range(1, len(pd["ml"]["P"])):
+                        for arr in list(pd["ml"]["P"][t].values()) + list(pd["ml"]["P_prev"][t].values()): n += arr.nbytes
+            for arr in fc.f_w_prev.values(): n += arr.nbytes
             for dft in fc.dfts: n += dft["dft"].nbytes
             if not mutable_only:  # what meepcu_sync_from_host uploads on top: materials, sigma, UPML profiles
                 sc = fc.s
@@ -941,10 +1039,18 @@ class fields:
                     if id(arr) in seen: continue  # H aliasing B
                     seen.add(id(arr))
                     out.append(("chunk%d.%s[%d][%d]" % (gi_, kind, c, cmp), arr))
+            for (c, cmp) in sorted(fc.f_w_prev):
+                out.append(("chunk%d.f_w_prev[%d][%d]" % (gi_, c, cmp), fc.f_w_prev[(c, cmp)]))
             for ip, pd in enumerate(fc.pol_data):
                 for kind in ("P", "P_prev"):
                     for (c, cmp) in sorted(pd[kind]):
                         out.append(("chunk%d.pol%d.%s[%d][%d]" % (gi_, ip, kind, c, cmp), pd[kind][(c, cmp)]))
+                if "ml" in pd:
+                    out.append(("chunk%d.pol%d.N" % (gi_, ip), pd["ml"]["N"]))
+                    for t in range(1, len(pd["ml"]["P"])):
+                        for kind in ("P", "P_prev"):
+                            for (c, cmp) in sorted(pd["ml"][kind][t]):
+                                out.append(("chunk%d.pol%d.%s[%d][%d][t%d]" % (gi_, ip, kind, c, cmp, t), pd["ml"][kind][t][(c, cmp)]))
             for k, d in enumerate(fc.dfts):
                 out.append(("chunk%d.dft%d[%d]" % (gi_, k, d["c"]), d["dft"]))
         return out

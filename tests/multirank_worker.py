@@ -69,6 +69,20 @@ def build(backend, rank, nranks, comm_id, case, rt, nslabs):
         inside = lambda x, y, z: ((np.abs(y - c[1]) < 0.5) & (np.abs(z - c[2]) < 0.5) & (x > 0.8) & (x < 2 * c[0] - 0.8)) * 1.0  # noqa: E731
         s = H.structure(gv, lambda x, y, z: 1.0 + 2.0 * inside(x, y, z), pml=0.4, realnum=rt, split=split)
         s.add_susceptibility(inside, H.E_stuff, H.lorentzian_susceptibility(0.35, 0.02))
+    elif base in ("mlatom", "noisy"):  # a gain / noisy block that straddles every cut, PML all around
+        inside = lambda x, y, z: ((np.abs(y - c[1]) < 0.5) & (np.abs(z - c[2]) < 0.5) & (x > 0.8) & (x < 2 * c[0] - 0.8)) * 1.0  # noqa: E731
+        s = H.structure(gv, lambda x, y, z: 1.0 + 1.25 * inside(x, y, z), pml=0.4, realnum=rt, split=split)
+        if base == "mlatom":  # three levels, two radiative transitions (tests' mlatom2d medium)
+            fa, fb = 0.3, 0.22
+            al = np.zeros(6)
+            al[0 * 2 + 0], al[1 * 2 + 0] = -1.0 / (2 * np.pi * fa), +1.0 / (2 * np.pi * fa)
+            al[1 * 2 + 1], al[2 * 2 + 1] = -1.0 / (2 * np.pi * fb), +1.0 / (2 * np.pi * fb)
+            s.add_susceptibility(inside, H.E_stuff, H.multilevel_susceptibility(
+                3, 2, [0.04, -0.03, 0, -0.04, 0.05, -0.01, 0, -0.02, 0.01], [0.9, 0.3, 0.1], al, [fa, fb], [0.05, 0.08],
+                [1.0, 1.2, 0.8, 0, 0, 0.7, 0.9, 1.1, 0, 0]))
+            s.add_susceptibility(inside, H.E_stuff, H.lorentzian_susceptibility(0.35, 0.02))
+        else:
+            s.add_susceptibility(inside, H.E_stuff, H.noisy_lorentzian_susceptibility(0.05, 0.35, 0.05))
     else:  # per / bloch: periodic in x (the wrap connection also crosses ranks), metallic elsewhere
         s = H.structure(gv, eps, pml=0.0, realnum=rt, split=split)
     cr = [rank_of(sc) for sc in s.chunks] if rank_of else None

@@ -25,7 +25,8 @@ def run(lib, case, steps, nl=0, syncmag=0, addsrc=0):
         return json.load(open(tf.name))
 
 
-@pytest.mark.parametrize("case", ["vac3d:32", "lorentz3d:16", "wvg2d", "nrslab3d:14", "kr_xper_ypml3d", "gyro3d:12", "dft3d:12"])
+@pytest.mark.parametrize("case", ["vac3d:32", "lorentz3d:16", "wvg2d", "nrslab3d:14", "kr_xper_ypml3d", "gyro3d:12", "dft3d:12",
+                                  "mlatom3d:12", "noisy2d:20"])
 def test_patched_reference_steps_through_the_abi(case):
     d = run(ORACLE_LIB, case, 40)
     assert d["attached"] == 1 and d["t_ref"] == d["t_abi"]
@@ -47,7 +48,8 @@ def test_patched_reference_steps_through_the_abi(case):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case,tol", [("vac3d:48", 1e-12), ("lorentz3d:32", 1e-12), ("nrslab3d:20", 1e-12), ("aniso3d:24", 1e-12)])
+@pytest.mark.parametrize("case,tol", [("vac3d:48", 1e-12), ("lorentz3d:32", 1e-12), ("nrslab3d:20", 1e-12), ("aniso3d:24", 1e-12),
+                                      ("mlatom3d:20", 1e-12), ("noisy3d:20", 1e-12)])
 def test_patched_reference_steps_on_the_gpu(case, tol):
     d = run(CUDA_LIB, case, 60)
     assert d["attached"] == 1 and d["t_ref"] == d["t_abi"]

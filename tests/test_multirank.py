@@ -53,7 +53,7 @@ def rel_l2(ref, got):
     return (num / den) ** 0.5
 
 
-@pytest.mark.parametrize("case", ["pml", "per", "beta2d", "lorentz", "bloch"])
+@pytest.mark.parametrize("case", ["pml", "per", "beta2d", "lorentz", "bloch", "mlatom", "noisy"])
 def test_two_ranks_equal_one_rank_oracle(case):
     one = run("oracle", case + "_presplit", "f64", 40, 1, 29611)
     two = run("oracle", case, "f64", 40, 2, 29612)
@@ -94,7 +94,8 @@ def gpus():
                                             ("pml", "f64", {"MEEPCU_NO_OVERLAP": "1"}),
                                             ("lorentz", "f64", None), ("lorentz", "f64", SHORT_TILES), ("bloch", "f64", None),
                                             ("bloch", "f32", SHORT_TILES), ("beta2d", "f64", None),
-                                            ("hetero_nr", "f64", None), ("hetero_dft", "f64", None)])
+                                            ("hetero_nr", "f64", None), ("hetero_dft", "f64", None),
+                                            ("mlatom", "f64", None), ("mlatom", "f32", SHORT_TILES), ("noisy", "f64", None)])
 def test_two_gpus_equal_oracle(case, dtype, env):
     if gpus() < 2:
         pytest.skip("needs 2 GPUs")
@@ -104,7 +105,8 @@ def test_two_gpus_equal_oracle(case, dtype, env):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case,env", [("pml", None), ("pml", SHORT_TILES), ("bloch", None), ("lorentz", SHORT_TILES)])
+@pytest.mark.parametrize("case,env", [("pml", None), ("pml", SHORT_TILES), ("bloch", None), ("lorentz", SHORT_TILES),
+                                      ("mlatom", None), ("noisy", None)])
 def test_two_gpus_equal_one_gpu_bitwise(case, env):
     """the N-GPU result must be the 1-GPU result bit for bit (same kernels, same arithmetic per point)"""
     if gpus() < 2:
