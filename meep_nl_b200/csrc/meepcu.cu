@@ -459,8 +459,28 @@ template <class T> struct Ctx : CtxBase {
   // time step (src/step.cpp:35, python/simulation.py:2831-2834) and the launches of step n+1 must be queued
   // while step n runs.
   struct Ring { char *h, *d; size_t cap, used; } ring;
+  static size_t ring_slot(size_t bytes) { return (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255; }
+  // Room for ALL the tables of one meepcu_step call at once: a wrap (or a re-allocation) between two ring_put calls of the
+  // same meepcu_step would hand the second table the slot of the first (seen with the noise table of noisy media, the
+  // first one big enough to wrap: the src_time samples of the same call were overwritten)
+  int ring_reserve(size_t total) {
+    if (ring.used + total <= ring.cap) return MEEPCU_OK;
+    CU(cudaStreamSynchronize(st)); // every kernel that read earlier slots has finished (side streams join st)
+    ring.used = 0;
+    if (total > ring.cap) {
+      if (ring.h) cudaFreeHost(ring.h);
+      if (ring.d) cudaFree(ring.d);
+      ring.h = ring.d = 0;
+      ring.cap = 0;
+      const size_t cap = std::max<size_t>(2 * total, (size_t)1 << 20);
+      CU(cudaHostAlloc((void **)&ring.h, cap, cudaHostAllocDefault));
+      CU(cudaMalloc((void **)&ring.d, cap));
+      ring.cap = cap;
+    }
+    return MEEPCU_OK;
+  }
   int ring_put(const void *src, size_t bytes, char **dptr) {
-    const size_t need = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+    const size_t need = ring_slot(bytes);
     if (ring.used + need > ring.cap) {
       CU(cudaStreamSynchronize(st)); // every kernel that read earlier slots has finished (side streams join st)
       ring.used = 0;
@@ -3487,6 +3507,9 @@ template <class T> struct Ctx : CtxBase {
     // reference), DFT decimation flags (dft.cpp:259) -- through the ring, no synchronisation
     const size_t ns = (size_t)std::max(nsrc, 1) * 8;
     char *p_smp = 0, *p_ph = 0, *p_act = 0;
+    RC(ring_reserve(ring_slot((size_t)(nsteps + 1) * ns * sizeof(double)) +
+                    ring_slot((size_t)(noise_total[0] + noise_total[1]) * nsteps * sizeof(double)) +
+                    ring_slot((size_t)2 * phase_row * nsteps * sizeof(T)) + ring_slot(h_dft.size() * nsteps)));
     {
       // row 0: the samples of the last step taken before this call (a virtual E holds ITS dipole_E), rows 1..: this call's
       std::vector<double> tab((size_t)(nsteps + 1) * ns, 0.0);
