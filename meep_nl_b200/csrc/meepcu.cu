@@ -2430,6 +2430,8 @@ template <class T> struct Ctx : CtxBase {
       }
     for (int half = 0; half < 2; ++half) aniso_half[half] = !polgen_tiles[half].empty() || !polgyro_tiles[half].empty();
     if (!mllev_tiles.empty() || n_wprev) aniso_half[1] = true; // multilevel atoms: ordered path (W, P halos around the passes)
+    for (int half = 0; half < 2; ++half)
+      if (n_noise_seg[half]) aniso_half[half] = true; // k_pol_noise follows the fused update on the ordered path only
     virt_any = !virt_comps.empty();
     if (n_ranks > 1) {
       int hflag[9] = {general_half[0], general_half[1], eager_db[0], eager_db[1], eager_p[0], eager_p[1], aniso_half[0], aniso_half[1],
