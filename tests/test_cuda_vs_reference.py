@@ -36,6 +36,7 @@ CASES = [("fp64", "vac3d:48", 60, 3, 1e-12), ("fp32", "vac3d:48", 60, 3, 1e-5),
          # the reference's own generator)
          ("fp64", "mlatom3d:24", 100, 2, 1e-12), ("fp32", "mlatom3d:24", 100, 2, 1e-5), ("fp64", "mlatom2d:60", 200, 2, 1e-12),
          ("fp32", "mlatom2d:60", 200, 2, 1e-5), ("fp64", "mlatom3d:40:0.6", 60, 0, 1e-12),
+         ("fp64", "mlatom1d", 40000, 0, 1e-12),
          ("fp64", "noisy3d:24", 100, 2, 1e-12), ("fp32", "noisy3d:24", 100, 2, 1e-5), ("fp64", "noisy2d:60", 200, 2, 1e-12),
          ("fp32", "noisy2d:60", 200, 2, 1e-5),
          ("fp64_pade", "kerr3d:20", 40, 2, 1e-12), ("fp64_pade", "kr_per3d_rods", 100, 0, 1e-12)]
