@@ -43,7 +43,7 @@ CASES = [("fp64", "vac3d:24", 25, 2), ("fp64", "kr_per3d_rods", 40, 0), ("fp64",
          ("fp64", "mlatom3d", 60, 2), ("fp32", "mlatom3d", 60, 2), ("fp64", "mlatom2d", 80, 2), ("fp32", "mlatom2d", 80, 2),
          ("fp64", "mlatom3d:18:0.6", 100, 0),
          # ... and the 1-D laser cavity of python/tests/test_multilevel_atom.py through its first relaxation spikes
-         ("fp64", "mlatom1d", 300000, 0), ("fp32", "mlatom1d", 120000, 0),
+         ("fp64", "mlatom1d", 120000, 0), ("fp32", "mlatom1d", 60000, 0),
          # noisy Lorentzian media (susceptibility.cpp:317-339): the reference's own generator draws the unit Gaussians in
          # its loop order for both twins; electric, and magnetic Drude + electric in one step with complex fields
          ("fp64", "noisy3d", 60, 2), ("fp32", "noisy3d", 60, 2), ("fp64", "noisy2d", 80, 2), ("fp32", "noisy2d", 80, 2),
