@@ -113,6 +113,18 @@ void fields::gpu_detach() {
 // true: the step was done on the device.  Mirrors the reference's own prologue / epilogue around the
 // stepping phases (restore, step, re-synchronize: src/step.cpp:36-41,128-134; NaN test :138-139).
 static bool dropin_step(fields *f) {
+  // opt-in without touching the caller: MEEP_CUDA_LIB=/path/to/libmeepcuda.so [MEEP_CUDA_NL_MODE=pade] [MEEP_CUDA_DEVICE=n]
+  // in the environment of an unchanged script (python/simulation.py:2831-2834 calls fields::step()); read once, and
+  // only while nobody has called fields::gpu_enable()
+  static bool env_checked = false;
+  if (!g_dropin_api && !env_checked) {
+    env_checked = true;
+    const char *lib = getenv("MEEP_CUDA_LIB");
+    if (lib && *lib) {
+      const char *nl = getenv("MEEP_CUDA_NL_MODE"), *dev = getenv("MEEP_CUDA_DEVICE");
+      fields::gpu_enable(lib, nl && !strcmp(nl, "pade") ? 1 : 0, dev ? atoi(dev) : 0);
+    }
+  }
   if (!g_dropin_api || f->is_phasing()) return false;
   // a source / DFT monitor / polarisation added or arrays re-allocated since the last step: the host arrays
   // become the truth again (sync back), and the object graph is described anew

@@ -813,9 +813,15 @@ int main(int argc, char **argv) {
     fprintf(jf,
             "{\"mode\":\"ref\",\"case\":\"%s\",\"realnum_bytes\":%d,\"steps\":%d,\"warmup\":%d,"
             "\"threads\":%d,\"cells\":%ld,\"num_chunks\":%d,\"seconds\":%.6f,"
-            "\"mcells_per_s\":%.4f,\"probe\":%.17g}\n",
+            "\"mcells_per_s\":%.4f,\"probe\":%.17g,\"attached\":%d}\n",
             cas.c_str(), (int)sizeof(realnum), steps, warmup, nthreads, p->cells, p->f->num_chunks,
-            t1 - t0, p->cells * (double)steps / (t1 - t0) / 1e6, probe_value(p));
+            t1 - t0, p->cells * (double)steps / (t1 - t0) / 1e6, probe_value(p),
+#ifdef MEEPCU_DROPIN
+            (int)(p->f->gpu != 0) // the patched reference: did MEEP_CUDA_LIB in the environment make step() delegate?
+#else
+            0
+#endif
+    );
     delete p;
   }
   else if (mode == "gpu") {

@@ -127,3 +127,25 @@ def test_patched_reference_reattaches_when_the_problem_changes(case):
     assert d["attached"] == 1 and d["t_ref"] == d["t_abi"]
     assert d["arrays"] > 0 and d["mismatched_elements"] == 0, d
     assert d["probe_mid"] == d["probe_mid_ref"]
+
+
+@pytest.mark.parametrize("case", ["lorentz3d:16", "noisy3d:10"])
+def test_environment_variable_opts_an_unchanged_program_in(case):
+    """MEEP_CUDA_LIB in the environment of an UNCHANGED caller (ref_driver --mode ref only calls fields::step() and
+    get_field, like python/simulation.py:2831-2834): the patched library delegates by itself, and the probe equals the
+    CPU run's bit for bit (CPU oracle behind the ABI here)"""
+    drv = ref_driver("fp64_dropin")
+    if drv is None:
+        pytest.skip("oracle/_ref/fp64_dropin not built (reference tree absent)")
+    out = []
+    for lib in (None, ORACLE_LIB):
+        with tempfile.NamedTemporaryFile(suffix=".json") as tf:
+            env = dict(os.environ, OMP_NUM_THREADS="2")
+            env.pop("MEEP_CUDA_LIB", None)
+            if lib:
+                env["MEEP_CUDA_LIB"] = lib
+            subprocess.run([drv, "--mode", "ref", "--case", case, "--steps", "40", "--json", tf.name], check=True, env=env,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+            out.append(json.load(open(tf.name)))
+    assert out[0]["attached"] == 0 and out[1]["attached"] == 1
+    assert out[0]["probe"] == out[1]["probe"] and out[0]["probe"] != 0
