@@ -100,3 +100,54 @@ def test_header_is_plain_c_and_every_symbol_has_c_linkage(tmp_path):
         # noise_amp took the place of two reserved ints: the size of the descriptor did not change
         assert d["sizeof_susceptibility_desc"] == C.sizeof(A.SusceptibilityDesc) == 24 + 8 + 8 * (100 + 40 + 40) + 32
         assert d["sizeof_multilevel_desc"] == C.sizeof(A.MultilevelDesc)
+
+
+def test_new_media_arguments_are_checked_by_both_libraries(oracle_backend, cuda_backend):
+    """meepcu_add_multilevel / meepcu_set_noise / meepcu_get_noise_count: the refusals (magnetic multilevel media, level /
+    transition counts, missing arrays, a wrong number of noise values) are the same in the CUDA library and the oracle;
+    none of them needs a device"""
+    import numpy as np
+    for b in (oracle_backend, cuda_backend):
+        cfg = A.Config()
+        cfg.abi_version, cfg.realnum_bytes, cfg.dim, cfg.is_real = A.ABI_VERSION, 8, A.D3, 1
+        cfg.a, cfg.dt, cfg.courant = 10, 0.05, 0.5
+        ctx = A.vp()
+        b.check(b.create(C.byref(cfg), C.byref(ctx)))
+        n = 5
+        ntot = (n + 1) ** 3
+        arr = {k: np.zeros(ntot) for k in ("ex", "dx", "P", "Pp", "sig")}
+        cd = A.ChunkDesc()
+        for k in range(3):
+            cd.num[k] = n
+        cd.f[A.Ex][0] = arr["ex"].ctypes.data
+        cd.f[A.Dx][0] = arr["dx"].ctypes.data
+        cid = C.c_int(-1)
+        b.check(b.add_chunk(ctx, C.byref(cd), C.byref(cid)))
+        small = np.ones(4)
+        N = np.zeros(2 * ntot)
+        md = A.MultilevelDesc()
+        md.ft, md.L, md.T = A.H_stuff, 2, 1
+        for name in ("Gamma", "GammaInv", "alpha", "omega", "gamma", "sigmat"):
+            setattr(md, name, small.ctypes.data)
+        md.N = N.ctypes.data
+        assert b.add_multilevel(ctx, 0, C.byref(md)) == A.EUNSUPPORTED  # magnetic multilevel media
+        md.ft, md.L = A.E_stuff, 9
+        assert b.add_multilevel(ctx, 0, C.byref(md)) == A.EUNSUPPORTED  # more levels than the kernels hold
+        md.L, md.N = 2, None
+        assert b.add_multilevel(ctx, 0, C.byref(md)) == A.EINVAL        # the populations are required
+        assert b.add_multilevel(ctx, 7, C.byref(md)) == A.EINVAL        # no such chunk
+        # a noisy Lorentzian on Ex: one unit Gaussian per owned point and step
+        sd = A.SusceptibilityDesc()
+        sd.ft, sd.omega_0, sd.gamma, sd.noise_amp = A.E_stuff, 1.1, 0.05, 0.1
+        sd.sigma[A.Ex][0] = arr["sig"].ctypes.data
+        sd.P[A.Ex][0], sd.P_prev[A.Ex][0] = arr["P"].ctypes.data, arr["Pp"].ctypes.data
+        b.check(b.add_susceptibility(ctx, 0, C.byref(sd)))
+        cnt = C.c_size_t(0)
+        b.check(b.get_noise_count(ctx, C.byref(cnt)))
+        assert cnt.value == n ** 3  # LOOP_OVER_VOL_OWNED: num points per direction
+        g = np.zeros(2 * cnt.value)
+        assert b.set_noise(ctx, 2, cnt.value + 1, g.ctypes.data) == A.EINVAL
+        assert b"values per step" in b.lib.meepcu_last_error()
+        assert b.set_noise(ctx, 2, cnt.value, None) == A.EINVAL
+        b.check(b.set_noise(ctx, 2, cnt.value, g.ctypes.data))
+        b.destroy(ctx)
