@@ -17,14 +17,19 @@ from conftest import ROOT
 WORKER = os.path.join(ROOT, "tests", "multirank_worker.py")
 
 
-def run(kind, case, dtype, steps, world, port, extra_env=None, nslabs=2):
+def start(kind, case, dtype, steps, world, port, extra_env=None, nslabs=2):
     out = tempfile.mkdtemp()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, kind, case, dtype, str(steps), out, str(nslabs)]
     env = dict(os.environ, OMP_NUM_THREADS="2")
     env.update(extra_env or {})
-    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
-    assert r.returncode == 0, r.stderr[-3000:]
+    return subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env), out, world
+
+
+def finish(job):
+    proc, out, world = job
+    _stdout, stderr = proc.communicate(timeout=900)
+    assert proc.returncode == 0, stderr[-3000:]
     vals = {}
     for k in range(world):
         with np.load(os.path.join(out, "rank%d.npz" % k)) as z:
@@ -32,6 +37,16 @@ def run(kind, case, dtype, steps, world, port, extra_env=None, nslabs=2):
                 assert name not in vals, "two ranks own " + name
                 vals[name] = z[name]
     return vals
+
+
+def run(kind, case, dtype, steps, world, port, extra_env=None, nslabs=2):
+    return finish(start(kind, case, dtype, steps, world, port, extra_env, nslabs))
+
+
+def run_both(one_args, many_args):
+    """the single-rank and the multi-rank job of a CPU test side by side (separate rendezvous ports)"""
+    a, b = start(*one_args[0], **one_args[1]), start(*many_args[0], **many_args[1])
+    return finish(a), finish(b)
 
 
 def bits(a):
@@ -55,16 +70,15 @@ def rel_l2(ref, got):
 
 @pytest.mark.parametrize("case", ["pml", "per", "beta2d", "lorentz", "bloch", "mlatom", "noisy"])
 def test_two_ranks_equal_one_rank_oracle(case):
-    one = run("oracle", case + "_presplit", "f64", 40, 1, 29611)
-    two = run("oracle", case, "f64", 40, 2, 29612)
+    one, two = run_both((("oracle", case + "_presplit", "f64", 40, 1, 29611), {}), (("oracle", case, "f64", 40, 2, 29612), {}))
     assert_bit_equal(one, two)
 
 
 @pytest.mark.parametrize("case", ["pml", "bloch"])
 def test_four_ranks_equal_one_rank_oracle(case):
     """middle ranks have TWO remote neighbours"""
-    one = run("oracle", case + "_presplit", "f64", 30, 1, 29615, nslabs=4)
-    four = run("oracle", case, "f64", 30, 4, 29616, nslabs=4)
+    one, four = run_both((("oracle", case + "_presplit", "f64", 30, 1, 29615), {"nslabs": 4}),
+                         (("oracle", case, "f64", 30, 4, 29616), {"nslabs": 4}))
     assert_bit_equal(one, four)
 
 
@@ -72,8 +86,7 @@ def test_four_ranks_equal_one_rank_oracle(case):
 def test_ranks_with_different_needs_oracle(case):
     """one rank owns only linear PML chunks, the other the Newton-Raphson medium / a D-component DFT: the
     halo-exchange schedule must still be the same on both (host-side lists; the library side is the gpu test below)"""
-    one = run("oracle", case + "_presplit", "f64", 30, 1, 29617)
-    two = run("oracle", case, "f64", 30, 2, 29618)
+    one, two = run_both((("oracle", case + "_presplit", "f64", 30, 1, 29617), {}), (("oracle", case, "f64", 30, 2, 29618), {}))
     assert_bit_equal(one, two)
 
 
