@@ -54,6 +54,14 @@ static double slab_mask_y(const vec &p) { return (p.y() > g_slab_lo && p.y() < g
 static double slab_mask_z(const vec &p) { return (p.z() > g_slab_lo && p.z() < g_slab_hi) ? 1.0 : 0.0; }
 static double slab_eps_z(const vec &p) { return (p.z() > g_slab_lo && p.z() < g_slab_hi) ? g_slab_eps : 1.0; }
 static std::complex<double> mlatom1d_seed(const vec &p) { return fabs(p.z() - 0.5) < 1e-9 ? 1.0 : 0.0; }
+static double g_sym_c;
+static double sym_r2(const vec &p) { // a function of the squared distances from the centre only: every symmetry's invariant
+  double r2 = 0;
+  LOOP_OVER_DIRECTIONS(p.dim, d) { r2 += (p.in_direction(d) - g_sym_c) * (p.in_direction(d) - g_sym_c); }
+  return r2;
+}
+static double sym_eps(const vec &p) { return sym_r2(p) < 0.09 * 4 * g_sym_c * g_sym_c ? 4.0 : 1.0; }
+static double sym_mask(const vec &p) { return sym_r2(p) < 0.09 * 4 * g_sym_c * g_sym_c ? 1.0 : 0.0; }
 static double ring_eps(const vec &p);
 static double ring_sigma(const vec &p);
 static double g_ring_c[3], g_ring_r0, g_ring_r1, g_ring_h;
@@ -431,6 +439,24 @@ static problem *build(const std::string &spec, int nchunks) {
     p->f = new fields(p->s);
     p->f->add_point_source(Ez, 0.3, 0.25, 0.0, 4.0, p->gv.center(), 1.0);
     p->f->add_point_source(Hx, 0.25, 0.25, 0.0, 4.0, p->gv.center(), 0.5);
+  }
+  else if (name == "sym3d" || name == "sym2d" || name == "symrot2d") { // tests/symmetry.cpp: the cell reduced by a symmetry
+    // (mirror planes / a four-fold rotation): the chunks connect to THEMSELVES through the symmetry's phases
+    // (boundaries.cpp:347-623 with S.multiplicity() > 1) -- COPY, NEGATE and complex PHASE connections the plain cells
+    // never produce
+    if (!n) n = 16;
+    const bool d3 = name == "sym3d";
+    const double L = n / a;
+    p->gv = d3 ? vol3d(L, L, L, a) : vol2d(L, L, a);
+    g_sym_c = 0.5 * L;
+    const symmetry S = name == "symrot2d" ? rotate4(Z, p->gv) : (d3 ? mirror(Y, p->gv) + mirror(Z, p->gv) : mirror(Y, p->gv) + mirror(X, p->gv));
+    p->s = new structure(p->gv, sym_eps, pml(0.1 * L > 0.5 ? 0.5 : 0.1 * L), S, nchunks, 0.5, false);
+    p->s->add_susceptibility(sym_mask, E_stuff, lorentzian_susceptibility(1.1, 0.02));
+    p->f = new fields(p->s);
+    if (d3) p->f->use_real_fields();
+    const vec c = p->gv.center();
+    p->f->add_point_source(Ez, 0.3, 0.25, 0.0, 4.0, d3 ? c + vec(0.2, 0.0, 0.0) : c, 1.0);
+    if (d3) p->f->add_point_source(Ex, 0.25, 0.25, 0.0, 4.0, c + vec(0.1, 0.2, 0.3), 0.5);
   }
   else if (name == "mlatom3d" || name == "mlatom2d") { // multilevel-atom gain medium (multilevel-atom.cpp)
     // mlatom3d: two levels, one radiative transition, real fields (python/tests/test_multilevel_atom.py physics);

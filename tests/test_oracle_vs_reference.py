@@ -47,6 +47,10 @@ CASES = [("fp64", "vac3d:24", 25, 2), ("fp64", "kr_per3d_rods", 40, 0), ("fp64",
          # noisy Lorentzian media (susceptibility.cpp:317-339): the reference's own generator draws the unit Gaussians in
          # its loop order for both twins; electric, and magnetic Drude + electric in one step with complex fields
          ("fp64", "noisy3d", 60, 2), ("fp32", "noisy3d", 60, 2), ("fp64", "noisy2d", 80, 2), ("fp32", "noisy2d", 80, 2),
+         # cells reduced by a symmetry (tests/symmetry.cpp): two mirror planes in 3-D and 2-D, a four-fold rotation in 2-D
+         # with complex fields -- the chunks connect to themselves through the symmetry's COPY / NEGATE / PHASE lists
+         ("fp64", "sym3d", 60, 2), ("fp32", "sym3d", 60, 2), ("fp64", "sym2d", 80, 2), ("fp64", "symrot2d", 80, 2),
+         ("fp32", "symrot2d", 80, 2),
          # UPSTREAM_PADE against the de-blocked reference flavour (oracle/deblock_pade.py)
          ("fp64_pade", "kerr3d:14", 40, 2), ("fp64_pade", "kerr1d", 80, 0), ("fp64_pade", "kr_per3d_rods", 40, 0)]
 
