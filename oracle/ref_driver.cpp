@@ -62,6 +62,10 @@ static double sym_r2(const vec &p) { // a function of the squared distances from
 }
 static double sym_eps(const vec &p) { return sym_r2(p) < 0.09 * 4 * g_sym_c * g_sym_c ? 4.0 : 1.0; }
 static double sym_mask(const vec &p) { return sym_r2(p) < 0.09 * 4 * g_sym_c * g_sym_c ? 1.0 : 0.0; }
+static std::complex<double> srcs_amp(const vec &p) { // a tilted-plane-wave profile (pw-source-ll.cpp)
+  return std::polar(1.0 + 0.3 * p.x(), 2.0 * 3.14159265358979323846 * (0.15 * p.x() + 0.1 * p.y()));
+}
+static std::complex<double> srcs_custom(double t, void *) { return std::complex<double>(sin(1.7 * t) * exp(-0.2 * t), 0.3 * cos(0.9 * t)); }
 static double ring_eps(const vec &p);
 static double ring_sigma(const vec &p);
 static double g_ring_c[3], g_ring_r0, g_ring_r1, g_ring_h;
@@ -145,6 +149,7 @@ struct problem {
   std::vector<dft_fields> dftfields;
   std::vector<dft_energy> energies;
   std::vector<dft_near2far> n2fs;
+  std::vector<dft_force> forces;
   long cells;
   double probe_z; // >= 0: the probe is Ex at this z (1-D cases with a test's own probe point)
   problem() : s(0), f(0), mat(0), cells(0), probe_z(-1) {}
@@ -457,6 +462,43 @@ static problem *build(const std::string &spec, int nchunks) {
     const vec c = p->gv.center();
     p->f->add_point_source(Ez, 0.3, 0.25, 0.0, 4.0, d3 ? c + vec(0.2, 0.0, 0.0) : c, 1.0);
     if (d3) p->f->add_point_source(Ex, 0.25, 0.25, 0.0, 4.0, c + vec(0.1, 0.2, 0.3), 0.5);
+  }
+  else if (name == "srcs3d" || name == "srcs2d") { // every kind of current source and the remaining kinds of DFT consumer:
+    // a plane source with an amplitude profile (pw-source-ll.cpp), a continuous source turned on smoothly, a custom
+    // source that is NOT integrated on an electric component (custom_src_time::current = dipole, meep.hpp:1066-1071), a
+    // magnetic line source; a near-to-far box face (near2far.cpp) and a force monitor (stress_tensor.cpp)
+    if (!n) n = 16;
+    const bool d3 = name == "srcs3d";
+    const double L = n / a;
+    p->gv = d3 ? vol3d(L, L, L, a) : vol2d(L, 1.25 * L, a);
+    g_slab_lo = 0.55 * L;
+    g_slab_hi = 0.75 * L;
+    g_slab_eps = 3.0;
+    p->s = new structure(p->gv, d3 ? slab_eps_z : slab_eps_y, pml(0.1 * L > 0.5 ? 0.5 : 0.1 * L), identity(), nchunks, 0.5, false);
+    p->f = new fields(p->s);
+    const vec c = p->gv.center();
+    continuous_src_time cw(0.3, 0.25, 0.0, 3.0);
+    custom_src_time cust(srcs_custom, NULL, 0.0, 5.0, 0.2, 0.3);
+    cust.is_integrated = false;
+    if (d3) {
+      p->f->use_real_fields();
+      p->f->add_volume_source(Ex, cw, volume(vec(0.2 * L, 0.2 * L, 0.3 * L), vec(0.8 * L, 0.8 * L, 0.3 * L)), srcs_amp, 1.0);
+      p->f->add_point_source(Ey, cust, c + vec(0.1, -0.1, 0.05), 0.7);
+      p->f->add_volume_source(Hz, gaussian_src_time(0.25, 0.2, 0.0, 4.0), volume(vec(0.3 * L, 0.4 * L, 0.45 * L), vec(0.7 * L, 0.4 * L, 0.45 * L)), 0.5);
+      volume_list vl(volume(vec(0.25 * L, 0.25 * L, 0.8 * L), vec(0.75 * L, 0.75 * L, 0.8 * L)), Sz, 1.0);
+      p->n2fs.push_back(p->f->add_dft_near2far(&vl, 0.2, 0.35, 3));
+      volume_list fl(volume(vec(0.7 * L, 0.3 * L, 0.3 * L), vec(0.7 * L, 0.7 * L, 0.7 * L)), Sx, 1.0);
+      p->forces.push_back(p->f->add_dft_force(&fl, 0.2, 0.35, 2));
+    }
+    else {
+      p->f->add_volume_source(Ez, cw, volume(vec(0.2 * L, 0.3 * L), vec(0.8 * L, 0.3 * L)), srcs_amp, 1.0);
+      p->f->add_point_source(Ex, cust, c + vec(0.1, -0.1), 0.7);
+      p->f->add_volume_source(Hz, gaussian_src_time(0.25, 0.2, 0.0, 4.0), volume(vec(0.3 * L, 0.5 * L), vec(0.7 * L, 0.5 * L)), 0.5);
+      volume_list vl(volume(vec(0.25 * L, 1.0 * L), vec(0.75 * L, 1.0 * L)), Sy, 1.0);
+      p->n2fs.push_back(p->f->add_dft_near2far(&vl, 0.2, 0.35, 3));
+      volume_list fl(volume(vec(0.7 * L, 0.3 * L), vec(0.7 * L, 0.9 * L)), Sx, 1.0);
+      p->forces.push_back(p->f->add_dft_force(&fl, 0.2, 0.35, 2));
+    }
   }
   else if (name == "mlatom3d" || name == "mlatom2d") { // multilevel-atom gain medium (multilevel-atom.cpp)
     // mlatom3d: two levels, one radiative transition, real fields (python/tests/test_multilevel_atom.py physics);

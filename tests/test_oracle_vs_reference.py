@@ -51,6 +51,9 @@ CASES = [("fp64", "vac3d:24", 25, 2), ("fp64", "kr_per3d_rods", 40, 0), ("fp64",
          # with complex fields -- the chunks connect to themselves through the symmetry's COPY / NEGATE / PHASE lists
          ("fp64", "sym3d", 60, 2), ("fp32", "sym3d", 60, 2), ("fp64", "sym2d", 80, 2), ("fp64", "symrot2d", 80, 2),
          ("fp32", "symrot2d", 80, 2),
+         # every kind of current source (plane source with an amplitude profile, continuous, a NON-integrated custom source on
+         # an electric component, a magnetic line source) and the remaining DFT consumers (near-to-far face, force monitor)
+         ("fp64", "srcs3d", 80, 2), ("fp32", "srcs3d", 80, 2), ("fp64", "srcs2d", 100, 2), ("fp32", "srcs2d", 100, 2),
          # UPSTREAM_PADE against the de-blocked reference flavour (oracle/deblock_pade.py)
          ("fp64_pade", "kerr3d:14", 40, 2), ("fp64_pade", "kerr1d", 80, 0), ("fp64_pade", "kr_per3d_rods", 40, 0)]
 
