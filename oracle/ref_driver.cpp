@@ -500,6 +500,25 @@ static problem *build(const std::string &spec, int nchunks) {
       p->forces.push_back(p->f->add_dft_force(&fl, 0.2, 0.35, 2));
     }
   }
+  else if (name == "pmlk3d" || name == "pmlk2d") { // stretched-coordinate PML: mean_stretch != 1 (kap != 1), a custom
+    // Rasymptotic, different thicknesses per face and one face without PML (tests/pml.cpp varies these)
+    if (!n) n = 18;
+    const bool d3 = name == "pmlk3d";
+    const double L = n / a;
+    p->gv = d3 ? vol3d(L, L, L, a) : vol2d(L, 1.25 * L, a);
+    g_slab_lo = 0.4 * L;
+    g_slab_hi = 0.6 * L;
+    g_slab_eps = 5.0;
+    const double ms = param != 0 ? param : 2.5;
+    boundary_region br = pml(0.3, X, Low, 1e-10, ms) + pml(0.5, X, High, 1e-12, 1.0) + pml(0.4, Y, 1e-8, ms);
+    if (d3) br = br + pml(0.3, Z, High, 1e-15, 1.7);
+    p->s = new structure(p->gv, d3 ? slab_eps_z : slab_eps_y, br, identity(), nchunks, 0.5, false);
+    p->s->add_susceptibility(d3 ? slab_mask_z : slab_mask_y, E_stuff, lorentzian_susceptibility(1.1, 0.02));
+    p->f = new fields(p->s);
+    if (d3) p->f->use_real_fields();
+    p->f->add_point_source(Ez, 0.3, 0.25, 0.0, 4.0, p->gv.center(), 1.0);
+    p->f->add_point_source(d3 ? Ex : Hz, 0.25, 0.25, 0.0, 4.0, p->gv.center() + (d3 ? vec(0.1, 0.2, -0.1) : vec(0.1, 0.2)), 0.5);
+  }
   else if (name == "mlatom3d" || name == "mlatom2d") { // multilevel-atom gain medium (multilevel-atom.cpp)
     // mlatom3d: two levels, one radiative transition, real fields (python/tests/test_multilevel_atom.py physics);
     // mlatom2d: three levels, two radiative transitions with different sigma factors, complex fields, plus an

@@ -54,6 +54,8 @@ CASES = [("fp64", "vac3d:24", 25, 2), ("fp64", "kr_per3d_rods", 40, 0), ("fp64",
          # every kind of current source (plane source with an amplitude profile, continuous, a NON-integrated custom source on
          # an electric component, a magnetic line source) and the remaining DFT consumers (near-to-far face, force monitor)
          ("fp64", "srcs3d", 80, 2), ("fp32", "srcs3d", 80, 2), ("fp64", "srcs2d", 100, 2), ("fp32", "srcs2d", 100, 2),
+         # stretched-coordinate PML (mean_stretch != 1: kap != 1), per-face thickness / Rasymptotic, one face without PML
+         ("fp64", "pmlk3d", 120, 2), ("fp32", "pmlk3d", 120, 2), ("fp64", "pmlk2d", 150, 2), ("fp32", "pmlk2d", 150, 2),
          # UPSTREAM_PADE against the de-blocked reference flavour (oracle/deblock_pade.py)
          ("fp64_pade", "kerr3d:14", 40, 2), ("fp64_pade", "kerr1d", 80, 0), ("fp64_pade", "kr_per3d_rods", 40, 0)]
 
@@ -99,7 +101,7 @@ SYNC_CASES = [("fp64", "vac3d:32", 40), ("fp64", "wvg2d", 60), ("fp64", "lorentz
               ("fp64", "kr_per3d_rods", 40), ("fp64", "cond3d:12", 40), ("fp64", "bfast3d:10", 40), ("fp32", "beta2d", 40),
               ("fp64", "magdrude3d", 40), ("fp32", "magdrude2d", 40), ("fp64", "gyrosat3d", 40),
               ("fp64", "cylpml:18:1", 40), ("fp64", "cyllor:18:0", 40), ("fp32", "cylcond:18:2", 40),
-              ("fp64", "mlatom3d", 40), ("fp32", "noisy2d", 40)]
+              ("fp64", "mlatom3d", 40), ("fp32", "noisy2d", 40), ("fp64", "pmlk3d", 40), ("fp64", "srcs2d", 40), ("fp64", "sym3d", 40)]
 
 
 @pytest.mark.parametrize("flavour,case,steps", SYNC_CASES)
