@@ -236,9 +236,9 @@ static problem *build(const std::string &spec, int nchunks) {
     p->f->add_point_source(d3 ? Ey : Ez, 0.25, 0.2, 0.0, 4.0, p->gv.center(), 1.0);
     p->f->add_point_source(Hx, 0.3, 0.2, 0.0, 4.0, p->gv.center(), 0.6);
   }
-  else if (name == "cond3d" || name == "cond2d") { // conductivity + PML: f_cond paths of step_curl
+  else if (name == "cond3d" || name == "cond2d" || name == "cond3d_cplx") { // conductivity + PML: f_cond paths of step_curl
     if (!n) n = 14;
-    const bool d3 = name == "cond3d";
+    const bool d3 = name != "cond2d";
     p->gv = d3 ? vol3d(n / a, n / a, n / a, a) : vol2d(n / a, n / a, a);
     g_slab_lo = 0.3 * n / a;
     g_slab_hi = 0.7 * n / a;
@@ -249,7 +249,11 @@ static problem *build(const std::string &spec, int nchunks) {
     p->s->set_conductivity(Dz, cond_fn);
     p->s->set_conductivity(By, cond_fn);
     p->f = new fields(p->s);
-    p->f->use_real_fields();
+    if (name == "cond3d_cplx") { // complex fields, Bloch-periodic in x: the f_cond chain on both cmp, PHASE connections
+      p->f->use_bloch(X, 0.21);
+    }
+    else
+      p->f->use_real_fields();
     p->f->add_point_source(Ez, 0.25, 0.2, 0.0, 4.0, p->gv.center(), 1.0);
     p->f->add_point_source(d3 ? Ex : Hz, 0.3, 0.2, 0.0, 4.0, p->gv.center(), 0.6);
   }
@@ -278,6 +282,7 @@ static problem *build(const std::string &spec, int nchunks) {
     if (name == "cyllor") p->s->add_susceptibility(rod_sigma_r, E_stuff, lorentzian_susceptibility(0.9, 0.02));
     p->f = new fields(p->s, param, 0, name != "cylpmlnz");
     if (name == "cylper") p->f->use_bloch(0.0);
+    if (name == "cylperk") p->f->use_bloch(0.37); // Bloch-periodic in z with a phase: PHASE connections in a cylindrical cell
     const double R = n / a, Zs = (2 * n / 3) / a;
     p->f->add_point_source(Ep, 0.7, 2.5, 0.0, 4.0, veccyl(0.33 * R, 0.5 * Zs), 1.0);
     p->f->add_point_source(Ez, 0.8, 0.6, 0.0, 4.0, veccyl(0.267 * R + 0.001, 0.376 * Zs + 0.001), 1.0);
@@ -518,6 +523,25 @@ static problem *build(const std::string &spec, int nchunks) {
     if (d3) p->f->use_real_fields();
     p->f->add_point_source(Ez, 0.3, 0.25, 0.0, 4.0, p->gv.center(), 1.0);
     p->f->add_point_source(d3 ? Ex : Hz, 0.25, 0.25, 0.0, 4.0, p->gv.center() + (d3 ? vec(0.1, 0.2, -0.1) : vec(0.1, 0.2)), 0.5);
+  }
+  else if (name == "lor4") { // four polarisations on one chunk (the most a chunk's parameter block holds): two Lorentzians, a
+    // Drude term and a noisy-free duplicate frequency, in a cavity with METALLIC walls that the medium touches
+    // (zero_metal and subtract_P on the same points), no PML
+    if (!n) n = 14;
+    const double L = n / a;
+    p->gv = vol3d(L, L, L, a);
+    g_slab_lo = -1.0;
+    g_slab_hi = 0.6 * L;
+    g_slab_eps = 2.0;
+    p->s = new structure(p->gv, slab_eps_z, no_pml(), identity(), nchunks, 0.5, false);
+    p->s->add_susceptibility(slab_mask_z, E_stuff, lorentzian_susceptibility(1.1, 0.02));
+    p->s->add_susceptibility(slab_mask_z, E_stuff, lorentzian_susceptibility(0.7, 0.05));
+    p->s->add_susceptibility(slab_mask_z, E_stuff, lorentzian_susceptibility(0.4, 0.1, true));
+    p->s->add_susceptibility(slab_mask_z, E_stuff, lorentzian_susceptibility(1.1, 0.3));
+    p->f = new fields(p->s);
+    p->f->use_real_fields();
+    p->f->add_point_source(Ez, 0.3, 0.25, 0.0, 4.0, p->gv.center(), 1.0);
+    p->f->add_point_source(Ex, 0.25, 0.25, 0.0, 4.0, p->gv.center() + vec(0.1, 0.2, -0.3), 0.5);
   }
   else if (name == "mlatom3d" || name == "mlatom2d") { // multilevel-atom gain medium (multilevel-atom.cpp)
     // mlatom3d: two levels, one radiative transition, real fields (python/tests/test_multilevel_atom.py physics);

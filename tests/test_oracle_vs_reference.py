@@ -56,6 +56,10 @@ CASES = [("fp64", "vac3d:24", 25, 2), ("fp64", "kr_per3d_rods", 40, 0), ("fp64",
          ("fp64", "srcs3d", 80, 2), ("fp32", "srcs3d", 80, 2), ("fp64", "srcs2d", 100, 2), ("fp32", "srcs2d", 100, 2),
          # stretched-coordinate PML (mean_stretch != 1: kap != 1), per-face thickness / Rasymptotic, one face without PML
          ("fp64", "pmlk3d", 120, 2), ("fp32", "pmlk3d", 120, 2), ("fp64", "pmlk2d", 150, 2), ("fp32", "pmlk2d", 150, 2),
+         # conductivity + PML with complex fields and a Bloch phase; a cylindrical cell periodic in z with a phase; four
+         # polarisations on one chunk in a cavity whose metallic walls the medium touches
+         ("fp64", "cond3d_cplx", 80, 2), ("fp32", "cond3d_cplx", 80, 2), ("fp64", "cylperk:15:1", 120, 0), ("fp32", "cylperk:16:0", 120, 0),
+         ("fp64", "lor4", 100, 2), ("fp32", "lor4", 100, 2),
          # UPSTREAM_PADE against the de-blocked reference flavour (oracle/deblock_pade.py)
          ("fp64_pade", "kerr3d:14", 40, 2), ("fp64_pade", "kerr1d", 80, 0), ("fp64_pade", "kr_per3d_rods", 40, 0)]
 

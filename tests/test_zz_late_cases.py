@@ -17,7 +17,9 @@ pytestmark = pytest.mark.gpu
 CASES = [("fp64", "sym3d", 60, 2, 1e-12), ("fp32", "sym3d", 60, 2, 1e-5), ("fp64", "sym2d", 80, 2, 1e-12),
          ("fp64", "symrot2d", 80, 2, 1e-12), ("fp32", "symrot2d", 80, 2, 1e-5),
          ("fp64", "srcs3d:24", 80, 2, 1e-12), ("fp32", "srcs3d:24", 80, 2, 1e-5), ("fp64", "srcs2d:48", 100, 2, 1e-12),
-         ("fp64", "pmlk3d:24", 120, 2, 1e-12), ("fp32", "pmlk3d:24", 120, 2, 1e-5), ("fp64", "pmlk2d:48", 150, 2, 1e-12)]
+         ("fp64", "pmlk3d:24", 120, 2, 1e-12), ("fp32", "pmlk3d:24", 120, 2, 1e-5), ("fp64", "pmlk2d:48", 150, 2, 1e-12),
+         ("fp64", "cond3d_cplx:24", 80, 2, 1e-12), ("fp32", "cond3d_cplx:24", 80, 2, 1e-5), ("fp64", "cylperk:30:1", 200, 0, 1e-12),
+         ("fp64", "lor4:24", 100, 2, 1e-12), ("fp32", "lor4:24", 100, 2, 1e-5)]
 
 
 @pytest.mark.xfail(strict=False, reason="first GPU run of these cases (added after the round's GPU budget was spent)")
